@@ -1,0 +1,244 @@
+"""bsmr-sddmm_b200: B200 (sm_100a) implementation of the BSMR-SDDMM hot path.
+
+The product is ``lib/libbsmr_b200.so`` (CUDA + a C ABI, see ``include/bsmr_b200.h``).  This
+package is a thin ctypes binding over that ABI plus seeded synthetic inputs; it holds no
+compute of its own and has no CPU fallback: if the shared library is missing, or no sm_100
+device is present, every compute entry point raises.
+
+The directory name carries a hyphen (it mirrors the reference's name), so it is imported as
+``bsmr_sddmm_b200`` through ``importlib`` -- see ``load_package()`` in ``__graft_entry__.py``.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_PATH = os.path.join(HERE, "lib", "libbsmr_b200.so")
+HEADER = os.path.join(ROOT, "include", "bsmr_b200.h")
+
+ROW_PANEL_SIZE = 16
+BLOCK_COL_SIZE = 16
+NULL_VALUE = 0xFFFFFFFF
+
+ROW_REFERENCE_COMPAT, ROW_EXACT_REDUCE, ROW_IDENTITY = 0, 1, 2
+SDDMM_DEFAULT, SDDMM_RESIDUAL_ONLY, SDDMM_NO_REORDER = 0, 1, 2
+
+VEC = dict(reordered_rows=0, dense_cols=1, dense_col_offsets=2, sparse_cols=3, sparse_col_offsets=4,
+           sparse_value_offsets=5, block_offsets=6, block_values=7, sparse_values=8,
+           sparse_relative_rows=9, sparse_col_indices=10, dispersions=11, cluster_ids=12)
+
+u32p = C.POINTER(C.c_uint32)
+f32p = C.POINTER(C.c_float)
+
+
+class BsmrError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("bsmr_b200 status %d: %s" % (status, message))
+        self.status = status
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [("M", C.c_uint32), ("N", C.c_uint32), ("nnz", C.c_uint32),
+                ("num_row_panels", C.c_uint32), ("num_clusters", C.c_int32), ("num_clusters_true", C.c_int32),
+                ("block_size", C.c_uint32), ("num_dense_blocks", C.c_uint32), ("num_dense_tiles", C.c_uint32),
+                ("num_dense_values", C.c_uint64), ("num_sparse_values", C.c_uint64),
+                ("row_reordering_ms", C.c_float), ("col_reordering_ms", C.c_float), ("format_build_ms", C.c_float)]
+
+
+class ReorderStats(C.Structure):
+    _fields_ = [("num_dense_blocks", C.c_int32), ("average_density", C.c_float),
+                ("num_dense_thread_blocks", C.c_int32), ("num_sparse_thread_blocks", C.c_int32),
+                ("num_dense_data", C.c_int32), ("num_sparse_data", C.c_int32),
+                ("original_num_dense_blocks", C.c_int32), ("original_average_density", C.c_float)]
+
+
+def build_library():
+    """Compile libbsmr_b200.so in-tree (nvcc cross-compiles sm_100a without a GPU)."""
+    subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(HERE, "csrc")])
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(
+                LIB_PATH + " is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, cp = C.c_void_p, C.c_char_p
+        L.bsmr_version.restype = cp
+        L.bsmr_last_error.restype = cp
+        L.bsmr_status_string.restype = cp
+        L.bsmr_status_string.argtypes = [C.c_int]
+        L.bsmr_ctx_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
+        L.bsmr_ctx_destroy.argtypes = [vp]
+        L.bsmr_ctx_synchronize.argtypes = [vp]
+        L.bsmr_ctx_device_name.argtypes = [vp, C.c_char_p, C.c_size_t]
+        L.bsmr_ctx_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.bsmr_calculate_block_size.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint64, u32p]
+        L.bsmr_plan_create.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.c_int, C.POINTER(vp)]
+        L.bsmr_plan_destroy.argtypes = [vp]
+        L.bsmr_plan_row_reorder.argtypes = [vp, C.c_float, C.c_uint32, C.c_uint32]
+        L.bsmr_plan_set_row_order.argtypes = [vp, u32p, C.c_uint32]
+        L.bsmr_plan_col_reorder.argtypes = [vp, C.c_float]
+        L.bsmr_plan_reorder.argtypes = [vp, C.c_float, C.c_float, C.c_uint32, C.c_uint32]
+        L.bsmr_plan_vector_size.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
+        L.bsmr_plan_vector_copy.argtypes = [vp, C.c_int, u32p, C.c_uint64]
+        L.bsmr_plan_get_info.argtypes = [vp, C.POINTER(PlanInfo)]
+        L.bsmr_plan_set_shard.argtypes = [vp, C.c_uint32, C.c_uint32, u32p, u32p, C.POINTER(C.c_uint64)]
+        L.bsmr_sddmm.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_int, C.c_uint32, f32p]
+        L.bsmr_sddmm_host.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_int, C.c_uint32, f32p, f32p]
+        L.bsmr_plan_evaluate.argtypes = [vp, C.c_float, C.POINTER(ReorderStats)]
+        L.bsmr_debug_set_dense_smem_dump.argtypes = [vp]
+        for name in ("bsmr_ctx_create", "bsmr_ctx_destroy", "bsmr_ctx_synchronize", "bsmr_ctx_device_name",
+                     "bsmr_ctx_launch_count", "bsmr_calculate_block_size", "bsmr_plan_create", "bsmr_plan_destroy",
+                     "bsmr_plan_row_reorder", "bsmr_plan_set_row_order", "bsmr_plan_col_reorder", "bsmr_plan_reorder",
+                     "bsmr_plan_vector_size", "bsmr_plan_vector_copy", "bsmr_plan_get_info", "bsmr_plan_set_shard",
+                     "bsmr_sddmm", "bsmr_sddmm_host", "bsmr_plan_evaluate"):
+            getattr(L, name).restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _check(status):
+    if status != 0:
+        raise BsmrError(status, lib().bsmr_last_error().decode(errors="replace"))
+
+
+def _ptr(x):
+    """Raw address of a numpy array, a torch tensor (host or device), or an int."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    return x.data_ptr()  # torch tensor
+
+
+class Context:
+    """One device + one stream (bsmr_ctx)."""
+
+    def __init__(self, device=0, stream=None):
+        self._h = C.c_void_p()
+        _check(lib().bsmr_ctx_create(device, stream, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().bsmr_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def synchronize(self):
+        _check(lib().bsmr_ctx_synchronize(self._h))
+
+    def device_name(self):
+        buf = C.create_string_buffer(256)
+        _check(lib().bsmr_ctx_device_name(self._h, buf, 256))
+        return buf.value.decode()
+
+    def launch_count(self):
+        n = C.c_uint64()
+        _check(lib().bsmr_ctx_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def calculate_block_size(self, M, N, free_mem_bytes=0):
+        out = C.c_uint32()
+        _check(lib().bsmr_calculate_block_size(self._h, M, N, free_mem_bytes, C.byref(out)))
+        return out.value
+
+
+class Plan:
+    """One sparsity pattern: the reference's BSMR object + RPHM device format (bsmr_plan)."""
+
+    def __init__(self, ctx, M, N, row_offsets, col_indices, on_device=False):
+        self.ctx = ctx
+        self.M, self.N = int(M), int(N)
+        if not on_device:
+            row_offsets = np.ascontiguousarray(row_offsets, dtype=np.uint32)
+            col_indices = np.ascontiguousarray(col_indices, dtype=np.uint32)
+            self.nnz = int(len(col_indices))
+        else:
+            self.nnz = int(col_indices.numel())
+        self._keep = (row_offsets, col_indices)
+        self._h = C.c_void_p()
+        _check(lib().bsmr_plan_create(ctx._h, self.M, self.N, self.nnz, _ptr(row_offsets), _ptr(col_indices),
+                                      int(on_device), C.byref(self._h)))
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().bsmr_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    # ---- BSMR ----
+    def row_reorder(self, alpha, block_size=0, flags=ROW_REFERENCE_COMPAT):
+        _check(lib().bsmr_plan_row_reorder(self._h, alpha, block_size, flags))
+
+    def set_row_order(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        _check(lib().bsmr_plan_set_row_order(self._h, rows.ctypes.data_as(u32p), len(rows)))
+
+    def col_reorder(self, delta):
+        _check(lib().bsmr_plan_col_reorder(self._h, delta))
+
+    def reorder(self, alpha, delta, block_size=0, flags=ROW_REFERENCE_COMPAT):
+        _check(lib().bsmr_plan_reorder(self._h, alpha, delta, block_size, flags))
+
+    def vector(self, name):
+        which = VEC[name]
+        n = C.c_uint64()
+        _check(lib().bsmr_plan_vector_size(self._h, which, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.uint32)
+        _check(lib().bsmr_plan_vector_copy(self._h, which, out.ctypes.data_as(u32p), n.value))
+        return out
+
+    def info(self):
+        info = PlanInfo()
+        _check(lib().bsmr_plan_get_info(self._h, C.byref(info)))
+        return {k: getattr(info, k) for k, _ in PlanInfo._fields_}
+
+    def evaluate(self, delta):
+        st = ReorderStats()
+        _check(lib().bsmr_plan_evaluate(self._h, delta, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in ReorderStats._fields_}
+
+    def set_shard(self, rank, world):
+        a, b, n = C.c_uint32(), C.c_uint32(), C.c_uint64()
+        _check(lib().bsmr_plan_set_shard(self._h, rank, world, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
+    # ---- SDDMM ----
+    def sddmm(self, K, dA, dB, dP, iterations=1, flags=SDDMM_DEFAULT, timed=True):
+        """Device pointers (torch CUDA tensors or raw addresses); returns ms per iteration."""
+        ms = C.c_float(0)
+        _check(lib().bsmr_sddmm(self._h, K, _ptr(dA), _ptr(dB), _ptr(dP), iterations, flags,
+                                C.byref(ms) if timed else None))
+        return ms.value
+
+    def sddmm_host(self, K, hA, hB, hP=None, iterations=1, flags=SDDMM_DEFAULT):
+        """Host buffers (numpy or pinned torch tensors); H2D/D2H inside.  Returns (P, kernel_ms, total_ms)."""
+        if isinstance(hA, np.ndarray):
+            hA = np.ascontiguousarray(hA, dtype=np.float32)
+        if isinstance(hB, np.ndarray):
+            hB = np.ascontiguousarray(hB, dtype=np.float32)
+        if hP is None:
+            hP = np.zeros(self.nnz, dtype=np.float32)
+        ms, tot = C.c_float(0), C.c_float(0)
+        _check(lib().bsmr_sddmm_host(self._h, K, _ptr(hA), _ptr(hB), _ptr(hP), iterations, flags, C.byref(ms),
+                                     C.byref(tot)))
+        return hP, ms.value, tot.value
+
+
+from . import synth  # noqa: E402,F401  (seeded synthetic inputs: numpy only)

@@ -1,0 +1,548 @@
+// C ABI of libbsmr_b200.so (declared in include/bsmr_b200.h).
+// Host-side orchestration only; kernels live in residual.cu / dense_tc.cu / colreorder.cu /
+// rowreorder.cu.  Nothing here falls back to the CPU: without a device every call fails.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace bsmr {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_error; }
+
+}  // namespace bsmr
+
+using namespace bsmr;
+
+extern "C" {
+
+const char* bsmr_version(void) { return "bsmr_b200 0.1 (sm_100a)"; }
+const char* bsmr_last_error(void) { return get_error(); }
+
+const char* bsmr_status_string(int status) {
+    switch (status) {
+        case BSMR_OK: return "ok";
+        case BSMR_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case BSMR_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (this library has no CPU path)";
+        case BSMR_ERR_CUDA: return "CUDA error";
+        case BSMR_ERR_OUT_OF_MEMORY: return "out of device memory";
+        case BSMR_ERR_BAD_STATE: return "call order violated";
+        case BSMR_ERR_UNSUPPORTED: return "unsupported";
+    }
+    return "unknown status";
+}
+
+int bsmr_ctx_create(int device, void* cuda_stream, bsmr_ctx** out) {
+    if (!out) {
+        set_error("bsmr_ctx_create: out is NULL");
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        (void)cudaGetLastError();
+        set_error("no CUDA device visible (%s); libbsmr_b200 has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return BSMR_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) {
+        set_error("device %d out of range (0..%d)", device, count - 1);
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    cudaDeviceProp prop{};
+    BSMR_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return BSMR_ERR_NO_DEVICE;
+    }
+    BSMR_CUDA_OK(cudaSetDevice(device));
+    bsmr_ctx* ctx = new bsmr_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major;
+    ctx->cc_minor = prop.minor;
+    ctx->device_name = prop.name;
+    if (cuda_stream) {
+        ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            set_error("cudaStreamCreate failed");
+            return BSMR_ERR_CUDA;
+        }
+        ctx->owns_stream = true;
+    }
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+    // cuTensorMapEncodeTiled through the runtime: no link-time dependency on libcuda.so
+    cudaDriverEntryPointQueryResult qres;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+        ctx->encode_tiled = fn;
+    } else {
+        (void)cudaGetLastError();
+    }
+    *out = ctx;
+    return BSMR_OK;
+}
+
+int bsmr_ctx_destroy(bsmr_ctx* ctx) {
+    if (!ctx) return BSMR_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return BSMR_OK;
+}
+
+int bsmr_ctx_synchronize(bsmr_ctx* ctx) {
+    if (!ctx) return BSMR_ERR_INVALID_ARGUMENT;
+    BSMR_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return BSMR_OK;
+}
+
+int bsmr_ctx_device_name(bsmr_ctx* ctx, char* buf, size_t cap) {
+    if (!ctx || !buf || cap == 0) return BSMR_ERR_INVALID_ARGUMENT;
+    snprintf(buf, cap, "%s", ctx->device_name.c_str());
+    return BSMR_OK;
+}
+
+int bsmr_ctx_launch_count(bsmr_ctx* ctx, uint64_t* count) {
+    if (!ctx || !count) return BSMR_ERR_INVALID_ARGUMENT;
+    *count = ctx->launches;
+    return BSMR_OK;
+}
+
+int bsmr_calculate_block_size(bsmr_ctx* ctx, uint32_t M, uint32_t N, uint64_t free_mem_bytes, uint32_t* block_size) {
+    if (!ctx || !block_size) return BSMR_ERR_INVALID_ARGUMENT;
+    if (free_mem_bytes == 0) {
+        size_t free_b = 0, total_b = 0;
+        BSMR_CUDA_OK(cudaSetDevice(ctx->device));
+        BSMR_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+        free_mem_bytes = free_b;
+    }
+    // src/rowReordering.cu:1014-1024 -- integer numerators, float divisors, ceil
+    const float gm = static_cast<float>(static_cast<uint64_t>(M) * M * 4u) / static_cast<float>(free_mem_bytes / 2);
+    const float sm = static_cast<float>(static_cast<uint64_t>(N) * 4u) / static_cast<float>(49152u / 2);
+    const uint32_t a = static_cast<uint32_t>(std::ceil(gm));
+    const uint32_t b = static_cast<uint32_t>(std::ceil(sm));
+    const uint32_t bs = std::max(a, b);
+    *block_size = bs > 16 ? bs : 16;
+    return BSMR_OK;
+}
+
+// ------------------------------------------------------------------------------- plan
+int bsmr_plan_create(bsmr_ctx* ctx, uint32_t M, uint32_t N, uint32_t nnz, const uint32_t* row_offsets,
+                     const uint32_t* col_indices, int on_device, bsmr_plan** out) {
+    if (!ctx || !out || !row_offsets || (nnz && !col_indices)) {
+        set_error("bsmr_plan_create: NULL argument");
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    *out = nullptr;
+    BSMR_CUDA_OK(cudaSetDevice(ctx->device));
+    bsmr_plan* p = new bsmr_plan();
+    p->ctx = ctx;
+    p->M = M;
+    p->N = N;
+    p->nnz = nnz;
+    int s = p->row_offsets.alloc(static_cast<size_t>(M) + 1);
+    if (s == BSMR_OK) s = p->col_indices.alloc(nnz);
+    if (s != BSMR_OK) {
+        delete p;
+        return s;
+    }
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    cudaError_t e = cudaMemcpyAsync(p->row_offsets.ptr, row_offsets, p->row_offsets.bytes(), kind, ctx->stream);
+    if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(p->col_indices.ptr, col_indices, p->col_indices.bytes(), kind, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        set_error("bsmr_plan_create: copy of the CSR pattern failed: %s", cudaGetErrorString(e));
+        delete p;
+        return BSMR_ERR_CUDA;
+    }
+    // consistency check the reference performs in its loaders (src/Matrix.cpp:442-465): offsets must end at nnz
+    uint32_t last = 0;
+    e = cudaMemcpy(&last, p->row_offsets.ptr + M, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess || last != nnz) {
+        set_error("bsmr_plan_create: row_offsets[M] = %u but nnz = %u", last, nnz);
+        delete p;
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    *out = p;
+    return BSMR_OK;
+}
+
+int bsmr_plan_destroy(bsmr_plan* plan) {
+    if (!plan) return BSMR_OK;
+    cudaSetDevice(plan->ctx->device);
+    delete plan;
+    return BSMR_OK;
+}
+
+static void reset_shard(bsmr_plan* p) {
+    p->sharded = false;
+    p->shard_first_panel = 0;
+    p->shard_end_panel = p->num_row_panels;
+    p->shard_res_begin = 0;
+    p->shard_res_end = p->num_res;
+    p->shard_tile_begin = 0;
+    p->shard_tile_end = p->num_tiles;
+}
+
+int bsmr_plan_row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flags) {
+    if (!plan) return BSMR_ERR_INVALID_ARGUMENT;
+    BSMR_CUDA_OK(cudaSetDevice(plan->ctx->device));
+    plan->have_cols = plan->have_format = false;
+    BSMR_TRY(row_reorder(plan, alpha, block_size, flags));
+    plan->have_rows = true;
+    return BSMR_OK;
+}
+
+int bsmr_plan_set_row_order(bsmr_plan* plan, const uint32_t* reordered_rows, uint32_t count) {
+    if (!plan || (count && !reordered_rows)) return BSMR_ERR_INVALID_ARGUMENT;
+    if (count > plan->M) {
+        set_error("bsmr_plan_set_row_order: %u rows given but the matrix has %u", count, plan->M);
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    for (uint32_t i = 0; i < count; ++i) {
+        if (reordered_rows[i] >= plan->M) {
+            set_error("bsmr_plan_set_row_order: row %u out of range", reordered_rows[i]);
+            return BSMR_ERR_INVALID_ARGUMENT;
+        }
+    }
+    BSMR_CUDA_OK(cudaSetDevice(plan->ctx->device));
+    plan->h_reordered_rows.assign(reordered_rows, reordered_rows + count);
+    BSMR_TRY(plan->reordered_rows.alloc(count));
+    if (count) {
+        BSMR_CUDA_OK(cudaMemcpyAsync(plan->reordered_rows.ptr, reordered_rows, count * sizeof(uint32_t),
+                                     cudaMemcpyHostToDevice, plan->ctx->stream));
+        BSMR_CUDA_OK(cudaStreamSynchronize(plan->ctx->stream));
+    }
+    // numRowPanels_ = ceil(size / ROW_PANEL_SIZE)   (src/BSMR.cpp:57)
+    plan->num_row_panels = (count + kPanel - 1) / kPanel;
+    plan->have_rows = true;
+    plan->have_cols = plan->have_format = false;
+    return BSMR_OK;
+}
+
+int bsmr_plan_col_reorder(bsmr_plan* plan, float delta) {
+    if (!plan) return BSMR_ERR_INVALID_ARGUMENT;
+    if (!plan->have_rows) {
+        set_error("bsmr_plan_col_reorder: no row order yet (call bsmr_plan_row_reorder or bsmr_plan_set_row_order)");
+        return BSMR_ERR_BAD_STATE;
+    }
+    BSMR_CUDA_OK(cudaSetDevice(plan->ctx->device));
+    BSMR_TRY(col_reorder_and_format(plan, delta));
+    plan->have_cols = plan->have_format = true;
+    reset_shard(plan);
+    return BSMR_OK;
+}
+
+int bsmr_plan_reorder(bsmr_plan* plan, float alpha, float delta, uint32_t block_size, uint32_t flags) {
+    BSMR_TRY(bsmr_plan_row_reorder(plan, alpha, block_size, flags));
+    return bsmr_plan_col_reorder(plan, delta);
+}
+
+// ---- accessors -----------------------------------------------------------------------
+static int rphm_reference_layout(bsmr_plan* p, int which, std::vector<uint32_t>& out);
+
+static int fetch_vector(bsmr_plan* p, int which, std::vector<uint32_t>& tmp, const std::vector<uint32_t>** ref) {
+    *ref = nullptr;
+    switch (which) {
+        case BSMR_VEC_REORDERED_ROWS:
+            if (!p->have_rows) break;
+            *ref = &p->h_reordered_rows;
+            return BSMR_OK;
+        case BSMR_VEC_DISPERSIONS: *ref = &p->h_dispersions; return BSMR_OK;
+        case BSMR_VEC_CLUSTER_IDS: *ref = &p->h_cluster_ids; return BSMR_OK;
+        case BSMR_VEC_DENSE_COLS: if (!p->have_cols) break; *ref = &p->h_dense_cols; return BSMR_OK;
+        case BSMR_VEC_DENSE_COL_OFFSETS: if (!p->have_cols) break; *ref = &p->h_dense_col_offsets; return BSMR_OK;
+        case BSMR_VEC_SPARSE_COLS: if (!p->have_cols) break; *ref = &p->h_sparse_cols; return BSMR_OK;
+        case BSMR_VEC_SPARSE_COL_OFFSETS: if (!p->have_cols) break; *ref = &p->h_sparse_col_offsets; return BSMR_OK;
+        case BSMR_VEC_SPARSE_VALUE_OFFSETS: if (!p->have_cols) break; *ref = &p->h_sparse_value_offsets; return BSMR_OK;
+        case BSMR_VEC_BLOCK_OFFSETS:
+        case BSMR_VEC_BLOCK_VALUES:
+        case BSMR_VEC_SPARSE_VALUES:
+        case BSMR_VEC_SPARSE_RELATIVE_ROWS:
+        case BSMR_VEC_SPARSE_COL_INDICES:
+            if (!p->have_format) break;
+            BSMR_TRY(rphm_reference_layout(p, which, tmp));
+            *ref = &tmp;
+            return BSMR_OK;
+        default:
+            set_error("unknown vector id %d", which);
+            return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    set_error("vector %d is not available yet (reorder not run)", which);
+    return BSMR_ERR_BAD_STATE;
+}
+
+int bsmr_plan_vector_size(bsmr_plan* plan, int which, uint64_t* size) {
+    if (!plan || !size) return BSMR_ERR_INVALID_ARGUMENT;
+    std::vector<uint32_t> tmp;
+    const std::vector<uint32_t>* v = nullptr;
+    // sizes of the on-demand RPHM vectors are known without materialising them
+    if (plan->have_format) {
+        switch (which) {
+            case BSMR_VEC_BLOCK_OFFSETS: *size = static_cast<uint64_t>(plan->num_row_panels) + 1; return BSMR_OK;
+            case BSMR_VEC_BLOCK_VALUES: *size = static_cast<uint64_t>(plan->num_dense_blocks) * 256u; return BSMR_OK;
+            case BSMR_VEC_SPARSE_VALUES:
+            case BSMR_VEC_SPARSE_RELATIVE_ROWS:
+            case BSMR_VEC_SPARSE_COL_INDICES: *size = plan->num_res; return BSMR_OK;
+            default: break;
+        }
+    }
+    BSMR_TRY(fetch_vector(plan, which, tmp, &v));
+    *size = v->size();
+    return BSMR_OK;
+}
+
+int bsmr_plan_vector_copy(bsmr_plan* plan, int which, uint32_t* host_out, uint64_t capacity) {
+    if (!plan) return BSMR_ERR_INVALID_ARGUMENT;
+    BSMR_CUDA_OK(cudaSetDevice(plan->ctx->device));
+    std::vector<uint32_t> tmp;
+    const std::vector<uint32_t>* v = nullptr;
+    BSMR_TRY(fetch_vector(plan, which, tmp, &v));
+    if (capacity < v->size()) {
+        set_error("bsmr_plan_vector_copy: capacity %llu < size %zu", (unsigned long long)capacity, v->size());
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    if (!v->empty()) {
+        if (!host_out) return BSMR_ERR_INVALID_ARGUMENT;
+        std::memcpy(host_out, v->data(), v->size() * sizeof(uint32_t));
+    }
+    return BSMR_OK;
+}
+
+// The RPHM accessors in the reference's own layout (src/BSMR.cpp:125-219), derived from our
+// device format: blockValues[(blockOffsets[p]+cb)*256 + r*16 + c] and the residual triplets.
+static int rphm_reference_layout(bsmr_plan* p, int which, std::vector<uint32_t>& out) {
+    bsmr_ctx* ctx = p->ctx;
+    const uint32_t panels = p->num_row_panels;
+    if (which == BSMR_VEC_BLOCK_OFFSETS) {
+        out.assign(static_cast<size_t>(panels) + 1, 0);
+        for (uint32_t q = 0; q < panels; ++q)
+            out[q + 1] = out[q] + (p->h_dense_col_offsets[q + 1] - p->h_dense_col_offsets[q] + kBlockCols - 1) / kBlockCols;
+        return BSMR_OK;
+    }
+    if (which == BSMR_VEC_BLOCK_VALUES) {
+        std::vector<uint32_t> scatter(static_cast<size_t>(p->num_tiles) * kPanel * kTileCols);
+        std::vector<uint32_t> tcb(p->num_tiles), tnc(p->num_tiles);
+        if (p->num_tiles) {
+            BSMR_CUDA_OK(cudaMemcpyAsync(scatter.data(), p->tile_scatter.ptr, scatter.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            BSMR_CUDA_OK(cudaMemcpyAsync(tcb.data(), p->tile_col_begin.ptr, tcb.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            BSMR_CUDA_OK(cudaMemcpyAsync(tnc.data(), p->tile_ncols.ptr, tnc.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            BSMR_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+        }
+        out.assign(static_cast<size_t>(p->num_dense_blocks) * 256u, kNull);
+        // dense_cols offsets are multiples of 16, so global block id = column offset / 16
+        for (uint32_t t = 0; t < p->num_tiles; ++t) {
+            for (uint32_t c = 0; c < tnc[t]; ++c) {
+                const size_t blk = (static_cast<size_t>(tcb[t]) + c) / kBlockCols;
+                for (uint32_t r = 0; r < kPanel; ++r) {
+                    out[blk * 256u + r * kBlockCols + (c % kBlockCols)] =
+                        scatter[(static_cast<size_t>(t) * kPanel + r) * kTileCols + c];
+                }
+            }
+        }
+        return BSMR_OK;
+    }
+    out.assign(p->num_res, 0);
+    if (p->num_res == 0) return BSMR_OK;
+    if (which == BSMR_VEC_SPARSE_VALUES) {
+        BSMR_CUDA_OK(cudaMemcpyAsync(out.data(), p->res_out.ptr, p->num_res * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (which == BSMR_VEC_SPARSE_COL_INDICES) {
+        BSMR_CUDA_OK(cudaMemcpyAsync(out.data(), p->res_col.ptr, p->num_res * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        std::vector<uint8_t> rel(p->num_res);
+        BSMR_CUDA_OK(cudaMemcpyAsync(rel.data(), p->res_rel.ptr, p->num_res, cudaMemcpyDeviceToHost, ctx->stream));
+        BSMR_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < rel.size(); ++i) out[i] = rel[i];
+        return BSMR_OK;
+    }
+    BSMR_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return BSMR_OK;
+}
+
+int bsmr_plan_get_info(bsmr_plan* plan, bsmr_plan_info* info) {
+    if (!plan || !info) return BSMR_ERR_INVALID_ARGUMENT;
+    std::memset(info, 0, sizeof(*info));
+    info->M = plan->M;
+    info->N = plan->N;
+    info->nnz = plan->nnz;
+    info->num_row_panels = plan->num_row_panels;
+    info->num_clusters = plan->num_clusters;
+    info->num_clusters_true = plan->num_clusters_true;
+    info->block_size = plan->block_size;
+    info->num_dense_blocks = plan->num_dense_blocks;
+    info->num_dense_tiles = plan->num_tiles;
+    info->num_dense_values = plan->num_dense_values;
+    info->num_sparse_values = plan->num_res;
+    info->row_reordering_ms = plan->row_ms;
+    info->col_reordering_ms = plan->col_ms;
+    info->format_build_ms = plan->format_ms;
+    return BSMR_OK;
+}
+
+int bsmr_plan_set_shard(bsmr_plan* plan, uint32_t rank, uint32_t world, uint32_t* first_panel, uint32_t* end_panel,
+                        uint64_t* shard_nnz) {
+    if (!plan || world == 0 || rank >= world) {
+        set_error("bsmr_plan_set_shard: bad rank/world %u/%u", rank, world);
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    if (!plan->have_format) {
+        set_error("bsmr_plan_set_shard: reorder first");
+        return BSMR_ERR_BAD_STATE;
+    }
+    // contiguous ranges of reordered row panels, boundaries where the nnz prefix crosses rank * total / world
+    const std::vector<uint64_t>& pre = plan->h_panel_nnz_prefix;  // size panels + 1
+    const uint32_t panels = plan->num_row_panels;
+    const uint64_t total = pre.empty() ? 0 : pre[panels];
+    auto boundary = [&](uint32_t r) -> uint32_t {
+        if (r == 0) return 0;
+        if (r >= world) return panels;
+        const uint64_t target = total / world * r + (total % world) * r / world;
+        return static_cast<uint32_t>(std::lower_bound(pre.begin(), pre.end(), target) - pre.begin());
+    };
+    uint32_t b = boundary(rank), e = boundary(rank + 1);
+    if (b > panels) b = panels;
+    if (e > panels) e = panels;
+    if (e < b) e = b;
+    plan->sharded = world > 1;
+    plan->shard_first_panel = b;
+    plan->shard_end_panel = e;
+    plan->shard_res_begin = plan->h_sparse_value_offsets.empty() ? 0 : plan->h_sparse_value_offsets[b];
+    plan->shard_res_end = plan->h_sparse_value_offsets.empty() ? 0 : plan->h_sparse_value_offsets[e];
+    // tiles are ordered by panel
+    const std::vector<uint32_t>& tp = plan->h_tile_panel;
+    plan->shard_tile_begin = static_cast<uint32_t>(std::lower_bound(tp.begin(), tp.end(), b) - tp.begin());
+    plan->shard_tile_end = static_cast<uint32_t>(std::lower_bound(tp.begin(), tp.end(), e) - tp.begin());
+    if (first_panel) *first_panel = b;
+    if (end_panel) *end_panel = e;
+    if (shard_nnz) *shard_nnz = pre.empty() ? 0 : pre[e] - pre[b];
+    return BSMR_OK;
+}
+
+// ------------------------------------------------------------------------------ SDDMM
+static int ensure_identity_rows(bsmr_plan* p) {
+    if (p->csr_row_of_nnz.ptr || p->nnz == 0) return BSMR_OK;
+    BSMR_TRY(p->csr_row_of_nnz.alloc(p->nnz));
+    return launch_expand_rows(p->ctx, p->M, p->nnz, p->row_offsets.ptr, p->csr_row_of_nnz.ptr);
+}
+
+// One SDDMM pass = dense-block kernel over the (sharded) tile range + residual kernel over the
+// (sharded) residual range.  The reference runs the two on separate streams
+// (src/sddmmKernel.cu:2555-2559); here they are issued back to back on the context's stream --
+// both are persistent-style grids that fill the machine on their own.
+static int run_once(bsmr_plan* p, uint32_t K, const float* dA, const float* dB, float* dP, uint32_t flags) {
+    bsmr_ctx* ctx = p->ctx;
+    if (flags & BSMR_SDDMM_NO_REORDER) {
+        // CSR order: A row from the expanded row list, B column = CSR column, P index = position
+        return launch_residual(ctx, K, dA, dB, dP, p->csr_row_of_nnz.ptr, p->col_indices.ptr, nullptr, 0, p->nnz);
+    }
+    if ((flags & BSMR_SDDMM_RESIDUAL_ONLY) && p->num_tiles != 0) {
+        set_error("BSMR_SDDMM_RESIDUAL_ONLY needs a plan whose column reorder ran with delta > 1 (no dense tiles); "
+                  "use BSMR_SDDMM_NO_REORDER for the CSR-order path");
+        return BSMR_ERR_BAD_STATE;
+    }
+    if (p->shard_tile_end > p->shard_tile_begin) {
+        BSMR_TRY(launch_dense(p, K, dA, dB, dP, p->shard_tile_begin, p->shard_tile_end));
+    }
+    return launch_residual(ctx, K, dA, dB, dP, p->res_row.ptr, p->res_col.ptr, p->res_out.ptr, p->shard_res_begin,
+                           p->shard_res_end);
+}
+
+int bsmr_sddmm(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP, int iterations, uint32_t flags,
+               float* ms_per_iteration) {
+    if (!plan || !dA || !dB || (plan->nnz && !dP) || K == 0) {
+        set_error("bsmr_sddmm: NULL pointer or K == 0");
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    if (!(flags & BSMR_SDDMM_NO_REORDER) && !plan->have_format) {
+        set_error("bsmr_sddmm: the plan has no reorder/format yet (call bsmr_plan_reorder)");
+        return BSMR_ERR_BAD_STATE;
+    }
+    bsmr_ctx* ctx = plan->ctx;
+    BSMR_CUDA_OK(cudaSetDevice(ctx->device));
+    if (ms_per_iteration) *ms_per_iteration = 0.f;
+    if (plan->nnz == 0) return BSMR_OK;
+    if (flags & BSMR_SDDMM_NO_REORDER) BSMR_TRY(ensure_identity_rows(plan));
+    if (iterations <= 0) iterations = 1;
+    if (ms_per_iteration) BSMR_CUDA_OK(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int it = 0; it < iterations; ++it) BSMR_TRY(run_once(plan, K, dA, dB, dP, flags));
+    if (ms_per_iteration) {
+        BSMR_CUDA_OK(cudaEventRecord(ctx->ev1, ctx->stream));
+        BSMR_CUDA_OK(cudaEventSynchronize(ctx->ev1));
+        float ms = 0.f;
+        BSMR_CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        *ms_per_iteration = ms / static_cast<float>(iterations);
+    }
+    return BSMR_OK;
+}
+
+int bsmr_sddmm_host(bsmr_plan* plan, uint32_t K, const float* hA, const float* hB, float* hP, int iterations,
+                    uint32_t flags, float* ms_per_iteration, float* total_ms) {
+    if (!plan || !hA || !hB || (plan->nnz && !hP) || K == 0) {
+        set_error("bsmr_sddmm_host: NULL pointer or K == 0");
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    bsmr_ctx* ctx = plan->ctx;
+    BSMR_CUDA_OK(cudaSetDevice(ctx->device));
+    const size_t na = static_cast<size_t>(plan->M) * K, nb = static_cast<size_t>(plan->N) * K;
+    BSMR_TRY(plan->dA.alloc(na));
+    BSMR_TRY(plan->dB.alloc(nb));
+    BSMR_TRY(plan->dP.alloc(plan->nnz));
+    cudaEvent_t t0, t1;
+    BSMR_CUDA_OK(cudaEventCreate(&t0));
+    BSMR_CUDA_OK(cudaEventCreate(&t1));
+    BSMR_CUDA_OK(cudaEventRecord(t0, ctx->stream));
+    BSMR_CUDA_OK(cudaMemcpyAsync(plan->dA.ptr, hA, na * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    BSMR_CUDA_OK(cudaMemcpyAsync(plan->dB.ptr, hB, nb * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    // dev::vector<float> matrixP_dev(nnz, 0)   (src/sddmmKernel.cu:2525)
+    if (plan->nnz) BSMR_CUDA_OK(cudaMemsetAsync(plan->dP.ptr, 0, plan->dP.bytes(), ctx->stream));
+    float ms = 0.f;
+    int s = bsmr_sddmm(plan, K, plan->dA.ptr, plan->dB.ptr, plan->dP.ptr, iterations, flags, &ms);
+    if (s == BSMR_OK && plan->nnz) {
+        cudaError_t e = cudaMemcpyAsync(hP, plan->dP.ptr, plan->dP.bytes(), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) {
+            set_error("D2H copy of P failed: %s", cudaGetErrorString(e));
+            s = BSMR_ERR_CUDA;
+        }
+    }
+    cudaEventRecord(t1, ctx->stream);
+    cudaError_t e = cudaEventSynchronize(t1);
+    float tot = 0.f;
+    if (e == cudaSuccess) cudaEventElapsedTime(&tot, t0, t1);
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    if (s == BSMR_OK && e != cudaSuccess) {
+        set_error("bsmr_sddmm_host: %s", cudaGetErrorString(e));
+        s = BSMR_ERR_CUDA;
+    }
+    if (ms_per_iteration) *ms_per_iteration = ms;
+    if (total_ms) *total_ms = tot;
+    return s;
+}
+
+int bsmr_plan_evaluate(bsmr_plan* plan, float delta, bsmr_reorder_stats* stats) {
+    if (!plan || !stats) return BSMR_ERR_INVALID_ARGUMENT;
+    if (!plan->have_format) {
+        set_error("bsmr_plan_evaluate: reorder first");
+        return BSMR_ERR_BAD_STATE;
+    }
+    BSMR_CUDA_OK(cudaSetDevice(plan->ctx->device));
+    return evaluate_reordering(plan, delta, stats);
+}
+
+}  // extern "C"

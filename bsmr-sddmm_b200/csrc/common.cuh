@@ -1,0 +1,156 @@
+// Shared internals of libbsmr_b200.so (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "bsmr_b200.h"
+
+namespace bsmr {
+
+constexpr uint32_t kPanel = BSMR_ROW_PANEL_SIZE;    // rows per row panel
+constexpr uint32_t kBlockCols = BSMR_BLOCK_COL_SIZE;  // columns per reference dense block
+constexpr uint32_t kTileCols = 128;                   // dense columns per tcgen05 tile (UMMA M)
+constexpr uint32_t kNull = BSMR_NULL_VALUE;
+
+// ---- error plumbing: every ABI function returns a status and records a message ---------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define BSMR_CUDA_OK(expr)                                                              \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            ::bsmr::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,             \
+                              cudaGetErrorString(_e));                                  \
+            return _e == cudaErrorMemoryAllocation ? BSMR_ERR_OUT_OF_MEMORY : BSMR_ERR_CUDA; \
+        }                                                                               \
+    } while (0)
+
+#define BSMR_TRY(expr)                      \
+    do {                                    \
+        int _s = (expr);                    \
+        if (_s != BSMR_OK) return _s;       \
+    } while (0)
+
+// ---- RAII device buffer (replaces the reference's dev::vector, include/devVector.cuh) ---
+template <typename T>
+struct DevBuf {
+    T* ptr = nullptr;
+    size_t count = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        count = 0;
+    }
+    // (re)allocate exactly n elements; contents undefined
+    int alloc(size_t n) {
+        if (n == count && ptr) return BSMR_OK;
+        release();
+        if (n == 0) return BSMR_OK;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ptr), n * sizeof(T));
+        if (e != cudaSuccess) {
+            ptr = nullptr;
+            set_error("cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            return BSMR_ERR_OUT_OF_MEMORY;
+        }
+        count = n;
+        return BSMR_OK;
+    }
+    size_t bytes() const { return count * sizeof(T); }
+};
+
+}  // namespace bsmr
+
+// ---- the two opaque ABI objects ----------------------------------------------------------
+struct bsmr_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    std::string device_name;
+    uint64_t launches = 0;  // kernels of this library launched through this context
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // tensor-map encoder resolved at runtime (no link-time dependency on libcuda)
+    void* encode_tiled = nullptr;
+};
+
+struct bsmr_plan {
+    bsmr_ctx* ctx = nullptr;
+    uint32_t M = 0, N = 0, nnz = 0;
+
+    // CSR pattern on the device
+    bsmr::DevBuf<uint32_t> row_offsets, col_indices;
+
+    // ---- BSMR object (host copies are what the accessors return) ----
+    bool have_rows = false, have_cols = false, have_format = false;
+    std::vector<uint32_t> h_reordered_rows;
+    bsmr::DevBuf<uint32_t> reordered_rows;
+    uint32_t num_row_panels = 0;
+    int num_clusters = 1, num_clusters_true = 1;
+    uint32_t block_size = 0;
+    std::vector<uint32_t> h_dispersions, h_cluster_ids;
+    float row_ms = 0.f, col_ms = 0.f, format_ms = 0.f;
+
+    std::vector<uint32_t> h_dense_cols, h_dense_col_offsets, h_sparse_cols, h_sparse_col_offsets,
+        h_sparse_value_offsets;
+    bsmr::DevBuf<uint32_t> dense_cols;  // per panel, multiple of 16, sentinel N possible
+
+    // ---- device format (our RPHM) ----
+    // residual entries ordered (panel, residual column order, row in panel): exactly the
+    // reference's sparseValues / sparseRelativeRows / sparseColIndices, with the A row made absolute
+    bsmr::DevBuf<uint32_t> res_out;   // CSR index (P position)
+    bsmr::DevBuf<uint32_t> res_col;   // B column
+    bsmr::DevBuf<uint32_t> res_row;   // A row (absolute)
+    bsmr::DevBuf<uint8_t> res_rel;    // row inside the panel (for the RPHM accessor)
+    uint64_t num_res = 0;
+    // dense tiles: up to 128 dense columns (8 reference blocks) of one panel
+    bsmr::DevBuf<uint32_t> tile_panel;     // panel id per tile
+    bsmr::DevBuf<uint32_t> tile_col_begin; // offset into dense_cols
+    bsmr::DevBuf<uint32_t> tile_ncols;     // 16..128
+    bsmr::DevBuf<uint32_t> tile_scatter;   // [tile][16 rows][128 cols] CSR index or NULL
+    std::vector<uint32_t> h_tile_panel;
+    uint32_t num_tiles = 0;
+    uint32_t num_dense_blocks = 0;
+    uint64_t num_dense_values = 0;
+    std::vector<uint64_t> h_panel_nnz_prefix;  // nnz (dense + residual) before each panel
+
+    // ---- identity ("no reorder") residual list, built lazily ----
+    bsmr::DevBuf<uint32_t> csr_row_of_nnz;
+
+    // ---- shard (multi-GPU) ----
+    uint32_t shard_first_panel = 0, shard_end_panel = 0;
+    uint64_t shard_res_begin = 0, shard_res_end = 0;
+    uint32_t shard_tile_begin = 0, shard_tile_end = 0;
+    bool sharded = false;
+
+    // scratch for the host-data overload
+    bsmr::DevBuf<float> dA, dB, dP;
+};
+
+namespace bsmr {
+
+// ---- kernels' host launchers (defined in the .cu files) ---------------------------------
+int launch_residual(bsmr_ctx* ctx, uint32_t K, const float* dA, const float* dB, float* dP,
+                    const uint32_t* res_row, const uint32_t* res_col, const uint32_t* res_out,
+                    uint64_t begin, uint64_t end);
+int launch_expand_rows(bsmr_ctx* ctx, uint32_t M, uint32_t nnz, const uint32_t* row_offsets, uint32_t* row_of_nnz);
+
+int col_reorder_and_format(bsmr_plan* plan, float delta);
+int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flags);
+int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP,
+                 uint32_t tile_begin, uint32_t tile_end);
+int evaluate_reordering(bsmr_plan* plan, float delta, bsmr_reorder_stats* stats);
+
+}  // namespace bsmr

@@ -1,0 +1,401 @@
+// Dense-block SDDMM kernel for sm_100a: TMA gather -> shared memory -> tcgen05.mma (TF32,
+// fp32 accumulate in TMEM) -> tcgen05.ld -> S-mask + scatter to CSR order, all in one kernel.
+//
+// Replaces sddmm_gpu_dense_block_m16n16k8_matrixA_rowMaj_matrixB_colMaj and its K<=32 twin
+// (src/sddmmKernel.cu:213-351, 355-488): wmma m16n16k8, one warp per 16x16 block, operands
+// staged with scalar __ldg into padded smem, accumulator fragments scattered through
+// blockValues.
+//
+// Why it is not a transliteration.  tcgen05.mma needs M in {64,128} per CTA; a BSMR row panel
+// has only 16 rows and every panel has its own dense column list, so panels cannot be stacked
+// along M.  The operands are therefore SWAPPED: one work item ("tile") is up to 128 dense
+// columns of one panel (8 reference blocks) and the MMA computes the transposed product
+//      D[128 cols x 16 rows] = Bcols[128 x K] * Arows[16 x K]^T
+//   * M side = 128 gathered columns of B.  B is column-major (ld = K), so a column is a
+//     contiguous K-vector: the matrix [N x K] is "K-major" as tcgen05 wants it.
+//   * N side = the panel's 16 gathered rows of A (row-major, K-major as well), N = 16.
+//   * K is consumed 32 floats (= 128 bytes = one SWIZZLE_128B atom row) per pipeline stage,
+//     4 tcgen05.mma.kind::tf32 (K = 8 each) per stage.
+// TMA: cp.async.bulk.tensor.2d ... tile::gather4 fetches 4 arbitrary rows of the [N x K] (or
+// [M x K]) tensor per request and lays them down as 4 consecutive 128-byte rows of the
+// swizzled smem tile; 32 requests fill the B-column tile, 4 the A-row tile.  Sentinel columns
+// (index N, the reference's padding) and rows past the last panel row are out of bounds for
+// the tensor map and arrive as zeros.
+// Warp roles (6 warps): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue
+// (tcgen05.ld of the warp's 32 TMEM lanes x 16 columns, mask + scatter P[idx] = acc).
+// Two TMEM accumulators (2 x 16 columns) let the epilogue of tile i overlap the MMAs of tile
+// i+1; a 5-stage smem ring (18 KB / stage) keeps ~90 KB of loads in flight per CTA.
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace bsmr {
+namespace {
+
+constexpr int kStages = 5;
+constexpr int kChunk = 32;                         // floats of K per stage (128 bytes)
+constexpr int kBTileBytes = kTileCols * kChunk * 4;   // 16384
+constexpr int kATileBytes = kPanel * kChunk * 4;      // 2048
+constexpr int kDenseThreads = 192;
+constexpr int kTmemCols = 32;                      // 2 accumulators x 16 fp32 columns
+constexpr uint32_t kSpinLimit = 1u << 28;
+
+struct __align__(16) DenseSmemTail {
+    uint64_t full[kStages];
+    uint64_t empty[kStages];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad[3];
+};
+constexpr size_t kDenseSmemBytes = 1024 /*alignment slack*/ + (size_t)kStages * (kBTileBytes + kATileBytes) + sizeof(DenseSmemTail);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a wrong transaction count must become an error, never a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* error_flag, uint32_t code) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > kSpinLimit) {
+            atomicExch(error_flag, code);
+            __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_gather4(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int4 rows) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes.cta_group::1"
+        " [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(rows.x), "r"(rows.y), "r"(rows.z), "r"(rows.w), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_row(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp, SmemDescriptor):
+// start address >> 4 in [0,14), LBO = 0, SBO = 1024 bytes (8 rows x 128 B) >> 4 in [32,46),
+// version = 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>(1024u >> 4) << 32;
+    d |= 1ull << 46;
+    d |= 2ull << 61;
+    return d;
+}
+
+// Instruction descriptor for kind::tf32, fp32 accumulate, A and B K-major, M x N
+// (InstrDescriptor: c_format [4,6) = 1 (F32), a_format [7,10) = 2 (TF32), b_format [10,13) = 2,
+//  a_major bit 15 = 0, b_major bit 16 = 0, n_dim [17,23) = N >> 3, m_dim [24,29) = M >> 4).
+__host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct DenseParams {
+    uint32_t K;
+    uint32_t M;              // rows of A (out-of-bounds row index for missing panel rows)
+    uint32_t N;
+    uint32_t num_rows;       // reordered (non-empty) rows
+    uint32_t tile_begin, tile_end;
+    const uint32_t* reordered_rows;
+    const uint32_t* dense_cols;
+    const uint32_t* tile_panel;
+    const uint32_t* tile_col_begin;
+    const uint32_t* tile_ncols;
+    const uint32_t* tile_scatter;
+    float* P;
+    uint32_t* error_flag;
+    uint32_t* debug_smem;    // optional: raw copy of stage 0 of the first tile (probe / tests)
+    int use_gather4;
+};
+
+__global__ void __launch_bounds__(kDenseThreads, 2)
+dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const DenseParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* b_tiles = smem;                                   // kStages x 16 KB, 1024-aligned
+    uint8_t* a_tiles = smem + (size_t)kStages * kBTileBytes;     // kStages x 2 KB, 1024-aligned
+    DenseSmemTail* tail = reinterpret_cast<DenseSmemTail*>(a_tiles + (size_t)kStages * kATileBytes);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t num_chunks = (p.K + kChunk - 1) / kChunk;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&tail->full[s], 1);
+            mbar_init(&tail->empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tail->tmem_full[a], 1);
+            mbar_init(&tail->tmem_empty[a], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tail->tmem_base)), "n"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tail->tmem_base;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        uint32_t stage = 0, phase = 0;
+        for (uint32_t t = p.tile_begin + blockIdx.x; t < p.tile_end; t += gridDim.x) {
+            const uint32_t panel = __ldg(p.tile_panel + t);
+            const uint32_t cb = __ldg(p.tile_col_begin + t);
+            const uint32_t nc = __ldg(p.tile_ncols + t);
+            // lane l owns dense columns 4l..4l+3 of the tile; lanes 0..3 also own panel rows 4l..4l+3
+            int4 cols = make_int4((int)p.N, (int)p.N, (int)p.N, (int)p.N);
+            const bool has_cols = lane * 4 < nc;
+            if (has_cols) cols = __ldg(reinterpret_cast<const int4*>(p.dense_cols + cb) + lane);
+            int4 rows = make_int4((int)p.M, (int)p.M, (int)p.M, (int)p.M);
+            if (lane < 4) {
+                const uint32_t r0 = panel * kPanel + lane * 4;
+                int* rp = reinterpret_cast<int*>(&rows);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (r0 + j < p.num_rows) rp[j] = (int)__ldg(p.reordered_rows + r0 + j);
+            }
+            const uint32_t tx_bytes = (nc / 4) * 512u + kATileBytes;
+            for (uint32_t kc = 0; kc < num_chunks; ++kc) {
+                mbar_wait(&tail->empty[stage], phase ^ 1, p.error_flag, 1);
+                if (lane == 0) mbar_arrive_expect_tx(&tail->full[stage], tx_bytes);
+                __syncwarp();
+                uint8_t* bt = b_tiles + (size_t)stage * kBTileBytes;
+                uint8_t* at = a_tiles + (size_t)stage * kATileBytes;
+                const int x = (int)(kc * kChunk);
+                if (p.use_gather4) {
+                    if (has_cols) tma_gather4(&map_b, &tail->full[stage], bt + lane * 512, x, cols);
+                    if (lane < 4) tma_gather4(&map_a, &tail->full[stage], at + lane * 512, x, rows);
+                } else {
+                    if (has_cols) {
+                        tma_row(&map_b, &tail->full[stage], bt + lane * 512 + 0, x, cols.x);
+                        tma_row(&map_b, &tail->full[stage], bt + lane * 512 + 128, x, cols.y);
+                        tma_row(&map_b, &tail->full[stage], bt + lane * 512 + 256, x, cols.z);
+                        tma_row(&map_b, &tail->full[stage], bt + lane * 512 + 384, x, cols.w);
+                    }
+                    if (lane < 4) {
+                        tma_row(&map_a, &tail->full[stage], at + lane * 512 + 0, x, rows.x);
+                        tma_row(&map_a, &tail->full[stage], at + lane * 512 + 128, x, rows.y);
+                        tma_row(&map_a, &tail->full[stage], at + lane * 512 + 256, x, rows.z);
+                        tma_row(&map_a, &tail->full[stage], at + lane * 512 + 384, x, rows.w);
+                    }
+                }
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = make_idesc_tf32(kTileCols, kPanel);
+        uint32_t stage = 0, phase = 0, it = 0;
+        for (uint32_t t = p.tile_begin + blockIdx.x; t < p.tile_end; t += gridDim.x, ++it) {
+            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            mbar_wait(&tail->tmem_empty[acc], acc_phase ^ 1, p.error_flag, 2);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * kPanel;
+            for (uint32_t kc = 0; kc < num_chunks; ++kc) {
+                mbar_wait(&tail->full[stage], phase, p.error_flag, 3);
+                tc_fence_after();
+                if (p.debug_smem && t == p.tile_begin && kc == 0 && blockIdx.x == 0) {
+                    // probe: raw image of stage 0 (B-column tile then A-row tile)
+                    const uint32_t* src_b = reinterpret_cast<const uint32_t*>(b_tiles);
+                    const uint32_t* src_a = reinterpret_cast<const uint32_t*>(a_tiles);
+                    for (uint32_t i = lane; i < kBTileBytes / 4; i += 32) p.debug_smem[i] = src_b[i];
+                    for (uint32_t i = lane; i < kATileBytes / 4; i += 32) p.debug_smem[kBTileBytes / 4 + i] = src_a[i];
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    const uint64_t da = make_smem_desc(smem_u32(b_tiles + (size_t)stage * kBTileBytes));
+                    const uint64_t db = make_smem_desc(smem_u32(a_tiles + (size_t)stage * kATileBytes));
+#pragma unroll
+                    for (uint32_t k = 0; k < kChunk / 8; ++k) {
+                        // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in the (>>4) address field
+                        umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&tail->empty[stage]);
+                    if (kc + 1 == num_chunks) umma_commit(&tail->tmem_full[acc]);
+                }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ================= epilogue (warps 2..5) =================
+        const uint32_t quarter = warp & 3;              // TMEM lanes [32*quarter, 32*quarter + 32)
+        const uint32_t c = quarter * 32 + lane;         // dense column of the tile owned by this thread
+        uint32_t it = 0;
+        for (uint32_t t = p.tile_begin + blockIdx.x; t < p.tile_end; t += gridDim.x, ++it) {
+            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            const uint32_t nc = __ldg(p.tile_ncols + t);
+            const bool active = quarter * 32 < nc;
+            uint32_t idx[kPanel];
+            if (active) {
+                const uint32_t* sc = p.tile_scatter + (size_t)t * kPanel * kTileCols + c;
+#pragma unroll
+                for (int r = 0; r < (int)kPanel; ++r) idx[r] = __ldg(sc + r * kTileCols);
+            }
+            mbar_wait(&tail->tmem_full[acc], acc_phase, p.error_flag, 4);
+            tc_fence_after();
+            uint32_t v[kPanel];
+            if (active) {
+                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kPanel;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
+            if (active) {
+#pragma unroll
+                for (int r = 0; r < (int)kPanel; ++r)
+                    if (idx[r] != kNull) p.P[idx[r]] = __uint_as_float(v[r]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D fp32 tensor [rows x K] with K contiguous; box = 32 floats of one row; SWIZZLE_128B.
+int make_row_gather_map(bsmr_ctx* ctx, const float* base, uint64_t rows, uint64_t K, CUtensorMap* out) {
+    if (!ctx->encode_tiled) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return BSMR_ERR_UNSUPPORTED;
+    }
+    const cuuint64_t dims[2] = {K, rows};
+    const cuuint64_t strides[1] = {K * sizeof(float)};
+    const cuuint32_t box[2] = {kChunk, 1};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+        out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu K=%llu)", (int)r, (unsigned long long)rows,
+                  (unsigned long long)K);
+        return BSMR_ERR_CUDA;
+    }
+    return BSMR_OK;
+}
+
+}  // namespace
+
+// test hook: when set, the next dense launch copies the first tile's stage-0 smem image here
+static uint32_t* g_debug_smem = nullptr;
+extern "C" void bsmr_debug_set_dense_smem_dump(uint32_t* device_buffer) { g_debug_smem = device_buffer; }
+
+int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP, uint32_t tile_begin, uint32_t tile_end) {
+    bsmr_ctx* ctx = plan->ctx;
+    if (tile_end <= tile_begin) return BSMR_OK;
+    if (K % 4 != 0 || (reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(dB)) % 16 != 0) {
+        set_error("dense-block path needs K %% 4 == 0 and 16-byte aligned A/B (TMA row stride); K = %u", K);
+        return BSMR_ERR_UNSUPPORTED;
+    }
+    CUtensorMap map_a, map_b;
+    BSMR_TRY(make_row_gather_map(ctx, dA, plan->M, K, &map_a));
+    BSMR_TRY(make_row_gather_map(ctx, dB, plan->N, K, &map_b));
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        BSMR_CUDA_OK(cudaFuncSetAttribute(dense_sddmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseSmemBytes));
+        attr_set = true;
+    }
+    static DevBuf<uint32_t> error_flag;  // one per process is enough: it only ever reports a broken pipeline
+    if (!error_flag.ptr) {
+        BSMR_TRY(error_flag.alloc(1));
+        BSMR_CUDA_OK(cudaMemsetAsync(error_flag.ptr, 0, 4, ctx->stream));
+    }
+    DenseParams p{};
+    p.K = K; p.M = plan->M; p.N = plan->N;
+    p.num_rows = static_cast<uint32_t>(plan->h_reordered_rows.size());
+    p.tile_begin = tile_begin; p.tile_end = tile_end;
+    p.reordered_rows = plan->reordered_rows.ptr;
+    p.dense_cols = plan->dense_cols.ptr;
+    p.tile_panel = plan->tile_panel.ptr;
+    p.tile_col_begin = plan->tile_col_begin.ptr;
+    p.tile_ncols = plan->tile_ncols.ptr;
+    p.tile_scatter = plan->tile_scatter.ptr;
+    p.P = dP;
+    p.error_flag = error_flag.ptr;
+    p.debug_smem = g_debug_smem;
+    g_debug_smem = nullptr;
+    const char* mode = std::getenv("BSMR_DENSE_TMA_MODE");  // "rows" = one TMA request per row instead of gather4
+    p.use_gather4 = !(mode && mode[0] == 'r');
+
+    const uint32_t tiles = tile_end - tile_begin;
+    const uint32_t max_ctas = static_cast<uint32_t>(ctx->sm_count) * 2;  // 2 CTAs (2 x 97 KB smem, 2 x 32 TMEM columns) per SM
+    const uint32_t grid = tiles < max_ctas ? tiles : max_ctas;
+    dense_sddmm_kernel<<<grid, kDenseThreads, kDenseSmemBytes, ctx->stream>>>(map_a, map_b, p);
+    ctx->launches++;
+    BSMR_CUDA_OK(cudaGetLastError());
+    return BSMR_OK;
+}
+
+int evaluate_reordering(bsmr_plan* plan, float delta, bsmr_reorder_stats* stats) {
+    (void)plan; (void)delta; (void)stats;
+    set_error("bsmr_plan_evaluate is not implemented yet");
+    return BSMR_ERR_UNSUPPORTED;
+}
+
+}  // namespace bsmr

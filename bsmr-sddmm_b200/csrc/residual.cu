@@ -1,0 +1,209 @@
+// Sparse-residual SDDMM kernel (CUDA cores) for sm_100a.
+//
+// Replaces the reference's sddmm_gpu_sparse_block_2_2threadOneData_shuffle and
+// sddmm_gpu_sparse_remainder_k32_2threadOneData_shuffle (src/sddmmKernel.cu:1994-2104,
+// 2109-2199).  Those use 2 threads per nnz, a 16x36 smem A tile rebuilt every 32 k and
+// two 16-byte loads per thread per step.  Here:
+//   * a warp owns 32 consecutive residual entries; their (A row, B column, P index)
+//     triples are read with one coalesced load each and handed around by shuffles
+//   * a group of LPN lanes (8 / 16 / 32, chosen from K) computes one entry: every lane
+//     loads 128-bit pieces of the A row and of the B column (a full K-vector is one or
+//     more perfectly coalesced 128..512-byte requests), 4 FMAs per piece, then a
+//     log2(LPN)-step xor-shuffle reduction
+//   * UNROLL entries are in flight per group, so every lane has 2*UNROLL*KV independent
+//     16-byte loads outstanding before the first FMA
+//   * results are moved to "lane j holds entry j" and stored with one warp-wide store,
+//     which is fully coalesced whenever the P indices are consecutive (CSR-order mode)
+// No shared memory, no block barrier; the A rows of a panel (16*K*4 bytes) live in L1.
+//
+// Roofline: HBM-bound on compulsory traffic; what it actually stresses is L2->SM gather
+// bandwidth (K*4 bytes of B per nnz), see DESIGN.md.
+#include "common.cuh"
+
+namespace bsmr {
+namespace {
+
+constexpr int kResThreads = 256;
+constexpr int kWarpsPerCta = kResThreads / 32;
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+    acc = fmaf(a.x, b.x, acc);
+    acc = fmaf(a.y, b.y, acc);
+    acc = fmaf(a.z, b.z, acc);
+    acc = fmaf(a.w, b.w, acc);
+    return acc;
+}
+
+// LPN: lanes per nnz.  KV: number of float4 pieces per lane (K == LPN*4*KV); KV == 0 -> runtime loop.
+template <int LPN, int KV, int UNROLL>
+__global__ void __launch_bounds__(kResThreads)
+residual_sddmm_kernel(const uint32_t K, const float* __restrict__ A, const float* __restrict__ B,
+                      float* __restrict__ P, const uint32_t* __restrict__ res_row,
+                      const uint32_t* __restrict__ res_col, const uint32_t* __restrict__ res_out,
+                      const uint64_t begin, const uint64_t end) {
+    constexpr int G = 32 / LPN;     // entries processed concurrently by one warp
+    constexpr int ITERS = 32 / G;   // passes to cover the warp's 32 entries
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t sub = lane / LPN;       // which concurrent entry this lane works on
+    const uint32_t sl = lane % LPN;        // lane inside the group
+    const uint64_t num_chunks = (end - begin + 31) / 32;
+    const uint64_t warp_global = (uint64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const uint64_t warp_stride = (uint64_t)gridDim.x * kWarpsPerCta;
+
+    for (uint64_t chunk = warp_global; chunk < num_chunks; chunk += warp_stride) {
+        const uint64_t e = begin + chunk * 32 + lane;
+        const bool valid = e < end;
+        // coalesced metadata loads; invalid lanes point at entry `begin` (always in range)
+        const uint64_t es = valid ? e : begin;
+        const uint32_t my_row = __ldg(res_row + es);
+        const uint32_t my_col = __ldg(res_col + es);
+        const uint32_t my_out = res_out ? __ldg(res_out + es) : (uint32_t)es;  // NULL = identity (CSR order)
+        float my_res = 0.f;
+
+#pragma unroll 1
+        for (int it0 = 0; it0 < ITERS; it0 += UNROLL) {
+            float acc[UNROLL];
+            if constexpr (KV > 0) {
+                float4 av[UNROLL][KV], bv[UNROLL][KV];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const int j = (it0 + u) * G + sub;  // entry (lane index) this group computes
+                    const uint32_t row = __shfl_sync(0xffffffffu, my_row, j);
+                    const uint32_t col = __shfl_sync(0xffffffffu, my_col, j);
+                    const float* ap = A + (size_t)row * K + sl * 4;
+                    const float* bp = B + (size_t)col * K + sl * 4;
+#pragma unroll
+                    for (int v = 0; v < KV; ++v) {
+                        av[u][v] = ldg4(ap + v * LPN * 4);
+                        bv[u][v] = ldg4(bp + v * LPN * 4);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    acc[u] = 0.f;
+#pragma unroll
+                    for (int v = 0; v < KV; ++v) acc[u] = dot4(av[u][v], bv[u][v], acc[u]);
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const int j = (it0 + u) * G + sub;
+                    const uint32_t row = __shfl_sync(0xffffffffu, my_row, j);
+                    const uint32_t col = __shfl_sync(0xffffffffu, my_col, j);
+                    const float* ap = A + (size_t)row * K;
+                    const float* bp = B + (size_t)col * K;
+                    float s = 0.f;
+                    for (uint32_t k = sl * 4; k < K; k += LPN * 4) s = dot4(ldg4(ap + k), ldg4(bp + k), s);
+                    acc[u] = s;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                float s = acc[u];
+#pragma unroll
+                for (int w = LPN / 2; w >= 1; w >>= 1) s += __shfl_xor_sync(0xffffffffu, s, w);
+                // entry j = (it0+u)*G + sub now lives in every lane of group `sub`; hand it to lane j
+                const float v = __shfl_sync(0xffffffffu, s, (lane % G) * LPN);
+                if ((int)(lane / G) == it0 + u) my_res = v;
+            }
+        }
+        if (valid) P[my_out] = my_res;
+    }
+}
+
+// Any K (no alignment assumption): one lane group of 32, scalar loads.
+__global__ void __launch_bounds__(kResThreads)
+residual_sddmm_generic_kernel(const uint32_t K, const float* __restrict__ A, const float* __restrict__ B,
+                              float* __restrict__ P, const uint32_t* __restrict__ res_row,
+                              const uint32_t* __restrict__ res_col, const uint32_t* __restrict__ res_out,
+                              const uint64_t begin, const uint64_t end) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp_global = (uint64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const uint64_t warp_stride = (uint64_t)gridDim.x * kWarpsPerCta;
+    for (uint64_t e = begin + warp_global; e < end; e += warp_stride) {
+        const float* ap = A + (size_t)__ldg(res_row + e) * K;
+        const float* bp = B + (size_t)__ldg(res_col + e) * K;
+        float s = 0.f;
+        for (uint32_t k = lane; k < K; k += 32) s = fmaf(__ldg(ap + k), __ldg(bp + k), s);
+#pragma unroll
+        for (int w = 16; w >= 1; w >>= 1) s += __shfl_xor_sync(0xffffffffu, s, w);
+        if (lane == 0) P[res_out ? __ldg(res_out + e) : (uint32_t)e] = s;
+    }
+}
+
+// row_of_nnz[i] = row that owns CSR position i (one warp per row, coalesced writes)
+__global__ void expand_rows_kernel(const uint32_t M, const uint32_t* __restrict__ row_offsets,
+                                   uint32_t* __restrict__ row_of_nnz) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < M; r += stride) {
+        const uint32_t b = __ldg(row_offsets + r), e = __ldg(row_offsets + r + 1);
+        for (uint32_t i = b + lane; i < e; i += 32) row_of_nnz[i] = (uint32_t)r;
+    }
+}
+
+template <int LPN, int KV, int UNROLL>
+void launch_one(bsmr_ctx* ctx, int grid, uint32_t K, const float* dA, const float* dB, float* dP,
+                const uint32_t* rr, const uint32_t* rc, const uint32_t* ro, uint64_t begin, uint64_t end) {
+    residual_sddmm_kernel<LPN, KV, UNROLL><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, rr, rc, ro, begin, end);
+}
+
+}  // namespace
+
+int launch_residual(bsmr_ctx* ctx, uint32_t K, const float* dA, const float* dB, float* dP,
+                    const uint32_t* res_row, const uint32_t* res_col, const uint32_t* res_out,
+                    uint64_t begin, uint64_t end) {
+    if (end <= begin) return BSMR_OK;
+    if (K == 0) {
+        set_error("K must be positive");
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    const uint64_t chunks = (end - begin + 31) / 32;
+    const uint64_t ctas_needed = (chunks + kWarpsPerCta - 1) / kWarpsPerCta;
+    // 8 CTAs of 256 threads = 64 warps = a full SM; grid is a multiple of the SM count
+    const uint64_t max_ctas = (uint64_t)ctx->sm_count * 8;
+    const int grid = (int)(ctas_needed < max_ctas ? ctas_needed : max_ctas);
+    const bool aligned = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(dB)) % 16 == 0);
+
+    if (!aligned) {
+        const uint64_t warps = end - begin;
+        const uint64_t need = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
+        const int g = (int)(need < max_ctas ? need : max_ctas);
+        residual_sddmm_generic_kernel<<<g, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+    } else if (K == 32) {
+        launch_one<8, 1, 4>(ctx, grid, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+    } else if (K == 64) {
+        launch_one<16, 1, 4>(ctx, grid, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+    } else if (K == 128) {
+        launch_one<32, 1, 4>(ctx, grid, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+    } else if (K == 256) {
+        launch_one<32, 2, 4>(ctx, grid, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+    } else if (K == 512) {
+        launch_one<32, 4, 2>(ctx, grid, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+    } else if (K < 64) {
+        launch_one<8, 0, 2>(ctx, grid, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+    } else if (K < 128) {
+        launch_one<16, 0, 2>(ctx, grid, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+    } else {
+        launch_one<32, 0, 2>(ctx, grid, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+    }
+    ctx->launches++;
+    BSMR_CUDA_OK(cudaGetLastError());
+    return BSMR_OK;
+}
+
+int launch_expand_rows(bsmr_ctx* ctx, uint32_t M, uint32_t nnz, const uint32_t* row_offsets, uint32_t* row_of_nnz) {
+    if (M == 0 || nnz == 0) return BSMR_OK;
+    const uint64_t warps_needed = M;
+    const uint64_t ctas = (warps_needed + 7) / 8;
+    const uint64_t max_ctas = (uint64_t)ctx->sm_count * 8;
+    expand_rows_kernel<<<(int)(ctas < max_ctas ? ctas : max_ctas), 256, 0, ctx->stream>>>(M, row_offsets, row_of_nnz);
+    ctx->launches++;
+    BSMR_CUDA_OK(cudaGetLastError());
+    return BSMR_OK;
+}
+
+}  // namespace bsmr

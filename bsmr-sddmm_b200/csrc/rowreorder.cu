@@ -1,0 +1,553 @@
+// Row reordering (BSA clustering) on the GPU, bit-compatible with the reference.
+//
+// Replaces bsa_rowReordering_gpu and everything under it (src/rowReordering.cu:1027-1095):
+//   kernel::calculateDispersion (:49-93), the host stable sort (:1055-1062),
+//   get_permutation_gpu (:893-1007) with kernel::bsa_clustering (:325-432) and
+//   calculate_similarity_norm_weighted_jaccard (:235-293), the final stable sort by
+//   cluster id (:986-995) and the empty-row strip (:1081-1090).
+//
+// The reference keeps a DENSE rows x nb encoding matrix, runs one CTA per live cluster
+// (launched from the device, chained by per-row mutexes) and spends a whole-CTA reduction over
+// all nb column blocks on every (cluster, row) pair.  Here:
+//   * encodings are SPARSE (row -> sorted (block, count) list) built with one radix sort +
+//     run-length encode; only the current cluster representative is dense, in shared memory
+//   * one persistent cooperative kernel (1 CTA of 1024 threads per SM) walks the clusters in
+//     order; every step evaluates the next gridDim*32 still-unassigned rows in parallel -- one
+//     warp per row -- against the current representative, the first row that joins is found
+//     with an atomicMin + one grid barrier, rows before it are rejected for this cluster and
+//     are appended (order preserving, no scan) to the next cluster's candidate list
+//   * a similarity evaluation touches only the threads of the reference CTA that own a
+//     non-zero block of the candidate; all other per-thread / per-warp partial sums are those
+//     of the representative alone and are computed once per representative version
+// Bit-compatibility: the reference decides "sim > alpha" on fp32 values produced by a
+// specific order of operations (strided per-thread sums, xor-shuffle butterfly, then a shared
+// memory tree that DROPS warps when the CTA has a non-power-of-two warp count,
+// include/cudaUtil.cuh:27-45).  Every float operation below is performed in that same order on
+// the same operands, so the decisions -- and therefore the permutation -- are identical.
+// BSMR_ROW_EXACT_REDUCE switches the lossy tree for a complete one.
+#include <cooperative_groups.h>
+#include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace bsmr {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kClusterThreads = 1024;
+constexpr uint32_t kInf = 0xFFFFFFFFu;
+
+inline int grid_for(uint64_t n, int per_cta, int sm_count) {
+    uint64_t g = (n + per_cta - 1) / per_cta;
+    const uint64_t cap = (uint64_t)sm_count * 16;
+    if (g > cap) g = cap;
+    if (g == 0) g = 1;
+    return (int)g;
+}
+
+// ---- sparse encodings ------------------------------------------------------------------------
+// key = row << 32 | (col / block_size), one warp per row
+__global__ void enc_keys_kernel(uint32_t M, const uint32_t* __restrict__ row_offsets, const uint32_t* __restrict__ col_indices,
+                                uint32_t block_size, uint64_t* __restrict__ keys) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < M; r += stride) {
+        const uint32_t b = row_offsets[r], e = row_offsets[r + 1];
+        for (uint32_t k = b + lane; k < e; k += 32) keys[k] = (r << 32) | (uint64_t)(col_indices[k] / block_size);
+    }
+}
+
+__global__ void runs_per_row_kernel(const uint64_t* __restrict__ ukeys, uint32_t num_runs, uint32_t* __restrict__ runs_per_row) {
+    for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < num_runs; u += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(runs_per_row + (uint32_t)(ukeys[u] >> 32), 1u);
+}
+
+// dispersion (src/rowReordering.cu:78-92) and the row's (possibly lossy) sum of squares, thread per row
+__global__ void dispersion_kernel(uint32_t M, const uint32_t* __restrict__ row_offsets, const uint32_t* __restrict__ enc_ptr,
+                                  const uint64_t* __restrict__ ukeys, const uint32_t* __restrict__ counts, uint32_t block_size,
+                                  uint32_t bd, uint32_t kept_mask, uint32_t* __restrict__ dispersion, uint32_t* __restrict__ row_sq) {
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t nz = row_offsets[r + 1] - row_offsets[r];
+        const uint32_t b = enc_ptr[r], e = enc_ptr[r + 1];
+        uint32_t res = 0, sq = 0;
+        for (uint32_t j = b; j < e; ++j) {
+            const uint32_t c = counts[j];
+            const uint32_t blk = (uint32_t)(ukeys[j] & 0xffffffffull);
+            res += block_size - c;
+            if ((kept_mask >> ((blk % bd) >> 5)) & 1u) sq += c * c;
+        }
+        dispersion[r] = nz ? res + nz * (e - b) : 0u;
+        row_sq[r] = sq;
+    }
+}
+
+__global__ void iota_kernel(uint32_t* p, uint32_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = (uint32_t)i;
+}
+
+__global__ void gather_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, uint32_t n, uint32_t* __restrict__ dst) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[idx[i]];
+}
+
+__global__ void count_zero_kernel(const uint32_t* __restrict__ v, uint32_t n, uint32_t* __restrict__ out) {
+    uint32_t c = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) c += (v[i] == 0);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+struct Low32Key {
+    __host__ __device__ uint64_t operator()(uint64_t k) const { return k; }
+};
+
+// ---- the clustering kernel ------------------------------------------------------------------
+struct ClusterParams {
+    uint32_t M;            // rows (positions in dispersion order)
+    uint32_t nb;           // column blocks per row
+    uint32_t bd;           // CTA size the REFERENCE would use (src/rowReordering.cu:911-920); defines the sum order
+    uint32_t first_stride; // first stride of the shared-memory tree (bd/64 in the reference)
+    uint32_t zero_rows;    // leading empty rows (cluster 0)
+    float alpha;
+    const uint32_t* asc;       // position -> row
+    const uint32_t* enc_ptr;   // row -> first run
+    const uint64_t* ukeys;     // run -> row << 32 | block
+    const uint32_t* counts;    // run -> nnz in the block
+    const uint32_t* row_sq;    // row -> (lossy) sum of squares
+    uint32_t* cluster_ids;     // position -> cluster id (pre-set: 0 for empty rows, NULL otherwise)
+    uint32_t* cand_a;          // candidate lists (positions), double buffered
+    uint32_t* cand_b;
+    uint32_t* first_join;      // 3 slots
+    uint32_t* num_clusters;    // out
+};
+
+// block reduction with the reference's structure, executed by threads [0, bd) of the CTA
+// (include/cudaUtil.cuh:13-45).  `shm` has >= 32 entries.  All kClusterThreads threads call it.
+template <typename T>
+__device__ __forceinline__ T ref_block_reduce(T value, T* shm, uint32_t bd, uint32_t first_stride) {
+    const uint32_t tid = threadIdx.x;
+    T tmp = value;
+#pragma unroll
+    for (int w = 1; w < 32; w <<= 1) tmp += __shfl_xor_sync(0xffffffffu, tmp, w);
+    const uint32_t warp = tid >> 5, lane = tid & 31;
+    if (tid < 32) shm[tid] = T(0);
+    __syncthreads();
+    if (lane == 0 && tid < bd) shm[warp] = tmp;
+    __syncthreads();
+    for (uint32_t stride = first_stride; stride >= 1; stride >>= 1) {
+        if (warp < stride && lane == 0 && warp + stride < 32) shm[warp] += shm[warp + stride];
+        __syncthreads();
+    }
+    const T r = shm[0];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(ClusterParams p) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ uint32_t smem[];
+    uint32_t* rep = smem;                                        // [nb]  representative encoding
+    float* repn = reinterpret_cast<float*>(smem + p.nb);         // [nb]  (float)rep / norm_rep
+    float* warp_max = repn + p.nb;                               // [32]  per-reference-warp max partial of the representative alone
+    uint32_t* red_u = reinterpret_cast<uint32_t*>(warp_max + 32);  // [32]
+    float* red_f = reinterpret_cast<float*>(red_u + 32);         // [32]
+    __shared__ uint32_t s_sq_rep;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t gwarp = blockIdx.x * (kClusterThreads / 32) + (tid >> 5);
+    const uint32_t W = gridDim.x * (kClusterThreads / 32);
+    const uint32_t nw = p.bd >> 5;
+
+    // refresh everything derived from `rep` (called by the whole CTA after rep changed)
+    auto refresh = [&]() {
+        // sum of squares: thread t of the reference CTA owns blocks t, t+bd, ...; int e*e wraps (:241-249)
+        uint32_t sq = 0;
+        if (tid < p.bd)
+            for (uint32_t i = tid; i < p.nb; i += p.bd) sq += rep[i] * rep[i];
+        sq = ref_block_reduce<uint32_t>(sq, red_u, p.bd, p.first_stride);
+        if (tid == 0) s_sq_rep = sq;
+        const float nr = sqrtf((float)sq);
+        for (uint32_t i = tid; i < p.nb; i += kClusterThreads) repn[i] = (float)rep[i] / nr;
+        __syncthreads();
+        // per-thread max partial of the representative alone, then the butterfly (:273-282)
+        float mx = 0.f;
+        if (tid < p.bd)
+            for (uint32_t i = tid; i < p.nb; i += p.bd) mx += repn[i];
+#pragma unroll
+        for (int w = 1; w < 32; w <<= 1) mx += __shfl_xor_sync(0xffffffffu, mx, w);
+        if (tid < 32) warp_max[tid] = 0.f;
+        __syncthreads();
+        if (lane == 0 && tid < p.bd) warp_max[tid >> 5] = mx;
+        __syncthreads();
+    };
+
+    // add row `row`'s encoding into rep (whole CTA)
+    auto absorb = [&](uint32_t row, bool assign) {
+        const uint32_t b = p.enc_ptr[row], e = p.enc_ptr[row + 1];
+        if (assign)
+            for (uint32_t i = tid; i < p.nb; i += kClusterThreads) rep[i] = 0;
+        __syncthreads();
+        for (uint32_t j = b + tid; j < e; j += kClusterThreads) rep[(uint32_t)(p.ukeys[j] & 0xffffffffull)] += p.counts[j];
+        __syncthreads();
+    };
+
+    uint32_t* cand = p.cand_a;
+    uint32_t* next = p.cand_b;
+    uint32_t n_un = p.M - p.zero_rows;  // candidates in `cand` (positions zero_rows .. M-1 initially, written by the host side)
+    uint32_t cluster = 0;
+    uint32_t step = 0;
+
+    while (n_un > 0) {
+        ++cluster;
+        const uint32_t start_pos = cand[0];
+        if (blockIdx.x == 0 && tid == 0) p.cluster_ids[start_pos] = cluster;
+        absorb(p.asc[start_pos], true);
+        refresh();
+        uint32_t cursor = 1, out = 0;
+        while (cursor < n_un) {
+            const uint32_t slot = step % 3;
+            // ---- evaluate one candidate per warp ----
+            const uint32_t ci = cursor + gwarp;
+            uint32_t my_pos = kInf;
+            if (ci < n_un) {
+                my_pos = cand[ci];
+                const uint32_t row = p.asc[my_pos];
+                const uint32_t s_cmp = p.row_sq[row];
+                const uint32_t s_rep = s_sq_rep;
+                float sim;
+                if (s_rep == 0 && s_cmp == 0) {
+                    sim = 1.0f;
+                } else if (s_rep == 0 || s_cmp == 0) {
+                    sim = 0.0f;
+                } else {
+                    const float nc = sqrtf((float)s_cmp);
+                    const uint32_t b = p.enc_ptr[row], e = p.enc_ptr[row + 1];
+                    // which reference warps own a non-zero block of this row
+                    uint32_t touched = 0;
+                    for (uint32_t j = b + lane; j < e; j += 32) {
+                        const uint32_t blk = (uint32_t)(p.ukeys[j] & 0xffffffffull);
+                        touched |= 1u << ((blk % p.bd) >> 5);
+                    }
+                    touched = __reduce_or_sync(0xffffffffu, touched);
+                    float my_min = 0.f, my_max = lane < nw ? warp_max[lane] : 0.f;  // lane w = reference warp w
+                    while (touched) {
+                        const uint32_t w = __ffs(touched) - 1;
+                        touched &= touched - 1;
+                        // this lane emulates reference thread t = w*32 + lane: terms i = t, t+bd, ... ascending
+                        const uint32_t t = (w << 5) + lane;
+                        float acc_min = 0.f, acc_max = 0.f;
+                        uint32_t next_i = t;
+                        for (uint32_t j0 = b; j0 < e; j0 += 32) {
+                            const uint32_t j = j0 + lane;
+                            uint32_t blk = 0, cnt = 0;
+                            bool hit = false;
+                            if (j < e) {
+                                blk = (uint32_t)(p.ukeys[j] & 0xffffffffull);
+                                cnt = p.counts[j];
+                                hit = ((blk % p.bd) >> 5) == w;
+                            }
+                            uint32_t sel = __ballot_sync(0xffffffffu, hit);
+                            while (sel) {
+                                const uint32_t src = __ffs(sel) - 1;
+                                sel &= sel - 1;
+                                const uint32_t blk_e = __shfl_sync(0xffffffffu, blk, src);
+                                const uint32_t cnt_e = __shfl_sync(0xffffffffu, cnt, src);
+                                if (((blk_e % p.bd) & 31) == lane) {
+                                    for (; next_i < blk_e; next_i += p.bd) acc_max += repn[next_i];
+                                    const float a = repn[blk_e];
+                                    const float c = (float)cnt_e / nc;
+                                    acc_min += fminf(a, c);
+                                    acc_max += fmaxf(a, c);
+                                    next_i = blk_e + p.bd;
+                                }
+                            }
+                        }
+                        for (; next_i < p.nb; next_i += p.bd) acc_max += repn[next_i];
+#pragma unroll
+                        for (int x = 1; x < 32; x <<= 1) {
+                            acc_min += __shfl_xor_sync(0xffffffffu, acc_min, x);
+                            acc_max += __shfl_xor_sync(0xffffffffu, acc_max, x);
+                        }
+                        if (lane == w) {
+                            my_min = acc_min;
+                            my_max = acc_max;
+                        }
+                    }
+                    // shared-memory tree of the reference over the per-warp values (lossy for odd warp counts)
+                    for (uint32_t stride = p.first_stride; stride >= 1; stride >>= 1) {
+                        const float tmin = __shfl_down_sync(0xffffffffu, my_min, stride);
+                        const float tmax = __shfl_down_sync(0xffffffffu, my_max, stride);
+                        if (lane < stride && lane + stride < 32) {
+                            my_min += tmin;
+                            my_max += tmax;
+                        }
+                    }
+                    sim = __shfl_sync(0xffffffffu, my_min, 0) / __shfl_sync(0xffffffffu, my_max, 0);
+                }
+                if (lane == 0 && sim > p.alpha) atomicMin(p.first_join + slot, ci);
+            }
+            grid.sync();
+            const uint32_t fj = *((volatile uint32_t*)(p.first_join + slot));
+            // slot used by the previous step is free again once everybody passed this barrier
+            if (blockIdx.x == 0 && tid == 0) p.first_join[(step + 2) % 3] = kInf;
+            ++step;
+            const uint32_t end_rejected = fj == kInf ? min(cursor + W, n_un) : fj;
+            if (my_pos != kInf && ci < end_rejected && lane == 0) next[out + (ci - cursor)] = my_pos;
+            out += end_rejected - cursor;
+            if (fj == kInf) {
+                cursor = end_rejected;
+            } else {
+                const uint32_t jpos = cand[fj];
+                if (blockIdx.x == 0 && tid == 0) p.cluster_ids[jpos] = cluster;
+                absorb(p.asc[jpos], false);
+                refresh();
+                cursor = fj + 1;
+            }
+        }
+        // next cluster works on the rejected rows, in order
+        grid.sync();
+        uint32_t* t = cand;
+        cand = next;
+        next = t;
+        n_un = out;
+    }
+    if (blockIdx.x == 0 && tid == 0) *p.num_clusters = cluster;
+}
+
+__global__ void init_cluster_state_kernel(uint32_t M, uint32_t zero_rows, uint32_t* cluster_ids, uint32_t* cand, uint32_t* first_join) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
+        cluster_ids[i] = i < zero_rows ? 0u : kInf;
+        if (i >= zero_rows) cand[i - zero_rows] = (uint32_t)i;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 3) first_join[threadIdx.x] = kInf;
+}
+
+int bits_for(uint64_t max_value) {
+    int b = 1;
+    while (b < 64 && (max_value >> b) != 0) ++b;
+    return b;
+}
+
+// src/rowReordering.cu:911-920
+uint32_t clustering_blockdim(uint32_t nb) {
+    if (nb < 32) return 32;
+    int cand = 32 * static_cast<int>(std::ceil(static_cast<float>(nb / 4) / 32.0f));
+    if (cand < 32) cand = 32;
+    return cand > 1024 ? 1024u : static_cast<uint32_t>(cand);
+}
+
+}  // namespace
+
+int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flags) {
+    bsmr_ctx* ctx = plan->ctx;
+    cudaStream_t st = ctx->stream;
+    const uint32_t M = plan->M, N = plan->N, nnz = plan->nnz;
+    const int sm = ctx->sm_count;
+    cudaEvent_t e0, e1;
+    BSMR_CUDA_OK(cudaEventCreate(&e0));
+    BSMR_CUDA_OK(cudaEventCreate(&e1));
+    struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } guard{e0, e1};
+    BSMR_CUDA_OK(cudaEventRecord(e0, st));
+
+    plan->h_dispersions.clear();
+    plan->h_cluster_ids.clear();
+    std::vector<uint32_t> h_ro(static_cast<size_t>(M) + 1);
+    BSMR_CUDA_OK(cudaMemcpyAsync(h_ro.data(), plan->row_offsets.ptr, h_ro.size() * 4, cudaMemcpyDeviceToHost, st));
+    BSMR_CUDA_OK(cudaStreamSynchronize(st));
+
+    std::vector<uint32_t>& perm = plan->h_reordered_rows;
+    perm.clear();
+    if ((flags & 3u) == BSMR_ROW_IDENTITY) {
+        // noReorderRow (src/rowReordering.cu:15-46): original order, empty rows removed
+        for (uint32_t r = 0; r < M; ++r)
+            if (h_ro[r + 1] != h_ro[r]) perm.push_back(r);
+        plan->num_clusters = plan->num_clusters_true = 1;
+        plan->block_size = 0;
+    } else {
+        if (block_size == 0) BSMR_TRY(bsmr_calculate_block_size(ctx, M, N, 0, &block_size));
+        plan->block_size = block_size;
+        const uint32_t nb = static_cast<uint32_t>(std::ceil(static_cast<float>(N) / static_cast<float>(block_size)));  // :1035
+        const uint32_t bd = clustering_blockdim(nb);
+        const uint32_t nw = bd / 32;
+        const bool exact = (flags & 3u) == BSMR_ROW_EXACT_REDUCE;
+        uint32_t first_stride = nw / 2;  // blockDim.x / (2 * warpSize)   (include/cudaUtil.cuh:37)
+        if (exact) {
+            uint32_t p2 = 1;
+            while (p2 < nw) p2 <<= 1;
+            first_stride = p2 / 2;
+        }
+        // which reference warps survive the tree (every warp at most once)
+        uint32_t kept_mask = 0;
+        {
+            std::vector<uint32_t> contrib(64, 0);
+            for (uint32_t w = 0; w < 32; ++w) contrib[w] = w < nw ? (1u << w) : 0u;
+            for (uint32_t s = first_stride; s >= 1; s >>= 1)
+                for (uint32_t w = 0; w < s; ++w) contrib[w] |= contrib[w + s];
+            kept_mask = contrib[0];
+        }
+        const size_t smem = (static_cast<size_t>(nb) * 2 + 96) * 4;
+        if (smem > 200 * 1024) {
+            set_error("row reorder: %u column blocks need %zu bytes of shared memory; raise block_size", nb, smem);
+            return BSMR_ERR_UNSUPPORTED;
+        }
+
+        DevBuf<uint8_t> temp;
+        auto ensure_temp = [&](size_t bytes) -> int {
+            if (bytes > temp.count) return temp.alloc(bytes + bytes / 8 + 256);
+            return BSMR_OK;
+        };
+        // ---- sparse encodings ----
+        DevBuf<uint64_t> keys_a, keys_b, ukeys;
+        DevBuf<uint32_t> counts, num_runs_d, runs_per_row, enc_ptr, disp, row_sq;
+        BSMR_TRY(runs_per_row.alloc(static_cast<size_t>(M) + 1));
+        BSMR_TRY(enc_ptr.alloc(static_cast<size_t>(M) + 1));
+        BSMR_TRY(disp.alloc(M ? M : 1));
+        BSMR_TRY(row_sq.alloc(M ? M : 1));
+        BSMR_CUDA_OK(cudaMemsetAsync(runs_per_row.ptr, 0, runs_per_row.bytes(), st));
+        uint32_t num_runs = 0;
+        if (nnz) {
+            BSMR_TRY(keys_a.alloc(nnz)); BSMR_TRY(keys_b.alloc(nnz)); BSMR_TRY(ukeys.alloc(nnz)); BSMR_TRY(counts.alloc(nnz));
+            BSMR_TRY(num_runs_d.alloc(1));
+            enc_keys_kernel<<<grid_for((uint64_t)M * 32, kThreads, sm), kThreads, 0, st>>>(M, plan->row_offsets.ptr, plan->col_indices.ptr, block_size, keys_a.ptr);
+            ctx->launches++;
+            // rows are already grouped; sort the block ids inside the rows (columns of a row need not be sorted,
+            // the .mtx loader keeps file order: src/Matrix.cpp:467-470)
+            cub::DoubleBuffer<uint64_t> dk(keys_a.ptr, keys_b.ptr);
+            size_t tb = 0;
+            const int end_bit = 32 + bits_for(M ? M - 1 : 0);
+            BSMR_CUDA_OK(cub::DeviceRadixSort::SortKeys(nullptr, tb, dk, static_cast<int64_t>(nnz), 0, end_bit, st));
+            BSMR_TRY(ensure_temp(tb));
+            BSMR_CUDA_OK(cub::DeviceRadixSort::SortKeys(temp.ptr, tb, dk, static_cast<int64_t>(nnz), 0, end_bit, st));
+            ctx->launches++;
+            BSMR_CUDA_OK(cub::DeviceRunLengthEncode::Encode(nullptr, tb, dk.Current(), ukeys.ptr, counts.ptr, num_runs_d.ptr, static_cast<int64_t>(nnz), st));
+            BSMR_TRY(ensure_temp(tb));
+            BSMR_CUDA_OK(cub::DeviceRunLengthEncode::Encode(temp.ptr, tb, dk.Current(), ukeys.ptr, counts.ptr, num_runs_d.ptr, static_cast<int64_t>(nnz), st));
+            ctx->launches++;
+            BSMR_CUDA_OK(cudaMemcpyAsync(&num_runs, num_runs_d.ptr, 4, cudaMemcpyDeviceToHost, st));
+            BSMR_CUDA_OK(cudaStreamSynchronize(st));
+            runs_per_row_kernel<<<grid_for(num_runs, kThreads, sm), kThreads, 0, st>>>(ukeys.ptr, num_runs, runs_per_row.ptr);
+            ctx->launches++;
+        }
+        {
+            size_t tb = 0;
+            BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb, runs_per_row.ptr, enc_ptr.ptr, static_cast<size_t>(M) + 1, st));
+            BSMR_TRY(ensure_temp(tb));
+            BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(temp.ptr, tb, runs_per_row.ptr, enc_ptr.ptr, static_cast<size_t>(M) + 1, st));
+            ctx->launches++;
+        }
+        DevBuf<uint32_t> asc_a, asc_b, dk_a, dk_b, zero_cnt;
+        BSMR_TRY(asc_a.alloc(M ? M : 1)); BSMR_TRY(asc_b.alloc(M ? M : 1)); BSMR_TRY(dk_a.alloc(M ? M : 1)); BSMR_TRY(dk_b.alloc(M ? M : 1));
+        BSMR_TRY(zero_cnt.alloc(1));
+        BSMR_CUDA_OK(cudaMemsetAsync(zero_cnt.ptr, 0, 4, st));
+        const uint32_t* asc = asc_a.ptr;
+        uint32_t zero_rows = 0;
+        if (M) {
+            dispersion_kernel<<<grid_for(M, kThreads, sm), kThreads, 0, st>>>(M, plan->row_offsets.ptr, enc_ptr.ptr, ukeys.ptr, counts.ptr,
+                                                                             block_size, bd, kept_mask, disp.ptr, row_sq.ptr);
+            // stable ascending sort of the rows by dispersion (:1055-1062)
+            BSMR_CUDA_OK(cudaMemcpyAsync(dk_a.ptr, disp.ptr, static_cast<size_t>(M) * 4, cudaMemcpyDeviceToDevice, st));
+            iota_kernel<<<grid_for(M, kThreads, sm), kThreads, 0, st>>>(asc_a.ptr, M);
+            cub::DoubleBuffer<uint32_t> k2(dk_a.ptr, dk_b.ptr), v2(asc_a.ptr, asc_b.ptr);
+            size_t tb = 0;
+            BSMR_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tb, k2, v2, static_cast<int64_t>(M), 0, 32, st));
+            BSMR_TRY(ensure_temp(tb));
+            BSMR_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp.ptr, tb, k2, v2, static_cast<int64_t>(M), 0, 32, st));
+            asc = v2.Current();
+            // rows with dispersion 0 are exactly the empty rows and sort first (:939-949)
+            count_zero_kernel<<<grid_for(M, kThreads, sm), kThreads, 0, st>>>(disp.ptr, M, zero_cnt.ptr);
+            ctx->launches += 4;
+            BSMR_CUDA_OK(cudaMemcpyAsync(&zero_rows, zero_cnt.ptr, 4, cudaMemcpyDeviceToHost, st));
+            BSMR_CUDA_OK(cudaStreamSynchronize(st));
+        }
+
+        // ---- clustering ----
+        DevBuf<uint32_t> cluster_ids, cand_a, cand_b, first_join, num_clusters_d;
+        BSMR_TRY(cluster_ids.alloc(M ? M : 1)); BSMR_TRY(cand_a.alloc(M ? M : 1)); BSMR_TRY(cand_b.alloc(M ? M : 1));
+        BSMR_TRY(first_join.alloc(4)); BSMR_TRY(num_clusters_d.alloc(1));
+        BSMR_CUDA_OK(cudaMemsetAsync(num_clusters_d.ptr, 0, 4, st));
+        uint32_t clusters_true = 0;
+        if (M) {
+            init_cluster_state_kernel<<<grid_for(M, kThreads, sm), kThreads, 0, st>>>(M, zero_rows, cluster_ids.ptr, cand_a.ptr, first_join.ptr);
+            ctx->launches++;
+        }
+        if (M > zero_rows) {
+            ClusterParams cp{};
+            cp.M = M; cp.nb = nb; cp.bd = bd; cp.first_stride = first_stride; cp.zero_rows = zero_rows; cp.alpha = alpha;
+            cp.asc = asc; cp.enc_ptr = enc_ptr.ptr; cp.ukeys = ukeys.ptr; cp.counts = counts.ptr; cp.row_sq = row_sq.ptr;
+            cp.cluster_ids = cluster_ids.ptr; cp.cand_a = cand_a.ptr; cp.cand_b = cand_b.ptr; cp.first_join = first_join.ptr;
+            cp.num_clusters = num_clusters_d.ptr;
+            BSMR_CUDA_OK(cudaFuncSetAttribute(bsa_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            int per_sm = 0;
+            BSMR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bsa_cluster_kernel, kClusterThreads, smem));
+            if (per_sm < 1) {
+                set_error("row reorder: clustering kernel does not fit on an SM (smem %zu)", smem);
+                return BSMR_ERR_UNSUPPORTED;
+            }
+            // never more warps than candidates: small inputs run on few CTAs (cheaper grid barrier)
+            int grid = sm;
+            const uint32_t need = (M - zero_rows + 31) / 32;
+            if (static_cast<uint32_t>(grid) > need) grid = static_cast<int>(need ? need : 1);
+            void* args[] = {&cp};
+            BSMR_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(bsa_cluster_kernel), dim3(grid), dim3(kClusterThreads), args, smem, st));
+            ctx->launches++;
+            BSMR_CUDA_OK(cudaMemcpyAsync(&clusters_true, num_clusters_d.ptr, 4, cudaMemcpyDeviceToHost, st));
+        }
+
+        // ---- permutation = stable sort of the positions by cluster id (:986-995) ----
+        DevBuf<uint32_t> ck_b, idx_a, idx_b, perm_d;
+        std::vector<uint32_t> h_sorted_ids, h_indices, h_perm;
+        if (M) {
+            BSMR_TRY(ck_b.alloc(M)); BSMR_TRY(idx_a.alloc(M)); BSMR_TRY(idx_b.alloc(M)); BSMR_TRY(perm_d.alloc(M));
+            // keep an unsorted copy of the ids for the diagnostics accessor
+            plan->h_cluster_ids.resize(M);
+            std::vector<uint32_t> h_ids_by_pos(M), h_asc(M);
+            BSMR_CUDA_OK(cudaMemcpyAsync(h_ids_by_pos.data(), cluster_ids.ptr, static_cast<size_t>(M) * 4, cudaMemcpyDeviceToHost, st));
+            BSMR_CUDA_OK(cudaMemcpyAsync(h_asc.data(), asc, static_cast<size_t>(M) * 4, cudaMemcpyDeviceToHost, st));
+            iota_kernel<<<grid_for(M, kThreads, sm), kThreads, 0, st>>>(idx_a.ptr, M);
+            cub::DoubleBuffer<uint32_t> k3(cluster_ids.ptr, ck_b.ptr), v3(idx_a.ptr, idx_b.ptr);
+            size_t tb = 0;
+            BSMR_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tb, k3, v3, static_cast<int64_t>(M), 0, 32, st));
+            BSMR_TRY(ensure_temp(tb));
+            BSMR_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp.ptr, tb, k3, v3, static_cast<int64_t>(M), 0, 32, st));
+            gather_kernel<<<grid_for(M, kThreads, sm), kThreads, 0, st>>>(asc, v3.Current(), M, perm_d.ptr);
+            ctx->launches += 3;
+            h_sorted_ids.resize(M); h_indices.resize(M); h_perm.resize(M);
+            BSMR_CUDA_OK(cudaMemcpyAsync(h_sorted_ids.data(), k3.Current(), static_cast<size_t>(M) * 4, cudaMemcpyDeviceToHost, st));
+            BSMR_CUDA_OK(cudaMemcpyAsync(h_indices.data(), v3.Current(), static_cast<size_t>(M) * 4, cudaMemcpyDeviceToHost, st));
+            BSMR_CUDA_OK(cudaMemcpyAsync(h_perm.data(), perm_d.ptr, static_cast<size_t>(M) * 4, cudaMemcpyDeviceToHost, st));
+            plan->h_dispersions.resize(M);
+            BSMR_CUDA_OK(cudaMemcpyAsync(plan->h_dispersions.data(), disp.ptr, static_cast<size_t>(M) * 4, cudaMemcpyDeviceToHost, st));
+            BSMR_CUDA_OK(cudaStreamSynchronize(st));
+            for (uint32_t i = 0; i < M; ++i) plan->h_cluster_ids[h_asc[i]] = h_ids_by_pos[i];
+            // cluster_cnt = cluster_ids[indices[rows-1]] + (zero_row_idx != 0)  -- the index is applied to the SORTED key
+            // array (src/rowReordering.cu:996); kept verbatim as the "reference" cluster count
+            plan->num_clusters = static_cast<int>(h_sorted_ids[h_indices[M - 1]]) + (zero_rows != 0 ? 1 : 0);
+            plan->num_clusters_true = static_cast<int>(clusters_true);
+            // strip the leading empty rows (:1081-1090)
+            uint32_t first = 0;
+            while (first < M && h_ro[h_perm[first] + 1] - h_ro[h_perm[first]] == 0) ++first;
+            perm.assign(h_perm.begin() + first, h_perm.end());
+        } else {
+            plan->num_clusters = plan->num_clusters_true = 0;
+        }
+    }
+
+    BSMR_TRY(plan->reordered_rows.alloc(perm.size()));
+    if (!perm.empty())
+        BSMR_CUDA_OK(cudaMemcpyAsync(plan->reordered_rows.ptr, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice, st));
+    // numRowPanels_ = ceil(reorderedRows.size() / ROW_PANEL_SIZE)   (src/BSMR.cpp:48)
+    plan->num_row_panels = static_cast<uint32_t>((perm.size() + kPanel - 1) / kPanel);
+    BSMR_CUDA_OK(cudaEventRecord(e1, st));
+    BSMR_CUDA_OK(cudaEventSynchronize(e1));
+    BSMR_CUDA_OK(cudaGetLastError());
+    BSMR_CUDA_OK(cudaEventElapsedTime(&plan->row_ms, e0, e1));
+    return BSMR_OK;
+}
+
+}  // namespace bsmr

@@ -1,0 +1,185 @@
+/* bsmr_b200.h -- C ABI of libbsmr_b200.so, the B200 (sm_100a) implementation of the
+ * BSMR-SDDMM hot path:  P[idx] = sum_k A[row,k] * B[k,col] at the CSR positions of S,
+ * with S reordered by BSMR (row clustering alpha + per-panel column reordering delta) into
+ * dense 16-row x 16-column tensor-core blocks plus a sparse residual.
+ *
+ * The reference (CX9898/BSMR-SDDMM) has no FFI layer; its boundary is a C++ host API.
+ * Every entry point below names the reference interface it replaces (file:line relative to
+ * the reference tree).  The header-only C++ mirror of that API (bsmr-sddmm_b200/host/*.hpp:
+ * Matrix, sparseMatrix::CSR, Options, Logger, BSMR, RPHM, sddmm(), sddmm_gpu()) is a thin
+ * layer over exactly these functions.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types cross this boundary
+ *   - every function returns a bsmr_status (0 = OK) and never throws; bsmr_last_error()
+ *     gives the text for the most recent failure on the calling thread
+ *   - indices are uint32_t ("UIN", include/TensorCoreConfig.cuh:10), values are fp32
+ *   - A is M x K row-major (ld = K), B is K x N column-major (ld = K)  (src/main.cu:25-29)
+ *   - one context = one device + one stream; one caller thread per context
+ *   - there is NO CPU fallback: without a usable sm_100 device every compute call fails
+ *     with BSMR_ERR_NO_DEVICE
+ */
+#ifndef BSMR_B200_H
+#define BSMR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSMR_ROW_PANEL_SIZE 16u        /* ROW_PANEL_SIZE, include/BSMR.hpp:8  */
+#define BSMR_BLOCK_COL_SIZE 16u        /* BLOCK_COL_SIZE, include/BSMR.hpp:9  */
+#define BSMR_NULL_VALUE 0xFFFFFFFFu    /* NULL_VALUE, include/TensorCoreConfig.cuh:12 */
+
+typedef enum {
+    BSMR_OK = 0,
+    BSMR_ERR_INVALID_ARGUMENT = 1,
+    BSMR_ERR_NO_DEVICE = 2,       /* no CUDA device / not sm_100: the product has no CPU path */
+    BSMR_ERR_CUDA = 3,            /* a CUDA runtime / driver call or kernel launch failed */
+    BSMR_ERR_OUT_OF_MEMORY = 4,
+    BSMR_ERR_BAD_STATE = 5,       /* e.g. SDDMM before the column reorder was run */
+    BSMR_ERR_UNSUPPORTED = 6
+} bsmr_status;
+
+typedef struct bsmr_ctx bsmr_ctx;     /* device + stream + scratch                       */
+typedef struct bsmr_plan bsmr_plan;   /* one sparsity pattern: BSMR object + RPHM format */
+
+const char* bsmr_version(void);
+const char* bsmr_last_error(void);
+const char* bsmr_status_string(int status);
+
+/* ---- context ------------------------------------------------------------------------
+ * Replaces the reference's implicit "device 0 + default stream + cudaDeviceSynchronize
+ * everywhere" (include/Logger.hpp:23-25, src/sddmmKernel.cu:2555-2559).
+ * `cuda_stream` is a cudaStream_t (may be NULL = a stream owned by the context).        */
+int bsmr_ctx_create(int device, void* cuda_stream, bsmr_ctx** out);
+int bsmr_ctx_destroy(bsmr_ctx* ctx);
+int bsmr_ctx_synchronize(bsmr_ctx* ctx);
+int bsmr_ctx_device_name(bsmr_ctx* ctx, char* buf, size_t cap);     /* Logger::gpu_ */
+
+/* calculateBlockSize (src/rowReordering.cu:1009-1025):
+ * max(16, ceil(M*M*4 / (free/2)), ceil(N*4 / 24576)).  free_mem_bytes == 0 -> query the
+ * device like the reference does (cudaMemGetInfo).                                       */
+int bsmr_calculate_block_size(bsmr_ctx* ctx, uint32_t M, uint32_t N, uint64_t free_mem_bytes,
+                              uint32_t* block_size);
+
+/* ---- plan = BSMR object (include/BSMR.hpp:21-63, src/BSMR.cpp:16-81) -----------------
+ * The CSR pattern is copied to the device (values of S are never used: the reference does
+ * not multiply by them, src/host.cpp:62-73).  `on_device` != 0 -> the two arrays are device
+ * pointers on ctx's device.                                                              */
+int bsmr_plan_create(bsmr_ctx* ctx, uint32_t M, uint32_t N, uint32_t nnz,
+                     const uint32_t* row_offsets, const uint32_t* col_indices, int on_device,
+                     bsmr_plan** out);
+int bsmr_plan_destroy(bsmr_plan* plan);
+
+/* flags for bsmr_plan_row_reorder */
+#define BSMR_ROW_REFERENCE_COMPAT 0u  /* reproduce the reference's lossy block reduction
+                                         (include/cudaUtil.cuh:27-45) -> bit-identical rows */
+#define BSMR_ROW_EXACT_REDUCE     1u  /* sum every warp (mathematically intended Jaccard)  */
+#define BSMR_ROW_IDENTITY         2u  /* noReorderRow (src/rowReordering.cu:15-46): keep the
+                                         original order, only strip empty rows              */
+
+/* BSMR::rowReordering -> bsa_rowReordering_gpu (src/BSMR.cpp:27-50,
+ * src/rowReordering.cu:1027-1095): dispersion scores, stable sort, BSA clustering with
+ * threshold alpha, stable sort by cluster, empty rows stripped.
+ * block_size == 0 -> calculateBlockSize() like BSMR::rowReordering does.                 */
+int bsmr_plan_row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flags);
+
+/* BSMR::colReordering(delta, matrix, reorderedRows) with a caller-supplied row order
+ * (src/BSMR.cpp:52-59; host pointer).                                                    */
+int bsmr_plan_set_row_order(bsmr_plan* plan, const uint32_t* reordered_rows, uint32_t count);
+
+/* BSMR::colReordering -> colReordering_cpu semantics, computed on the GPU
+ * (src/BSMR.cpp:52-81, src/colReordering.cu:274-404, 244-271), followed by the device
+ * format build that replaces RPHM::RPHM (src/BSMR.cpp:83-265).                           */
+int bsmr_plan_col_reorder(bsmr_plan* plan, float delta);
+
+/* One call = BSMR::BSMR(alpha, delta, matrix) + RPHM(matrix, bsmr).                       */
+int bsmr_plan_reorder(bsmr_plan* plan, float alpha, float delta, uint32_t block_size, uint32_t flags);
+
+/* Accessors of BSMR (include/BSMR.hpp:40-50).                                            */
+typedef enum {
+    BSMR_VEC_REORDERED_ROWS = 0,
+    BSMR_VEC_DENSE_COLS = 1,
+    BSMR_VEC_DENSE_COL_OFFSETS = 2,
+    BSMR_VEC_SPARSE_COLS = 3,
+    BSMR_VEC_SPARSE_COL_OFFSETS = 4,
+    BSMR_VEC_SPARSE_VALUE_OFFSETS = 5,
+    /* RPHM accessors (include/BSMR.hpp:91-103), reference layout, produced on demand */
+    BSMR_VEC_BLOCK_OFFSETS = 6,
+    BSMR_VEC_BLOCK_VALUES = 7,
+    BSMR_VEC_SPARSE_VALUES = 8,
+    BSMR_VEC_SPARSE_RELATIVE_ROWS = 9,
+    BSMR_VEC_SPARSE_COL_INDICES = 10,
+    /* diagnostics of the row reorder */
+    BSMR_VEC_DISPERSIONS = 11,
+    BSMR_VEC_CLUSTER_IDS = 12      /* cluster id per ORIGINAL row (0 = empty row) */
+} bsmr_vector_id;
+int bsmr_plan_vector_size(bsmr_plan* plan, int which, uint64_t* size);
+int bsmr_plan_vector_copy(bsmr_plan* plan, int which, uint32_t* host_out, uint64_t capacity);
+
+typedef struct {
+    uint32_t M, N, nnz;
+    uint32_t num_row_panels;      /* BSMR::numRowPanels()                                 */
+    int32_t  num_clusters;        /* BSMR::numClusters(), the reference's value (quirk kept) */
+    int32_t  num_clusters_true;   /* distinct clusters of non-empty rows                  */
+    uint32_t block_size;          /* clustering column-block size actually used           */
+    uint32_t num_dense_blocks;    /* 16x16 blocks in the dense part                       */
+    uint32_t num_dense_tiles;     /* tcgen05 work items (<= 8 blocks each)                */
+    uint64_t num_dense_values;    /* nnz computed by the dense-block kernel               */
+    uint64_t num_sparse_values;   /* nnz computed by the residual kernel                  */
+    float row_reordering_ms;      /* BSMR::rowReorderingTime()                            */
+    float col_reordering_ms;      /* BSMR::colReorderingTime()                            */
+    float format_build_ms;        /* RPHM::time()                                         */
+} bsmr_plan_info;
+int bsmr_plan_get_info(bsmr_plan* plan, bsmr_plan_info* info);
+
+/* ---- multi-GPU sharding (no counterpart in the reference, which is single-GPU) --------
+ * Restrict the plan to the rank-th of world nnz-balanced contiguous ranges of reordered
+ * row panels.  SDDMM calls then compute (and write) only the nnz of that range.
+ * first_panel / last_panel (exclusive) / shard_nnz are outputs (may be NULL).            */
+int bsmr_plan_set_shard(bsmr_plan* plan, uint32_t rank, uint32_t world,
+                        uint32_t* first_panel, uint32_t* end_panel, uint64_t* shard_nnz);
+
+/* ---- SDDMM ---------------------------------------------------------------------------
+ * sddmm_gpu(M, N, K, dA, dB, rphm, dP, logger) (include/sddmmKernel.cuh:25-30,
+ * src/sddmmKernel.cu:2540-2665 and sddmm_gpu_k32 :2667-2762): device pointers, caller-owned,
+ * P in CSR order (length nnz).  Runs `iterations` back-to-back iterations (dense-block kernel
+ * and residual kernel per iteration) and returns the average ms per iteration like
+ * Logger::sddmmTime_.  iterations <= 0 -> 1.  ms_per_iteration may be NULL (then nothing is
+ * synchronised and the call is fully asynchronous on the context's stream).               */
+#define BSMR_SDDMM_DEFAULT        0u
+#define BSMR_SDDMM_RESIDUAL_ONLY  1u   /* every nnz through the CUDA-core kernel (delta > 1) */
+#define BSMR_SDDMM_NO_REORDER     2u   /* ignore the plan's reorder: CSR order, residual kernel */
+int bsmr_sddmm(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP,
+               int iterations, uint32_t flags, float* ms_per_iteration);
+
+/* sddmm_gpu(matrixA, matrixB, rphm, matrixP, logger) host-data overload
+ * (include/sddmmKernel.cuh:19-23, src/sddmmKernel.cu:2518-2538): H2D A and B, zero P,
+ * compute, D2H P.  The copies are inside the call; ms_per_iteration covers kernels only,
+ * total_ms (may be NULL) covers copies + kernels.                                        */
+int bsmr_sddmm_host(bsmr_plan* plan, uint32_t K, const float* hA, const float* hB, float* hP,
+                    int iterations, uint32_t flags, float* ms_per_iteration, float* total_ms);
+
+/* Number of kernels of this library launched on the context so far (bench.py's gpu_launches). */
+int bsmr_ctx_launch_count(bsmr_ctx* ctx, uint64_t* count);
+
+/* evaluationReordering (src/BSMR.cpp:826-930): density statistics for the Logger.        */
+typedef struct {
+    int32_t num_dense_blocks;      /* Logger::numDenseBlock_      */
+    float   average_density;       /* Logger::averageDensity_     */
+    int32_t num_dense_thread_blocks;
+    int32_t num_sparse_thread_blocks;
+    int32_t num_dense_data;        /* Logger::numDenseData_       */
+    int32_t num_sparse_data;       /* Logger::numSparseData_      */
+    int32_t original_num_dense_blocks;
+    float   original_average_density;
+} bsmr_reorder_stats;
+int bsmr_plan_evaluate(bsmr_plan* plan, float delta, bsmr_reorder_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSMR_B200_H */

@@ -1,0 +1,254 @@
+"""GPU parity tests (run on a B200 with `-m gpu`): the CUDA product, called through its C ABI,
+against the oracle (oracle/bsmr_oracle.c) and -- where the prebuilt oracle/_ref library travelled
+with the snapshot -- against the reference's own GPU code on the same inputs.
+
+Bars: bit-exact for every integer result (row permutation in reference_compat mode, the five
+column-reorder vectors, the RPHM index tables); SDDMM values within the reference's own
+tolerance (include/checkData.hpp:21-30: |a-b| < 1e-5 or |a-b| / max(|a|,|b|,1e-3) < 1e-3).
+"""
+import numpy as np
+import pytest
+
+from cases import small_cases
+
+pytestmark = pytest.mark.gpu
+
+COL_VECS = ["dense_cols", "dense_col_offsets", "sparse_cols", "sparse_col_offsets", "sparse_value_offsets"]
+DELTAS = [0.0, 0.1, 0.3, 0.5, 0.9, 1.1]
+
+
+def nonempty_rows(ro):
+    return np.nonzero(np.diff(ro.astype(np.int64)))[0].astype(np.uint32)
+
+
+def torch_dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------------------------ a8 / a9
+@pytest.mark.parametrize("delta", DELTAS)
+def test_col_reorder_bit_exact_vs_oracle(pkg, ctx, oracle, delta):
+    for name, M, N, ro, ci in small_cases(pkg):
+        rows = nonempty_rows(ro)
+        rng = np.random.default_rng(5)
+        rows = rows[rng.permutation(len(rows))]          # arbitrary caller-supplied order
+        want = oracle.col_reordering(M, N, ro, ci, rows, delta, with_rphm=True)
+        plan = pkg.Plan(ctx, M, N, ro, ci)
+        plan.set_row_order(rows)
+        plan.col_reorder(delta)
+        for k in COL_VECS:
+            got = plan.vector(k)
+            assert np.array_equal(got, want[k]), "%s delta=%s %s differs" % (name, delta, k)
+        for k in ["block_offsets", "block_values", "sparse_values", "sparse_relative_rows", "sparse_col_indices"]:
+            got = plan.vector(k)
+            assert np.array_equal(got, want[k]), "%s delta=%s RPHM %s differs" % (name, delta, k)
+        info = plan.info()
+        assert info["num_row_panels"] == want["num_row_panels"]
+        assert info["num_dense_values"] + info["num_sparse_values"] == len(ci)
+        plan.close()
+
+
+def test_col_reorder_unsorted_columns(pkg, ctx, oracle):
+    """The .mtx loader keeps file order inside a row (src/Matrix.cpp:467-470): columns need not be sorted."""
+    M, N, ro, ci = pkg.synth.block_structured(200, 300, seed=3)
+    rng = np.random.default_rng(9)
+    ci = ci.copy()
+    for r in range(M):
+        seg = ci[ro[r]:ro[r + 1]]
+        ci[ro[r]:ro[r + 1]] = seg[rng.permutation(len(seg))]
+    rows = nonempty_rows(ro)
+    want = oracle.col_reordering(M, N, ro, ci, rows, 0.3, with_rphm=True)
+    plan = pkg.Plan(ctx, M, N, ro, ci)
+    plan.set_row_order(rows)
+    plan.col_reorder(0.3)
+    for k in COL_VECS + ["block_values", "sparse_values", "sparse_relative_rows", "sparse_col_indices"]:
+        assert np.array_equal(plan.vector(k), want[k]), k
+
+
+# ------------------------------------------------------------------------------------ a3-a6
+@pytest.mark.parametrize("alpha", [0.1, 0.3, 0.5, 0.7, 0.9])
+def test_row_reorder_bit_exact_vs_oracle(pkg, ctx, oracle, alpha):
+    for name, M, N, ro, ci in small_cases(pkg):
+        for block_size in (16, 37):
+            want, want_compat, want_true = oracle.row_reordering(M, N, ro, ci, alpha, block_size)
+            plan = pkg.Plan(ctx, M, N, ro, ci)
+            plan.row_reorder(alpha, block_size=block_size, flags=pkg.ROW_REFERENCE_COMPAT)
+            got = plan.vector("reordered_rows")
+            info = plan.info()
+            assert np.array_equal(got, want), "%s alpha=%s bs=%d permutation differs" % (name, alpha, block_size)
+            assert info["num_clusters"] == want_compat, (name, alpha, block_size)
+            assert info["num_clusters_true"] == want_true, (name, alpha, block_size)
+            _, disp = oracle.dispersion(M, N, ro, ci, block_size)
+            assert np.array_equal(plan.vector("dispersions"), disp)
+            plan.close()
+
+
+def test_row_reorder_exact_reduce_mode(pkg, ctx, oracle):
+    name, M, N, ro, ci = [c for c in small_cases(pkg) if c[0] == "wide_33x9000"][0]
+    want, _, want_true = oracle.row_reordering(M, N, ro, ci, 0.3, 16, exact=True)
+    plan = pkg.Plan(ctx, M, N, ro, ci)
+    plan.row_reorder(0.3, block_size=16, flags=pkg.ROW_EXACT_REDUCE)
+    assert np.array_equal(plan.vector("reordered_rows"), want)
+    assert plan.info()["num_clusters_true"] == want_true
+
+
+def test_row_reorder_identity(pkg, ctx):
+    M, N, ro, ci = pkg.synth.block_structured(300, 520, seed=7)
+    plan = pkg.Plan(ctx, M, N, ro, ci)
+    plan.row_reorder(0.3, flags=pkg.ROW_IDENTITY)
+    assert np.array_equal(plan.vector("reordered_rows"), nonempty_rows(ro))
+
+
+def test_block_size_formula(pkg, ctx, oracle):
+    for M, N, free in [(1500, 12419, 170 << 30), (1 << 20, 1 << 20, 170 << 30), (4096, 4096, 8 << 30), (100000, 100000, 20 << 30)]:
+        assert ctx.calculate_block_size(M, N, free) == oracle.calculate_block_size(M, N, free)
+
+
+def test_row_reorder_vs_reference_gpu(pkg, ctx, ref):
+    """The reference's own bsa_rowReordering_gpu (device-side launches, mutexes) on the same input."""
+    for name, M, N, ro, ci in small_cases(pkg):
+        if M < 2:
+            continue
+        for alpha in (0.3, 0.7):
+            want, want_clusters, _ = ref.row_reordering_gpu(M, N, ro, ci, alpha, 16)
+            plan = pkg.Plan(ctx, M, N, ro, ci)
+            plan.row_reorder(alpha, block_size=16)
+            assert np.array_equal(plan.vector("reordered_rows"), want), (name, alpha)
+            assert plan.info()["num_clusters"] == want_clusters, (name, alpha)
+            plan.close()
+
+
+# ------------------------------------------------------------------------------------ a10-a14
+def run_sddmm(pkg, ctx, M, N, ro, ci, K, alpha, delta, flags=0, block_size=16, row_flags=0):
+    import torch
+    A, B = pkg.synth.make_ab(M, N, K)
+    plan = pkg.Plan(ctx, M, N, ro, ci)
+    if not (flags & pkg.SDDMM_NO_REORDER):
+        plan.reorder(alpha, delta, block_size=block_size, flags=row_flags)
+    dA, dB = torch_dev(A), torch_dev(B)
+    dP = torch.full((len(ci),), -7.0, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    plan.sddmm(K, dA, dB, dP, iterations=1, flags=flags)
+    torch.cuda.synchronize()
+    return plan, A, B, dP.cpu().numpy()
+
+
+@pytest.mark.parametrize("K", [32, 64, 128, 256, 96, 40, 33, 7])
+def test_sddmm_csr_order_residual_kernel(pkg, ctx, oracle, K):
+    for name, M, N, ro, ci in small_cases(pkg):
+        plan, A, B, got = run_sddmm(pkg, ctx, M, N, ro, ci, K, 0.3, 0.3, flags=pkg.SDDMM_NO_REORDER)
+        want = oracle.sddmm_cpu(M, N, K, A, B, ro, ci)
+        assert oracle.check_data(want, got) == 0, (name, K)
+        # fp32 FMA path: far inside the tolerance
+        assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-3)) < 2e-5, (name, K)
+
+
+@pytest.mark.parametrize("K", [32, 128, 40])
+def test_sddmm_all_residual_after_reorder(pkg, ctx, oracle, K):
+    """delta > 1: nothing is dense, every nnz goes through the residual kernel in RPHM order."""
+    for name, M, N, ro, ci in small_cases(pkg):
+        plan, A, B, got = run_sddmm(pkg, ctx, M, N, ro, ci, K, 0.3, 1.1)
+        assert plan.info()["num_dense_tiles"] == 0
+        want = oracle.sddmm_cpu(M, N, K, A, B, ro, ci)
+        assert oracle.check_data(want, got) == 0, (name, K)
+
+
+@pytest.mark.parametrize("K,delta", [(32, 0.3), (64, 0.1), (128, 0.3), (256, 0.0), (128, 0.0), (96, 0.1), (40, 0.1)])
+def test_sddmm_dense_plus_residual(pkg, ctx, oracle, K, delta):
+    """Full hot path: tcgen05 dense-block kernel + residual kernel, TF32 x TF32 -> fp32 on the dense part."""
+    worst = 0.0
+    for name, M, N, ro, ci in small_cases(pkg):
+        plan, A, B, got = run_sddmm(pkg, ctx, M, N, ro, ci, K, 0.3, delta)
+        want = oracle.sddmm_cpu(M, N, K, A, B, ro, ci)
+        bad = oracle.check_data(want, got)
+        rel = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-3)))
+        worst = max(worst, rel)
+        assert bad == 0, "%s K=%d delta=%s: %d mismatches, max rel %.3e, info %s" % (name, K, delta, bad, rel, plan.info())
+        assert not np.any(got == -7.0), "some nnz were never written"
+    print("dense+residual K=%d delta=%s worst rel err %.3e" % (K, delta, worst))
+
+
+def test_sddmm_host_overload(pkg, ctx, oracle):
+    M, N, ro, ci = pkg.synth.block_structured(300, 520, seed=7)
+    K = 64
+    A, B = pkg.synth.make_ab(M, N, K)
+    plan = pkg.Plan(ctx, M, N, ro, ci)
+    plan.reorder(0.3, 0.3, block_size=16)
+    P, ms, total = plan.sddmm_host(K, A, B, iterations=3)
+    assert total >= ms > 0
+    assert oracle.check_data(oracle.sddmm_cpu(M, N, K, A, B, ro, ci), P) == 0
+
+
+def test_sddmm_linearity_and_idempotence(pkg, ctx):
+    """Size-independent properties: SDDMM is linear in A and repeated calls give identical bits."""
+    import torch
+    M, N, ro, ci = pkg.synth.block_structured(1000, 2000, seed=11, groups=12, cols_per_group=64)
+    K = 128
+    A, B = pkg.synth.make_ab(M, N, K)
+    plan = pkg.Plan(ctx, M, N, ro, ci)
+    plan.reorder(0.3, 1.1, block_size=16)       # fp32 path -> exact scaling by powers of two
+    dA, dB = torch_dev(A), torch_dev(B)
+    p1 = torch.zeros(len(ci), device="cuda")
+    p2 = torch.zeros(len(ci), device="cuda")
+    plan.sddmm(K, dA, dB, p1)
+    plan.sddmm(K, dA * 2.0, dB, p2)
+    torch.cuda.synchronize()
+    assert torch.equal(p1 * 2.0, p2)
+    p3 = torch.zeros(len(ci), device="cuda")
+    plan.sddmm(K, dA, dB, p3)
+    torch.cuda.synchronize()
+    assert torch.equal(p1, p3)
+
+
+def test_full_pipeline_vs_reference_gpu(pkg, ctx, ref, oracle):
+    """Reference binary path (bsa_rowReordering_gpu -> colReordering_cpu -> RPHM -> sddmm_gpu) vs ours."""
+    M, N, ro, ci = pkg.synth.block_structured(1000, 2000, seed=11, groups=12, cols_per_group=64)
+    for K in (32, 128):
+        A, B = pkg.synth.make_ab(M, N, K)
+        want = ref.bsmr_sddmm_gpu(M, N, K, ro, ci, A, B, 0.3, 0.3, 16, iters=2)
+        plan, _, _, got = run_sddmm(pkg, ctx, M, N, ro, ci, K, 0.3, 0.3)
+        for k in ["reordered_rows"] + COL_VECS:
+            assert np.array_equal(plan.vector(k), want[k]), (K, k)
+        assert plan.info()["num_clusters"] == want["num_clusters"]
+        assert oracle.check_data(want["P"], got) == 0
+        assert ref.check_data(want["P"], got) == 0
+
+
+def test_errors_are_reported_not_swallowed(pkg, ctx):
+    M, N, ro, ci = pkg.synth.random_uniform(64, 96, 900, seed=1)
+    plan = pkg.Plan(ctx, M, N, ro, ci)
+    with pytest.raises(pkg.BsmrError):
+        plan.col_reorder(0.3)                      # no row order yet
+    with pytest.raises(pkg.BsmrError):
+        plan.sddmm(32, 1, 1, 1)                    # no reorder yet
+    with pytest.raises(pkg.BsmrError):
+        pkg.Plan(ctx, M, N, ro, ci[:-1])           # row_offsets[M] != nnz
+
+
+def test_shards_partition_the_nnz(pkg, ctx, oracle):
+    import torch
+    M, N, ro, ci = pkg.synth.block_structured(1000, 2000, seed=11, groups=12, cols_per_group=64)
+    K = 64
+    A, B = pkg.synth.make_ab(M, N, K)
+    want = oracle.sddmm_cpu(M, N, K, A, B, ro, ci)
+    dA, dB = torch_dev(A), torch_dev(B)
+    for world in (2, 3, 8):
+        plan = pkg.Plan(ctx, M, N, ro, ci)
+        plan.reorder(0.3, 0.3, block_size=16)
+        acc = torch.zeros(len(ci), device="cuda")
+        covered = torch.zeros(len(ci), device="cuda")
+        total = 0
+        for rank in range(world):
+            a, b, n = plan.set_shard(rank, world)
+            total += n
+            p = torch.full((len(ci),), float("nan"), device="cuda")
+            plan.sddmm(K, dA, dB, p)
+            torch.cuda.synchronize()
+            mask = ~torch.isnan(p)
+            assert int(mask.sum()) == n
+            covered += mask.float()
+            acc += torch.nan_to_num(p)
+        assert total == len(ci)
+        assert bool((covered == 1).all())
+        assert oracle.check_data(want, acc.cpu().numpy()) == 0

@@ -1,0 +1,140 @@
+"""CPU: the oracle (oracle/bsmr_oracle.c) against the reference's own CPU code compiled unmodified
+(oracle/_ref/libbsmr_ref.so, only where it was built) and against the committed golden fixtures
+that were generated from that library (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from cases import small_cases
+
+COL_VECS = ["dense_cols", "dense_col_offsets", "sparse_cols", "sparse_col_offsets", "sparse_value_offsets"]
+
+
+def nonempty_rows(ro):
+    return np.nonzero(np.diff(ro.astype(np.int64)))[0].astype(np.uint32)
+
+
+def test_make_data_matches_reference(oracle, ref):
+    assert np.array_equal(oracle.make_data(5000), ref.make_data(50, 100))
+    # column-major B draws the same stream (a fresh default-seeded engine per call, src/Matrix.cpp:131)
+    assert np.array_equal(oracle.make_data(640), ref.make_data(64, 10, col_major=True))
+
+
+def test_sddmm_cpu_matches_reference(pkg, oracle, ref):
+    for name, M, N, ro, ci in small_cases(pkg):
+        for K in (32, 40, 128):
+            A, B = pkg.synth.make_ab(M, N, K)
+            assert np.array_equal(oracle.sddmm_cpu(M, N, K, A, B, ro, ci), ref.sddmm_cpu(M, N, K, A, B, ro, ci)), (name, K)
+
+
+@pytest.mark.parametrize("delta", [0.0, 0.1, 0.3, 0.5, 0.9, 1.1])
+def test_col_reordering_matches_reference(pkg, oracle, ref, delta):
+    for name, M, N, ro, ci in small_cases(pkg):
+        rows = nonempty_rows(ro)
+        rows = rows[np.random.default_rng(5).permutation(len(rows))]
+        a = oracle.col_reordering(M, N, ro, ci, rows, delta)
+        b = ref.col_reordering_cpu(M, N, ro, ci, rows, delta)
+        for k in COL_VECS:
+            assert np.array_equal(a[k], b[k]), (name, delta, k)
+
+
+def test_check_data_matches_reference(oracle, ref):
+    rng = np.random.default_rng(0)
+    a = (rng.random(20000, dtype=np.float32) * 100).astype(np.float32)
+    b = a * (1 + rng.normal(0, 7e-4, size=a.shape)).astype(np.float32)
+    b[:100] = a[:100] + 5e-6
+    a[100:200] = 0
+    b[100:200] = rng.normal(0, 1e-5, 100).astype(np.float32)
+    assert oracle.check_data(a, b) == ref.check_data(a, b)
+    assert 0 < oracle.check_data(a, b) < len(a)
+
+
+def test_mtx_loader_matches_reference(pkg, oracle, ref, tmp_path):
+    M, N, ro, ci = pkg.synth.random_uniform(50, 70, 600, seed=8)
+    vals = np.random.default_rng(1).random(len(ci)).astype(np.float32)
+    p = str(tmp_path / "m.mtx")
+    pkg.synth.write_mtx(p, M, N, ro, ci, values=vals, shuffle_seed=3)   # shuffled lines: row-stable sort only
+    a = oracle.load_mtx(p)
+    b = ref.load_matrix_file(p)
+    assert a is not None and b is not None
+    assert a[0] == b[0] and a[1] == b[1]
+    for x, y in zip(a[2:], b[2:]):
+        assert np.array_equal(x, y)
+    # in-row column order is file order, not sorted
+    assert not all(np.all(np.diff(a[3][a[2][r]:a[2][r + 1]].astype(np.int64)) > 0) for r in range(M))
+
+
+def test_mtx_loader_rejections(oracle, ref, tmp_path):
+    cases = {
+        "dup.mtx": "%%MatrixMarket\n3 3 3\n1 1 1\n2 2 1\n1 1 2\n",
+        "range.mtx": "%%MatrixMarket\n3 3 2\n1 1 1\n4 2 1\n",
+        "few.mtx": "%%MatrixMarket\n3 3 3\n1 1 1\n2 2 1\n",
+        "many.mtx": "%%MatrixMarket\n3 3 2\n1 1 1\n2 2 1\n3 3 1\n",
+        "one.mtx": "%%MatrixMarket\n3 3 1\n1 1 1\n",
+        "ok_novalue.mtx": "%%MatrixMarket\n% comment\n3 4 3\n3 1\n1 4\n\n2 2\n",
+    }
+    for name, text in cases.items():
+        p = str(tmp_path / name)
+        open(p, "w").write(text)
+        a, b = oracle.load_mtx(p), ref.load_matrix_file(p)
+        assert (a is None) == (b is None), name
+        if a is not None:
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y), name
+
+
+def test_golden_fixtures(pkg, oracle, golden_dir):
+    """Fixtures produced by the reference library (tests/golden/make_golden.py); they travel to the GPU box."""
+    files = sorted(f for f in os.listdir(golden_dir) if f.endswith(".npz"))
+    assert files, "no golden fixtures committed"
+    for f in files:
+        g = np.load(os.path.join(golden_dir, f))
+        M, N, K = int(g["M"]), int(g["N"]), int(g["K"])
+        ro, ci = g["row_offsets"], g["col_indices"]
+        A, B = pkg.synth.make_ab(M, N, K)
+        assert np.array_equal(oracle.sddmm_cpu(M, N, K, A, B, ro, ci), g["P_ref_cpu"]), f
+        rows = g["rows"]
+        for delta in (0.1, 0.3):
+            got = oracle.col_reordering(M, N, ro, ci, rows, delta)
+            for k in COL_VECS:
+                assert np.array_equal(got[k], g["d%02d_%s" % (int(delta * 10), k)]), (f, delta, k)
+        if "perm_ref_gpu" in g.files:   # row permutation produced by the reference's GPU code on a B200
+            perm, compat, _ = oracle.row_reordering(M, N, ro, ci, float(g["alpha"]), int(g["block_size"]))
+            assert np.array_equal(perm, g["perm_ref_gpu"]), f
+            assert compat == int(g["clusters_ref_gpu"]), f
+
+
+def test_similarity_lossy_reduction_drops_warps(oracle):
+    """7 reference warps (nb = 777 like nips): blocks owned by warps 2, 5 and 6 are ignored."""
+    nb = 777
+    bd = oracle.clustering_blockdim(nb)
+    assert bd == 224
+    rep = np.zeros(nb, dtype=np.uint32)
+    cmp_ = np.zeros(nb, dtype=np.uint32)
+    rep[10] = 3
+    cmp_[10] = 3
+    cmp_[70] = 9          # thread 70 -> warp 2 -> dropped
+    assert oracle.similarity(rep, cmp_, bd) == 1.0
+    assert oracle.similarity(rep, cmp_, bd, exact=True) < 1.0
+    cmp2 = np.zeros(nb, dtype=np.uint32)
+    cmp2[70] = 5          # only dropped blocks: lossy norm is 0 -> similarity 0
+    assert oracle.similarity(rep, cmp2, bd) == 0.0
+
+
+def test_row_reordering_invariants(pkg, oracle):
+    """check_rowReordering (src/BSMR.cpp:444-486): no duplicates, no empty rows, nothing missing."""
+    for name, M, N, ro, ci in small_cases(pkg):
+        for alpha in (0.1, 0.5, 0.9):
+            perm, compat, true = oracle.row_reordering(M, N, ro, ci, alpha, 16)
+            assert sorted(perm.tolist()) == nonempty_rows(ro).tolist(), (name, alpha)
+            assert true >= 1
+
+
+def test_block_size_and_blockdim_rules(oracle):
+    assert oracle.calculate_block_size(1500, 12419, 170 << 30) == 16
+    assert oracle.calculate_block_size(1 << 20, 1 << 20, 170 << 30) == 171
+    assert oracle.clustering_blockdim(10) == 32
+    assert oracle.clustering_blockdim(256) == 64
+    assert oracle.clustering_blockdim(777) == 224
+    assert oracle.clustering_blockdim(6133) == 1024
