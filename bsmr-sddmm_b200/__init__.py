@@ -95,13 +95,14 @@ def lib():
         L.bsmr_plan_set_shard.argtypes = [vp, C.c_uint32, C.c_uint32, u32p, u32p, C.POINTER(C.c_uint64)]
         L.bsmr_sddmm.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_int, C.c_uint32, f32p]
         L.bsmr_sddmm_host.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_int, C.c_uint32, f32p, f32p]
+        L.bsmr_sddmm_profile.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_uint32, f32p, f32p]
         L.bsmr_plan_evaluate.argtypes = [vp, C.c_float, C.POINTER(ReorderStats)]
         L.bsmr_debug_set_dense_smem_dump.argtypes = [vp]
         for name in ("bsmr_ctx_create", "bsmr_ctx_destroy", "bsmr_ctx_synchronize", "bsmr_ctx_device_name",
                      "bsmr_ctx_launch_count", "bsmr_calculate_block_size", "bsmr_plan_create", "bsmr_plan_destroy",
                      "bsmr_plan_row_reorder", "bsmr_plan_set_row_order", "bsmr_plan_col_reorder", "bsmr_plan_reorder",
                      "bsmr_plan_vector_size", "bsmr_plan_vector_copy", "bsmr_plan_get_info", "bsmr_plan_set_shard",
-                     "bsmr_sddmm", "bsmr_sddmm_host", "bsmr_plan_evaluate"):
+                     "bsmr_sddmm", "bsmr_sddmm_host", "bsmr_sddmm_profile", "bsmr_plan_evaluate"):
             getattr(L, name).restype = C.c_int
         _lib = L
     return _lib
@@ -226,6 +227,12 @@ class Plan:
         _check(lib().bsmr_sddmm(self._h, K, _ptr(dA), _ptr(dB), _ptr(dP), iterations, flags,
                                 C.byref(ms) if timed else None))
         return ms.value
+
+    def sddmm_profile(self, K, dA, dB, dP, flags=SDDMM_DEFAULT):
+        """One pass, the two kernels timed separately: (dense_ms, residual_ms)."""
+        a, b = C.c_float(0), C.c_float(0)
+        _check(lib().bsmr_sddmm_profile(self._h, K, _ptr(dA), _ptr(dB), _ptr(dP), flags, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def sddmm_host(self, K, hA, hB, hP=None, iterations=1, flags=SDDMM_DEFAULT):
         """Host buffers (numpy or pinned torch tensors); H2D/D2H inside.  Returns (P, kernel_ms, total_ms)."""

@@ -491,6 +491,42 @@ int bsmr_sddmm(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, fl
     return BSMR_OK;
 }
 
+int bsmr_sddmm_profile(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP, uint32_t flags,
+                       float* dense_ms, float* residual_ms) {
+    if (!plan || !dA || !dB || (plan->nnz && !dP) || K == 0) return BSMR_ERR_INVALID_ARGUMENT;
+    if (!plan->have_format || (flags & BSMR_SDDMM_NO_REORDER)) {
+        set_error("bsmr_sddmm_profile: needs a reordered plan");
+        return BSMR_ERR_BAD_STATE;
+    }
+    bsmr_ctx* ctx = plan->ctx;
+    BSMR_CUDA_OK(cudaSetDevice(ctx->device));
+    cudaEvent_t mid;
+    BSMR_CUDA_OK(cudaEventCreate(&mid));
+    int s = BSMR_OK;
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    if (plan->shard_tile_end > plan->shard_tile_begin)
+        s = launch_dense(plan, K, dA, dB, dP, plan->shard_tile_begin, plan->shard_tile_end);
+    cudaEventRecord(mid, ctx->stream);
+    if (s == BSMR_OK)
+        s = launch_residual(ctx, K, dA, dB, dP, plan->res_row.ptr, plan->res_col.ptr, plan->res_out.ptr,
+                            plan->shard_res_begin, plan->shard_res_end);
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    cudaError_t e = cudaEventSynchronize(ctx->ev1);
+    float a = 0.f, b = 0.f;
+    if (e == cudaSuccess) {
+        cudaEventElapsedTime(&a, ctx->ev0, mid);
+        cudaEventElapsedTime(&b, mid, ctx->ev1);
+    }
+    cudaEventDestroy(mid);
+    if (s == BSMR_OK && e != cudaSuccess) {
+        set_error("bsmr_sddmm_profile: %s", cudaGetErrorString(e));
+        s = BSMR_ERR_CUDA;
+    }
+    if (dense_ms) *dense_ms = a;
+    if (residual_ms) *residual_ms = b;
+    return s;
+}
+
 int bsmr_sddmm_host(bsmr_plan* plan, uint32_t K, const float* hA, const float* hB, float* hP, int iterations,
                     uint32_t flags, float* ms_per_iteration, float* total_ms) {
     if (!plan || !hA || !hB || (plan->nnz && !hP) || K == 0) {

@@ -21,8 +21,14 @@
 // swizzled smem tile; 32 requests fill the B-column tile, 4 the A-row tile.  Sentinel columns
 // (index N, the reference's padding) and rows past the last panel row are out of bounds for
 // the tensor map and arrive as zeros.
-// Warp roles (6 warps): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue
-// (tcgen05.ld of the warp's 32 TMEM lanes x 16 columns, mask + scatter P[idx] = acc).
+// Precision: tcgen05 kind::tf32 reads the fp32 bit patterns and IGNORES the low 13 mantissa
+// bits (truncation; measured on B200: mean signed error -6.5e-4 on all-positive inputs).  The
+// reference rounds to nearest (wmma::__float_to_tf32 = cvt.rna, src/sddmmKernel.cu:317-322), so
+// four converter warps round every landed stage in place with cvt.rna.tf32.f32 before the MMA
+// warp may read it (generic-proxy writes -> fence.proxy.async -> mbarrier).
+// Warp roles (10 warps): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue
+// (tcgen05.ld of the warp's 32 TMEM lanes x 16 columns, mask + scatter P[idx] = acc),
+// 6..9 = TF32 round-to-nearest converters.
 // Two TMEM accumulators (2 x 16 columns) let the epilogue of tile i overlap the MMAs of tile
 // i+1; a 5-stage smem ring (18 KB / stage) keeps ~90 KB of loads in flight per CTA.
 #include <cuda.h>
@@ -38,13 +44,15 @@ constexpr int kStages = 5;
 constexpr int kChunk = 32;                         // floats of K per stage (128 bytes)
 constexpr int kBTileBytes = kTileCols * kChunk * 4;   // 16384
 constexpr int kATileBytes = kPanel * kChunk * 4;      // 2048
-constexpr int kDenseThreads = 192;
+constexpr int kDenseThreads = 320;
+constexpr int kConvWarp0 = 6;                     // first converter warp
 constexpr int kTmemCols = 32;                      // 2 accumulators x 16 fp32 columns
 constexpr uint32_t kSpinLimit = 1u << 28;
 
 struct __align__(16) DenseSmemTail {
-    uint64_t full[kStages];
-    uint64_t empty[kStages];
+    uint64_t full[kStages];    // TMA bytes landed
+    uint64_t ready[kStages];   // operands rounded to TF32 (4 converter warps arrived)
+    uint64_t empty[kStages];   // MMAs that read the stage have completed
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
     uint32_t tmem_base;
@@ -98,6 +106,12 @@ __device__ __forceinline__ void tma_row(const CUtensorMap* map, uint64_t* bar, v
         " [%0], [%1, {%2, %3}], [%4];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
         : "memory");
+}
+
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -166,6 +180,7 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&tail->full[s], 1);
+            mbar_init(&tail->ready[s], 4);
             mbar_init(&tail->empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -241,7 +256,7 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * kPanel;
             for (uint32_t kc = 0; kc < num_chunks; ++kc) {
-                mbar_wait(&tail->full[stage], phase, p.error_flag, 3);
+                mbar_wait(&tail->ready[stage], phase, p.error_flag, 3);
                 tc_fence_after();
                 if (p.debug_smem && t == p.tile_begin && kc == 0 && blockIdx.x == 0) {
                     // probe: raw image of stage 0 (B-column tile then A-row tile)
@@ -263,6 +278,39 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     if (kc + 1 == num_chunks) umma_commit(&tail->tmem_full[acc]);
                 }
                 __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= kConvWarp0) {
+        // ================= TF32 converters (warps 6..9) =================
+        // cvt.rna.tf32.f32 on every element of the landed stage, in place; element-wise, so the
+        // 128-byte swizzle does not matter.  Thread i owns float4 #i, #i+128, ... of the B-column
+        // tile (8 of them) and float4 #i of the A-row tile.
+        const uint32_t ci = threadIdx.x - kConvWarp0 * 32;   // 0..127
+        uint32_t stage = 0, phase = 0;
+        for (uint32_t t = p.tile_begin + blockIdx.x; t < p.tile_end; t += gridDim.x) {
+            for (uint32_t kc = 0; kc < num_chunks; ++kc) {
+                mbar_wait(&tail->full[stage], phase, p.error_flag, 5);
+                float4* bt = reinterpret_cast<float4*>(b_tiles + (size_t)stage * kBTileBytes);
+                float4* at = reinterpret_cast<float4*>(a_tiles + (size_t)stage * kATileBytes);
+                float4 v[9];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = bt[ci + 128 * j];
+                v[8] = at[ci];
+#pragma unroll
+                for (int j = 0; j < 9; ++j) {
+                    v[j].x = rna_tf32(v[j].x);
+                    v[j].y = rna_tf32(v[j].y);
+                    v[j].z = rna_tf32(v[j].z);
+                    v[j].w = rna_tf32(v[j].w);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bt[ci + 128 * j] = v[j];
+                at[ci] = v[8];
+                // make the generic-proxy stores visible to the tensor core (async proxy) before signalling
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tail->ready[stage]);
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -384,7 +432,7 @@ int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, 
     p.use_gather4 = !(mode && mode[0] == 'r');
 
     const uint32_t tiles = tile_end - tile_begin;
-    const uint32_t max_ctas = static_cast<uint32_t>(ctx->sm_count) * 2;  // 2 CTAs (2 x 97 KB smem, 2 x 32 TMEM columns) per SM
+    const uint32_t max_ctas = static_cast<uint32_t>(ctx->sm_count) * 2;  // 2 CTAs (2 x 94 KB smem, 2 x 32 TMEM columns) per SM
     const uint32_t grid = tiles < max_ctas ? tiles : max_ctas;
     dense_sddmm_kernel<<<grid, kDenseThreads, kDenseSmemBytes, ctx->stream>>>(map_a, map_b, p);
     ctx->launches++;

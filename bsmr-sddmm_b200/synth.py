@@ -138,6 +138,33 @@ def write_mtx(path, M, N, row_offsets, col_indices, values=None, shuffle_seed=No
                 f.write("%d %d %.9g\n" % (rows[i] + 1, cols[i] + 1, values[i]))
 
 
+def read_mtx(path):
+    """MatrixMarket coordinate file -> CSR pattern with the reference loader's ordering
+    (1-based, '%' comment lines, stable sort by row only: src/Matrix.cpp:399-480)."""
+    rows, cols = [], []
+    header = None
+    with open(path) as f:
+        for line in f:
+            if header is None:
+                if line.startswith("%"):
+                    continue
+                header = [int(float(x)) for x in line.split()[:3]]
+                continue
+            w = line.split()
+            if len(w) >= 2:
+                rows.append(int(w[0]) - 1)
+                cols.append(int(w[1]) - 1)
+    M, N, nnz = header
+    rows = np.asarray(rows, dtype=np.int64)
+    cols = np.asarray(cols, dtype=np.uint32)
+    if len(rows) != nnz:
+        raise ValueError("%s: %d entries, header says %d" % (path, len(rows), nnz))
+    order = np.argsort(rows, kind="stable")
+    ro = np.zeros(M + 1, dtype=np.int64)
+    np.add.at(ro, rows + 1, 1)
+    return M, N, np.cumsum(ro).astype(np.uint32), cols[order]
+
+
 def algorithmic_bytes(M, N, K, row_offsets, col_indices):
     """Compulsory traffic of one SDDMM: 4K(M_nz + N_nz) + 8 nnz + 4(M + 1)."""
     nnz = len(col_indices)

@@ -163,6 +163,11 @@ int bsmr_sddmm(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, fl
 int bsmr_sddmm_host(bsmr_plan* plan, uint32_t K, const float* hA, const float* hB, float* hP,
                     int iterations, uint32_t flags, float* ms_per_iteration, float* total_ms);
 
+/* One pass with the two kernels timed separately (CUDA events on the context's stream):
+ * what bench.py's roofline block reports per kernel.  Either output may be NULL.          */
+int bsmr_sddmm_profile(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP,
+                       uint32_t flags, float* dense_ms, float* residual_ms);
+
 /* Number of kernels of this library launched on the context so far (bench.py's gpu_launches). */
 int bsmr_ctx_launch_count(bsmr_ctx* ctx, uint64_t* count);
 

@@ -127,6 +127,11 @@ def main():
             for r in range(min(16, len(rrows))):
                 exp_a[r] = A[rrows[r], :32]
 
+            def rna(x):   # cvt.rna.tf32.f32: round to nearest (ties away) on the low 13 mantissa bits
+                b = x.view(np.uint32).astype(np.uint64)
+                return ((b + 0x1000) & 0xFFFFE000).astype(np.uint32).view(np.float32)
+            exp_a, exp_b = rna(exp_a), rna(exp_b)
+
             def swz(x):
                 out = np.zeros_like(x)
                 for r in range(x.shape[0]):
@@ -145,7 +150,7 @@ def main():
             traceback.print_exc()
             break
 
-    if os.path.exists(REF_SO):
+    if os.path.exists(REF_SO) and "--with-ref" in sys.argv:
         section("reference GPU pipeline on the same input (oracle/_ref)")
         try:
             ref = Ref()
