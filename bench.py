@@ -176,7 +176,11 @@ def main():
     M, N, ro, ci, source = load_workload(pkg, world)
     nnz = len(ci)
     A, B = pkg.synth.make_ab(M, N, K)
-    stream = torch.cuda.current_stream()
+    # an explicit (non-default) stream shared by torch and the library: the CUDA events below must be
+    # recorded on the stream the kernels are launched on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = pkg.Context(local_rank, stream.cuda_stream)
     plan = pkg.Plan(ctx, M, N, ro, ci)
     t0 = time.perf_counter()

@@ -571,6 +571,81 @@ int bsmr_sddmm_host(bsmr_plan* plan, uint32_t K, const float* hA, const float* h
     return s;
 }
 
+}  // extern "C"
+
+namespace bsmr {
+// evaluationReordering + calculateNumDenseBlocksAndAverageDensityInOriginalMatrix
+// (src/BSMR.cpp:826-930, 955-994).  Host-side statistics for the Logger; float sums are taken in
+// the reference's order (panel, then block) so the printed averages agree to the last digit.
+int evaluate_reordering(bsmr_plan* p, float delta, bsmr_reorder_stats* st) {
+    std::memset(st, 0, sizeof(*st));
+    bsmr_ctx* ctx = p->ctx;
+    const uint32_t panels = p->num_row_panels;
+    // nnz of every dense 16x16 block, in (panel, block) order, from the scatter tables
+    std::vector<uint32_t> bv;
+    BSMR_TRY(rphm_reference_layout(p, BSMR_VEC_BLOCK_VALUES, bv));
+    int num_dense_blocks = 0, dense_tb = 0, sparse_tb = 0;
+    float total_density = 0.0f;
+    size_t blk = 0;
+    for (uint32_t q = 0; q < panels; ++q) {
+        const uint32_t nblk = (p->h_dense_col_offsets[q + 1] - p->h_dense_col_offsets[q] + kBlockCols - 1) / kBlockCols;
+        dense_tb += static_cast<int>((nblk + 3) / 4);                                   // 4 blocks per reference CTA
+        const uint32_t sd = p->h_sparse_value_offsets[q + 1] - p->h_sparse_value_offsets[q];
+        sparse_tb += static_cast<int>((sd + 127) / 128);                                // 128 nnz per reference CTA
+        for (uint32_t b = 0; b < nblk; ++b, ++blk) {
+            uint32_t n = 0;
+            for (uint32_t i = 0; i < 256; ++i) n += bv[blk * 256 + i] != kNull;
+            if (n > 0) {
+                const float density = static_cast<float>(n) / 256.0f;
+                total_density += density;
+                if (density >= delta) ++num_dense_blocks;
+            }
+        }
+    }
+    st->num_dense_blocks = num_dense_blocks;
+    st->average_density = total_density / num_dense_blocks > 0 ? total_density / num_dense_blocks : 0.0f;
+    st->num_dense_thread_blocks = dense_tb;
+    st->num_sparse_thread_blocks = sparse_tb;
+    st->num_sparse_data = static_cast<int32_t>(p->num_res);
+    st->num_dense_data = static_cast<int32_t>(p->nnz - p->num_res);
+
+    // original matrix: 16 x 16 grid blocks in (row panel, column block) order
+    std::vector<uint32_t> ro(static_cast<size_t>(p->M) + 1), ci(p->nnz);
+    BSMR_CUDA_OK(cudaMemcpyAsync(ro.data(), p->row_offsets.ptr, ro.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (p->nnz) BSMR_CUDA_OK(cudaMemcpyAsync(ci.data(), p->col_indices.ptr, ci.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    BSMR_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    const uint32_t rp = (p->M + kPanel - 1) / kPanel, cb = (p->N + kBlockCols - 1) / kBlockCols;
+    std::vector<uint32_t> cnt(cb, 0), touched;
+    int orig_blocks = 0;
+    float orig_total = 0.0f;
+    for (uint32_t q = 0; q < rp; ++q) {
+        const uint32_t r0 = q * kPanel, r1 = std::min(r0 + kPanel, p->M);
+        touched.clear();
+        for (uint32_t r = r0; r < r1; ++r)
+            for (uint32_t k = ro[r]; k < ro[r + 1]; ++k) {
+                const uint32_t b = ci[k] / kBlockCols;
+                if (cnt[b]++ == 0) touched.push_back(b);
+            }
+        std::sort(touched.begin(), touched.end());
+        for (uint32_t b : touched) {
+            const uint32_t c0 = b * kBlockCols, c1 = std::min(c0 + kBlockCols, p->N);
+            const float block_size = static_cast<float>((r1 - r0) * (c1 - c0));
+            const float density = static_cast<float>(cnt[b]) / block_size;
+            if (density >= delta) {
+                orig_total += density;
+                ++orig_blocks;
+            }
+            cnt[b] = 0;
+        }
+    }
+    st->original_num_dense_blocks = orig_blocks;
+    st->original_average_density = orig_blocks > 0 ? orig_total / orig_blocks : 0.0f;
+    return BSMR_OK;
+}
+}  // namespace bsmr
+
+extern "C" {
+
 int bsmr_plan_evaluate(bsmr_plan* plan, float delta, bsmr_reorder_stats* stats) {
     if (!plan || !stats) return BSMR_ERR_INVALID_ARGUMENT;
     if (!plan->have_format) {

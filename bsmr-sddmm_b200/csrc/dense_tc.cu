@@ -440,10 +440,4 @@ int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, 
     return BSMR_OK;
 }
 
-int evaluate_reordering(bsmr_plan* plan, float delta, bsmr_reorder_stats* stats) {
-    (void)plan; (void)delta; (void)stats;
-    set_error("bsmr_plan_evaluate is not implemented yet");
-    return BSMR_ERR_UNSUPPORTED;
-}
-
 }  // namespace bsmr

@@ -5,7 +5,7 @@
  *
  * The reference (CX9898/BSMR-SDDMM) has no FFI layer; its boundary is a C++ host API.
  * Every entry point below names the reference interface it replaces (file:line relative to
- * the reference tree).  The header-only C++ mirror of that API (bsmr-sddmm_b200/host/*.hpp:
+ * the reference tree).  The header-only C++ mirror of that API (the .hpp files in bsmr-sddmm_b200/host:
  * Matrix, sparseMatrix::CSR, Options, Logger, BSMR, RPHM, sddmm(), sddmm_gpu()) is a thin
  * layer over exactly these functions.
  *

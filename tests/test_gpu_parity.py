@@ -105,17 +105,38 @@ def test_block_size_formula(pkg, ctx, oracle):
         assert ctx.calculate_block_size(M, N, free) == oracle.calculate_block_size(M, N, free)
 
 
-def test_row_reorder_vs_reference_gpu(pkg, ctx, ref):
+def run_ref_child(tmp_path, case, K, alpha, delta, block_size, rows_only=False):
+    """The reference's GPU code runs in its own process (it changes device-wide limits and its K > 32
+    kernels fault on sm_100); results come back through an .npz."""
+    import os
+    import subprocess
+    import sys
+    from oracle.bindings import REF_SO
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref/libbsmr_ref.so not built")
+    out = str(tmp_path / ("ref_%s_%d_%s_%s.npz" % (case, K, alpha, delta)))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "tests", "ref_gpu_child.py"), case, str(K), str(alpha), str(delta), str(block_size), out]
+    if rows_only:
+        cmd.append("rows-only")
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    if p.returncode != 0 or not os.path.exists(out):
+        return None
+    return dict(np.load(out))
+
+
+def test_row_reorder_vs_reference_gpu(pkg, ctx, tmp_path):
     """The reference's own bsa_rowReordering_gpu (device-side launches, mutexes) on the same input."""
     for name, M, N, ro, ci in small_cases(pkg):
         if M < 2:
             continue
         for alpha in (0.3, 0.7):
-            want, want_clusters, _ = ref.row_reordering_gpu(M, N, ro, ci, alpha, 16)
+            want = run_ref_child(tmp_path, name, 32, alpha, 0.3, 16, rows_only=True)
+            assert want is not None, "reference row reordering crashed on " + name
             plan = pkg.Plan(ctx, M, N, ro, ci)
             plan.row_reorder(alpha, block_size=16)
-            assert np.array_equal(plan.vector("reordered_rows"), want), (name, alpha)
-            assert plan.info()["num_clusters"] == want_clusters, (name, alpha)
+            assert np.array_equal(plan.vector("reordered_rows"), want["reordered_rows"]), (name, alpha)
+            assert plan.info()["num_clusters"] == int(want["num_clusters"]), (name, alpha)
             plan.close()
 
 
@@ -201,18 +222,29 @@ def test_sddmm_linearity_and_idempotence(pkg, ctx):
     assert torch.equal(p1, p3)
 
 
-def test_full_pipeline_vs_reference_gpu(pkg, ctx, ref, oracle):
-    """Reference binary path (bsa_rowReordering_gpu -> colReordering_cpu -> RPHM -> sddmm_gpu) vs ours."""
-    M, N, ro, ci = pkg.synth.block_structured(1000, 2000, seed=11, groups=12, cols_per_group=64)
+def test_full_pipeline_vs_reference_gpu(pkg, ctx, oracle, tmp_path):
+    """Reference binary path (bsa_rowReordering_gpu -> colReordering_cpu -> RPHM -> sddmm_gpu) vs ours.
+    K = 32 exercises the reference's sddmm_gpu_k32 kernels, which run on sm_100.  Its K > 32 kernels build
+    their shuffle mask with `1 << tId` for tId up to 255 (src/sddmmKernel.cu:2096) and produce no output on
+    B200, so for K = 128 only the reorder vectors are compared and the values are checked against the oracle."""
+    name = "blocks_1000x2000"
+    _, M, N, ro, ci = [c for c in small_cases(pkg) if c[0] == name][0]
     for K in (32, 128):
-        A, B = pkg.synth.make_ab(M, N, K)
-        want = ref.bsmr_sddmm_gpu(M, N, K, ro, ci, A, B, 0.3, 0.3, 16, iters=2)
-        plan, _, _, got = run_sddmm(pkg, ctx, M, N, ro, ci, K, 0.3, 0.3)
+        want = run_ref_child(tmp_path, name, K, 0.3, 0.3, 16)
+        plan, A, B, got = run_sddmm(pkg, ctx, M, N, ro, ci, K, 0.3, 0.3)
+        cpu = oracle.sddmm_cpu(M, N, K, A, B, ro, ci)
+        assert oracle.check_data(cpu, got) == 0
+        if want is None:
+            assert K != 32, "the reference's K <= 32 path is expected to run on sm_100"
+            continue
         for k in ["reordered_rows"] + COL_VECS:
             assert np.array_equal(plan.vector(k), want[k]), (K, k)
-        assert plan.info()["num_clusters"] == want["num_clusters"]
-        assert oracle.check_data(want["P"], got) == 0
-        assert ref.check_data(want["P"], got) == 0
+        assert plan.info()["num_clusters"] == int(want["num_clusters"])
+        ref_ok = oracle.check_data(cpu, want["P"]) == 0       # did the reference itself compute anything?
+        if K == 32:
+            assert ref_ok
+        if ref_ok:
+            assert oracle.check_data(want["P"], got) == 0, K
 
 
 def test_errors_are_reported_not_swallowed(pkg, ctx):
