@@ -459,7 +459,7 @@ static int run_once(bsmr_plan* p, uint32_t K, const float* dA, const float* dB, 
     if (p->shard_tile_end > p->shard_tile_begin) {
         BSMR_TRY(launch_dense(p, K, dA, dB, dP, p->shard_tile_begin, p->shard_tile_end));
     }
-    return launch_residual(ctx, K, dA, dB, dP, p->res_row.ptr, p->res_col.ptr, p->res_out.ptr, p->shard_res_begin,
+    return launch_residual(ctx, K, dA, dB, dP, p->rr_row.ptr, p->rr_col.ptr, p->rr_out.ptr, p->shard_res_begin,
                            p->shard_res_end);
 }
 
@@ -508,7 +508,7 @@ int bsmr_sddmm_profile(bsmr_plan* plan, uint32_t K, const float* dA, const float
         s = launch_dense(plan, K, dA, dB, dP, plan->shard_tile_begin, plan->shard_tile_end);
     cudaEventRecord(mid, ctx->stream);
     if (s == BSMR_OK)
-        s = launch_residual(ctx, K, dA, dB, dP, plan->res_row.ptr, plan->res_col.ptr, plan->res_out.ptr,
+        s = launch_residual(ctx, K, dA, dB, dP, plan->rr_row.ptr, plan->rr_col.ptr, plan->rr_out.ptr,
                             plan->shard_res_begin, plan->shard_res_end);
     cudaEventRecord(ctx->ev1, ctx->stream);
     cudaError_t e = cudaEventSynchronize(ctx->ev1);

@@ -81,37 +81,42 @@ struct ShiftRel {
     __host__ __device__ uint64_t operator()(uint64_t k) const { return k >> 4; }
 };
 
-// C0: key2 = panel << 4 | (16 - count); also count runs per panel
+// C0: key2 = panel << 4 | (16 - count); runs per panel counted with one atomic per (warp, distinct panel)
 __global__ void run_keys_kernel(const uint64_t* __restrict__ ukeys, const uint32_t* __restrict__ counts, uint32_t num_runs,
                                 int cbits, uint32_t* __restrict__ key2, uint32_t* __restrict__ iota,
                                 uint32_t* __restrict__ runs_per_panel) {
-    for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < num_runs; u += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t panel = (uint32_t)(ukeys[u] >> cbits);
-        key2[u] = (panel << 4) | (16u - counts[u]);
-        iota[u] = (uint32_t)u;
-        atomicAdd(runs_per_panel + panel, 1u);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t n32 = ((uint64_t)num_runs + 31) & ~31ull;
+    for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n32; u += (uint64_t)gridDim.x * blockDim.x) {
+        const bool valid = u < num_runs;
+        const uint32_t panel = valid ? (uint32_t)(ukeys[u] >> cbits) : 0xFFFFFFFFu;
+        if (valid) {
+            key2[u] = (panel << 4) | (16u - counts[u]);
+            iota[u] = (uint32_t)u;
+        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, panel);
+        if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(runs_per_panel + panel, (uint32_t)__popc(peers));
     }
 }
 
-// E: classify the 16-column blocks of one panel (one warp per panel)
-__global__ void classify_kernel(uint32_t panels, const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ order,
-                                const uint32_t* __restrict__ counts, uint32_t threshold,
-                                uint32_t* __restrict__ n_dense, uint32_t* __restrict__ n_sparse,
-                                uint32_t* __restrict__ n_sparse_data, uint32_t* __restrict__ n_dense_data,
-                                uint32_t* __restrict__ n_tiles) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t p = warp; p < panels; p += stride) {
+// E: classify the 16-column blocks of one panel (one CTA per panel; a warp pass covers two blocks)
+__global__ void __launch_bounds__(256)
+classify_kernel(uint32_t panels, const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ order,
+                const uint32_t* __restrict__ counts, uint32_t threshold,
+                uint32_t* __restrict__ n_dense, uint32_t* __restrict__ n_sparse,
+                uint32_t* __restrict__ n_sparse_data, uint32_t* __restrict__ n_dense_data,
+                uint32_t* __restrict__ n_tiles) {
+    __shared__ uint32_t red[3][8];
+    const uint32_t lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+    for (uint32_t p = blockIdx.x; p < panels; p += gridDim.x) {
         const uint32_t s0 = run_start[p], s1 = run_start[p + 1];
         const uint32_t U = s1 - s0;
         const uint32_t padded = (U + kBlockCols - 1) / kBlockCols * kBlockCols;
         uint32_t dense_cols = 0, dense_data = 0, total = 0;
-        // two blocks per warp pass: lanes 0-15 -> block b, lanes 16-31 -> block b+1
-        for (uint32_t base = 0; base < padded; base += 32) {
+        // lanes 0-15 -> block b, lanes 16-31 -> block b+1
+        for (uint32_t base = wv * 32; base < padded; base += 256) {
             const uint32_t k = base + lane;
-            uint32_t c = (k < U) ? counts[order[s0 + k]] : 0u;
-            uint32_t s = c;
+            uint32_t s = (k < U) ? counts[order[s0 + k]] : 0u;
 #pragma unroll
             for (int w = 8; w >= 1; w >>= 1) s += __shfl_xor_sync(0xffffffffu, s, w);
             const uint32_t s_lo = __shfl_sync(0xffffffffu, s, 0), s_hi = __shfl_sync(0xffffffffu, s, 16);
@@ -119,13 +124,18 @@ __global__ void classify_kernel(uint32_t panels, const uint32_t* __restrict__ ru
             if (s_lo >= threshold) { dense_cols += kBlockCols; dense_data += s_lo; }
             if (base + 16 < padded && s_hi >= threshold) { dense_cols += kBlockCols; dense_data += s_hi; }
         }
-        if (lane == 0) {
-            n_dense[p] = dense_cols;
-            n_sparse[p] = padded - dense_cols;
-            n_dense_data[p] = dense_data;
-            n_sparse_data[p] = total - dense_data;
-            n_tiles[p] = (dense_cols + kTileCols - 1) / kTileCols;
+        if (lane == 0) { red[0][wv] = dense_cols; red[1][wv] = dense_data; red[2][wv] = total; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t dc = 0, dd = 0, tt = 0;
+            for (int i = 0; i < 8; ++i) { dc += red[0][i]; dd += red[1][i]; tt += red[2][i]; }
+            n_dense[p] = dc;
+            n_sparse[p] = padded - dc;
+            n_dense_data[p] = dd;
+            n_sparse_data[p] = tt - dd;
+            n_tiles[p] = (dc + kTileCols - 1) / kTileCols;
         }
+        __syncthreads();
     }
 }
 
@@ -176,7 +186,8 @@ __global__ void place_entries_kernel(uint32_t num_runs, const uint64_t* __restri
                                      const uint32_t* __restrict__ rows, uint32_t R, int cbits,
                                      uint32_t* __restrict__ scatter, uint32_t* __restrict__ res_out,
                                      uint32_t* __restrict__ res_col, uint32_t* __restrict__ res_row,
-                                     uint8_t* __restrict__ res_rel) {
+                                     uint8_t* __restrict__ res_rel, const uint32_t* __restrict__ start,
+                                     const uint32_t* __restrict__ row_offsets, uint32_t* __restrict__ res_flag) {
     for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < num_runs; u += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t p = (uint32_t)(ukeys[u] >> cbits);
         const uint32_t col = (uint32_t)(ukeys[u] & 0xffffffffull);
@@ -197,8 +208,35 @@ __global__ void place_entries_kernel(uint32_t num_runs, const uint64_t* __restri
                 const uint32_t ri = p * kPanel + rel;
                 res_out[pos0 + j] = vals_sorted[e0 + j];
                 res_col[pos0 + j] = col;
-                res_row[pos0 + j] = rows[ri < R ? ri : R - 1];
+                const uint32_t row = rows[ri < R ? ri : R - 1];
+                res_row[pos0 + j] = row;
                 res_rel[pos0 + j] = (uint8_t)rel;
+                // position of this nnz in the reordered-row enumeration (make_keys_kernel's index)
+                res_flag[start[ri] + (vals_sorted[e0 + j] - row_offsets[row])] = 1u;
+            }
+        }
+    }
+}
+
+// H2: the residual entries once more, ROW-sorted, for the residual kernel (one warp per reordered row)
+__global__ void compact_rows_kernel(const uint32_t* __restrict__ rows, uint32_t R, const uint32_t* __restrict__ row_offsets,
+                                    const uint32_t* __restrict__ col_indices, const uint32_t* __restrict__ start,
+                                    const uint32_t* __restrict__ res_flag, const uint32_t* __restrict__ res_pos,
+                                    uint32_t* __restrict__ rr_row, uint32_t* __restrict__ rr_col, uint32_t* __restrict__ rr_out) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t i = warp; i < R; i += stride) {
+        const uint32_t r = rows[i];
+        const uint32_t b = row_offsets[r], e = row_offsets[r + 1];
+        const uint32_t q0 = start[i];
+        for (uint32_t k = b + lane; k < e; k += 32) {
+            const uint32_t q = q0 + (k - b);
+            if (res_flag[q]) {
+                const uint32_t pos = res_pos[q];
+                rr_row[pos] = r;
+                rr_col[pos] = col_indices[k];
+                rr_out[pos] = k;
             }
         }
     }
@@ -226,6 +264,8 @@ int col_reorder_and_format(bsmr_plan* plan, float delta) {
     const uint32_t panels = plan->num_row_panels;
     const uint32_t N = plan->N;
     const int sm = ctx->sm_count;
+    Workspace* ws = &ctx->ws;
+    ws->reset();
     // numNonZeroThreshold = (UIN)ceil(delta * BLOCK_SIZE)   (src/colReordering.cu:246)
     const uint32_t threshold = static_cast<uint32_t>(std::ceil(delta * static_cast<float>(kPanel * kBlockCols)));
 
@@ -237,21 +277,20 @@ int col_reorder_and_format(bsmr_plan* plan, float delta) {
     BSMR_CUDA_OK(cudaEventRecord(e0, st));
 
     // per-panel outputs (+1 for the scans)
-    DevBuf<uint32_t> n_dense, n_sparse, n_sparse_data, n_dense_data, n_tiles, d_off, s_off, sv_off, tile_base, run_start,
-        runs_per_panel;
+    TmpBuf<uint32_t> n_dense(ws), n_sparse(ws), n_sparse_data(ws), n_dense_data(ws), n_tiles(ws), d_off(ws), s_off(ws), sv_off(ws), tile_base(ws), run_start(ws), runs_per_panel(ws);
     const size_t P1 = static_cast<size_t>(panels) + 1;
     BSMR_TRY(n_dense.alloc(P1)); BSMR_TRY(n_sparse.alloc(P1)); BSMR_TRY(n_sparse_data.alloc(P1));
     BSMR_TRY(n_dense_data.alloc(P1)); BSMR_TRY(n_tiles.alloc(P1)); BSMR_TRY(d_off.alloc(P1)); BSMR_TRY(s_off.alloc(P1));
     BSMR_TRY(sv_off.alloc(P1)); BSMR_TRY(tile_base.alloc(P1)); BSMR_TRY(run_start.alloc(P1)); BSMR_TRY(runs_per_panel.alloc(P1));
-    for (DevBuf<uint32_t>* b : {&n_dense, &n_sparse, &n_sparse_data, &n_dense_data, &n_tiles, &runs_per_panel})
+    for (TmpBuf<uint32_t>* b : {&n_dense, &n_sparse, &n_sparse_data, &n_dense_data, &n_tiles, &runs_per_panel})
         BSMR_CUDA_OK(cudaMemsetAsync(b->ptr, 0, b->bytes(), st));
 
     // ---- A: keys ------------------------------------------------------------------------
-    DevBuf<uint32_t> len, start;
+    TmpBuf<uint32_t> len(ws), start(ws);
     BSMR_TRY(len.alloc(static_cast<size_t>(R) + 1));
     BSMR_TRY(start.alloc(static_cast<size_t>(R) + 1));
     BSMR_CUDA_OK(cudaMemsetAsync(len.ptr, 0, len.bytes(), st));
-    DevBuf<uint8_t> temp;
+    TmpBuf<uint8_t> temp(ws);
     auto ensure_temp = [&](size_t bytes) -> int {
         if (bytes > temp.count) return temp.alloc(bytes + bytes / 8 + 256);
         return BSMR_OK;
@@ -271,8 +310,8 @@ int col_reorder_and_format(bsmr_plan* plan, float delta) {
 
     const int cbits = 32;                                  // column field width inside the run key
     const int pbits = bits_for(panels ? panels - 1 : 0);
-    DevBuf<uint64_t> keys_a, keys_b, ukeys;
-    DevBuf<uint32_t> vals_a, vals_b, counts, num_runs_d, key2_a, key2_b, ord_a, ord_b, run_off, sparse_cnt, res_start, rank_of_run;
+    TmpBuf<uint64_t> keys_a(ws), keys_b(ws), ukeys(ws);
+    TmpBuf<uint32_t> vals_a(ws), vals_b(ws), counts(ws), num_runs_d(ws), key2_a(ws), key2_b(ws), ord_a(ws), ord_b(ws), run_off(ws), sparse_cnt(ws), res_start(ws), rank_of_run(ws);
     uint32_t num_runs = 0;
     const uint64_t* keys_sorted = nullptr;
     const uint32_t* vals_sorted = nullptr;
@@ -338,7 +377,7 @@ int col_reorder_and_format(bsmr_plan* plan, float delta) {
     }
     // ---- E: dense / residual split per panel -------------------------------------------------
     if (panels) {
-        classify_kernel<<<grid_for((uint64_t)panels * 32, kThreads, sm), kThreads, 0, st>>>(
+        classify_kernel<<<(panels < (uint32_t)sm * 8 ? panels : (uint32_t)sm * 8), 256, 0, st>>>(
             panels, run_start.ptr, order, counts.ptr, threshold, n_dense.ptr, n_sparse.ptr, n_sparse_data.ptr, n_dense_data.ptr, n_tiles.ptr);
         ctx->launches++;
     }
@@ -367,7 +406,7 @@ int col_reorder_and_format(bsmr_plan* plan, float delta) {
     const uint32_t total_tiles = h_tile_base[panels];
 
     // ---- G: column lists ---------------------------------------------------------------------
-    DevBuf<uint32_t> sparse_cols;
+    TmpBuf<uint32_t> sparse_cols(ws);
     BSMR_TRY(plan->dense_cols.alloc(total_dense_cols));
     BSMR_TRY(sparse_cols.alloc(total_sparse_cols));
     if (total_dense_cols) fill_u32_kernel<<<grid_for(total_dense_cols, kThreads, sm), kThreads, 0, st>>>(plan->dense_cols.ptr, total_dense_cols, N);
@@ -394,6 +433,11 @@ int col_reorder_and_format(bsmr_plan* plan, float delta) {
     plan->num_dense_blocks = total_dense_cols / kBlockCols;
     BSMR_TRY(plan->res_out.alloc(total_res)); BSMR_TRY(plan->res_col.alloc(total_res));
     BSMR_TRY(plan->res_row.alloc(total_res)); BSMR_TRY(plan->res_rel.alloc(total_res));
+    BSMR_TRY(plan->rr_row.alloc(total_res)); BSMR_TRY(plan->rr_col.alloc(total_res)); BSMR_TRY(plan->rr_out.alloc(total_res));
+    TmpBuf<uint32_t> res_flag(ws), res_pos(ws);
+    BSMR_TRY(res_flag.alloc(static_cast<size_t>(total) + 1));
+    BSMR_TRY(res_pos.alloc(static_cast<size_t>(total) + 1));
+    BSMR_CUDA_OK(cudaMemsetAsync(res_flag.ptr, 0, res_flag.bytes(), st));
     BSMR_TRY(plan->tile_panel.alloc(total_tiles)); BSMR_TRY(plan->tile_col_begin.alloc(total_tiles));
     BSMR_TRY(plan->tile_ncols.alloc(total_tiles));
     BSMR_TRY(plan->tile_scatter.alloc(static_cast<size_t>(total_tiles) * kPanel * kTileCols));
@@ -416,8 +460,17 @@ int col_reorder_and_format(bsmr_plan* plan, float delta) {
         place_entries_kernel<<<grid_for(num_runs, kThreads, sm), kThreads, 0, st>>>(
             num_runs, ukeys.ptr, counts.ptr, run_off.ptr, rank_of_run.ptr, run_start.ptr, n_dense.ptr, tile_base.ptr, res_start.ptr,
             keys_sorted, vals_sorted, plan->reordered_rows.ptr, R, cbits, plan->tile_scatter.ptr, plan->res_out.ptr,
-            plan->res_col.ptr, plan->res_row.ptr, plan->res_rel.ptr);
+            plan->res_col.ptr, plan->res_row.ptr, plan->res_rel.ptr, start.ptr, plan->row_offsets.ptr, res_flag.ptr);
         ctx->launches++;
+        if (total_res) {
+            BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb, res_flag.ptr, res_pos.ptr, static_cast<size_t>(total) + 1, st));
+            BSMR_TRY(ensure_temp(tb));
+            BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(temp.ptr, tb, res_flag.ptr, res_pos.ptr, static_cast<size_t>(total) + 1, st));
+            compact_rows_kernel<<<grid_for((uint64_t)R * 32, kThreads, sm), kThreads, 0, st>>>(
+                plan->reordered_rows.ptr, R, plan->row_offsets.ptr, plan->col_indices.ptr, start.ptr, res_flag.ptr, res_pos.ptr,
+                plan->rr_row.ptr, plan->rr_col.ptr, plan->rr_out.ptr);
+            ctx->launches += 2;
+        }
     }
     BSMR_TRY(d2h(plan->h_tile_panel, plan->tile_panel.ptr, total_tiles, st));
     BSMR_CUDA_OK(cudaEventRecord(e2, st));

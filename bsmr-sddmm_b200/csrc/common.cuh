@@ -52,10 +52,15 @@ struct DevBuf {
         ptr = nullptr;
         count = 0;
     }
-    // (re)allocate exactly n elements; contents undefined
+    // make room for n elements (grow-only: a smaller request keeps the block); contents undefined
+    size_t capacity = 0;
     int alloc(size_t n) {
-        if (n == count && ptr) return BSMR_OK;
+        if (ptr && n <= capacity) {
+            count = n;
+            return BSMR_OK;
+        }
         release();
+        capacity = 0;
         if (n == 0) return BSMR_OK;
         cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ptr), n * sizeof(T));
         if (e != cudaSuccess) {
@@ -64,8 +69,74 @@ struct DevBuf {
             (void)cudaGetLastError();
             return BSMR_ERR_OUT_OF_MEMORY;
         }
-        count = n;
+        count = capacity = n;
         return BSMR_OK;
+    }
+    size_t bytes() const { return count * sizeof(T); }
+};
+
+// ---- scratch arena for the reorder passes ---------------------------------------------------
+// cudaMalloc / cudaFree cost 0.1-1 ms each; the reorder passes need ~30 temporaries.  The arena is a
+// bump allocator over one device block that is reset at the start of a pass; if a pass outgrows it the
+// overflow is served by extra blocks and the main block is regrown to the high-water mark at the next
+// reset, so that from the second call on a pass performs no device allocation at all.
+struct Workspace {
+    char* base = nullptr;
+    size_t cap = 0, off = 0, high = 0;
+    std::vector<void*> overflow;
+    ~Workspace() { release(); }
+    void release() {
+        for (void* p : overflow) cudaFree(p);
+        overflow.clear();
+        if (base) cudaFree(base);
+        base = nullptr;
+        cap = off = 0;
+    }
+    // start of a pass (the stream must be idle with respect to the previous pass' scratch)
+    void reset() {
+        if (!overflow.empty() || high > cap) {
+            for (void* p : overflow) cudaFree(p);
+            overflow.clear();
+            if (base) cudaFree(base);
+            base = nullptr;
+            cap = 0;
+            const size_t want = high + high / 4 + (1u << 20);
+            if (cudaMalloc(reinterpret_cast<void**>(&base), want) == cudaSuccess) cap = want; else { base = nullptr; (void)cudaGetLastError(); }
+        }
+        off = 0;
+        high = 0;
+    }
+    void* get(size_t bytes) {
+        bytes = (bytes + 255) & ~static_cast<size_t>(255);
+        if (bytes == 0) bytes = 256;
+        high += bytes;
+        if (base && off + bytes <= cap) {
+            void* p = base + off;
+            off += bytes;
+            return p;
+        }
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            (void)cudaGetLastError();
+            set_error("scratch allocation of %zu bytes failed", bytes);
+            return nullptr;
+        }
+        overflow.push_back(p);
+        return p;
+    }
+};
+
+// DevBuf-shaped handle on arena memory (never freed individually)
+template <typename T>
+struct TmpBuf {
+    T* ptr = nullptr;
+    size_t count = 0;
+    Workspace* ws;
+    explicit TmpBuf(Workspace* w) : ws(w) {}
+    int alloc(size_t n) {
+        count = n;
+        ptr = static_cast<T*>(ws->get(n * sizeof(T)));
+        return ptr ? BSMR_OK : BSMR_ERR_OUT_OF_MEMORY;
     }
     size_t bytes() const { return count * sizeof(T); }
 };
@@ -84,6 +155,7 @@ struct bsmr_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // tensor-map encoder resolved at runtime (no link-time dependency on libcuda)
     void* encode_tiled = nullptr;
+    bsmr::Workspace ws;     // scratch of the reorder passes
 };
 
 struct bsmr_plan {
@@ -115,6 +187,10 @@ struct bsmr_plan {
     bsmr::DevBuf<uint32_t> res_row;   // A row (absolute)
     bsmr::DevBuf<uint8_t> res_rel;    // row inside the panel (for the RPHM accessor)
     uint64_t num_res = 0;
+    // the same entries ROW-sorted (reordered row, then CSR position): what the residual kernel walks, so
+    // that an A row stays in registers across its entries.  Panel p still owns the contiguous range
+    // [sparse_value_offsets[p], sparse_value_offsets[p+1]).
+    bsmr::DevBuf<uint32_t> rr_row, rr_col, rr_out;
     // dense tiles: up to 128 dense columns (8 reference blocks) of one panel
     bsmr::DevBuf<uint32_t> tile_panel;     // panel id per tile
     bsmr::DevBuf<uint32_t> tile_col_begin; // offset into dense_cols

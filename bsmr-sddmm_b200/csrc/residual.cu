@@ -3,20 +3,26 @@
 // Replaces the reference's sddmm_gpu_sparse_block_2_2threadOneData_shuffle and
 // sddmm_gpu_sparse_remainder_k32_2threadOneData_shuffle (src/sddmmKernel.cu:1994-2104,
 // 2109-2199).  Those use 2 threads per nnz, a 16x36 smem A tile rebuilt every 32 k and
-// two 16-byte loads per thread per step.  Here:
-//   * a warp owns 32 consecutive residual entries; their (A row, B column, P index)
-//     triples are read with one coalesced load each and handed around by shuffles
-//   * a group of LPN lanes (8 / 16 / 32, chosen from K) computes one entry: every lane
-//     loads 128-bit pieces of the A row and of the B column (a full K-vector is one or
-//     more perfectly coalesced 128..512-byte requests), 4 FMAs per piece, then a
-//     log2(LPN)-step xor-shuffle reduction
-//   * UNROLL entries are in flight per group, so every lane has 2*UNROLL*KV independent
-//     16-byte loads outstanding before the first FMA
-//   * results are moved to "lane j holds entry j" and stored with one warp-wide store,
-//     which is fully coalesced whenever the P indices are consecutive (CSR-order mode)
-// No shared memory, no block barrier; the A rows of a panel (16*K*4 bytes) live in L1.
+// two 16-byte loads per thread per step.
 //
-// Roofline: HBM-bound on compulsory traffic; what it actually stresses is L2->SM gather
+// residual_rows_kernel (the fast path, K in {32, 64, 128, 256, 512}):
+//   * the residual entries are stored ROW-sorted (reordered row, then CSR position); a warp
+//     owns 32 consecutive entries whose (A row, B column, P index) triples are read with one
+//     coalesced load each and handed around by shuffles
+//   * a group of LPN lanes (8 / 16 / 32, chosen from K) computes one entry; the A row lives
+//     in REGISTERS (K/LPN floats per lane) and is reloaded only when the row changes, so the
+//     steady state moves exactly one K-vector of B per nnz through L1 -- the first version
+//     re-read the A row per nnz and was L1-bound (ncu: l1tex 76 %, profiles/r01a_*)
+//   * every lane loads 128-bit pieces of the B column (a K-vector is one or more perfectly
+//     coalesced 128..512-byte requests); UNROLL entries are in flight before the first FMA
+//   * the dot products of a whole chunk are reduced together: lane-local partials p[it] for
+//     the LPN entries a group handles, then a transposing butterfly (LPN-1 shuffles per LPN
+//     results instead of LPN*log2(LPN)); lane s ends up with the finished value of entry
+//     s*G + group and stores it
+// No shared memory, no block barrier.
+// residual_sddmm_kernel / residual_sddmm_generic_kernel: any other K (runtime K loop; A from L1).
+//
+// Roofline: HBM-bound on compulsory traffic; what it actually stresses is L2 -> SM gather
 // bandwidth (K*4 bytes of B per nnz), see DESIGN.md.
 #include "common.cuh"
 
@@ -113,6 +119,97 @@ residual_sddmm_kernel(const uint32_t K, const float* __restrict__ A, const float
     }
 }
 
+// Row-sorted fast path.  LPN lanes per entry, KV float4 pieces per lane: K == LPN * 4 * KV.
+template <int LPN, int KV>
+__global__ void __launch_bounds__(kResThreads, 3)
+residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const float* __restrict__ B,
+                     float* __restrict__ P, const uint32_t* __restrict__ res_row,
+                     const uint32_t* __restrict__ res_col, const uint32_t* __restrict__ res_out,
+                     const uint64_t begin, const uint64_t end) {
+    constexpr int G = 32 / LPN;      // entries in flight per warp instruction
+    constexpr int UNROLL = KV >= 4 ? 2 : 4;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t sub = lane / LPN;
+    const uint32_t sl = lane % LPN;
+    const uint64_t num_chunks = (end - begin + 31) / 32;
+    const uint64_t warp_global = (uint64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const uint64_t warp_stride = (uint64_t)gridDim.x * kWarpsPerCta;
+
+    uint32_t cur_row = 0xFFFFFFFFu;
+    float4 a_cur[KV];
+#pragma unroll
+    for (int v = 0; v < KV; ++v) a_cur[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (uint64_t chunk = warp_global; chunk < num_chunks; chunk += warp_stride) {
+        const uint64_t e = begin + chunk * 32 + lane;
+        const bool valid = e < end;
+        const uint64_t es = valid ? e : begin;       // idle lanes recompute entry `begin`; never stored
+        const uint32_t my_row = __ldg(res_row + es);
+        const uint32_t my_col = __ldg(res_col + es);
+        const uint32_t my_out = res_out ? __ldg(res_out + es) : (uint32_t)es;   // NULL = identity (CSR order)
+        // Pass s (s = 0..ITERS-1, entries in list order so that the A row in registers is reused) fills
+        // accumulator slot it(s) = (s >> 1) + (s & 1) * H: the two passes of a pair (i, i + H) are adjacent,
+        // and the first butterfly step (offset H) is folded in as soon as both are known, which keeps only
+        // H accumulators live.
+        constexpr int H = LPN / 2;
+        float q[H];
+        const bool upper0 = (sl & H) != 0;
+#pragma unroll
+        for (int i0 = 0; i0 < H; i0 += UNROLL / 2) {
+            float4 bv[UNROLL][KV];
+            uint32_t rows_u[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int s_pass = 2 * i0 + u;            // list-order pass
+                const int j = s_pass * G + sub;           // entry handled by this group in that pass
+                rows_u[u] = __shfl_sync(0xffffffffu, my_row, j);
+                const uint32_t col = __shfl_sync(0xffffffffu, my_col, j);
+                const float* bp = B + (size_t)col * K + sl * 4;
+#pragma unroll
+                for (int v = 0; v < KV; ++v) bv[u][v] = ldg4(bp + v * LPN * 4);
+            }
+            float d[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (rows_u[u] != cur_row) {              // uniform inside the group (warp-uniform for LPN == 32)
+                    const float* ap = A + (size_t)rows_u[u] * K + sl * 4;
+#pragma unroll
+                    for (int v = 0; v < KV; ++v) a_cur[v] = ldg4(ap + v * LPN * 4);
+                    cur_row = rows_u[u];
+                }
+                float acc = 0.f;
+#pragma unroll
+                for (int v = 0; v < KV; ++v) acc = dot4(a_cur[v], bv[u][v], acc);
+                d[u] = acc;
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; u += 2) {
+                const float send = upper0 ? d[u] : d[u + 1];     // slots i (pass 2i) and i + H (pass 2i + 1)
+                const float keep = upper0 ? d[u + 1] : d[u];
+                q[i0 + u / 2] = keep + __shfl_xor_sync(0xffffffffu, send, H);
+            }
+            asm volatile("" ::: "memory");   // keep the loads of later batches from being hoisted (register pressure)
+        }
+        // remaining steps of the transposing butterfly over the LPN lanes of a group: after the step with
+        // offset h, lanes whose bit h is clear hold the sums of slots [0,h), the others those of [h,2h)
+#pragma unroll
+        for (int h = H / 2; h >= 1; h >>= 1) {
+            const bool upper = (sl & h) != 0;
+#pragma unroll
+            for (int i = 0; i < h; ++i) {
+                const float send = upper ? q[i] : q[i + h];
+                const float keep = upper ? q[i + h] : q[i];
+                q[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+            }
+        }
+        // this lane holds the finished dot product of slot `sl`, i.e. of pass s = 2 * (sl % H) + sl / H
+        const int mine = (int)((2 * (sl % H) + sl / H) * G + sub);
+        const uint32_t out = __shfl_sync(0xffffffffu, my_out, mine);
+        const bool ok = __shfl_sync(0xffffffffu, (int)valid, mine) != 0;
+        if (ok) P[out] = q[0];
+    }
+}
+
 // Any K (no alignment assumption): one lane group of 32, scalar loads.
 __global__ void __launch_bounds__(kResThreads)
 residual_sddmm_generic_kernel(const uint32_t K, const float* __restrict__ A, const float* __restrict__ B,
@@ -165,7 +262,10 @@ int launch_residual(bsmr_ctx* ctx, uint32_t K, const float* dA, const float* dB,
     const uint64_t ctas_needed = (chunks + kWarpsPerCta - 1) / kWarpsPerCta;
     // 8 CTAs of 256 threads = 64 warps = a full SM; grid is a multiple of the SM count
     const uint64_t max_ctas = (uint64_t)ctx->sm_count * 8;
-    const int grid = (int)(ctas_needed < max_ctas ? ctas_needed : max_ctas);
+    const bool fast_k = K == 32 || K == 64 || K == 128 || K == 256 || K == 512;
+    // residual_rows_kernel: 3 resident CTAs per SM (register budget), persistent grid-stride over the chunks
+    const uint64_t cap = fast_k ? (uint64_t)ctx->sm_count * 3 : max_ctas;
+    const int grid = (int)(ctas_needed < cap ? ctas_needed : cap);
     const bool aligned = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(dB)) % 16 == 0);
 
     if (!aligned) {
@@ -174,15 +274,15 @@ int launch_residual(bsmr_ctx* ctx, uint32_t K, const float* dA, const float* dB,
         const int g = (int)(need < max_ctas ? need : max_ctas);
         residual_sddmm_generic_kernel<<<g, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end);
     } else if (K == 32) {
-        launch_one<8, 1, 4>(ctx, grid, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+        residual_rows_kernel<8, 1><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end);
     } else if (K == 64) {
-        launch_one<16, 1, 4>(ctx, grid, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+        residual_rows_kernel<16, 1><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end);
     } else if (K == 128) {
-        launch_one<32, 1, 4>(ctx, grid, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+        residual_rows_kernel<32, 1><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end);
     } else if (K == 256) {
-        launch_one<32, 2, 4>(ctx, grid, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+        residual_rows_kernel<32, 2><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end);
     } else if (K == 512) {
-        launch_one<32, 4, 2>(ctx, grid, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+        residual_rows_kernel<32, 4><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end);
     } else if (K < 64) {
         launch_one<8, 0, 2>(ctx, grid, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
     } else if (K < 128) {

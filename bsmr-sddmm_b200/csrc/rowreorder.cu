@@ -64,27 +64,43 @@ __global__ void enc_keys_kernel(uint32_t M, const uint32_t* __restrict__ row_off
     }
 }
 
-__global__ void runs_per_row_kernel(const uint64_t* __restrict__ ukeys, uint32_t num_runs, uint32_t* __restrict__ runs_per_row) {
-    for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < num_runs; u += (uint64_t)gridDim.x * blockDim.x)
-        atomicAdd(runs_per_row + (uint32_t)(ukeys[u] >> 32), 1u);
+// enc_blk[u] = column block of run u; runs per row counted with one atomic per (warp, distinct row)
+__global__ void runs_split_kernel(const uint64_t* __restrict__ ukeys, uint32_t num_runs, uint32_t* __restrict__ enc_blk,
+                                  uint32_t* __restrict__ runs_per_row) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t n32 = ((uint64_t)num_runs + 31) & ~31ull;
+    for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n32; u += (uint64_t)gridDim.x * blockDim.x) {
+        const bool valid = u < num_runs;
+        const uint64_t key = valid ? ukeys[u] : ~0ull;
+        const uint32_t row = (uint32_t)(key >> 32);
+        if (valid) enc_blk[u] = (uint32_t)(key & 0xffffffffull);
+        const uint32_t peers = __match_any_sync(0xffffffffu, row);
+        if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(runs_per_row + row, (uint32_t)__popc(peers));
+    }
 }
 
-// dispersion (src/rowReordering.cu:78-92) and the row's (possibly lossy) sum of squares, thread per row
+// dispersion (src/rowReordering.cu:78-92) and the row's (possibly lossy) sum of squares, one warp per row
 __global__ void dispersion_kernel(uint32_t M, const uint32_t* __restrict__ row_offsets, const uint32_t* __restrict__ enc_ptr,
-                                  const uint64_t* __restrict__ ukeys, const uint32_t* __restrict__ counts, uint32_t block_size,
+                                  const uint32_t* __restrict__ enc_blk, const uint32_t* __restrict__ counts, uint32_t block_size,
                                   uint32_t bd, uint32_t kept_mask, uint32_t* __restrict__ dispersion, uint32_t* __restrict__ row_sq) {
-    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < M; r += stride) {
         const uint32_t nz = row_offsets[r + 1] - row_offsets[r];
         const uint32_t b = enc_ptr[r], e = enc_ptr[r + 1];
         uint32_t res = 0, sq = 0;
-        for (uint32_t j = b; j < e; ++j) {
+        for (uint32_t j = b + lane; j < e; j += 32) {
             const uint32_t c = counts[j];
-            const uint32_t blk = (uint32_t)(ukeys[j] & 0xffffffffull);
             res += block_size - c;
-            if ((kept_mask >> ((blk % bd) >> 5)) & 1u) sq += c * c;
+            if ((kept_mask >> ((enc_blk[j] % bd) >> 5)) & 1u) sq += c * c;
         }
-        dispersion[r] = nz ? res + nz * (e - b) : 0u;
-        row_sq[r] = sq;
+        res = __reduce_add_sync(0xffffffffu, res);
+        sq = __reduce_add_sync(0xffffffffu, sq);
+        if (lane == 0) {
+            dispersion[r] = nz ? res + nz * (e - b) : 0u;
+            row_sq[r] = sq;
+        }
     }
 }
 
@@ -107,6 +123,26 @@ struct Low32Key {
     __host__ __device__ uint64_t operator()(uint64_t k) const { return k; }
 };
 
+// first position in [lo, hi) whose value is >= target; warp-cooperative 32-ary search over a sorted array,
+// every lane returns the same result
+__device__ __forceinline__ uint32_t warp_lower_bound(const uint32_t* __restrict__ a, uint32_t lo, uint32_t hi, uint32_t target,
+                                                     uint32_t lane) {
+    while (hi - lo > 32) {
+        const uint32_t step = (hi - lo + 31) >> 5;
+        const uint32_t pos = lo + lane * step;
+        const bool less = pos < hi && a[pos] < target;
+        const uint32_t k = __popc(__ballot_sync(0xffffffffu, less));   // probes are sorted: the mask is a prefix
+        if (k == 0) return lo;
+        const uint32_t nlo = lo + (k - 1) * step + 1;
+        const uint32_t nhi = lo + k * step;
+        lo = nlo;
+        hi = nhi < hi ? nhi : hi;
+    }
+    const uint32_t pos = lo + lane;
+    const bool less = pos < hi && a[pos] < target;
+    return lo + __popc(__ballot_sync(0xffffffffu, less));
+}
+
 // ---- the clustering kernel ------------------------------------------------------------------
 struct ClusterParams {
     uint32_t M;            // rows (positions in dispersion order)
@@ -117,7 +153,7 @@ struct ClusterParams {
     float alpha;
     const uint32_t* asc;       // position -> row
     const uint32_t* enc_ptr;   // row -> first run
-    const uint64_t* ukeys;     // run -> row << 32 | block
+    const uint32_t* enc_blk;   // run -> column block (ascending inside a row)
     const uint32_t* counts;    // run -> nnz in the block
     const uint32_t* row_sq;    // row -> (lossy) sum of squares
     uint32_t* cluster_ids;     // position -> cluster id (pre-set: 0 for empty rows, NULL otherwise)
@@ -193,7 +229,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
         if (assign)
             for (uint32_t i = tid; i < p.nb; i += kClusterThreads) rep[i] = 0;
         __syncthreads();
-        for (uint32_t j = b + tid; j < e; j += kClusterThreads) rep[(uint32_t)(p.ukeys[j] & 0xffffffffull)] += p.counts[j];
+        for (uint32_t j = b + tid; j < e; j += kClusterThreads) rep[p.enc_blk[j]] += p.counts[j];
         __syncthreads();
     };
 
@@ -230,45 +266,37 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
                     const uint32_t b = p.enc_ptr[row], e = p.enc_ptr[row + 1];
                     // which reference warps own a non-zero block of this row
                     uint32_t touched = 0;
-                    for (uint32_t j = b + lane; j < e; j += 32) {
-                        const uint32_t blk = (uint32_t)(p.ukeys[j] & 0xffffffffull);
-                        touched |= 1u << ((blk % p.bd) >> 5);
-                    }
+                    for (uint32_t j = b + lane; j < e; j += 32) touched |= 1u << ((p.enc_blk[j] % p.bd) >> 5);
                     touched = __reduce_or_sync(0xffffffffu, touched);
                     float my_min = 0.f, my_max = lane < nw ? warp_max[lane] : 0.f;  // lane w = reference warp w
                     while (touched) {
                         const uint32_t w = __ffs(touched) - 1;
                         touched &= touched - 1;
-                        // this lane emulates reference thread t = w*32 + lane: terms i = t, t+bd, ... ascending
-                        const uint32_t t = (w << 5) + lane;
+                        // this lane emulates reference thread t = w*32 + lane: terms i = t, t+bd, ... ascending.
+                        // The 32 threads of the warp own 32 CONSECUTIVE blocks per term, i.e. one contiguous slice of
+                        // the row's sorted block list: one cooperative search + one coalesced load per term.
                         float acc_min = 0.f, acc_max = 0.f;
-                        uint32_t next_i = t;
-                        for (uint32_t j0 = b; j0 < e; j0 += 32) {
-                            const uint32_t j = j0 + lane;
-                            uint32_t blk = 0, cnt = 0;
-                            bool hit = false;
-                            if (j < e) {
-                                blk = (uint32_t)(p.ukeys[j] & 0xffffffffull);
-                                cnt = p.counts[j];
-                                hit = ((blk % p.bd) >> 5) == w;
-                            }
-                            uint32_t sel = __ballot_sync(0xffffffffu, hit);
-                            while (sel) {
-                                const uint32_t src = __ffs(sel) - 1;
-                                sel &= sel - 1;
-                                const uint32_t blk_e = __shfl_sync(0xffffffffu, blk, src);
-                                const uint32_t cnt_e = __shfl_sync(0xffffffffu, cnt, src);
-                                if (((blk_e % p.bd) & 31) == lane) {
-                                    for (; next_i < blk_e; next_i += p.bd) acc_max += repn[next_i];
-                                    const float a = repn[blk_e];
-                                    const float c = (float)cnt_e / nc;
+                        uint32_t lo = b;
+                        for (uint32_t base = w << 5; base < p.nb; base += p.bd) {
+                            lo = warp_lower_bound(p.enc_blk, lo, e, base, lane);
+                            const uint32_t x = lo + lane;
+                            const uint32_t blk_x = x < e ? p.enc_blk[x] : 0xFFFFFFFFu;
+                            const bool in = blk_x < base + 32;
+                            const uint32_t cnt_x = in ? p.counts[x] : 0u;
+                            const uint32_t has = __reduce_or_sync(0xffffffffu, in ? 1u << (blk_x - base) : 0u);
+                            const uint32_t cnt = __shfl_sync(0xffffffffu, cnt_x, __popc(has & ((1u << lane) - 1u)));
+                            const uint32_t i = base + lane;
+                            if (i < p.nb) {
+                                const float a = repn[i];
+                                if ((has >> lane) & 1u) {
+                                    const float c = (float)cnt / nc;
                                     acc_min += fminf(a, c);
                                     acc_max += fmaxf(a, c);
-                                    next_i = blk_e + p.bd;
+                                } else {
+                                    acc_max += a;
                                 }
                             }
                         }
-                        for (; next_i < p.nb; next_i += p.bd) acc_max += repn[next_i];
 #pragma unroll
                         for (int x = 1; x < 32; x <<= 1) {
                             acc_min += __shfl_xor_sync(0xffffffffu, acc_min, x);
@@ -349,6 +377,8 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
     cudaStream_t st = ctx->stream;
     const uint32_t M = plan->M, N = plan->N, nnz = plan->nnz;
     const int sm = ctx->sm_count;
+    Workspace* ws = &ctx->ws;
+    ws->reset();
     cudaEvent_t e0, e1;
     BSMR_CUDA_OK(cudaEventCreate(&e0));
     BSMR_CUDA_OK(cudaEventCreate(&e1));
@@ -397,14 +427,14 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
             return BSMR_ERR_UNSUPPORTED;
         }
 
-        DevBuf<uint8_t> temp;
+        TmpBuf<uint8_t> temp(ws);
         auto ensure_temp = [&](size_t bytes) -> int {
             if (bytes > temp.count) return temp.alloc(bytes + bytes / 8 + 256);
             return BSMR_OK;
         };
         // ---- sparse encodings ----
-        DevBuf<uint64_t> keys_a, keys_b, ukeys;
-        DevBuf<uint32_t> counts, num_runs_d, runs_per_row, enc_ptr, disp, row_sq;
+        TmpBuf<uint64_t> keys_a(ws), keys_b(ws), ukeys(ws);
+        TmpBuf<uint32_t> counts(ws), num_runs_d(ws), runs_per_row(ws), enc_ptr(ws), disp(ws), row_sq(ws), enc_blk(ws);
         BSMR_TRY(runs_per_row.alloc(static_cast<size_t>(M) + 1));
         BSMR_TRY(enc_ptr.alloc(static_cast<size_t>(M) + 1));
         BSMR_TRY(disp.alloc(M ? M : 1));
@@ -431,7 +461,8 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
             ctx->launches++;
             BSMR_CUDA_OK(cudaMemcpyAsync(&num_runs, num_runs_d.ptr, 4, cudaMemcpyDeviceToHost, st));
             BSMR_CUDA_OK(cudaStreamSynchronize(st));
-            runs_per_row_kernel<<<grid_for(num_runs, kThreads, sm), kThreads, 0, st>>>(ukeys.ptr, num_runs, runs_per_row.ptr);
+            BSMR_TRY(enc_blk.alloc(num_runs));
+            runs_split_kernel<<<grid_for(num_runs, kThreads, sm), kThreads, 0, st>>>(ukeys.ptr, num_runs, enc_blk.ptr, runs_per_row.ptr);
             ctx->launches++;
         }
         {
@@ -441,14 +472,14 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
             BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(temp.ptr, tb, runs_per_row.ptr, enc_ptr.ptr, static_cast<size_t>(M) + 1, st));
             ctx->launches++;
         }
-        DevBuf<uint32_t> asc_a, asc_b, dk_a, dk_b, zero_cnt;
+        TmpBuf<uint32_t> asc_a(ws), asc_b(ws), dk_a(ws), dk_b(ws), zero_cnt(ws);
         BSMR_TRY(asc_a.alloc(M ? M : 1)); BSMR_TRY(asc_b.alloc(M ? M : 1)); BSMR_TRY(dk_a.alloc(M ? M : 1)); BSMR_TRY(dk_b.alloc(M ? M : 1));
         BSMR_TRY(zero_cnt.alloc(1));
         BSMR_CUDA_OK(cudaMemsetAsync(zero_cnt.ptr, 0, 4, st));
         const uint32_t* asc = asc_a.ptr;
         uint32_t zero_rows = 0;
         if (M) {
-            dispersion_kernel<<<grid_for(M, kThreads, sm), kThreads, 0, st>>>(M, plan->row_offsets.ptr, enc_ptr.ptr, ukeys.ptr, counts.ptr,
+            dispersion_kernel<<<grid_for((uint64_t)M * 32, kThreads, sm), kThreads, 0, st>>>(M, plan->row_offsets.ptr, enc_ptr.ptr, enc_blk.ptr, counts.ptr,
                                                                              block_size, bd, kept_mask, disp.ptr, row_sq.ptr);
             // stable ascending sort of the rows by dispersion (:1055-1062)
             BSMR_CUDA_OK(cudaMemcpyAsync(dk_a.ptr, disp.ptr, static_cast<size_t>(M) * 4, cudaMemcpyDeviceToDevice, st));
@@ -467,7 +498,7 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
         }
 
         // ---- clustering ----
-        DevBuf<uint32_t> cluster_ids, cand_a, cand_b, first_join, num_clusters_d;
+        TmpBuf<uint32_t> cluster_ids(ws), cand_a(ws), cand_b(ws), first_join(ws), num_clusters_d(ws);
         BSMR_TRY(cluster_ids.alloc(M ? M : 1)); BSMR_TRY(cand_a.alloc(M ? M : 1)); BSMR_TRY(cand_b.alloc(M ? M : 1));
         BSMR_TRY(first_join.alloc(4)); BSMR_TRY(num_clusters_d.alloc(1));
         BSMR_CUDA_OK(cudaMemsetAsync(num_clusters_d.ptr, 0, 4, st));
@@ -479,7 +510,7 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
         if (M > zero_rows) {
             ClusterParams cp{};
             cp.M = M; cp.nb = nb; cp.bd = bd; cp.first_stride = first_stride; cp.zero_rows = zero_rows; cp.alpha = alpha;
-            cp.asc = asc; cp.enc_ptr = enc_ptr.ptr; cp.ukeys = ukeys.ptr; cp.counts = counts.ptr; cp.row_sq = row_sq.ptr;
+            cp.asc = asc; cp.enc_ptr = enc_ptr.ptr; cp.enc_blk = enc_blk.ptr; cp.counts = counts.ptr; cp.row_sq = row_sq.ptr;
             cp.cluster_ids = cluster_ids.ptr; cp.cand_a = cand_a.ptr; cp.cand_b = cand_b.ptr; cp.first_join = first_join.ptr;
             cp.num_clusters = num_clusters_d.ptr;
             BSMR_CUDA_OK(cudaFuncSetAttribute(bsa_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -500,7 +531,7 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
         }
 
         // ---- permutation = stable sort of the positions by cluster id (:986-995) ----
-        DevBuf<uint32_t> ck_b, idx_a, idx_b, perm_d;
+        TmpBuf<uint32_t> ck_b(ws), idx_a(ws), idx_b(ws), perm_d(ws);
         std::vector<uint32_t> h_sorted_ids, h_indices, h_perm;
         if (M) {
             BSMR_TRY(ck_b.alloc(M)); BSMR_TRY(idx_a.alloc(M)); BSMR_TRY(idx_b.alloc(M)); BSMR_TRY(perm_d.alloc(M));
