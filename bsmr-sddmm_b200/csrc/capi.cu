@@ -83,6 +83,9 @@ int bsmr_ctx_create(int device, void* cuda_stream, bsmr_ctx** out) {
     }
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
+    cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     // cuTensorMapEncodeTiled through the runtime: no link-time dependency on libcuda.so
     cudaDriverEntryPointQueryResult qres;
     void* fn = nullptr;
@@ -101,6 +104,9 @@ int bsmr_ctx_destroy(bsmr_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return BSMR_OK;
@@ -456,11 +462,21 @@ static int run_once(bsmr_plan* p, uint32_t K, const float* dA, const float* dB, 
                   "use BSMR_SDDMM_NO_REORDER for the CSR-order path");
         return BSMR_ERR_BAD_STATE;
     }
-    if (p->shard_tile_end > p->shard_tile_begin) {
-        BSMR_TRY(launch_dense(p, K, dA, dB, dP, p->shard_tile_begin, p->shard_tile_end));
+    // dense-block kernel on the side stream (launched first: its CTAs take their shared memory / TMEM slots,
+    // the residual CTAs fill the remaining registers and warps), residual kernel on the main stream, join.
+    const bool dense = p->shard_tile_end > p->shard_tile_begin;
+    const bool residual = p->shard_res_end > p->shard_res_begin;
+    if (dense && residual) {
+        BSMR_CUDA_OK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+        BSMR_TRY(launch_dense(p, K, dA, dB, dP, p->shard_tile_begin, p->shard_tile_end, ctx->side_stream));
+        BSMR_CUDA_OK(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+        BSMR_TRY(launch_residual(ctx, K, dA, dB, dP, p->rr_row.ptr, p->rr_col.ptr, p->rr_out.ptr, p->shard_res_begin, p->shard_res_end));
+        BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        return BSMR_OK;
     }
-    return launch_residual(ctx, K, dA, dB, dP, p->rr_row.ptr, p->rr_col.ptr, p->rr_out.ptr, p->shard_res_begin,
-                           p->shard_res_end);
+    if (dense) return launch_dense(p, K, dA, dB, dP, p->shard_tile_begin, p->shard_tile_end, ctx->stream);
+    return launch_residual(ctx, K, dA, dB, dP, p->rr_row.ptr, p->rr_col.ptr, p->rr_out.ptr, p->shard_res_begin, p->shard_res_end);
 }
 
 int bsmr_sddmm(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP, int iterations, uint32_t flags,
@@ -505,7 +521,7 @@ int bsmr_sddmm_profile(bsmr_plan* plan, uint32_t K, const float* dA, const float
     int s = BSMR_OK;
     cudaEventRecord(ctx->ev0, ctx->stream);
     if (plan->shard_tile_end > plan->shard_tile_begin)
-        s = launch_dense(plan, K, dA, dB, dP, plan->shard_tile_begin, plan->shard_tile_end);
+        s = launch_dense(plan, K, dA, dB, dP, plan->shard_tile_begin, plan->shard_tile_end, ctx->stream);
     cudaEventRecord(mid, ctx->stream);
     if (s == BSMR_OK)
         s = launch_residual(ctx, K, dA, dB, dP, plan->rr_row.ptr, plan->rr_col.ptr, plan->rr_out.ptr,

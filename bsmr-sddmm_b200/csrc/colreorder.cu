@@ -165,7 +165,8 @@ __global__ void scatter_cols_kernel(uint32_t num_runs, const uint32_t* __restric
 // H0: tile metadata (thread per panel)
 __global__ void tile_meta_kernel(uint32_t panels, const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ n_dense,
                                  const uint32_t* __restrict__ d_off, uint32_t* __restrict__ tile_panel,
-                                 uint32_t* __restrict__ tile_col_begin, uint32_t* __restrict__ tile_ncols) {
+                                 uint32_t* __restrict__ tile_col_begin, uint32_t* __restrict__ tile_ncols,
+                                 uint4* __restrict__ tile_meta) {
     for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < panels; p += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t nd = n_dense[p];
         const uint32_t t0 = tile_base[p];
@@ -173,6 +174,7 @@ __global__ void tile_meta_kernel(uint32_t panels, const uint32_t* __restrict__ t
             tile_panel[t] = (uint32_t)p;
             tile_col_begin[t] = d_off[p] + c;
             tile_ncols[t] = nd - c < kTileCols ? nd - c : kTileCols;
+            tile_meta[t] = make_uint4((uint32_t)p, d_off[p] + c, nd - c < kTileCols ? nd - c : kTileCols, 0u);
         }
     }
 }
@@ -440,12 +442,13 @@ int col_reorder_and_format(bsmr_plan* plan, float delta) {
     BSMR_CUDA_OK(cudaMemsetAsync(res_flag.ptr, 0, res_flag.bytes(), st));
     BSMR_TRY(plan->tile_panel.alloc(total_tiles)); BSMR_TRY(plan->tile_col_begin.alloc(total_tiles));
     BSMR_TRY(plan->tile_ncols.alloc(total_tiles));
+    BSMR_TRY(plan->tile_meta.alloc(total_tiles));
     BSMR_TRY(plan->tile_scatter.alloc(static_cast<size_t>(total_tiles) * kPanel * kTileCols));
     if (total_tiles) {
         const uint64_t n = static_cast<uint64_t>(total_tiles) * kPanel * kTileCols;
         fill_u32_kernel<<<grid_for(n, kThreads, sm), kThreads, 0, st>>>(plan->tile_scatter.ptr, n, kNull);
         tile_meta_kernel<<<grid_for(panels, kThreads, sm), kThreads, 0, st>>>(panels, tile_base.ptr, n_dense.ptr, d_off.ptr,
-                                                                              plan->tile_panel.ptr, plan->tile_col_begin.ptr, plan->tile_ncols.ptr);
+                                                                              plan->tile_panel.ptr, plan->tile_col_begin.ptr, plan->tile_ncols.ptr, plan->tile_meta.ptr);
         ctx->launches += 2;
     }
     if (num_runs) {

@@ -153,6 +153,10 @@ struct bsmr_ctx {
     std::string device_name;
     uint64_t launches = 0;  // kernels of this library launched through this context
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // the dense-block kernel runs on a side stream so that it overlaps the residual kernel
+    // (the reference also uses one stream per kernel, src/sddmmKernel.cu:2555-2559)
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // tensor-map encoder resolved at runtime (no link-time dependency on libcuda)
     void* encode_tiled = nullptr;
     bsmr::Workspace ws;     // scratch of the reorder passes
@@ -196,6 +200,7 @@ struct bsmr_plan {
     bsmr::DevBuf<uint32_t> tile_col_begin; // offset into dense_cols
     bsmr::DevBuf<uint32_t> tile_ncols;     // 16..128
     bsmr::DevBuf<uint32_t> tile_scatter;   // [tile][16 rows][128 cols] CSR index or NULL
+    bsmr::DevBuf<uint4> tile_meta;         // {panel, col_begin, ncols, 0}: what the dense kernel reads per tile
     std::vector<uint32_t> h_tile_panel;
     uint32_t num_tiles = 0;
     uint32_t num_dense_blocks = 0;
@@ -226,7 +231,7 @@ int launch_expand_rows(bsmr_ctx* ctx, uint32_t M, uint32_t nnz, const uint32_t* 
 int col_reorder_and_format(bsmr_plan* plan, float delta);
 int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flags);
 int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP,
-                 uint32_t tile_begin, uint32_t tile_end);
+                 uint32_t tile_begin, uint32_t tile_end, cudaStream_t stream);
 int evaluate_reordering(bsmr_plan* plan, float delta, bsmr_reorder_stats* stats);
 
 }  // namespace bsmr

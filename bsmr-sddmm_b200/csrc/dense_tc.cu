@@ -160,6 +160,7 @@ struct DenseParams {
     const uint32_t* tile_col_begin;
     const uint32_t* tile_ncols;
     const uint32_t* tile_scatter;
+    const uint4* tile_meta;      // {panel, first dense column (offset into dense_cols), #columns, 0} per tile
     float* P;
     uint32_t* error_flag;
     uint32_t* debug_smem;    // optional: raw copy of stage 0 of the first tile (probe / tests)
@@ -202,22 +203,31 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if (warp == 0) {
         // ================= TMA producer =================
         uint32_t stage = 0, phase = 0;
-        for (uint32_t t = p.tile_begin + blockIdx.x; t < p.tile_end; t += gridDim.x) {
-            const uint32_t panel = __ldg(p.tile_panel + t);
-            const uint32_t cb = __ldg(p.tile_col_begin + t);
-            const uint32_t nc = __ldg(p.tile_ncols + t);
-            // lane l owns dense columns 4l..4l+3 of the tile; lanes 0..3 also own panel rows 4l..4l+3
-            int4 cols = make_int4((int)p.N, (int)p.N, (int)p.N, (int)p.N);
-            const bool has_cols = lane * 4 < nc;
-            if (has_cols) cols = __ldg(reinterpret_cast<const int4*>(p.dense_cols + cb) + lane);
-            int4 rows = make_int4((int)p.M, (int)p.M, (int)p.M, (int)p.M);
+        // gather indices of a tile: lane l owns dense columns 4l..4l+3; lanes 0..3 also own panel rows 4l..4l+3.
+        // They are fetched one tile ahead, so that their (dependent, L2/DRAM latency) loads overlap the
+        // streaming of the current tile instead of draining the pipeline at every tile boundary.
+        auto fetch = [&](uint32_t t, uint32_t& nc, int4& cols, int4& rows) {
+            const uint4 m = __ldg(p.tile_meta + t);
+            nc = m.z;
+            cols = make_int4((int)p.N, (int)p.N, (int)p.N, (int)p.N);
+            if (lane * 4 < nc) cols = __ldg(reinterpret_cast<const int4*>(p.dense_cols + m.y) + lane);
+            rows = make_int4((int)p.M, (int)p.M, (int)p.M, (int)p.M);
             if (lane < 4) {
-                const uint32_t r0 = panel * kPanel + lane * 4;
+                const uint32_t r0 = m.x * kPanel + lane * 4;
                 int* rp = reinterpret_cast<int*>(&rows);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (r0 + j < p.num_rows) rp[j] = (int)__ldg(p.reordered_rows + r0 + j);
             }
+        };
+        uint32_t nc = 0, nc_next = 0;
+        int4 cols, rows, cols_next, rows_next;
+        cols = rows = cols_next = rows_next = make_int4(0, 0, 0, 0);
+        uint32_t t = p.tile_begin + blockIdx.x;
+        if (t < p.tile_end) fetch(t, nc, cols, rows);
+        for (; t < p.tile_end; t += gridDim.x) {
+            if (t + gridDim.x < p.tile_end) fetch(t + gridDim.x, nc_next, cols_next, rows_next);
+            const bool has_cols = lane * 4 < nc;
             const uint32_t tx_bytes = (nc / 4) * 512u + kATileBytes;
             for (uint32_t kc = 0; kc < num_chunks; ++kc) {
                 mbar_wait(&tail->empty[stage], phase ^ 1, p.error_flag, 1);
@@ -245,6 +255,9 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 }
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
+            nc = nc_next;
+            cols = cols_next;
+            rows = rows_next;
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
@@ -321,7 +334,7 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         uint32_t it = 0;
         for (uint32_t t = p.tile_begin + blockIdx.x; t < p.tile_end; t += gridDim.x, ++it) {
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            const uint32_t nc = __ldg(p.tile_ncols + t);
+            const uint32_t nc = __ldg(p.tile_meta + t).z;
             const bool active = quarter * 32 < nc;
             uint32_t idx[kPanel];
             if (active) {
@@ -393,7 +406,8 @@ int make_row_gather_map(bsmr_ctx* ctx, const float* base, uint64_t rows, uint64_
 static uint32_t* g_debug_smem = nullptr;
 extern "C" void bsmr_debug_set_dense_smem_dump(uint32_t* device_buffer) { g_debug_smem = device_buffer; }
 
-int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP, uint32_t tile_begin, uint32_t tile_end) {
+int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP, uint32_t tile_begin, uint32_t tile_end,
+                 cudaStream_t stream) {
     bsmr_ctx* ctx = plan->ctx;
     if (tile_end <= tile_begin) return BSMR_OK;
     if (K % 4 != 0 || (reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(dB)) % 16 != 0) {
@@ -424,6 +438,7 @@ int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, 
     p.tile_col_begin = plan->tile_col_begin.ptr;
     p.tile_ncols = plan->tile_ncols.ptr;
     p.tile_scatter = plan->tile_scatter.ptr;
+    p.tile_meta = plan->tile_meta.ptr;
     p.P = dP;
     p.error_flag = error_flag.ptr;
     p.debug_smem = g_debug_smem;
@@ -434,7 +449,7 @@ int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, 
     const uint32_t tiles = tile_end - tile_begin;
     const uint32_t max_ctas = static_cast<uint32_t>(ctx->sm_count) * 2;  // 2 CTAs (2 x 94 KB smem, 2 x 32 TMEM columns) per SM
     const uint32_t grid = tiles < max_ctas ? tiles : max_ctas;
-    dense_sddmm_kernel<<<grid, kDenseThreads, kDenseSmemBytes, ctx->stream>>>(map_a, map_b, p);
+    dense_sddmm_kernel<<<grid, kDenseThreads, kDenseSmemBytes, stream>>>(map_a, map_b, p);
     ctx->launches++;
     BSMR_CUDA_OK(cudaGetLastError());
     return BSMR_OK;

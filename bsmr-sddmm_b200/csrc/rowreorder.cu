@@ -150,6 +150,8 @@ struct ClusterParams {
     uint32_t bd;           // CTA size the REFERENCE would use (src/rowReordering.cu:911-920); defines the sum order
     uint32_t first_stride; // first stride of the shared-memory tree (bd/64 in the reference)
     uint32_t zero_rows;    // leading empty rows (cluster 0)
+    uint32_t list_cap;     // entries per candidate list (= M - zero_rows)
+    uint32_t num_slots;    // gridDim.x + 1 candidate lists in rotation
     float alpha;
     const uint32_t* asc;       // position -> row
     const uint32_t* enc_ptr;   // row -> first run
@@ -157,10 +159,9 @@ struct ClusterParams {
     const uint32_t* counts;    // run -> nnz in the block
     const uint32_t* row_sq;    // row -> (lossy) sum of squares
     uint32_t* cluster_ids;     // position -> cluster id (pre-set: 0 for empty rows, NULL otherwise)
-    uint32_t* cand_a;          // candidate lists (positions), double buffered
-    uint32_t* cand_b;
-    uint32_t* first_join;      // 3 slots
-    uint32_t* num_clusters;    // out
+    uint32_t* lists;           // num_slots x list_cap positions; list of cluster c lives in slot c % num_slots
+    unsigned long long* ctrl;  // per slot: list id << 33 | entries << 1 | producer-done   (single writer, release-published)
+    uint32_t* status;          // [0] = number of clusters (set once), [1] = finished flag, [2] = abort (watchdog)
 };
 
 // block reduction with the reference's structure, executed by threads [0, bd) of the CTA
@@ -185,20 +186,50 @@ __device__ __forceinline__ T ref_block_reduce(T value, T* shm, uint32_t bd, uint
     return r;
 }
 
+// Control word of a candidate list.
+__device__ __forceinline__ unsigned long long make_ctrl(uint32_t id, uint32_t count, uint32_t done) {
+    return ((unsigned long long)id << 33) | ((unsigned long long)count << 1) | done;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// BSA clustering as a PIPELINE of clusters, one CTA (32 warps) per live cluster.
+//
+// The reference chains its cluster CTAs with one mutex per row (hand-over-hand, src/rowReordering.cu:347-357,
+// 427-430): cluster c+1 may look at a row only after cluster c has passed it.  Equivalently, cluster c+1 consumes
+// -- in order -- exactly the rows cluster c rejected, and its representative is the first of them.  Here that stream
+// is explicit: cluster c appends the rows it rejects to list c+1 and publishes the length with a release store;
+// the CTA that owns cluster c+1 polls the control word and evaluates whatever has arrived.  CTA b owns clusters
+// b+1, b+1+G, b+1+2G, ... (G = gridDim.x, all CTAs co-resident: cooperative launch), so a cluster's parent is always
+// owned by a CTA that is running or done -- the chain cannot deadlock -- and G+1 list buffers suffice.
+// Inside a CTA every step evaluates up to 32*cpw of the arrived candidates in parallel (one warp per candidate,
+// cpw candidates per warp) against the current representative; the first that joins is absorbed, the ones before it
+// are rejected (appended to the child's list), the ones after it are re-evaluated against the new representative.
+// cpw doubles after a step without a join and falls back to 1 after a join.
+// A candidate that shares no column block with the representative has min-sum 0, i.e. similarity 0 <= alpha, and is
+// rejected after one pass over its block list (alpha >= 0 only).
 __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(ClusterParams p) {
-    cg::grid_group grid = cg::this_grid();
     extern __shared__ uint32_t smem[];
     uint32_t* rep = smem;                                        // [nb]  representative encoding
     float* repn = reinterpret_cast<float*>(smem + p.nb);         // [nb]  (float)rep / norm_rep
     float* warp_max = repn + p.nb;                               // [32]  per-reference-warp max partial of the representative alone
     uint32_t* red_u = reinterpret_cast<uint32_t*>(warp_max + 32);  // [32]
-    float* red_f = reinterpret_cast<float*>(red_u + 32);         // [32]
     __shared__ uint32_t s_sq_rep;
+    __shared__ unsigned long long s_ctrl;
+    __shared__ uint32_t s_joined[8];       // bit k: candidate k of the step joins (up to 256 candidates)
+    __shared__ uint32_t s_stop;
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
-    const uint32_t gwarp = blockIdx.x * (kClusterThreads / 32) + (tid >> 5);
-    const uint32_t W = gridDim.x * (kClusterThreads / 32);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t nw = p.bd >> 5;
+    const bool prune = p.alpha >= 0.0f;
+    constexpr uint32_t kMaxCpw = 8;
+    constexpr uint32_t kWarps = kClusterThreads / 32;
 
     // refresh everything derived from `rep` (called by the whole CTA after rep changed)
     auto refresh = [&]() {
@@ -222,8 +253,6 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
         if (lane == 0 && tid < p.bd) warp_max[tid >> 5] = mx;
         __syncthreads();
     };
-
-    // add row `row`'s encoding into rep (whole CTA)
     auto absorb = [&](uint32_t row, bool assign) {
         const uint32_t b = p.enc_ptr[row], e = p.enc_ptr[row + 1];
         if (assign)
@@ -232,128 +261,195 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
         for (uint32_t j = b + tid; j < e; j += kClusterThreads) rep[p.enc_blk[j]] += p.counts[j];
         __syncthreads();
     };
-
-    uint32_t* cand = p.cand_a;
-    uint32_t* next = p.cand_b;
-    uint32_t n_un = p.M - p.zero_rows;  // candidates in `cand` (positions zero_rows .. M-1 initially, written by the host side)
-    uint32_t cluster = 0;
-    uint32_t step = 0;
-
-    while (n_un > 0) {
-        ++cluster;
-        const uint32_t start_pos = cand[0];
-        if (blockIdx.x == 0 && tid == 0) p.cluster_ids[start_pos] = cluster;
-        absorb(p.asc[start_pos], true);
-        refresh();
-        uint32_t cursor = 1, out = 0;
-        while (cursor < n_un) {
-            const uint32_t slot = step % 3;
-            // ---- evaluate one candidate per warp ----
-            const uint32_t ci = cursor + gwarp;
-            uint32_t my_pos = kInf;
-            if (ci < n_un) {
-                my_pos = cand[ci];
-                const uint32_t row = p.asc[my_pos];
-                const uint32_t s_cmp = p.row_sq[row];
-                const uint32_t s_rep = s_sq_rep;
-                float sim;
-                if (s_rep == 0 && s_cmp == 0) {
-                    sim = 1.0f;
-                } else if (s_rep == 0 || s_cmp == 0) {
-                    sim = 0.0f;
-                } else {
-                    const float nc = sqrtf((float)s_cmp);
-                    const uint32_t b = p.enc_ptr[row], e = p.enc_ptr[row + 1];
-                    // which reference warps own a non-zero block of this row
-                    uint32_t touched = 0;
-                    for (uint32_t j = b + lane; j < e; j += 32) touched |= 1u << ((p.enc_blk[j] % p.bd) >> 5);
-                    touched = __reduce_or_sync(0xffffffffu, touched);
-                    float my_min = 0.f, my_max = lane < nw ? warp_max[lane] : 0.f;  // lane w = reference warp w
-                    while (touched) {
-                        const uint32_t w = __ffs(touched) - 1;
-                        touched &= touched - 1;
-                        // this lane emulates reference thread t = w*32 + lane: terms i = t, t+bd, ... ascending.
-                        // The 32 threads of the warp own 32 CONSECUTIVE blocks per term, i.e. one contiguous slice of
-                        // the row's sorted block list: one cooperative search + one coalesced load per term.
-                        float acc_min = 0.f, acc_max = 0.f;
-                        uint32_t lo = b;
-                        for (uint32_t base = w << 5; base < p.nb; base += p.bd) {
-                            lo = warp_lower_bound(p.enc_blk, lo, e, base, lane);
-                            const uint32_t x = lo + lane;
-                            const uint32_t blk_x = x < e ? p.enc_blk[x] : 0xFFFFFFFFu;
-                            const bool in = blk_x < base + 32;
-                            const uint32_t cnt_x = in ? p.counts[x] : 0u;
-                            const uint32_t has = __reduce_or_sync(0xffffffffu, in ? 1u << (blk_x - base) : 0u);
-                            const uint32_t cnt = __shfl_sync(0xffffffffu, cnt_x, __popc(has & ((1u << lane) - 1u)));
-                            const uint32_t i = base + lane;
-                            if (i < p.nb) {
-                                const float a = repn[i];
-                                if ((has >> lane) & 1u) {
-                                    const float c = (float)cnt / nc;
-                                    acc_min += fminf(a, c);
-                                    acc_max += fmaxf(a, c);
-                                } else {
-                                    acc_max += a;
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int x = 1; x < 32; x <<= 1) {
-                            acc_min += __shfl_xor_sync(0xffffffffu, acc_min, x);
-                            acc_max += __shfl_xor_sync(0xffffffffu, acc_max, x);
-                        }
-                        if (lane == w) {
-                            my_min = acc_min;
-                            my_max = acc_max;
-                        }
+    // does this candidate join the current representative?  (one warp; every lane returns the same answer)
+    auto evaluate = [&](uint32_t row) -> bool {
+        const uint32_t s_cmp = p.row_sq[row];
+        const uint32_t s_rep = s_sq_rep;
+        if (s_rep == 0 && s_cmp == 0) return 1.0f > p.alpha;       // :258-260
+        if (s_rep == 0 || s_cmp == 0) return 0.0f > p.alpha;       // :261-263
+        const uint32_t b = p.enc_ptr[row], e = p.enc_ptr[row + 1];
+        // which reference warps own a non-zero block of this row; does the row share a block with the representative
+        uint32_t touched = 0, shared = 0;
+        for (uint32_t j = b + lane; j < e; j += 32) {
+            const uint32_t blk = p.enc_blk[j];
+            touched |= 1u << ((blk % p.bd) >> 5);
+            shared |= rep[blk];
+        }
+        if (prune && !__any_sync(0xffffffffu, shared != 0)) return false;   // min-sum is exactly 0
+        touched = __reduce_or_sync(0xffffffffu, touched);
+        const float nc = sqrtf((float)s_cmp);
+        float my_min = 0.f, my_max = lane < nw ? warp_max[lane] : 0.f;  // lane w = reference warp w
+        while (touched) {
+            const uint32_t w = __ffs(touched) - 1;
+            touched &= touched - 1;
+            // this lane emulates reference thread t = w*32 + lane: terms i = t, t+bd, ... ascending.  The 32 threads of
+            // the warp own 32 CONSECUTIVE blocks per term, i.e. one contiguous slice of the row's sorted block list:
+            // one cooperative search + one coalesced load per term.
+            float acc_min = 0.f, acc_max = 0.f;
+            uint32_t lo = b;
+            for (uint32_t base = w << 5; base < p.nb; base += p.bd) {
+                lo = warp_lower_bound(p.enc_blk, lo, e, base, lane);
+                const uint32_t x = lo + lane;
+                const uint32_t blk_x = x < e ? p.enc_blk[x] : 0xFFFFFFFFu;
+                const bool in = blk_x < base + 32;
+                const uint32_t cnt_x = in ? p.counts[x] : 0u;
+                const uint32_t has = __reduce_or_sync(0xffffffffu, in ? 1u << (blk_x - base) : 0u);
+                const uint32_t cnt = __shfl_sync(0xffffffffu, cnt_x, __popc(has & ((1u << lane) - 1u)));
+                const uint32_t i = base + lane;
+                if (i < p.nb) {
+                    const float a = repn[i];
+                    if ((has >> lane) & 1u) {
+                        const float c = (float)cnt / nc;
+                        acc_min += fminf(a, c);
+                        acc_max += fmaxf(a, c);
+                    } else {
+                        acc_max += a;
                     }
-                    // shared-memory tree of the reference over the per-warp values (lossy for odd warp counts)
-                    for (uint32_t stride = p.first_stride; stride >= 1; stride >>= 1) {
-                        const float tmin = __shfl_down_sync(0xffffffffu, my_min, stride);
-                        const float tmax = __shfl_down_sync(0xffffffffu, my_max, stride);
-                        if (lane < stride && lane + stride < 32) {
-                            my_min += tmin;
-                            my_max += tmax;
-                        }
-                    }
-                    sim = __shfl_sync(0xffffffffu, my_min, 0) / __shfl_sync(0xffffffffu, my_max, 0);
                 }
-                if (lane == 0 && sim > p.alpha) atomicMin(p.first_join + slot, ci);
             }
-            grid.sync();
-            const uint32_t fj = *((volatile uint32_t*)(p.first_join + slot));
-            // slot used by the previous step is free again once everybody passed this barrier
-            if (blockIdx.x == 0 && tid == 0) p.first_join[(step + 2) % 3] = kInf;
-            ++step;
-            const uint32_t end_rejected = fj == kInf ? min(cursor + W, n_un) : fj;
-            if (my_pos != kInf && ci < end_rejected && lane == 0) next[out + (ci - cursor)] = my_pos;
-            out += end_rejected - cursor;
-            if (fj == kInf) {
-                cursor = end_rejected;
-            } else {
-                const uint32_t jpos = cand[fj];
-                if (blockIdx.x == 0 && tid == 0) p.cluster_ids[jpos] = cluster;
-                absorb(p.asc[jpos], false);
-                refresh();
-                cursor = fj + 1;
+#pragma unroll
+            for (int x = 1; x < 32; x <<= 1) {
+                acc_min += __shfl_xor_sync(0xffffffffu, acc_min, x);
+                acc_max += __shfl_xor_sync(0xffffffffu, acc_max, x);
+            }
+            if (lane == w) {
+                my_min = acc_min;
+                my_max = acc_max;
             }
         }
-        // next cluster works on the rejected rows, in order
-        grid.sync();
-        uint32_t* t = cand;
-        cand = next;
-        next = t;
-        n_un = out;
+        // shared-memory tree of the reference over the per-warp values (lossy for odd warp counts)
+        for (uint32_t stride = p.first_stride; stride >= 1; stride >>= 1) {
+            const float tmin = __shfl_down_sync(0xffffffffu, my_min, stride);
+            const float tmax = __shfl_down_sync(0xffffffffu, my_max, stride);
+            if (lane < stride && lane + stride < 32) {
+                my_min += tmin;
+                my_max += tmax;
+            }
+        }
+        const float sim = __shfl_sync(0xffffffffu, my_min, 0) / __shfl_sync(0xffffffffu, my_max, 0);
+        return sim > p.alpha;
+    };
+    // thread 0 polls the control word of list `id` until it belongs to that list and (has > have entries or is done);
+    // returns false when the run is over (no such list will ever exist) or the watchdog fired
+    auto poll = [&](uint32_t id, uint32_t have) -> bool {
+        if (tid == 0) {
+            const unsigned long long* cw = p.ctrl + (id % p.num_slots);
+            uint32_t spins = 0;
+            unsigned long long v, t0 = 0;
+            uint32_t stop = 0;
+            for (;;) {
+                v = ld_acquire_u64(cw);
+                if ((uint32_t)(v >> 33) == id && ((uint32_t)((v >> 1) & 0xFFFFFFFFu) > have || (v & 1ull))) break;
+                if (((volatile uint32_t*)p.status)[1] | ((volatile uint32_t*)p.status)[2]) { stop = 1; break; }
+                if ((++spins & 1023u) == 0) {                 // watchdog: a stalled pipeline must end as an error, not hang
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t0 == 0) t0 = now;
+                    if (now - t0 > 120ull * 1000000000ull) { atomicExch(p.status + 2, 1u); stop = 1; break; }
+                }
+                __nanosleep(spins < 64 ? 20 : 200);
+            }
+            s_ctrl = v;
+            s_stop = stop;
+        }
+        __syncthreads();
+        const bool ok = s_stop == 0;
+        __syncthreads();
+        return ok;
+    };
+
+    for (uint32_t c = blockIdx.x + 1;; c += gridDim.x) {
+        const uint32_t* in = p.lists + (size_t)(c % p.num_slots) * p.list_cap;
+        uint32_t* out = p.lists + (size_t)((c + 1) % p.num_slots) * p.list_cap;
+        unsigned long long* out_ctrl = p.ctrl + ((c + 1) % p.num_slots);
+        if (!poll(c, 0)) return;
+        uint32_t avail = (uint32_t)((s_ctrl >> 1) & 0xFFFFFFFFu);
+        bool in_done = (s_ctrl & 1ull) != 0;
+        if (avail == 0) {
+            // the parent rejected nothing: cluster c does not exist and the run is over
+            if (tid == 0) {
+                p.status[0] = c - 1;
+                __threadfence();
+                atomicExch(p.status + 1, 1u);
+            }
+            return;
+        }
+        if (tid == 0) st_release_u64(out_ctrl, make_ctrl(c + 1, 0, 0));
+        const uint32_t start_pos = __ldcg(in);
+        if (tid == 0) p.cluster_ids[start_pos] = c;
+        absorb(p.asc[start_pos], true);
+        refresh();
+        uint32_t cursor = 1, produced = 0, cpw = 1;
+        for (;;) {
+            if (cursor >= avail) {
+                if (in_done) break;
+                if (!poll(c, cursor)) return;
+                avail = (uint32_t)((s_ctrl >> 1) & 0xFFFFFFFFu);
+                in_done = (s_ctrl & 1ull) != 0;
+                continue;
+            }
+            const uint32_t take = min(avail - cursor, kWarps * cpw);
+            if (tid < 8) s_joined[tid] = 0;
+            __syncthreads();
+            uint32_t my_pos[kMaxCpw];
+#pragma unroll
+            for (uint32_t q = 0; q < kMaxCpw; ++q) {
+                const uint32_t k = q * kWarps + wid;        // candidate k of this step: interleaved over the warps
+                my_pos[q] = 0xFFFFFFFFu;
+                if (q < cpw && k < take) {
+                    my_pos[q] = __ldcg(in + cursor + k);
+                    if (evaluate(p.asc[my_pos[q]]) && lane == 0) atomicOr(&s_joined[k >> 5], 1u << (k & 31));
+                }
+            }
+            __syncthreads();
+            uint32_t fj = 0xFFFFFFFFu;
+#pragma unroll
+            for (int i = 7; i >= 0; --i)
+                if (s_joined[i]) fj = i * 32 + (__ffs(s_joined[i]) - 1);
+            const uint32_t n_rej = fj == 0xFFFFFFFFu ? take : fj;
+#pragma unroll
+            for (uint32_t q = 0; q < kMaxCpw; ++q) {
+                const uint32_t k = q * kWarps + wid;
+                if (q < cpw && k < n_rej && lane == 0) out[produced + k] = my_pos[q];
+            }
+            produced += n_rej;
+            __syncthreads();                                  // all list stores issued ...
+            if (tid == 0) {
+                __threadfence();                              // ... and ordered before the new length becomes visible
+                st_release_u64(out_ctrl, make_ctrl(c + 1, produced, 0));
+            }
+            if (fj == 0xFFFFFFFFu) {
+                cursor += take;
+                if (cpw < kMaxCpw) cpw <<= 1;
+            } else {
+                const uint32_t jpos = __ldcg(in + cursor + fj);
+                if (tid == 0) p.cluster_ids[jpos] = c;
+                absorb(p.asc[jpos], false);
+                refresh();
+                cursor += fj + 1;
+                cpw = 1;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            st_release_u64(out_ctrl, make_ctrl(c + 1, produced, 1));
+        }
     }
-    if (blockIdx.x == 0 && tid == 0) *p.num_clusters = cluster;
 }
 
-__global__ void init_cluster_state_kernel(uint32_t M, uint32_t zero_rows, uint32_t* cluster_ids, uint32_t* cand, uint32_t* first_join) {
+__global__ void init_cluster_state_kernel(uint32_t M, uint32_t zero_rows, uint32_t num_slots, uint32_t* cluster_ids, uint32_t* list1,
+                                          unsigned long long* ctrl, uint32_t* status) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
         cluster_ids[i] = i < zero_rows ? 0u : kInf;
-        if (i >= zero_rows) cand[i - zero_rows] = (uint32_t)i;
+        if (i >= zero_rows) list1[i - zero_rows] = (uint32_t)i;      // list of cluster 1: every non-empty row, in order
     }
-    if (blockIdx.x == 0 && threadIdx.x < 3) first_join[threadIdx.x] = kInf;
+    if (blockIdx.x == 0) {
+        // list ids are >= 1, so id 0 marks "never written"; list 1 is complete from the start
+        for (uint32_t sidx = threadIdx.x; sidx < num_slots; sidx += blockDim.x)
+            ctrl[sidx] = sidx == (1 % num_slots) ? (((unsigned long long)1 << 33) | ((unsigned long long)(M - zero_rows) << 1) | 1ull) : 0ull;
+        if (threadIdx.x < 4) status[threadIdx.x] = 0;
+    }
 }
 
 int bits_for(uint64_t max_value) {
@@ -421,7 +517,7 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
                 for (uint32_t w = 0; w < s; ++w) contrib[w] |= contrib[w + s];
             kept_mask = contrib[0];
         }
-        const size_t smem = (static_cast<size_t>(nb) * 2 + 96) * 4;
+        const size_t smem = (static_cast<size_t>(nb) * 2 + 64) * 4;
         if (smem > 200 * 1024) {
             set_error("row reorder: %u column blocks need %zu bytes of shared memory; raise block_size", nb, smem);
             return BSMR_ERR_UNSUPPORTED;
@@ -498,21 +594,12 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
         }
 
         // ---- clustering ----
-        TmpBuf<uint32_t> cluster_ids(ws), cand_a(ws), cand_b(ws), first_join(ws), num_clusters_d(ws);
-        BSMR_TRY(cluster_ids.alloc(M ? M : 1)); BSMR_TRY(cand_a.alloc(M ? M : 1)); BSMR_TRY(cand_b.alloc(M ? M : 1));
-        BSMR_TRY(first_join.alloc(4)); BSMR_TRY(num_clusters_d.alloc(1));
-        BSMR_CUDA_OK(cudaMemsetAsync(num_clusters_d.ptr, 0, 4, st));
+        TmpBuf<uint32_t> cluster_ids(ws), lists(ws), status(ws);
+        TmpBuf<unsigned long long> ctrl(ws);
+        BSMR_TRY(cluster_ids.alloc(M ? M : 1));
+        BSMR_TRY(status.alloc(4));
         uint32_t clusters_true = 0;
-        if (M) {
-            init_cluster_state_kernel<<<grid_for(M, kThreads, sm), kThreads, 0, st>>>(M, zero_rows, cluster_ids.ptr, cand_a.ptr, first_join.ptr);
-            ctx->launches++;
-        }
         if (M > zero_rows) {
-            ClusterParams cp{};
-            cp.M = M; cp.nb = nb; cp.bd = bd; cp.first_stride = first_stride; cp.zero_rows = zero_rows; cp.alpha = alpha;
-            cp.asc = asc; cp.enc_ptr = enc_ptr.ptr; cp.enc_blk = enc_blk.ptr; cp.counts = counts.ptr; cp.row_sq = row_sq.ptr;
-            cp.cluster_ids = cluster_ids.ptr; cp.cand_a = cand_a.ptr; cp.cand_b = cand_b.ptr; cp.first_join = first_join.ptr;
-            cp.num_clusters = num_clusters_d.ptr;
             BSMR_CUDA_OK(cudaFuncSetAttribute(bsa_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             int per_sm = 0;
             BSMR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bsa_cluster_kernel, kClusterThreads, smem));
@@ -520,14 +607,34 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
                 set_error("row reorder: clustering kernel does not fit on an SM (smem %zu)", smem);
                 return BSMR_ERR_UNSUPPORTED;
             }
-            // never more warps than candidates: small inputs run on few CTAs (cheaper grid barrier)
-            int grid = sm;
-            const uint32_t need = (M - zero_rows + 31) / 32;
-            if (static_cast<uint32_t>(grid) > need) grid = static_cast<int>(need ? need : 1);
+            // one CTA per live cluster; never more CTAs than rows
+            int grid = sm * per_sm;
+            if (static_cast<uint32_t>(grid) > M - zero_rows) grid = static_cast<int>(M - zero_rows);
+            const uint32_t num_slots = static_cast<uint32_t>(grid) + 1;
+            const uint32_t list_cap = M - zero_rows;
+            BSMR_TRY(lists.alloc(static_cast<size_t>(num_slots) * list_cap));
+            BSMR_TRY(ctrl.alloc(num_slots));
+            init_cluster_state_kernel<<<grid_for(M, kThreads, sm), kThreads, 0, st>>>(
+                M, zero_rows, num_slots, cluster_ids.ptr, lists.ptr + static_cast<size_t>(1 % num_slots) * list_cap, ctrl.ptr, status.ptr);
+            ClusterParams cp{};
+            cp.M = M; cp.nb = nb; cp.bd = bd; cp.first_stride = first_stride; cp.zero_rows = zero_rows; cp.alpha = alpha;
+            cp.list_cap = list_cap; cp.num_slots = num_slots;
+            cp.asc = asc; cp.enc_ptr = enc_ptr.ptr; cp.enc_blk = enc_blk.ptr; cp.counts = counts.ptr; cp.row_sq = row_sq.ptr;
+            cp.cluster_ids = cluster_ids.ptr; cp.lists = lists.ptr; cp.ctrl = ctrl.ptr; cp.status = status.ptr;
             void* args[] = {&cp};
             BSMR_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(bsa_cluster_kernel), dim3(grid), dim3(kClusterThreads), args, smem, st));
+            ctx->launches += 2;
+            uint32_t h_status[4] = {0, 0, 0, 0};
+            BSMR_CUDA_OK(cudaMemcpyAsync(h_status, status.ptr, sizeof(h_status), cudaMemcpyDeviceToHost, st));
+            BSMR_CUDA_OK(cudaStreamSynchronize(st));
+            if (h_status[2] != 0 || h_status[1] == 0) {
+                set_error("row reorder: clustering pipeline stalled (watchdog %u, finished %u)", h_status[2], h_status[1]);
+                return BSMR_ERR_CUDA;
+            }
+            clusters_true = h_status[0];
+        } else if (M) {
+            init_cluster_state_kernel<<<grid_for(M, kThreads, sm), kThreads, 0, st>>>(M, zero_rows, 0, cluster_ids.ptr, nullptr, nullptr, status.ptr);
             ctx->launches++;
-            BSMR_CUDA_OK(cudaMemcpyAsync(&clusters_true, num_clusters_d.ptr, 4, cudaMemcpyDeviceToHost, st));
         }
 
         // ---- permutation = stable sort of the positions by cluster id (:986-995) ----
