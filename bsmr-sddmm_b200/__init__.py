@@ -45,7 +45,8 @@ class PlanInfo(C.Structure):
                 ("num_row_panels", C.c_uint32), ("num_clusters", C.c_int32), ("num_clusters_true", C.c_int32),
                 ("block_size", C.c_uint32), ("num_dense_blocks", C.c_uint32), ("num_dense_tiles", C.c_uint32),
                 ("num_dense_values", C.c_uint64), ("num_sparse_values", C.c_uint64),
-                ("row_reordering_ms", C.c_float), ("col_reordering_ms", C.c_float), ("format_build_ms", C.c_float)]
+                ("row_reordering_ms", C.c_float), ("col_reordering_ms", C.c_float), ("format_build_ms", C.c_float),
+                ("cluster_kernel_ms", C.c_float)]
 
 
 class ReorderStats(C.Structure):

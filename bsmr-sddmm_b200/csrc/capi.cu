@@ -398,6 +398,7 @@ int bsmr_plan_get_info(bsmr_plan* plan, bsmr_plan_info* info) {
     info->row_reordering_ms = plan->row_ms;
     info->col_reordering_ms = plan->col_ms;
     info->format_build_ms = plan->format_ms;
+    info->cluster_kernel_ms = plan->cluster_ms;
     return BSMR_OK;
 }
 

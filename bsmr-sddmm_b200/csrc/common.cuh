@@ -177,7 +177,7 @@ struct bsmr_plan {
     int num_clusters = 1, num_clusters_true = 1;
     uint32_t block_size = 0;
     std::vector<uint32_t> h_dispersions, h_cluster_ids;
-    float row_ms = 0.f, col_ms = 0.f, format_ms = 0.f;
+    float row_ms = 0.f, col_ms = 0.f, format_ms = 0.f, cluster_ms = 0.f;
 
     std::vector<uint32_t> h_dense_cols, h_dense_col_offsets, h_sparse_cols, h_sparse_col_offsets,
         h_sparse_value_offsets;

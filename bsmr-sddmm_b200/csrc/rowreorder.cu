@@ -104,6 +104,14 @@ __global__ void dispersion_kernel(uint32_t M, const uint32_t* __restrict__ row_o
     }
 }
 
+__global__ void pos_info_kernel(uint32_t M, const uint32_t* __restrict__ asc, const uint32_t* __restrict__ enc_ptr,
+                                const uint32_t* __restrict__ row_sq, uint4* __restrict__ info) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = asc[i];
+        info[i] = make_uint4(r, enc_ptr[r], enc_ptr[r + 1], row_sq[r]);
+    }
+}
+
 __global__ void iota_kernel(uint32_t* p, uint32_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = (uint32_t)i;
 }
@@ -152,12 +160,14 @@ struct ClusterParams {
     uint32_t zero_rows;    // leading empty rows (cluster 0)
     uint32_t list_cap;     // entries per candidate list (= M - zero_rows)
     uint32_t num_slots;    // gridDim.x + 1 candidate lists in rotation
+    uint32_t kept_mask;    // reference warps that survive the (lossy) shared-memory tree
     float alpha;
     const uint32_t* asc;       // position -> row
     const uint32_t* enc_ptr;   // row -> first run
     const uint32_t* enc_blk;   // run -> column block (ascending inside a row)
     const uint32_t* counts;    // run -> nnz in the block
     const uint32_t* row_sq;    // row -> (lossy) sum of squares
+    const uint4* pos_info;     // position -> {row, first run, end run, (lossy) sum of squares}
     uint32_t* cluster_ids;     // position -> cluster id (pre-set: 0 for empty rows, NULL otherwise)
     uint32_t* lists;           // num_slots x list_cap positions; list of cluster c lives in slot c % num_slots
     unsigned long long* ctrl;  // per slot: list id << 33 | entries << 1 | producer-done   (single writer, release-published)
@@ -218,103 +228,185 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
     extern __shared__ uint32_t smem[];
     uint32_t* rep = smem;                                        // [nb]  representative encoding
     float* repn = reinterpret_cast<float*>(smem + p.nb);         // [nb]  (float)rep / norm_rep
-    float* warp_max = repn + p.nb;                               // [32]  per-reference-warp max partial of the representative alone
-    uint32_t* red_u = reinterpret_cast<uint32_t*>(warp_max + 32);  // [32]
+    float* part_max = repn + p.nb;                               // [1024] per-reference-thread max partial of the representative alone
+    float* warp_max = part_max + 1024;                           // [32]  the same after the warp butterfly
     __shared__ uint32_t s_sq_rep;
     __shared__ unsigned long long s_ctrl;
-    __shared__ uint32_t s_joined[8];       // bit k: candidate k of the step joins (up to 256 candidates)
+    __shared__ uint32_t s_joined[2][8];    // bit k: candidate k of the step joins (up to 256 candidates); double buffered
     __shared__ uint32_t s_stop;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t nw = p.bd >> 5;
     const bool prune = p.alpha >= 0.0f;
+    // integer form of the cheap upper bound  sim <= (nnz of the row in blocks shared with the representative) / (nnz of
+    // the row), both over the blocks the reference's reduction keeps: reject when shared * 2^20 < (alpha - 1e-3) * total * 2^20
+    const float bound = p.alpha - 1e-3f;
     constexpr uint32_t kMaxCpw = 8;
     constexpr uint32_t kWarps = kClusterThreads / 32;
 
-    // refresh everything derived from `rep` (called by the whole CTA after rep changed)
+    // everything derived from `rep`; called by the whole CTA after rep changed (rep complete and visible on entry)
     auto refresh = [&]() {
-        // sum of squares: thread t of the reference CTA owns blocks t, t+bd, ...; int e*e wraps (:241-249)
+        if (tid == 0) s_sq_rep = 0;
+        __syncthreads();
+        // sum of squares: thread t of the reference CTA owns blocks t, t+bd, ...; int e*e wraps (:241-249).  Integer
+        // sums are order independent, so the reference's tree (which keeps each warp at most once) is the sum of the
+        // warp sums of the kept warps.
         uint32_t sq = 0;
         if (tid < p.bd)
             for (uint32_t i = tid; i < p.nb; i += p.bd) sq += rep[i] * rep[i];
-        sq = ref_block_reduce<uint32_t>(sq, red_u, p.bd, p.first_stride);
-        if (tid == 0) s_sq_rep = sq;
-        const float nr = sqrtf((float)sq);
-        for (uint32_t i = tid; i < p.nb; i += kClusterThreads) repn[i] = (float)rep[i] / nr;
+        sq = __reduce_add_sync(0xffffffffu, sq);
+        if (lane == 0 && tid < p.bd && ((p.kept_mask >> wid) & 1u)) atomicAdd(&s_sq_rep, sq);
         __syncthreads();
-        // per-thread max partial of the representative alone, then the butterfly (:273-282)
+        const float nr = sqrtf((float)s_sq_rep);
+        // normalised representative and, in the same pass, thread t's max partial of the representative alone (:273-282)
         float mx = 0.f;
-        if (tid < p.bd)
-            for (uint32_t i = tid; i < p.nb; i += p.bd) mx += repn[i];
+        if (tid < p.bd) {
+            for (uint32_t i = tid; i < p.nb; i += p.bd) {
+                const float v = (float)rep[i] / nr;
+                repn[i] = v;
+                mx += v;
+            }
+            part_max[tid] = mx;
+        }
 #pragma unroll
         for (int w = 1; w < 32; w <<= 1) mx += __shfl_xor_sync(0xffffffffu, mx, w);
-        if (tid < 32) warp_max[tid] = 0.f;
-        __syncthreads();
-        if (lane == 0 && tid < p.bd) warp_max[tid >> 5] = mx;
+        if (lane == 0) warp_max[wid] = tid < p.bd ? mx : 0.f;
         __syncthreads();
     };
-    auto absorb = [&](uint32_t row, bool assign) {
-        const uint32_t b = p.enc_ptr[row], e = p.enc_ptr[row + 1];
-        if (assign)
+    auto absorb = [&](uint32_t b, uint32_t e, bool assign) {
+        if (assign) {
             for (uint32_t i = tid; i < p.nb; i += kClusterThreads) rep[i] = 0;
-        __syncthreads();
+            __syncthreads();
+        }
         for (uint32_t j = b + tid; j < e; j += kClusterThreads) rep[p.enc_blk[j]] += p.counts[j];
-        __syncthreads();
     };
     // does this candidate join the current representative?  (one warp; every lane returns the same answer)
-    auto evaluate = [&](uint32_t row) -> bool {
-        const uint32_t s_cmp = p.row_sq[row];
+    auto evaluate = [&](const uint4 info) -> bool {
+        const uint32_t b = info.y, e = info.z, s_cmp = info.w;
         const uint32_t s_rep = s_sq_rep;
         if (s_rep == 0 && s_cmp == 0) return 1.0f > p.alpha;       // :258-260
         if (s_rep == 0 || s_cmp == 0) return 0.0f > p.alpha;       // :261-263
-        const uint32_t b = p.enc_ptr[row], e = p.enc_ptr[row + 1];
-        // which reference warps own a non-zero block of this row; does the row share a block with the representative
-        uint32_t touched = 0, shared = 0;
-        for (uint32_t j = b + lane; j < e; j += 32) {
-            const uint32_t blk = p.enc_blk[j];
-            touched |= 1u << ((blk % p.bd) >> 5);
-            shared |= rep[blk];
-        }
-        if (prune && !__any_sync(0xffffffffu, shared != 0)) return false;   // min-sum is exactly 0
-        touched = __reduce_or_sync(0xffffffffu, touched);
+        const uint32_t n = e - b;
         const float nc = sqrtf((float)s_cmp);
         float my_min = 0.f, my_max = lane < nw ? warp_max[lane] : 0.f;  // lane w = reference warp w
-        while (touched) {
-            const uint32_t w = __ffs(touched) - 1;
-            touched &= touched - 1;
-            // this lane emulates reference thread t = w*32 + lane: terms i = t, t+bd, ... ascending.  The 32 threads of
-            // the warp own 32 CONSECUTIVE blocks per term, i.e. one contiguous slice of the row's sorted block list:
-            // one cooperative search + one coalesced load per term.
-            float acc_min = 0.f, acc_max = 0.f;
-            uint32_t lo = b;
-            for (uint32_t base = w << 5; base < p.nb; base += p.bd) {
-                lo = warp_lower_bound(p.enc_blk, lo, e, base, lane);
-                const uint32_t x = lo + lane;
-                const uint32_t blk_x = x < e ? p.enc_blk[x] : 0xFFFFFFFFu;
-                const bool in = blk_x < base + 32;
-                const uint32_t cnt_x = in ? p.counts[x] : 0u;
-                const uint32_t has = __reduce_or_sync(0xffffffffu, in ? 1u << (blk_x - base) : 0u);
-                const uint32_t cnt = __shfl_sync(0xffffffffu, cnt_x, __popc(has & ((1u << lane) - 1u)));
-                const uint32_t i = base + lane;
-                if (i < p.nb) {
+        if (n <= 32) {
+            // ---- short block list: patch only the reference threads that own one of the row's blocks ----
+            const bool valid = lane < n;
+            const uint32_t blk = valid ? p.enc_blk[b + lane] : 0u;
+            const uint32_t cnt = valid ? p.counts[b + lane] : 0u;
+            const uint32_t t = blk % p.bd;
+            const bool kept = valid && ((p.kept_mask >> (t >> 5)) & 1u);
+            if (prune) {
+                const uint32_t sh = __reduce_add_sync(0xffffffffu, (kept && rep[blk] != 0) ? cnt : 0u);
+                const uint32_t tot = __reduce_add_sync(0xffffffffu, kept ? cnt : 0u);
+                if (sh == 0 || (float)sh < bound * (float)tot) return false;
+            }
+            // entries of the same reference thread (blk = t, t+bd, ...) form a group; its first lane sums the thread's
+            // terms in ascending block order, taking the candidate's counts from the group members (ascending lanes)
+            const uint32_t peers = __match_any_sync(0xffffffffu, valid ? t : 0xFFFF0000u + lane);
+            const bool leader = valid && lane == (uint32_t)(__ffs(peers) - 1);
+            uint32_t rest = peers;
+            float pmin = 0.f, pmax = 0.f;
+            for (uint32_t m = 0; m * p.bd < p.nb; ++m) {
+                const uint32_t i = t + m * p.bd;
+                const int q = rest ? __ffs(rest) - 1 : 0;
+                const uint32_t blk_q = __shfl_sync(0xffffffffu, blk, q);
+                const uint32_t cnt_q = __shfl_sync(0xffffffffu, cnt, q);
+                if (leader && i < p.nb) {
                     const float a = repn[i];
-                    if ((has >> lane) & 1u) {
-                        const float c = (float)cnt / nc;
-                        acc_min += fminf(a, c);
-                        acc_max += fmaxf(a, c);
+                    if (rest && blk_q == i) {
+                        const float c = (float)cnt_q / nc;
+                        pmin += fminf(a, c);
+                        pmax += fmaxf(a, c);
+                        rest &= rest - 1;
                     } else {
-                        acc_max += a;
+                        pmax += a;
                     }
                 }
             }
+            uint32_t touched = __reduce_or_sync(0xffffffffu, leader ? 1u << (t >> 5) : 0u);
+            while (touched) {
+                const uint32_t w = __ffs(touched) - 1;
+                touched &= touched - 1;
+                float leaf_min = 0.f, leaf_max = part_max[(w << 5) + lane];
+                uint32_t sel = __ballot_sync(0xffffffffu, leader && (t >> 5) == w);
+                while (sel) {
+                    const int src = __ffs(sel) - 1;
+                    sel &= sel - 1;
+                    const uint32_t tl = __shfl_sync(0xffffffffu, t & 31u, src);
+                    const float vmin = __shfl_sync(0xffffffffu, pmin, src);
+                    const float vmax = __shfl_sync(0xffffffffu, pmax, src);
+                    if (lane == tl) {
+                        leaf_min = vmin;
+                        leaf_max = vmax;
+                    }
+                }
 #pragma unroll
-            for (int x = 1; x < 32; x <<= 1) {
-                acc_min += __shfl_xor_sync(0xffffffffu, acc_min, x);
-                acc_max += __shfl_xor_sync(0xffffffffu, acc_max, x);
+                for (int x = 1; x < 32; x <<= 1) {
+                    leaf_min += __shfl_xor_sync(0xffffffffu, leaf_min, x);
+                    leaf_max += __shfl_xor_sync(0xffffffffu, leaf_max, x);
+                }
+                if (lane == w) {
+                    my_min = leaf_min;
+                    my_max = leaf_max;
+                }
             }
-            if (lane == w) {
-                my_min = acc_min;
-                my_max = acc_max;
+        } else {
+            // ---- long block list: every touched reference warp is recomputed term by term ----
+            uint32_t touched = 0, sh = 0, tot = 0;
+            for (uint32_t j = b + lane; j < e; j += 32) {
+                const uint32_t blk = p.enc_blk[j];
+                const uint32_t w = (blk % p.bd) >> 5;
+                touched |= 1u << w;
+                if ((p.kept_mask >> w) & 1u) {
+                    const uint32_t cnt = p.counts[j];
+                    tot += cnt;
+                    if (rep[blk] != 0) sh += cnt;
+                }
+            }
+            if (prune) {
+                sh = __reduce_add_sync(0xffffffffu, sh);
+                tot = __reduce_add_sync(0xffffffffu, tot);
+                if (sh == 0 || (float)sh < bound * (float)tot) return false;
+            }
+            touched = __reduce_or_sync(0xffffffffu, touched);
+            while (touched) {
+                const uint32_t w = __ffs(touched) - 1;
+                touched &= touched - 1;
+                // this lane emulates reference thread t = w*32 + lane: terms i = t, t+bd, ... ascending.  The 32 threads
+                // of the warp own 32 CONSECUTIVE blocks per term, i.e. one contiguous slice of the row's sorted block
+                // list: one cooperative search + one coalesced load per term.
+                float acc_min = 0.f, acc_max = 0.f;
+                uint32_t lo = b;
+                for (uint32_t base = w << 5; base < p.nb; base += p.bd) {
+                    lo = warp_lower_bound(p.enc_blk, lo, e, base, lane);
+                    const uint32_t x = lo + lane;
+                    const uint32_t blk_x = x < e ? p.enc_blk[x] : 0xFFFFFFFFu;
+                    const bool in = blk_x < base + 32;
+                    const uint32_t cnt_x = in ? p.counts[x] : 0u;
+                    const uint32_t has = __reduce_or_sync(0xffffffffu, in ? 1u << (blk_x - base) : 0u);
+                    const uint32_t cnt = __shfl_sync(0xffffffffu, cnt_x, __popc(has & ((1u << lane) - 1u)));
+                    const uint32_t i = base + lane;
+                    if (i < p.nb) {
+                        const float a = repn[i];
+                        if ((has >> lane) & 1u) {
+                            const float c = (float)cnt / nc;
+                            acc_min += fminf(a, c);
+                            acc_max += fmaxf(a, c);
+                        } else {
+                            acc_max += a;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int x = 1; x < 32; x <<= 1) {
+                    acc_min += __shfl_xor_sync(0xffffffffu, acc_min, x);
+                    acc_max += __shfl_xor_sync(0xffffffffu, acc_max, x);
+                }
+                if (lane == w) {
+                    my_min = acc_min;
+                    my_max = acc_max;
+                }
             }
         }
         // shared-memory tree of the reference over the per-warp values (lossy for odd warp counts)
@@ -329,6 +421,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
         const float sim = __shfl_sync(0xffffffffu, my_min, 0) / __shfl_sync(0xffffffffu, my_max, 0);
         return sim > p.alpha;
     };
+    unsigned long long s_ctrl_copy = 0;
     // thread 0 polls the control word of list `id` until it belongs to that list and (has > have entries or is done);
     // returns false when the run is over (no such list will ever exist) or the watchdog fired
     auto poll = [&](uint32_t id, uint32_t have) -> bool {
@@ -354,17 +447,21 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
         }
         __syncthreads();
         const bool ok = s_stop == 0;
+        const unsigned long long v = s_ctrl;
         __syncthreads();
+        s_ctrl_copy = v;
         return ok;
     };
 
+    if (tid < 16) s_joined[tid >> 3][tid & 7] = 0;
+    uint32_t parity = 0;
     for (uint32_t c = blockIdx.x + 1;; c += gridDim.x) {
         const uint32_t* in = p.lists + (size_t)(c % p.num_slots) * p.list_cap;
         uint32_t* out = p.lists + (size_t)((c + 1) % p.num_slots) * p.list_cap;
         unsigned long long* out_ctrl = p.ctrl + ((c + 1) % p.num_slots);
         if (!poll(c, 0)) return;
-        uint32_t avail = (uint32_t)((s_ctrl >> 1) & 0xFFFFFFFFu);
-        bool in_done = (s_ctrl & 1ull) != 0;
+        uint32_t avail = (uint32_t)((s_ctrl_copy >> 1) & 0xFFFFFFFFu);
+        bool in_done = (s_ctrl_copy & 1ull) != 0;
         if (avail == 0) {
             // the parent rejected nothing: cluster c does not exist and the run is over
             if (tid == 0) {
@@ -377,64 +474,78 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
         if (tid == 0) st_release_u64(out_ctrl, make_ctrl(c + 1, 0, 0));
         const uint32_t start_pos = __ldcg(in);
         if (tid == 0) p.cluster_ids[start_pos] = c;
-        absorb(p.asc[start_pos], true);
-        refresh();
+        {
+            const uint4 si = __ldg(p.pos_info + start_pos);
+            absorb(si.y, si.z, true);
+            __syncthreads();
+            refresh();
+        }
         uint32_t cursor = 1, produced = 0, cpw = 1;
         for (;;) {
             if (cursor >= avail) {
                 if (in_done) break;
                 if (!poll(c, cursor)) return;
-                avail = (uint32_t)((s_ctrl >> 1) & 0xFFFFFFFFu);
-                in_done = (s_ctrl & 1ull) != 0;
+                avail = (uint32_t)((s_ctrl_copy >> 1) & 0xFFFFFFFFu);
+                in_done = (s_ctrl_copy & 1ull) != 0;
                 continue;
             }
             const uint32_t take = min(avail - cursor, kWarps * cpw);
-            if (tid < 8) s_joined[tid] = 0;
-            __syncthreads();
+            // candidate k of this step goes to warp k % 32 (interleaved); fetch everything first, then evaluate
             uint32_t my_pos[kMaxCpw];
+            uint4 my_info[kMaxCpw];
 #pragma unroll
             for (uint32_t q = 0; q < kMaxCpw; ++q) {
-                const uint32_t k = q * kWarps + wid;        // candidate k of this step: interleaved over the warps
-                my_pos[q] = 0xFFFFFFFFu;
-                if (q < cpw && k < take) {
-                    my_pos[q] = __ldcg(in + cursor + k);
-                    if (evaluate(p.asc[my_pos[q]]) && lane == 0) atomicOr(&s_joined[k >> 5], 1u << (k & 31));
+                const uint32_t k = q * kWarps + wid;
+                my_pos[q] = (q < cpw && k < take) ? __ldcg(in + cursor + k) : 0xFFFFFFFFu;
+            }
+#pragma unroll
+            for (uint32_t q = 0; q < kMaxCpw; ++q)
+                if (my_pos[q] != 0xFFFFFFFFu) my_info[q] = __ldg(p.pos_info + my_pos[q]);
+#pragma unroll
+            for (uint32_t q = 0; q < kMaxCpw; ++q) {
+                if (my_pos[q] != 0xFFFFFFFFu) {
+                    const uint32_t k = q * kWarps + wid;
+                    if (evaluate(my_info[q]) && lane == 0) atomicOr(&s_joined[parity][k >> 5], 1u << (k & 31));
                 }
             }
-            __syncthreads();
+            __syncthreads();                                  // #1: all verdicts in
             uint32_t fj = 0xFFFFFFFFu;
 #pragma unroll
-            for (int i = 7; i >= 0; --i)
-                if (s_joined[i]) fj = i * 32 + (__ffs(s_joined[i]) - 1);
+            for (int i = 7; i >= 0; --i) {
+                const uint32_t bits = s_joined[parity][i];
+                if (bits) fj = i * 32 + (__ffs(bits) - 1);
+            }
             const uint32_t n_rej = fj == 0xFFFFFFFFu ? take : fj;
 #pragma unroll
             for (uint32_t q = 0; q < kMaxCpw; ++q) {
                 const uint32_t k = q * kWarps + wid;
-                if (q < cpw && k < n_rej && lane == 0) out[produced + k] = my_pos[q];
+                if (my_pos[q] != 0xFFFFFFFFu && k < n_rej && lane == 0) out[produced + k] = my_pos[q];
             }
             produced += n_rej;
-            __syncthreads();                                  // all list stores issued ...
-            if (tid == 0) {
-                __threadfence();                              // ... and ordered before the new length becomes visible
-                st_release_u64(out_ctrl, make_ctrl(c + 1, produced, 0));
+            uint4 ji = make_uint4(0, 0, 0, 0);
+            uint32_t jpos = 0;
+            if (fj != 0xFFFFFFFFu) {
+                jpos = __ldcg(in + cursor + fj);
+                ji = __ldg(p.pos_info + jpos);
             }
+            __syncthreads();                                  // #2: verdicts read by everybody, rejected rows stored
+            if (tid < 8) s_joined[parity][tid] = 0;           // next use of this buffer is two steps away
+            parity ^= 1;
+            // release: the list stores of the other threads are ordered before this store by the barrier (cumulativity)
+            if (tid == 0 && n_rej) st_release_u64(out_ctrl, make_ctrl(c + 1, produced, 0));
             if (fj == 0xFFFFFFFFu) {
                 cursor += take;
                 if (cpw < kMaxCpw) cpw <<= 1;
             } else {
-                const uint32_t jpos = __ldcg(in + cursor + fj);
                 if (tid == 0) p.cluster_ids[jpos] = c;
-                absorb(p.asc[jpos], false);
-                refresh();
+                absorb(ji.y, ji.z, false);
+                refresh();                                    // its first barrier also closes the absorb
                 cursor += fj + 1;
                 cpw = 1;
             }
         }
         __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            st_release_u64(out_ctrl, make_ctrl(c + 1, produced, 1));
-        }
+        if (tid == 0) st_release_u64(out_ctrl, make_ctrl(c + 1, produced, 1));
     }
 }
 
@@ -517,7 +628,7 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
                 for (uint32_t w = 0; w < s; ++w) contrib[w] |= contrib[w + s];
             kept_mask = contrib[0];
         }
-        const size_t smem = (static_cast<size_t>(nb) * 2 + 64) * 4;
+        const size_t smem = (static_cast<size_t>(nb) * 2 + 1024 + 32) * 4;
         if (smem > 200 * 1024) {
             set_error("row reorder: %u column blocks need %zu bytes of shared memory; raise block_size", nb, smem);
             return BSMR_ERR_UNSUPPORTED;
@@ -596,6 +707,7 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
         // ---- clustering ----
         TmpBuf<uint32_t> cluster_ids(ws), lists(ws), status(ws);
         TmpBuf<unsigned long long> ctrl(ws);
+        TmpBuf<uint4> pos_info(ws);
         BSMR_TRY(cluster_ids.alloc(M ? M : 1));
         BSMR_TRY(status.alloc(4));
         uint32_t clusters_true = 0;
@@ -616,13 +728,19 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
             BSMR_TRY(ctrl.alloc(num_slots));
             init_cluster_state_kernel<<<grid_for(M, kThreads, sm), kThreads, 0, st>>>(
                 M, zero_rows, num_slots, cluster_ids.ptr, lists.ptr + static_cast<size_t>(1 % num_slots) * list_cap, ctrl.ptr, status.ptr);
+            BSMR_TRY(pos_info.alloc(M));
+            pos_info_kernel<<<grid_for(M, kThreads, sm), kThreads, 0, st>>>(M, asc, enc_ptr.ptr, row_sq.ptr, pos_info.ptr);
+            ctx->launches++;
             ClusterParams cp{};
+            cp.kept_mask = kept_mask; cp.pos_info = pos_info.ptr;
             cp.M = M; cp.nb = nb; cp.bd = bd; cp.first_stride = first_stride; cp.zero_rows = zero_rows; cp.alpha = alpha;
             cp.list_cap = list_cap; cp.num_slots = num_slots;
             cp.asc = asc; cp.enc_ptr = enc_ptr.ptr; cp.enc_blk = enc_blk.ptr; cp.counts = counts.ptr; cp.row_sq = row_sq.ptr;
             cp.cluster_ids = cluster_ids.ptr; cp.lists = lists.ptr; cp.ctrl = ctrl.ptr; cp.status = status.ptr;
             void* args[] = {&cp};
+            BSMR_CUDA_OK(cudaEventRecord(ctx->ev0, st));
             BSMR_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(bsa_cluster_kernel), dim3(grid), dim3(kClusterThreads), args, smem, st));
+            BSMR_CUDA_OK(cudaEventRecord(ctx->ev1, st));
             ctx->launches += 2;
             uint32_t h_status[4] = {0, 0, 0, 0};
             BSMR_CUDA_OK(cudaMemcpyAsync(h_status, status.ptr, sizeof(h_status), cudaMemcpyDeviceToHost, st));
@@ -632,6 +750,7 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
                 return BSMR_ERR_CUDA;
             }
             clusters_true = h_status[0];
+            BSMR_CUDA_OK(cudaEventElapsedTime(&plan->cluster_ms, ctx->ev0, ctx->ev1));
         } else if (M) {
             init_cluster_state_kernel<<<grid_for(M, kThreads, sm), kThreads, 0, st>>>(M, zero_rows, 0, cluster_ids.ptr, nullptr, nullptr, status.ptr);
             ctx->launches++;

@@ -133,6 +133,7 @@ typedef struct {
     float row_reordering_ms;      /* BSMR::rowReorderingTime()                            */
     float col_reordering_ms;      /* BSMR::colReorderingTime()                            */
     float format_build_ms;        /* RPHM::time()                                         */
+    float cluster_kernel_ms;      /* part of row_reordering_ms spent in the clustering kernel */
 } bsmr_plan_info;
 int bsmr_plan_get_info(bsmr_plan* plan, bsmr_plan_info* info);
 

@@ -58,7 +58,7 @@ def main():
             dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
             dP = torch.zeros(nnz, device="cuda")
             out = {"workload": name, "M": M, "N": N, "nnz": nnz, "K": K, "row_ms": info_r["row_reordering_ms"], "row_wall_ms": row_wall,
-                   "clusters": info_r["num_clusters_true"], "block_size": info_r["block_size"]}
+                   "clusters": info_r["num_clusters_true"], "block_size": info_r["block_size"], "cluster_ms": info_r["cluster_kernel_ms"]}
             for delta in (0.3, 0.0):
                 for rep in range(2):
                     t0 = time.perf_counter()
