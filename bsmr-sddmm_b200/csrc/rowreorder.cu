@@ -31,6 +31,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -161,6 +162,7 @@ struct ClusterParams {
     uint32_t list_cap;     // entries per candidate list (= M - zero_rows)
     uint32_t num_slots;    // gridDim.x + 1 candidate lists in rotation
     uint32_t kept_mask;    // reference warps that survive the (lossy) shared-memory tree
+    uint32_t scratch;      // 16-bit entries of per-warp dense scratch (0 = none; else >= nb, even)
     float alpha;
     const uint32_t* asc;       // position -> row
     const uint32_t* enc_ptr;   // row -> first run
@@ -172,6 +174,7 @@ struct ClusterParams {
     uint32_t* lists;           // num_slots x list_cap positions; list of cluster c lives in slot c % num_slots
     unsigned long long* ctrl;  // per slot: list id << 33 | entries << 1 | producer-done   (single writer, release-published)
     uint32_t* status;          // [0] = number of clusters (set once), [1] = finished flag, [2] = abort (watchdog)
+    unsigned long long* trace; // [0] steps [1] candidates [2] joins [3] polls [4] poll cycles [5] eval cycles [6] update cycles [7] busy cycles
 };
 
 // block reduction with the reference's structure, executed by threads [0, bd) of the CTA
@@ -230,6 +233,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
     float* repn = reinterpret_cast<float*>(smem + p.nb);         // [nb]  (float)rep / norm_rep
     float* part_max = repn + p.nb;                               // [1024] per-reference-thread max partial of the representative alone
     float* warp_max = part_max + 1024;                           // [32]  the same after the warp butterfly
+    // per evaluating warp: the candidate's encoding expanded to nb 16-bit counts (only when p.scratch != 0)
+    uint16_t* scratch = reinterpret_cast<uint16_t*>(warp_max + 32) + (size_t)(threadIdx.x >> 5) * p.scratch;
     __shared__ uint32_t s_sq_rep;
     __shared__ unsigned long long s_ctrl;
     __shared__ uint32_t s_joined[2][8];    // bit k: candidate k of the step joins (up to 256 candidates); double buffered
@@ -370,6 +375,40 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
                 if (sh == 0 || (float)sh < bound * (float)tot) return false;
             }
             touched = __reduce_or_sync(0xffffffffu, touched);
+            if (p.scratch) {
+                // expand the row into the warp's dense scratch: every term of every reference thread is then one
+                // shared-memory read (no search); counts fit 16 bits because a count never exceeds the block size
+                for (uint32_t i = lane; i < p.scratch / 2; i += 32) reinterpret_cast<uint32_t*>(scratch)[i] = 0u;
+                __syncwarp();
+                for (uint32_t j = b + lane; j < e; j += 32) scratch[p.enc_blk[j]] = (uint16_t)p.counts[j];
+                __syncwarp();
+                while (touched) {
+                    const uint32_t w = __ffs(touched) - 1;
+                    touched &= touched - 1;
+                    float acc_min = 0.f, acc_max = 0.f;
+                    for (uint32_t i = (w << 5) + lane; i < p.nb; i += p.bd) {   // reference thread t = w*32 + lane
+                        const float a = repn[i];
+                        const uint32_t cnt = scratch[i];
+                        if (cnt) {
+                            const float c = (float)cnt / nc;
+                            acc_min += fminf(a, c);
+                            acc_max += fmaxf(a, c);
+                        } else {
+                            acc_max += a;
+                        }
+                    }
+#pragma unroll
+                    for (int x = 1; x < 32; x <<= 1) {
+                        acc_min += __shfl_xor_sync(0xffffffffu, acc_min, x);
+                        acc_max += __shfl_xor_sync(0xffffffffu, acc_max, x);
+                    }
+                    if (lane == w) {
+                        my_min = acc_min;
+                        my_max = acc_max;
+                    }
+                }
+                __syncwarp();
+            } else
             while (touched) {
                 const uint32_t w = __ffs(touched) - 1;
                 touched &= touched - 1;
@@ -455,11 +494,26 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
 
     if (tid < 16) s_joined[tid >> 3][tid & 7] = 0;
     uint32_t parity = 0;
+    unsigned long long tr_steps = 0, tr_cand = 0, tr_joins = 0, tr_polls = 0, tr_poll_cyc = 0, tr_eval_cyc = 0, tr_upd_cyc = 0;
+    const long long tr_begin = clock64();
+    auto flush_trace = [&]() {
+        if (tid == 0 && p.trace) {
+            atomicAdd(p.trace + 0, tr_steps); atomicAdd(p.trace + 1, tr_cand); atomicAdd(p.trace + 2, tr_joins);
+            atomicAdd(p.trace + 3, tr_polls); atomicAdd(p.trace + 4, tr_poll_cyc); atomicAdd(p.trace + 5, tr_eval_cyc);
+            atomicAdd(p.trace + 6, tr_upd_cyc); atomicAdd(p.trace + 7, (unsigned long long)(clock64() - tr_begin));
+        }
+    };
     for (uint32_t c = blockIdx.x + 1;; c += gridDim.x) {
         const uint32_t* in = p.lists + (size_t)(c % p.num_slots) * p.list_cap;
         uint32_t* out = p.lists + (size_t)((c + 1) % p.num_slots) * p.list_cap;
         unsigned long long* out_ctrl = p.ctrl + ((c + 1) % p.num_slots);
-        if (!poll(c, 0)) return;
+        {
+            const long long t0 = clock64();
+            const bool ok = poll(c, 0);
+            tr_poll_cyc += clock64() - t0;
+            ++tr_polls;
+            if (!ok) { flush_trace(); return; }
+        }
         uint32_t avail = (uint32_t)((s_ctrl_copy >> 1) & 0xFFFFFFFFu);
         bool in_done = (s_ctrl_copy & 1ull) != 0;
         if (avail == 0) {
@@ -469,6 +523,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
                 __threadfence();
                 atomicExch(p.status + 1, 1u);
             }
+            flush_trace();
             return;
         }
         if (tid == 0) st_release_u64(out_ctrl, make_ctrl(c + 1, 0, 0));
@@ -484,12 +539,21 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
         for (;;) {
             if (cursor >= avail) {
                 if (in_done) break;
-                if (!poll(c, cursor)) return;
+                {
+                    const long long t0 = clock64();
+                    const bool ok = poll(c, cursor);
+                    tr_poll_cyc += clock64() - t0;
+                    ++tr_polls;
+                    if (!ok) { flush_trace(); return; }
+                }
                 avail = (uint32_t)((s_ctrl_copy >> 1) & 0xFFFFFFFFu);
                 in_done = (s_ctrl_copy & 1ull) != 0;
                 continue;
             }
             const uint32_t take = min(avail - cursor, kWarps * cpw);
+            const long long tr_t0 = clock64();
+            ++tr_steps;
+            tr_cand += take;
             // candidate k of this step goes to warp k % 32 (interleaved); fetch everything first, then evaluate
             uint32_t my_pos[kMaxCpw];
             uint4 my_info[kMaxCpw];
@@ -509,6 +573,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
                 }
             }
             __syncthreads();                                  // #1: all verdicts in
+            const long long tr_t1 = clock64();
+            tr_eval_cyc += tr_t1 - tr_t0;
             uint32_t fj = 0xFFFFFFFFu;
 #pragma unroll
             for (int i = 7; i >= 0; --i) {
@@ -542,6 +608,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
                 refresh();                                    // its first barrier also closes the absorb
                 cursor += fj + 1;
                 cpw = 1;
+                ++tr_joins;
+                tr_upd_cyc += clock64() - tr_t1;
             }
         }
         __syncthreads();
@@ -628,7 +696,11 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
                 for (uint32_t w = 0; w < s; ++w) contrib[w] |= contrib[w + s];
             kept_mask = contrib[0];
         }
-        const size_t smem = (static_cast<size_t>(nb) * 2 + 1024 + 32) * 4;
+        // per-warp dense scratch for rows with more than 32 column blocks, when it fits next to the representative
+        const uint32_t scratch_entries = (nb + 7u) & ~7u;
+        const size_t base_smem = (static_cast<size_t>(nb) * 2 + 1024 + 32) * 4;
+        const bool use_scratch = block_size <= 65535u && base_smem + static_cast<size_t>(scratch_entries) * 2 * 32 <= 200 * 1024;
+        const size_t smem = base_smem + (use_scratch ? static_cast<size_t>(scratch_entries) * 2 * 32 : 0);
         if (smem > 200 * 1024) {
             set_error("row reorder: %u column blocks need %zu bytes of shared memory; raise block_size", nb, smem);
             return BSMR_ERR_UNSUPPORTED;
@@ -708,6 +780,10 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
         TmpBuf<uint32_t> cluster_ids(ws), lists(ws), status(ws);
         TmpBuf<unsigned long long> ctrl(ws);
         TmpBuf<uint4> pos_info(ws);
+        TmpBuf<unsigned long long> trace(ws);
+        const bool want_trace = std::getenv("BSMR_TRACE") != nullptr;
+        BSMR_TRY(trace.alloc(8));
+        BSMR_CUDA_OK(cudaMemsetAsync(trace.ptr, 0, trace.bytes(), st));
         BSMR_TRY(cluster_ids.alloc(M ? M : 1));
         BSMR_TRY(status.alloc(4));
         uint32_t clusters_true = 0;
@@ -732,7 +808,8 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
             pos_info_kernel<<<grid_for(M, kThreads, sm), kThreads, 0, st>>>(M, asc, enc_ptr.ptr, row_sq.ptr, pos_info.ptr);
             ctx->launches++;
             ClusterParams cp{};
-            cp.kept_mask = kept_mask; cp.pos_info = pos_info.ptr;
+            cp.trace = want_trace ? trace.ptr : nullptr;
+            cp.kept_mask = kept_mask; cp.pos_info = pos_info.ptr; cp.scratch = use_scratch ? scratch_entries : 0u;
             cp.M = M; cp.nb = nb; cp.bd = bd; cp.first_stride = first_stride; cp.zero_rows = zero_rows; cp.alpha = alpha;
             cp.list_cap = list_cap; cp.num_slots = num_slots;
             cp.asc = asc; cp.enc_ptr = enc_ptr.ptr; cp.enc_blk = enc_blk.ptr; cp.counts = counts.ptr; cp.row_sq = row_sq.ptr;
@@ -750,6 +827,14 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
                 return BSMR_ERR_CUDA;
             }
             clusters_true = h_status[0];
+            if (want_trace) {
+                unsigned long long h_tr[8];
+                BSMR_CUDA_OK(cudaMemcpy(h_tr, trace.ptr, sizeof(h_tr), cudaMemcpyDeviceToHost));
+                fprintf(stderr, "[bsmr trace] clustering: rows %u nb %u bd %u grid %d scratch %d | clusters %u steps %llu candidates %llu joins %llu "
+                                "polls %llu | Mcycles: poll %.1f eval %.1f update %.1f busy(all CTAs) %.1f\n",
+                        M, nb, bd, grid, (int)use_scratch, clusters_true, h_tr[0], h_tr[1], h_tr[2], h_tr[3], h_tr[4] / 1e6, h_tr[5] / 1e6,
+                        h_tr[6] / 1e6, h_tr[7] / 1e6);
+            }
             BSMR_CUDA_OK(cudaEventElapsedTime(&plan->cluster_ms, ctx->ev0, ctx->ev1));
         } else if (M) {
             init_cluster_state_kernel<<<grid_for(M, kThreads, sm), kThreads, 0, st>>>(M, zero_rows, 0, cluster_ids.ptr, nullptr, nullptr, status.ptr);
