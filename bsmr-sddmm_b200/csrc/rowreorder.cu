@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
     __shared__ unsigned long long s_ctrl;
     __shared__ uint32_t s_joined[2][8];    // bit k: candidate k of the step joins (up to 256 candidates); double buffered
     __shared__ uint32_t s_stop;
+    __shared__ uint32_t s_cpw;             // candidates per warp of the next step (thread 0 decides from the step's duration)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t nw = p.bd >> 5;
@@ -359,14 +360,29 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
         } else {
             // ---- long block list: every touched reference warp is recomputed term by term ----
             uint32_t touched = 0, sh = 0, tot = 0;
-            for (uint32_t j = b + lane; j < e; j += 32) {
-                const uint32_t blk = p.enc_blk[j];
-                const uint32_t w = (blk % p.bd) >> 5;
-                touched |= 1u << w;
-                if ((p.kept_mask >> w) & 1u) {
-                    const uint32_t cnt = p.counts[j];
-                    tot += cnt;
-                    if (rep[blk] != 0) sh += cnt;
+            if (p.scratch) {
+                // zero the warp's dense scratch while the first entries are in flight
+                for (uint32_t i = lane; i < p.scratch / 2; i += 32) reinterpret_cast<uint32_t*>(scratch)[i] = 0u;
+                __syncwarp();
+            }
+            for (uint32_t j0 = b + lane; j0 < e; j0 += 128) {
+                uint32_t blk4[4], cnt4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {                // four independent loads in flight per array
+                    const uint32_t j = j0 + 32 * u;
+                    blk4[u] = j < e ? __ldg(p.enc_blk + j) : 0xFFFFFFFFu;
+                    cnt4[u] = j < e ? __ldg(p.counts + j) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (blk4[u] == 0xFFFFFFFFu) continue;
+                    const uint32_t w = (blk4[u] % p.bd) >> 5;
+                    touched |= 1u << w;
+                    if ((p.kept_mask >> w) & 1u) {
+                        tot += cnt4[u];
+                        if (rep[blk4[u]] != 0) sh += cnt4[u];
+                    }
+                    if (p.scratch) scratch[blk4[u]] = (uint16_t)cnt4[u];
                 }
             }
             if (prune) {
@@ -376,11 +392,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
             }
             touched = __reduce_or_sync(0xffffffffu, touched);
             if (p.scratch) {
-                // expand the row into the warp's dense scratch: every term of every reference thread is then one
+                // the row was expanded into the warp's dense scratch above: every term of every reference thread is one
                 // shared-memory read (no search); counts fit 16 bits because a count never exceeds the block size
-                for (uint32_t i = lane; i < p.scratch / 2; i += 32) reinterpret_cast<uint32_t*>(scratch)[i] = 0u;
-                __syncwarp();
-                for (uint32_t j = b + lane; j < e; j += 32) scratch[p.enc_blk[j]] = (uint16_t)p.counts[j];
                 __syncwarp();
                 while (touched) {
                     const uint32_t w = __ffs(touched) - 1;
@@ -575,6 +588,15 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
             __syncthreads();                                  // #1: all verdicts in
             const long long tr_t1 = clock64();
             tr_eval_cyc += tr_t1 - tr_t0;
+            if (tid == 0) {
+                // a step should take a few microseconds: long steps starve the whole chain of descendants (they only
+                // receive rows when this cluster publishes), short ones waste time in barriers
+                const long long dur = tr_t1 - tr_t0;
+                uint32_t next = cpw;
+                if (dur < 6000 && cpw < kMaxCpw) next = cpw << 1;
+                else if (dur > 24000 && cpw > 1) next = cpw >> 1;
+                s_cpw = next;
+            }
             uint32_t fj = 0xFFFFFFFFu;
 #pragma unroll
             for (int i = 7; i >= 0; --i) {
@@ -601,7 +623,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
             if (tid == 0 && n_rej) st_release_u64(out_ctrl, make_ctrl(c + 1, produced, 0));
             if (fj == 0xFFFFFFFFu) {
                 cursor += take;
-                if (cpw < kMaxCpw) cpw <<= 1;
+                cpw = s_cpw;
             } else {
                 if (tid == 0) p.cluster_ids[jpos] = c;
                 absorb(ji.y, ji.z, false);
