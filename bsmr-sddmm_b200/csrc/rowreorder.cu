@@ -174,6 +174,7 @@ struct ClusterParams {
     uint32_t* lists;           // num_slots x list_cap positions; list of cluster c lives in slot c % num_slots
     unsigned long long* ctrl;  // per slot: list id << 33 | entries << 1 | producer-done   (single writer, release-published)
     uint32_t* status;          // [0] = number of clusters (set once), [1] = finished flag, [2] = abort (watchdog)
+    unsigned long long* trace_ts; // optional: per cluster {start, first publish, end} in ns (globaltimer)
     unsigned long long* trace; // [0] steps [1] candidates [2] joins [3] polls [4] poll cycles [5] eval cycles [6] update cycles [7] busy cycles
 };
 
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
     __shared__ uint32_t s_sq_rep;
     __shared__ unsigned long long s_ctrl;
     __shared__ uint32_t s_joined[2][8];    // bit k: candidate k of the step joins (up to 256 candidates); double buffered
+    __shared__ uint32_t s_inscratch[2][8]; // bit k: ... and its encoding is expanded in the evaluating warp's scratch
     __shared__ uint32_t s_stop;
     __shared__ uint32_t s_cpw;             // candidates per warp of the next step (thread 0 decides from the step's duration)
 
@@ -287,7 +289,12 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
         for (uint32_t j = b + tid; j < e; j += kClusterThreads) rep[p.enc_blk[j]] += p.counts[j];
     };
     // does this candidate join the current representative?  (one warp; every lane returns the same answer)
-    auto evaluate = [&](const uint4 info) -> bool {
+    // Scratch cache: the candidate with list index x is always evaluated by warp x % 32, so when a join shifts the window
+    // by a few rows the same warp meets the same candidate again and finds its encoding still expanded in its scratch
+    // (c_idx / c_touched, warp-uniform registers): no global loads, no refill -- this is what bounds the cost of a long
+    // run of consecutive joins.
+    uint32_t c_idx = 0xFFFFFFFFu, c_touched = 0;
+    auto evaluate = [&](const uint4 info, const uint32_t x) -> bool {
         const uint32_t b = info.y, e = info.z, s_cmp = info.w;
         const uint32_t s_rep = s_sq_rep;
         if (s_rep == 0 && s_cmp == 0) return 1.0f > p.alpha;       // :258-260
@@ -360,6 +367,10 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
         } else {
             // ---- long block list: every touched reference warp is recomputed term by term ----
             uint32_t touched = 0, sh = 0, tot = 0;
+            const bool cached = p.scratch && c_idx == x;
+            if (cached) {
+                touched = c_touched;
+            } else {
             if (p.scratch) {
                 // zero the warp's dense scratch while the first entries are in flight
                 for (uint32_t i = lane; i < p.scratch / 2; i += 32) reinterpret_cast<uint32_t*>(scratch)[i] = 0u;
@@ -385,12 +396,17 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
                     if (p.scratch) scratch[blk4[u]] = (uint16_t)cnt4[u];
                 }
             }
+            touched = __reduce_or_sync(0xffffffffu, touched);
+            if (p.scratch) {
+                c_idx = x;
+                c_touched = touched;
+            }
             if (prune) {
                 sh = __reduce_add_sync(0xffffffffu, sh);
                 tot = __reduce_add_sync(0xffffffffu, tot);
                 if (sh == 0 || (float)sh < bound * (float)tot) return false;
             }
-            touched = __reduce_or_sync(0xffffffffu, touched);
+            }
             if (p.scratch) {
                 // the row was expanded into the warp's dense scratch above: every term of every reference thread is one
                 // shared-memory read (no search); counts fit 16 bits because a count never exceeds the block size
@@ -505,10 +521,14 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
         return ok;
     };
 
-    if (tid < 16) s_joined[tid >> 3][tid & 7] = 0;
+    if (tid < 16) {
+        s_joined[tid >> 3][tid & 7] = 0;
+        s_inscratch[tid >> 3][tid & 7] = 0;
+    }
     uint32_t parity = 0;
     unsigned long long tr_steps = 0, tr_cand = 0, tr_joins = 0, tr_polls = 0, tr_poll_cyc = 0, tr_eval_cyc = 0, tr_upd_cyc = 0;
     const long long tr_begin = clock64();
+    auto now_ns = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
     auto flush_trace = [&]() {
         if (tid == 0 && p.trace) {
             atomicAdd(p.trace + 0, tr_steps); atomicAdd(p.trace + 1, tr_cand); atomicAdd(p.trace + 2, tr_joins);
@@ -540,6 +560,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
             return;
         }
         if (tid == 0) st_release_u64(out_ctrl, make_ctrl(c + 1, 0, 0));
+        if (tid == 0 && p.trace_ts && c <= p.M) { p.trace_ts[3 * c] = now_ns(); p.trace_ts[3 * c + 1] = 0; }
         const uint32_t start_pos = __ldcg(in);
         if (tid == 0) p.cluster_ids[start_pos] = c;
         {
@@ -549,6 +570,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
             refresh();
         }
         uint32_t cursor = 1, produced = 0, cpw = 1;
+        c_idx = 0xFFFFFFFFu;                                   // list indices of the previous cluster mean nothing here
         for (;;) {
             if (cursor >= avail) {
                 if (in_done) break;
@@ -567,12 +589,13 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
             const long long tr_t0 = clock64();
             ++tr_steps;
             tr_cand += take;
-            // candidate k of this step goes to warp k % 32 (interleaved); fetch everything first, then evaluate
+            // the candidate with list index x goes to warp x % 32; fetch everything first, then evaluate
             uint32_t my_pos[kMaxCpw];
             uint4 my_info[kMaxCpw];
+            const uint32_t k0 = (wid + kWarps - (cursor % kWarps)) % kWarps;     // first candidate of this step owned by this warp
 #pragma unroll
             for (uint32_t q = 0; q < kMaxCpw; ++q) {
-                const uint32_t k = q * kWarps + wid;
+                const uint32_t k = q * kWarps + k0;
                 my_pos[q] = (q < cpw && k < take) ? __ldcg(in + cursor + k) : 0xFFFFFFFFu;
             }
 #pragma unroll
@@ -581,8 +604,12 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
 #pragma unroll
             for (uint32_t q = 0; q < kMaxCpw; ++q) {
                 if (my_pos[q] != 0xFFFFFFFFu) {
-                    const uint32_t k = q * kWarps + wid;
-                    if (evaluate(my_info[q]) && lane == 0) atomicOr(&s_joined[parity][k >> 5], 1u << (k & 31));
+                    const uint32_t k = q * kWarps + k0;
+                    if (evaluate(my_info[q], cursor + k) && lane == 0) {
+                        atomicOr(&s_joined[parity][k >> 5], 1u << (k & 31));
+                        // (with several candidates per warp a later one overwrites the scratch)
+                        if (cpw == 1 && c_idx == cursor + k) atomicOr(&s_inscratch[parity][k >> 5], 1u << (k & 31));
+                    }
                 }
             }
             __syncthreads();                                  // #1: all verdicts in
@@ -606,27 +633,41 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
             const uint32_t n_rej = fj == 0xFFFFFFFFu ? take : fj;
 #pragma unroll
             for (uint32_t q = 0; q < kMaxCpw; ++q) {
-                const uint32_t k = q * kWarps + wid;
+                const uint32_t k = q * kWarps + k0;
                 if (my_pos[q] != 0xFFFFFFFFu && k < n_rej && lane == 0) out[produced + k] = my_pos[q];
             }
             produced += n_rej;
             uint4 ji = make_uint4(0, 0, 0, 0);
             uint32_t jpos = 0;
+            bool from_scratch = false;
             if (fj != 0xFFFFFFFFu) {
                 jpos = __ldcg(in + cursor + fj);
                 ji = __ldg(p.pos_info + jpos);
+                from_scratch = (s_inscratch[parity][fj >> 5] >> (fj & 31)) & 1u;
             }
             __syncthreads();                                  // #2: verdicts read by everybody, rejected rows stored
-            if (tid < 8) s_joined[parity][tid] = 0;           // next use of this buffer is two steps away
+            if (tid < 8) {                                    // next use of these buffers is two steps away
+                s_joined[parity][tid] = 0;
+                s_inscratch[parity][tid] = 0;
+            }
             parity ^= 1;
             // release: the list stores of the other threads are ordered before this store by the barrier (cumulativity)
-            if (tid == 0 && n_rej) st_release_u64(out_ctrl, make_ctrl(c + 1, produced, 0));
+            if (tid == 0 && n_rej) {
+                st_release_u64(out_ctrl, make_ctrl(c + 1, produced, 0));
+                if (p.trace_ts && c <= p.M && p.trace_ts[3 * c + 1] == 0) p.trace_ts[3 * c + 1] = now_ns();
+            }
             if (fj == 0xFFFFFFFFu) {
                 cursor += take;
                 cpw = s_cpw;
             } else {
                 if (tid == 0) p.cluster_ids[jpos] = c;
-                absorb(ji.y, ji.z, false);
+                if (from_scratch) {
+                    // the joining row is still expanded in the scratch of the warp that evaluated it
+                    const uint16_t* js = reinterpret_cast<const uint16_t*>(warp_max + 32) + (size_t)((cursor + fj) % kWarps) * p.scratch;
+                    for (uint32_t i = tid; i < p.nb; i += kClusterThreads) rep[i] += js[i];
+                } else {
+                    absorb(ji.y, ji.z, false);
+                }
                 refresh();                                    // its first barrier also closes the absorb
                 cursor += fj + 1;
                 cpw = 1;
@@ -636,6 +677,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
         }
         __syncthreads();
         if (tid == 0) st_release_u64(out_ctrl, make_ctrl(c + 1, produced, 1));
+        if (tid == 0 && p.trace_ts && c <= p.M) p.trace_ts[3 * c + 2] = now_ns();
     }
 }
 
@@ -806,6 +848,11 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
         const bool want_trace = std::getenv("BSMR_TRACE") != nullptr;
         BSMR_TRY(trace.alloc(8));
         BSMR_CUDA_OK(cudaMemsetAsync(trace.ptr, 0, trace.bytes(), st));
+        TmpBuf<unsigned long long> trace_ts(ws);
+        if (want_trace) {
+            BSMR_TRY(trace_ts.alloc(3 * (static_cast<size_t>(M) + 2)));
+            BSMR_CUDA_OK(cudaMemsetAsync(trace_ts.ptr, 0, trace_ts.bytes(), st));
+        }
         BSMR_TRY(cluster_ids.alloc(M ? M : 1));
         BSMR_TRY(status.alloc(4));
         uint32_t clusters_true = 0;
@@ -831,6 +878,7 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
             ctx->launches++;
             ClusterParams cp{};
             cp.trace = want_trace ? trace.ptr : nullptr;
+            cp.trace_ts = want_trace ? trace_ts.ptr : nullptr;
             cp.kept_mask = kept_mask; cp.pos_info = pos_info.ptr; cp.scratch = use_scratch ? scratch_entries : 0u;
             cp.M = M; cp.nb = nb; cp.bd = bd; cp.first_stride = first_stride; cp.zero_rows = zero_rows; cp.alpha = alpha;
             cp.list_cap = list_cap; cp.num_slots = num_slots;
@@ -856,6 +904,17 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
                                 "polls %llu | Mcycles: poll %.1f eval %.1f update %.1f busy(all CTAs) %.1f\n",
                         M, nb, bd, grid, (int)use_scratch, clusters_true, h_tr[0], h_tr[1], h_tr[2], h_tr[3], h_tr[4] / 1e6, h_tr[5] / 1e6,
                         h_tr[6] / 1e6, h_tr[7] / 1e6);
+                const uint32_t nc = clusters_true < M ? clusters_true : M;
+                std::vector<unsigned long long> ts(3 * (static_cast<size_t>(nc) + 1));
+                BSMR_CUDA_OK(cudaMemcpy(ts.data(), trace_ts.ptr, ts.size() * 8, cudaMemcpyDeviceToHost));
+                if (nc >= 2) {
+                    const unsigned long long t0 = ts[3];
+                    auto us = [&](unsigned long long t) { return (double)(t - t0) / 1e3; };
+                    fprintf(stderr, "[bsmr trace]   cluster: start / first publish / end (us)\n");
+                    for (uint32_t c = 1; c <= nc; c = c < 8 ? c + 1 : c + (nc / 12 ? nc / 12 : 1))
+                        fprintf(stderr, "[bsmr trace]   %6u: %10.1f %10.1f %10.1f\n", c, us(ts[3 * c]), us(ts[3 * c + 1]), us(ts[3 * c + 2]));
+                    fprintf(stderr, "[bsmr trace]   %6u: %10.1f %10.1f %10.1f\n", nc, us(ts[3 * nc]), us(ts[3 * nc + 1]), us(ts[3 * nc + 2]));
+                }
             }
             BSMR_CUDA_OK(cudaEventElapsedTime(&plan->cluster_ms, ctx->ev0, ctx->ev1));
         } else if (M) {
