@@ -293,7 +293,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
     // by a few rows the same warp meets the same candidate again and finds its encoding still expanded in its scratch
     // (c_idx / c_touched, warp-uniform registers): no global loads, no refill -- this is what bounds the cost of a long
     // run of consecutive joins.
-    uint32_t c_idx = 0xFFFFFFFFu, c_touched = 0;
+    uint32_t c_idx = 0xFFFFFFFFu, c_touched = 0, c_pos = 0;
+    uint4 c_info = make_uint4(0, 0, 0, 0);
     auto evaluate = [&](const uint4 info, const uint32_t x) -> bool {
         const uint32_t b = info.y, e = info.z, s_cmp = info.w;
         const uint32_t s_rep = s_sq_rep;
@@ -593,19 +594,25 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
             uint32_t my_pos[kMaxCpw];
             uint4 my_info[kMaxCpw];
             const uint32_t k0 = (wid + kWarps - (cursor % kWarps)) % kWarps;     // first candidate of this step owned by this warp
+            const bool hit0 = k0 < take && c_idx == cursor + k0;     // first candidate already expanded in this warp's scratch
 #pragma unroll
             for (uint32_t q = 0; q < kMaxCpw; ++q) {
                 const uint32_t k = q * kWarps + k0;
-                my_pos[q] = (q < cpw && k < take) ? __ldcg(in + cursor + k) : 0xFFFFFFFFu;
+                my_pos[q] = (q < cpw && k < take) ? ((q == 0 && hit0) ? c_pos : __ldcg(in + cursor + k)) : 0xFFFFFFFFu;
             }
 #pragma unroll
             for (uint32_t q = 0; q < kMaxCpw; ++q)
-                if (my_pos[q] != 0xFFFFFFFFu) my_info[q] = __ldg(p.pos_info + my_pos[q]);
+                if (my_pos[q] != 0xFFFFFFFFu) my_info[q] = (q == 0 && hit0) ? c_info : __ldg(p.pos_info + my_pos[q]);
 #pragma unroll
             for (uint32_t q = 0; q < kMaxCpw; ++q) {
                 if (my_pos[q] != 0xFFFFFFFFu) {
                     const uint32_t k = q * kWarps + k0;
-                    if (evaluate(my_info[q], cursor + k) && lane == 0) {
+                    const bool joins = evaluate(my_info[q], cursor + k);
+                    if (c_idx == cursor + k) {                 // evaluate() left this candidate in the scratch
+                        c_pos = my_pos[q];
+                        c_info = my_info[q];
+                    }
+                    if (joins && lane == 0) {
                         atomicOr(&s_joined[parity][k >> 5], 1u << (k & 31));
                         // (with several candidates per warp a later one overwrites the scratch)
                         if (cpw == 1 && c_idx == cursor + k) atomicOr(&s_inscratch[parity][k >> 5], 1u << (k & 31));
@@ -641,9 +648,14 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
             uint32_t jpos = 0;
             bool from_scratch = false;
             if (fj != 0xFFFFFFFFu) {
-                jpos = __ldcg(in + cursor + fj);
-                ji = __ldg(p.pos_info + jpos);
                 from_scratch = (s_inscratch[parity][fj >> 5] >> (fj & 31)) & 1u;
+                if (!from_scratch) {
+                    jpos = __ldcg(in + cursor + fj);
+                    ji = __ldg(p.pos_info + jpos);
+                }
+#pragma unroll
+                for (uint32_t q = 0; q < kMaxCpw; ++q)       // the warp that evaluated the joiner records its cluster
+                    if (my_pos[q] != 0xFFFFFFFFu && q * kWarps + k0 == fj && lane == 0) p.cluster_ids[my_pos[q]] = c;
             }
             __syncthreads();                                  // #2: verdicts read by everybody, rejected rows stored
             if (tid < 8) {                                    // next use of these buffers is two steps away
@@ -660,7 +672,6 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
                 cursor += take;
                 cpw = s_cpw;
             } else {
-                if (tid == 0) p.cluster_ids[jpos] = c;
                 if (from_scratch) {
                     // the joining row is still expanded in the scratch of the warp that evaluated it
                     const uint16_t* js = reinterpret_cast<const uint16_t*>(warp_max + 32) + (size_t)((cursor + fj) % kWarps) * p.scratch;
