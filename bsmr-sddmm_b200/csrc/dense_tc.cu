@@ -26,9 +26,11 @@
 // reference rounds to nearest (wmma::__float_to_tf32 = cvt.rna, src/sddmmKernel.cu:317-322), so
 // four converter warps round every landed stage in place with cvt.rna.tf32.f32 before the MMA
 // warp may read it (generic-proxy writes -> fence.proxy.async -> mbarrier).
-// Warp roles (10 warps): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue
-// (tcgen05.ld of the warp's 32 TMEM lanes x 16 columns, mask + scatter P[idx] = acc),
-// 6..9 = TF32 round-to-nearest converters.
+// Warp roles (13 warps): 0..3 = TMA producers (one quarter of the B-column tile each; a gather4 request takes its
+// coordinates from uniform registers, so the requests of a warp are issued one lane at a time -- ncu showed a single
+// producer warp spending ~1.7 us per stage on 36 serialised requests -- hence four issuing warps),
+// 4 = TMEM allocator + MMA issuer, 5..8 = epilogue (tcgen05.ld of the warp's 32 TMEM lanes x 16 columns, mask +
+// scatter P[idx] = acc), 9..12 = TF32 round-to-nearest converters.
 // Two TMEM accumulators (2 x 16 columns) let the epilogue of tile i overlap the MMAs of tile
 // i+1; a 5-stage smem ring (18 KB / stage) keeps ~90 KB of loads in flight per CTA.
 #include <cuda.h>
@@ -44,8 +46,11 @@ constexpr int kStages = 5;
 constexpr int kChunk = 32;                         // floats of K per stage (128 bytes)
 constexpr int kBTileBytes = kTileCols * kChunk * 4;   // 16384
 constexpr int kATileBytes = kPanel * kChunk * 4;      // 2048
-constexpr int kDenseThreads = 320;
-constexpr int kConvWarp0 = 6;                     // first converter warp
+constexpr int kProducerWarps = 4;
+constexpr int kMmaWarp = 4;
+constexpr int kEpiWarp0 = 5;
+constexpr int kConvWarp0 = 9;                     // first converter warp
+constexpr int kDenseThreads = 13 * 32;
 constexpr int kTmemCols = 32;                      // 2 accumulators x 16 fp32 columns
 constexpr uint32_t kSpinLimit = 1u << 28;
 
@@ -100,14 +105,6 @@ __device__ __forceinline__ void tma_gather4(const CUtensorMap* map, uint64_t* ba
         ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(rows.x), "r"(rows.y), "r"(rows.z), "r"(rows.w), "r"(smem_u32(bar))
         : "memory");
 }
-__device__ __forceinline__ void tma_row(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
-        : "memory");
-}
-
 __device__ __forceinline__ float rna_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -164,7 +161,6 @@ struct DenseParams {
     float* P;
     uint32_t* error_flag;
     uint32_t* debug_smem;    // optional: raw copy of stage 0 of the first tile (probe / tests)
-    int use_gather4;
 };
 
 __global__ void __launch_bounds__(kDenseThreads, 2)
@@ -191,7 +187,7 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tail->tmem_base)), "n"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -200,20 +196,22 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = tail->tmem_base;
 
-    if (warp == 0) {
-        // ================= TMA producer =================
+    if (warp < kProducerWarps) {
+        // ================= TMA producers (warps 0..3) =================
+        // Producer warp w owns B-tile rows [32w, 32w + 32): lane l < 8 issues the gather4 of dense columns
+        // 32w + 4l .. + 3; warp 0 lanes 8..11 additionally issue the four gather4 requests of the A-row tile.
+        // Lane 0 of warp 0 arms the stage's mbarrier with the byte count of ALL requests of the stage (a complete_tx
+        // that lands before the expect_tx only makes the transaction count transiently negative).
         uint32_t stage = 0, phase = 0;
-        // gather indices of a tile: lane l owns dense columns 4l..4l+3; lanes 0..3 also own panel rows 4l..4l+3.
-        // They are fetched one tile ahead, so that their (dependent, L2/DRAM latency) loads overlap the
-        // streaming of the current tile instead of draining the pipeline at every tile boundary.
         auto fetch = [&](uint32_t t, uint32_t& nc, int4& cols, int4& rows) {
             const uint4 m = __ldg(p.tile_meta + t);
             nc = m.z;
             cols = make_int4((int)p.N, (int)p.N, (int)p.N, (int)p.N);
-            if (lane * 4 < nc) cols = __ldg(reinterpret_cast<const int4*>(p.dense_cols + m.y) + lane);
+            const uint32_t c0 = warp * 32 + lane * 4;           // first dense column of this lane's request
+            if (lane < 8 && c0 < nc) cols = __ldg(reinterpret_cast<const int4*>(p.dense_cols + m.y + c0));
             rows = make_int4((int)p.M, (int)p.M, (int)p.M, (int)p.M);
-            if (lane < 4) {
-                const uint32_t r0 = m.x * kPanel + lane * 4;
+            if (warp == 0 && lane >= 8 && lane < 12) {
+                const uint32_t r0 = m.x * kPanel + (lane - 8) * 4;
                 int* rp = reinterpret_cast<int*>(&rows);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -226,40 +224,26 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         uint32_t t = p.tile_begin + blockIdx.x;
         if (t < p.tile_end) fetch(t, nc, cols, rows);
         for (; t < p.tile_end; t += gridDim.x) {
+            // indices of the next tile are fetched while this one streams (dependent L2/DRAM loads off the critical path)
             if (t + gridDim.x < p.tile_end) fetch(t + gridDim.x, nc_next, cols_next, rows_next);
-            const bool has_cols = lane * 4 < nc;
+            const bool has_cols = lane < 8 && warp * 32 + lane * 4 < nc;
+            const bool has_rows = warp == 0 && lane >= 8 && lane < 12;
             const uint32_t tx_bytes = (nc / 4) * 512u + kATileBytes;
             for (uint32_t kc = 0; kc < num_chunks; ++kc) {
                 mbar_wait(&tail->empty[stage], phase ^ 1, p.error_flag, 1);
-                if (lane == 0) mbar_arrive_expect_tx(&tail->full[stage], tx_bytes);
-                __syncwarp();
+                if (warp == 0 && lane == 0) mbar_arrive_expect_tx(&tail->full[stage], tx_bytes);
                 uint8_t* bt = b_tiles + (size_t)stage * kBTileBytes;
                 uint8_t* at = a_tiles + (size_t)stage * kATileBytes;
                 const int x = (int)(kc * kChunk);
-                if (p.use_gather4) {
-                    if (has_cols) tma_gather4(&map_b, &tail->full[stage], bt + lane * 512, x, cols);
-                    if (lane < 4) tma_gather4(&map_a, &tail->full[stage], at + lane * 512, x, rows);
-                } else {
-                    if (has_cols) {
-                        tma_row(&map_b, &tail->full[stage], bt + lane * 512 + 0, x, cols.x);
-                        tma_row(&map_b, &tail->full[stage], bt + lane * 512 + 128, x, cols.y);
-                        tma_row(&map_b, &tail->full[stage], bt + lane * 512 + 256, x, cols.z);
-                        tma_row(&map_b, &tail->full[stage], bt + lane * 512 + 384, x, cols.w);
-                    }
-                    if (lane < 4) {
-                        tma_row(&map_a, &tail->full[stage], at + lane * 512 + 0, x, rows.x);
-                        tma_row(&map_a, &tail->full[stage], at + lane * 512 + 128, x, rows.y);
-                        tma_row(&map_a, &tail->full[stage], at + lane * 512 + 256, x, rows.z);
-                        tma_row(&map_a, &tail->full[stage], at + lane * 512 + 384, x, rows.w);
-                    }
-                }
+                if (has_cols) tma_gather4(&map_b, &tail->full[stage], bt + (warp * 8 + lane) * 512, x, cols);
+                if (has_rows) tma_gather4(&map_a, &tail->full[stage], at + (lane - 8) * 512, x, rows);
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
             nc = nc_next;
             cols = cols_next;
             rows = rows_next;
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         // ================= MMA issuer =================
         const uint32_t idesc = make_idesc_tf32(kTileCols, kPanel);
         uint32_t stage = 0, phase = 0, it = 0;
@@ -295,7 +279,7 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
         }
     } else if (warp >= kConvWarp0) {
-        // ================= TF32 converters (warps 6..9) =================
+        // ================= TF32 converters (warps 9..12) =================
         // cvt.rna.tf32.f32 on every element of the landed stage, in place; element-wise, so the
         // 128-byte swizzle does not matter.  Thread i owns float4 #i, #i+128, ... of the B-column
         // tile (8 of them) and float4 #i of the A-row tile.
@@ -328,7 +312,7 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
         }
     } else {
-        // ================= epilogue (warps 2..5) =================
+        // ================= epilogue (warps 5..8) =================
         const uint32_t quarter = warp & 3;              // TMEM lanes [32*quarter, 32*quarter + 32)
         const uint32_t c = quarter * 32 + lane;         // dense column of the tile owned by this thread
         uint32_t it = 0;
@@ -368,7 +352,7 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
     }
@@ -443,9 +427,6 @@ int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, 
     p.error_flag = error_flag.ptr;
     p.debug_smem = g_debug_smem;
     g_debug_smem = nullptr;
-    const char* mode = std::getenv("BSMR_DENSE_TMA_MODE");  // "rows" = one TMA request per row instead of gather4
-    p.use_gather4 = !(mode && mode[0] == 'r');
-
     const uint32_t tiles = tile_end - tile_begin;
     const uint32_t max_ctas = static_cast<uint32_t>(ctx->sm_count) * 2;  // 2 CTAs (2 x 94 KB smem, 2 x 32 TMEM columns) per SM
     const uint32_t grid = tiles < max_ctas ? tiles : max_ctas;

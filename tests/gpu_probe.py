@@ -86,7 +86,7 @@ def main():
 
     if "--skip-dense" in sys.argv:
         return
-    for mode in ("gather4", "rows"):
+    for mode in ("gather4",):
         section("dense tcgen05 kernel, TMA mode = " + mode)
         try:
             os.environ["BSMR_DENSE_TMA_MODE"] = mode
