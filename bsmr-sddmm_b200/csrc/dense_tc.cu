@@ -31,8 +31,8 @@
 // producer warp spending ~1.7 us per stage on 36 serialised requests -- hence four issuing warps),
 // 4 = TMEM allocator + MMA issuer, 5..8 = epilogue (tcgen05.ld of the warp's 32 TMEM lanes x 16 columns, mask +
 // scatter P[idx] = acc), 9..12 = TF32 round-to-nearest converters.
-// Two TMEM accumulators (2 x 16 columns) let the epilogue of tile i overlap the MMAs of tile
-// i+1; a 5-stage smem ring (18 KB / stage) keeps ~90 KB of loads in flight per CTA.
+// Four TMEM accumulators (4 x 16 columns) let the epilogue of tile i overlap the MMAs of tiles i+1..i+3; a 5-stage
+// smem ring (18 KB / stage) keeps ~90 KB of loads in flight per CTA.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -51,15 +51,16 @@ constexpr int kMmaWarp = 4;
 constexpr int kEpiWarp0 = 5;
 constexpr int kConvWarp0 = 9;                     // first converter warp
 constexpr int kDenseThreads = 13 * 32;
-constexpr int kTmemCols = 32;                      // 2 accumulators x 16 fp32 columns
+constexpr int kAccs = 4;                           // TMEM accumulators in rotation (tile i+4 waits for the epilogue of tile i)
+constexpr int kTmemCols = kAccs * 16;              // 16 fp32 columns each
 constexpr uint32_t kSpinLimit = 1u << 28;
 
 struct __align__(16) DenseSmemTail {
     uint64_t full[kStages];    // TMA bytes landed
     uint64_t ready[kStages];   // operands rounded to TF32 (4 converter warps arrived)
     uint64_t empty[kStages];   // MMAs that read the stage have completed
-    uint64_t tmem_full[2];
-    uint64_t tmem_empty[2];
+    uint64_t tmem_full[kAccs];
+    uint64_t tmem_empty[kAccs];
     uint32_t tmem_base;
     uint32_t pad[3];
 };
@@ -180,7 +181,7 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             mbar_init(&tail->ready[s], 4);
             mbar_init(&tail->empty[s], 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < kAccs; ++a) {
             mbar_init(&tail->tmem_full[a], 1);
             mbar_init(&tail->tmem_empty[a], 4);
         }
@@ -248,7 +249,7 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const uint32_t idesc = make_idesc_tf32(kTileCols, kPanel);
         uint32_t stage = 0, phase = 0, it = 0;
         for (uint32_t t = p.tile_begin + blockIdx.x; t < p.tile_end; t += gridDim.x, ++it) {
-            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            const uint32_t acc = it % kAccs, acc_phase = (it / kAccs) & 1;
             mbar_wait(&tail->tmem_empty[acc], acc_phase ^ 1, p.error_flag, 2);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * kPanel;
@@ -316,16 +317,24 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const uint32_t quarter = warp & 3;              // TMEM lanes [32*quarter, 32*quarter + 32)
         const uint32_t c = quarter * 32 + lane;         // dense column of the tile owned by this thread
         uint32_t it = 0;
-        for (uint32_t t = p.tile_begin + blockIdx.x; t < p.tile_end; t += gridDim.x, ++it) {
-            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            const uint32_t nc = __ldg(p.tile_meta + t).z;
-            const bool active = quarter * 32 < nc;
-            uint32_t idx[kPanel];
-            if (active) {
+        // scatter indices (and the tile's column count) are fetched one tile ahead: 16 coalesced 128-byte loads per
+        // warp whose DRAM latency would otherwise sit between two tiles of the epilogue
+        auto fetch_idx = [&](uint32_t t, uint32_t& nc, uint32_t (&idx)[kPanel]) {
+            nc = __ldg(p.tile_meta + t).z;
+            if (quarter * 32 < nc) {
                 const uint32_t* sc = p.tile_scatter + (size_t)t * kPanel * kTileCols + c;
 #pragma unroll
                 for (int r = 0; r < (int)kPanel; ++r) idx[r] = __ldg(sc + r * kTileCols);
             }
+        };
+        uint32_t nc = 0, nc_next = 0;
+        uint32_t idx[kPanel], idx_next[kPanel];
+        uint32_t t = p.tile_begin + blockIdx.x;
+        if (t < p.tile_end) fetch_idx(t, nc, idx);
+        for (; t < p.tile_end; t += gridDim.x, ++it) {
+            const uint32_t acc = it % kAccs, acc_phase = (it / kAccs) & 1;
+            if (t + gridDim.x < p.tile_end) fetch_idx(t + gridDim.x, nc_next, idx_next);
+            const bool active = quarter * 32 < nc;
             mbar_wait(&tail->tmem_full[acc], acc_phase, p.error_flag, 4);
             tc_fence_after();
             uint32_t v[kPanel];
@@ -347,6 +356,9 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 for (int r = 0; r < (int)kPanel; ++r)
                     if (idx[r] != kNull) p.P[idx[r]] = __uint_as_float(v[r]);
             }
+            nc = nc_next;
+#pragma unroll
+            for (int r = 0; r < (int)kPanel; ++r) idx[r] = idx_next[r];
         }
     }
 
