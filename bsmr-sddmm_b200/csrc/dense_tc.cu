@@ -43,10 +43,10 @@ namespace bsmr {
 namespace {
 
 constexpr int kStages = 5;
+constexpr int kProducerWarps = 4;
 constexpr int kChunk = 32;                         // floats of K per stage (128 bytes)
 constexpr int kBTileBytes = kTileCols * kChunk * 4;   // 16384
 constexpr int kATileBytes = kPanel * kChunk * 4;      // 2048
-constexpr int kProducerWarps = 4;
 constexpr int kMmaWarp = 4;
 constexpr int kEpiWarp0 = 5;
 constexpr int kConvWarp0 = 9;                     // first converter warp
@@ -63,6 +63,7 @@ struct __align__(16) DenseSmemTail {
     uint64_t tmem_empty[kAccs];
     uint32_t tmem_base;
     uint32_t pad[3];
+    uint32_t gather_idx[kProducerWarps][2 * 48];   // per producer warp: column (32) + row (16) indices of a tile, double buffered
 };
 constexpr size_t kDenseSmemBytes = 1024 /*alignment slack*/ + (size_t)kStages * (kBTileBytes + kATileBytes) + sizeof(DenseSmemTail);
 
@@ -162,6 +163,7 @@ struct DenseParams {
     float* P;
     uint32_t* error_flag;
     uint32_t* debug_smem;    // optional: raw copy of stage 0 of the first tile (probe / tests)
+    int skip_rna;            // experiment only (BSMR_DENSE_NO_RNA=1): leave the operands unrounded (tf32 truncation)
 };
 
 __global__ void __launch_bounds__(kDenseThreads, 2)
@@ -199,50 +201,67 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
     if (warp < kProducerWarps) {
         // ================= TMA producers (warps 0..3) =================
-        // Producer warp w owns B-tile rows [32w, 32w + 32): lane l < 8 issues the gather4 of dense columns
-        // 32w + 4l .. + 3; warp 0 lanes 8..11 additionally issue the four gather4 requests of the A-row tile.
-        // Lane 0 of warp 0 arms the stage's mbarrier with the byte count of ALL requests of the stage (a complete_tx
-        // that lands before the expect_tx only makes the transaction count transiently negative).
+        // Producer warp w owns B-tile rows [32w, 32w + 32) = 8 gather4 requests per stage; warp 3 additionally owns the
+        // four requests of the A-row tile.  All requests of a warp are issued by ONE lane from straight-line code: a
+        // gather4 takes its coordinates from uniform registers, and when several lanes issue with different coordinates
+        // ptxas serialises them with an ELECT / R2UR loop that costs ~140 cycles per request (ncu source view), which
+        // made request issue -- not memory -- the limiter of the pipeline.
+        // The 32 (+16) gather indices of a tile are loaded cooperatively (one coalesced load per warp) one tile ahead,
+        // parked in shared memory, and picked up by lane 0 with 128-bit shared loads when the tile starts.
         uint32_t stage = 0, phase = 0;
-        auto fetch = [&](uint32_t t, uint32_t& nc, int4& cols, int4& rows) {
+        uint32_t* my_idx = tail->gather_idx[warp];              // [2][48]: 32 column indices + 16 row indices, double buffered
+        auto stage_indices = [&](uint32_t t, uint32_t buf) -> uint32_t {   // returns the tile's column count
             const uint4 m = __ldg(p.tile_meta + t);
-            nc = m.z;
-            cols = make_int4((int)p.N, (int)p.N, (int)p.N, (int)p.N);
-            const uint32_t c0 = warp * 32 + lane * 4;           // first dense column of this lane's request
-            if (lane < 8 && c0 < nc) cols = __ldg(reinterpret_cast<const int4*>(p.dense_cols + m.y + c0));
-            rows = make_int4((int)p.M, (int)p.M, (int)p.M, (int)p.M);
-            if (warp == 0 && lane >= 8 && lane < 12) {
-                const uint32_t r0 = m.x * kPanel + (lane - 8) * 4;
-                int* rp = reinterpret_cast<int*>(&rows);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (r0 + j < p.num_rows) rp[j] = (int)__ldg(p.reordered_rows + r0 + j);
+            const uint32_t c = warp * 32 + lane;                 // dense column of the tile handled by this lane
+            my_idx[buf * 48 + lane] = c < m.z ? __ldg(p.dense_cols + m.y + c) : p.N;
+            if (warp == kProducerWarps - 1 && lane < kPanel) {
+                const uint32_t r = m.x * kPanel + lane;
+                my_idx[buf * 48 + 32 + lane] = r < p.num_rows ? __ldg(p.reordered_rows + r) : p.M;
             }
+            return m.z;
         };
-        uint32_t nc = 0, nc_next = 0;
-        int4 cols, rows, cols_next, rows_next;
-        cols = rows = cols_next = rows_next = make_int4(0, 0, 0, 0);
         uint32_t t = p.tile_begin + blockIdx.x;
-        if (t < p.tile_end) fetch(t, nc, cols, rows);
-        for (; t < p.tile_end; t += gridDim.x) {
-            // indices of the next tile are fetched while this one streams (dependent L2/DRAM loads off the critical path)
-            if (t + gridDim.x < p.tile_end) fetch(t + gridDim.x, nc_next, cols_next, rows_next);
-            const bool has_cols = lane < 8 && warp * 32 + lane * 4 < nc;
-            const bool has_rows = warp == 0 && lane >= 8 && lane < 12;
+        uint32_t nc = 0, nc_next = 0, buf = 0;
+        if (t < p.tile_end) nc = stage_indices(t, 0);
+        __syncwarp();
+        for (; t < p.tile_end; t += gridDim.x, buf ^= 1) {
+            int4 cols[8], rows[4];
+            uint32_t nreq = 0;                                    // B requests of this warp that carry real columns
+            if (lane == 0) {
+                const int4* src = reinterpret_cast<const int4*>(my_idx + buf * 48);
+#pragma unroll
+                for (int g = 0; g < 8; ++g) cols[g] = src[g];
+                if (warp == kProducerWarps - 1) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) rows[g] = src[8 + g];
+                }
+                const uint32_t first = warp * 32;
+                nreq = nc > first ? (nc - first + 3) / 4 : 0;
+                if (nreq > 8) nreq = 8;
+            }
+            // indices of the next tile: global loads now, parked in the other buffer (read one tile later)
+            if (t + gridDim.x < p.tile_end) nc_next = stage_indices(t + gridDim.x, buf ^ 1);
             const uint32_t tx_bytes = (nc / 4) * 512u + kATileBytes;
             for (uint32_t kc = 0; kc < num_chunks; ++kc) {
                 mbar_wait(&tail->empty[stage], phase ^ 1, p.error_flag, 1);
-                if (warp == 0 && lane == 0) mbar_arrive_expect_tx(&tail->full[stage], tx_bytes);
-                uint8_t* bt = b_tiles + (size_t)stage * kBTileBytes;
-                uint8_t* at = a_tiles + (size_t)stage * kATileBytes;
-                const int x = (int)(kc * kChunk);
-                if (has_cols) tma_gather4(&map_b, &tail->full[stage], bt + (warp * 8 + lane) * 512, x, cols);
-                if (has_rows) tma_gather4(&map_a, &tail->full[stage], at + (lane - 8) * 512, x, rows);
+                if (lane == 0) {
+                    if (warp == 0) mbar_arrive_expect_tx(&tail->full[stage], tx_bytes);
+                    uint8_t* bt = b_tiles + (size_t)stage * kBTileBytes + warp * 8 * 512;
+                    const int x = (int)(kc * kChunk);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        if ((uint32_t)g < nreq) tma_gather4(&map_b, &tail->full[stage], bt + g * 512, x, cols[g]);
+                    if (warp == kProducerWarps - 1) {
+                        uint8_t* at = a_tiles + (size_t)stage * kATileBytes;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) tma_gather4(&map_a, &tail->full[stage], at + g * 512, x, rows[g]);
+                    }
+                }
+                __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
             nc = nc_next;
-            cols = cols_next;
-            rows = rows_next;
+            __syncwarp();                                          // next tile's indices are in shared memory
         }
     } else if (warp == kMmaWarp) {
         // ================= MMA issuer =================
@@ -291,6 +310,12 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 mbar_wait(&tail->full[stage], phase, p.error_flag, 5);
                 float4* bt = reinterpret_cast<float4*>(b_tiles + (size_t)stage * kBTileBytes);
                 float4* at = reinterpret_cast<float4*>(a_tiles + (size_t)stage * kATileBytes);
+                if (p.skip_rna) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tail->ready[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    continue;
+                }
                 float4 v[9];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = bt[ci + 128 * j];
@@ -438,6 +463,10 @@ int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, 
     p.P = dP;
     p.error_flag = error_flag.ptr;
     p.debug_smem = g_debug_smem;
+    {
+        const char* e = std::getenv("BSMR_DENSE_NO_RNA");
+        p.skip_rna = e && e[0] == '1';
+    }
     g_debug_smem = nullptr;
     const uint32_t tiles = tile_end - tile_begin;
     const uint32_t max_ctas = static_cast<uint32_t>(ctx->sm_count) * 2;  // 2 CTAs (2 x 94 KB smem, 2 x 32 TMEM columns) per SM
