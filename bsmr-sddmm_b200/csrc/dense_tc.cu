@@ -63,7 +63,7 @@ struct __align__(16) DenseSmemTail {
     uint64_t tmem_empty[kAccs];
     uint32_t tmem_base;
     uint32_t pad[3];
-    uint32_t gather_idx[kProducerWarps][2 * 48];   // per producer warp: column (32) + row (16) indices of a tile, double buffered
+    alignas(16) uint32_t gather_idx[kProducerWarps][2 * 48];   // per producer warp: column (32) + row (16) indices of a tile, double buffered
 };
 constexpr size_t kDenseSmemBytes = 1024 /*alignment slack*/ + (size_t)kStages * (kBTileBytes + kATileBytes) + sizeof(DenseSmemTail);
 
