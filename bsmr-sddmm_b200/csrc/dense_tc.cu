@@ -26,11 +26,9 @@
 // reference rounds to nearest (wmma::__float_to_tf32 = cvt.rna, src/sddmmKernel.cu:317-322), so
 // four converter warps round every landed stage in place with cvt.rna.tf32.f32 before the MMA
 // warp may read it (generic-proxy writes -> fence.proxy.async -> mbarrier).
-// Warp roles (13 warps): 0..3 = TMA producers (one quarter of the B-column tile each; a gather4 request takes its
-// coordinates from uniform registers, so the requests of a warp are issued one lane at a time -- ncu showed a single
-// producer warp spending ~1.7 us per stage on 36 serialised requests -- hence four issuing warps),
-// 4 = TMEM allocator + MMA issuer, 5..8 = epilogue (tcgen05.ld of the warp's 32 TMEM lanes x 16 columns, mask +
-// scatter P[idx] = acc), 9..12 = TF32 round-to-nearest converters.
+// Warp roles (17 warps): 0..7 = TMA producers (16 columns of the B-column tile each, see the producer section for
+// why so many), 8 = TMEM allocator + MMA issuer, 9..12 = epilogue (tcgen05.ld of the warp's 32 TMEM lanes x 16 columns,
+// mask + scatter P[idx] = acc), 13..16 = TF32 round-to-nearest converters.
 // Four TMEM accumulators (4 x 16 columns) let the epilogue of tile i overlap the MMAs of tiles i+1..i+3; a 5-stage
 // smem ring (18 KB / stage) keeps ~90 KB of loads in flight per CTA.
 #include <cuda.h>
@@ -43,14 +41,16 @@ namespace bsmr {
 namespace {
 
 constexpr int kStages = 5;
-constexpr int kProducerWarps = 4;
 constexpr int kChunk = 32;                         // floats of K per stage (128 bytes)
 constexpr int kBTileBytes = kTileCols * kChunk * 4;   // 16384
 constexpr int kATileBytes = kPanel * kChunk * 4;      // 2048
-constexpr int kMmaWarp = 4;
-constexpr int kEpiWarp0 = 5;
-constexpr int kConvWarp0 = 9;                     // first converter warp
-constexpr int kDenseThreads = 13 * 32;
+constexpr int kProducerWarps = 8;                 // each owns 16 dense columns = 4 gather4 requests per stage
+constexpr int kColsPerProducer = 128 / kProducerWarps;
+constexpr int kReqPerProducer = kColsPerProducer / 4;
+constexpr int kMmaWarp = kProducerWarps;
+constexpr int kEpiWarp0 = kProducerWarps + 1;     // 4 epilogue warps (kEpiWarp0 % 4 is irrelevant: quarter = warp & 3 covers all four)
+constexpr int kConvWarp0 = kProducerWarps + 5;    // first of 4 converter warps
+constexpr int kDenseThreads = (kProducerWarps + 9) * 32;
 constexpr int kAccs = 4;                           // TMEM accumulators in rotation (tile i+4 waits for the epilogue of tile i)
 constexpr int kTmemCols = kAccs * 16;              // 16 fp32 columns each
 constexpr uint32_t kSpinLimit = 1u << 28;
@@ -63,7 +63,6 @@ struct __align__(16) DenseSmemTail {
     uint64_t tmem_empty[kAccs];
     uint32_t tmem_base;
     uint32_t pad[3];
-    alignas(16) uint32_t gather_idx[kProducerWarps][2 * 48];   // per producer warp: column (32) + row (16) indices of a tile, double buffered
 };
 constexpr size_t kDenseSmemBytes = 1024 /*alignment slack*/ + (size_t)kStages * (kBTileBytes + kATileBytes) + sizeof(DenseSmemTail);
 
@@ -163,7 +162,6 @@ struct DenseParams {
     float* P;
     uint32_t* error_flag;
     uint32_t* debug_smem;    // optional: raw copy of stage 0 of the first tile (probe / tests)
-    int skip_rna;            // experiment only (BSMR_DENSE_NO_RNA=1): leave the operands unrounded (tf32 truncation)
 };
 
 __global__ void __launch_bounds__(kDenseThreads, 2)
@@ -200,68 +198,55 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const uint32_t tmem_base = tail->tmem_base;
 
     if (warp < kProducerWarps) {
-        // ================= TMA producers (warps 0..3) =================
-        // Producer warp w owns B-tile rows [32w, 32w + 32) = 8 gather4 requests per stage; warp 3 additionally owns the
-        // four requests of the A-row tile.  All requests of a warp are issued by ONE lane from straight-line code: a
-        // gather4 takes its coordinates from uniform registers, and when several lanes issue with different coordinates
-        // ptxas serialises them with an ELECT / R2UR loop that costs ~140 cycles per request (ncu source view), which
-        // made request issue -- not memory -- the limiter of the pipeline.
-        // The 32 (+16) gather indices of a tile are loaded cooperatively (one coalesced load per warp) one tile ahead,
-        // parked in shared memory, and picked up by lane 0 with 128-bit shared loads when the tile starts.
+        // ================= TMA producers (warps 0..7) =================
+        // Producer warp w owns B-tile rows [16w, 16w + 16): lane l < 4 issues the gather4 of dense columns
+        // 16w + 4l .. + 3; the last producer warp's lanes 4..7 additionally issue the four gather4 requests of the A-row
+        // tile.  Lane 0 of warp 0 arms the stage's mbarrier with the byte count of ALL requests of the stage (a
+        // complete_tx that lands before the expect_tx only makes the transaction count transiently negative).
+        // Why eight warps: a gather4 takes its coordinates from uniform registers, ptxas serialises the issuing lanes of
+        // a warp with an ELECT / R2UR loop at ~140 cycles per request (ncu source view); one warp issuing all 36 requests
+        // of a stage needed ~1.7 us per stage, four warps ~0.6 us.  (One lane issuing 8 requests from straight-line code
+        // was slower still: measured.)
         uint32_t stage = 0, phase = 0;
-        uint32_t* my_idx = tail->gather_idx[warp];              // [2][48]: 32 column indices + 16 row indices, double buffered
-        auto stage_indices = [&](uint32_t t, uint32_t buf) -> uint32_t {   // returns the tile's column count
+        auto fetch = [&](uint32_t t, uint32_t& nc, int4& cols, int4& rows) {
             const uint4 m = __ldg(p.tile_meta + t);
-            const uint32_t c = warp * 32 + lane;                 // dense column of the tile handled by this lane
-            my_idx[buf * 48 + lane] = c < m.z ? __ldg(p.dense_cols + m.y + c) : p.N;
-            if (warp == kProducerWarps - 1 && lane < kPanel) {
-                const uint32_t r = m.x * kPanel + lane;
-                my_idx[buf * 48 + 32 + lane] = r < p.num_rows ? __ldg(p.reordered_rows + r) : p.M;
+            nc = m.z;
+            cols = make_int4((int)p.N, (int)p.N, (int)p.N, (int)p.N);
+            const uint32_t c0 = warp * kColsPerProducer + lane * 4;      // first dense column of this lane's request
+            if (lane < kReqPerProducer && c0 < nc) cols = __ldg(reinterpret_cast<const int4*>(p.dense_cols + m.y + c0));
+            rows = make_int4((int)p.M, (int)p.M, (int)p.M, (int)p.M);
+            if (warp == kProducerWarps - 1 && lane >= 4 && lane < 8) {
+                const uint32_t r0 = m.x * kPanel + (lane - 4) * 4;
+                int* rp = reinterpret_cast<int*>(&rows);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (r0 + j < p.num_rows) rp[j] = (int)__ldg(p.reordered_rows + r0 + j);
             }
-            return m.z;
         };
+        uint32_t nc = 0, nc_next = 0;
+        int4 cols, rows, cols_next, rows_next;
+        cols = rows = cols_next = rows_next = make_int4(0, 0, 0, 0);
         uint32_t t = p.tile_begin + blockIdx.x;
-        uint32_t nc = 0, nc_next = 0, buf = 0;
-        if (t < p.tile_end) nc = stage_indices(t, 0);
-        __syncwarp();
-        for (; t < p.tile_end; t += gridDim.x, buf ^= 1) {
-            int4 cols[8], rows[4];
-            uint32_t nreq = 0;                                    // B requests of this warp that carry real columns
-            if (lane == 0) {
-                const int4* src = reinterpret_cast<const int4*>(my_idx + buf * 48);
-#pragma unroll
-                for (int g = 0; g < 8; ++g) cols[g] = src[g];
-                if (warp == kProducerWarps - 1) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) rows[g] = src[8 + g];
-                }
-                const uint32_t first = warp * 32;
-                nreq = nc > first ? (nc - first + 3) / 4 : 0;
-                if (nreq > 8) nreq = 8;
-            }
-            // indices of the next tile: global loads now, parked in the other buffer (read one tile later)
-            if (t + gridDim.x < p.tile_end) nc_next = stage_indices(t + gridDim.x, buf ^ 1);
+        if (t < p.tile_end) fetch(t, nc, cols, rows);
+        for (; t < p.tile_end; t += gridDim.x) {
+            // indices of the next tile are fetched while this one streams (dependent L2/DRAM loads off the critical path)
+            if (t + gridDim.x < p.tile_end) fetch(t + gridDim.x, nc_next, cols_next, rows_next);
+            const bool has_cols = lane < kReqPerProducer && warp * kColsPerProducer + lane * 4 < nc;
+            const bool has_rows = warp == kProducerWarps - 1 && lane >= 4 && lane < 8;
             const uint32_t tx_bytes = (nc / 4) * 512u + kATileBytes;
             for (uint32_t kc = 0; kc < num_chunks; ++kc) {
                 mbar_wait(&tail->empty[stage], phase ^ 1, p.error_flag, 1);
-                if (lane == 0) {
-                    if (warp == 0) mbar_arrive_expect_tx(&tail->full[stage], tx_bytes);
-                    uint8_t* bt = b_tiles + (size_t)stage * kBTileBytes + warp * 8 * 512;
-                    const int x = (int)(kc * kChunk);
-#pragma unroll
-                    for (int g = 0; g < 8; ++g)
-                        if ((uint32_t)g < nreq) tma_gather4(&map_b, &tail->full[stage], bt + g * 512, x, cols[g]);
-                    if (warp == kProducerWarps - 1) {
-                        uint8_t* at = a_tiles + (size_t)stage * kATileBytes;
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) tma_gather4(&map_a, &tail->full[stage], at + g * 512, x, rows[g]);
-                    }
-                }
-                __syncwarp();
+                if (warp == 0 && lane == 0) mbar_arrive_expect_tx(&tail->full[stage], tx_bytes);
+                uint8_t* bt = b_tiles + (size_t)stage * kBTileBytes;
+                uint8_t* at = a_tiles + (size_t)stage * kATileBytes;
+                const int x = (int)(kc * kChunk);
+                if (has_cols) tma_gather4(&map_b, &tail->full[stage], bt + (warp * kReqPerProducer + lane) * 512, x, cols);
+                if (has_rows) tma_gather4(&map_a, &tail->full[stage], at + (lane - 4) * 512, x, rows);
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
             nc = nc_next;
-            __syncwarp();                                          // next tile's indices are in shared memory
+            cols = cols_next;
+            rows = rows_next;
         }
     } else if (warp == kMmaWarp) {
         // ================= MMA issuer =================
@@ -299,7 +284,7 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
         }
     } else if (warp >= kConvWarp0) {
-        // ================= TF32 converters (warps 9..12) =================
+        // ================= TF32 converters (last four warps) =================
         // cvt.rna.tf32.f32 on every element of the landed stage, in place; element-wise, so the
         // 128-byte swizzle does not matter.  Thread i owns float4 #i, #i+128, ... of the B-column
         // tile (8 of them) and float4 #i of the A-row tile.
@@ -310,12 +295,6 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 mbar_wait(&tail->full[stage], phase, p.error_flag, 5);
                 float4* bt = reinterpret_cast<float4*>(b_tiles + (size_t)stage * kBTileBytes);
                 float4* at = reinterpret_cast<float4*>(a_tiles + (size_t)stage * kATileBytes);
-                if (p.skip_rna) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tail->ready[stage]);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
-                    continue;
-                }
                 float4 v[9];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = bt[ci + 128 * j];
@@ -338,28 +317,20 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
         }
     } else {
-        // ================= epilogue (warps 5..8) =================
+        // ================= epilogue (four warps after the MMA warp) =================
         const uint32_t quarter = warp & 3;              // TMEM lanes [32*quarter, 32*quarter + 32)
         const uint32_t c = quarter * 32 + lane;         // dense column of the tile owned by this thread
         uint32_t it = 0;
-        // scatter indices (and the tile's column count) are fetched one tile ahead: 16 coalesced 128-byte loads per
-        // warp whose DRAM latency would otherwise sit between two tiles of the epilogue
-        auto fetch_idx = [&](uint32_t t, uint32_t& nc, uint32_t (&idx)[kPanel]) {
-            nc = __ldg(p.tile_meta + t).z;
-            if (quarter * 32 < nc) {
+        for (uint32_t t = p.tile_begin + blockIdx.x; t < p.tile_end; t += gridDim.x, ++it) {
+            const uint32_t acc = it % kAccs, acc_phase = (it / kAccs) & 1;
+            const uint32_t nc = __ldg(p.tile_meta + t).z;
+            const bool active = quarter * 32 < nc;
+            uint32_t idx[kPanel];
+            if (active) {      // issued before the accumulator is waited for: the loads overlap the tile's MMAs
                 const uint32_t* sc = p.tile_scatter + (size_t)t * kPanel * kTileCols + c;
 #pragma unroll
                 for (int r = 0; r < (int)kPanel; ++r) idx[r] = __ldg(sc + r * kTileCols);
             }
-        };
-        uint32_t nc = 0, nc_next = 0;
-        uint32_t idx[kPanel], idx_next[kPanel];
-        uint32_t t = p.tile_begin + blockIdx.x;
-        if (t < p.tile_end) fetch_idx(t, nc, idx);
-        for (; t < p.tile_end; t += gridDim.x, ++it) {
-            const uint32_t acc = it % kAccs, acc_phase = (it / kAccs) & 1;
-            if (t + gridDim.x < p.tile_end) fetch_idx(t + gridDim.x, nc_next, idx_next);
-            const bool active = quarter * 32 < nc;
             mbar_wait(&tail->tmem_full[acc], acc_phase, p.error_flag, 4);
             tc_fence_after();
             uint32_t v[kPanel];
@@ -381,9 +352,6 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 for (int r = 0; r < (int)kPanel; ++r)
                     if (idx[r] != kNull) p.P[idx[r]] = __uint_as_float(v[r]);
             }
-            nc = nc_next;
-#pragma unroll
-            for (int r = 0; r < (int)kPanel; ++r) idx[r] = idx_next[r];
         }
     }
 
@@ -463,10 +431,6 @@ int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, 
     p.P = dP;
     p.error_flag = error_flag.ptr;
     p.debug_smem = g_debug_smem;
-    {
-        const char* e = std::getenv("BSMR_DENSE_NO_RNA");
-        p.skip_rna = e && e[0] == '1';
-    }
     g_debug_smem = nullptr;
     const uint32_t tiles = tile_end - tile_begin;
     const uint32_t max_ctas = static_cast<uint32_t>(ctx->sm_count) * 2;  // 2 CTAs (2 x 94 KB smem, 2 x 32 TMEM columns) per SM

@@ -22,7 +22,7 @@ inline void sddmm_gpu(UIN M, UIN N, UIN K, const float* matrixA, const float* ma
     bsmr_plan_info info{};
     bsmr_plan_get_info(rphm.plan(), &info);
     logger.gridDim_dense_.x = info.num_dense_tiles;            // persistent grids; the tile / chunk counts are the work sizes
-    logger.blockDim_dense_.x = 416;
+    logger.blockDim_dense_.x = 544;
     logger.gridDim_sparse_.x = static_cast<unsigned>((info.num_sparse_values + 255) / 256);
     logger.blockDim_sparse_.x = 256;
 }
@@ -51,7 +51,7 @@ inline void sddmm_gpu(const Matrix<float>& matrixA, const Matrix<float>& matrixB
     bsmr_plan_info info{};
     bsmr_plan_get_info(rphm.plan(), &info);
     logger.gridDim_dense_.x = info.num_dense_tiles;
-    logger.blockDim_dense_.x = 416;
+    logger.blockDim_dense_.x = 544;
     logger.gridDim_sparse_.x = static_cast<unsigned>((info.num_sparse_values + 255) / 256);
     logger.blockDim_sparse_.x = 256;
 }
