@@ -24,6 +24,8 @@
 //
 // Roofline: HBM-bound on compulsory traffic; what it actually stresses is L2 -> SM gather
 // bandwidth (K*4 bytes of B per nnz), see DESIGN.md.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace bsmr {
@@ -210,6 +212,151 @@ residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const float*
     }
 }
 
+// ---- residual_async_kernel: the same computation with the B columns staged through shared memory by cp.async ----
+// residual_rows_kernel keeps every in-flight B piece in a register, so the bytes in flight per SM are bounded by the
+// register file (ncu on the nips-shaped matrix, K = 128: 24 warps x 4 x 512 B = 49 KB in flight, L2->L1 9.2 TB/s, LSU
+// 46 %, L2 39 % -- latency bound, nothing saturated).  Here each lane copies its own 16-byte pieces with
+// cp.async.cg (LDGSTS, L1 bypass) into a per-warp ring of 4 groups x 8 entries and reads them back with LDS.128 when
+// their group is complete: a lane only ever reads what it copied itself, so cp.async.wait_group is the only
+// synchronisation, and 3 groups (24 entries x K*4 bytes) per warp are always in flight -- ~170 KB per SM at K = 128.
+// Steady state per group: wait_group 3 -> 8 dot products from shared memory (A row in registers) -> re-issue the
+// group's slots with the next chunk's entries.
+template <int LPN, int KV, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+residual_async_kernel(const uint32_t K, const float* __restrict__ A, const float* __restrict__ B,
+                      float* __restrict__ P, const uint32_t* __restrict__ res_row,
+                      const uint32_t* __restrict__ res_col, const uint32_t* __restrict__ res_out,
+                      const uint64_t begin, const uint64_t end) {
+    extern __shared__ __align__(16) uint8_t ring_smem[];
+    constexpr int G = 32 / LPN;                 // entries per warp instruction
+    constexpr int H = LPN / 2;
+    constexpr int kEntryBytes = LPN * KV * 16;  // K * 4
+    constexpr int kGroups = 4, kGroupEntries = 8;
+    constexpr int kPassesPerGroup = kGroupEntries / G;
+    static_assert(kPassesPerGroup % 2 == 0, "pairs of passes are folded together");
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t sub = lane / LPN;
+    const uint32_t sl = lane % LPN;
+    uint8_t* ring = ring_smem + (size_t)(threadIdx.x >> 5) * 32 * kEntryBytes;
+    const uint32_t ring_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(ring));
+    const uint64_t num_chunks = (end - begin + 31) / 32;
+    const uint64_t warp_stride = (uint64_t)gridDim.x * WARPS;
+    uint64_t chunk = (uint64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (chunk >= num_chunks) return;
+
+    uint32_t my_row, my_col, my_out, nx_row = 0, nx_col = 0, nx_out = 0;
+    bool my_valid, nx_valid = false;
+    auto load_meta = [&](uint64_t c, uint32_t& row, uint32_t& col, uint32_t& out, bool& valid) {
+        const uint64_t e = begin + c * 32 + lane;
+        valid = e < end;
+        const uint64_t es = valid ? e : begin;   // idle lanes recompute entry `begin`; never stored
+        row = __ldg(res_row + es);
+        col = __ldg(res_col + es);
+        out = res_out ? __ldg(res_out + es) : (uint32_t)es;
+    };
+    // copy the B pieces of group g (entries 8g .. 8g+7 of the chunk whose columns are in `col_reg`) into their slots
+    auto issue_group = [&](int g, uint32_t col_reg) {
+#pragma unroll
+        for (int it = 0; it < kPassesPerGroup; ++it) {
+            const int j = (g * kPassesPerGroup + it) * G + sub;
+            const uint32_t col = __shfl_sync(0xffffffffu, col_reg, j);
+            const float* src = B + (size_t)col * K + sl * 4;
+            const uint32_t dst = ring_u32 + j * kEntryBytes + sl * 16;
+#pragma unroll
+            for (int v = 0; v < KV; ++v)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + v * LPN * 16), "l"(src + v * LPN * 4) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    load_meta(chunk, my_row, my_col, my_out, my_valid);
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) issue_group(g, my_col);
+
+    uint32_t cur_row = 0xFFFFFFFFu;
+    float4 a_cur[KV];
+#pragma unroll
+    for (int v = 0; v < KV; ++v) a_cur[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool upper0 = (sl & H) != 0;
+
+    for (;;) {
+        const uint64_t next = chunk + warp_stride;
+        const bool has_next = next < num_chunks;
+        if (has_next) load_meta(next, nx_row, nx_col, nx_out, nx_valid);   // in flight while this chunk is computed
+        float q[H];
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+            asm volatile("cp.async.wait_group 3;" ::: "memory");           // the oldest outstanding group (this one) has landed
+#pragma unroll
+            for (int it = 0; it < kPassesPerGroup; it += 2) {
+                float d[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int pass = g * kPassesPerGroup + it + u;
+                    const int j = pass * G + sub;
+                    const uint32_t row = __shfl_sync(0xffffffffu, my_row, j);
+                    if (row != cur_row) {                    // uniform inside the group (warp-uniform for LPN == 32)
+                        const float* ap = A + (size_t)row * K + sl * 4;
+#pragma unroll
+                        for (int v = 0; v < KV; ++v) a_cur[v] = ldg4(ap + v * LPN * 4);
+                        cur_row = row;
+                    }
+                    const float4* bp = reinterpret_cast<const float4*>(ring + j * kEntryBytes + sl * 16);
+                    float acc = 0.f;
+#pragma unroll
+                    for (int v = 0; v < KV; ++v) acc = dot4(a_cur[v], bp[v * LPN], acc);
+                    d[u] = acc;
+                }
+                // slots i (pass 2i) and i + H (pass 2i + 1): first butterfly step folded in
+                const float send = upper0 ? d[0] : d[1];
+                const float keep = upper0 ? d[1] : d[0];
+                q[(g * kPassesPerGroup + it) / 2] = keep + __shfl_xor_sync(0xffffffffu, send, H);
+            }
+            // the group's slots are free again (their contents were consumed into d[]): refill with the next chunk
+            if (has_next) issue_group(g, nx_col);
+            else asm volatile("cp.async.commit_group;" ::: "memory");      // keeps the group count uniform
+        }
+#pragma unroll
+        for (int h = H / 2; h >= 1; h >>= 1) {
+            const bool upper = (sl & h) != 0;
+#pragma unroll
+            for (int i = 0; i < h; ++i) {
+                const float send = upper ? q[i] : q[i + h];
+                const float keep = upper ? q[i + h] : q[i];
+                q[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+            }
+        }
+        const int mine = (int)((2 * (sl % H) + sl / H) * G + sub);
+        const uint32_t out = __shfl_sync(0xffffffffu, my_out, mine);
+        const bool ok = __shfl_sync(0xffffffffu, (int)my_valid, mine) != 0;
+        if (ok) P[out] = q[0];
+        if (!has_next) break;
+        chunk = next;
+        my_row = nx_row; my_col = nx_col; my_out = nx_out; my_valid = nx_valid;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+template <int LPN, int KV, int WARPS>
+int launch_async(bsmr_ctx* ctx, uint32_t K, const float* dA, const float* dB, float* dP, const uint32_t* rr, const uint32_t* rc,
+                 const uint32_t* ro, uint64_t begin, uint64_t end) {
+    constexpr size_t smem = (size_t)WARPS * 32 * LPN * KV * 16;
+    static bool configured = false;
+    static int per_sm = 1;
+    if (!configured) {
+        BSMR_CUDA_OK(cudaFuncSetAttribute(residual_async_kernel<LPN, KV, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BSMR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, residual_async_kernel<LPN, KV, WARPS>, WARPS * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        configured = true;
+    }
+    const uint64_t chunks = (end - begin + 31) / 32;
+    const uint64_t need = (chunks + WARPS - 1) / WARPS;
+    const uint64_t cap = (uint64_t)ctx->sm_count * per_sm;      // persistent: exactly the resident CTAs
+    const int grid = (int)(need < cap ? need : cap);
+    residual_async_kernel<LPN, KV, WARPS><<<grid, WARPS * 32, smem, ctx->stream>>>(K, dA, dB, dP, rr, rc, ro, begin, end);
+    return BSMR_OK;
+}
+
 // Any K (no alignment assumption): one lane group of 32, scalar loads.
 __global__ void __launch_bounds__(kResThreads)
 residual_sddmm_generic_kernel(const uint32_t K, const float* __restrict__ A, const float* __restrict__ B,
@@ -263,6 +410,7 @@ int launch_residual(bsmr_ctx* ctx, uint32_t K, const float* dA, const float* dB,
     // 8 CTAs of 256 threads = 64 warps = a full SM; grid is a multiple of the SM count
     const uint64_t max_ctas = (uint64_t)ctx->sm_count * 8;
     const bool fast_k = K == 32 || K == 64 || K == 128 || K == 256 || K == 512;
+    static const bool use_rows_kernel = [] { const char* e = std::getenv("BSMR_RESIDUAL"); return e && e[0] == 'r'; }();   // A/B switch: "rows" = register-staged kernel
     // residual_rows_kernel: 3 resident CTAs per SM (register budget), persistent grid-stride over the chunks
     const uint64_t cap = fast_k ? (uint64_t)ctx->sm_count * 3 : max_ctas;
     const int grid = (int)(ctas_needed < cap ? ctas_needed : cap);
@@ -273,6 +421,14 @@ int launch_residual(bsmr_ctx* ctx, uint32_t K, const float* dA, const float* dB,
         const uint64_t need = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
         const int g = (int)(need < max_ctas ? need : max_ctas);
         residual_sddmm_generic_kernel<<<g, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+    } else if (fast_k && !use_rows_kernel) {
+        int st = BSMR_OK;
+        if (K == 32) st = launch_async<8, 1, 8>(ctx, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+        else if (K == 64) st = launch_async<16, 1, 8>(ctx, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+        else if (K == 128) st = launch_async<32, 1, 7>(ctx, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+        else if (K == 256) st = launch_async<32, 2, 7>(ctx, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+        else st = launch_async<32, 4, 3>(ctx, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+        BSMR_TRY(st);
     } else if (K == 32) {
         residual_rows_kernel<8, 1><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end);
     } else if (K == 64) {
