@@ -213,6 +213,7 @@ residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const float*
 }
 
 // ---- residual_async_kernel: the same computation with the B columns staged through shared memory by cp.async ----
+// EXPERIMENT (opt-in, BSMR_RESIDUAL=async; measured slower than residual_rows_kernel, kept for the record).
 // residual_rows_kernel keeps every in-flight B piece in a register, so the bytes in flight per SM are bounded by the
 // register file (ncu on the nips-shaped matrix, K = 128: 24 warps x 4 x 512 B = 49 KB in flight, L2->L1 9.2 TB/s, LSU
 // 46 %, L2 39 % -- latency bound, nothing saturated).  Here each lane copies its own 16-byte pieces with
@@ -410,7 +411,10 @@ int launch_residual(bsmr_ctx* ctx, uint32_t K, const float* dA, const float* dB,
     // 8 CTAs of 256 threads = 64 warps = a full SM; grid is a multiple of the SM count
     const uint64_t max_ctas = (uint64_t)ctx->sm_count * 8;
     const bool fast_k = K == 32 || K == 64 || K == 128 || K == 256 || K == 512;
-    static const bool use_rows_kernel = [] { const char* e = std::getenv("BSMR_RESIDUAL"); return e && e[0] == 'r'; }();   // A/B switch: "rows" = register-staged kernel
+    // default: the register-staged kernel.  BSMR_RESIDUAL=async selects the cp.async-staged variant, which keeps 3.5x
+    // more bytes in flight per SM but measured SLOWER on B200 (graph17 K=128: 164 us vs 127 us; nips K=256: 79 vs 50 us):
+    // the gather is not limited by bytes in flight.
+    static const bool use_rows_kernel = [] { const char* e = std::getenv("BSMR_RESIDUAL"); return !(e && e[0] == 'a'); }();
     // residual_rows_kernel: 3 resident CTAs per SM (register budget), persistent grid-stride over the chunks
     const uint64_t cap = fast_k ? (uint64_t)ctx->sm_count * 3 : max_ctas;
     const int grid = (int)(ctas_needed < cap ? ctas_needed : cap);
