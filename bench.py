@@ -102,6 +102,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """Host threads this process may use (its CPU affinity mask), independent of OMP_NUM_THREADS."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path (sddmm_cpu, OpenMP, all host
     threads) from oracle/_ref; the oracle port when that library did not travel.  Rank 0 only."""
@@ -112,12 +120,13 @@ def run_reference(args, rank, world):
     M, N, ro, ci, source = load_workload(pkg, max(1, args.gpus))
     K = args.k
     A, B = pkg.synth.make_ab(M, N, K)
+    # all the host threads the box offers: torchrun exports OMP_NUM_THREADS=1, which would otherwise pin the
+    # reference's OpenMP loop to one core (the harness calls omp_set_num_threads(threads) around the call)
+    threads = host_threads()
     if os.path.exists(REF_SO):
         impl, kind = Ref(), "reference"
-        threads = impl.omp_max_threads()
     else:
         impl, kind = Oracle(), "port"
-        threads = os.cpu_count()
     steps = max(1, min(args.steps, 20))
     for _ in range(max(1, min(args.warmup, 2))):
         impl.sddmm_cpu(M, N, K, A, B, ro, ci, num_threads=threads)
@@ -316,12 +325,11 @@ def main():
     cpu_baseline = None
     if world == 1:
         from oracle.bindings import Oracle, Ref, REF_SO
+        threads = host_threads()
         if os.path.exists(REF_SO):
             impl, kind = Ref(), "reference"
-            threads = impl.omp_max_threads()
         else:
             impl, kind = Oracle(), "port"
-            threads = os.cpu_count()
         impl.sddmm_cpu(M, N, K, A, B, ro, ci, num_threads=threads)
         reps = 5
         t0 = time.perf_counter()
