@@ -24,7 +24,8 @@ BLOCK_COL_SIZE = 16
 NULL_VALUE = 0xFFFFFFFF
 
 ROW_REFERENCE_COMPAT, ROW_EXACT_REDUCE, ROW_IDENTITY = 0, 1, 2
-SDDMM_DEFAULT, SDDMM_RESIDUAL_ONLY, SDDMM_NO_REORDER = 0, 1, 2
+SDDMM_DEFAULT, SDDMM_RESIDUAL_ONLY, SDDMM_NO_REORDER, SDDMM_NO_WIDE = 0, 1, 2, 4
+WIDE_GROUP_ROWS, WIDE_TILE_COLS = 128, 128
 
 VEC = dict(reordered_rows=0, dense_cols=1, dense_col_offsets=2, sparse_cols=3, sparse_col_offsets=4,
            sparse_value_offsets=5, block_offsets=6, block_values=7, sparse_values=8,
@@ -46,7 +47,10 @@ class PlanInfo(C.Structure):
                 ("block_size", C.c_uint32), ("num_dense_blocks", C.c_uint32), ("num_dense_tiles", C.c_uint32),
                 ("num_dense_values", C.c_uint64), ("num_sparse_values", C.c_uint64),
                 ("row_reordering_ms", C.c_float), ("col_reordering_ms", C.c_float), ("format_build_ms", C.c_float),
-                ("cluster_kernel_ms", C.c_float)]
+                ("cluster_kernel_ms", C.c_float),
+                ("num_row_groups", C.c_uint32), ("num_wide_groups", C.c_uint32), ("num_wide_tiles", C.c_uint32),
+                ("num_block_tiles", C.c_uint32), ("num_wide_values", C.c_uint64), ("num_block_values", C.c_uint64),
+                ("num_residual_values", C.c_uint64), ("wide_format_ms", C.c_float)]
 
 
 class ReorderStats(C.Structure):
@@ -97,13 +101,16 @@ def lib():
         L.bsmr_sddmm.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_int, C.c_uint32, f32p]
         L.bsmr_sddmm_host.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_int, C.c_uint32, f32p, f32p]
         L.bsmr_sddmm_profile.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_uint32, f32p, f32p]
+        L.bsmr_sddmm_profile3.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_uint32, f32p, f32p, f32p]
+        L.bsmr_plan_set_wide_ratio.argtypes = [vp, C.c_float]
         L.bsmr_plan_evaluate.argtypes = [vp, C.c_float, C.POINTER(ReorderStats)]
         L.bsmr_debug_set_dense_smem_dump.argtypes = [vp]
         for name in ("bsmr_ctx_create", "bsmr_ctx_destroy", "bsmr_ctx_synchronize", "bsmr_ctx_device_name",
                      "bsmr_ctx_launch_count", "bsmr_calculate_block_size", "bsmr_plan_create", "bsmr_plan_destroy",
                      "bsmr_plan_row_reorder", "bsmr_plan_set_row_order", "bsmr_plan_col_reorder", "bsmr_plan_reorder",
                      "bsmr_plan_vector_size", "bsmr_plan_vector_copy", "bsmr_plan_get_info", "bsmr_plan_set_shard",
-                     "bsmr_sddmm", "bsmr_sddmm_host", "bsmr_sddmm_profile", "bsmr_plan_evaluate"):
+                     "bsmr_sddmm", "bsmr_sddmm_host", "bsmr_sddmm_profile", "bsmr_sddmm_profile3",
+                     "bsmr_plan_set_wide_ratio", "bsmr_plan_evaluate"):
             getattr(L, name).restype = C.c_int
         _lib = L
     return _lib
@@ -192,6 +199,10 @@ class Plan:
         rows = np.ascontiguousarray(rows, dtype=np.uint32)
         _check(lib().bsmr_plan_set_row_order(self._h, rows.ctypes.data_as(u32p), len(rows)))
 
+    def set_wide_ratio(self, ratio):
+        """Policy of the wide row-group path, applied at the next column reorder (<= 0 disables it)."""
+        _check(lib().bsmr_plan_set_wide_ratio(self._h, ratio))
+
     def col_reorder(self, delta):
         _check(lib().bsmr_plan_col_reorder(self._h, delta))
 
@@ -234,6 +245,12 @@ class Plan:
         a, b = C.c_float(0), C.c_float(0)
         _check(lib().bsmr_sddmm_profile(self._h, K, _ptr(dA), _ptr(dB), _ptr(dP), flags, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def sddmm_profile3(self, K, dA, dB, dP, flags=SDDMM_DEFAULT):
+        """One pass, the three kernels timed separately: (wide_ms, dense_block_ms, residual_ms)."""
+        w, a, b = C.c_float(0), C.c_float(0), C.c_float(0)
+        _check(lib().bsmr_sddmm_profile3(self._h, K, _ptr(dA), _ptr(dB), _ptr(dP), flags, C.byref(w), C.byref(a), C.byref(b)))
+        return w.value, a.value, b.value
 
     def sddmm_host(self, K, hA, hB, hP=None, iterations=1, flags=SDDMM_DEFAULT):
         """Host buffers (numpy or pinned torch tensors); H2D/D2H inside.  Returns (P, kernel_ms, total_ms)."""

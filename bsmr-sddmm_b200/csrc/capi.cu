@@ -84,8 +84,10 @@ int bsmr_ctx_create(int device, void* cuda_stream, bsmr_ctx** out) {
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
     cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->side_stream2, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming);
     // cuTensorMapEncodeTiled through the runtime: no link-time dependency on libcuda.so
     cudaDriverEntryPointQueryResult qres;
     void* fn = nullptr;
@@ -106,7 +108,9 @@ int bsmr_ctx_destroy(bsmr_ctx* ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
     if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    if (ctx->side_stream2) cudaStreamDestroy(ctx->side_stream2);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return BSMR_OK;
@@ -204,6 +208,18 @@ static void reset_shard(bsmr_plan* p) {
     p->shard_res_end = p->num_res;
     p->shard_tile_begin = 0;
     p->shard_tile_end = p->num_tiles;
+    p->shard_wt_begin = 0;
+    p->shard_wt_end = p->num_wide_tiles;
+    p->shard_tile2_begin = 0;
+    p->shard_tile2_end = p->num_tiles2;
+    p->shard_res2_begin = 0;
+    p->shard_res2_end = p->num_res2;
+}
+
+int bsmr_plan_set_wide_ratio(bsmr_plan* plan, float ratio) {
+    if (!plan) return BSMR_ERR_INVALID_ARGUMENT;
+    plan->wide_ratio = ratio;
+    return BSMR_OK;
 }
 
 int bsmr_plan_row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flags) {
@@ -399,6 +415,15 @@ int bsmr_plan_get_info(bsmr_plan* plan, bsmr_plan_info* info) {
     info->col_reordering_ms = plan->col_ms;
     info->format_build_ms = plan->format_ms;
     info->cluster_kernel_ms = plan->cluster_ms;
+    info->num_row_groups = plan->num_groups;
+    info->num_wide_groups = plan->num_wide_groups;
+    info->num_wide_tiles = plan->num_wide_tiles;
+    const bool wide = plan->num_wide_tiles != 0;
+    info->num_block_tiles = wide ? plan->num_tiles2 : plan->num_tiles;
+    info->num_wide_values = plan->num_wide_values;
+    info->num_block_values = wide ? plan->num_block_values2 : plan->num_dense_values;
+    info->num_residual_values = wide ? plan->num_res2 : plan->num_res;
+    info->wide_format_ms = plan->wide_ms;
     return BSMR_OK;
 }
 
@@ -425,6 +450,17 @@ int bsmr_plan_set_shard(bsmr_plan* plan, uint32_t rank, uint32_t world, uint32_t
     uint32_t b = boundary(rank), e = boundary(rank + 1);
     if (b > panels) b = panels;
     if (e > panels) e = panels;
+    const uint32_t ppg = BSMR_WIDE_GROUP_ROWS / kPanel;
+    if (plan->num_wide_tiles) {
+        // a wide row group (8 panels) is one unit of work: move the boundaries to the nearest group boundary
+        auto snap = [&](uint32_t q) -> uint32_t {
+            if (q >= panels) return panels;
+            const uint32_t r = (q + ppg / 2) / ppg * ppg;
+            return r > panels ? panels : r;
+        };
+        b = rank == 0 ? 0 : snap(b);
+        e = rank + 1 == world ? panels : snap(e);
+    }
     if (e < b) e = b;
     plan->sharded = world > 1;
     plan->shard_first_panel = b;
@@ -435,6 +471,19 @@ int bsmr_plan_set_shard(bsmr_plan* plan, uint32_t rank, uint32_t world, uint32_t
     const std::vector<uint32_t>& tp = plan->h_tile_panel;
     plan->shard_tile_begin = static_cast<uint32_t>(std::lower_bound(tp.begin(), tp.end(), b) - tp.begin());
     plan->shard_tile_end = static_cast<uint32_t>(std::lower_bound(tp.begin(), tp.end(), e) - tp.begin());
+    if (plan->num_wide_tiles) {
+        const uint32_t gb = (b + ppg - 1) / ppg, ge = e >= panels ? plan->num_groups : e / ppg;   // b, e are group aligned here
+        plan->shard_wt_begin = plan->h_wt_group_off[gb];
+        plan->shard_wt_end = plan->h_wt_group_off[ge];
+        plan->shard_res2_begin = plan->h_rr2_group_off[gb];
+        plan->shard_res2_end = plan->h_rr2_group_off[ge];
+        const std::vector<uint32_t>& tp2 = plan->h_tile2_panel;
+        plan->shard_tile2_begin = static_cast<uint32_t>(std::lower_bound(tp2.begin(), tp2.end(), b) - tp2.begin());
+        plan->shard_tile2_end = static_cast<uint32_t>(std::lower_bound(tp2.begin(), tp2.end(), e) - tp2.begin());
+        BSMR_TRY(wide_partition(plan, plan->shard_wt_begin, plan->shard_wt_end));
+    } else {
+        plan->shard_wt_begin = plan->shard_wt_end = 0;
+    }
     if (first_panel) *first_panel = b;
     if (end_panel) *end_panel = e;
     if (shard_nnz) *shard_nnz = pre.empty() ? 0 : pre[e] - pre[b];
@@ -463,21 +512,44 @@ static int run_once(bsmr_plan* p, uint32_t K, const float* dA, const float* dB, 
                   "use BSMR_SDDMM_NO_REORDER for the CSR-order path");
         return BSMR_ERR_BAD_STATE;
     }
-    // dense-block kernel on the side stream (launched first: its CTAs take their shared memory / TMEM slots,
-    // the residual CTAs fill the remaining registers and warps), residual kernel on the main stream, join.
-    const bool dense = p->shard_tile_end > p->shard_tile_begin;
-    const bool residual = p->shard_res_end > p->shard_res_begin;
-    if (dense && residual) {
-        BSMR_CUDA_OK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-        BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
-        BSMR_TRY(launch_dense(p, K, dA, dB, dP, p->shard_tile_begin, p->shard_tile_end, ctx->side_stream));
-        BSMR_CUDA_OK(cudaEventRecord(ctx->ev_join, ctx->side_stream));
-        BSMR_TRY(launch_residual(ctx, K, dA, dB, dP, p->rr_row.ptr, p->rr_col.ptr, p->rr_out.ptr, p->shard_res_begin, p->shard_res_end));
-        BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-        return BSMR_OK;
+    // Three kernels over disjoint sets of nnz: the wide row-group kernel (side stream 2), the dense-block kernel
+    // (side stream; launched before the residual kernel so that its CTAs take their shared memory / TMEM slots) and
+    // the residual kernel (main stream), joined on the main stream.  Without wide groups -- or when the caller asks
+    // for the reference's split, or K does not fit the wide kernel -- the full BSMR lists are used.
+    const bool wide = p->num_wide_tiles != 0 && !(flags & BSMR_SDDMM_NO_WIDE) && wide_supports(K, dA, dB);
+    const uint32_t wt_b = wide ? p->shard_wt_begin : 0, wt_e = wide ? p->shard_wt_end : 0;
+    const uint32_t tl_b = wide ? p->shard_tile2_begin : p->shard_tile_begin, tl_e = wide ? p->shard_tile2_end : p->shard_tile_end;
+    const uint64_t rs_b = wide ? p->shard_res2_begin : p->shard_res_begin, rs_e = wide ? p->shard_res2_end : p->shard_res_end;
+    const uint32_t* tile_list = wide ? p->tile_list2.ptr : nullptr;
+    const uint32_t* rr_row = wide ? p->rr2_row.ptr : p->rr_row.ptr;
+    const uint32_t* rr_col = wide ? p->rr2_col.ptr : p->rr_col.ptr;
+    const uint32_t* rr_out = wide ? p->rr2_out.ptr : p->rr_out.ptr;
+    const bool do_wide = wt_e > wt_b, do_dense = tl_e > tl_b, do_res = rs_e > rs_b;
+    const int kinds = (int)do_wide + (int)do_dense + (int)do_res;
+    if (kinds <= 1) {
+        if (do_wide) return launch_wide(p, K, dA, dB, dP, wt_b, wt_e, ctx->stream);
+        if (do_dense) return launch_dense(p, K, dA, dB, dP, tl_b, tl_e, tile_list, ctx->stream);
+        return launch_residual(ctx, K, dA, dB, dP, rr_row, rr_col, rr_out, rs_b, rs_e);
     }
-    if (dense) return launch_dense(p, K, dA, dB, dP, p->shard_tile_begin, p->shard_tile_end, ctx->stream);
-    return launch_residual(ctx, K, dA, dB, dP, p->rr_row.ptr, p->rr_col.ptr, p->rr_out.ptr, p->shard_res_begin, p->shard_res_end);
+    BSMR_CUDA_OK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    if (do_wide) {
+        BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->side_stream2, ctx->ev_fork, 0));
+        BSMR_TRY(launch_wide(p, K, dA, dB, dP, wt_b, wt_e, ctx->side_stream2));
+        BSMR_CUDA_OK(cudaEventRecord(ctx->ev_join2, ctx->side_stream2));
+    }
+    if (do_dense && do_res) {
+        BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+        BSMR_TRY(launch_dense(p, K, dA, dB, dP, tl_b, tl_e, tile_list, ctx->side_stream));
+        BSMR_CUDA_OK(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+        BSMR_TRY(launch_residual(ctx, K, dA, dB, dP, rr_row, rr_col, rr_out, rs_b, rs_e));
+        BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    } else if (do_dense) {
+        BSMR_TRY(launch_dense(p, K, dA, dB, dP, tl_b, tl_e, tile_list, ctx->stream));
+    } else if (do_res) {
+        BSMR_TRY(launch_residual(ctx, K, dA, dB, dP, rr_row, rr_col, rr_out, rs_b, rs_e));
+    }
+    if (do_wide) BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));
+    return BSMR_OK;
 }
 
 int bsmr_sddmm(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP, int iterations, uint32_t flags,
@@ -508,39 +580,56 @@ int bsmr_sddmm(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, fl
     return BSMR_OK;
 }
 
-int bsmr_sddmm_profile(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP, uint32_t flags,
-                       float* dense_ms, float* residual_ms) {
+int bsmr_sddmm_profile3(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP, uint32_t flags,
+                        float* wide_ms, float* dense_ms, float* residual_ms) {
     if (!plan || !dA || !dB || (plan->nnz && !dP) || K == 0) return BSMR_ERR_INVALID_ARGUMENT;
     if (!plan->have_format || (flags & BSMR_SDDMM_NO_REORDER)) {
         set_error("bsmr_sddmm_profile: needs a reordered plan");
         return BSMR_ERR_BAD_STATE;
     }
+    bsmr_plan* p = plan;
     bsmr_ctx* ctx = plan->ctx;
     BSMR_CUDA_OK(cudaSetDevice(ctx->device));
-    cudaEvent_t mid;
+    const bool wide = p->num_wide_tiles != 0 && !(flags & BSMR_SDDMM_NO_WIDE) && wide_supports(K, dA, dB);
+    const uint32_t tl_b = wide ? p->shard_tile2_begin : p->shard_tile_begin, tl_e = wide ? p->shard_tile2_end : p->shard_tile_end;
+    const uint64_t rs_b = wide ? p->shard_res2_begin : p->shard_res_begin, rs_e = wide ? p->shard_res2_end : p->shard_res_end;
+    cudaEvent_t mid0, mid;
+    BSMR_CUDA_OK(cudaEventCreate(&mid0));
     BSMR_CUDA_OK(cudaEventCreate(&mid));
     int s = BSMR_OK;
     cudaEventRecord(ctx->ev0, ctx->stream);
-    if (plan->shard_tile_end > plan->shard_tile_begin)
-        s = launch_dense(plan, K, dA, dB, dP, plan->shard_tile_begin, plan->shard_tile_end, ctx->stream);
+    if (wide) s = launch_wide(p, K, dA, dB, dP, p->shard_wt_begin, p->shard_wt_end, ctx->stream);
+    cudaEventRecord(mid0, ctx->stream);
+    if (s == BSMR_OK) s = launch_dense(p, K, dA, dB, dP, tl_b, tl_e, wide ? p->tile_list2.ptr : nullptr, ctx->stream);
     cudaEventRecord(mid, ctx->stream);
     if (s == BSMR_OK)
-        s = launch_residual(ctx, K, dA, dB, dP, plan->rr_row.ptr, plan->rr_col.ptr, plan->rr_out.ptr,
-                            plan->shard_res_begin, plan->shard_res_end);
+        s = launch_residual(ctx, K, dA, dB, dP, wide ? p->rr2_row.ptr : p->rr_row.ptr, wide ? p->rr2_col.ptr : p->rr_col.ptr,
+                            wide ? p->rr2_out.ptr : p->rr_out.ptr, rs_b, rs_e);
     cudaEventRecord(ctx->ev1, ctx->stream);
     cudaError_t e = cudaEventSynchronize(ctx->ev1);
-    float a = 0.f, b = 0.f;
+    float w = 0.f, a = 0.f, b = 0.f;
     if (e == cudaSuccess) {
-        cudaEventElapsedTime(&a, ctx->ev0, mid);
+        cudaEventElapsedTime(&w, ctx->ev0, mid0);
+        cudaEventElapsedTime(&a, mid0, mid);
         cudaEventElapsedTime(&b, mid, ctx->ev1);
     }
+    cudaEventDestroy(mid0);
     cudaEventDestroy(mid);
     if (s == BSMR_OK && e != cudaSuccess) {
         set_error("bsmr_sddmm_profile: %s", cudaGetErrorString(e));
         s = BSMR_ERR_CUDA;
     }
+    if (wide_ms) *wide_ms = w;
     if (dense_ms) *dense_ms = a;
     if (residual_ms) *residual_ms = b;
+    return s;
+}
+
+int bsmr_sddmm_profile(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP, uint32_t flags,
+                       float* dense_ms, float* residual_ms) {
+    float w = 0.f, a = 0.f;
+    const int s = bsmr_sddmm_profile3(plan, K, dA, dB, dP, flags, &w, &a, residual_ms);
+    if (dense_ms) *dense_ms = w + a;
     return s;
 }
 

@@ -28,6 +28,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -35,6 +36,11 @@ namespace bsmr {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr uint32_t kWideRows = BSMR_WIDE_GROUP_ROWS;
+constexpr uint32_t kWideCols = BSMR_WIDE_TILE_COLS;
+constexpr uint32_t kWW = kWideCols / 32;                       // mask words per (tile, row) = 32-column chunks of a tile
+constexpr uint32_t kWH = kWideCols >= 128 ? kWideCols / 128 : 1;   // run starts per (tile, row): one per 128 columns
+constexpr uint32_t kWideStageRowWords = 36;   // row pitch of the wide kernel's epilogue staging (wide_tc.cu: kWEpiRowWords)
 
 inline int grid_for(uint64_t n, int per_cta, int sm_count) {
     uint64_t g = (n + per_cta - 1) / per_cta;
@@ -244,6 +250,159 @@ __global__ void compact_rows_kernel(const uint32_t* __restrict__ rows, uint32_t 
     }
 }
 
+
+// ---- wide row-group format (csrc/wide_tc.cu) ------------------------------------------------------------------
+// W0: (panel, column) runs -> key (group = panel / 8, column), value = nnz of the run
+__global__ void group_keys_kernel(const uint64_t* __restrict__ ukeys, const uint32_t* __restrict__ counts, uint32_t num_runs,
+                                  uint64_t* __restrict__ gkeys, uint32_t* __restrict__ gvals) {
+    for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < num_runs; u += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = ukeys[u];
+        gkeys[u] = (((k >> 32) / (kWideRows / kPanel)) << 32) | (k & 0xffffffffull);
+        gvals[u] = counts[u];
+    }
+}
+
+struct GroupOf {
+    __host__ __device__ uint32_t operator()(uint64_t k) const { return (uint32_t)(k >> 32); }
+};
+
+// W1: the distinct columns of every wide group, ascending (one CTA per wide group)
+__global__ void gather_wide_cols_kernel(uint32_t num_wide, const uint64_t* __restrict__ dkeys, const uint32_t* __restrict__ seg_begin,
+                                        const uint32_t* __restrict__ col_off, const uint32_t* __restrict__ ncols,
+                                        uint32_t* __restrict__ w_cols) {
+    for (uint32_t wi = blockIdx.x; wi < num_wide; wi += gridDim.x) {
+        const uint32_t s0 = seg_begin[wi], d0 = col_off[wi], n = ncols[wi];
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) w_cols[d0 + i] = (uint32_t)(dkeys[s0 + i] & 0xffffffffull);
+    }
+}
+
+// W2: masks and run starts (one warp per row of a wide group).  Also verifies that the row is sorted by column:
+// the contiguous-run epilogue of the wide kernel depends on it.
+__global__ void fill_wide_kernel(uint32_t num_wide, const uint32_t* __restrict__ wg_group, const uint32_t* __restrict__ col_off,
+                                 const uint32_t* __restrict__ ncols, const uint32_t* __restrict__ tile_off,
+                                 const uint32_t* __restrict__ rows, uint32_t R, const uint32_t* __restrict__ row_offsets,
+                                 const uint32_t* __restrict__ col_indices, const uint32_t* __restrict__ w_cols,
+                                 uint32_t* __restrict__ mask, uint32_t* __restrict__ base, uint32_t* __restrict__ unsorted) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t w = warp; w < (uint64_t)num_wide * kWideRows; w += stride) {
+        const uint32_t wi = (uint32_t)(w / kWideRows), r = (uint32_t)(w % kWideRows);
+        const uint64_t i = (uint64_t)wg_group[wi] * kWideRows + r;
+        if (i >= R) continue;
+        const uint32_t row = rows[i];
+        const uint32_t b = row_offsets[row], e = row_offsets[row + 1];
+        const uint32_t* cl = w_cols + col_off[wi];
+        const uint32_t n = ncols[wi], t0 = tile_off[wi];
+        for (uint32_t k = b + lane; k < e; k += 32) {
+            const uint32_t c = col_indices[k];
+            if (k > b && col_indices[k - 1] >= c) atomicExch(unsorted, 1u);
+            uint32_t lo = 0, hi = n;                      // lower_bound: the column is present by construction
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (cl[mid] < c) lo = mid + 1; else hi = mid;
+            }
+            const uint32_t t = t0 + lo / kWideCols, bit = lo % kWideCols;
+            atomicOr(mask + ((size_t)t * kWW + (bit >> 5)) * kWideRows + r, 1u << (bit & 31));
+            atomicMin(base + ((size_t)t * kWH + (bit >> 7)) * kWideRows + r, k);
+        }
+    }
+}
+
+// W2b: nnz of every 32 x 32 sub-block (tile, TMEM lane quarter, 32-column chunk); one warp per sub-block, lane = row
+__global__ void wide_subblock_count_kernel(uint32_t num_sb, const uint32_t* __restrict__ mask, uint32_t* __restrict__ sb_cnt) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t sb = warp; sb < num_sb; sb += stride) {
+        const uint32_t t = (uint32_t)(sb / (4 * kWW)), q = (uint32_t)(sb / kWW) & 3, j = (uint32_t)(sb % kWW);
+        uint32_t c = __popc(mask[((size_t)t * kWW + j) * kWideRows + q * 32 + lane]);
+#pragma unroll
+        for (int w = 16; w >= 1; w >>= 1) c += __shfl_xor_sync(0xffffffffu, c, w);
+        if (lane == 0) sb_cnt[sb] = c;
+    }
+}
+
+// W2b': entries of every (tile, quarter), padded to a multiple of 8 so that a quarter's list starts 16-byte aligned in
+// both entry arrays (the kernel copies it to shared memory with 16-byte cp.async)
+__global__ void wide_quarter_totals_kernel(uint32_t num_q, const uint32_t* __restrict__ sb_cnt, uint32_t* __restrict__ q_tot) {
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < num_q; q += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t s = 0;
+        for (uint32_t j = 0; j < kWW; ++j) s += sb_cnt[q * kWW + j];
+        q_tot[q] = (s + 7u) & ~7u;
+    }
+}
+// sb_off9[q * (kWW + 1) + j] = first entry of chunk j of quarter-tile q (j = kWW: end of the last chunk)
+__global__ void wide_subblock_offsets_kernel(uint32_t num_q, const uint32_t* __restrict__ sb_cnt, const uint32_t* __restrict__ q_base,
+                                             uint32_t* __restrict__ sb_off9) {
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < num_q; q += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t o = q_base[q];
+        for (uint32_t j = 0; j < kWW; ++j) {
+            sb_off9[q * (kWW + 1) + j] = o;
+            o += sb_cnt[q * kWW + j];
+        }
+        sb_off9[q * (kWW + 1) + kWW] = o;
+    }
+}
+
+// W2c: the epilogue's work list: per sub-block its entries in (row, column) order as
+// (byte offset of the element inside the epilogue's padded 32 x 32 staging image, CSR position).  Everything follows from the masks and the run
+// starts: a row's entries inside a tile half are consecutive CSR positions in ascending column order.
+__global__ void wide_subblock_fill_kernel(uint32_t num_sb, const uint32_t* __restrict__ mask, const uint32_t* __restrict__ base,
+                                          const uint32_t* __restrict__ sb_off, uint2* __restrict__ entries) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t sb = warp; sb < num_sb; sb += stride) {
+        const uint32_t t = (uint32_t)(sb / (4 * kWW)), q = (uint32_t)(sb / kWW) & 3, j = (uint32_t)(sb % kWW);
+        const uint32_t row = q * 32 + lane;
+        uint32_t m = mask[((size_t)t * kWW + j) * kWideRows + row];
+        const uint32_t cnt = __popc(m);
+        uint32_t incl = cnt;                          // inclusive warp scan over the rows
+#pragma unroll
+        for (int w = 1; w < 32; w <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, w);
+            if (lane >= (uint32_t)w) incl += o;
+        }
+        if (cnt == 0) continue;
+        uint32_t k = base[((size_t)t * kWH + (j >> 2)) * kWideRows + row];
+        for (uint32_t jj = j & ~3u; jj < j; ++jj) k += __popc(mask[((size_t)t * kWW + jj) * kWideRows + row]);
+        uint32_t e = sb_off[(sb / kWW) * (kWW + 1) + j] + incl - cnt;
+        while (m) {
+            const uint32_t b = __ffs(m) - 1;
+            m &= m - 1;
+            entries[e] = make_uint2((lane * kWideStageRowWords + b) * 4u, k);
+            ++e;
+            ++k;
+        }
+    }
+}
+
+// W3: first row-sorted residual entry of every row group
+__global__ void group_res_offsets_kernel(uint32_t groups, uint32_t R, const uint32_t* __restrict__ start,
+                                         const uint32_t* __restrict__ res_pos, uint32_t* __restrict__ out) {
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g <= groups; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = g * kWideRows < R ? g * kWideRows : R;
+        out[g] = res_pos[start[i]];
+    }
+}
+
+// W4: the residual entries of the groups that stay on the BSMR path, compacted (one CTA per group)
+__global__ void copy_group_ranges_kernel(uint32_t groups, const uint8_t* __restrict__ wide, const uint32_t* __restrict__ src_off,
+                                         const uint32_t* __restrict__ dst_off, const uint32_t* __restrict__ a0,
+                                         const uint32_t* __restrict__ a1, const uint32_t* __restrict__ a2,
+                                         uint32_t* __restrict__ b0, uint32_t* __restrict__ b1, uint32_t* __restrict__ b2) {
+    for (uint32_t g = blockIdx.x; g < groups; g += gridDim.x) {
+        if (wide[g]) continue;
+        const uint32_t s = src_off[g], n = src_off[g + 1] - s, d = dst_off[g];
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            b0[d + i] = a0[s + i];
+            b1[d + i] = a1[s + i];
+            b2[d + i] = a2[s + i];
+        }
+    }
+}
+
 int bits_for(uint64_t max_value) {
     int b = 1;
     while (b < 64 && (max_value >> b) != 0) ++b;
@@ -255,6 +414,231 @@ int d2h(std::vector<T>& dst, const T* src, size_t n, cudaStream_t s) {
     dst.resize(n);
     if (n) BSMR_CUDA_OK(cudaMemcpyAsync(dst.data(), src, n * sizeof(T), cudaMemcpyDeviceToHost, s));
     return BSMR_OK;
+}
+
+}  // namespace
+
+
+namespace {
+
+template <typename T>
+int h2d(T* dst, const std::vector<T>& src, cudaStream_t s) {
+    if (!src.empty()) BSMR_CUDA_OK(cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    return BSMR_OK;
+}
+
+float wide_ratio_of(const bsmr_plan* plan) {
+    if (plan->wide_ratio >= 0.f) return plan->wide_ratio;
+    if (const char* e = std::getenv("BSMR_WIDE_RATIO")) return static_cast<float>(std::atof(e));
+    return 2.0f;
+}
+
+// Everything the SDDMM kernels need to treat some row groups "wide" (see wide_tc.cu) and the others the BSMR way.
+// ukeys/counts: the (panel << 32 | column) runs of step B with their nnz; start: first enumerated nnz of every
+// reordered row; res_pos: exclusive scan of the residual flags over that enumeration (nullptr when there is no residual).
+int build_wide_format(bsmr_plan* plan, Workspace* ws, const uint64_t* ukeys, const uint32_t* counts, uint32_t num_runs,
+                      const uint32_t* start, const uint32_t* res_pos, const std::vector<uint32_t>& h_n_dense_data) {
+    bsmr_ctx* ctx = plan->ctx;
+    cudaStream_t st = ctx->stream;
+    const int sm = ctx->sm_count;
+    const uint32_t R = (uint32_t)plan->h_reordered_rows.size();
+    const uint32_t G = (R + kWideRows - 1) / kWideRows;
+    const uint32_t panels_per_group = kWideRows / kPanel;
+    plan->num_groups = G;
+    plan->num_wide_groups = plan->num_wide_tiles = 0;
+    plan->num_wide_values = 0;
+    plan->h_group_wide.assign(G, 0);
+    plan->h_wt_group_off.assign(static_cast<size_t>(G) + 1, 0);
+    plan->num_tiles2 = plan->num_tiles;
+    plan->num_res2 = plan->num_res;
+    plan->num_block_values2 = plan->num_dense_values;
+    plan->h_tile2_panel.clear();
+    plan->h_rr2_group_off.clear();
+    const float ratio = wide_ratio_of(plan);
+    if (ratio <= 0.f || num_runs == 0 || G == 0 || plan->N == 0) return BSMR_OK;
+
+    TmpBuf<uint8_t> temp(ws);
+    auto ensure_temp = [&](size_t bytes) -> int {
+        if (bytes > temp.count) return temp.alloc(bytes + bytes / 8 + 256);
+        return BSMR_OK;
+    };
+    // ---- distinct (group, column) pairs with their nnz ------------------------------------------------------
+    TmpBuf<uint64_t> gk_a(ws), gk_b(ws), dkeys(ws);
+    TmpBuf<uint32_t> gv_a(ws), gv_b(ws), dcnt(ws), num_d_dev(ws), gid(ws), gnnz(ws), gncols(ws), num_g_dev(ws);
+    BSMR_TRY(gk_a.alloc(num_runs)); BSMR_TRY(gk_b.alloc(num_runs)); BSMR_TRY(gv_a.alloc(num_runs)); BSMR_TRY(gv_b.alloc(num_runs));
+    group_keys_kernel<<<grid_for(num_runs, kThreads, sm), kThreads, 0, st>>>(ukeys, counts, num_runs, gk_a.ptr, gv_a.ptr);
+    ctx->launches++;
+    const int col_bits = bits_for(plan->N - 1), gbits = bits_for(G - 1);
+    size_t tb = 0, tb2 = 0;
+    cub::DoubleBuffer<uint64_t> dk(gk_a.ptr, gk_b.ptr);
+    cub::DoubleBuffer<uint32_t> dv(gv_a.ptr, gv_b.ptr);
+    BSMR_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, static_cast<int64_t>(num_runs), 0, col_bits, st));
+    BSMR_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tb2, dk, dv, static_cast<int64_t>(num_runs), 32, 32 + gbits, st));
+    BSMR_TRY(ensure_temp(std::max(tb, tb2)));
+    BSMR_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp.ptr, tb, dk, dv, static_cast<int64_t>(num_runs), 0, col_bits, st));
+    BSMR_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp.ptr, tb2, dk, dv, static_cast<int64_t>(num_runs), 32, 32 + gbits, st));
+    ctx->launches += 2;
+    BSMR_TRY(dkeys.alloc(num_runs)); BSMR_TRY(dcnt.alloc(num_runs)); BSMR_TRY(num_d_dev.alloc(1));
+    BSMR_CUDA_OK(cub::DeviceReduce::ReduceByKey(nullptr, tb, dk.Current(), dkeys.ptr, dv.Current(), dcnt.ptr, num_d_dev.ptr, cub::Sum(),
+                                                static_cast<int64_t>(num_runs), st));
+    BSMR_TRY(ensure_temp(tb));
+    BSMR_CUDA_OK(cub::DeviceReduce::ReduceByKey(temp.ptr, tb, dk.Current(), dkeys.ptr, dv.Current(), dcnt.ptr, num_d_dev.ptr, cub::Sum(),
+                                                static_cast<int64_t>(num_runs), st));
+    ctx->launches++;
+    uint32_t num_d = 0;
+    BSMR_CUDA_OK(cudaMemcpyAsync(&num_d, num_d_dev.ptr, 4, cudaMemcpyDeviceToHost, st));
+    BSMR_CUDA_OK(cudaStreamSynchronize(st));
+    // ---- per group: distinct columns and nnz ----------------------------------------------------------------
+    BSMR_TRY(gid.alloc(static_cast<size_t>(G) + 1)); BSMR_TRY(gnnz.alloc(static_cast<size_t>(G) + 1));
+    BSMR_TRY(gncols.alloc(static_cast<size_t>(G) + 1)); BSMR_TRY(num_g_dev.alloc(1));
+    auto group_it = thrust::make_transform_iterator(static_cast<const uint64_t*>(dkeys.ptr), GroupOf());
+    BSMR_CUDA_OK(cub::DeviceReduce::ReduceByKey(nullptr, tb, group_it, gid.ptr, dcnt.ptr, gnnz.ptr, num_g_dev.ptr, cub::Sum(),
+                                                static_cast<int64_t>(num_d), st));
+    BSMR_CUDA_OK(cub::DeviceRunLengthEncode::Encode(nullptr, tb2, group_it, gid.ptr, gncols.ptr, num_g_dev.ptr, static_cast<int64_t>(num_d), st));
+    BSMR_TRY(ensure_temp(std::max(tb, tb2)));
+    BSMR_CUDA_OK(cub::DeviceReduce::ReduceByKey(temp.ptr, tb, group_it, gid.ptr, dcnt.ptr, gnnz.ptr, num_g_dev.ptr, cub::Sum(),
+                                                static_cast<int64_t>(num_d), st));
+    BSMR_CUDA_OK(cub::DeviceRunLengthEncode::Encode(temp.ptr, tb2, group_it, gid.ptr, gncols.ptr, num_g_dev.ptr, static_cast<int64_t>(num_d), st));
+    ctx->launches += 2;
+    uint32_t num_g = 0;
+    BSMR_CUDA_OK(cudaMemcpyAsync(&num_g, num_g_dev.ptr, 4, cudaMemcpyDeviceToHost, st));
+    BSMR_CUDA_OK(cudaStreamSynchronize(st));
+    std::vector<uint32_t> h_gid, h_gnnz, h_gncols;
+    BSMR_TRY(d2h(h_gid, gid.ptr, num_g, st)); BSMR_TRY(d2h(h_gnnz, gnnz.ptr, num_g, st)); BSMR_TRY(d2h(h_gncols, gncols.ptr, num_g, st));
+    BSMR_CUDA_OK(cudaStreamSynchronize(st));
+
+    // ---- which groups go wide: nnz >= ratio * (256 * tiles + 128) ------------------------------------------
+    // (a tile moves (256 + its share of the 128 resident rows) K-vectors through L2 whatever its fill, the BSMR kernels
+    //  at most one K-vector per nnz)
+    std::vector<uint32_t> wg_group, wg_seg, wg_ncols, wg_col_off, wg_tile_off;
+    std::vector<uint4> h_meta;
+    uint32_t seg = 0, col_total = 0;
+    uint64_t wide_values = 0;
+    for (uint32_t i = 0; i < num_g; ++i) {
+        const uint32_t g = h_gid[i], nc = h_gncols[i];
+        const uint32_t tiles = (nc + kWideCols - 1) / kWideCols;
+        if (g < G && static_cast<double>(h_gnnz[i]) >= static_cast<double>(ratio) * (static_cast<double>(kWideCols) * tiles + kWideRows)) {
+            plan->h_group_wide[g] = 1;
+            wg_group.push_back(g); wg_seg.push_back(seg); wg_ncols.push_back(nc); wg_col_off.push_back(col_total);
+            wg_tile_off.push_back(static_cast<uint32_t>(h_meta.size()));
+            for (uint32_t c = 0; c < nc; c += kWideCols)
+                h_meta.push_back(make_uint4(g, col_total + c, nc - c < kWideCols ? nc - c : kWideCols, 0u));
+            col_total += nc;
+            wide_values += h_gnnz[i];
+        }
+        seg += nc;
+    }
+    const uint32_t num_wide = static_cast<uint32_t>(wg_group.size());
+    if (num_wide == 0) return BSMR_OK;
+    const uint32_t wtiles = static_cast<uint32_t>(h_meta.size());
+
+    TmpBuf<uint32_t> d_wg_group(ws), d_wg_seg(ws), d_wg_ncols(ws), d_wg_col_off(ws), d_wg_tile_off(ws), d_unsorted(ws);
+    BSMR_TRY(d_wg_group.alloc(num_wide)); BSMR_TRY(d_wg_seg.alloc(num_wide)); BSMR_TRY(d_wg_ncols.alloc(num_wide));
+    BSMR_TRY(d_wg_col_off.alloc(num_wide)); BSMR_TRY(d_wg_tile_off.alloc(num_wide)); BSMR_TRY(d_unsorted.alloc(1));
+    BSMR_TRY(h2d(d_wg_group.ptr, wg_group, st)); BSMR_TRY(h2d(d_wg_seg.ptr, wg_seg, st)); BSMR_TRY(h2d(d_wg_ncols.ptr, wg_ncols, st));
+    BSMR_TRY(h2d(d_wg_col_off.ptr, wg_col_off, st)); BSMR_TRY(h2d(d_wg_tile_off.ptr, wg_tile_off, st));
+    BSMR_CUDA_OK(cudaMemsetAsync(d_unsorted.ptr, 0, 4, st));
+    BSMR_TRY(plan->wt_meta.alloc(wtiles)); BSMR_TRY(plan->w_cols.alloc(col_total));
+    BSMR_TRY(plan->w_mask.alloc(static_cast<size_t>(wtiles) * kWW * kWideRows));
+    BSMR_TRY(plan->w_base.alloc(static_cast<size_t>(wtiles) * kWH * kWideRows));
+    BSMR_TRY(h2d(plan->wt_meta.ptr, h_meta, st));
+    BSMR_CUDA_OK(cudaMemsetAsync(plan->w_mask.ptr, 0, plan->w_mask.bytes(), st));
+    BSMR_CUDA_OK(cudaMemsetAsync(plan->w_base.ptr, 0xFF, plan->w_base.bytes(), st));
+    gather_wide_cols_kernel<<<(num_wide < (uint32_t)sm * 8 ? num_wide : (uint32_t)sm * 8), 256, 0, st>>>(
+        num_wide, dkeys.ptr, d_wg_seg.ptr, d_wg_col_off.ptr, d_wg_ncols.ptr, plan->w_cols.ptr);
+    fill_wide_kernel<<<grid_for((uint64_t)num_wide * kWideRows * 32, kThreads, sm), kThreads, 0, st>>>(
+        num_wide, d_wg_group.ptr, d_wg_col_off.ptr, d_wg_ncols.ptr, d_wg_tile_off.ptr, plan->reordered_rows.ptr, R,
+        plan->row_offsets.ptr, plan->col_indices.ptr, plan->w_cols.ptr, plan->w_mask.ptr, plan->w_base.ptr, d_unsorted.ptr);
+    ctx->launches += 2;
+    // the epilogue's work lists (32 sub-blocks per tile)
+    const uint32_t num_sb = wtiles * 4u * kWW;
+    const uint32_t num_q = wtiles * 4u;
+    TmpBuf<uint32_t> sb_cnt(ws), q_tot(ws), q_base(ws);
+    BSMR_TRY(sb_cnt.alloc(num_sb));
+    BSMR_TRY(q_tot.alloc(static_cast<size_t>(num_q) + 1));
+    BSMR_TRY(q_base.alloc(static_cast<size_t>(num_q) + 1));
+    BSMR_TRY(plan->w_sb_off.alloc(static_cast<size_t>(num_q) * (kWW + 1)));
+    // every quarter-tile list is padded to 8 entries; 16 more so that the kernel's 16-byte copies may run past the end
+    const size_t list_cap = static_cast<size_t>(wide_values) + 8u * num_q + 16;
+    BSMR_TRY(plan->w_entries.alloc(list_cap));
+    BSMR_CUDA_OK(cudaMemsetAsync(plan->w_entries.ptr, 0, plan->w_entries.bytes(), st));
+    BSMR_CUDA_OK(cudaMemsetAsync(q_tot.ptr + num_q, 0, 4, st));
+    wide_subblock_count_kernel<<<grid_for((uint64_t)num_sb * 32, kThreads, sm), kThreads, 0, st>>>(num_sb, plan->w_mask.ptr, sb_cnt.ptr);
+    wide_quarter_totals_kernel<<<grid_for(num_q, kThreads, sm), kThreads, 0, st>>>(num_q, sb_cnt.ptr, q_tot.ptr);
+    BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb, q_tot.ptr, q_base.ptr, static_cast<size_t>(num_q) + 1, st));
+    BSMR_TRY(ensure_temp(tb));
+    BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(temp.ptr, tb, q_tot.ptr, q_base.ptr, static_cast<size_t>(num_q) + 1, st));
+    wide_subblock_offsets_kernel<<<grid_for(num_q, kThreads, sm), kThreads, 0, st>>>(num_q, sb_cnt.ptr, q_base.ptr, plan->w_sb_off.ptr);
+    wide_subblock_fill_kernel<<<grid_for((uint64_t)num_sb * 32, kThreads, sm), kThreads, 0, st>>>(
+        num_sb, plan->w_mask.ptr, plan->w_base.ptr, plan->w_sb_off.ptr, plan->w_entries.ptr);
+    ctx->launches += 2;
+    ctx->launches += 3;
+    uint32_t unsorted = 0;
+    BSMR_CUDA_OK(cudaMemcpyAsync(&unsorted, d_unsorted.ptr, 4, cudaMemcpyDeviceToHost, st));
+    BSMR_CUDA_OK(cudaStreamSynchronize(st));   // also keeps the host vectors above alive until their copies are done
+    if (unsorted) {
+        // a CSR row that is not sorted by column breaks the contiguous-run epilogue: stay on the BSMR kernels
+        plan->h_group_wide.assign(G, 0);
+        return BSMR_OK;
+    }
+
+    // ---- the BSMR-path work lists without the wide groups ---------------------------------------------------
+    std::vector<uint32_t> h_rr_goff(static_cast<size_t>(G) + 1, 0);
+    if (plan->num_res) {
+        TmpBuf<uint32_t> d_goff(ws);
+        BSMR_TRY(d_goff.alloc(static_cast<size_t>(G) + 1));
+        group_res_offsets_kernel<<<grid_for(static_cast<uint64_t>(G) + 1, kThreads, sm), kThreads, 0, st>>>(G, R, start, res_pos, d_goff.ptr);
+        ctx->launches++;
+        BSMR_TRY(d2h(h_rr_goff, d_goff.ptr, static_cast<size_t>(G) + 1, st));
+        BSMR_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    std::vector<uint32_t> h_dst(static_cast<size_t>(G) + 1, 0);
+    plan->h_rr2_group_off.assign(static_cast<size_t>(G) + 1, 0);
+    for (uint32_t g = 0; g < G; ++g) {
+        const uint32_t n = plan->h_group_wide[g] ? 0u : h_rr_goff[g + 1] - h_rr_goff[g];
+        h_dst[g + 1] = h_dst[g] + n;
+        plan->h_rr2_group_off[g + 1] = h_dst[g + 1];
+    }
+    plan->num_res2 = h_dst[G];
+    BSMR_TRY(plan->rr2_row.alloc(plan->num_res2)); BSMR_TRY(plan->rr2_col.alloc(plan->num_res2)); BSMR_TRY(plan->rr2_out.alloc(plan->num_res2));
+    if (plan->num_res2) {
+        TmpBuf<uint32_t> d_src(ws), d_dst(ws);
+        TmpBuf<uint8_t> d_wide(ws);
+        BSMR_TRY(d_src.alloc(static_cast<size_t>(G) + 1)); BSMR_TRY(d_dst.alloc(static_cast<size_t>(G) + 1)); BSMR_TRY(d_wide.alloc(G));
+        BSMR_TRY(h2d(d_src.ptr, h_rr_goff, st)); BSMR_TRY(h2d(d_dst.ptr, h_dst, st)); BSMR_TRY(h2d(d_wide.ptr, plan->h_group_wide, st));
+        copy_group_ranges_kernel<<<(G < (uint32_t)sm * 8 ? G : (uint32_t)sm * 8), 256, 0, st>>>(
+            G, d_wide.ptr, d_src.ptr, d_dst.ptr, plan->rr_row.ptr, plan->rr_col.ptr, plan->rr_out.ptr,
+            plan->rr2_row.ptr, plan->rr2_col.ptr, plan->rr2_out.ptr);
+        ctx->launches++;
+        BSMR_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    std::vector<uint32_t> h_list;
+    uint64_t block_values = 0;
+    for (uint32_t t = 0; t < plan->num_tiles; ++t) {
+        const uint32_t pnl = plan->h_tile_panel[t];
+        if (!plan->h_group_wide[pnl / panels_per_group]) {
+            h_list.push_back(t);
+            plan->h_tile2_panel.push_back(pnl);
+        }
+    }
+    for (uint32_t q = 0; q < plan->num_row_panels; ++q)
+        if (!plan->h_group_wide[q / panels_per_group]) block_values += h_n_dense_data[q];
+    plan->num_tiles2 = static_cast<uint32_t>(h_list.size());
+    plan->num_block_values2 = block_values;
+    BSMR_TRY(plan->tile_list2.alloc(h_list.size()));
+    BSMR_TRY(h2d(plan->tile_list2.ptr, h_list, st));
+    BSMR_CUDA_OK(cudaStreamSynchronize(st));
+
+    for (uint32_t i = 0, g = 0; g <= G; ++g) {      // first wide tile at or after every group
+        while (i < num_wide && wg_group[i] < g) ++i;
+        plan->h_wt_group_off[g] = i < num_wide ? wg_tile_off[i] : wtiles;
+    }
+    plan->num_wide_groups = num_wide;
+    plan->num_wide_tiles = wtiles;
+    plan->num_wide_values = wide_values;
+    plan->h_wt_group.resize(wtiles);
+    for (uint32_t t = 0; t < wtiles; ++t) plan->h_wt_group[t] = h_meta[t].x;
+    return wide_partition(plan, 0, wtiles);
 }
 
 }  // namespace
@@ -476,8 +860,19 @@ int col_reorder_and_format(bsmr_plan* plan, float delta) {
         }
     }
     BSMR_TRY(d2h(plan->h_tile_panel, plan->tile_panel.ptr, total_tiles, st));
+    BSMR_CUDA_OK(cudaStreamSynchronize(st));
+    plan->num_dense_values = 0;
+    for (uint32_t p = 0; p < panels; ++p) plan->num_dense_values += h_n_dense_data[p];
+    // ---- W: wide row groups (our own execution plan on top of the BSMR split) ------------------------------
+    cudaEvent_t ew;
+    BSMR_CUDA_OK(cudaEventCreate(&ew));
+    BSMR_CUDA_OK(cudaEventRecord(ew, st));
+    const int ws_status = build_wide_format(plan, ws, ukeys.ptr, counts.ptr, num_runs, start.ptr, total_res ? res_pos.ptr : nullptr, h_n_dense_data);
+    if (ws_status != BSMR_OK) { cudaEventDestroy(ew); return ws_status; }
     BSMR_CUDA_OK(cudaEventRecord(e2, st));
     BSMR_CUDA_OK(cudaEventSynchronize(e2));
+    cudaEventElapsedTime(&plan->wide_ms, ew, e2);
+    cudaEventDestroy(ew);
     BSMR_CUDA_OK(cudaGetLastError());
     BSMR_CUDA_OK(cudaEventElapsedTime(&plan->col_ms, e0, e1));
     BSMR_CUDA_OK(cudaEventElapsedTime(&plan->format_ms, e1, e2));

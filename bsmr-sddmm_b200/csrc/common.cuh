@@ -155,8 +155,8 @@ struct bsmr_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // the dense-block kernel runs on a side stream so that it overlaps the residual kernel
     // (the reference also uses one stream per kernel, src/sddmmKernel.cu:2555-2559)
-    cudaStream_t side_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t side_stream = nullptr, side_stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
     // tensor-map encoder resolved at runtime (no link-time dependency on libcuda)
     void* encode_tiled = nullptr;
     bsmr::Workspace ws;     // scratch of the reorder passes
@@ -207,6 +207,32 @@ struct bsmr_plan {
     uint64_t num_dense_values = 0;
     std::vector<uint64_t> h_panel_nnz_prefix;  // nnz (dense + residual) before each panel
 
+    // ---- wide row groups (128 reordered rows = 8 panels each; csrc/wide_tc.cu) ----
+    float wide_ratio = -1.f;                  // < 0: default / environment
+    uint32_t num_groups = 0, num_wide_groups = 0, num_wide_tiles = 0;
+    uint64_t num_wide_values = 0;
+    float wide_ms = 0.f;
+    std::vector<uint8_t> h_group_wide;        // per row group
+    std::vector<uint32_t> h_wt_group_off;     // per row group (+1): first wide tile
+    bsmr::DevBuf<uint4> wt_meta;              // {group, first column (offset into w_cols), #columns, 0} per wide tile
+    bsmr::DevBuf<uint32_t> w_cols;            // distinct columns of the wide groups, ascending inside a group
+    bsmr::DevBuf<uint32_t> w_mask;            // [tile][8][128]
+    bsmr::DevBuf<uint32_t> w_base;            // [tile][2][128]
+    bsmr::DevBuf<uint32_t> w_sb_off;          // [(tile * 4 + quarter) * 9 + chunk]: first entry of the 32 x 32 sub-block (chunk 8: end);
+                                              // a quarter-tile's list starts at a multiple of 8 entries
+    bsmr::DevBuf<uint2> w_entries;            // entry: {byte offset inside the epilogue's staging image, CSR position}
+    std::vector<uint32_t> h_wt_group;         // row group of every wide tile
+    bsmr::DevBuf<uint32_t> w_cta_begin;       // CTA -> first tile, for tiles [w_part_begin, w_part_end) (wide_partition)
+    uint32_t w_part_begin = 0, w_part_end = 0, w_grid = 0;
+    // dense-block tiles and residual entries of the groups that are NOT wide (what runs next to the wide kernel)
+    bsmr::DevBuf<uint32_t> tile_list2;        // tile ids (ascending)
+    std::vector<uint32_t> h_tile2_panel;      // panel of tile_list2[i]
+    uint32_t num_tiles2 = 0;
+    bsmr::DevBuf<uint32_t> rr2_row, rr2_col, rr2_out;
+    uint64_t num_res2 = 0;
+    std::vector<uint64_t> h_rr2_group_off;    // per row group (+1): first entry of the group in rr2
+    uint64_t num_block_values2 = 0;           // nnz of the dense-block tiles outside the wide groups
+
     // ---- identity ("no reorder") residual list, built lazily ----
     bsmr::DevBuf<uint32_t> csr_row_of_nnz;
 
@@ -214,6 +240,9 @@ struct bsmr_plan {
     uint32_t shard_first_panel = 0, shard_end_panel = 0;
     uint64_t shard_res_begin = 0, shard_res_end = 0;
     uint32_t shard_tile_begin = 0, shard_tile_end = 0;
+    uint32_t shard_wt_begin = 0, shard_wt_end = 0;        // wide tiles
+    uint32_t shard_tile2_begin = 0, shard_tile2_end = 0;  // positions in tile_list2
+    uint64_t shard_res2_begin = 0, shard_res2_end = 0;    // positions in rr2
     bool sharded = false;
 
     // scratch for the host-data overload
@@ -230,8 +259,13 @@ int launch_expand_rows(bsmr_ctx* ctx, uint32_t M, uint32_t nnz, const uint32_t* 
 
 int col_reorder_and_format(bsmr_plan* plan, float delta);
 int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flags);
+// tile_list != nullptr: positions [tile_begin, tile_end) of that list of tile ids; else the tile ids themselves
 int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP,
-                 uint32_t tile_begin, uint32_t tile_end, cudaStream_t stream);
+                 uint32_t tile_begin, uint32_t tile_end, const uint32_t* tile_list, cudaStream_t stream);
+bool wide_supports(uint32_t K, const float* dA, const float* dB);
+int wide_partition(bsmr_plan* plan, uint32_t tile_begin, uint32_t tile_end);
+int launch_wide(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP,
+                uint32_t tile_begin, uint32_t tile_end, cudaStream_t stream);
 int evaluate_reordering(bsmr_plan* plan, float delta, bsmr_reorder_stats* stats);
 
 }  // namespace bsmr

@@ -36,9 +36,12 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace bsmr {
 namespace {
+
+using namespace tc;
 
 constexpr int kStages = 5;
 constexpr int kChunk = 32;                         // floats of K per stage (128 bytes)
@@ -53,7 +56,6 @@ constexpr int kConvWarp0 = kProducerWarps + 5;    // first of 4 converter warps
 constexpr int kDenseThreads = (kProducerWarps + 9) * 32;
 constexpr int kAccs = 4;                           // TMEM accumulators in rotation (tile i+4 waits for the epilogue of tile i)
 constexpr int kTmemCols = kAccs * 16;              // 16 fp32 columns each
-constexpr uint32_t kSpinLimit = 1u << 28;
 
 struct __align__(16) DenseSmemTail {
     uint64_t full[kStages];    // TMA bytes landed
@@ -65,86 +67,6 @@ struct __align__(16) DenseSmemTail {
     uint32_t pad[3];
 };
 constexpr size_t kDenseSmemBytes = 1024 /*alignment slack*/ + (size_t)kStages * (kBTileBytes + kATileBytes) + sizeof(DenseSmemTail);
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a wrong transaction count must become an error, never a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* error_flag, uint32_t code) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > kSpinLimit) {
-            atomicExch(error_flag, code);
-            __trap();
-        }
-    }
-}
-
-__device__ __forceinline__ void tma_gather4(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int4 rows) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes.cta_group::1"
-        " [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(rows.x), "r"(rows.y), "r"(rows.z), "r"(rows.w), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ float rna_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp, SmemDescriptor):
-// start address >> 4 in [0,14), LBO = 0, SBO = 1024 bytes (8 rows x 128 B) >> 4 in [32,46),
-// version = 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
-    d |= static_cast<uint64_t>(1024u >> 4) << 32;
-    d |= 1ull << 46;
-    d |= 2ull << 61;
-    return d;
-}
-
-// Instruction descriptor for kind::tf32, fp32 accumulate, A and B K-major, M x N
-// (InstrDescriptor: c_format [4,6) = 1 (F32), a_format [7,10) = 2 (TF32), b_format [10,13) = 2,
-//  a_major bit 15 = 0, b_major bit 16 = 0, n_dim [17,23) = N >> 3, m_dim [24,29) = M >> 4).
-__host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 struct DenseParams {
     uint32_t K;
@@ -159,6 +81,7 @@ struct DenseParams {
     const uint32_t* tile_ncols;
     const uint32_t* tile_scatter;
     const uint4* tile_meta;      // {panel, first dense column (offset into dense_cols), #columns, 0} per tile
+    const uint32_t* tile_list;   // optional: [tile_begin, tile_end) index this list of tile ids (groups on the wide path removed)
     float* P;
     uint32_t* error_flag;
     uint32_t* debug_smem;    // optional: raw copy of stage 0 of the first tile (probe / tests)
@@ -167,7 +90,9 @@ struct DenseParams {
 __global__ void __launch_bounds__(kDenseThreads, 2)
 dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const DenseParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array: an integer round trip loses the address space
+    // and every access below would become a generic LD/ST instead of LDS/STS (seen in SASS, 3-5x slower)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* b_tiles = smem;                                   // kStages x 16 KB, 1024-aligned
     uint8_t* a_tiles = smem + (size_t)kStages * kBTileBytes;     // kStages x 2 KB, 1024-aligned
     DenseSmemTail* tail = reinterpret_cast<DenseSmemTail*>(a_tiles + (size_t)kStages * kATileBytes);
@@ -208,7 +133,8 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         // of a stage needed ~1.7 us per stage, four warps ~0.6 us.  (One lane issuing 8 requests from straight-line code
         // was slower still: measured.)
         uint32_t stage = 0, phase = 0;
-        auto fetch = [&](uint32_t t, uint32_t& nc, int4& cols, int4& rows) {
+        auto fetch = [&](uint32_t ti, uint32_t& nc, int4& cols, int4& rows) {
+            const uint32_t t = p.tile_list ? __ldg(p.tile_list + ti) : ti;
             const uint4 m = __ldg(p.tile_meta + t);
             nc = m.z;
             cols = make_int4((int)p.N, (int)p.N, (int)p.N, (int)p.N);
@@ -321,7 +247,8 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const uint32_t quarter = warp & 3;              // TMEM lanes [32*quarter, 32*quarter + 32)
         const uint32_t c = quarter * 32 + lane;         // dense column of the tile owned by this thread
         uint32_t it = 0;
-        for (uint32_t t = p.tile_begin + blockIdx.x; t < p.tile_end; t += gridDim.x, ++it) {
+        for (uint32_t ti = p.tile_begin + blockIdx.x; ti < p.tile_end; ti += gridDim.x, ++it) {
+            const uint32_t t = p.tile_list ? __ldg(p.tile_list + ti) : ti;
             const uint32_t acc = it % kAccs, acc_phase = (it / kAccs) & 1;
             const uint32_t nc = __ldg(p.tile_meta + t).z;
             const bool active = quarter * 32 < nc;
@@ -396,7 +323,7 @@ static uint32_t* g_debug_smem = nullptr;
 extern "C" void bsmr_debug_set_dense_smem_dump(uint32_t* device_buffer) { g_debug_smem = device_buffer; }
 
 int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP, uint32_t tile_begin, uint32_t tile_end,
-                 cudaStream_t stream) {
+                 const uint32_t* tile_list, cudaStream_t stream) {
     bsmr_ctx* ctx = plan->ctx;
     if (tile_end <= tile_begin) return BSMR_OK;
     if (K % 4 != 0 || (reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(dB)) % 16 != 0) {
@@ -428,6 +355,7 @@ int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, 
     p.tile_ncols = plan->tile_ncols.ptr;
     p.tile_scatter = plan->tile_scatter.ptr;
     p.tile_meta = plan->tile_meta.ptr;
+    p.tile_list = tile_list;
     p.P = dP;
     p.error_flag = error_flag.ptr;
     p.debug_smem = g_debug_smem;

@@ -1,0 +1,99 @@
+// Device-side building blocks shared by the tcgen05 kernels (dense_tc.cu, wide_tc.cu): mbarrier, TMA gather,
+// tcgen05 fences / MMA / commit, UMMA shared-memory and instruction descriptors.  Inline PTX only.
+#pragma once
+
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace bsmr {
+namespace tc {
+
+constexpr uint32_t kSpinLimit = 1u << 24;   // x >= 200 ns: seconds
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a wrong transaction count must become an error, never a hung GPU.  After a few immediate polls the
+// warp backs off with nanosleep: a warp that spins on try_wait is always "ready" and takes issue slots from the warps
+// that share its scheduler (measured in the wide kernel: the epilogue warps ran 3x slower next to spinning producers).
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* error_flag, uint32_t code) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > 4) __nanosleep(spins < 64 ? 40 : 200);
+        if (spins > kSpinLimit) {
+            atomicExch(error_flag, code);
+            __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_gather4(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int4 rows) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes.cta_group::1"
+        " [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(rows.x), "r"(rows.y), "r"(rows.z), "r"(rows.w), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp, SmemDescriptor):
+// start address >> 4 in [0,14), LBO = 0, SBO = 1024 bytes (8 rows x 128 B) >> 4 in [32,46),
+// version = 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>(1024u >> 4) << 32;
+    d |= 1ull << 46;
+    d |= 2ull << 61;
+    return d;
+}
+
+// Instruction descriptor for kind::tf32, fp32 accumulate, A and B K-major, M x N
+// (InstrDescriptor: c_format [4,6) = 1 (F32), a_format [7,10) = 2 (TF32), b_format [10,13) = 2,
+//  a_major bit 15 = 0, b_major bit 16 = 0, n_dim [17,23) = N >> 3, m_dim [24,29) = M >> 4).
+__host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+
+}  // namespace tc
+}  // namespace bsmr

@@ -32,6 +32,10 @@ extern "C" {
 #define BSMR_ROW_PANEL_SIZE 16u        /* ROW_PANEL_SIZE, include/BSMR.hpp:8  */
 #define BSMR_BLOCK_COL_SIZE 16u        /* BLOCK_COL_SIZE, include/BSMR.hpp:9  */
 #define BSMR_NULL_VALUE 0xFFFFFFFFu    /* NULL_VALUE, include/TensorCoreConfig.cuh:12 */
+/* wide row groups (no counterpart in the reference): 128 consecutive reordered rows (8 panels) whose
+ * distinct columns stream through one 128 x 128 tcgen05 tile at a time; see csrc/wide_tc.cu          */
+#define BSMR_WIDE_GROUP_ROWS 128u
+#define BSMR_WIDE_TILE_COLS  128u
 
 typedef enum {
     BSMR_OK = 0,
@@ -134,6 +138,17 @@ typedef struct {
     float col_reordering_ms;      /* BSMR::colReorderingTime()                            */
     float format_build_ms;        /* RPHM::time()                                         */
     float cluster_kernel_ms;      /* part of row_reordering_ms spent in the clustering kernel */
+    /* execution plan of the SDDMM kernels (internal layout, not part of the reference's BSMR object):
+     * row groups that are dense enough at 128-row scale run through the wide tcgen05 kernel, the
+     * remaining groups through the dense-block + residual kernels                                 */
+    uint32_t num_row_groups;      /* ceil(#reordered rows / 128)                               */
+    uint32_t num_wide_groups;     /* row groups on the wide path                               */
+    uint32_t num_wide_tiles;      /* 128 x <=128 tcgen05 work items of the wide path           */
+    uint32_t num_block_tiles;     /* dense-block tiles left outside the wide groups            */
+    uint64_t num_wide_values;     /* nnz computed by the wide kernel                           */
+    uint64_t num_block_values;    /* nnz computed by the dense-block kernel (outside wide groups) */
+    uint64_t num_residual_values; /* nnz computed by the residual kernel (outside wide groups) */
+    float wide_format_ms;         /* part of format_build_ms spent on the wide-group format    */
 } bsmr_plan_info;
 int bsmr_plan_get_info(bsmr_plan* plan, bsmr_plan_info* info);
 
@@ -154,6 +169,7 @@ int bsmr_plan_set_shard(bsmr_plan* plan, uint32_t rank, uint32_t world,
 #define BSMR_SDDMM_DEFAULT        0u
 #define BSMR_SDDMM_RESIDUAL_ONLY  1u   /* every nnz through the CUDA-core kernel (delta > 1) */
 #define BSMR_SDDMM_NO_REORDER     2u   /* ignore the plan's reorder: CSR order, residual kernel */
+#define BSMR_SDDMM_NO_WIDE        4u   /* dense-block + residual kernels only, exactly the reference's split */
 int bsmr_sddmm(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP,
                int iterations, uint32_t flags, float* ms_per_iteration);
 
@@ -168,6 +184,14 @@ int bsmr_sddmm_host(bsmr_plan* plan, uint32_t K, const float* hA, const float* h
  * what bench.py's roofline block reports per kernel.  Either output may be NULL.          */
 int bsmr_sddmm_profile(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP,
                        uint32_t flags, float* dense_ms, float* residual_ms);
+/* The same with the wide row-group kernel timed on its own (dense_ms above = wide + dense-block). */
+int bsmr_sddmm_profile3(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP,
+                        uint32_t flags, float* wide_ms, float* dense_ms, float* residual_ms);
+
+/* Wide-path policy of a plan, applied at the next column reorder: a row group goes wide when
+ * nnz(group) >= ratio * (128 * tiles(group) + 128).  ratio <= 0 disables the wide path; the default
+ * is 2.0 (environment override: BSMR_WIDE_RATIO).                                              */
+int bsmr_plan_set_wide_ratio(bsmr_plan* plan, float ratio);
 
 /* Number of kernels of this library launched on the context so far (bench.py's gpu_launches). */
 int bsmr_ctx_launch_count(bsmr_ctx* ctx, uint64_t* count);

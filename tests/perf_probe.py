@@ -66,18 +66,24 @@ def main():
                     col_wall = (time.perf_counter() - t0) * 1e3
                 info = plan.info()
                 hot = plan.sddmm(K, dA, dB, dP, iterations=100)
-                dms, rms = [], []
+                wms, dms, rms = [], [], []
                 for _ in range(10):
                     flush.fill_(1)
-                    a, b = plan.sddmm_profile(K, dA, dB, dP)
+                    w, a, b = plan.sddmm_profile3(K, dA, dB, dP)
+                    wms.append(w)
                     dms.append(a)
                     rms.append(b)
+                hot_nowide = plan.sddmm(K, dA, dB, dP, iterations=100, flags=pkg.SDDMM_NO_WIDE)
                 tag = "d%.1f" % delta
                 out[tag] = {"col_ms": info["col_reordering_ms"], "fmt_ms": info["format_build_ms"], "col_wall_ms": col_wall,
                             "dense_nnz": int(info["num_dense_values"]), "res_nnz": int(info["num_sparse_values"]),
                             "tiles": info["num_dense_tiles"], "hot_ms": hot, "hot_gflops": 2.0 * nnz * K / hot / 1e6,
+                            "hot_nowide_ms": hot_nowide,
+                            "wide": [info["num_wide_groups"], info["num_row_groups"], info["num_wide_tiles"], int(info["num_wide_values"]),
+                                     int(info["num_block_values"]), int(info["num_residual_values"]), info["wide_format_ms"]],
+                            "cold_wide_ms": float(np.median(wms)),
                             "cold_dense_ms": float(np.median(dms)), "cold_res_ms": float(np.median(rms)),
-                            "cold_gflops": 2.0 * nnz * K / (np.median(dms) + np.median(rms)) / 1e6}
+                            "cold_gflops": 2.0 * nnz * K / (np.median(wms) + np.median(dms) + np.median(rms)) / 1e6}
             hot = plan.sddmm(K, dA, dB, dP, iterations=100, flags=pkg.SDDMM_NO_REORDER)
             out["csr_order"] = {"hot_ms": hot, "hot_gflops": 2.0 * nnz * K / hot / 1e6}
             print(json.dumps(out), flush=True)

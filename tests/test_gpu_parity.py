@@ -175,12 +175,15 @@ def test_sddmm_all_residual_after_reorder(pkg, ctx, oracle, K):
         assert oracle.check_data(want, got) == 0, (name, K)
 
 
+@pytest.mark.parametrize("wide", [False, True])
 @pytest.mark.parametrize("K,delta", [(32, 0.3), (64, 0.1), (128, 0.3), (256, 0.0), (128, 0.0), (96, 0.1), (40, 0.1)])
-def test_sddmm_dense_plus_residual(pkg, ctx, oracle, K, delta):
-    """Full hot path: tcgen05 dense-block kernel + residual kernel, TF32 x TF32 -> fp32 on the dense part."""
+def test_sddmm_dense_plus_residual(pkg, ctx, oracle, K, delta, wide):
+    """Full hot path: tcgen05 dense-block kernel + residual kernel, TF32 x TF32 -> fp32 on the dense part.
+    wide=False pins the reference's split (every nnz through one of those two kernels); wide=True is the default
+    execution plan, in which row groups that are dense at 128-row scale run through the wide tcgen05 kernel."""
     worst = 0.0
     for name, M, N, ro, ci in small_cases(pkg):
-        plan, A, B, got = run_sddmm(pkg, ctx, M, N, ro, ci, K, 0.3, delta)
+        plan, A, B, got = run_sddmm(pkg, ctx, M, N, ro, ci, K, 0.3, delta, flags=0 if wide else pkg.SDDMM_NO_WIDE)
         want = oracle.sddmm_cpu(M, N, K, A, B, ro, ci)
         bad = oracle.check_data(want, got)
         rel = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-3)))
@@ -188,6 +191,88 @@ def test_sddmm_dense_plus_residual(pkg, ctx, oracle, K, delta):
         assert bad == 0, "%s K=%d delta=%s: %d mismatches, max rel %.3e, info %s" % (name, K, delta, bad, rel, plan.info())
         assert not np.any(got == -7.0), "some nnz were never written"
     print("dense+residual K=%d delta=%s worst rel err %.3e" % (K, delta, worst))
+
+
+def wide_cases(pkg):
+    """Matrices that are dense at row-group scale (wide path) and a mixed one (wide + BSMR groups side by side)."""
+    s = pkg.synth
+    cases = [("nips_like", *s.nips_like()), ("mask90", *s.dlmc_mask(0.90)), ("mask98", *s.dlmc_mask(0.98))]
+    # mixed: 300 rows at 12 % density stacked on 1300 rows at 0.15 % density, 3000 columns
+    rng = np.random.default_rng(21)
+    M, N = 1600, 3000
+    rows = []
+    for r in range(M):
+        dens = 0.12 if r < 300 else 0.0015
+        n = max(1, int(rng.binomial(N, dens)))
+        rows.append(np.sort(rng.choice(N, size=n, replace=False)).astype(np.uint32))
+    ro = np.zeros(M + 1, dtype=np.uint32)
+    ro[1:] = np.cumsum([len(r) for r in rows])
+    cases.append(("mixed_1600x3000", M, N, ro, np.concatenate(rows)))
+    return cases
+
+
+@pytest.mark.parametrize("K", [32, 64, 128, 256])
+def test_sddmm_wide_row_groups(pkg, ctx, oracle, K):
+    """The wide tcgen05 kernel (128-row groups x 256-column tiles, masked contiguous-run epilogue) against the oracle,
+    next to the same plan forced onto the reference's split."""
+    for name, M, N, ro, ci in wide_cases(pkg):
+        if K != 128 and name in ("mask98",):
+            continue
+        plan, A, B, got = run_sddmm(pkg, ctx, M, N, ro, ci, K, 0.3, 0.3, row_flags=pkg.ROW_IDENTITY)
+        info = plan.info()
+        assert info["num_wide_groups"] > 0, (name, info)
+        if name.startswith("mixed"):
+            assert info["num_wide_groups"] < info["num_row_groups"], info
+            assert info["num_residual_values"] > 0
+        assert info["num_wide_values"] + info["num_block_values"] + info["num_residual_values"] == len(ci), info
+        want = oracle.sddmm_cpu(M, N, K, A, B, ro, ci)
+        assert not np.any(got == -7.0), "%s K=%d: some nnz were never written" % (name, K)
+        bad = oracle.check_data(want, got)
+        rel = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-3)))
+        assert bad == 0, "%s K=%d: %d mismatches, max rel %.3e, info %s" % (name, K, bad, rel, info)
+        # the same plan on the reference's split
+        import torch
+        dP = torch.full((len(ci),), -7.0, dtype=torch.float32, device="cuda")
+        plan.sddmm(K, torch_dev(A), torch_dev(B), dP, flags=pkg.SDDMM_NO_WIDE)
+        assert oracle.check_data(want, dP.cpu().numpy()) == 0, (name, K)
+        plan.close()
+
+
+def test_wide_after_row_clustering_and_policy(pkg, ctx, oracle):
+    """Wide groups are cut from the REORDERED rows; ratio <= 0 switches the path off; a CSR whose rows are not
+    sorted by column cannot use the contiguous-run epilogue and silently stays on the BSMR kernels."""
+    import torch
+    M, N, ro, ci = pkg.synth.nips_like()
+    K = 64
+    A, B = pkg.synth.make_ab(M, N, K)
+    want = oracle.sddmm_cpu(M, N, K, A, B, ro, ci)
+    dA, dB = torch_dev(A), torch_dev(B)
+    plan = pkg.Plan(ctx, M, N, ro, ci)
+    plan.reorder(0.3, 0.3)
+    assert plan.info()["num_wide_groups"] > 0
+    dP = torch.full((len(ci),), -7.0, dtype=torch.float32, device="cuda")
+    plan.sddmm(K, dA, dB, dP)
+    assert oracle.check_data(want, dP.cpu().numpy()) == 0
+    plan.set_wide_ratio(0.0)
+    plan.col_reorder(0.3)
+    assert plan.info()["num_wide_groups"] == 0
+    dP.fill_(-7.0)
+    plan.sddmm(K, dA, dB, dP)
+    assert oracle.check_data(want, dP.cpu().numpy()) == 0
+    plan.close()
+    # unsorted rows
+    rng = np.random.default_rng(4)
+    ci2 = ci.copy()
+    for r in range(0, M, 7):
+        seg = ci2[ro[r]:ro[r + 1]]
+        ci2[ro[r]:ro[r + 1]] = seg[rng.permutation(len(seg))]
+    want2 = oracle.sddmm_cpu(M, N, K, A, B, ro, ci2)
+    plan = pkg.Plan(ctx, M, N, ro, ci2)
+    plan.reorder(0.3, 0.3, flags=pkg.ROW_IDENTITY)
+    assert plan.info()["num_wide_groups"] == 0
+    dP.fill_(-7.0)
+    plan.sddmm(K, dA, dB, dP)
+    assert oracle.check_data(want2, dP.cpu().numpy()) == 0
 
 
 def test_sddmm_host_overload(pkg, ctx, oracle):
@@ -258,9 +343,13 @@ def test_errors_are_reported_not_swallowed(pkg, ctx):
         pkg.Plan(ctx, M, N, ro, ci[:-1])           # row_offsets[M] != nnz
 
 
-def test_shards_partition_the_nnz(pkg, ctx, oracle):
+@pytest.mark.parametrize("workload", ["blocks", "mixed_wide"])
+def test_shards_partition_the_nnz(pkg, ctx, oracle, workload):
     import torch
-    M, N, ro, ci = pkg.synth.block_structured(1000, 2000, seed=11, groups=12, cols_per_group=64)
+    if workload == "blocks":
+        M, N, ro, ci = pkg.synth.block_structured(1000, 2000, seed=11, groups=12, cols_per_group=64)
+    else:
+        _, M, N, ro, ci = wide_cases(pkg)[-1]
     K = 64
     A, B = pkg.synth.make_ab(M, N, K)
     want = oracle.sddmm_cpu(M, N, K, A, B, ro, ci)

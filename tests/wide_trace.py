@@ -1,0 +1,61 @@
+"""B200 box: per-CTA time stamps of the wide kernel (not a pytest test).  python tests/wide_trace.py [K] [workload]"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+NAMES = ["prologue", "regs", "A stored", "B0", "B1", "B2", "B3", "prod done", "mma first", "mma last", "acc0 full", "epi0 done",
+         "acc1 full", "epi1 done", "epi done", "exit"]
+
+
+def main():
+    import torch
+    pkg = entry.load_package()
+    K = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+    wl = sys.argv[2] if len(sys.argv) > 2 else "nips"
+    s = pkg.synth
+    M, N, ro, ci = {"nips": s.nips_like, "mask90": lambda: s.dlmc_mask(0.90)}[wl]()
+    A, B = s.make_ab(M, N, K)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = pkg.Context(0, stream.cuda_stream)
+    plan = pkg.Plan(ctx, M, N, ro, ci)
+    plan.reorder(0.3, 0.3, flags=pkg.ROW_IDENTITY)
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    dP = torch.zeros(len(ci), device="cuda")
+    for _ in range(5):
+        plan.sddmm(K, dA, dB, dP)
+    trace = torch.zeros(148 * 32, dtype=torch.int64, device="cuda")
+    lib = pkg.lib()
+    lib.bsmr_debug_set_wide_trace.argtypes = [C.c_void_p]
+    lib.bsmr_debug_set_wide_trace(trace.data_ptr())
+    ms = plan.sddmm(K, dA, dB, dP)
+    torch.cuda.synchronize()
+    raw = trace.cpu().numpy().reshape(148, 32)
+    t = raw[:, :16].astype(np.float64)
+    used = t[:, 0] > 0
+    t = t[used]
+    t0 = t[:, 0].min()
+    rel = (t - t0) / 1e3
+    rel[t == 0] = np.nan
+    print("K=%d %s: %d CTAs, event time %.1f us" % (K, wl, used.sum(), ms * 1e3))
+    for i, n in enumerate(NAMES):
+        col = rel[:, i]
+        print("%-10s min %6.2f  med %6.2f  max %6.2f us" % (n, np.nanmin(col), np.nanmedian(col), np.nanmax(col)))
+    c = raw[used][:, 16:32].astype(np.float64)
+    ok = c[:, 0] > 0
+    c = c[ok]
+    lab = ["ldtm", "sts", "gather", "next"]
+    for j in range(3):
+        d = [np.median(c[:, j * 4 + k + 1] - c[:, j * 4 + k]) for k in range(3)]
+        nxt = np.median(c[:, (j + 1) * 4] - c[:, j * 4 + 3]) if j < 2 else float("nan")
+        print("tile 1 chunk %d cycles: ldtm+wait %.0f  sts+sync %.0f  gather %.0f  to next chunk %.0f" % (j, d[0], d[1], d[2], nxt))
+
+
+if __name__ == "__main__":
+    main()
