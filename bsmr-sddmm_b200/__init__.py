@@ -25,7 +25,7 @@ NULL_VALUE = 0xFFFFFFFF
 
 ROW_REFERENCE_COMPAT, ROW_EXACT_REDUCE, ROW_IDENTITY = 0, 1, 2
 SDDMM_DEFAULT, SDDMM_RESIDUAL_ONLY, SDDMM_NO_REORDER, SDDMM_NO_WIDE = 0, 1, 2, 4
-WIDE_GROUP_ROWS, WIDE_TILE_COLS = 128, 128
+WIDE_GROUP_ROWS, WIDE_TILE_COLS = 256, 128
 
 VEC = dict(reordered_rows=0, dense_cols=1, dense_col_offsets=2, sparse_cols=3, sparse_col_offsets=4,
            sparse_value_offsets=5, block_offsets=6, block_values=7, sparse_values=8,

@@ -38,6 +38,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr uint32_t kWideRows = BSMR_WIDE_GROUP_ROWS;
 constexpr uint32_t kWideCols = BSMR_WIDE_TILE_COLS;
+constexpr uint32_t kWQ = kWideRows / 32;                       // 32-row quarters per tile (sub-group x TMEM lane quarter)
 constexpr uint32_t kWW = kWideCols / 32;                       // mask words per (tile, row) = 32-column chunks of a tile
 constexpr uint32_t kWH = kWideCols >= 128 ? kWideCols / 128 : 1;   // run starts per (tile, row): one per 128 columns
 constexpr uint32_t kWideStageRowWords = 36;   // row pitch of the wide kernel's epilogue staging (wide_tc.cu: kWEpiRowWords)
@@ -315,7 +316,7 @@ __global__ void wide_subblock_count_kernel(uint32_t num_sb, const uint32_t* __re
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t sb = warp; sb < num_sb; sb += stride) {
-        const uint32_t t = (uint32_t)(sb / (4 * kWW)), q = (uint32_t)(sb / kWW) & 3, j = (uint32_t)(sb % kWW);
+        const uint32_t t = (uint32_t)(sb / (kWQ * kWW)), q = (uint32_t)(sb / kWW) % kWQ, j = (uint32_t)(sb % kWW);
         uint32_t c = __popc(mask[((size_t)t * kWW + j) * kWideRows + q * 32 + lane]);
 #pragma unroll
         for (int w = 16; w >= 1; w >>= 1) c += __shfl_xor_sync(0xffffffffu, c, w);
@@ -323,38 +324,47 @@ __global__ void wide_subblock_count_kernel(uint32_t num_sb, const uint32_t* __re
     }
 }
 
+// stream position of the work list of quarter-tile tq = tile * kWQ + sub-group * 4 + TMEM quarter: the lists are laid out
+// by (TMEM quarter, tile, sub-group), i.e. everything ONE epilogue warp of the wide kernel consumes while it walks a
+// range of tiles is one contiguous stream of entries (it pages through it with cp.async)
+__host__ __device__ inline uint64_t wide_stream_index(uint64_t tq, uint32_t wtiles) {
+    const uint64_t t = tq / kWQ, rowq = tq % kWQ;
+    return ((rowq % 4) * wtiles + t) * (kWQ / 4) + rowq / 4;
+}
+
 // W2b': entries of every (tile, quarter), padded to a multiple of 8 so that a quarter's list starts 16-byte aligned in
 // both entry arrays (the kernel copies it to shared memory with 16-byte cp.async)
-__global__ void wide_quarter_totals_kernel(uint32_t num_q, const uint32_t* __restrict__ sb_cnt, uint32_t* __restrict__ q_tot) {
+__global__ void wide_quarter_totals_kernel(uint32_t num_q, uint32_t wtiles, const uint32_t* __restrict__ sb_cnt, uint32_t* __restrict__ q_tot) {
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < num_q; q += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t s = 0;
         for (uint32_t j = 0; j < kWW; ++j) s += sb_cnt[q * kWW + j];
-        q_tot[q] = (s + 7u) & ~7u;
+        q_tot[wide_stream_index(q, wtiles)] = (s + 7u) & ~7u;
     }
 }
-// sb_off9[q * (kWW + 1) + j] = first entry of chunk j of quarter-tile q (j = kWW: end of the last chunk)
-__global__ void wide_subblock_offsets_kernel(uint32_t num_q, const uint32_t* __restrict__ sb_cnt, const uint32_t* __restrict__ q_base,
-                                             uint32_t* __restrict__ sb_off9) {
+// sb_off9[stream_index(q) * (kWW + 1) + j] = first entry of chunk j of quarter-tile q (j = kWW: end of the last chunk)
+__global__ void wide_subblock_offsets_kernel(uint32_t num_q, uint32_t wtiles, const uint32_t* __restrict__ sb_cnt,
+                                             const uint32_t* __restrict__ q_base, uint32_t* __restrict__ sb_off9) {
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < num_q; q += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t o = q_base[q];
+        const uint64_t si = wide_stream_index(q, wtiles);
+        uint32_t o = q_base[si];
         for (uint32_t j = 0; j < kWW; ++j) {
-            sb_off9[q * (kWW + 1) + j] = o;
+            sb_off9[si * (kWW + 1) + j] = o;
             o += sb_cnt[q * kWW + j];
         }
-        sb_off9[q * (kWW + 1) + kWW] = o;
+        sb_off9[si * (kWW + 1) + kWW] = o;
     }
 }
 
 // W2c: the epilogue's work list: per sub-block its entries in (row, column) order as
 // (byte offset of the element inside the epilogue's padded 32 x 32 staging image, CSR position).  Everything follows from the masks and the run
 // starts: a row's entries inside a tile half are consecutive CSR positions in ascending column order.
-__global__ void wide_subblock_fill_kernel(uint32_t num_sb, const uint32_t* __restrict__ mask, const uint32_t* __restrict__ base,
+__global__ void wide_subblock_fill_kernel(uint32_t num_sb, uint32_t wtiles, const uint32_t* __restrict__ mask, const uint32_t* __restrict__ base,
                                           const uint32_t* __restrict__ sb_off, uint2* __restrict__ entries) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t sb = warp; sb < num_sb; sb += stride) {
-        const uint32_t t = (uint32_t)(sb / (4 * kWW)), q = (uint32_t)(sb / kWW) & 3, j = (uint32_t)(sb % kWW);
+        const uint32_t t = (uint32_t)(sb / (kWQ * kWW)), q = (uint32_t)(sb / kWW) % kWQ, j = (uint32_t)(sb % kWW);
         const uint32_t row = q * 32 + lane;
         uint32_t m = mask[((size_t)t * kWW + j) * kWideRows + row];
         const uint32_t cnt = __popc(m);
@@ -367,7 +377,7 @@ __global__ void wide_subblock_fill_kernel(uint32_t num_sb, const uint32_t* __res
         if (cnt == 0) continue;
         uint32_t k = base[((size_t)t * kWH + (j >> 2)) * kWideRows + row];
         for (uint32_t jj = j & ~3u; jj < j; ++jj) k += __popc(mask[((size_t)t * kWW + jj) * kWideRows + row]);
-        uint32_t e = sb_off[(sb / kWW) * (kWW + 1) + j] + incl - cnt;
+        uint32_t e = sb_off[wide_stream_index(sb / kWW, wtiles) * (kWW + 1) + j] + incl - cnt;
         while (m) {
             const uint32_t b = __ffs(m) - 1;
             m &= m - 1;
@@ -519,6 +529,7 @@ int build_wide_format(bsmr_plan* plan, Workspace* ws, const uint64_t* ukeys, con
         const uint32_t tiles = (nc + kWideCols - 1) / kWideCols;
         if (g < G && static_cast<double>(h_gnnz[i]) >= static_cast<double>(ratio) * (static_cast<double>(kWideCols) * tiles + kWideRows)) {
             plan->h_group_wide[g] = 1;
+            col_total = (col_total + 3u) & ~3u;   // the kernel reads a tile's column ids four at a time (16-byte loads)
             wg_group.push_back(g); wg_seg.push_back(seg); wg_ncols.push_back(nc); wg_col_off.push_back(col_total);
             wg_tile_off.push_back(static_cast<uint32_t>(h_meta.size()));
             for (uint32_t c = 0; c < nc; c += kWideCols)
@@ -538,7 +549,8 @@ int build_wide_format(bsmr_plan* plan, Workspace* ws, const uint64_t* ukeys, con
     BSMR_TRY(h2d(d_wg_group.ptr, wg_group, st)); BSMR_TRY(h2d(d_wg_seg.ptr, wg_seg, st)); BSMR_TRY(h2d(d_wg_ncols.ptr, wg_ncols, st));
     BSMR_TRY(h2d(d_wg_col_off.ptr, wg_col_off, st)); BSMR_TRY(h2d(d_wg_tile_off.ptr, wg_tile_off, st));
     BSMR_CUDA_OK(cudaMemsetAsync(d_unsorted.ptr, 0, 4, st));
-    BSMR_TRY(plan->wt_meta.alloc(wtiles)); BSMR_TRY(plan->w_cols.alloc(col_total));
+    BSMR_TRY(plan->wt_meta.alloc(wtiles)); BSMR_TRY(plan->w_cols.alloc(static_cast<size_t>(col_total) + 4));
+    BSMR_CUDA_OK(cudaMemsetAsync(plan->w_cols.ptr, 0xFF, plan->w_cols.bytes(), st));
     BSMR_TRY(plan->w_mask.alloc(static_cast<size_t>(wtiles) * kWW * kWideRows));
     BSMR_TRY(plan->w_base.alloc(static_cast<size_t>(wtiles) * kWH * kWideRows));
     BSMR_TRY(h2d(plan->wt_meta.ptr, h_meta, st));
@@ -551,26 +563,27 @@ int build_wide_format(bsmr_plan* plan, Workspace* ws, const uint64_t* ukeys, con
         plan->row_offsets.ptr, plan->col_indices.ptr, plan->w_cols.ptr, plan->w_mask.ptr, plan->w_base.ptr, d_unsorted.ptr);
     ctx->launches += 2;
     // the epilogue's work lists (32 sub-blocks per tile)
-    const uint32_t num_sb = wtiles * 4u * kWW;
-    const uint32_t num_q = wtiles * 4u;
+    const uint32_t num_sb = wtiles * kWQ * kWW;
+    const uint32_t num_q = wtiles * kWQ;
     TmpBuf<uint32_t> sb_cnt(ws), q_tot(ws), q_base(ws);
     BSMR_TRY(sb_cnt.alloc(num_sb));
     BSMR_TRY(q_tot.alloc(static_cast<size_t>(num_q) + 1));
     BSMR_TRY(q_base.alloc(static_cast<size_t>(num_q) + 1));
     BSMR_TRY(plan->w_sb_off.alloc(static_cast<size_t>(num_q) * (kWW + 1)));
     // every quarter-tile list is padded to 8 entries; 16 more so that the kernel's 16-byte copies may run past the end
-    const size_t list_cap = static_cast<size_t>(wide_values) + 8u * num_q + 16;
+    // slack: the kernel's last page copies run past the end of a warp's stream
+    const size_t list_cap = static_cast<size_t>(wide_values) + 8u * num_q + 1024;
     BSMR_TRY(plan->w_entries.alloc(list_cap));
     BSMR_CUDA_OK(cudaMemsetAsync(plan->w_entries.ptr, 0, plan->w_entries.bytes(), st));
     BSMR_CUDA_OK(cudaMemsetAsync(q_tot.ptr + num_q, 0, 4, st));
     wide_subblock_count_kernel<<<grid_for((uint64_t)num_sb * 32, kThreads, sm), kThreads, 0, st>>>(num_sb, plan->w_mask.ptr, sb_cnt.ptr);
-    wide_quarter_totals_kernel<<<grid_for(num_q, kThreads, sm), kThreads, 0, st>>>(num_q, sb_cnt.ptr, q_tot.ptr);
+    wide_quarter_totals_kernel<<<grid_for(num_q, kThreads, sm), kThreads, 0, st>>>(num_q, wtiles, sb_cnt.ptr, q_tot.ptr);
     BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb, q_tot.ptr, q_base.ptr, static_cast<size_t>(num_q) + 1, st));
     BSMR_TRY(ensure_temp(tb));
     BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(temp.ptr, tb, q_tot.ptr, q_base.ptr, static_cast<size_t>(num_q) + 1, st));
-    wide_subblock_offsets_kernel<<<grid_for(num_q, kThreads, sm), kThreads, 0, st>>>(num_q, sb_cnt.ptr, q_base.ptr, plan->w_sb_off.ptr);
+    wide_subblock_offsets_kernel<<<grid_for(num_q, kThreads, sm), kThreads, 0, st>>>(num_q, wtiles, sb_cnt.ptr, q_base.ptr, plan->w_sb_off.ptr);
     wide_subblock_fill_kernel<<<grid_for((uint64_t)num_sb * 32, kThreads, sm), kThreads, 0, st>>>(
-        num_sb, plan->w_mask.ptr, plan->w_base.ptr, plan->w_sb_off.ptr, plan->w_entries.ptr);
+        num_sb, wtiles, plan->w_mask.ptr, plan->w_base.ptr, plan->w_sb_off.ptr, plan->w_entries.ptr);
     ctx->launches += 2;
     ctx->launches += 3;
     uint32_t unsorted = 0;

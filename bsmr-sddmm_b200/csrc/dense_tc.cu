@@ -290,32 +290,6 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// 2-D fp32 tensor [rows x K] with K contiguous; box = 32 floats of one row; SWIZZLE_128B.
-int make_row_gather_map(bsmr_ctx* ctx, const float* base, uint64_t rows, uint64_t K, CUtensorMap* out) {
-    if (!ctx->encode_tiled) {
-        set_error("cuTensorMapEncodeTiled is not available from this driver");
-        return BSMR_ERR_UNSUPPORTED;
-    }
-    const cuuint64_t dims[2] = {K, rows};
-    const cuuint64_t strides[1] = {K * sizeof(float)};
-    const cuuint32_t box[2] = {kChunk, 1};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
-        out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu K=%llu)", (int)r, (unsigned long long)rows,
-                  (unsigned long long)K);
-        return BSMR_ERR_CUDA;
-    }
-    return BSMR_OK;
-}
-
 }  // namespace
 
 // test hook: when set, the next dense launch copies the first tile's stage-0 smem image here

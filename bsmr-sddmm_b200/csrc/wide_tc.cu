@@ -1,28 +1,30 @@
-// Wide row-group SDDMM kernel for sm_100a: a 128-row group of the reordered matrix stays resident in shared memory
-// as the M operand of tcgen05.mma (TF32, fp32 accumulators in TMEM), the group's non-empty B columns stream past it
-// 256 at a time as the N operand, and the epilogue keeps only the accumulator elements S has: thread = row, one
-// 32-bit mask word per 32 columns, the kept values of a (row, tile half) land in ONE contiguous run of P because a
-// CSR row is sorted by column and the tile's columns are the group's distinct columns in ascending order.
+// Wide row-group SDDMM kernel for sm_100a.  A 256-row group of the reordered matrix stays resident in shared memory as
+// two 128-row M operands of tcgen05.mma (TF32, fp32 accumulators in TMEM); the group's distinct B columns stream past
+// them 128 at a time as the N operand (one B stage feeds both sub-groups); the epilogue keeps only the accumulator
+// elements S has, driven by per-sub-block work lists.
 //
-// Why it exists (no counterpart in the reference, whose only tensor-core unit is the 16x16 block of
+// Why it exists (no counterpart in the reference, whose only tensor-core unit is the 16 x 16 block of
 // src/sddmmKernel.cu:213-351): on matrices that are dense-ish at the scale of a row group (the nips example is 4 %
-// dense, DLMC masks 2-30 %) both reference-shaped kernels are bound by the L2 -> SM gather of one K-vector of B per
-// nnz (or per 16-row panel column): ~10 TB/s, measured.  Here a B column is fetched once per 128 rows, the gather
-// traffic drops by nnz(group) / distinct_columns(group) (8x on nips), and the work that replaces it -- 128 x 256 x K
-// MACs per tile whatever the fill -- is what the tensor pipe has to spare.  A group takes this path when
-// nnz(group) >= ratio * (256 * tiles + 128) (colreorder.cu: build_wide_format); every other group keeps the BSMR
-// dense-block + residual kernels.
+// dense, DLMC masks 2-30 %) both reference-shaped kernels are bound by the L2 -> SM gather of one K-vector of B per nnz
+// (or per 16-row panel column), which saturates near 5.4 TB/s on B200 (measured with both kernels).  Here a B column
+// is fetched once per 256 rows: the gather traffic drops by nnz(group) / distinct_columns(group) (~11x on nips), and
+// the work that replaces it -- 256 x 128 x K MACs per tile whatever the fill -- is what the tensor pipe has to spare.
+// A group takes this path when nnz(group) >= ratio * (128 * tiles + 256) (colreorder.cu: build_wide_format); every
+// other group keeps the BSMR dense-block + residual kernels.
 //
-// Pipeline (13 warps, one CTA per SM, persistent over a contiguous range of tiles):
-//   warps 0-7  producers: LDG.128 (8 lanes x 16 B = one 128-byte K-chunk of a column) -> cvt.rna.tf32.f32 (the
-//              reference rounds to nearest, wmma::__float_to_tf32; tcgen05 kind::tf32 truncates) -> STS.128 into the
-//              SWIZZLE_128B K-major image the MMA expects (16-byte chunk c of row r at chunk c ^ (r & 7)) ->
-//              fence.proxy.async -> mbarrier.  Three stages of loads are in flight per lane (register ring).
-//              The same warps (re)load the group's A rows, one 16 KB image per 32 floats of K.
-//   warp  8    TMEM allocator (512 columns = two 128 x 256 fp32 accumulators) + single-lane MMA issuer
-//   warps 9-12 epilogue: warp (quarter q = warp % 4) reads TMEM lanes 32q..32q+31 of the finished accumulator with
-//              tcgen05.ld 32x32b.x32, 32 columns at a time, and stores the masked elements.
-// Shared memory: K/32 x 16 KB (A, resident) + S x 32 KB (B ring); S is kept small (2-3) on purpose, see launch_wide.
+// Pipeline (17 warps, one CTA per SM, persistent over a contiguous range of tiles of one row group):
+//   warps 0-7   TMA producers: cp.async.bulk.tensor.2d tile::gather4 (4 arbitrary rows of the [N x K] / [M x K] tensor
+//               per request, SWIZZLE_128B K-major image, 32 floats of K per stage); first the A images of the group
+//               ([sub-group][K-chunk] x 16 KB), then the B ring (S x 16 KB)
+//   warps 12-15 converters: cvt.rna.tf32.f32 in place on every landed image (tcgen05 kind::tf32 truncates, the reference
+//               rounds to nearest), fence.proxy.async, mbarrier
+//   warp  16    TMEM allocator (512 columns) + single-lane MMA issuer: per B stage 4 MMAs (M=128, N<=128, K=8) per
+//               resident sub-group; accumulator sets rotate so that the epilogue of tile i overlaps the MMAs of tile i+1
+//   warps 8-11  epilogue (TMEM lane quarter = warp % 4): tcgen05.ld 32x32b.x32 -> padded staging -> work list -> P
+// Shared memory (K = 128): 128 KB A + 4 x 16 KB B ring + 18 KB staging + 14 KB lists.  A first version staged the
+// operands with LDG -> cvt -> STS from producer warps (no converter pass, less shared-memory traffic): every load in
+// flight held an L1 line, L1 is what shared memory leaves over, and the epilogue's LDS/STG queued behind the loads in
+// the LSU; measured slower at every depth of prefetch.  TMA does not touch the LSU / L1 miss path at all.
 // Roofline: HBM on the compulsory bytes of the step; inside, L2 -> SM traffic (distinct columns x K x 4 per group).
 #include <cstdlib>
 #include <vector>
@@ -30,62 +32,61 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
-#ifndef BSMR_WIDE_NBUF
-#define BSMR_WIDE_NBUF 4
-#endif
-
 namespace bsmr {
 namespace {
 
 using namespace tc;
 
-constexpr int kWRows = BSMR_WIDE_GROUP_ROWS;   // rows of a row group = UMMA M = TMEM lanes
-constexpr int kWCols = BSMR_WIDE_TILE_COLS;    // max columns of a wide tile = UMMA N
-constexpr int kWChunk = 32;                    // floats of K per stage (128 bytes = one swizzle row)
-constexpr int kWAChunkBytes = kWRows * 128;    // 16 KB
-constexpr int kWBStageBytes = kWCols * 128;    // 16 KB
-constexpr int kWRounds = kWCols / 32;          // LDG.128 per producer lane per stage (a warp instruction covers 4 columns)
-constexpr int kWWords = kWCols / 32;           // 32-column chunks of a tile
-constexpr int kWAccs = 512 / kWCols;           // TMEM accumulators in rotation
-constexpr int kWProducerWarps = 8;
-constexpr int kWEpiWarp0 = kWProducerWarps;          // warps 8-11: TMEM lane quarter = warp % 4
+constexpr int kWSubRows = 128;                        // UMMA M = TMEM lanes: one sub-group of a row group
+constexpr int kWGroupRows = BSMR_WIDE_GROUP_ROWS;     // 256
+constexpr int kWSub = kWGroupRows / kWSubRows;        // sub-groups per row group
+constexpr int kWCols = BSMR_WIDE_TILE_COLS;           // max columns of a wide tile = UMMA N = 128
+constexpr int kWChunk = 32;                           // floats of K per stage (128 bytes = one swizzle row)
+constexpr int kWAImgBytes = kWSubRows * 128;          // 16 KB: one sub-group x one K-chunk of A
+constexpr int kWBStageBytes = kWCols * 128;           // 16 KB
+constexpr int kWWords = kWCols / 32;                  // 32-column chunks of a tile
+constexpr int kWProducerWarps = 8;                    // warps 0-7: TMA gather4 issue
+constexpr int kWEpiWarp0 = 8;                         // warps 8-11: epilogue, TMEM lane quarter = warp % 4
 constexpr int kWEpiWarps = 4;
-constexpr int kWMmaWarp = kWEpiWarp0 + kWEpiWarps;   // warp 12 (13-15 idle: setmaxnreg works on whole warpgroups)
-constexpr int kWThreads = 512;
-constexpr int kWProducerRegs = 168;                  // 256 threads x 168 + 256 threads x 88 = 64 K registers
-constexpr int kWOtherRegs = 88;
-constexpr int kWMaxStages = 5;
-constexpr int kNBuf = BSMR_WIDE_NBUF;                       // B stages in flight per producer lane (register ring)
-constexpr int kWMaxKChunks = 8;                // K <= 256
-constexpr int kWTmemCols = 512;                // kWAccs accumulators of kWCols fp32 columns
+constexpr int kWConvWarp0 = 12;                       // warps 12-15: TF32 round-to-nearest converters
+constexpr int kWConvWarps = 4;
+constexpr int kWMmaWarp = 16;
+constexpr int kWThreads = 17 * 32;
+constexpr int kWMaxStages = 8;
+constexpr int kWMaxKChunks = 8;                       // K <= 256
+constexpr int kWTmemCols = 512;
+constexpr int kWMaxAccs = 4;
 constexpr uint32_t kNoCol = 0xFFFFFFFFu;
 constexpr int kWEpiRowWords = 36;                              // padded row of the epilogue staging (conflict-free STS.128)
 constexpr int kWEpiStageBytes = 32 * kWEpiRowWords * 4;        // 4608 bytes per epilogue warp
-constexpr int kWListCap = 384;                                 // work-list entries of a quarter-tile held in shared memory
-constexpr int kWListBytes = kWListCap * 8;                     // 3 KB per epilogue warp
+constexpr int kWListPage = 224;                                // work-list entries per page of an epilogue warp's list stream
+constexpr int kWListBytes = 2 * kWListPage * 8;                // two pages in shared memory per epilogue warp: 3.5 KB
 
 struct __align__(16) WideSmemTail {
-    uint64_t b_full[kWMaxStages];    // 8 producer warps stored (and fenced) their rows of the stage
+    uint64_t b_full[kWMaxStages];    // TMA bytes of the stage landed
+    uint64_t b_ready[kWMaxStages];   // stage rounded to TF32 by the 4 converter warps
     uint64_t b_empty[kWMaxStages];   // the MMAs that read the stage have completed (tcgen05.commit)
-    uint64_t a_ready[kWMaxKChunks];  // A image of K-chunk kc stored by the 8 producer warps
-    uint64_t a_free;                 // every MMA of the current group has completed: A may be overwritten
-    uint64_t tmem_full[kWAccs];
-    uint64_t tmem_empty[kWAccs];     // the epilogue warps have read the accumulator
+    uint64_t a_full[kWMaxKChunks];   // A images of K-chunk kc landed
+    uint64_t a_ready[kWMaxKChunks];  // ... and rounded
+    uint64_t a_free;                 // every MMA that reads the current A images has completed
+    uint64_t tmem_full[kWMaxAccs];
+    uint64_t tmem_empty[kWMaxAccs];  // the 4 epilogue warps have read the accumulator
     uint32_t tmem_base;
     uint32_t pad[3];
 };
 
 struct WideParams {
     uint32_t K, kchunks, stages;
+    uint32_t sgp;                    // sub-groups per pass: 2 (A images of the whole group resident, K <= 128) or 1 (K = 256)
     uint32_t num_rows;               // reordered (non-empty) rows
+    uint32_t M, N;                   // out-of-bounds coordinates for missing rows / columns (TMA zero fill)
     const uint32_t* cta_begin;       // gridDim.x + 1 tile indices: CTA b owns tiles [cta_begin[b], cta_begin[b + 1])
-    const uint4* tile_meta;          // {group, first column (offset into cols), #columns, 0}
+    const uint4* tile_meta;          // {group, first column (offset into cols, multiple of 4), #columns, 0}
     const uint32_t* cols;            // distinct columns of the wide groups, ascending inside a group
-    const uint32_t* sb_off;          // [(tile * 4 + quarter) * (chunks + 1) + chunk]: first work-list entry of a 32 x 32 sub-block
+    uint32_t num_tiles;              // wide tiles of the plan (stride of the per-quarter list streams)
+    const uint32_t* sb_off;          // [((quarter * num_tiles + tile) * 2 + sub-group) * 5 + chunk]: first work-list entry of a 32 x 32 sub-block
     const uint2* entries;            // entry: {byte offset inside the staging image (row * 36 + column) * 4, CSR position}
     const uint32_t* reordered_rows;
-    const float* A;
-    const float* B;
     float* P;
     uint32_t* error_flag;
     unsigned long long* trace;       // optional (tests/perf probes): 32 time stamps per CTA
@@ -96,51 +97,60 @@ __device__ __forceinline__ unsigned long long gtime() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#define WCLOCK(slot)                                                                          \
-    do {                                                                                      \
-        if (p.trace && lane == 0) p.trace[(size_t)blockIdx.x * 32 + (slot)] = clock64();      \
-    } while (0)
 #define WTRACE(slot)                                                                          \
     do {                                                                                      \
         if (p.trace && lane == 0) p.trace[(size_t)blockIdx.x * 32 + (slot)] = gtime();        \
     } while (0)
 
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-
-__device__ __forceinline__ uint4 rna4(const float4& v) {
-    uint4 o;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(o.x) : "f"(v.x));
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(o.y) : "f"(v.y));
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(o.z) : "f"(v.z));
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(o.w) : "f"(v.w));
-    return o;
+// in-place cvt.rna.tf32.f32 of `n4` float4 per thread (128 converter threads, float4 #ci + 128 * j)
+template <int N4>
+__device__ __forceinline__ void round_image(uint8_t* img, uint32_t ci) {
+    float4* v4 = reinterpret_cast<float4*>(img);
+    float4 v[N4];
+#pragma unroll
+    for (int j = 0; j < N4; ++j) v[j] = v4[ci + 128 * j];
+#pragma unroll
+    for (int j = 0; j < N4; ++j) {
+        v[j].x = rna_tf32(v[j].x);
+        v[j].y = rna_tf32(v[j].y);
+        v[j].z = rna_tf32(v[j].z);
+        v[j].w = rna_tf32(v[j].w);
+    }
+#pragma unroll
+    for (int j = 0; j < N4; ++j) v4[ci + 128 * j] = v[j];
 }
 
 __global__ void __launch_bounds__(kWThreads, 1)
-wide_sddmm_kernel(const WideParams p) {
+wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const WideParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment by pointer arithmetic on the __shared__ array: an integer round trip loses the address space
-    // and every access below would become a generic LD/ST instead of LDS/STS (seen in SASS, 3-5x slower)
+    // and every access below would become a generic LD/ST instead of LDS/STS (seen in SASS)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* a_img = smem;                                             // kchunks x 16 KB
-    uint8_t* b_ring = smem + (size_t)p.kchunks * kWAChunkBytes;        // stages x 32 KB
-    uint8_t* epi_stage = b_ring + (size_t)p.stages * kWBStageBytes;    // 4 epilogue warps x 32 rows x 36 words
+    const uint32_t KC = p.kchunks, S = p.stages, SGP = p.sgp;
+    uint8_t* a_img = smem;                                                   // [SGP][KC] x 16 KB
+    uint8_t* b_ring = a_img + (size_t)SGP * KC * kWAImgBytes;                // S x 16 KB
+    uint8_t* epi_stage = b_ring + (size_t)S * kWBStageBytes;                 // 4 epilogue warps x 32 rows x 36 words
     uint8_t* epi_lists = epi_stage + (size_t)kWEpiWarps * kWEpiStageBytes;   // 4 x 3 KB
     WideSmemTail* tail = reinterpret_cast<WideSmemTail*>(epi_lists + (size_t)kWEpiWarps * kWListBytes);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t KC = p.kchunks, S = p.stages;
+    const uint32_t passes = kWSub / SGP;                  // K = 256: the tile range is walked once per sub-group
+    const uint32_t naccs = kWTmemCols / (kWCols * SGP);   // accumulator sets in rotation (one set = SGP x 128 columns)
     // tile range of this CTA (host-side partition: CTAs do not straddle row groups when there are enough of them)
     const uint32_t my_begin = __ldg(p.cta_begin + blockIdx.x), my_end = __ldg(p.cta_begin + blockIdx.x + 1);
 
     if (warp == 0 && lane == 0) {
         for (uint32_t s = 0; s < S; ++s) {
-            mbar_init(&tail->b_full[s], kWProducerWarps);
+            mbar_init(&tail->b_full[s], 1);
+            mbar_init(&tail->b_ready[s], kWConvWarps);
             mbar_init(&tail->b_empty[s], 1);
         }
-        for (uint32_t k = 0; k < KC; ++k) mbar_init(&tail->a_ready[k], kWProducerWarps);
+        for (uint32_t k = 0; k < KC; ++k) {
+            mbar_init(&tail->a_full[k], 1);
+            mbar_init(&tail->a_ready[k], kWConvWarps);
+        }
         mbar_init(&tail->a_free, 1);
-        for (int a = 0; a < kWAccs; ++a) {
+        for (int a = 0; a < kWMaxAccs; ++a) {
             mbar_init(&tail->tmem_full[a], 1);
             mbar_init(&tail->tmem_empty[a], kWEpiWarps);
         }
@@ -158,280 +168,273 @@ wide_sddmm_kernel(const WideParams p) {
     if (warp == 0) WTRACE(0);                      // prologue done
 
     if (warp < kWProducerWarps) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWProducerRegs));
-        if (warp == 0) WTRACE(1);                  // registers granted
-        // ================= producers =================
-        // lane -> (row slot, 16-byte chunk): a warp instruction covers 4 rows x 128 bytes; round r of a stage
-        // covers rows r*32 + warp*4 + lane/8.  kNBuf stages of B are in flight per lane (register ring): the
-        // bytes in flight per SM (8 warps x 32 lanes x kNBuf x 64 B = 80 KB) are what hides the L2 latency.
-        const uint32_t rbase = warp * 4 + (lane >> 3);
-        const uint32_t c16 = lane & 7;
-        const uint32_t swz = ((c16 ^ (rbase & 7)) << 4);          // (r*32 + rbase) & 7 == rbase & 7
-        const uint32_t K = p.K;
-        if (my_begin < my_end) {
-            float4 buf[kNBuf][kWRounds];
-            uint32_t cols_i[kWRounds], cols_n[kWRounds];
-            auto load_cols = [&](uint32_t t, uint32_t (&cols)[kWRounds]) {
-                const uint4 m = __ldg(p.tile_meta + t);
-#pragma unroll
-                for (int r = 0; r < kWRounds; ++r) {
-                    const uint32_t rr = r * 32 + rbase;
-                    cols[r] = rr < m.z ? __ldg(p.cols + m.y + rr) : kNoCol;
-                }
-            };
-            auto issue_b = [&](const uint32_t (&cols)[kWRounds], uint32_t kc, float4 (&v)[kWRounds]) {
-#pragma unroll
-                for (int r = 0; r < kWRounds; ++r) {
-                    v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (cols[r] != kNoCol) v[r] = ldg4(p.B + (size_t)cols[r] * K + kc * kWChunk + c16 * 4);
-                }
-            };
-            auto load_arows = [&](uint32_t g, uint32_t (&arow)[4]) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const uint32_t gi = g * kWRows + r * 32 + rbase;
-                    arow[r] = gi < p.num_rows ? __ldg(p.reordered_rows + gi) : kNoCol;
-                }
-            };
-            auto issue_a = [&](const uint32_t (&arow)[4], uint32_t kc, float4* v) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (arow[r] != kNoCol) v[r] = ldg4(p.A + (size_t)arow[r] * K + kc * kWChunk + c16 * 4);
-                }
-            };
-            auto store_a = [&](uint32_t kc, const float4* v) {
-                uint8_t* img = a_img + (size_t)kc * kWAChunkBytes;
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-                    *reinterpret_cast<uint4*>(img + (r * 32 + rbase) * 128 + swz) = rna4(v[r]);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tail->a_ready[kc]);
-            };
-
-            // ---- start-up: column lists, then the whole A image of the first group with every load in flight at once
-            // (the B ring registers double as staging: 4 chunks = 16 float4 per pass)
-            uint32_t ti = my_begin, kci = 0;             // issue cursor
-            uint32_t ts = my_begin, kcs = 0;             // store cursor
-            const uint32_t n_items = (my_end - my_begin) * KC;
-            uint32_t issued = 0, stored = 0, stage = 0, phase = 0, a_loads = 1;
-            uint32_t cur_group = __ldg(p.tile_meta + my_begin).x;
-            auto issue_next = [&](float4 (&v)[kWRounds]) {
-                if (issued < n_items) {
-                    issue_b(cols_i, kci, v);
-                    ++issued;
-                    if (++kci == KC) {
-                        kci = 0;
-                        ++ti;
-#pragma unroll
-                        for (int r = 0; r < kWRounds; ++r) cols_i[r] = cols_n[r];
-                        if (ti + 1 < my_end) load_cols(ti + 1, cols_n);
-                    }
-                }
-            };
-            {
-                uint32_t arow[4];
-                load_arows(cur_group, arow);
-                load_cols(ti, cols_i);
-                if (ti + 1 < my_end) load_cols(ti + 1, cols_n);
-                issue_next(buf[0]);                  // the first B stage travels together with the A image
-                constexpr int kAPerBuf = kWRounds / 4;              // a K-chunk of A is 4 float4 per lane
-                constexpr int kAPass = (kNBuf - 1) * kAPerBuf;      // K-chunks of A staged per pass in buf[1 .. kNBuf-1]
-                for (uint32_t k0 = 0; k0 < KC; k0 += kAPass) {
-#pragma unroll
-                    for (int j = 0; j < kAPass; ++j)
-                        if (k0 + j < KC) issue_a(arow, k0 + j, &buf[1 + j / kAPerBuf][(j % kAPerBuf) * 4]);
-#pragma unroll
-                    for (int j = 0; j < kAPass; ++j)
-                        if (k0 + j < KC) store_a(k0 + j, &buf[1 + j / kAPerBuf][(j % kAPerBuf) * 4]);
-                }
+        // ================= TMA producers (warps 0..7) =================
+        // A stage is 32 gather4 requests (4 B columns x 128 bytes each, laid down as 4 consecutive rows of the
+        // SWIZZLE_128B K-major image); producer warp w issues requests 4w..4w+3 from its lanes 0..3 (a gather4 takes its
+        // coordinates from uniform registers, so ptxas serialises the lanes of a warp: eight warps issue in parallel).
+        // Lane 0 of warp 0 arms the stage's mbarrier with the byte count of all its requests.  Missing columns / rows
+        // carry the out-of-bounds coordinate and arrive as zeros.  Nothing here touches the LSU / L1 miss path: with
+        // LDG-staged operands every load in flight held an L1 line and the epilogue's LDS/STG queued behind them.
+        const uint32_t rq = warp * 4 + lane;         // request (= group of 4 rows of the image) of this lane, lanes 0..3
+        const bool issuer = lane < 4;
+        auto fetch_cols = [&](uint32_t t, uint32_t& ncols, int4& cols) {
+            const uint4 m = __ldg(p.tile_meta + t);
+            ncols = m.z;
+            cols = make_int4((int)p.N, (int)p.N, (int)p.N, (int)p.N);
+            const uint32_t c0 = rq * 4;
+            if (issuer && c0 < m.z) {
+                cols = __ldg(reinterpret_cast<const int4*>(p.cols + m.y + c0));
+                if (c0 + 1 >= m.z) cols.y = (int)p.N;
+                if (c0 + 2 >= m.z) cols.z = (int)p.N;
+                if (c0 + 3 >= m.z) cols.w = (int)p.N;
             }
-            if (warp == 0) WTRACE(2);              // A image stored
+        };
+        uint32_t stage = 0, phase = 0, a_loads = 0, cur_key = kNoCol;
+        for (uint32_t pass = 0; pass < passes; ++pass) {
+            uint32_t ncols = 0, ncols_next = 0;
+            int4 cols = make_int4(0, 0, 0, 0), cols_next = make_int4(0, 0, 0, 0);
+            if (my_begin < my_end) fetch_cols(my_begin, ncols, cols);
+            for (uint32_t t = my_begin; t < my_end; ++t) {
+                if (t + 1 < my_end) fetch_cols(t + 1, ncols_next, cols_next);   // indices of the next tile: off the critical path
+                const uint32_t g = __ldg(p.tile_meta + t).x;
+                const uint32_t key = g * 2 + pass;
+                if (key != cur_key) {
+                    // (re)load the A images: [sub-group of the pass][K-chunk], 32 requests each
+                    if (a_loads > 0) mbar_wait(&tail->a_free, (a_loads - 1) & 1, p.error_flag, 11);
+                    for (uint32_t sg = 0; sg < SGP; ++sg) {
+                        int4 rows = make_int4((int)p.M, (int)p.M, (int)p.M, (int)p.M);
+                        if (issuer) {
+                            const uint32_t r0 = g * kWGroupRows + (pass * SGP + sg) * kWSubRows + rq * 4;
+                            int* rp = reinterpret_cast<int*>(&rows);
 #pragma unroll
-            for (int b = 1; b < kNBuf - 1; ++b) issue_next(buf[b]);
-            bool done = false;
-            while (!done) {
-#pragma unroll
-                for (int b = 0; b < kNBuf; ++b) {
-                    if (stored == n_items) { done = true; break; }
-                    issue_next(buf[(b + kNBuf - 1) % kNBuf]);
-                    if (kcs == 0 && ts != my_begin) {
-                        const uint32_t g = __ldg(p.tile_meta + ts).x;
-                        if (g != cur_group) {
-                            // group switch inside a CTA's range (more groups than CTAs): the previous group's MMAs must
-                            // have finished reading A before it is overwritten; chunk by chunk (registers are taken)
-                            mbar_wait(&tail->a_free, (a_loads - 1) & 1, p.error_flag, 11);
-                            uint32_t arow[4];
-                            load_arows(g, arow);
-                            for (uint32_t kc = 0; kc < KC; ++kc) {
-                                float4 v[4];
-                                issue_a(arow, kc, v);
-                                store_a(kc, v);
-                            }
-                            cur_group = g;
-                            ++a_loads;
+                            for (int j = 0; j < 4; ++j)
+                                if (r0 + j < p.num_rows) rp[j] = (int)__ldg(p.reordered_rows + r0 + j);
+                        }
+                        for (uint32_t kc = 0; kc < KC; ++kc) {
+                            if (sg == 0 && warp == 0 && lane == 0) mbar_arrive_expect_tx(&tail->a_full[kc], SGP * kWAImgBytes);
+                            if (issuer)
+                                tma_gather4(&map_a, &tail->a_full[kc], a_img + ((size_t)sg * KC + kc) * kWAImgBytes + rq * 512,
+                                            (int)(kc * kWChunk), rows);
                         }
                     }
+                    cur_key = key;
+                    ++a_loads;
+                }
+                const bool has_cols = issuer && rq * 4 < ncols;
+                const uint32_t tx_bytes = ((ncols + 3) / 4) * 512u;
+                for (uint32_t kc = 0; kc < KC; ++kc) {
                     mbar_wait(&tail->b_empty[stage], phase ^ 1, p.error_flag, 12);
-                    uint8_t* st = b_ring + (size_t)stage * kWBStageBytes;
-#pragma unroll
-                    for (int r = 0; r < kWRounds; ++r)
-                        *reinterpret_cast<uint4*>(st + (r * 32 + rbase) * 128 + swz) = rna4(buf[b][r]);
+                    if (warp == 0 && lane == 0) mbar_arrive_expect_tx(&tail->b_full[stage], tx_bytes);
+                    if (has_cols)
+                        tma_gather4(&map_b, &tail->b_full[stage], b_ring + (size_t)stage * kWBStageBytes + rq * 512, (int)(kc * kWChunk), cols);
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+                ncols = ncols_next;
+                cols = cols_next;
+            }
+        }
+    } else if (warp >= kWConvWarp0 && warp < kWConvWarp0 + kWConvWarps) {
+        // ================= TF32 converters (warps 12..15) =================
+        // tcgen05 kind::tf32 ignores the low 13 mantissa bits (truncation); the reference rounds to nearest
+        // (wmma::__float_to_tf32, src/sddmmKernel.cu:317-322): every landed image is rounded in place with
+        // cvt.rna.tf32.f32 (element-wise, so the swizzle does not matter), then fence.proxy.async -> mbarrier.
+        const uint32_t ci = threadIdx.x - kWConvWarp0 * 32;   // 0..127
+        uint32_t stage = 0, phase = 0, a_idx = 0, cur_key = kNoCol;
+        for (uint32_t pass = 0; pass < passes; ++pass) {
+            for (uint32_t t = my_begin; t < my_end; ++t) {
+                const uint32_t key = __ldg(p.tile_meta + t).x * 2 + pass;
+                if (key != cur_key) {
+                    for (uint32_t kc = 0; kc < KC; ++kc) {
+                        mbar_wait(&tail->a_full[kc], a_idx & 1, p.error_flag, 17);
+                        for (uint32_t sg = 0; sg < SGP; ++sg) round_image<8>(a_img + ((size_t)sg * KC + kc) * kWAImgBytes, ci);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tail->a_ready[kc]);
+                    }
+                    cur_key = key;
+                    ++a_idx;
+                    if (warp == kWConvWarp0) WTRACE(2);        // A images rounded
+                }
+                for (uint32_t kc = 0; kc < KC; ++kc) {
+                    mbar_wait(&tail->b_full[stage], phase, p.error_flag, 18);
+                    round_image<8>(b_ring + (size_t)stage * kWBStageBytes, ci);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tail->b_full[stage]);
+                    if (lane == 0) mbar_arrive(&tail->b_ready[stage]);
                     if (++stage == S) { stage = 0; phase ^= 1; }
-                    if (warp == 0 && stored < 4) WTRACE(3 + stored);   // first four B stages stored
-                    ++stored;
-                    if (++kcs == KC) { kcs = 0; ++ts; }
                 }
             }
-            if (warp == 0) WTRACE(7);              // producer done
         }
-    } else if (warp >= kWMmaWarp) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWOtherRegs));
-        if (warp == kWMmaWarp) {
+        if (warp == kWConvWarp0) WTRACE(7);                    // converters done
+    } else if (warp == kWMmaWarp) {
         // ================= MMA issuer =================
-        uint32_t stage = 0, phase = 0, it = 0, a_idx = 0, cur_group = kNoCol;
-        for (uint32_t t = my_begin; t < my_end; ++t, ++it) {
-            const uint4 m = __ldg(p.tile_meta + t);
-            const uint32_t acc = it % kWAccs, acc_phase = (it / kWAccs) & 1;
-            const bool new_group = m.x != cur_group;
-            cur_group = m.x;
-            const bool last_of_group = (t + 1 == my_end) || (__ldg(p.tile_meta + t + 1).x != m.x);
-            const uint32_t n_mma = (m.z + 15u) & ~15u;
-            const uint32_t idesc = make_idesc_tf32(kWRows, n_mma);
-            mbar_wait(&tail->tmem_empty[acc], acc_phase ^ 1, p.error_flag, 13);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + acc * kWCols;
-            for (uint32_t kc = 0; kc < KC; ++kc) {
-                if (new_group) mbar_wait(&tail->a_ready[kc], a_idx & 1, p.error_flag, 14);
-                mbar_wait(&tail->b_full[stage], phase, p.error_flag, 15);
+        uint32_t stage = 0, phase = 0, it = 0, a_idx = 0, cur_key = kNoCol;
+        for (uint32_t pass = 0; pass < passes; ++pass) {
+            for (uint32_t t = my_begin; t < my_end; ++t, ++it) {
+                const uint4 m = __ldg(p.tile_meta + t);
+                const uint32_t acc = it % naccs, acc_phase = (it / naccs) & 1;
+                const uint32_t key = m.x * 2 + pass;
+                const bool new_key = key != cur_key;
+                cur_key = key;
+                const bool last_of_key = (t + 1 == my_end) || (__ldg(p.tile_meta + t + 1).x != m.x);
+                const uint32_t n_mma = (m.z + 15u) & ~15u;
+                const uint32_t idesc = make_idesc_tf32(kWSubRows, n_mma);
+                mbar_wait(&tail->tmem_empty[acc], acc_phase ^ 1, p.error_flag, 13);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint64_t da = make_smem_desc(smem_u32(a_img + (size_t)kc * kWAChunkBytes));
-                    const uint64_t db = make_smem_desc(smem_u32(b_ring + (size_t)stage * kWBStageBytes));
+                for (uint32_t kc = 0; kc < KC; ++kc) {
+                    if (new_key) mbar_wait(&tail->a_ready[kc], a_idx & 1, p.error_flag, 14);
+                    mbar_wait(&tail->b_ready[stage], phase, p.error_flag, 15);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint64_t db = make_smem_desc(smem_u32(b_ring + (size_t)stage * kWBStageBytes));
+                        for (uint32_t sg = 0; sg < SGP; ++sg) {
+                            const uint64_t da = make_smem_desc(smem_u32(a_img + ((size_t)sg * KC + kc) * kWAImgBytes));
+                            const uint32_t tmem_d = tmem_base + (acc * SGP + sg) * kWCols;
 #pragma unroll
-                    for (uint32_t k = 0; k < kWChunk / 8; ++k)
-                        umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
-                    umma_commit(&tail->b_empty[stage]);
-                    if (it == 0 && kc == 0) WTRACE(8);             // first MMAs issued
-                    if (kc + 1 == KC) {
-                        umma_commit(&tail->tmem_full[acc]);
-                        if (last_of_group) umma_commit(&tail->a_free);
+                            for (uint32_t k = 0; k < kWChunk / 8; ++k)
+                                umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(&tail->b_empty[stage]);
+                        if (it == 0 && kc == 0) WTRACE(8);             // first MMAs issued
+                        if (kc + 1 == KC) {
+                            umma_commit(&tail->tmem_full[acc]);
+                            if (last_of_key) umma_commit(&tail->a_free);
+                        }
                     }
+                    __syncwarp();
+                    if (++stage == S) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == S) { stage = 0; phase ^= 1; }
+                if (new_key) ++a_idx;
             }
-            if (new_group) ++a_idx;
         }
         WTRACE(9);                                 // last MMA issued
-        }
     } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWOtherRegs));
-        // ================= epilogue (4 warps) =================
-        // Per 32-column chunk: tcgen05.ld of the warp's 32 x 32 accumulator sub-block -> padded shared-memory staging
-        // (row stride 36 words: conflict-free 128-bit stores) -> the sub-block's work list, 32 entries per pass: one
-        // LDS gather and one STG per entry.  The instruction count follows the nnz, not the 128 x 256 tile area (a
-        // predicated store per accumulator element cost 4.6 us per tile, measured).  The quarter-tile's list (position,
-        // CSR index) is copied to shared memory with cp.async one tile ahead: read from global memory inside the chunk
-        // loop it put one L2 round trip per chunk on the critical path (3.5 us per tile, measured).
+        // ================= epilogue (warps 8..11) =================
+        // Per (tile, sub-group) and 32-column chunk: tcgen05.ld of the warp's 32 x 32 accumulator sub-block -> padded
+        // shared-memory staging (row stride 36 words: conflict-free 128-bit stores) -> the sub-block's work list, four
+        // passes of 32 entries at a time: one LDS.64 (entry), one LDS (value), one STG per entry.  The instruction count
+        // follows the nnz, not the tile area (a predicated store per accumulator element cost 4.6 us per 128 x 256
+        // tile, measured: one epilogue warp per scheduler pays every dependent instruction's full latency).  The list of
+        // stream of the warp is paged through shared memory with cp.async.
         const uint32_t quarter = warp & 3;          // TMEM lanes [32*quarter, +32): fixed by warp id % 4
         float* stg = reinterpret_cast<float*>(epi_stage + (size_t)quarter * kWEpiStageBytes);
-        const uint2* lent = reinterpret_cast<const uint2*>(epi_lists + (size_t)quarter * kWListBytes);
-        const uint32_t lent_u32 = smem_u32(lent);
         const uint8_t* stg_bytes = reinterpret_cast<const uint8_t*>(stg);
-        // lane j < 9 holds the first entry of chunk j of the tile in hand (lane 8: end of chunk 7)
-        auto fetch_offsets = [&](uint32_t t) -> uint32_t {
-            return lane <= kWWords ? __ldg(p.sb_off + ((size_t)t * 4 + quarter) * (kWWords + 1) + lane) : 0u;
+        const uint2* lpage = reinterpret_cast<const uint2*>(epi_lists + (size_t)quarter * kWListBytes);
+        const uint32_t lpage_u32 = smem_u32(lpage);
+        // The lists of this warp's units (tile, sub-group), tile ascending, are ONE contiguous stream of entries in
+        // global memory (layout: quarter, tile, sub-group).  The warp pages through it: two pages of kWListPage entries in
+        // shared memory, page n + 2 requested (cp.async) the moment page n is used up, whatever the fill of the tiles.
+        auto unit_offsets = [&](uint32_t t, uint32_t s) -> uint32_t {   // lane j <= 4: first entry of chunk j (lane 4: end)
+            return lane <= (uint32_t)kWWords
+                       ? __ldg(p.sb_off + (((size_t)quarter * p.num_tiles + t) * kWSub + s) * (kWWords + 1) + lane) : 0u;
         };
-        auto copy_lists = [&](uint32_t offs) {      // entries [E0, E1) of the quarter-tile; E0 is a multiple of 8
-            const uint32_t E0 = __shfl_sync(0xffffffffu, offs, 0), E1 = __shfl_sync(0xffffffffu, offs, kWWords);
-            uint32_t n = E1 - E0;
-            if (n > (uint32_t)kWListCap) n = kWListCap;
-            for (uint32_t i = lane * 2; i < n; i += 64)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(lent_u32 + i * 8), "l"(p.entries + E0 + i) : "memory");
+        uint32_t stream_base = 0;
+        auto request_page = [&](uint32_t pg) {
+            const uint2* src = p.entries + stream_base + (size_t)pg * kWListPage;
+            const uint32_t dst = lpage_u32 + (pg & 1u) * (kWListPage * 8);
+            for (uint32_t i = lane * 2; i < (uint32_t)kWListPage; i += 64)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 8), "l"(src + i) : "memory");
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        uint32_t it = 0;
-        uint32_t off_cur = 0, off_next = 0;
-        if (my_begin < my_end) {
-            off_cur = fetch_offsets(my_begin);
-            copy_lists(off_cur);
-            if (my_begin + 1 < my_end) off_next = fetch_offsets(my_begin + 1);
-        }
-        for (uint32_t t = my_begin; t < my_end; ++t, ++it) {
-            const uint32_t acc = it % kWAccs, acc_phase = (it / kWAccs) & 1;
-            const uint32_t E0 = __shfl_sync(0xffffffffu, off_cur, 0);
-            uint32_t eoff[kWWords + 1];             // chunk boundaries relative to the quarter-tile's list
-#pragma unroll
-            for (int j = 0; j <= kWWords; ++j) eoff[j] = __shfl_sync(0xffffffffu, off_cur, j) - E0;
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();
-            mbar_wait(&tail->tmem_full[acc], acc_phase, p.error_flag, 16);
-            tc_fence_after();
-            if (quarter == 0 && it < 2) WTRACE(10 + 2 * it);   // accumulator of tile 0 / 1 complete
-#pragma unroll
-            for (int j = 0; j < kWWords; ++j) {
-                const uint32_t e0 = eoff[j], e1 = eoff[j + 1];
-                if (e0 == e1) continue;
-                uint32_t v[32];
-                const bool tr = quarter == 0 && it == 1 && j < 3;
-                if (tr) WCLOCK(16 + j * 4);
-                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kWCols + j * 32u;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (tr) WCLOCK(17 + j * 4);
-                uint4* srow = reinterpret_cast<uint4*>(stg + lane * kWEpiRowWords);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) srow[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        uint32_t cur_page = 0;
+        auto ensure_page = [&](uint32_t pg) {       // pages are consumed in ascending order
+            while (cur_page < pg) {
+                // page cur_page must have LANDED (a skipped page may still be in flight) and every lane must be done with
+                // it before its buffer takes page cur_page + 2
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
                 __syncwarp();
-                if (tr) WCLOCK(18 + j * 4);
-                // four passes of 32 entries at a time: the list reads, the gathers and the stores of a group are
-                // independent of one another (one epilogue warp per scheduler: every dependent instruction costs its
-                // full latency, so the loop is written for instruction count and ILP)
-                if (e1 <= (uint32_t)kWListCap) {
-                    for (uint32_t eb = e0; eb < e1; eb += 128) {
-                        uint2 en[4];
-                        float val[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const uint32_t e = eb + u * 32 + lane;
-                            en[u] = lent[e < e1 ? e : e0];
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) val[u] = *reinterpret_cast<const float*>(stg_bytes + en[u].x);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (eb + u * 32 + lane < e1) p.P[en[u].y] = val[u];
+                request_page(cur_page + 2);
+                ++cur_page;
+            }
+            asm volatile("cp.async.wait_group 1;" ::: "memory");    // all but the newest request (page cur_page + 1) have landed
+            __syncwarp();
+        };
+        uint32_t it = 0;
+        if (my_begin < my_end) {
+            stream_base = __shfl_sync(0xffffffffu, unit_offsets(my_begin, 0), 0);   // multiple of 8 entries: 16-byte aligned pages
+            request_page(0);
+            request_page(1);
+        }
+        for (uint32_t pass = 0; pass < passes; ++pass) {
+            if (pass > 0 && my_begin < my_end) {    // K = 256: the second walk starts the stream again
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                stream_base = __shfl_sync(0xffffffffu, unit_offsets(my_begin, pass * SGP), 0);
+                cur_page = 0;
+                request_page(0);
+                request_page(1);
+            }
+            uint32_t off_next = my_begin < my_end ? unit_offsets(my_begin, pass * SGP) : 0u;
+            for (uint32_t t = my_begin; t < my_end; ++t, ++it) {
+                const uint32_t acc = it % naccs, acc_phase = (it / naccs) & 1;
+                for (uint32_t sg = 0; sg < SGP; ++sg) {
+                    const uint32_t off_cur = off_next;
+                    {   // offsets of the next unit: requested now, used one unit later
+                        uint32_t tn = t, sn = sg + 1;
+                        if (sn == SGP) { sn = 0; ++tn; }
+                        if (tn < my_end) off_next = unit_offsets(tn, pass * SGP + sn);
                     }
-                } else {                              // list longer than the shared-memory copy: straight from global memory
-                    for (uint32_t e = e0 + lane; e < e1; e += 32) {
-                        const uint2 en = e < (uint32_t)kWListCap ? lent[e] : __ldg(p.entries + E0 + e);
-                        p.P[en.y] = *reinterpret_cast<const float*>(stg_bytes + en.x);
+                    uint32_t eoff[kWWords + 1];             // chunk boundaries relative to the stream
+#pragma unroll
+                    for (int j = 0; j <= kWWords; ++j) eoff[j] = __shfl_sync(0xffffffffu, off_cur, j) - stream_base;
+                    if (sg == 0) {
+                        mbar_wait(&tail->tmem_full[acc], acc_phase, p.error_flag, 16);
+                        tc_fence_after();
+                        if (quarter == 0 && it < 2) WTRACE(10 + 2 * it);   // accumulators of tile 0 / 1 complete
+                    }
+#pragma unroll
+                    for (int j = 0; j < kWWords; ++j) {
+                        const uint32_t e0 = eoff[j], e1 = eoff[j + 1];
+                        if (e0 == e1) continue;
+                        uint32_t v[32];
+                        const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + (acc * SGP + sg) * kWCols + j * 32u;
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                            : "r"(taddr));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        uint4* srow = reinterpret_cast<uint4*>(stg + lane * kWEpiRowWords);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) srow[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        __syncwarp();
+                        // the chunk's entries, page by page, four passes of 32 entries at a time
+                        for (uint32_t e = e0; e < e1;) {
+                            const uint32_t pg = e / kWListPage;
+                            ensure_page(pg);
+                            const uint32_t pend = (pg + 1) * kWListPage;
+                            const uint32_t seg_end = e1 < pend ? e1 : pend;
+                            const uint2* lent = lpage + (pg & 1u) * kWListPage - (size_t)pg * kWListPage;   // lent[e] = entry e of the stream
+                            for (uint32_t eb = e; eb < seg_end; eb += 128) {
+                                uint2 en[4];
+                                float val[4];
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const uint32_t ee = eb + q * 32 + lane;
+                                    en[q] = lent[ee < seg_end ? ee : e];
+                                }
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) val[q] = *reinterpret_cast<const float*>(stg_bytes + en[q].x);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    if (eb + q * 32 + lane < seg_end) p.P[en[q].y] = val[q];
+                            }
+                            e = seg_end;
+                        }
+                        __syncwarp();
+                    }
+                    if (sg + 1 == SGP) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
+                        if (quarter == 0 && it < 2) WTRACE(11 + 2 * it);   // epilogue of tile 0 / 1 done
                     }
                 }
-                __syncwarp();
-                if (tr) WCLOCK(19 + j * 4);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
-            if (quarter == 0 && it < 2) WTRACE(11 + 2 * it);   // epilogue of tile 0 / 1 done
-            // next tile: its list goes into the buffer this tile no longer needs
-            off_cur = off_next;
-            if (t + 1 < my_end) copy_lists(off_cur);
-            if (t + 2 < my_end) off_next = fetch_offsets(t + 2);
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (quarter == 0) WTRACE(14);              // epilogue done
@@ -512,16 +515,15 @@ int launch_wide(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, f
         return BSMR_ERR_UNSUPPORTED;
     }
     const uint32_t kchunks = K / kWChunk;
-    // Shared memory and L1 share 228 KB per SM, and every LDG in flight holds an L1 line: with the full 227 KB of
-    // shared memory the producers could keep only ~1 KB of B in flight per SM (measured: 3 us per 32 KB stage).  The
-    // ring is therefore short (the register ring is the prefetch pipeline, the smem ring only decouples the stores from
-    // the MMAs): 2 stages keep K <= 128 under the 132 KB carve-out (96 KB of L1 for kNBuf x 16 KB in flight).
+    // the A images of both sub-groups stay resident when they fit (K <= 128: 2 x K/32 x 16 KB <= 128 KB); at K = 256
+    // one sub-group is resident at a time and the CTA walks its tile range twice
+    const uint32_t sgp = kchunks <= 4 ? 2u : 1u;
     const size_t max_smem = 232448;   // 227 KB per CTA on sm_100
-    const size_t fixed = 1024 + sizeof(WideSmemTail) + (size_t)kWEpiWarps * (kWEpiStageBytes + kWListBytes) + (size_t)kchunks * kWAChunkBytes;
+    const size_t fixed = 1024 + sizeof(WideSmemTail) + (size_t)kWEpiWarps * (kWEpiStageBytes + kWListBytes) +
+                         (size_t)sgp * kchunks * kWAImgBytes;
     uint32_t stages = static_cast<uint32_t>((max_smem - fixed) / kWBStageBytes);
     static const uint32_t stage_cap = [] { const char* e = std::getenv("BSMR_WIDE_STAGES"); return e ? (uint32_t)std::atoi(e) : 0u; }();
-    const uint32_t want = stage_cap ? stage_cap : 2u;
-    if (stages > want) stages = want;
+    if (stage_cap && stages > stage_cap) stages = stage_cap;
     if (stages > (uint32_t)kWMaxStages) stages = kWMaxStages;
     const size_t smem = fixed + (size_t)stages * kWBStageBytes;
     static bool attr_set = false;
@@ -535,16 +537,21 @@ int launch_wide(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, f
         BSMR_CUDA_OK(cudaMemsetAsync(error_flag.ptr, 0, 4, ctx->stream));
         BSMR_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     }
+    CUtensorMap map_a, map_b;
+    BSMR_TRY(make_row_gather_map(ctx, dA, plan->M, K, &map_a));
+    BSMR_TRY(make_row_gather_map(ctx, dB, plan->N, K, &map_b));
     WideParams p{};
-    p.K = K; p.kchunks = kchunks; p.stages = stages;
+    p.K = K; p.kchunks = kchunks; p.stages = stages; p.sgp = sgp;
     p.num_rows = static_cast<uint32_t>(plan->h_reordered_rows.size());
+    p.M = plan->M; p.N = plan->N;
     p.cta_begin = plan->w_cta_begin.ptr;
     p.tile_meta = plan->wt_meta.ptr;
     p.cols = plan->w_cols.ptr;
+    p.num_tiles = plan->num_wide_tiles;
     p.sb_off = plan->w_sb_off.ptr;
     p.entries = plan->w_entries.ptr;
     p.reordered_rows = plan->reordered_rows.ptr;
-    p.A = dA; p.B = dB; p.P = dP;
+    p.P = dP;
     p.error_flag = error_flag.ptr;
     p.trace = g_wide_trace;
     g_wide_trace = nullptr;
@@ -553,7 +560,7 @@ int launch_wide(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, f
         return BSMR_ERR_BAD_STATE;
     }
     const uint32_t grid = plan->w_grid;   // one CTA per SM
-    wide_sddmm_kernel<<<grid, kWThreads, smem, stream>>>(p);
+    wide_sddmm_kernel<<<grid, kWThreads, smem, stream>>>(map_a, map_b, p);
     ctx->launches++;
     BSMR_CUDA_OK(cudaGetLastError());
     return BSMR_OK;

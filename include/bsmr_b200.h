@@ -32,9 +32,10 @@ extern "C" {
 #define BSMR_ROW_PANEL_SIZE 16u        /* ROW_PANEL_SIZE, include/BSMR.hpp:8  */
 #define BSMR_BLOCK_COL_SIZE 16u        /* BLOCK_COL_SIZE, include/BSMR.hpp:9  */
 #define BSMR_NULL_VALUE 0xFFFFFFFFu    /* NULL_VALUE, include/TensorCoreConfig.cuh:12 */
-/* wide row groups (no counterpart in the reference): 128 consecutive reordered rows (8 panels) whose
- * distinct columns stream through one 128 x 128 tcgen05 tile at a time; see csrc/wide_tc.cu          */
-#define BSMR_WIDE_GROUP_ROWS 128u
+/* wide row groups (no counterpart in the reference): 256 consecutive reordered rows (16 panels, two
+ * 128-row tcgen05 operands resident in shared memory) whose distinct columns stream past them 128 at
+ * a time; see csrc/wide_tc.cu                                                                       */
+#define BSMR_WIDE_GROUP_ROWS 256u
 #define BSMR_WIDE_TILE_COLS  128u
 
 typedef enum {
@@ -141,9 +142,9 @@ typedef struct {
     /* execution plan of the SDDMM kernels (internal layout, not part of the reference's BSMR object):
      * row groups that are dense enough at 128-row scale run through the wide tcgen05 kernel, the
      * remaining groups through the dense-block + residual kernels                                 */
-    uint32_t num_row_groups;      /* ceil(#reordered rows / 128)                               */
+    uint32_t num_row_groups;      /* ceil(#reordered rows / 256)                               */
     uint32_t num_wide_groups;     /* row groups on the wide path                               */
-    uint32_t num_wide_tiles;      /* 128 x <=128 tcgen05 work items of the wide path           */
+    uint32_t num_wide_tiles;      /* 256 x <=128 work items (two 128 x 128 tcgen05 accumulators) of the wide path           */
     uint32_t num_block_tiles;     /* dense-block tiles left outside the wide groups            */
     uint64_t num_wide_values;     /* nnz computed by the wide kernel                           */
     uint64_t num_block_values;    /* nnz computed by the dense-block kernel (outside wide groups) */
@@ -189,7 +190,7 @@ int bsmr_sddmm_profile3(bsmr_plan* plan, uint32_t K, const float* dA, const floa
                         uint32_t flags, float* wide_ms, float* dense_ms, float* residual_ms);
 
 /* Wide-path policy of a plan, applied at the next column reorder: a row group goes wide when
- * nnz(group) >= ratio * (128 * tiles(group) + 128).  ratio <= 0 disables the wide path; the default
+ * nnz(group) >= ratio * (128 * tiles(group) + 256).  ratio <= 0 disables the wide path; the default
  * is 2.0 (environment override: BSMR_WIDE_RATIO).                                              */
 int bsmr_plan_set_wide_ratio(bsmr_plan* plan, float ratio);
 
