@@ -11,8 +11,8 @@ At N GPUs the job is N such row blocks stacked into one matrix, reordered global
 over the ranks by nnz-balanced ranges of reordered row panels (bsmr_plan_set_shard): weak scaling,
 per-GPU work fixed, no collective on the data path (B is replicated before the clock starts).
 
-A "step" = one pass of the hot path (dense-block tcgen05 kernel + residual kernel) over the
-matrix.  The inputs (27 MB) fit in L2, so L2 is flushed (a 512 MB buffer is rewritten) between
+A "step" = one pass of the hot path (wide row-group tcgen05 kernel + dense-block tcgen05 kernel +
+residual kernel, each over its share of the nnz) over the matrix.  The inputs (27 MB) fit in L2, so L2 is flushed (a 512 MB buffer is rewritten) between
 timed steps, outside the event pairs.  Times are CUDA events on the stream the kernels run on.
 """
 import argparse
@@ -247,13 +247,14 @@ def main():
     value = 2.0 * nnz * K / (ms_per_step * 1e-3) / 1e9
 
     # ---- per-kernel times (cold L2), the roofline of the dominant kernel -------------------------
-    dense_ms, res_ms = [], []
+    wide_ms, dense_ms, res_ms = [], [], []
     for _ in range(min(args.steps, 20)):
         flush.fill_(1)
-        a, b = plan.sddmm_profile(K, dA, dB, dP)
+        w, a, b = plan.sddmm_profile3(K, dA, dB, dP)
+        wide_ms.append(w)
         dense_ms.append(a)
         res_ms.append(b)
-    dense_ms, res_ms = float(np.mean(dense_ms)), float(np.mean(res_ms))
+    wide_ms, dense_ms, res_ms = float(np.mean(wide_ms)), float(np.mean(dense_ms)), float(np.mean(res_ms))
     # back-to-back, L2-resident figure (diagnostic: what the reference's own timing loop measures)
     hot_ms = plan.sddmm(K, dA, dB, dP, iterations=100)
 
@@ -292,32 +293,47 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    # which nnz each of the three kernels computes (rank 0's shard when N > 1): the wide kernel owns whole row groups
+    # (256 reordered rows = 16 panels); outside them the BSMR split applies (residual list / dense blocks)
     rows = plan.vector("reordered_rows")
     sv = plan.vector("sparse_values")
     svo = plan.vector("sparse_value_offsets")
+    gw = plan.vector("group_wide").astype(bool)
     p0, p1 = (0, info["num_row_panels"]) if world == 1 else plan.set_shard(rank, world)[:2]
-    res_idx = sv[svo[p0]:svo[p1]]
     row_of = np.repeat(np.arange(M, dtype=np.int64), np.diff(ro.astype(np.int64)))
-    res_bytes = kernel_alg_bytes(K, len(np.unique(row_of[res_idx])), len(np.unique(ci[res_idx])), len(res_idx), 8)
-    shard_rows = rows[p0 * 16:p1 * 16]
-    in_shard = np.zeros(M, dtype=bool)
-    in_shard[shard_rows] = True
-    nz_mask = in_shard[row_of]
+    pos_of_row = np.full(M, -1, dtype=np.int64)
+    pos_of_row[rows] = np.arange(len(rows))
+    pos = pos_of_row[row_of]                                   # reordered position of every nnz's row
+    in_shard = (pos >= p0 * 16) & (pos < p1 * 16)
+    is_wide = np.zeros(nnz, dtype=bool)
+    if info["num_wide_tiles"]:
+        is_wide = in_shard & gw[np.clip(pos // pkg.WIDE_GROUP_ROWS, 0, len(gw) - 1)]
     is_res = np.zeros(nnz, dtype=bool)
-    is_res[res_idx] = True
-    dense_mask = nz_mask & ~is_res
-    n_dense = int(dense_mask.sum())
-    dense_bytes = kernel_alg_bytes(K, len(np.unique(row_of[dense_mask])), len(np.unique(ci[dense_mask])), n_dense, 0)
-    step_bytes = pkg.synth.algorithmic_bytes(M, N, K, ro, ci) if world == 1 else dense_bytes + res_bytes
-    if res_ms >= dense_ms:
-        dom, dom_ms, dom_bytes = "residual_sddmm_kernel", res_ms, res_bytes
-    else:
-        dom, dom_ms, dom_bytes = "dense_sddmm_kernel (tcgen05)", dense_ms, dense_bytes
+    is_res[sv[svo[p0]:svo[p1]]] = True
+    is_res &= ~is_wide
+    is_blk = in_shard & ~is_wide & ~is_res
+
+    def part_bytes(mask, extra):
+        n = int(mask.sum())
+        if n == 0:
+            return 0
+        return kernel_alg_bytes(K, len(np.unique(row_of[mask])), len(np.unique(ci[mask])), n, extra)
+
+    parts = [("wide_sddmm_kernel (tcgen05, 256-row groups)", wide_ms, part_bytes(is_wide, 0)),
+             ("dense_sddmm_kernel (tcgen05, 16x16 blocks)", dense_ms, part_bytes(is_blk, 0)),
+             ("residual_rows_kernel", res_ms, part_bytes(is_res, 8))]
+    step_bytes = pkg.synth.algorithmic_bytes(M, N, K, ro, ci) if world == 1 else sum(x[2] for x in parts)
+    dom, dom_ms, dom_bytes = max(parts, key=lambda x: x[1])
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    # DRAM bytes per launch of that kernel from the committed ncu --set full capture of this workload, if any
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath) and world == 1:
+        traffic = json.load(open(tpath)).get("K%d" % K, {}).get(dom.split(" ")[0])
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(dom_bytes), "kernel_ms": dom_ms,
-                "other_kernel_ms": dense_ms if dom.startswith("residual") else res_ms,
+                "other_kernels_ms": {n: ms for n, ms, _ in parts if n != dom},
                 "step": {"algorithmic_bytes": int(step_bytes), "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
                          "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak}}
 
@@ -345,7 +361,7 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32 (dense blocks) / f32 (residual), f32 accumulate", "data": "synthetic",
+            "vs_baseline": None, "dtype": "tf32 (tcgen05 wide groups and dense blocks) / f32 (residual), f32 accumulate", "data": "synthetic",
             "config": workload_config(M, N, nnz, K, source, world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
@@ -358,8 +374,13 @@ def main():
                         "block_size": info["block_size"], "clusters": info["num_clusters_true"],
                         "dense_nnz": int(info["num_dense_values"]), "residual_nnz": int(info["num_sparse_values"]),
                         "dense_tiles": info["num_dense_tiles"],
+                        "plan": {"row_groups": info["num_row_groups"], "wide_groups": info["num_wide_groups"],
+                                 "wide_tiles": info["num_wide_tiles"], "wide_nnz": int(info["num_wide_values"]),
+                                 "block_tiles": info["num_block_tiles"], "block_nnz": int(info["num_block_values"]),
+                                 "residual_nnz_outside_wide": int(info["num_residual_values"]),
+                                 "wide_format_ms": info["wide_format_ms"]},
                         "gflops_incl_reorder": 2.0 * nnz * K / ((ms_per_step + reorder_wall_ms) * 1e-3) / 1e9},
-            "kernels": {"dense_ms_cold": dense_ms, "residual_ms_cold": res_ms, "step_ms_hot_l2": hot_ms,
+            "kernels": {"wide_ms_cold": wide_ms, "dense_ms_cold": dense_ms, "residual_ms_cold": res_ms, "step_ms_hot_l2": hot_ms,
                         "gflops_hot_l2": 2.0 * shard_nnz * K / (hot_ms * 1e-3) / 1e9}}
     print(json.dumps(line), flush=True)
     if world > 1:

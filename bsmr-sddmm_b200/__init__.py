@@ -29,7 +29,7 @@ WIDE_GROUP_ROWS, WIDE_TILE_COLS = 256, 128
 
 VEC = dict(reordered_rows=0, dense_cols=1, dense_col_offsets=2, sparse_cols=3, sparse_col_offsets=4,
            sparse_value_offsets=5, block_offsets=6, block_values=7, sparse_values=8,
-           sparse_relative_rows=9, sparse_col_indices=10, dispersions=11, cluster_ids=12)
+           sparse_relative_rows=9, sparse_col_indices=10, dispersions=11, cluster_ids=12, group_wide=13)
 
 u32p = C.POINTER(C.c_uint32)
 f32p = C.POINTER(C.c_float)

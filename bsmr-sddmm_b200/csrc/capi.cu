@@ -288,6 +288,11 @@ static int fetch_vector(bsmr_plan* p, int which, std::vector<uint32_t>& tmp, con
             return BSMR_OK;
         case BSMR_VEC_DISPERSIONS: *ref = &p->h_dispersions; return BSMR_OK;
         case BSMR_VEC_CLUSTER_IDS: *ref = &p->h_cluster_ids; return BSMR_OK;
+        case BSMR_VEC_GROUP_WIDE:
+            if (!p->have_format) break;
+            tmp.assign(p->h_group_wide.begin(), p->h_group_wide.end());
+            *ref = &tmp;
+            return BSMR_OK;
         case BSMR_VEC_DENSE_COLS: if (!p->have_cols) break; *ref = &p->h_dense_cols; return BSMR_OK;
         case BSMR_VEC_DENSE_COL_OFFSETS: if (!p->have_cols) break; *ref = &p->h_dense_col_offsets; return BSMR_OK;
         case BSMR_VEC_SPARSE_COLS: if (!p->have_cols) break; *ref = &p->h_sparse_cols; return BSMR_OK;

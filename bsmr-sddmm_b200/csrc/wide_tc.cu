@@ -89,6 +89,7 @@ struct WideParams {
     const uint32_t* reordered_rows;
     float* P;
     uint32_t* error_flag;
+    uint32_t debug;                  // timing experiments only (BSMR_WIDE_DEBUG): 4 = epilogue skips every chunk (wrong results)
     unsigned long long* trace;       // optional (tests/perf probes): 32 time stamps per CTA
 };
 
@@ -198,23 +199,21 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (t + 1 < my_end) fetch_cols(t + 1, ncols_next, cols_next);   // indices of the next tile: off the critical path
                 const uint32_t g = __ldg(p.tile_meta + t).x;
                 const uint32_t key = g * 2 + pass;
-                if (key != cur_key) {
-                    // (re)load the A images: [sub-group of the pass][K-chunk], 32 requests each
+                const bool new_key = key != cur_key;
+                int4 arows[2];
+                arows[0] = arows[1] = make_int4((int)p.M, (int)p.M, (int)p.M, (int)p.M);
+                if (new_key) {
+                    // (re)load the A images, [sub-group of the pass][K-chunk] x 32 requests, interleaved with the B stages of
+                    // this tile: chunk kc of A, then stage kc of B, so that the first MMAs start after one chunk has landed
+                    // instead of after the whole 128 KB image
                     if (a_loads > 0) mbar_wait(&tail->a_free, (a_loads - 1) & 1, p.error_flag, 11);
-                    for (uint32_t sg = 0; sg < SGP; ++sg) {
-                        int4 rows = make_int4((int)p.M, (int)p.M, (int)p.M, (int)p.M);
-                        if (issuer) {
+                    if (issuer) {
+                        for (uint32_t sg = 0; sg < SGP; ++sg) {
                             const uint32_t r0 = g * kWGroupRows + (pass * SGP + sg) * kWSubRows + rq * 4;
-                            int* rp = reinterpret_cast<int*>(&rows);
+                            int* rp = reinterpret_cast<int*>(&arows[sg]);
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
                                 if (r0 + j < p.num_rows) rp[j] = (int)__ldg(p.reordered_rows + r0 + j);
-                        }
-                        for (uint32_t kc = 0; kc < KC; ++kc) {
-                            if (sg == 0 && warp == 0 && lane == 0) mbar_arrive_expect_tx(&tail->a_full[kc], SGP * kWAImgBytes);
-                            if (issuer)
-                                tma_gather4(&map_a, &tail->a_full[kc], a_img + ((size_t)sg * KC + kc) * kWAImgBytes + rq * 512,
-                                            (int)(kc * kWChunk), rows);
                         }
                     }
                     cur_key = key;
@@ -223,6 +222,14 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const bool has_cols = issuer && rq * 4 < ncols;
                 const uint32_t tx_bytes = ((ncols + 3) / 4) * 512u;
                 for (uint32_t kc = 0; kc < KC; ++kc) {
+                    if (new_key) {
+                        if (warp == 0 && lane == 0) mbar_arrive_expect_tx(&tail->a_full[kc], SGP * kWAImgBytes);
+                        if (issuer) {
+                            for (uint32_t sg = 0; sg < SGP; ++sg)
+                                tma_gather4(&map_a, &tail->a_full[kc], a_img + ((size_t)sg * KC + kc) * kWAImgBytes + rq * 512,
+                                            (int)(kc * kWChunk), arows[sg]);
+                        }
+                    }
                     mbar_wait(&tail->b_empty[stage], phase ^ 1, p.error_flag, 12);
                     if (warp == 0 && lane == 0) mbar_arrive_expect_tx(&tail->b_full[stage], tx_bytes);
                     if (has_cols)
@@ -243,25 +250,26 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (uint32_t pass = 0; pass < passes; ++pass) {
             for (uint32_t t = my_begin; t < my_end; ++t) {
                 const uint32_t key = __ldg(p.tile_meta + t).x * 2 + pass;
-                if (key != cur_key) {
-                    for (uint32_t kc = 0; kc < KC; ++kc) {
+                const bool new_key = key != cur_key;
+                for (uint32_t kc = 0; kc < KC; ++kc) {
+                    if (new_key) {
                         mbar_wait(&tail->a_full[kc], a_idx & 1, p.error_flag, 17);
                         for (uint32_t sg = 0; sg < SGP; ++sg) round_image<8>(a_img + ((size_t)sg * KC + kc) * kWAImgBytes, ci);
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tail->a_ready[kc]);
                     }
-                    cur_key = key;
-                    ++a_idx;
-                    if (warp == kWConvWarp0) WTRACE(2);        // A images rounded
-                }
-                for (uint32_t kc = 0; kc < KC; ++kc) {
                     mbar_wait(&tail->b_full[stage], phase, p.error_flag, 18);
-                    round_image<8>(b_ring + (size_t)stage * kWBStageBytes, ci);
+                    if (!(p.debug & 8u)) round_image<8>(b_ring + (size_t)stage * kWBStageBytes, ci);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tail->b_ready[stage]);
                     if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+                if (new_key) {
+                    cur_key = key;
+                    ++a_idx;
+                    if (warp == kWConvWarp0) WTRACE(2);        // A images rounded
                 }
             }
         }
@@ -287,7 +295,7 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     tc_fence_after();
                     if (lane == 0) {
                         const uint64_t db = make_smem_desc(smem_u32(b_ring + (size_t)stage * kWBStageBytes));
-                        for (uint32_t sg = 0; sg < SGP; ++sg) {
+                        for (uint32_t sg = 0; sg < ((p.debug & 16u) ? 0u : SGP); ++sg) {
                             const uint64_t da = make_smem_desc(smem_u32(a_img + ((size_t)sg * KC + kc) * kWAImgBytes));
                             const uint32_t tmem_d = tmem_base + (acc * SGP + sg) * kWCols;
 #pragma unroll
@@ -385,7 +393,7 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < kWWords; ++j) {
                         const uint32_t e0 = eoff[j], e1 = eoff[j + 1];
-                        if (e0 == e1) continue;
+                        if (e0 == e1 || (p.debug & 4u)) continue;
                         uint32_t v[32];
                         const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + (acc * SGP + sg) * kWCols + j * 32u;
                         asm volatile(
@@ -553,6 +561,8 @@ int launch_wide(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, f
     p.reordered_rows = plan->reordered_rows.ptr;
     p.P = dP;
     p.error_flag = error_flag.ptr;
+    static const uint32_t dbg = [] { const char* e = std::getenv("BSMR_WIDE_DEBUG"); return e ? (uint32_t)std::atoi(e) : 0u; }();
+    p.debug = dbg;
     p.trace = g_wide_trace;
     g_wide_trace = nullptr;
     if (plan->w_part_begin != tile_begin || plan->w_part_end != tile_end || plan->w_grid == 0) {

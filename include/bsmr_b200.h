@@ -120,7 +120,9 @@ typedef enum {
     BSMR_VEC_SPARSE_COL_INDICES = 10,
     /* diagnostics of the row reorder */
     BSMR_VEC_DISPERSIONS = 11,
-    BSMR_VEC_CLUSTER_IDS = 12      /* cluster id per ORIGINAL row (0 = empty row) */
+    BSMR_VEC_CLUSTER_IDS = 12,     /* cluster id per ORIGINAL row (0 = empty row) */
+    /* execution plan: 1 per row group (256 reordered rows) that runs through the wide kernel */
+    BSMR_VEC_GROUP_WIDE = 13
 } bsmr_vector_id;
 int bsmr_plan_vector_size(bsmr_plan* plan, int which, uint64_t* size);
 int bsmr_plan_vector_copy(bsmr_plan* plan, int which, uint32_t* host_out, uint64_t capacity);
