@@ -440,7 +440,7 @@ int h2d(T* dst, const std::vector<T>& src, cudaStream_t s) {
 float wide_ratio_of(const bsmr_plan* plan) {
     if (plan->wide_ratio >= 0.f) return plan->wide_ratio;
     if (const char* e = std::getenv("BSMR_WIDE_RATIO")) return static_cast<float>(std::atof(e));
-    return 2.0f;
+    return 5.0f;
 }
 
 // Everything the SDDMM kernels need to treat some row groups "wide" (see wide_tc.cu) and the others the BSMR way.

@@ -193,7 +193,9 @@ int bsmr_sddmm_profile3(bsmr_plan* plan, uint32_t K, const float* dA, const floa
 
 /* Wide-path policy of a plan, applied at the next column reorder: a row group goes wide when
  * nnz(group) >= ratio * (128 * tiles(group) + 256).  ratio <= 0 disables the wide path; the default
- * is 2.0 (environment override: BSMR_WIDE_RATIO).                                              */
+ * is 5.0, i.e. ~2 % fill of a 256 x 128 tile: below that the residual kernel's one K-vector
+ * of B per nnz is cheaper than streaming the tile (measured on R-MAT hub groups; environment override:
+ * BSMR_WIDE_RATIO).                                              */
 int bsmr_plan_set_wide_ratio(bsmr_plan* plan, float ratio);
 
 /* Number of kernels of this library launched on the context so far (bench.py's gpu_launches). */

@@ -1,4 +1,4 @@
-"""Small fixed workload for ncu captures (B200 box): python tests/ncu_target.py <workload> <K> <delta> [identity]
+"""Small fixed workload for ncu captures (B200 box): python tests/ncu_target.py <workload> <K> <delta> [identity] [nowide]
 
 Runs the reorder once and a handful of SDDMM passes, so that `ncu -k regex:... -s N -c M` can pick launches."""
 import os
@@ -15,7 +15,8 @@ def main():
     import torch
     pkg = entry.load_package()
     name, K, delta = sys.argv[1], int(sys.argv[2]), float(sys.argv[3])
-    identity = len(sys.argv) > 4
+    identity = "identity" in sys.argv[4:]
+    nowide = "nowide" in sys.argv[4:]          # force the reference's split: dense-block + residual kernels only
     s = pkg.synth
     gen = {"nips": lambda: s.nips_like(), "graph17": lambda: s.rmat(17, 3_000_000, 17),
            "blocks16k": lambda: s.block_structured(16000, 16000, seed=5, groups=200, cols_per_group=96, noise=0.001),
@@ -33,7 +34,7 @@ def main():
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
     for _ in range(6):
         flush.fill_(1)
-        plan.sddmm_profile(K, dA, dB, dP)
+        plan.sddmm_profile(K, dA, dB, dP, flags=pkg.SDDMM_NO_WIDE if nowide else pkg.SDDMM_DEFAULT)
     torch.cuda.synchronize()
     print(plan.info())
 
