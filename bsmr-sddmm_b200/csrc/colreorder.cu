@@ -310,62 +310,62 @@ __global__ void fill_wide_kernel(uint32_t num_wide, const uint32_t* __restrict__
     }
 }
 
-// W2b: nnz of every 32 x 32 sub-block (tile, TMEM lane quarter, 32-column chunk); one warp per sub-block, lane = row
+// W2b: nnz of every 32 x 32 sub-block, sb = (tile * kWW + column quarter j) * kWQ + row quarter rq; one warp per
+// sub-block, lane = row
 __global__ void wide_subblock_count_kernel(uint32_t num_sb, const uint32_t* __restrict__ mask, uint32_t* __restrict__ sb_cnt) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t sb = warp; sb < num_sb; sb += stride) {
-        const uint32_t t = (uint32_t)(sb / (kWQ * kWW)), q = (uint32_t)(sb / kWW) % kWQ, j = (uint32_t)(sb % kWW);
-        uint32_t c = __popc(mask[((size_t)t * kWW + j) * kWideRows + q * 32 + lane]);
+        const uint32_t rq = (uint32_t)(sb % kWQ), j = (uint32_t)(sb / kWQ) % kWW, t = (uint32_t)(sb / (kWQ * kWW));
+        uint32_t c = __popc(mask[((size_t)t * kWW + j) * kWideRows + rq * 32 + lane]);
 #pragma unroll
         for (int w = 16; w >= 1; w >>= 1) c += __shfl_xor_sync(0xffffffffu, c, w);
         if (lane == 0) sb_cnt[sb] = c;
     }
 }
 
-// stream position of the work list of quarter-tile tq = tile * kWQ + sub-group * 4 + TMEM quarter: the lists are laid out
-// by (TMEM quarter, tile, sub-group), i.e. everything ONE epilogue warp of the wide kernel consumes while it walks a
-// range of tiles is one contiguous stream of entries (it pages through it with cp.async)
-__host__ __device__ inline uint64_t wide_stream_index(uint64_t tq, uint32_t wtiles) {
-    const uint64_t t = tq / kWQ, rowq = tq % kWQ;
-    return ((rowq % 4) * wtiles + t) * (kWQ / 4) + rowq / 4;
-}
+// The wide kernel computes the TRANSPOSED tile (lanes = the tile's 128 columns, TMEM columns = the group's 256 rows), so
+// an epilogue warp owns 32 tile columns (TMEM lane quarter j) and walks the 8 row quarters of the group.  Unit = (tile,
+// column quarter j): kWQ sub-blocks of 32 rows x 32 columns.  The lists are laid out by (j, tile): everything one
+// epilogue warp consumes while it walks a range of tiles is one contiguous stream (it pages through it with cp.async).
+__host__ __device__ inline uint64_t wide_unit_stream_index(uint64_t t, uint32_t j, uint32_t wtiles) { return (uint64_t)j * wtiles + t; }
 
-// W2b': entries of every (tile, quarter), padded to a multiple of 8 so that a quarter's list starts 16-byte aligned in
-// both entry arrays (the kernel copies it to shared memory with 16-byte cp.async)
-__global__ void wide_quarter_totals_kernel(uint32_t num_q, uint32_t wtiles, const uint32_t* __restrict__ sb_cnt, uint32_t* __restrict__ q_tot) {
-    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < num_q; q += (uint64_t)gridDim.x * blockDim.x) {
+// W2b': entries of every unit, padded to a multiple of 8 so that a unit's list starts 16-byte aligned
+__global__ void wide_unit_totals_kernel(uint32_t num_units, uint32_t wtiles, const uint32_t* __restrict__ sb_cnt, uint32_t* __restrict__ u_tot) {
+    for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < num_units; u += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t s = 0;
-        for (uint32_t j = 0; j < kWW; ++j) s += sb_cnt[q * kWW + j];
-        q_tot[wide_stream_index(q, wtiles)] = (s + 7u) & ~7u;
+        for (uint32_t rq = 0; rq < kWQ; ++rq) s += sb_cnt[u * kWQ + rq];
+        u_tot[wide_unit_stream_index(u / kWW, (uint32_t)(u % kWW), wtiles)] = (s + 7u) & ~7u;
     }
 }
-// sb_off9[stream_index(q) * (kWW + 1) + j] = first entry of chunk j of quarter-tile q (j = kWW: end of the last chunk)
-__global__ void wide_subblock_offsets_kernel(uint32_t num_q, uint32_t wtiles, const uint32_t* __restrict__ sb_cnt,
-                                             const uint32_t* __restrict__ q_base, uint32_t* __restrict__ sb_off9) {
-    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < num_q; q += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t si = wide_stream_index(q, wtiles);
-        uint32_t o = q_base[si];
-        for (uint32_t j = 0; j < kWW; ++j) {
-            sb_off9[si * (kWW + 1) + j] = o;
-            o += sb_cnt[q * kWW + j];
+// sb_off[stream_index(unit) * (kWQ + 1) + rq] = first entry of row quarter rq of the unit (rq = kWQ: end of the last one)
+__global__ void wide_subblock_offsets_kernel(uint32_t num_units, uint32_t wtiles, const uint32_t* __restrict__ sb_cnt,
+                                             const uint32_t* __restrict__ u_base, uint32_t* __restrict__ sb_off) {
+    for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < num_units; u += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t si = wide_unit_stream_index(u / kWW, (uint32_t)(u % kWW), wtiles);
+        uint32_t o = u_base[si];
+        for (uint32_t rq = 0; rq < kWQ; ++rq) {
+            sb_off[si * (kWQ + 1) + rq] = o;
+            o += sb_cnt[u * kWQ + rq];
         }
-        sb_off9[si * (kWW + 1) + kWW] = o;
+        sb_off[si * (kWQ + 1) + kWQ] = o;
     }
 }
 
 // W2c: the epilogue's work list: per sub-block its entries in (row, column) order as
-// (byte offset of the element inside the epilogue's padded 32 x 32 staging image, CSR position).  Everything follows from the masks and the run
-// starts: a row's entries inside a tile half are consecutive CSR positions in ascending column order.
-__global__ void wide_subblock_fill_kernel(uint32_t num_sb, uint32_t wtiles, const uint32_t* __restrict__ mask, const uint32_t* __restrict__ base,
-                                          const uint32_t* __restrict__ sb_off, uint2* __restrict__ entries) {
+// (byte offset of the element inside the epilogue's padded staging image [column][row], CSR position).  Everything
+// follows from the masks and the run starts: a row's entries inside a tile are consecutive CSR positions in ascending
+// column order.
+__global__ void wide_subblock_fill_kernel(uint32_t num_sb, uint32_t wtiles, const uint32_t* __restrict__ mask,
+                                          const uint32_t* __restrict__ base, const uint32_t* __restrict__ sb_off,
+                                          uint2* __restrict__ entries) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t sb = warp; sb < num_sb; sb += stride) {
-        const uint32_t t = (uint32_t)(sb / (kWQ * kWW)), q = (uint32_t)(sb / kWW) % kWQ, j = (uint32_t)(sb % kWW);
-        const uint32_t row = q * 32 + lane;
+        const uint32_t rq = (uint32_t)(sb % kWQ), j = (uint32_t)(sb / kWQ) % kWW, t = (uint32_t)(sb / (kWQ * kWW));
+        const uint32_t row = rq * 32 + lane;
         uint32_t m = mask[((size_t)t * kWW + j) * kWideRows + row];
         const uint32_t cnt = __popc(m);
         uint32_t incl = cnt;                          // inclusive warp scan over the rows
@@ -377,11 +377,11 @@ __global__ void wide_subblock_fill_kernel(uint32_t num_sb, uint32_t wtiles, cons
         if (cnt == 0) continue;
         uint32_t k = base[((size_t)t * kWH + (j >> 2)) * kWideRows + row];
         for (uint32_t jj = j & ~3u; jj < j; ++jj) k += __popc(mask[((size_t)t * kWW + jj) * kWideRows + row]);
-        uint32_t e = sb_off[wide_stream_index(sb / kWW, wtiles) * (kWW + 1) + j] + incl - cnt;
+        uint32_t e = sb_off[wide_unit_stream_index(t, j, wtiles) * (kWQ + 1) + rq] + incl - cnt;
         while (m) {
             const uint32_t b = __ffs(m) - 1;
             m &= m - 1;
-            entries[e] = make_uint2((lane * kWideStageRowWords + b) * 4u, k);
+            entries[e] = make_uint2((b * kWideStageRowWords + lane) * 4u, k);
             ++e;
             ++k;
         }
@@ -564,24 +564,23 @@ int build_wide_format(bsmr_plan* plan, Workspace* ws, const uint64_t* ukeys, con
     ctx->launches += 2;
     // the epilogue's work lists (32 sub-blocks per tile)
     const uint32_t num_sb = wtiles * kWQ * kWW;
-    const uint32_t num_q = wtiles * kWQ;
-    TmpBuf<uint32_t> sb_cnt(ws), q_tot(ws), q_base(ws);
+    const uint32_t num_units = wtiles * kWW;
+    TmpBuf<uint32_t> sb_cnt(ws), u_tot(ws), u_base(ws);
     BSMR_TRY(sb_cnt.alloc(num_sb));
-    BSMR_TRY(q_tot.alloc(static_cast<size_t>(num_q) + 1));
-    BSMR_TRY(q_base.alloc(static_cast<size_t>(num_q) + 1));
-    BSMR_TRY(plan->w_sb_off.alloc(static_cast<size_t>(num_q) * (kWW + 1)));
-    // every quarter-tile list is padded to 8 entries; 16 more so that the kernel's 16-byte copies may run past the end
-    // slack: the kernel's last page copies run past the end of a warp's stream
-    const size_t list_cap = static_cast<size_t>(wide_values) + 8u * num_q + 1024;
+    BSMR_TRY(u_tot.alloc(static_cast<size_t>(num_units) + 1));
+    BSMR_TRY(u_base.alloc(static_cast<size_t>(num_units) + 1));
+    BSMR_TRY(plan->w_sb_off.alloc(static_cast<size_t>(num_units) * (kWQ + 1)));
+    // every unit list is padded to 8 entries; slack: the kernel's last page copies run past the end of a warp's stream
+    const size_t list_cap = static_cast<size_t>(wide_values) + 8u * num_units + 1024;
     BSMR_TRY(plan->w_entries.alloc(list_cap));
     BSMR_CUDA_OK(cudaMemsetAsync(plan->w_entries.ptr, 0, plan->w_entries.bytes(), st));
-    BSMR_CUDA_OK(cudaMemsetAsync(q_tot.ptr + num_q, 0, 4, st));
+    BSMR_CUDA_OK(cudaMemsetAsync(u_tot.ptr + num_units, 0, 4, st));
     wide_subblock_count_kernel<<<grid_for((uint64_t)num_sb * 32, kThreads, sm), kThreads, 0, st>>>(num_sb, plan->w_mask.ptr, sb_cnt.ptr);
-    wide_quarter_totals_kernel<<<grid_for(num_q, kThreads, sm), kThreads, 0, st>>>(num_q, wtiles, sb_cnt.ptr, q_tot.ptr);
-    BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb, q_tot.ptr, q_base.ptr, static_cast<size_t>(num_q) + 1, st));
+    wide_unit_totals_kernel<<<grid_for(num_units, kThreads, sm), kThreads, 0, st>>>(num_units, wtiles, sb_cnt.ptr, u_tot.ptr);
+    BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb, u_tot.ptr, u_base.ptr, static_cast<size_t>(num_units) + 1, st));
     BSMR_TRY(ensure_temp(tb));
-    BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(temp.ptr, tb, q_tot.ptr, q_base.ptr, static_cast<size_t>(num_q) + 1, st));
-    wide_subblock_offsets_kernel<<<grid_for(num_q, kThreads, sm), kThreads, 0, st>>>(num_q, wtiles, sb_cnt.ptr, q_base.ptr, plan->w_sb_off.ptr);
+    BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(temp.ptr, tb, u_tot.ptr, u_base.ptr, static_cast<size_t>(num_units) + 1, st));
+    wide_subblock_offsets_kernel<<<grid_for(num_units, kThreads, sm), kThreads, 0, st>>>(num_units, wtiles, sb_cnt.ptr, u_base.ptr, plan->w_sb_off.ptr);
     wide_subblock_fill_kernel<<<grid_for((uint64_t)num_sb * 32, kThreads, sm), kThreads, 0, st>>>(
         num_sb, wtiles, plan->w_mask.ptr, plan->w_base.ptr, plan->w_sb_off.ptr, plan->w_entries.ptr);
     ctx->launches += 2;

@@ -218,8 +218,8 @@ struct bsmr_plan {
     bsmr::DevBuf<uint32_t> w_cols;            // distinct columns of the wide groups, ascending inside a group
     bsmr::DevBuf<uint32_t> w_mask;            // [tile][8][128]
     bsmr::DevBuf<uint32_t> w_base;            // [tile][2][128]
-    bsmr::DevBuf<uint32_t> w_sb_off;          // [(tile * 4 + quarter) * 9 + chunk]: first entry of the 32 x 32 sub-block (chunk 8: end);
-                                              // a quarter-tile's list starts at a multiple of 8 entries
+    bsmr::DevBuf<uint32_t> w_sb_off;          // [(column quarter * #tiles + tile) * 9 + row quarter]: first entry of the 32 x 32
+                                              // sub-block (9th: end); a unit's list starts at a multiple of 8 entries
     bsmr::DevBuf<uint2> w_entries;            // entry: {byte offset inside the epilogue's staging image, CSR position}
     std::vector<uint32_t> h_wt_group;         // row group of every wide tile
     bsmr::DevBuf<uint32_t> w_cta_begin;       // CTA -> first tile, for tiles [w_part_begin, w_part_end) (wide_partition)

@@ -33,14 +33,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a wrong transaction count must become an error, never a hung GPU.  After a few immediate polls the
-// warp backs off with nanosleep: a warp that spins on try_wait is always "ready" and takes issue slots from the warps
-// that share its scheduler (measured in the wide kernel: the epilogue warps ran 3x slower next to spinning producers).
+// Bounded wait: a wrong transaction count must become an error, never a hung GPU.
+// kBackoff: after a few immediate polls the warp sleeps between polls.  A warp that spins on try_wait is always "ready"
+// and takes issue slots from the warps that share its scheduler (measured in the wide kernel: the epilogue warps ran 3x
+// slower next to spinning producers), but every sleep also adds its length to the hand-over latency, so the
+// latency-critical hops of a pipeline (converter -> MMA issuer) poll without it.
+template <bool kBackoff = true>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* error_flag, uint32_t code) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > 4) __nanosleep(spins < 64 ? 40 : 200);
-        if (spins > kSpinLimit) {
+        ++spins;
+        if (kBackoff && spins > 4) __nanosleep(spins < 64 ? 40 : 200);
+        if (spins > (kBackoff ? kSpinLimit : (kSpinLimit << 4))) {
             atomicExch(error_flag, code);
             __trap();
         }

@@ -44,7 +44,8 @@ constexpr int kWCols = BSMR_WIDE_TILE_COLS;           // max columns of a wide t
 constexpr int kWChunk = 32;                           // floats of K per stage (128 bytes = one swizzle row)
 constexpr int kWAImgBytes = kWSubRows * 128;          // 16 KB: one sub-group x one K-chunk of A
 constexpr int kWBStageBytes = kWCols * 128;           // 16 KB
-constexpr int kWWords = kWCols / 32;                  // 32-column chunks of a tile
+constexpr int kWWords = kWCols / 32;                  // 32-column quarters of a tile (= TMEM lane quarters)
+constexpr int kWRowQ = kWGroupRows / 32;              // 32-row quarters of a row group
 constexpr int kWProducerWarps = 8;                    // warps 0-7: TMA gather4 issue
 constexpr int kWEpiWarp0 = 8;                         // warps 8-11: epilogue, TMEM lane quarter = warp % 4
 constexpr int kWEpiWarps = 4;
@@ -84,8 +85,8 @@ struct WideParams {
     const uint4* tile_meta;          // {group, first column (offset into cols, multiple of 4), #columns, 0}
     const uint32_t* cols;            // distinct columns of the wide groups, ascending inside a group
     uint32_t num_tiles;              // wide tiles of the plan (stride of the per-quarter list streams)
-    const uint32_t* sb_off;          // [((quarter * num_tiles + tile) * 2 + sub-group) * 5 + chunk]: first work-list entry of a 32 x 32 sub-block
-    const uint2* entries;            // entry: {byte offset inside the staging image (row * 36 + column) * 4, CSR position}
+    const uint32_t* sb_off;          // [(column quarter * num_tiles + tile) * 9 + row quarter]: first work-list entry of a 32 x 32 sub-block
+    const uint2* entries;            // entry: {byte offset inside the staging image (column * 36 + row) * 4, CSR position}
     const uint32_t* reordered_rows;
     float* P;
     uint32_t* error_flag;
@@ -128,7 +129,7 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // and every access below would become a generic LD/ST instead of LDS/STS (seen in SASS)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t KC = p.kchunks, S = p.stages, SGP = p.sgp;
-    uint8_t* a_img = smem;                                                   // [SGP][KC] x 16 KB
+    uint8_t* a_img = smem;                                                   // [KC][SGP] x 16 KB: per K-chunk one (SGP x 128)-row image
     uint8_t* b_ring = a_img + (size_t)SGP * KC * kWAImgBytes;                // S x 16 KB
     uint8_t* epi_stage = b_ring + (size_t)S * kWBStageBytes;                 // 4 epilogue warps x 32 rows x 36 words
     uint8_t* epi_lists = epi_stage + (size_t)kWEpiWarps * kWEpiStageBytes;   // 4 x 3 KB
@@ -226,7 +227,7 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         if (warp == 0 && lane == 0) mbar_arrive_expect_tx(&tail->a_full[kc], SGP * kWAImgBytes);
                         if (issuer) {
                             for (uint32_t sg = 0; sg < SGP; ++sg)
-                                tma_gather4(&map_a, &tail->a_full[kc], a_img + ((size_t)sg * KC + kc) * kWAImgBytes + rq * 512,
+                                tma_gather4(&map_a, &tail->a_full[kc], a_img + ((size_t)kc * SGP + sg) * kWAImgBytes + rq * 512,
                                             (int)(kc * kWChunk), arows[sg]);
                         }
                     }
@@ -253,13 +254,13 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const bool new_key = key != cur_key;
                 for (uint32_t kc = 0; kc < KC; ++kc) {
                     if (new_key) {
-                        mbar_wait(&tail->a_full[kc], a_idx & 1, p.error_flag, 17);
-                        for (uint32_t sg = 0; sg < SGP; ++sg) round_image<8>(a_img + ((size_t)sg * KC + kc) * kWAImgBytes, ci);
+                        mbar_wait<false>(&tail->a_full[kc], a_idx & 1, p.error_flag, 17);
+                        for (uint32_t sg = 0; sg < SGP; ++sg) round_image<8>(a_img + ((size_t)kc * SGP + sg) * kWAImgBytes, ci);
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tail->a_ready[kc]);
                     }
-                    mbar_wait(&tail->b_full[stage], phase, p.error_flag, 18);
+                    mbar_wait<false>(&tail->b_full[stage], phase, p.error_flag, 18);
                     if (!(p.debug & 8u)) round_image<8>(b_ring + (size_t)stage * kWBStageBytes, ci);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
@@ -285,19 +286,21 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const bool new_key = key != cur_key;
                 cur_key = key;
                 const bool last_of_key = (t + 1 == my_end) || (__ldg(p.tile_meta + t + 1).x != m.x);
-                const uint32_t n_mma = (m.z + 15u) & ~15u;
-                const uint32_t idesc = make_idesc_tf32(kWSubRows, n_mma);
+                // transposed product: M = the tile's 128 B columns (TMEM lanes), N = the resident rows (SGP x 128 TMEM columns);
+                // one MMA reads 4 KB of B and SGP x 4 KB of A for 128 x N x 8 MACs -- 96 B/cycle of shared memory at N = 256
+                // instead of the 128 B/cycle (the whole pipe) of two M = 128, N = 128 MMAs, which starved the TMA writes
+                const uint32_t idesc = make_idesc_tf32(kWCols, SGP * kWSubRows);
                 mbar_wait(&tail->tmem_empty[acc], acc_phase ^ 1, p.error_flag, 13);
                 tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * (SGP * kWSubRows);
                 for (uint32_t kc = 0; kc < KC; ++kc) {
-                    if (new_key) mbar_wait(&tail->a_ready[kc], a_idx & 1, p.error_flag, 14);
-                    mbar_wait(&tail->b_ready[stage], phase, p.error_flag, 15);
+                    if (new_key) mbar_wait<false>(&tail->a_ready[kc], a_idx & 1, p.error_flag, 14);
+                    mbar_wait<false>(&tail->b_ready[stage], phase, p.error_flag, 15);
                     tc_fence_after();
                     if (lane == 0) {
-                        const uint64_t db = make_smem_desc(smem_u32(b_ring + (size_t)stage * kWBStageBytes));
-                        for (uint32_t sg = 0; sg < ((p.debug & 16u) ? 0u : SGP); ++sg) {
-                            const uint64_t da = make_smem_desc(smem_u32(a_img + ((size_t)sg * KC + kc) * kWAImgBytes));
-                            const uint32_t tmem_d = tmem_base + (acc * SGP + sg) * kWCols;
+                        const uint64_t da = make_smem_desc(smem_u32(b_ring + (size_t)stage * kWBStageBytes));
+                        const uint64_t db = make_smem_desc(smem_u32(a_img + (size_t)kc * SGP * kWAImgBytes));
+                        if (!(p.debug & 16u)) {
 #pragma unroll
                             for (uint32_t k = 0; k < kWChunk / 8; ++k)
                                 umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
@@ -324,17 +327,17 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // follows the nnz, not the tile area (a predicated store per accumulator element cost 4.6 us per 128 x 256
         // tile, measured: one epilogue warp per scheduler pays every dependent instruction's full latency).  The list of
         // stream of the warp is paged through shared memory with cp.async.
-        const uint32_t quarter = warp & 3;          // TMEM lanes [32*quarter, +32): fixed by warp id % 4
+        const uint32_t quarter = warp & 3;          // TMEM lanes [32*quarter, +32) = tile columns: fixed by warp id % 4
         float* stg = reinterpret_cast<float*>(epi_stage + (size_t)quarter * kWEpiStageBytes);
         const uint8_t* stg_bytes = reinterpret_cast<const uint8_t*>(stg);
         const uint2* lpage = reinterpret_cast<const uint2*>(epi_lists + (size_t)quarter * kWListBytes);
         const uint32_t lpage_u32 = smem_u32(lpage);
-        // The lists of this warp's units (tile, sub-group), tile ascending, are ONE contiguous stream of entries in
-        // global memory (layout: quarter, tile, sub-group).  The warp pages through it: two pages of kWListPage entries in
-        // shared memory, page n + 2 requested (cp.async) the moment page n is used up, whatever the fill of the tiles.
-        auto unit_offsets = [&](uint32_t t, uint32_t s) -> uint32_t {   // lane j <= 4: first entry of chunk j (lane 4: end)
-            return lane <= (uint32_t)kWWords
-                       ? __ldg(p.sb_off + (((size_t)quarter * p.num_tiles + t) * kWSub + s) * (kWWords + 1) + lane) : 0u;
+        const uint32_t nch = SGP * 4;               // 32-row chunks of the resident rows per tile
+        // The lists of this warp's units (tile, column quarter), tile ascending, are ONE contiguous stream of entries in
+        // global memory.  The warp pages through it: two pages of kWListPage entries in shared memory, page n + 2
+        // requested (cp.async) the moment page n is used up, whatever the fill of the tiles.
+        auto unit_offsets = [&](uint32_t t) -> uint32_t {   // lane rq <= 8: first entry of row quarter rq (lane 8: end)
+            return lane <= (uint32_t)kWRowQ ? __ldg(p.sb_off + ((size_t)quarter * p.num_tiles + t) * (kWRowQ + 1) + lane) : 0u;
         };
         uint32_t stream_base = 0;
         auto request_page = [&](uint32_t pg) {
@@ -358,90 +361,78 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             __syncwarp();
         };
         uint32_t it = 0;
-        if (my_begin < my_end) {
-            stream_base = __shfl_sync(0xffffffffu, unit_offsets(my_begin, 0), 0);   // multiple of 8 entries: 16-byte aligned pages
-            request_page(0);
-            request_page(1);
-        }
         for (uint32_t pass = 0; pass < passes; ++pass) {
-            if (pass > 0 && my_begin < my_end) {    // K = 256: the second walk starts the stream again
+            const uint32_t rq0 = pass * nch;        // first row quarter of the pass (K = 256: the second walk takes rows 128..255)
+            uint32_t off_next = my_begin < my_end ? unit_offsets(my_begin) : 0u;
+            if (my_begin < my_end) {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 __syncwarp();
-                stream_base = __shfl_sync(0xffffffffu, unit_offsets(my_begin, pass * SGP), 0);
+                stream_base = __shfl_sync(0xffffffffu, off_next, rq0) & ~7u;     // 16-byte aligned pages
                 cur_page = 0;
                 request_page(0);
                 request_page(1);
             }
-            uint32_t off_next = my_begin < my_end ? unit_offsets(my_begin, pass * SGP) : 0u;
             for (uint32_t t = my_begin; t < my_end; ++t, ++it) {
                 const uint32_t acc = it % naccs, acc_phase = (it / naccs) & 1;
-                for (uint32_t sg = 0; sg < SGP; ++sg) {
-                    const uint32_t off_cur = off_next;
-                    {   // offsets of the next unit: requested now, used one unit later
-                        uint32_t tn = t, sn = sg + 1;
-                        if (sn == SGP) { sn = 0; ++tn; }
-                        if (tn < my_end) off_next = unit_offsets(tn, pass * SGP + sn);
-                    }
-                    uint32_t eoff[kWWords + 1];             // chunk boundaries relative to the stream
+                const uint32_t off_cur = off_next;
+                if (t + 1 < my_end) off_next = unit_offsets(t + 1);    // requested now, used one tile later
+                uint32_t eoff[9];                   // chunk boundaries relative to the stream
 #pragma unroll
-                    for (int j = 0; j <= kWWords; ++j) eoff[j] = __shfl_sync(0xffffffffu, off_cur, j) - stream_base;
-                    if (sg == 0) {
-                        mbar_wait(&tail->tmem_full[acc], acc_phase, p.error_flag, 16);
-                        tc_fence_after();
-                        if (quarter == 0 && it < 2) WTRACE(10 + 2 * it);   // accumulators of tile 0 / 1 complete
-                    }
+                for (int c = 0; c <= 8; ++c) eoff[c] = __shfl_sync(0xffffffffu, off_cur, (rq0 + c) & 15) - stream_base;
+                mbar_wait(&tail->tmem_full[acc], acc_phase, p.error_flag, 16);
+                tc_fence_after();
+                if (quarter == 0 && it < 2) WTRACE(10 + 2 * it);   // accumulators of tile 0 / 1 complete
 #pragma unroll
-                    for (int j = 0; j < kWWords; ++j) {
-                        const uint32_t e0 = eoff[j], e1 = eoff[j + 1];
-                        if (e0 == e1 || (p.debug & 4u)) continue;
-                        uint32_t v[32];
-                        const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + (acc * SGP + sg) * kWCols + j * 32u;
-                        asm volatile(
-                            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                            : "r"(taddr));
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        uint4* srow = reinterpret_cast<uint4*>(stg + lane * kWEpiRowWords);
+                for (int c = 0; c < 8; ++c) {
+                    if ((uint32_t)c >= nch) break;
+                    const uint32_t e0 = eoff[c], e1 = eoff[c + 1];
+                    if (e0 == e1 || (p.debug & 4u)) continue;
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * (SGP * kWSubRows) + c * 32u;
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    // staging image [column = lane][row]: thread writes the 32 rows of its column
+                    uint4* srow = reinterpret_cast<uint4*>(stg + lane * kWEpiRowWords);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) srow[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                        __syncwarp();
-                        // the chunk's entries, page by page, four passes of 32 entries at a time
-                        for (uint32_t e = e0; e < e1;) {
-                            const uint32_t pg = e / kWListPage;
-                            ensure_page(pg);
-                            const uint32_t pend = (pg + 1) * kWListPage;
-                            const uint32_t seg_end = e1 < pend ? e1 : pend;
-                            const uint2* lent = lpage + (pg & 1u) * kWListPage - (size_t)pg * kWListPage;   // lent[e] = entry e of the stream
-                            for (uint32_t eb = e; eb < seg_end; eb += 128) {
-                                uint2 en[4];
-                                float val[4];
+                    for (int i = 0; i < 8; ++i) srow[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    __syncwarp();
+                    // the chunk's entries, page by page, four groups of 32 entries at a time
+                    for (uint32_t e = e0; e < e1;) {
+                        const uint32_t pg = e / kWListPage;
+                        ensure_page(pg);
+                        const uint32_t pend = (pg + 1) * kWListPage;
+                        const uint32_t seg_end = e1 < pend ? e1 : pend;
+                        const uint2* lent = lpage + (pg & 1u) * kWListPage - (size_t)pg * kWListPage;   // lent[e] = entry e of the stream
+                        for (uint32_t eb = e; eb < seg_end; eb += 128) {
+                            uint2 en[4];
+                            float val[4];
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const uint32_t ee = eb + q * 32 + lane;
-                                    en[q] = lent[ee < seg_end ? ee : e];
-                                }
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) val[q] = *reinterpret_cast<const float*>(stg_bytes + en[q].x);
-#pragma unroll
-                                for (int q = 0; q < 4; ++q)
-                                    if (eb + q * 32 + lane < seg_end) p.P[en[q].y] = val[q];
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t ee = eb + q * 32 + lane;
+                                en[q] = lent[ee < seg_end ? ee : e];
                             }
-                            e = seg_end;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) val[q] = *reinterpret_cast<const float*>(stg_bytes + en[q].x);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (eb + q * 32 + lane < seg_end) p.P[en[q].y] = val[q];
                         }
-                        __syncwarp();
+                        e = seg_end;
                     }
-                    if (sg + 1 == SGP) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
-                        if (quarter == 0 && it < 2) WTRACE(11 + 2 * it);   // epilogue of tile 0 / 1 done
-                    }
+                    __syncwarp();
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
+                if (quarter == 0 && it < 2) WTRACE(11 + 2 * it);   // epilogue of tile 0 / 1 done
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
