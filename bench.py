@@ -194,7 +194,10 @@ def main():
     plan = pkg.Plan(ctx, M, N, ro, ci)
     t0 = time.perf_counter()
     plan.reorder(ALPHA, DELTA)                     # block_size from calculateBlockSize, reference_compat reduction
-    reorder_wall_ms = (time.perf_counter() - t0) * 1e3
+    reorder_wall_ms = (time.perf_counter() - t0) * 1e3          # first call of the process: module load + allocations
+    t0 = time.perf_counter()
+    plan.reorder(ALPHA, DELTA)
+    reorder_warm_ms = (time.perf_counter() - t0) * 1e3          # scratch arena and plan buffers in place
     info = plan.info()
     shard_nnz = nnz
     if world > 1:
@@ -258,11 +261,23 @@ def main():
     # back-to-back, L2-resident figure (diagnostic: what the reference's own timing loop measures)
     hot_ms = plan.sddmm(K, dA, dB, dP, iterations=100)
 
-    # ---- e2e: host buffers through the C ABI (H2D A,B + kernels + D2H P inside the call) ----------
+    # ---- e2e: host buffers through the C ABI (H2D A,B + kernels + D2H P inside every step) -------
+    # (1) latency: one blocking bsmr_sddmm_host call per step; (2) throughput (the reported e2e value): the same
+    # per-step work through bsmr_sddmm_host_submit / _wait, two steps in flight, so the copy-in of step i+1 and the
+    # copy-out of step i-1 overlap the kernels of step i.  Every step copies its own A, B in and its own P out.
     hA = torch.from_numpy(A).pin_memory()
     hB = torch.from_numpy(B).pin_memory()
-    hP = torch.zeros(nnz, dtype=torch.float32).pin_memory()
+    hPs = [torch.zeros(nnz, dtype=torch.float32).pin_memory() for _ in range(2)]
+    hP = hPs[0]
+    dPfull = torch.empty(nnz, dtype=torch.float32, device="cuda") if world > 1 else None
     e2e_steps = max(3, min(args.steps, 20))
+
+    def assemble(buf):
+        # N > 1: P is assembled on every rank; the shards are disjoint index sets of the CSR value array
+        dPfull.copy_(buf, non_blocking=True)
+        dist.all_reduce(dPfull)
+        buf.copy_(dPfull, non_blocking=False)
+
     for _ in range(2):
         plan.sddmm_host(K, hA, hB, hP)
     barrier()
@@ -270,17 +285,33 @@ def main():
     for _ in range(e2e_steps):
         plan.sddmm_host(K, hA, hB, hP)
         if world > 1:
-            # assemble P on every rank: the shards are disjoint index sets of the CSR value array
-            dPfull = torch.from_numpy(hP.numpy()).cuda(non_blocking=True)
-            dist.all_reduce(dPfull)
-            hP.copy_(dPfull, non_blocking=False)
+            assemble(hP)
+    barrier()
+    e2e_serial_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+
+    def pipelined(n):
+        tickets = []
+        for i in range(n):
+            tickets.append(plan.sddmm_host_submit(K, hA, hB, hPs[i % 2]))
+            if world > 1 and i >= 1:
+                plan.sddmm_host_wait(tickets[i - 1])
+                assemble(hPs[(i - 1) % 2])
+        plan.sddmm_host_wait()
+        if world > 1:
+            assemble(hPs[(n - 1) % 2])
+
+    pipelined(4)
+    barrier()
+    t0 = time.perf_counter()
+    pipelined(e2e_steps)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([e2e_ms, e2e_serial_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+    e2e_ms, e2e_serial_ms = float(t[0].item()), float(t[1].item())
     e2e_value = 2.0 * nnz * K / (e2e_ms * 1e-3) / 1e9
+    hP = hPs[(e2e_steps - 1) % 2]
 
     if rank != 0:
         if world > 1:
@@ -365,12 +396,17 @@ def main():
             "config": workload_config(M, N, nnz, K, source, world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int((M + N) * K * 4), "d2h_bytes_per_step": int(nnz * 4)},
+                    "h2d_bytes_per_step": int((M + N) * K * 4), "d2h_bytes_per_step": int(nnz * 4),
+                    "how": "bsmr_sddmm_host_submit/_wait, pinned host buffers, 2 steps in flight (copies of "
+                           "neighbouring steps overlap the kernels); %d steps" % e2e_steps,
+                    "blocking_call_ms": e2e_serial_ms,
+                    "blocking_call_value": 2.0 * nnz * K / (e2e_serial_ms * 1e-3) / 1e9},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "reorder": {"row_ms": info["row_reordering_ms"], "col_ms": info["col_reordering_ms"],
-                        "format_ms": info["format_build_ms"], "wall_ms": reorder_wall_ms,
+                        "format_ms": info["format_build_ms"], "wall_ms": reorder_warm_ms,
+                        "first_call_wall_ms": reorder_wall_ms,
                         "block_size": info["block_size"], "clusters": info["num_clusters_true"],
                         "dense_nnz": int(info["num_dense_values"]), "residual_nnz": int(info["num_sparse_values"]),
                         "dense_tiles": info["num_dense_tiles"],
@@ -379,7 +415,7 @@ def main():
                                  "block_tiles": info["num_block_tiles"], "block_nnz": int(info["num_block_values"]),
                                  "residual_nnz_outside_wide": int(info["num_residual_values"]),
                                  "wide_format_ms": info["wide_format_ms"]},
-                        "gflops_incl_reorder": 2.0 * nnz * K / ((ms_per_step + reorder_wall_ms) * 1e-3) / 1e9},
+                        "gflops_incl_reorder": 2.0 * nnz * K / ((ms_per_step + reorder_warm_ms) * 1e-3) / 1e9},
             "kernels": {"wide_ms_cold": wide_ms, "dense_ms_cold": dense_ms, "residual_ms_cold": res_ms, "step_ms_hot_l2": hot_ms,
                         "gflops_hot_l2": 2.0 * shard_nnz * K / (hot_ms * 1e-3) / 1e9}}
     print(json.dumps(line), flush=True)

@@ -25,6 +25,7 @@ NULL_VALUE = 0xFFFFFFFF
 
 ROW_REFERENCE_COMPAT, ROW_EXACT_REDUCE, ROW_IDENTITY = 0, 1, 2
 SDDMM_DEFAULT, SDDMM_RESIDUAL_ONLY, SDDMM_NO_REORDER, SDDMM_NO_WIDE = 0, 1, 2, 4
+TICKET_ALL = 0xFFFFFFFFFFFFFFFF
 WIDE_GROUP_ROWS, WIDE_TILE_COLS = 256, 128
 
 VEC = dict(reordered_rows=0, dense_cols=1, dense_col_offsets=2, sparse_cols=3, sparse_col_offsets=4,
@@ -100,6 +101,10 @@ def lib():
         L.bsmr_plan_set_shard.argtypes = [vp, C.c_uint32, C.c_uint32, u32p, u32p, C.POINTER(C.c_uint64)]
         L.bsmr_sddmm.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_int, C.c_uint32, f32p]
         L.bsmr_sddmm_host.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_int, C.c_uint32, f32p, f32p]
+        L.bsmr_sddmm_host_submit.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_uint32, C.POINTER(C.c_uint64)]
+        L.bsmr_sddmm_host_wait.argtypes = [vp, C.c_uint64]
+        L.bsmr_sddmm_batch.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint32, f32p]
+        L.bsmr_sddmm_host_batch.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint32, f32p]
         L.bsmr_sddmm_profile.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_uint32, f32p, f32p]
         L.bsmr_sddmm_profile3.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_uint32, f32p, f32p, f32p]
         L.bsmr_plan_set_wide_ratio.argtypes = [vp, C.c_float]
@@ -110,6 +115,7 @@ def lib():
                      "bsmr_plan_row_reorder", "bsmr_plan_set_row_order", "bsmr_plan_col_reorder", "bsmr_plan_reorder",
                      "bsmr_plan_vector_size", "bsmr_plan_vector_copy", "bsmr_plan_get_info", "bsmr_plan_set_shard",
                      "bsmr_sddmm", "bsmr_sddmm_host", "bsmr_sddmm_profile", "bsmr_sddmm_profile3",
+                     "bsmr_sddmm_host_submit", "bsmr_sddmm_host_wait", "bsmr_sddmm_batch", "bsmr_sddmm_host_batch",
                      "bsmr_plan_set_wide_ratio", "bsmr_plan_evaluate"):
             getattr(L, name).restype = C.c_int
         _lib = L
@@ -264,6 +270,27 @@ class Plan:
         _check(lib().bsmr_sddmm_host(self._h, K, _ptr(hA), _ptr(hB), _ptr(hP), iterations, flags, C.byref(ms),
                                      C.byref(tot)))
         return hP, ms.value, tot.value
+
+    def sddmm_host_submit(self, K, hA, hB, hP, flags=SDDMM_DEFAULT):
+        """Pipelined host-data call (pinned host buffers): queues H2D -> kernels -> D2H and returns a ticket."""
+        t = C.c_uint64(0)
+        _check(lib().bsmr_sddmm_host_submit(self._h, K, _ptr(hA), _ptr(hB), _ptr(hP), flags, C.byref(t)))
+        return t.value
+
+    def sddmm_host_wait(self, ticket=TICKET_ALL):
+        _check(lib().bsmr_sddmm_host_wait(self._h, ticket))
+
+    def sddmm_batch(self, num_batch, K, dA, dB, dP, flags=SDDMM_DEFAULT, timed=True):
+        """sddmm_gpu_batch: device pointers, batch b at dA + b*M*K, dB + b*N*K, dP + b*nnz.  Returns total ms."""
+        ms = C.c_float(0)
+        _check(lib().bsmr_sddmm_batch(self._h, num_batch, K, _ptr(dA), _ptr(dB), _ptr(dP), flags, C.byref(ms) if timed else None))
+        return ms.value
+
+    def sddmm_host_batch(self, num_batch, K, hA, hB, hP, flags=SDDMM_DEFAULT):
+        """The batch with host buffers, pipelined over the batch elements.  Returns wall ms."""
+        ms = C.c_float(0)
+        _check(lib().bsmr_sddmm_host_batch(self._h, num_batch, K, _ptr(hA), _ptr(hB), _ptr(hP), flags, C.byref(ms)))
+        return ms.value
 
 
 from . import synth  # noqa: E402,F401  (seeded synthetic inputs: numpy only)

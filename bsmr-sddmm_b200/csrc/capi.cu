@@ -2,6 +2,7 @@
 // Host-side orchestration only; kernels live in residual.cu / dense_tc.cu / colreorder.cu /
 // rowreorder.cu.  Nothing here falls back to the CPU: without a device every call fails.
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 
 #include "common.cuh"
@@ -111,6 +112,8 @@ int bsmr_ctx_destroy(bsmr_ctx* ctx) {
     if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
     if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     if (ctx->side_stream2) cudaStreamDestroy(ctx->side_stream2);
+    if (ctx->copy_in_stream) cudaStreamDestroy(ctx->copy_in_stream);
+    if (ctx->copy_out_stream) cudaStreamDestroy(ctx->copy_out_stream);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return BSMR_OK;
@@ -196,6 +199,8 @@ int bsmr_plan_create(bsmr_ctx* ctx, uint32_t M, uint32_t N, uint32_t nnz, const 
 int bsmr_plan_destroy(bsmr_plan* plan) {
     if (!plan) return BSMR_OK;
     cudaSetDevice(plan->ctx->device);
+    for (bsmr_plan::HostSlot& s : plan->host_slots)       // pipelined host-data calls still in flight use the plan's buffers
+        if (s.in_flight) cudaEventSynchronize(s.d2h_done);
     delete plan;
     return BSMR_OK;
 }
@@ -680,6 +685,127 @@ int bsmr_sddmm_host(bsmr_plan* plan, uint32_t K, const float* hA, const float* h
     if (ms_per_iteration) *ms_per_iteration = ms;
     if (total_ms) *total_ms = tot;
     return s;
+}
+
+// ---- pipelined host-data SDDMM --------------------------------------------------------------------------------
+// A call = H2D A,B -> zero P -> kernels -> D2H P, exactly what bsmr_sddmm_host does, but the three phases run on
+// three streams (copy-in, the context's stream, copy-out) and successive calls alternate between two slots of device
+// buffers: while call i computes, call i + 1 copies in and call i - 1 copies out (PCIe is full duplex, the copy
+// engines run next to the SMs).  Ordering is carried by the slot's events only; the host blocks only in _wait.
+static int ensure_host_pipeline(bsmr_plan* plan) {
+    bsmr_ctx* ctx = plan->ctx;
+    if (!ctx->copy_in_stream) BSMR_CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_in_stream, cudaStreamNonBlocking));
+    if (!ctx->copy_out_stream) BSMR_CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_out_stream, cudaStreamNonBlocking));
+    for (bsmr_plan::HostSlot& s : plan->host_slots) {
+        if (!s.h2d_done) BSMR_CUDA_OK(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+        if (!s.compute_done) BSMR_CUDA_OK(cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming));
+        if (!s.d2h_done) BSMR_CUDA_OK(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
+    }
+    return BSMR_OK;
+}
+
+int bsmr_sddmm_host_submit(bsmr_plan* plan, uint32_t K, const float* hA, const float* hB, float* hP, uint32_t flags,
+                           uint64_t* ticket) {
+    if (!plan || !hA || !hB || (plan->nnz && !hP) || K == 0) {
+        set_error("bsmr_sddmm_host_submit: NULL pointer or K == 0");
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    if (!(flags & BSMR_SDDMM_NO_REORDER) && !plan->have_format) {
+        set_error("bsmr_sddmm_host_submit: the plan has no reorder/format yet (call bsmr_plan_reorder)");
+        return BSMR_ERR_BAD_STATE;
+    }
+    bsmr_ctx* ctx = plan->ctx;
+    BSMR_CUDA_OK(cudaSetDevice(ctx->device));
+    BSMR_TRY(ensure_host_pipeline(plan));
+    const uint64_t id = plan->host_submits;
+    bsmr_plan::HostSlot& s = plan->host_slots[id % bsmr_plan::kHostSlots];
+    const size_t na = static_cast<size_t>(plan->M) * K, nb = static_cast<size_t>(plan->N) * K;
+    if (s.in_flight && (na > s.dA.capacity || nb > s.dB.capacity || plan->nnz > s.dP.capacity))
+        BSMR_CUDA_OK(cudaEventSynchronize(s.d2h_done));      // the buffers are about to be reallocated
+    BSMR_TRY(s.dA.alloc(na));
+    BSMR_TRY(s.dB.alloc(nb));
+    BSMR_TRY(s.dP.alloc(plan->nnz));
+    // copy-in: the slot's previous kernels must be done with dA / dB
+    if (s.in_flight) BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->copy_in_stream, s.compute_done, 0));
+    BSMR_CUDA_OK(cudaMemcpyAsync(s.dA.ptr, hA, na * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in_stream));
+    BSMR_CUDA_OK(cudaMemcpyAsync(s.dB.ptr, hB, nb * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in_stream));
+    BSMR_CUDA_OK(cudaEventRecord(s.h2d_done, ctx->copy_in_stream));
+    // kernels: after the copy-in, and after the slot's previous copy-out has read dP
+    BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->stream, s.h2d_done, 0));
+    if (s.in_flight) BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->stream, s.d2h_done, 0));
+    if (plan->nnz) BSMR_CUDA_OK(cudaMemsetAsync(s.dP.ptr, 0, s.dP.bytes(), ctx->stream));   // src/sddmmKernel.cu:2525
+    BSMR_TRY(bsmr_sddmm(plan, K, s.dA.ptr, s.dB.ptr, s.dP.ptr, 1, flags, nullptr));
+    BSMR_CUDA_OK(cudaEventRecord(s.compute_done, ctx->stream));
+    // copy-out
+    BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->copy_out_stream, s.compute_done, 0));
+    if (plan->nnz) BSMR_CUDA_OK(cudaMemcpyAsync(hP, s.dP.ptr, s.dP.bytes(), cudaMemcpyDeviceToHost, ctx->copy_out_stream));
+    BSMR_CUDA_OK(cudaEventRecord(s.d2h_done, ctx->copy_out_stream));
+    s.in_flight = true;
+    plan->host_submits = id + 1;
+    if (ticket) *ticket = id;
+    return BSMR_OK;
+}
+
+int bsmr_sddmm_host_wait(bsmr_plan* plan, uint64_t ticket) {
+    if (!plan) return BSMR_ERR_INVALID_ARGUMENT;
+    BSMR_CUDA_OK(cudaSetDevice(plan->ctx->device));
+    if (ticket == BSMR_TICKET_ALL) {
+        for (bsmr_plan::HostSlot& s : plan->host_slots)
+            if (s.in_flight) BSMR_CUDA_OK(cudaEventSynchronize(s.d2h_done));
+        return BSMR_OK;
+    }
+    if (ticket >= plan->host_submits) {
+        set_error("bsmr_sddmm_host_wait: ticket %llu was never issued", (unsigned long long)ticket);
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    // a ticket older than the slot's latest call completed before that call's kernels started
+    bsmr_plan::HostSlot& s = plan->host_slots[ticket % bsmr_plan::kHostSlots];
+    if (s.in_flight) BSMR_CUDA_OK(cudaEventSynchronize(s.d2h_done));
+    return BSMR_OK;
+}
+
+// sddmm_gpu_batch (include/sddmmKernel.cuh:41-47, src/sddmmKernel.cu:2764-2848): numBatch (A, B, P) triples on one
+// pattern, batch b at A + b*M*K, B + b*N*K, P + b*nnz.  The reference folds the batch into gridDim.z of its two
+// kernels; here every batch element is one pass of the plan's kernels, issued back to back (asynchronously) on the
+// context's streams.
+int bsmr_sddmm_batch(bsmr_plan* plan, uint32_t num_batch, uint32_t K, const float* dA, const float* dB, float* dP,
+                     uint32_t flags, float* total_ms) {
+    if (!plan || !dA || !dB || (plan->nnz && !dP) || K == 0) {
+        set_error("bsmr_sddmm_batch: NULL pointer or K == 0");
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    bsmr_ctx* ctx = plan->ctx;
+    BSMR_CUDA_OK(cudaSetDevice(ctx->device));
+    if (total_ms) {
+        *total_ms = 0.f;
+        BSMR_CUDA_OK(cudaEventRecord(ctx->ev0, ctx->stream));
+    }
+    const size_t sa = static_cast<size_t>(plan->M) * K, sb = static_cast<size_t>(plan->N) * K;
+    for (uint32_t b = 0; b < num_batch; ++b)
+        BSMR_TRY(bsmr_sddmm(plan, K, dA + b * sa, dB + b * sb, dP + static_cast<size_t>(b) * plan->nnz, 1, flags, nullptr));
+    if (total_ms) {
+        BSMR_CUDA_OK(cudaEventRecord(ctx->ev1, ctx->stream));
+        BSMR_CUDA_OK(cudaEventSynchronize(ctx->ev1));
+        BSMR_CUDA_OK(cudaEventElapsedTime(total_ms, ctx->ev0, ctx->ev1));
+    }
+    return BSMR_OK;
+}
+
+// The batch with host data: one pipelined host-data call per batch element (copy-in of element b + 1 and copy-out of
+// element b - 1 overlap the kernels of element b); returns when every P has landed.
+int bsmr_sddmm_host_batch(bsmr_plan* plan, uint32_t num_batch, uint32_t K, const float* hA, const float* hB, float* hP,
+                          uint32_t flags, float* total_ms) {
+    if (!plan || !hA || !hB || (plan->nnz && !hP) || K == 0) {
+        set_error("bsmr_sddmm_host_batch: NULL pointer or K == 0");
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    const size_t sa = static_cast<size_t>(plan->M) * K, sb = static_cast<size_t>(plan->N) * K;
+    for (uint32_t b = 0; b < num_batch; ++b)
+        BSMR_TRY(bsmr_sddmm_host_submit(plan, K, hA + b * sa, hB + b * sb, hP + static_cast<size_t>(b) * plan->nnz, flags, nullptr));
+    BSMR_TRY(bsmr_sddmm_host_wait(plan, BSMR_TICKET_ALL));
+    if (total_ms) *total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return BSMR_OK;
 }
 
 }  // extern "C"

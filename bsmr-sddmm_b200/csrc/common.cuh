@@ -157,6 +157,8 @@ struct bsmr_ctx {
     // (the reference also uses one stream per kernel, src/sddmmKernel.cu:2555-2559)
     cudaStream_t side_stream = nullptr, side_stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+    // copy engines' streams of the pipelined host-data path (created on first use)
+    cudaStream_t copy_in_stream = nullptr, copy_out_stream = nullptr;
     // tensor-map encoder resolved at runtime (no link-time dependency on libcuda)
     void* encode_tiled = nullptr;
     bsmr::Workspace ws;     // scratch of the reorder passes
@@ -247,6 +249,24 @@ struct bsmr_plan {
 
     // scratch for the host-data overload
     bsmr::DevBuf<float> dA, dB, dP;
+    // pipelined host-data calls (bsmr_sddmm_host_submit / _wait): two slots of device buffers; the copy-in of call
+    // i + 1 (copy-in stream), the kernels of call i (context stream) and the copy-out of call i - 1 (copy-out stream)
+    // run concurrently, ordered by the slots' events
+    struct HostSlot {
+        bsmr::DevBuf<float> dA, dB, dP;
+        cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
+        bool in_flight = false;
+    };
+    static constexpr int kHostSlots = 2;
+    HostSlot host_slots[kHostSlots];
+    uint64_t host_submits = 0;
+    ~bsmr_plan() {
+        for (HostSlot& s : host_slots) {
+            if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+            if (s.compute_done) cudaEventDestroy(s.compute_done);
+            if (s.d2h_done) cudaEventDestroy(s.d2h_done);
+        }
+    }
 };
 
 namespace bsmr {

@@ -4,6 +4,8 @@
 
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace bsmr {
@@ -105,7 +107,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // 2-D fp32 tensor [rows x K] with K contiguous; box = 32 floats of one row; SWIZZLE_128B.
-inline int make_row_gather_map(bsmr_ctx* ctx, const float* base, uint64_t rows, uint64_t K, CUtensorMap* out) {
+// tf32_rounding: the tensor map carries CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 and the TMA unit rounds every fp32 element to
+// TF32 (to nearest) on its way into shared memory -- measured on B200 against cvt.rna.tf32.f32 in a converter pass: same
+// maximum error (1.4e-4 at K = 128), mean signed error -3e-7 (tests/tf32_probe.py); with a FLOAT32 map the tensor core
+// truncates (mean -6.5e-4).
+inline int make_row_gather_map(bsmr_ctx* ctx, const float* base, uint64_t rows, uint64_t K, CUtensorMap* out, bool tf32_rounding = false) {
     if (!ctx->encode_tiled) {
         set_error("cuTensorMapEncodeTiled is not available from this driver");
         return BSMR_ERR_UNSUPPORTED;
@@ -114,8 +120,10 @@ inline int make_row_gather_map(bsmr_ctx* ctx, const float* base, uint64_t rows, 
     const cuuint64_t strides[1] = {K * sizeof(float)};
     const cuuint32_t box[2] = {32, 1};
     const cuuint32_t estr[2] = {1, 1};
+    static const bool tf32_env = std::getenv("BSMR_TMA_TF32") != nullptr;
+    const bool tf32_map = tf32_rounding || tf32_env;
     CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
-        out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+        out, tf32_map ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {

@@ -49,10 +49,8 @@ constexpr int kWRowQ = kWGroupRows / 32;              // 32-row quarters of a ro
 constexpr int kWProducerWarps = 8;                    // warps 0-7: TMA gather4 issue
 constexpr int kWEpiWarp0 = 8;                         // warps 8-11: epilogue, TMEM lane quarter = warp % 4
 constexpr int kWEpiWarps = 4;
-constexpr int kWConvWarp0 = 12;                       // warps 12-15: TF32 round-to-nearest converters
-constexpr int kWConvWarps = 4;
-constexpr int kWMmaWarp = 16;
-constexpr int kWThreads = 17 * 32;
+constexpr int kWMmaWarp = 12;
+constexpr int kWThreads = 13 * 32;
 constexpr int kWMaxStages = 8;
 constexpr int kWMaxKChunks = 8;                       // K <= 256
 constexpr int kWTmemCols = 512;
@@ -65,10 +63,8 @@ constexpr int kWListBytes = 2 * kWListPage * 8;                // two pages in s
 
 struct __align__(16) WideSmemTail {
     uint64_t b_full[kWMaxStages];    // TMA bytes of the stage landed
-    uint64_t b_ready[kWMaxStages];   // stage rounded to TF32 by the 4 converter warps
     uint64_t b_empty[kWMaxStages];   // the MMAs that read the stage have completed (tcgen05.commit)
     uint64_t a_full[kWMaxKChunks];   // A images of K-chunk kc landed
-    uint64_t a_ready[kWMaxKChunks];  // ... and rounded
     uint64_t a_free;                 // every MMA that reads the current A images has completed
     uint64_t tmem_full[kWMaxAccs];
     uint64_t tmem_empty[kWMaxAccs];  // the 4 epilogue warps have read the accumulator
@@ -104,24 +100,6 @@ __device__ __forceinline__ unsigned long long gtime() {
         if (p.trace && lane == 0) p.trace[(size_t)blockIdx.x * 32 + (slot)] = gtime();        \
     } while (0)
 
-// in-place cvt.rna.tf32.f32 of `n4` float4 per thread (128 converter threads, float4 #ci + 128 * j)
-template <int N4>
-__device__ __forceinline__ void round_image(uint8_t* img, uint32_t ci) {
-    float4* v4 = reinterpret_cast<float4*>(img);
-    float4 v[N4];
-#pragma unroll
-    for (int j = 0; j < N4; ++j) v[j] = v4[ci + 128 * j];
-#pragma unroll
-    for (int j = 0; j < N4; ++j) {
-        v[j].x = rna_tf32(v[j].x);
-        v[j].y = rna_tf32(v[j].y);
-        v[j].z = rna_tf32(v[j].z);
-        v[j].w = rna_tf32(v[j].w);
-    }
-#pragma unroll
-    for (int j = 0; j < N4; ++j) v4[ci + 128 * j] = v[j];
-}
-
 __global__ void __launch_bounds__(kWThreads, 1)
 wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const WideParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -144,12 +122,10 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (warp == 0 && lane == 0) {
         for (uint32_t s = 0; s < S; ++s) {
             mbar_init(&tail->b_full[s], 1);
-            mbar_init(&tail->b_ready[s], kWConvWarps);
             mbar_init(&tail->b_empty[s], 1);
         }
         for (uint32_t k = 0; k < KC; ++k) {
             mbar_init(&tail->a_full[k], 1);
-            mbar_init(&tail->a_ready[k], kWConvWarps);
         }
         mbar_init(&tail->a_free, 1);
         for (int a = 0; a < kWMaxAccs; ++a) {
@@ -241,40 +217,6 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 cols = cols_next;
             }
         }
-    } else if (warp >= kWConvWarp0 && warp < kWConvWarp0 + kWConvWarps) {
-        // ================= TF32 converters (warps 12..15) =================
-        // tcgen05 kind::tf32 ignores the low 13 mantissa bits (truncation); the reference rounds to nearest
-        // (wmma::__float_to_tf32, src/sddmmKernel.cu:317-322): every landed image is rounded in place with
-        // cvt.rna.tf32.f32 (element-wise, so the swizzle does not matter), then fence.proxy.async -> mbarrier.
-        const uint32_t ci = threadIdx.x - kWConvWarp0 * 32;   // 0..127
-        uint32_t stage = 0, phase = 0, a_idx = 0, cur_key = kNoCol;
-        for (uint32_t pass = 0; pass < passes; ++pass) {
-            for (uint32_t t = my_begin; t < my_end; ++t) {
-                const uint32_t key = __ldg(p.tile_meta + t).x * 2 + pass;
-                const bool new_key = key != cur_key;
-                for (uint32_t kc = 0; kc < KC; ++kc) {
-                    if (new_key) {
-                        mbar_wait<false>(&tail->a_full[kc], a_idx & 1, p.error_flag, 17);
-                        for (uint32_t sg = 0; sg < SGP; ++sg) round_image<8>(a_img + ((size_t)kc * SGP + sg) * kWAImgBytes, ci);
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tail->a_ready[kc]);
-                    }
-                    mbar_wait<false>(&tail->b_full[stage], phase, p.error_flag, 18);
-                    if (!(p.debug & 8u)) round_image<8>(b_ring + (size_t)stage * kWBStageBytes, ci);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tail->b_ready[stage]);
-                    if (++stage == S) { stage = 0; phase ^= 1; }
-                }
-                if (new_key) {
-                    cur_key = key;
-                    ++a_idx;
-                    if (warp == kWConvWarp0) WTRACE(2);        // A images rounded
-                }
-            }
-        }
-        if (warp == kWConvWarp0) WTRACE(7);                    // converters done
     } else if (warp == kWMmaWarp) {
         // ================= MMA issuer =================
         uint32_t stage = 0, phase = 0, it = 0, a_idx = 0, cur_key = kNoCol;
@@ -294,8 +236,8 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * (SGP * kWSubRows);
                 for (uint32_t kc = 0; kc < KC; ++kc) {
-                    if (new_key) mbar_wait<false>(&tail->a_ready[kc], a_idx & 1, p.error_flag, 14);
-                    mbar_wait<false>(&tail->b_ready[stage], phase, p.error_flag, 15);
+                    if (new_key) mbar_wait<false>(&tail->a_full[kc], a_idx & 1, p.error_flag, 14);
+                    mbar_wait<false>(&tail->b_full[stage], phase, p.error_flag, 15);
                     tc_fence_after();
                     if (lane == 0) {
                         const uint64_t da = make_smem_desc(smem_u32(b_ring + (size_t)stage * kWBStageBytes));
@@ -537,8 +479,9 @@ int launch_wide(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, f
         BSMR_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     }
     CUtensorMap map_a, map_b;
-    BSMR_TRY(make_row_gather_map(ctx, dA, plan->M, K, &map_a));
-    BSMR_TRY(make_row_gather_map(ctx, dB, plan->N, K, &map_b));
+    static const bool fp32_maps = std::getenv("BSMR_WIDE_FP32_MAPS") != nullptr;   // experiment: truncating operands
+    BSMR_TRY(make_row_gather_map(ctx, dA, plan->M, K, &map_a, !fp32_maps));
+    BSMR_TRY(make_row_gather_map(ctx, dB, plan->N, K, &map_b, !fp32_maps));
     WideParams p{};
     p.K = K; p.kchunks = kchunks; p.stages = stages; p.sgp = sgp;
     p.num_rows = static_cast<uint32_t>(plan->h_reordered_rows.size());

@@ -183,6 +183,28 @@ int bsmr_sddmm(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, fl
 int bsmr_sddmm_host(bsmr_plan* plan, uint32_t K, const float* hA, const float* hB, float* hP,
                     int iterations, uint32_t flags, float* ms_per_iteration, float* total_ms);
 
+/* Pipelined form of the host-data overload: the same H2D A,B -> zero P -> kernels -> D2H P, but the call returns as
+ * soon as the work is queued.  Successive calls alternate between two slots of device buffers and three streams
+ * (copy-in, the context's stream, copy-out), so the copy-in of call i+1 and the copy-out of call i-1 overlap the
+ * kernels of call i.  hA / hB must stay valid and hP must not be read until bsmr_sddmm_host_wait(plan, ticket)
+ * returns (BSMR_TICKET_ALL: every call submitted so far); pinned host memory is needed for the copies to be
+ * asynchronous.  One caller thread per plan, as everywhere in this ABI.                                    */
+#define BSMR_TICKET_ALL 0xFFFFFFFFFFFFFFFFull
+int bsmr_sddmm_host_submit(bsmr_plan* plan, uint32_t K, const float* hA, const float* hB, float* hP,
+                           uint32_t flags, uint64_t* ticket);
+int bsmr_sddmm_host_wait(bsmr_plan* plan, uint64_t ticket);
+
+/* sddmm_gpu_batch(numBatch, M, N, K, nnz, dA, dB, rphm, dP, time) (include/sddmmKernel.cuh:41-47,
+ * src/sddmmKernel.cu:2764-2848): num_batch (A, B, P) triples on the plan's pattern, device pointers, batch b at
+ * dA + b*M*K (row-major M x K), dB + b*N*K (column-major K x N) and dP + b*nnz (CSR order).  total_ms (may be NULL:
+ * then the call is asynchronous on the context's stream) = Logger-style total time of the batch.           */
+int bsmr_sddmm_batch(bsmr_plan* plan, uint32_t num_batch, uint32_t K, const float* dA, const float* dB, float* dP,
+                     uint32_t flags, float* total_ms);
+/* The batch with host buffers (same strides): one pipelined host-data call per batch element; returns when
+ * every P has landed.  total_ms (may be NULL) = wall time of the call.                                      */
+int bsmr_sddmm_host_batch(bsmr_plan* plan, uint32_t num_batch, uint32_t K, const float* hA, const float* hB, float* hP,
+                          uint32_t flags, float* total_ms);
+
 /* One pass with the two kernels timed separately (CUDA events on the context's stream):
  * what bench.py's roofline block reports per kernel.  Either output may be NULL.          */
 int bsmr_sddmm_profile(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP,

@@ -290,6 +290,53 @@ def test_sddmm_host_overload(pkg, ctx, oracle):
     assert oracle.check_data(oracle.sddmm_cpu(M, N, K, A, B, ro, ci), P) == 0
 
 
+def test_sddmm_host_pipelined_submit_wait(pkg, ctx, oracle):
+    """bsmr_sddmm_host_submit / _wait: five calls in flight over two slots, each with its own A, B and P (pinned)."""
+    import torch
+    M, N, ro, ci = pkg.synth.block_structured(1000, 2000, seed=11, groups=12, cols_per_group=64)
+    K = 128
+    plan = pkg.Plan(ctx, M, N, ro, ci)
+    plan.reorder(0.3, 0.3, block_size=16)
+    rng = np.random.default_rng(3)
+    calls = []
+    for i in range(5):
+        A = (rng.random((M, K), dtype=np.float32) * 2.0).astype(np.float32)
+        B = (rng.random((N, K), dtype=np.float32) * 2.0).astype(np.float32)
+        hA, hB = torch.from_numpy(A).pin_memory(), torch.from_numpy(B).pin_memory()
+        hP = torch.full((len(ci),), -3.0).pin_memory()
+        calls.append((A, B, hA, hB, hP, plan.sddmm_host_submit(K, hA, hB, hP)))
+    assert [c[5] for c in calls] == list(range(5))
+    plan.sddmm_host_wait(calls[1][5])
+    assert oracle.check_data(oracle.sddmm_cpu(M, N, K, calls[1][0], calls[1][1], ro, ci), calls[1][4].numpy()) == 0
+    plan.sddmm_host_wait()
+    for A, B, _, _, hP, _ in calls:
+        assert oracle.check_data(oracle.sddmm_cpu(M, N, K, A, B, ro, ci), hP.numpy()) == 0
+    with pytest.raises(pkg.BsmrError):
+        plan.sddmm_host_wait(99)
+
+
+@pytest.mark.parametrize("host", [False, True])
+def test_sddmm_batch(pkg, ctx, oracle, host):
+    """sddmm_gpu_batch (src/sddmmKernel.cu:2764-2848): numBatch (A, B, P) triples strided by M*K, N*K, nnz."""
+    import torch
+    M, N, ro, ci = pkg.synth.dlmc_mask(0.90, n=512, seed=4)
+    K, nb = 64, 3
+    plan = pkg.Plan(ctx, M, N, ro, ci)
+    plan.reorder(0.3, 0.3, block_size=16)
+    rng = np.random.default_rng(5)
+    A = (rng.random((nb, M, K), dtype=np.float32) * 2.0).astype(np.float32)
+    B = (rng.random((nb, N, K), dtype=np.float32) * 2.0).astype(np.float32)
+    if host:
+        P = np.full((nb, len(ci)), -1.0, dtype=np.float32)
+        assert plan.sddmm_host_batch(nb, K, A, B, P) > 0
+    else:
+        dP = torch.full((nb, len(ci)), -1.0, device="cuda")
+        assert plan.sddmm_batch(nb, K, torch_dev(A), torch_dev(B), dP) > 0
+        P = dP.cpu().numpy()
+    for b in range(nb):
+        assert oracle.check_data(oracle.sddmm_cpu(M, N, K, A[b], B[b], ro, ci), P[b]) == 0
+
+
 def test_sddmm_linearity_and_idempotence(pkg, ctx):
     """Size-independent properties: SDDMM is linear in A and repeated calls give identical bits."""
     import torch
