@@ -11,11 +11,30 @@ namespace bsmr {
 
 static thread_local char g_error[512] = "";
 
+// Error code of the tcgen05 kernels' bounded mbarrier waits: one word of mapped pinned host memory, so that the code
+// written just before __trap() can still be read after the context has gone into its sticky error state.
+static uint32_t* g_flag_host = nullptr;
+static uint32_t* g_flag_dev = nullptr;
+uint32_t* kernel_error_flag() {
+    if (!g_flag_dev) {
+        void* h = nullptr;
+        if (cudaHostAlloc(&h, sizeof(uint32_t), cudaHostAllocMapped) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+        g_flag_host = static_cast<uint32_t*>(h);
+        *g_flag_host = 0;
+        void* d = nullptr;
+        if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+        g_flag_dev = static_cast<uint32_t*>(d);
+    }
+    return g_flag_dev;
+}
+
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
-    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    int n = vsnprintf(g_error, sizeof(g_error), fmt, ap);
     va_end(ap);
+    if (g_flag_host && *g_flag_host != 0 && n >= 0 && n < (int)sizeof(g_error) - 64)
+        snprintf(g_error + n, sizeof(g_error) - n, " [kernel wait code %u: a pipeline barrier timed out]", *g_flag_host);
 }
 const char* get_error() { return g_error; }
 

@@ -325,31 +325,36 @@ __global__ void wide_subblock_count_kernel(uint32_t num_sb, const uint32_t* __re
     }
 }
 
-// The wide kernel computes the TRANSPOSED tile (lanes = the tile's 128 columns, TMEM columns = the group's 256 rows), so
-// an epilogue warp owns 32 tile columns (TMEM lane quarter j) and walks the 8 row quarters of the group.  Unit = (tile,
-// column quarter j): kWQ sub-blocks of 32 rows x 32 columns.  The lists are laid out by (j, tile): everything one
-// epilogue warp consumes while it walks a range of tiles is one contiguous stream (it pages through it with cp.async).
-__host__ __device__ inline uint64_t wide_unit_stream_index(uint64_t t, uint32_t j, uint32_t wtiles) { return (uint64_t)j * wtiles + t; }
+// The wide kernel computes the TRANSPOSED tile (lanes = the tile's 128 columns, TMEM columns = the group's 256 rows).  An
+// epilogue warp owns 32 tile columns (TMEM lane quarter j) and one half h of the group's rows (4 row quarters).
+// Unit u = (tile * kWW + j) * 2 + h: kWUQ sub-blocks of 32 rows x 32 columns.  The lists are laid out by (j, h, tile):
+// everything one epilogue warp consumes while it walks a range of tiles is one contiguous stream (it pages through it
+// with cp.async).
+constexpr uint32_t kWUQ = kWQ / 2;                              // row quarters per unit
+constexpr uint32_t kWUnitsPerTile = kWW * 2;
+__host__ __device__ inline uint64_t wide_unit_stream_index(uint64_t u, uint32_t wtiles) {
+    return (u % kWUnitsPerTile) * wtiles + u / kWUnitsPerTile;
+}
 
 // W2b': entries of every unit, padded to a multiple of 8 so that a unit's list starts 16-byte aligned
 __global__ void wide_unit_totals_kernel(uint32_t num_units, uint32_t wtiles, const uint32_t* __restrict__ sb_cnt, uint32_t* __restrict__ u_tot) {
     for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < num_units; u += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t s = 0;
-        for (uint32_t rq = 0; rq < kWQ; ++rq) s += sb_cnt[u * kWQ + rq];
-        u_tot[wide_unit_stream_index(u / kWW, (uint32_t)(u % kWW), wtiles)] = (s + 7u) & ~7u;
+        for (uint32_t r = 0; r < kWUQ; ++r) s += sb_cnt[u * kWUQ + r];
+        u_tot[wide_unit_stream_index(u, wtiles)] = (s + 7u) & ~7u;
     }
 }
-// sb_off[stream_index(unit) * (kWQ + 1) + rq] = first entry of row quarter rq of the unit (rq = kWQ: end of the last one)
+// sb_off[stream_index(unit) * (kWUQ + 1) + r] = first entry of row quarter r of the unit (r = kWUQ: end of the last one)
 __global__ void wide_subblock_offsets_kernel(uint32_t num_units, uint32_t wtiles, const uint32_t* __restrict__ sb_cnt,
                                              const uint32_t* __restrict__ u_base, uint32_t* __restrict__ sb_off) {
     for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < num_units; u += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t si = wide_unit_stream_index(u / kWW, (uint32_t)(u % kWW), wtiles);
+        const uint64_t si = wide_unit_stream_index(u, wtiles);
         uint32_t o = u_base[si];
-        for (uint32_t rq = 0; rq < kWQ; ++rq) {
-            sb_off[si * (kWQ + 1) + rq] = o;
-            o += sb_cnt[u * kWQ + rq];
+        for (uint32_t r = 0; r < kWUQ; ++r) {
+            sb_off[si * (kWUQ + 1) + r] = o;
+            o += sb_cnt[u * kWUQ + r];
         }
-        sb_off[si * (kWQ + 1) + kWQ] = o;
+        sb_off[si * (kWUQ + 1) + kWUQ] = o;
     }
 }
 
@@ -377,7 +382,7 @@ __global__ void wide_subblock_fill_kernel(uint32_t num_sb, uint32_t wtiles, cons
         if (cnt == 0) continue;
         uint32_t k = base[((size_t)t * kWH + (j >> 2)) * kWideRows + row];
         for (uint32_t jj = j & ~3u; jj < j; ++jj) k += __popc(mask[((size_t)t * kWW + jj) * kWideRows + row]);
-        uint32_t e = sb_off[wide_unit_stream_index(t, j, wtiles) * (kWQ + 1) + rq] + incl - cnt;
+        uint32_t e = sb_off[wide_unit_stream_index(sb / kWUQ, wtiles) * (kWUQ + 1) + sb % kWUQ] + incl - cnt;
         while (m) {
             const uint32_t b = __ffs(m) - 1;
             m &= m - 1;
@@ -564,12 +569,12 @@ int build_wide_format(bsmr_plan* plan, Workspace* ws, const uint64_t* ukeys, con
     ctx->launches += 2;
     // the epilogue's work lists (32 sub-blocks per tile)
     const uint32_t num_sb = wtiles * kWQ * kWW;
-    const uint32_t num_units = wtiles * kWW;
+    const uint32_t num_units = wtiles * kWUnitsPerTile;
     TmpBuf<uint32_t> sb_cnt(ws), u_tot(ws), u_base(ws);
     BSMR_TRY(sb_cnt.alloc(num_sb));
     BSMR_TRY(u_tot.alloc(static_cast<size_t>(num_units) + 1));
     BSMR_TRY(u_base.alloc(static_cast<size_t>(num_units) + 1));
-    BSMR_TRY(plan->w_sb_off.alloc(static_cast<size_t>(num_units) * (kWQ + 1)));
+    BSMR_TRY(plan->w_sb_off.alloc(static_cast<size_t>(num_units) * (kWUQ + 1)));
     // every unit list is padded to 8 entries; slack: the kernel's last page copies run past the end of a warp's stream
     const size_t list_cap = static_cast<size_t>(wide_values) + 8u * num_units + 1024;
     BSMR_TRY(plan->w_entries.alloc(list_cap));

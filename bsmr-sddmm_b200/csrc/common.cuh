@@ -20,6 +20,7 @@ constexpr uint32_t kNull = BSMR_NULL_VALUE;
 
 // ---- error plumbing: every ABI function returns a status and records a message ---------
 void set_error(const char* fmt, ...);
+uint32_t* kernel_error_flag();   // device pointer to a host-mapped word: wait code of a timed-out mbarrier (0 = none)
 const char* get_error();
 
 #define BSMR_CUDA_OK(expr)                                                              \
@@ -220,8 +221,9 @@ struct bsmr_plan {
     bsmr::DevBuf<uint32_t> w_cols;            // distinct columns of the wide groups, ascending inside a group
     bsmr::DevBuf<uint32_t> w_mask;            // [tile][8][128]
     bsmr::DevBuf<uint32_t> w_base;            // [tile][2][128]
-    bsmr::DevBuf<uint32_t> w_sb_off;          // [(column quarter * #tiles + tile) * 9 + row quarter]: first entry of the 32 x 32
-                                              // sub-block (9th: end); a unit's list starts at a multiple of 8 entries
+    bsmr::DevBuf<uint32_t> w_sb_off;          // [((column quarter * 2 + row half) * #tiles + tile) * 5 + row quarter of the half]:
+                                              // first entry of the 32 x 32 sub-block (5th: end); a unit's list starts at a
+                                              // multiple of 8 entries
     bsmr::DevBuf<uint2> w_entries;            // entry: {byte offset inside the epilogue's staging image, CSR position}
     std::vector<uint32_t> h_wt_group;         // row group of every wide tile
     bsmr::DevBuf<uint32_t> w_cta_begin;       // CTA -> first tile, for tiles [w_part_begin, w_part_end) (wide_partition)

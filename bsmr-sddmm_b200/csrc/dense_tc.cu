@@ -313,10 +313,10 @@ int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, 
         BSMR_CUDA_OK(cudaFuncSetAttribute(dense_sddmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseSmemBytes));
         attr_set = true;
     }
-    static DevBuf<uint32_t> error_flag;  // one per process is enough: it only ever reports a broken pipeline
-    if (!error_flag.ptr) {
-        BSMR_TRY(error_flag.alloc(1));
-        BSMR_CUDA_OK(cudaMemsetAsync(error_flag.ptr, 0, 4, ctx->stream));
+    uint32_t* error_flag = kernel_error_flag();
+    if (!error_flag) {
+        set_error("no mapped host memory for the kernels' error flag");
+        return BSMR_ERR_CUDA;
     }
     DenseParams p{};
     p.K = K; p.M = plan->M; p.N = plan->N;
@@ -331,7 +331,7 @@ int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, 
     p.tile_meta = plan->tile_meta.ptr;
     p.tile_list = tile_list;
     p.P = dP;
-    p.error_flag = error_flag.ptr;
+    p.error_flag = error_flag;
     p.debug_smem = g_debug_smem;
     g_debug_smem = nullptr;
     const uint32_t tiles = tile_end - tile_begin;

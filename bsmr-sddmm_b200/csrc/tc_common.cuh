@@ -11,7 +11,7 @@
 namespace bsmr {
 namespace tc {
 
-constexpr uint32_t kSpinLimit = 1u << 24;   // x >= 200 ns: seconds
+constexpr unsigned long long kWaitLimitNs = 2000000000ull;   // a pipeline wait longer than 2 s is a broken pipeline
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -43,12 +43,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 template <bool kBackoff = true>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* error_flag, uint32_t code) {
     uint32_t spins = 0;
+    unsigned long long t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
         ++spins;
         if (kBackoff && spins > 4) __nanosleep(spins < 64 ? 40 : 200);
-        if (spins > (kBackoff ? kSpinLimit : (kSpinLimit << 4))) {
-            atomicExch(error_flag, code);
-            __trap();
+        if ((spins & 0xFFFu) == 0) {          // every 4096 polls: wall-clock limit (2 s) on the whole wait
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            if (now - t0 > kWaitLimitNs) {
+                atomicExch(error_flag, code);     // host-mapped word: readable after the trap (common.cuh)
+                __threadfence_system();
+                __trap();
+            }
         }
     }
 }

@@ -47,10 +47,10 @@ constexpr int kWBStageBytes = kWCols * 128;           // 16 KB
 constexpr int kWWords = kWCols / 32;                  // 32-column quarters of a tile (= TMEM lane quarters)
 constexpr int kWRowQ = kWGroupRows / 32;              // 32-row quarters of a row group
 constexpr int kWProducerWarps = 8;                    // warps 0-7: TMA gather4 issue
-constexpr int kWEpiWarp0 = 8;                         // warps 8-11: epilogue, TMEM lane quarter = warp % 4
-constexpr int kWEpiWarps = 4;
-constexpr int kWMmaWarp = 12;
-constexpr int kWThreads = 13 * 32;
+constexpr int kWEpiWarp0 = 8;                         // warps 8-15: epilogue, TMEM lane quarter = warp % 4, row half = (warp - 8) / 4
+constexpr int kWEpiWarps = 8;
+constexpr int kWMmaWarp = 16;
+constexpr int kWThreads = 17 * 32;
 constexpr int kWMaxStages = 8;
 constexpr int kWMaxKChunks = 8;                       // K <= 256
 constexpr int kWTmemCols = 512;
@@ -58,8 +58,8 @@ constexpr int kWMaxAccs = 4;
 constexpr uint32_t kNoCol = 0xFFFFFFFFu;
 constexpr int kWEpiRowWords = 36;                              // padded row of the epilogue staging (conflict-free STS.128)
 constexpr int kWEpiStageBytes = 32 * kWEpiRowWords * 4;        // 4608 bytes per epilogue warp
-constexpr int kWListPage = 224;                                // work-list entries per page of an epilogue warp's list stream
-constexpr int kWListBytes = 2 * kWListPage * 8;                // two pages in shared memory per epilogue warp: 3.5 KB
+constexpr int kWListPage = 104;                                // work-list entries per page of an epilogue warp's list stream
+constexpr int kWListBytes = 2 * kWListPage * 8;                // two pages in shared memory per epilogue warp: 1.6 KB
 
 struct __align__(16) WideSmemTail {
     uint64_t b_full[kWMaxStages];    // TMA bytes of the stage landed
@@ -67,7 +67,7 @@ struct __align__(16) WideSmemTail {
     uint64_t a_full[kWMaxKChunks];   // A images of K-chunk kc landed
     uint64_t a_free;                 // every MMA that reads the current A images has completed
     uint64_t tmem_full[kWMaxAccs];
-    uint64_t tmem_empty[kWMaxAccs];  // the 4 epilogue warps have read the accumulator
+    uint64_t tmem_empty[kWMaxAccs];  // the epilogue warps have read the accumulator
     uint32_t tmem_base;
     uint32_t pad[3];
 };
@@ -269,17 +269,19 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // follows the nnz, not the tile area (a predicated store per accumulator element cost 4.6 us per 128 x 256
         // tile, measured: one epilogue warp per scheduler pays every dependent instruction's full latency).  The list of
         // stream of the warp is paged through shared memory with cp.async.
+        const uint32_t ew = warp - kWEpiWarp0;
         const uint32_t quarter = warp & 3;          // TMEM lanes [32*quarter, +32) = tile columns: fixed by warp id % 4
-        float* stg = reinterpret_cast<float*>(epi_stage + (size_t)quarter * kWEpiStageBytes);
+        const uint32_t half = ew >> 2;              // rows [128*half, +128) of the group
+        float* stg = reinterpret_cast<float*>(epi_stage + (size_t)ew * kWEpiStageBytes);
         const uint8_t* stg_bytes = reinterpret_cast<const uint8_t*>(stg);
-        const uint2* lpage = reinterpret_cast<const uint2*>(epi_lists + (size_t)quarter * kWListBytes);
+        const uint2* lpage = reinterpret_cast<const uint2*>(epi_lists + (size_t)ew * kWListBytes);
         const uint32_t lpage_u32 = smem_u32(lpage);
-        const uint32_t nch = SGP * 4;               // 32-row chunks of the resident rows per tile
-        // The lists of this warp's units (tile, column quarter), tile ascending, are ONE contiguous stream of entries in
-        // global memory.  The warp pages through it: two pages of kWListPage entries in shared memory, page n + 2
-        // requested (cp.async) the moment page n is used up, whatever the fill of the tiles.
-        auto unit_offsets = [&](uint32_t t) -> uint32_t {   // lane rq <= 8: first entry of row quarter rq (lane 8: end)
-            return lane <= (uint32_t)kWRowQ ? __ldg(p.sb_off + ((size_t)quarter * p.num_tiles + t) * (kWRowQ + 1) + lane) : 0u;
+        // The lists of this warp's units (tile, column quarter, row half), tile ascending, are ONE contiguous stream of
+        // entries in global memory.  The warp pages through it: two pages of kWListPage entries in shared memory, page
+        // n + 2 requested (cp.async) the moment page n is used up, whatever the fill of the tiles.
+        const size_t stream_row = (size_t)(quarter * 2 + half) * p.num_tiles;
+        auto unit_offsets = [&](uint32_t t) -> uint32_t {   // lane r <= 4: first entry of row quarter r of the unit (lane 4: end)
+            return lane <= 4u ? __ldg(p.sb_off + (stream_row + t) * 5 + lane) : 0u;
         };
         uint32_t stream_base = 0;
         auto request_page = [&](uint32_t pg) {
@@ -304,12 +306,24 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         };
         uint32_t it = 0;
         for (uint32_t pass = 0; pass < passes; ++pass) {
-            const uint32_t rq0 = pass * nch;        // first row quarter of the pass (K = 256: the second walk takes rows 128..255)
+            // K = 256: one row half is resident per pass and only the warps of that half have work.  The others still take
+            // part in the accumulator hand-shake tile by tile: a warp that skipped ahead would test the parity of a phase
+            // the barrier has not reached yet (a parity wait can only tell the current phase from the previous one).
+            if (SGP == 1 && half != pass) {
+                for (uint32_t t = my_begin; t < my_end; ++t, ++it) {
+                    const uint32_t acc = it % naccs, acc_phase = (it / naccs) & 1;
+                    mbar_wait(&tail->tmem_full[acc], acc_phase, p.error_flag, 19);
+                    if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
+                    __syncwarp();
+                }
+                continue;
+            }
+            const uint32_t col0 = SGP == 2 ? half * 128u : 0u;      // first accumulator column of this warp's rows
             uint32_t off_next = my_begin < my_end ? unit_offsets(my_begin) : 0u;
             if (my_begin < my_end) {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 __syncwarp();
-                stream_base = __shfl_sync(0xffffffffu, off_next, rq0) & ~7u;     // 16-byte aligned pages
+                stream_base = __shfl_sync(0xffffffffu, off_next, 0);     // multiple of 8 entries: 16-byte aligned pages
                 cur_page = 0;
                 request_page(0);
                 request_page(1);
@@ -318,19 +332,18 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const uint32_t acc = it % naccs, acc_phase = (it / naccs) & 1;
                 const uint32_t off_cur = off_next;
                 if (t + 1 < my_end) off_next = unit_offsets(t + 1);    // requested now, used one tile later
-                uint32_t eoff[9];                   // chunk boundaries relative to the stream
+                uint32_t eoff[5];                   // chunk boundaries relative to the stream
 #pragma unroll
-                for (int c = 0; c <= 8; ++c) eoff[c] = __shfl_sync(0xffffffffu, off_cur, (rq0 + c) & 15) - stream_base;
+                for (int c = 0; c <= 4; ++c) eoff[c] = __shfl_sync(0xffffffffu, off_cur, c) - stream_base;
                 mbar_wait(&tail->tmem_full[acc], acc_phase, p.error_flag, 16);
                 tc_fence_after();
-                if (quarter == 0 && it < 2) WTRACE(10 + 2 * it);   // accumulators of tile 0 / 1 complete
+                if (ew == 0 && it < 2) WTRACE(10 + 2 * it);   // accumulators of tile 0 / 1 complete
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    if ((uint32_t)c >= nch) break;
+                for (int c = 0; c < 4; ++c) {
                     const uint32_t e0 = eoff[c], e1 = eoff[c + 1];
                     if (e0 == e1 || (p.debug & 4u)) continue;
                     uint32_t v[32];
-                    const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * (SGP * kWSubRows) + c * 32u;
+                    const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * (SGP * kWSubRows) + col0 + c * 32u;
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -374,11 +387,11 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
-                if (quarter == 0 && it < 2) WTRACE(11 + 2 * it);   // epilogue of tile 0 / 1 done
+                if (ew == 0 && it < 2) WTRACE(11 + 2 * it);   // epilogue of tile 0 / 1 done
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (quarter == 0) WTRACE(14);              // epilogue done
+        if (ew == 0) WTRACE(14);                   // epilogue done
     }
 
     tc_fence_before();
@@ -472,11 +485,10 @@ int launch_wide(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, f
         BSMR_CUDA_OK(cudaFuncSetAttribute(wide_sddmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
         attr_set = true;
     }
-    static DevBuf<uint32_t> error_flag;
-    if (!error_flag.ptr) {
-        BSMR_TRY(error_flag.alloc(1));
-        BSMR_CUDA_OK(cudaMemsetAsync(error_flag.ptr, 0, 4, ctx->stream));
-        BSMR_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    uint32_t* error_flag = kernel_error_flag();
+    if (!error_flag) {
+        set_error("no mapped host memory for the kernels' error flag");
+        return BSMR_ERR_CUDA;
     }
     CUtensorMap map_a, map_b;
     static const bool fp32_maps = std::getenv("BSMR_WIDE_FP32_MAPS") != nullptr;   // experiment: truncating operands
@@ -494,7 +506,7 @@ int launch_wide(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, f
     p.entries = plan->w_entries.ptr;
     p.reordered_rows = plan->reordered_rows.ptr;
     p.P = dP;
-    p.error_flag = error_flag.ptr;
+    p.error_flag = error_flag;
     static const uint32_t dbg = [] { const char* e = std::getenv("BSMR_WIDE_DEBUG"); return e ? (uint32_t)std::atoi(e) : 0u; }();
     p.debug = dbg;
     p.trace = g_wide_trace;
