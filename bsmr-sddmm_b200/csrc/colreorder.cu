@@ -41,7 +41,7 @@ constexpr uint32_t kWideCols = BSMR_WIDE_TILE_COLS;
 constexpr uint32_t kWQ = kWideRows / 32;                       // 32-row quarters per tile (sub-group x TMEM lane quarter)
 constexpr uint32_t kWW = kWideCols / 32;                       // mask words per (tile, row) = 32-column chunks of a tile
 constexpr uint32_t kWH = kWideCols >= 128 ? kWideCols / 128 : 1;   // run starts per (tile, row): one per 128 columns
-constexpr uint32_t kWideStageRowWords = 36;   // row pitch of the wide kernel's epilogue staging (wide_tc.cu: kWEpiRowWords)
+constexpr uint32_t kWideStageRowWords = kWideStagePitchWords;
 
 inline int grid_for(uint64_t n, int per_cta, int sm_count) {
     uint64_t g = (n + per_cta - 1) / per_cta;
@@ -310,86 +310,117 @@ __global__ void fill_wide_kernel(uint32_t num_wide, const uint32_t* __restrict__
     }
 }
 
-// W2b: nnz of every 32 x 32 sub-block, sb = (tile * kWW + column quarter j) * kWQ + row quarter rq; one warp per
-// sub-block, lane = row
-__global__ void wide_subblock_count_kernel(uint32_t num_sb, const uint32_t* __restrict__ mask, uint32_t* __restrict__ sb_cnt) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t sb = warp; sb < num_sb; sb += stride) {
-        const uint32_t rq = (uint32_t)(sb % kWQ), j = (uint32_t)(sb / kWQ) % kWW, t = (uint32_t)(sb / (kWQ * kWW));
-        uint32_t c = __popc(mask[((size_t)t * kWW + j) * kWideRows + rq * 32 + lane]);
-#pragma unroll
-        for (int w = 16; w >= 1; w >>= 1) c += __shfl_xor_sync(0xffffffffu, c, w);
-        if (lane == 0) sb_cnt[sb] = c;
-    }
-}
-
 // The wide kernel computes the TRANSPOSED tile (lanes = the tile's 128 columns, TMEM columns = the group's 256 rows).  An
-// epilogue warp owns 32 tile columns (TMEM lane quarter j) and one half h of the group's rows (4 row quarters).
-// Unit u = (tile * kWW + j) * 2 + h: kWUQ sub-blocks of 32 rows x 32 columns.  The lists are laid out by (j, h, tile):
-// everything one epilogue warp consumes while it walks a range of tiles is one contiguous stream (it pages through it
-// with cp.async).
-constexpr uint32_t kWUQ = kWQ / 2;                              // row quarters per unit
+// epilogue warp owns 32 tile columns (TMEM lane quarter j) and one half h of the group's rows, and handles them as
+// kWUSB sub-blocks of 32 columns x 16 rows.  Unit u = (tile * kWW + j) * 2 + h; sub-block sbi = u * kWUSB + s.
+// The work lists are laid out by (j, h, tile): everything one epilogue warp consumes while it walks a range of tiles is
+// one contiguous stream of 8-byte slots, which it pages through shared memory with bulk copies.  A unit's list is
+//   4 slots of header: 8 words, word s < kWUSB = number of entries in sub-blocks 0..s of the unit
+//   the entries of sub-block 0, 1, ... in (row, column) order: {byte offset in the staging image, CSR position}
+//   padding to a multiple of 8 slots (so that every unit, and every page of the kernel, starts 64-byte aligned)
+constexpr uint32_t kWSbRows = kWideSbRows;
+constexpr uint32_t kWSbPerQ = 32 / kWSbRows;                    // sub-blocks per 32-row quarter
+constexpr uint32_t kWUSB = (kWideRows / 2) / kWSbRows;          // sub-blocks per unit: 8
 constexpr uint32_t kWUnitsPerTile = kWW * 2;
+constexpr uint32_t kWHeaderSlots = 4;
 __host__ __device__ inline uint64_t wide_unit_stream_index(uint64_t u, uint32_t wtiles) {
     return (u % kWUnitsPerTile) * wtiles + u / kWUnitsPerTile;
 }
 
-// W2b': entries of every unit, padded to a multiple of 8 so that a unit's list starts 16-byte aligned
+// W2b: nnz of every sub-block; one warp per (tile, column quarter j, 32-row quarter rq) = two sub-blocks, lane = row
+__global__ void wide_subblock_count_kernel(uint32_t num_q, const uint32_t* __restrict__ mask, uint32_t* __restrict__ sb_cnt) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t q = warp; q < num_q; q += stride) {
+        const uint32_t rq = (uint32_t)(q % kWQ), j = (uint32_t)(q / kWQ) % kWW, t = (uint32_t)(q / (kWQ * kWW));
+        uint32_t c = __popc(mask[((size_t)t * kWW + j) * kWideRows + rq * 32 + lane]);
+#pragma unroll
+        for (int w = kWSbRows / 2; w >= 1; w >>= 1) c += __shfl_xor_sync(0xffffffffu, c, w);
+        if ((lane & (kWSbRows - 1)) == 0) sb_cnt[q * kWSbPerQ + lane / kWSbRows] = c;   // sub-block ((t * kWW + j) * kWQ + rq) * kWSbPerQ + part
+    }
+}
+
+// W2b': slots of every unit (header + entries, padded to a multiple of 8), in stream order
 __global__ void wide_unit_totals_kernel(uint32_t num_units, uint32_t wtiles, const uint32_t* __restrict__ sb_cnt, uint32_t* __restrict__ u_tot) {
     for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < num_units; u += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t s = 0;
-        for (uint32_t r = 0; r < kWUQ; ++r) s += sb_cnt[u * kWUQ + r];
-        u_tot[wide_unit_stream_index(u, wtiles)] = (s + 7u) & ~7u;
+        for (uint32_t r = 0; r < kWUSB; ++r) s += sb_cnt[u * kWUSB + r];
+        u_tot[wide_unit_stream_index(u, wtiles)] = (kWHeaderSlots + s + 7u) & ~7u;
     }
 }
-// sb_off[stream_index(unit) * (kWUQ + 1) + r] = first entry of row quarter r of the unit (r = kWUQ: end of the last one)
-__global__ void wide_subblock_offsets_kernel(uint32_t num_units, uint32_t wtiles, const uint32_t* __restrict__ sb_cnt,
-                                             const uint32_t* __restrict__ u_base, uint32_t* __restrict__ sb_off) {
+// the unit headers: word s = entries in sub-blocks 0..s
+__global__ void wide_unit_header_kernel(uint32_t num_units, uint32_t wtiles, const uint32_t* __restrict__ sb_cnt,
+                                        const uint32_t* __restrict__ unit_start, uint2* __restrict__ slots) {
     for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < num_units; u += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t si = wide_unit_stream_index(u, wtiles);
-        uint32_t o = u_base[si];
-        for (uint32_t r = 0; r < kWUQ; ++r) {
-            sb_off[si * (kWUQ + 1) + r] = o;
-            o += sb_cnt[u * kWUQ + r];
+        uint32_t* hdr = reinterpret_cast<uint32_t*>(slots + unit_start[wide_unit_stream_index(u, wtiles)]);
+        uint32_t o = 0;
+        for (uint32_t r = 0; r < kWUSB; ++r) {
+            o += sb_cnt[u * kWUSB + r];
+            hdr[r] = o;
         }
-        sb_off[si * (kWUQ + 1) + kWUQ] = o;
     }
 }
 
 // W2c: the epilogue's work list: per sub-block its entries in (row, column) order as
 // (byte offset of the element inside the epilogue's padded staging image [column][row], CSR position).  Everything
 // follows from the masks and the run starts: a row's entries inside a tile are consecutive CSR positions in ascending
-// column order.
-__global__ void wide_subblock_fill_kernel(uint32_t num_sb, uint32_t wtiles, const uint32_t* __restrict__ mask,
-                                          const uint32_t* __restrict__ base, const uint32_t* __restrict__ sb_off,
-                                          uint2* __restrict__ entries) {
+// column order.  One warp per (tile, column quarter, 32-row quarter) = two sub-blocks.
+__global__ void wide_subblock_fill_kernel(uint32_t num_q, uint32_t wtiles, const uint32_t* __restrict__ mask,
+                                          const uint32_t* __restrict__ base, const uint32_t* __restrict__ sb_cnt,
+                                          const uint32_t* __restrict__ unit_start, uint2* __restrict__ slots) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t sb = warp; sb < num_sb; sb += stride) {
-        const uint32_t rq = (uint32_t)(sb % kWQ), j = (uint32_t)(sb / kWQ) % kWW, t = (uint32_t)(sb / (kWQ * kWW));
+    for (uint64_t q = warp; q < num_q; q += stride) {
+        const uint32_t rq = (uint32_t)(q % kWQ), j = (uint32_t)(q / kWQ) % kWW, t = (uint32_t)(q / (kWQ * kWW));
         const uint32_t row = rq * 32 + lane;
         uint32_t m = mask[((size_t)t * kWW + j) * kWideRows + row];
         const uint32_t cnt = __popc(m);
-        uint32_t incl = cnt;                          // inclusive warp scan over the rows
+        uint32_t incl = cnt;                          // inclusive scan over the rows of the lane's sub-block
 #pragma unroll
-        for (int w = 1; w < 32; w <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, w);
-            if (lane >= (uint32_t)w) incl += o;
+        for (int w = 1; w < (int)kWSbRows; w <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, w, kWSbRows);
+            if ((lane & (kWSbRows - 1)) >= (uint32_t)w) incl += o;
         }
         if (cnt == 0) continue;
         uint32_t k = base[((size_t)t * kWH + (j >> 2)) * kWideRows + row];
         for (uint32_t jj = j & ~3u; jj < j; ++jj) k += __popc(mask[((size_t)t * kWW + jj) * kWideRows + row]);
-        uint32_t e = sb_off[wide_unit_stream_index(sb / kWUQ, wtiles) * (kWUQ + 1) + sb % kWUQ] + incl - cnt;
+        const uint64_t sbi = q * kWSbPerQ + lane / kWSbRows;     // sub-block of this lane
+        const uint64_t u = sbi / kWUSB;
+        uint32_t e = unit_start[wide_unit_stream_index(u, wtiles)] + kWHeaderSlots + incl - cnt;
+        for (uint64_t sp = u * kWUSB; sp < sbi; ++sp) e += sb_cnt[sp];
         while (m) {
             const uint32_t b = __ffs(m) - 1;
             m &= m - 1;
-            entries[e] = make_uint2((b * kWideStageRowWords + lane) * 4u, k);
+            slots[e] = make_uint2((b * kWideStageRowWords + (lane & (kWSbRows - 1))) * 4u, k);
             ++e;
             ++k;
         }
+    }
+}
+
+// W2d: which parts of a wide tile's column list are runs of consecutive columns (meta.w): bit q = the columns of
+// 32-column quarter q, bit 4 = all of the tile's columns.  The wide kernel fetches such a part with ONE tiled TMA load
+// (32 or 128 rows of the [N x K] tensor) instead of one gather4 per 4 columns.
+__global__ void wide_tile_flags_kernel(uint32_t wtiles, uint4* __restrict__ meta, const uint32_t* __restrict__ cols) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t t = warp; t < wtiles; t += stride) {
+        const uint4 m = meta[t];
+        const uint32_t* c = cols + m.y;
+        uint32_t flags = 0;
+        bool all = m.z > 0;
+        for (uint32_t q = 0; q < kWW; ++q) {
+            const uint32_t i = q * 32 + lane;
+            const bool ok = i >= m.z || i == 0 || c[i] == c[i - 1] + 1;            // consecutive with its predecessor
+            const bool okq = i >= m.z || lane == 0 || c[i] == c[i - 1] + 1;        // ... inside the quarter
+            all = all && __all_sync(0xffffffffu, ok);
+            if (q * 32 < m.z && __all_sync(0xffffffffu, okq)) flags |= 1u << q;
+        }
+        if (all) flags |= 16u;
+        if (lane == 0) meta[t].w = flags;
     }
 }
 
@@ -563,31 +594,33 @@ int build_wide_format(bsmr_plan* plan, Workspace* ws, const uint64_t* ukeys, con
     BSMR_CUDA_OK(cudaMemsetAsync(plan->w_base.ptr, 0xFF, plan->w_base.bytes(), st));
     gather_wide_cols_kernel<<<(num_wide < (uint32_t)sm * 8 ? num_wide : (uint32_t)sm * 8), 256, 0, st>>>(
         num_wide, dkeys.ptr, d_wg_seg.ptr, d_wg_col_off.ptr, d_wg_ncols.ptr, plan->w_cols.ptr);
+    wide_tile_flags_kernel<<<grid_for((uint64_t)wtiles * 32, kThreads, sm), kThreads, 0, st>>>(wtiles, plan->wt_meta.ptr, plan->w_cols.ptr);
+    ctx->launches++;
     fill_wide_kernel<<<grid_for((uint64_t)num_wide * kWideRows * 32, kThreads, sm), kThreads, 0, st>>>(
         num_wide, d_wg_group.ptr, d_wg_col_off.ptr, d_wg_ncols.ptr, d_wg_tile_off.ptr, plan->reordered_rows.ptr, R,
         plan->row_offsets.ptr, plan->col_indices.ptr, plan->w_cols.ptr, plan->w_mask.ptr, plan->w_base.ptr, d_unsorted.ptr);
     ctx->launches += 2;
-    // the epilogue's work lists (32 sub-blocks per tile)
-    const uint32_t num_sb = wtiles * kWQ * kWW;
+    // the epilogue's work lists (64 sub-blocks of 32 columns x 16 rows per tile, 8 units per tile)
+    const uint32_t num_q = wtiles * kWQ * kWW;                 // (tile, column quarter, 32-row quarter)
     const uint32_t num_units = wtiles * kWUnitsPerTile;
-    TmpBuf<uint32_t> sb_cnt(ws), u_tot(ws), u_base(ws);
-    BSMR_TRY(sb_cnt.alloc(num_sb));
+    TmpBuf<uint32_t> sb_cnt(ws), u_tot(ws);
+    BSMR_TRY(sb_cnt.alloc(static_cast<size_t>(num_q) * kWSbPerQ));
     BSMR_TRY(u_tot.alloc(static_cast<size_t>(num_units) + 1));
-    BSMR_TRY(u_base.alloc(static_cast<size_t>(num_units) + 1));
-    BSMR_TRY(plan->w_sb_off.alloc(static_cast<size_t>(num_units) * (kWUQ + 1)));
-    // every unit list is padded to 8 entries; slack: the kernel's last page copies run past the end of a warp's stream
-    const size_t list_cap = static_cast<size_t>(wide_values) + 8u * num_units + 1024;
+    // w_sb_off[stream index of the unit] = first slot of the unit's list (+1 entry: the end); a unit takes 4 header
+    // slots + its entries, padded to 8
+    BSMR_TRY(plan->w_sb_off.alloc(static_cast<size_t>(num_units) + 1));
+    const size_t list_cap = static_cast<size_t>(wide_values) + (kWHeaderSlots + 8u) * num_units + 64;
     BSMR_TRY(plan->w_entries.alloc(list_cap));
     BSMR_CUDA_OK(cudaMemsetAsync(plan->w_entries.ptr, 0, plan->w_entries.bytes(), st));
     BSMR_CUDA_OK(cudaMemsetAsync(u_tot.ptr + num_units, 0, 4, st));
-    wide_subblock_count_kernel<<<grid_for((uint64_t)num_sb * 32, kThreads, sm), kThreads, 0, st>>>(num_sb, plan->w_mask.ptr, sb_cnt.ptr);
+    wide_subblock_count_kernel<<<grid_for((uint64_t)num_q * 32, kThreads, sm), kThreads, 0, st>>>(num_q, plan->w_mask.ptr, sb_cnt.ptr);
     wide_unit_totals_kernel<<<grid_for(num_units, kThreads, sm), kThreads, 0, st>>>(num_units, wtiles, sb_cnt.ptr, u_tot.ptr);
-    BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb, u_tot.ptr, u_base.ptr, static_cast<size_t>(num_units) + 1, st));
+    BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb, u_tot.ptr, plan->w_sb_off.ptr, static_cast<size_t>(num_units) + 1, st));
     BSMR_TRY(ensure_temp(tb));
-    BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(temp.ptr, tb, u_tot.ptr, u_base.ptr, static_cast<size_t>(num_units) + 1, st));
-    wide_subblock_offsets_kernel<<<grid_for(num_units, kThreads, sm), kThreads, 0, st>>>(num_units, wtiles, sb_cnt.ptr, u_base.ptr, plan->w_sb_off.ptr);
-    wide_subblock_fill_kernel<<<grid_for((uint64_t)num_sb * 32, kThreads, sm), kThreads, 0, st>>>(
-        num_sb, wtiles, plan->w_mask.ptr, plan->w_base.ptr, plan->w_sb_off.ptr, plan->w_entries.ptr);
+    BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(temp.ptr, tb, u_tot.ptr, plan->w_sb_off.ptr, static_cast<size_t>(num_units) + 1, st));
+    wide_unit_header_kernel<<<grid_for(num_units, kThreads, sm), kThreads, 0, st>>>(num_units, wtiles, sb_cnt.ptr, plan->w_sb_off.ptr, plan->w_entries.ptr);
+    wide_subblock_fill_kernel<<<grid_for((uint64_t)num_q * 32, kThreads, sm), kThreads, 0, st>>>(
+        num_q, wtiles, plan->w_mask.ptr, plan->w_base.ptr, sb_cnt.ptr, plan->w_sb_off.ptr, plan->w_entries.ptr);
     ctx->launches += 2;
     ctx->launches += 3;
     uint32_t unsorted = 0;

@@ -23,12 +23,13 @@
 // the tensor map and arrive as zeros.
 // Precision: tcgen05 kind::tf32 reads the fp32 bit patterns and IGNORES the low 13 mantissa
 // bits (truncation; measured on B200: mean signed error -6.5e-4 on all-positive inputs).  The
-// reference rounds to nearest (wmma::__float_to_tf32 = cvt.rna, src/sddmmKernel.cu:317-322), so
-// four converter warps round every landed stage in place with cvt.rna.tf32.f32 before the MMA
-// warp may read it (generic-proxy writes -> fence.proxy.async -> mbarrier).
-// Warp roles (17 warps): 0..7 = TMA producers (16 columns of the B-column tile each, see the producer section for
+// reference rounds to nearest (wmma::__float_to_tf32 = cvt.rna, src/sddmmKernel.cu:317-322).  The rounding is done
+// by the TMA unit: the tensor maps carry CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, which makes it round every fp32 element
+// to TF32 on the way into shared memory (measured against a cvt.rna converter pass in shared memory, which this
+// kernel used before: same maximum error, mean signed error -3e-7; tests/tf32_probe.py).
+// Warp roles (13 warps): 0..7 = TMA producers (16 columns of the B-column tile each, see the producer section for
 // why so many), 8 = TMEM allocator + MMA issuer, 9..12 = epilogue (tcgen05.ld of the warp's 32 TMEM lanes x 16 columns,
-// mask + scatter P[idx] = acc), 13..16 = TF32 round-to-nearest converters.
+// mask + scatter P[idx] = acc).
 // Four TMEM accumulators (4 x 16 columns) let the epilogue of tile i overlap the MMAs of tiles i+1..i+3; a 5-stage
 // smem ring (18 KB / stage) keeps ~90 KB of loads in flight per CTA.
 #include <cuda.h>
@@ -52,14 +53,12 @@ constexpr int kColsPerProducer = 128 / kProducerWarps;
 constexpr int kReqPerProducer = kColsPerProducer / 4;
 constexpr int kMmaWarp = kProducerWarps;
 constexpr int kEpiWarp0 = kProducerWarps + 1;     // 4 epilogue warps (kEpiWarp0 % 4 is irrelevant: quarter = warp & 3 covers all four)
-constexpr int kConvWarp0 = kProducerWarps + 5;    // first of 4 converter warps
-constexpr int kDenseThreads = (kProducerWarps + 9) * 32;
+constexpr int kDenseThreads = (kProducerWarps + 5) * 32;
 constexpr int kAccs = 4;                           // TMEM accumulators in rotation (tile i+4 waits for the epilogue of tile i)
 constexpr int kTmemCols = kAccs * 16;              // 16 fp32 columns each
 
 struct __align__(16) DenseSmemTail {
     uint64_t full[kStages];    // TMA bytes landed
-    uint64_t ready[kStages];   // operands rounded to TF32 (4 converter warps arrived)
     uint64_t empty[kStages];   // MMAs that read the stage have completed
     uint64_t tmem_full[kAccs];
     uint64_t tmem_empty[kAccs];
@@ -102,8 +101,7 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(&tail->full[s], 1);
-            mbar_init(&tail->ready[s], 4);
+            mbar_init(&tail->full[s], kProducerWarps);   // every producer warp arrives (see the producer loop)
             mbar_init(&tail->empty[s], 1);
         }
         for (int a = 0; a < kAccs; ++a) {
@@ -162,7 +160,12 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const uint32_t tx_bytes = (nc / 4) * 512u + kATileBytes;
             for (uint32_t kc = 0; kc < num_chunks; ++kc) {
                 mbar_wait(&tail->empty[stage], phase ^ 1, p.error_flag, 1);
-                if (warp == 0 && lane == 0) mbar_arrive_expect_tx(&tail->full[stage], tx_bytes);
+                // every producer warp arrives, with or without requests for this tile: a warp that only watched could fall
+                // a whole ring cycle behind, and a parity wait cannot tell phase n from phase n + 2
+                if (lane == 0) {
+                    if (warp == 0) mbar_arrive_expect_tx(&tail->full[stage], tx_bytes);
+                    else mbar_arrive(&tail->full[stage]);
+                }
                 uint8_t* bt = b_tiles + (size_t)stage * kBTileBytes;
                 uint8_t* at = a_tiles + (size_t)stage * kATileBytes;
                 const int x = (int)(kc * kChunk);
@@ -184,7 +187,7 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * kPanel;
             for (uint32_t kc = 0; kc < num_chunks; ++kc) {
-                mbar_wait(&tail->ready[stage], phase, p.error_flag, 3);
+                mbar_wait<false>(&tail->full[stage], phase, p.error_flag, 3);
                 tc_fence_after();
                 if (p.debug_smem && t == p.tile_begin && kc == 0 && blockIdx.x == 0) {
                     // probe: raw image of stage 0 (B-column tile then A-row tile)
@@ -206,39 +209,6 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     if (kc + 1 == num_chunks) umma_commit(&tail->tmem_full[acc]);
                 }
                 __syncwarp();
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
-            }
-        }
-    } else if (warp >= kConvWarp0) {
-        // ================= TF32 converters (last four warps) =================
-        // cvt.rna.tf32.f32 on every element of the landed stage, in place; element-wise, so the
-        // 128-byte swizzle does not matter.  Thread i owns float4 #i, #i+128, ... of the B-column
-        // tile (8 of them) and float4 #i of the A-row tile.
-        const uint32_t ci = threadIdx.x - kConvWarp0 * 32;   // 0..127
-        uint32_t stage = 0, phase = 0;
-        for (uint32_t t = p.tile_begin + blockIdx.x; t < p.tile_end; t += gridDim.x) {
-            for (uint32_t kc = 0; kc < num_chunks; ++kc) {
-                mbar_wait(&tail->full[stage], phase, p.error_flag, 5);
-                float4* bt = reinterpret_cast<float4*>(b_tiles + (size_t)stage * kBTileBytes);
-                float4* at = reinterpret_cast<float4*>(a_tiles + (size_t)stage * kATileBytes);
-                float4 v[9];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = bt[ci + 128 * j];
-                v[8] = at[ci];
-#pragma unroll
-                for (int j = 0; j < 9; ++j) {
-                    v[j].x = rna_tf32(v[j].x);
-                    v[j].y = rna_tf32(v[j].y);
-                    v[j].z = rna_tf32(v[j].z);
-                    v[j].w = rna_tf32(v[j].w);
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) bt[ci + 128 * j] = v[j];
-                at[ci] = v[8];
-                // make the generic-proxy stores visible to the tensor core (async proxy) before signalling
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tail->ready[stage]);
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -305,8 +275,8 @@ int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, 
         return BSMR_ERR_UNSUPPORTED;
     }
     CUtensorMap map_a, map_b;
-    BSMR_TRY(make_row_gather_map(ctx, dA, plan->M, K, &map_a));
-    BSMR_TRY(make_row_gather_map(ctx, dB, plan->N, K, &map_b));
+    BSMR_TRY(make_row_gather_map(ctx, dA, plan->M, K, &map_a, true));   // TFLOAT32 maps: the TMA unit rounds to TF32
+    BSMR_TRY(make_row_gather_map(ctx, dB, plan->N, K, &map_b, true));
 
     static bool attr_set = false;
     if (!attr_set) {

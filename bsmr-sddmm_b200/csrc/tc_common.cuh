@@ -67,6 +67,13 @@ __device__ __forceinline__ void tma_gather4(const CUtensorMap* map, uint64_t* ba
         ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(rows.x), "r"(rows.y), "r"(rows.z), "r"(rows.w), "r"(smem_u32(bar))
         : "memory");
 }
+// plain tiled load of a box of the tensor map (rows y .. y + box rows - 1, elements x .. x + 31)
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ float rna_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -118,14 +125,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 // TF32 (to nearest) on its way into shared memory -- measured on B200 against cvt.rna.tf32.f32 in a converter pass: same
 // maximum error (1.4e-4 at K = 128), mean signed error -3e-7 (tests/tf32_probe.py); with a FLOAT32 map the tensor core
 // truncates (mean -6.5e-4).
-inline int make_row_gather_map(bsmr_ctx* ctx, const float* base, uint64_t rows, uint64_t K, CUtensorMap* out, bool tf32_rounding = false) {
+// box_rows: 1 for tile::gather4 requests (4 arbitrary rows each), 32 / 128 for plain tiled loads of consecutive rows
+inline int make_row_gather_map(bsmr_ctx* ctx, const float* base, uint64_t rows, uint64_t K, CUtensorMap* out, bool tf32_rounding = false,
+                               uint32_t box_rows = 1) {
     if (!ctx->encode_tiled) {
         set_error("cuTensorMapEncodeTiled is not available from this driver");
         return BSMR_ERR_UNSUPPORTED;
     }
     const cuuint64_t dims[2] = {K, rows};
     const cuuint64_t strides[1] = {K * sizeof(float)};
-    const cuuint32_t box[2] = {32, 1};
+    const cuuint32_t box[2] = {32, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     static const bool tf32_env = std::getenv("BSMR_TMA_TF32") != nullptr;
     const bool tf32_map = tf32_rounding || tf32_env;

@@ -56,10 +56,15 @@ constexpr int kWMaxKChunks = 8;                       // K <= 256
 constexpr int kWTmemCols = 512;
 constexpr int kWMaxAccs = 4;
 constexpr uint32_t kNoCol = 0xFFFFFFFFu;
-constexpr int kWEpiRowWords = 36;                              // padded row of the epilogue staging (conflict-free STS.128)
+constexpr int kWSbRows = kWideSbRows;                          // rows of an epilogue sub-block (32 columns x 32 rows)
+static_assert(kWSbRows == 32, "the epilogue loads a sub-block with tcgen05.ld 32x32b.x32");
+constexpr int kWUSB = (kWGroupRows / 2) / kWSbRows;            // sub-blocks per unit (tile x column quarter x row half): 4
+constexpr int kWEpiRowWords = kWideStagePitchWords;            // pitch of the staging image [32 columns][32 rows] (conflict-free STS.128)
 constexpr int kWEpiStageBytes = 32 * kWEpiRowWords * 4;        // 4608 bytes per epilogue warp
-constexpr int kWListPage = 104;                                // work-list entries per page of an epilogue warp's list stream
-constexpr int kWListBytes = 2 * kWListPage * 8;                // two pages in shared memory per epilogue warp: 1.6 KB
+constexpr int kWListPage = 216;                                // 8-byte slots per page of an epilogue warp's list stream
+constexpr int kWListPages = 2;                                 // pages in shared memory per epilogue warp (bulk-copy ring)
+constexpr int kWListBytes = kWListPages * kWListPage * 8;      // 1.7 KB per epilogue warp
+constexpr int kWHeaderSlots = 4;                               // a unit's list starts with 8 words: entries in sub-blocks 0..s
 
 struct __align__(16) WideSmemTail {
     uint64_t b_full[kWMaxStages];    // TMA bytes of the stage landed
@@ -68,6 +73,7 @@ struct __align__(16) WideSmemTail {
     uint64_t a_free;                 // every MMA that reads the current A images has completed
     uint64_t tmem_full[kWMaxAccs];
     uint64_t tmem_empty[kWMaxAccs];  // the epilogue warps have read the accumulator
+    uint64_t l_full[kWEpiWarps][kWListPages];   // a page of an epilogue warp's list stream has landed (bulk copy)
     uint32_t tmem_base;
     uint32_t pad[3];
 };
@@ -101,7 +107,8 @@ __device__ __forceinline__ unsigned long long gtime() {
     } while (0)
 
 __global__ void __launch_bounds__(kWThreads, 1)
-wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const WideParams p) {
+wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const __grid_constant__ CUtensorMap map_b32, const __grid_constant__ CUtensorMap map_b128, const WideParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment by pointer arithmetic on the __shared__ array: an integer round trip loses the address space
     // and every access below would become a generic LD/ST instead of LDS/STS (seen in SASS)
@@ -121,7 +128,7 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
     if (warp == 0 && lane == 0) {
         for (uint32_t s = 0; s < S; ++s) {
-            mbar_init(&tail->b_full[s], 1);
+            mbar_init(&tail->b_full[s], kWProducerWarps);   // every producer warp arrives (see the producer loop)
             mbar_init(&tail->b_empty[s], 1);
         }
         for (uint32_t k = 0; k < KC; ++k) {
@@ -132,6 +139,8 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             mbar_init(&tail->tmem_full[a], 1);
             mbar_init(&tail->tmem_empty[a], kWEpiWarps);
         }
+        for (int w = 0; w < kWEpiWarps; ++w)
+            for (int k = 0; k < kWListPages; ++k) mbar_init(&tail->l_full[w][k], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -155,9 +164,14 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // LDG-staged operands every load in flight held an L1 line and the epilogue's LDS/STG queued behind them.
         const uint32_t rq = warp * 4 + lane;         // request (= group of 4 rows of the image) of this lane, lanes 0..3
         const bool issuer = lane < 4;
-        auto fetch_cols = [&](uint32_t t, uint32_t& ncols, int4& cols) {
+        // Runs of consecutive columns (flags from the format builder, tile_meta.w) are fetched with ONE tiled load per
+        // 32-column quarter, or per tile, instead of 8 / 32 gather4 requests: every request passes through the MIO queue
+        // of its warp's scheduler, and with 32 of them per stage the epilogue warps' LDS / STS waited ~700-1000 cycles
+        // behind them (measured with clock64 stamps).
+        auto fetch_cols = [&](uint32_t t, uint32_t& ncols, uint32_t& flags, int4& cols) {
             const uint4 m = __ldg(p.tile_meta + t);
             ncols = m.z;
+            flags = (p.debug & 256u) ? 0u : m.w;
             cols = make_int4((int)p.N, (int)p.N, (int)p.N, (int)p.N);
             const uint32_t c0 = rq * 4;
             if (issuer && c0 < m.z) {
@@ -167,13 +181,14 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (c0 + 3 >= m.z) cols.w = (int)p.N;
             }
         };
+        const uint32_t myq = warp >> 1;              // 32-column quarter of the tile this warp's requests belong to
         uint32_t stage = 0, phase = 0, a_loads = 0, cur_key = kNoCol;
         for (uint32_t pass = 0; pass < passes; ++pass) {
-            uint32_t ncols = 0, ncols_next = 0;
+            uint32_t ncols = 0, ncols_next = 0, flags = 0, flags_next = 0;
             int4 cols = make_int4(0, 0, 0, 0), cols_next = make_int4(0, 0, 0, 0);
-            if (my_begin < my_end) fetch_cols(my_begin, ncols, cols);
+            if (my_begin < my_end) fetch_cols(my_begin, ncols, flags, cols);
             for (uint32_t t = my_begin; t < my_end; ++t) {
-                if (t + 1 < my_end) fetch_cols(t + 1, ncols_next, cols_next);   // indices of the next tile: off the critical path
+                if (t + 1 < my_end) fetch_cols(t + 1, ncols_next, flags_next, cols_next);   // indices of the next tile: off the critical path
                 const uint32_t g = __ldg(p.tile_meta + t).x;
                 const uint32_t key = g * 2 + pass;
                 const bool new_key = key != cur_key;
@@ -196,8 +211,22 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     cur_key = key;
                     ++a_loads;
                 }
-                const bool has_cols = issuer && rq * 4 < ncols;
-                const uint32_t tx_bytes = ((ncols + 3) / 4) * 512u;
+                // what this lane issues per stage, and the bytes the stage's barrier has to see
+                const bool whole = (flags & 16u) != 0;
+                const bool qrun = ((flags >> myq) & 1u) != 0;
+                const bool do_whole = whole && warp == 0 && lane == 0;
+                const bool do_qrun = !whole && qrun && (warp & 1u) == 0 && lane == 0;
+                const bool do_gather = !whole && !qrun && issuer && rq * 4 < ncols;
+                uint32_t tx_bytes = 0;
+                if (whole) {
+                    tx_bytes = kWBStageBytes;
+                } else {
+#pragma unroll
+                    for (uint32_t q = 0; q < (uint32_t)kWWords; ++q) {
+                        const uint32_t nq = ncols > q * 32 ? (ncols - q * 32 < 32u ? ncols - q * 32 : 32u) : 0u;
+                        tx_bytes += ((flags >> q) & 1u) ? 4096u : ((nq + 3) / 4) * 512u;
+                    }
+                }
                 for (uint32_t kc = 0; kc < KC; ++kc) {
                     if (new_key) {
                         if (warp == 0 && lane == 0) mbar_arrive_expect_tx(&tail->a_full[kc], SGP * kWAImgBytes);
@@ -208,12 +237,21 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         }
                     }
                     mbar_wait(&tail->b_empty[stage], phase ^ 1, p.error_flag, 12);
-                    if (warp == 0 && lane == 0) mbar_arrive_expect_tx(&tail->b_full[stage], tx_bytes);
-                    if (has_cols)
-                        tma_gather4(&map_b, &tail->b_full[stage], b_ring + (size_t)stage * kWBStageBytes + rq * 512, (int)(kc * kWChunk), cols);
+                    // every producer warp arrives on the stage's barrier, whether it has requests to issue for this tile or
+                    // not: a warp that only watched could otherwise fall a whole ring cycle behind the others, and a parity
+                    // wait cannot tell phase n from phase n + 2 (seen as a rare hang once a single lane issued a whole stage)
+                    if (lane == 0) {
+                        if (warp == 0) mbar_arrive_expect_tx(&tail->b_full[stage], tx_bytes);
+                        else mbar_arrive(&tail->b_full[stage]);
+                    }
+                    uint8_t* bst = b_ring + (size_t)stage * kWBStageBytes;
+                    if (do_whole) tma_load_2d(&map_b128, &tail->b_full[stage], bst, (int)(kc * kWChunk), cols.x);
+                    if (do_qrun) tma_load_2d(&map_b32, &tail->b_full[stage], bst + myq * 4096, (int)(kc * kWChunk), cols.x);
+                    if (do_gather) tma_gather4(&map_b, &tail->b_full[stage], bst + rq * 512, (int)(kc * kWChunk), cols);
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
                 ncols = ncols_next;
+                flags = flags_next;
                 cols = cols_next;
             }
         }
@@ -262,48 +300,26 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         WTRACE(9);                                 // last MMA issued
     } else {
-        // ================= epilogue (warps 8..11) =================
-        // Per (tile, sub-group) and 32-column chunk: tcgen05.ld of the warp's 32 x 32 accumulator sub-block -> padded
-        // shared-memory staging (row stride 36 words: conflict-free 128-bit stores) -> the sub-block's work list, four
-        // passes of 32 entries at a time: one LDS.64 (entry), one LDS (value), one STG per entry.  The instruction count
-        // follows the nnz, not the tile area (a predicated store per accumulator element cost 4.6 us per 128 x 256
-        // tile, measured: one epilogue warp per scheduler pays every dependent instruction's full latency).  The list of
-        // stream of the warp is paged through shared memory with cp.async.
+        // ================= epilogue (warps 8..15) =================
+        // Warp = (TMEM lane quarter = 32 tile columns, row half of the group).  Per tile it walks 8 sub-blocks of 32 columns
+        // x 16 rows: tcgen05.ld 32x32b.x16 -> padded shared-memory staging image [column][row] (pitch 20 words:
+        // conflict-free STS.128) -> the sub-block's work list: one LDS.64 (entry), one LDS (value), one STG per entry, so
+        // the instruction count follows the nnz, not the tile area (a predicated store per accumulator element cost
+        // 4.6 us per 128 x 256 tile, measured).
+        // The lists of this warp's units, tile ascending, are ONE contiguous stream of 8-byte slots in global memory
+        // (colreorder.cu); the warp pages through it with cp.async.bulk into a ring of kWListPages pages, each with its
+        // own mbarrier.  (Paging with cp.async / LDG went through the LSU and whatever L1 the 227 KB of shared memory
+        // leave: every list access then waited ~700 cycles behind those loads -- measured with clock64 stamps.)
         const uint32_t ew = warp - kWEpiWarp0;
         const uint32_t quarter = warp & 3;          // TMEM lanes [32*quarter, +32) = tile columns: fixed by warp id % 4
         const uint32_t half = ew >> 2;              // rows [128*half, +128) of the group
         float* stg = reinterpret_cast<float*>(epi_stage + (size_t)ew * kWEpiStageBytes);
         const uint8_t* stg_bytes = reinterpret_cast<const uint8_t*>(stg);
-        const uint2* lpage = reinterpret_cast<const uint2*>(epi_lists + (size_t)ew * kWListBytes);
-        const uint32_t lpage_u32 = smem_u32(lpage);
-        // The lists of this warp's units (tile, column quarter, row half), tile ascending, are ONE contiguous stream of
-        // entries in global memory.  The warp pages through it: two pages of kWListPage entries in shared memory, page
-        // n + 2 requested (cp.async) the moment page n is used up, whatever the fill of the tiles.
-        const size_t stream_row = (size_t)(quarter * 2 + half) * p.num_tiles;
-        auto unit_offsets = [&](uint32_t t) -> uint32_t {   // lane r <= 4: first entry of row quarter r of the unit (lane 4: end)
-            return lane <= 4u ? __ldg(p.sb_off + (stream_row + t) * 5 + lane) : 0u;
-        };
-        uint32_t stream_base = 0;
-        auto request_page = [&](uint32_t pg) {
-            const uint2* src = p.entries + stream_base + (size_t)pg * kWListPage;
-            const uint32_t dst = lpage_u32 + (pg & 1u) * (kWListPage * 8);
-            for (uint32_t i = lane * 2; i < (uint32_t)kWListPage; i += 64)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 8), "l"(src + i) : "memory");
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        uint32_t cur_page = 0;
-        auto ensure_page = [&](uint32_t pg) {       // pages are consumed in ascending order
-            while (cur_page < pg) {
-                // page cur_page must have LANDED (a skipped page may still be in flight) and every lane must be done with
-                // it before its buffer takes page cur_page + 2
-                asm volatile("cp.async.wait_group 1;" ::: "memory");
-                __syncwarp();
-                request_page(cur_page + 2);
-                ++cur_page;
-            }
-            asm volatile("cp.async.wait_group 1;" ::: "memory");    // all but the newest request (page cur_page + 1) have landed
-            __syncwarp();
-        };
+        const uint8_t* lring = epi_lists + (size_t)ew * kWListBytes;
+        const uint32_t lring_u32 = smem_u32(lring);
+        uint64_t* lfull = tail->l_full[ew];
+        const uint32_t* ustart = p.sb_off + (size_t)(quarter * 2 + half) * p.num_tiles;
+        uint32_t gp_base = 0;                       // pages issued in earlier passes (ring position of local page 0)
         uint32_t it = 0;
         for (uint32_t pass = 0; pass < passes; ++pass) {
             // K = 256: one row half is resident per pass and only the warps of that half have work.  The others still take
@@ -318,32 +334,92 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
                 continue;
             }
+            if (my_begin >= my_end) continue;
             const uint32_t col0 = SGP == 2 ? half * 128u : 0u;      // first accumulator column of this warp's rows
-            uint32_t off_next = my_begin < my_end ? unit_offsets(my_begin) : 0u;
-            if (my_begin < my_end) {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                __syncwarp();
-                stream_base = __shfl_sync(0xffffffffu, off_next, 0);     // multiple of 8 entries: 16-byte aligned pages
-                cur_page = 0;
-                request_page(0);
-                request_page(1);
-            }
+            const uint32_t s_begin = __ldg(ustart + my_begin), s_end = __ldg(ustart + my_end);   // slots of this warp's stream
+            const uint32_t npages = (s_end - s_begin + kWListPage - 1) / kWListPage;
+            auto issue_page = [&](uint32_t pg) {     // local page pg -> ring buffer (gp_base + pg) % kWListPages
+                if (lane == 0) {
+                    const uint32_t g = gp_base + pg;
+                    const uint32_t first = pg * kWListPage;
+                    const uint32_t n = s_end - s_begin - first < (uint32_t)kWListPage ? s_end - s_begin - first : (uint32_t)kWListPage;
+                    uint64_t* bar = &lfull[g % kWListPages];
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer's last readers were generic-proxy loads
+                    mbar_arrive_expect_tx(bar, n * 8u);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(lring_u32 + (g % kWListPages) * (kWListPage * 8)), "l"(p.entries + s_begin + first), "r"(n * 8u),
+                                   "r"(smem_u32(bar))
+                                 : "memory");
+                }
+            };
+            auto wait_page = [&](uint32_t pg) {
+                const uint32_t g = gp_base + pg;
+                mbar_wait(&lfull[g % kWListPages], (g / kWListPages) & 1, p.error_flag, 20);
+            };
+            for (uint32_t pg = 0; pg < npages && pg < (uint32_t)kWListPages; ++pg) issue_page(pg);
+            uint32_t cur_page = 0;
+            bool cur_landed = false;                 // cur_page has been waited for (an mbarrier poll costs ~200 cycles: only once per page)
+            auto ensure_page = [&](uint32_t pg) {    // pages are consumed in ascending order
+                if (pg == cur_page && cur_landed) return;
+                while (cur_page < pg) {
+                    // leaving cur_page: it has landed (it may never have been read), every lane is done with it, and its
+                    // buffer takes page cur_page + kWListPages
+                    if (!cur_landed) wait_page(cur_page);
+                    __syncwarp();
+                    if (cur_page + kWListPages < npages) issue_page(cur_page + kWListPages);
+                    ++cur_page;
+                    cur_landed = false;
+                }
+                wait_page(pg);
+                cur_landed = true;
+            };
+            // slot e of the stream (relative to s_begin) inside the ring
+            auto slot_addr = [&](uint32_t e) -> const uint8_t* {
+                const uint32_t pg = e / kWListPage;
+                return lring + ((gp_base + pg) % kWListPages) * (kWListPage * 8) + (e - pg * kWListPage) * 8;
+            };
+            uint32_t pos = 0;                        // first slot of the current unit
             for (uint32_t t = my_begin; t < my_end; ++t, ++it) {
                 const uint32_t acc = it % naccs, acc_phase = (it / naccs) & 1;
-                const uint32_t off_cur = off_next;
-                if (t + 1 < my_end) off_next = unit_offsets(t + 1);    // requested now, used one tile later
-                uint32_t eoff[5];                   // chunk boundaries relative to the stream
-#pragma unroll
-                for (int c = 0; c <= 4; ++c) eoff[c] = __shfl_sync(0xffffffffu, off_cur, c) - stream_base;
+                // the unit's header: the cumulative sub-block counts (4 slots, never straddles a page: pages and units start
+                // at multiples of 8 slots)
+                ensure_page(pos / kWListPage);
+                const uint32_t hw = lane < 8u ? reinterpret_cast<const uint32_t*>(slot_addr(pos))[lane] : 0u;
+                const uint32_t ebase = pos + kWHeaderSlots;
+                const uint32_t total = __shfl_sync(0xffffffffu, hw, kWUSB - 1);
                 mbar_wait(&tail->tmem_full[acc], acc_phase, p.error_flag, 16);
                 tc_fence_after();
                 if (ew == 0 && it < 2) WTRACE(10 + 2 * it);   // accumulators of tile 0 / 1 complete
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint32_t e0 = eoff[c], e1 = eoff[c + 1];
+                const bool ctr = p.trace && ew == 0 && it == 1 && lane == 0;   // cycle stamps of tile 1's sub-blocks (slots 16..31)
+#define CTRACE(slot) do { if (ctr) p.trace[(size_t)blockIdx.x * 32 + (slot)] = (unsigned long long)clock64(); } while (0)
+                // not unrolled: eight copies of this body are ~50 KB of SASS, and eight warps walking different copies kept
+                // missing the instruction cache (the body took >1000 cycles per sub-block, measured)
+                uint32_t e1 = ebase;
+#pragma unroll 1
+                for (uint32_t c = 0; c < (uint32_t)kWUSB; ++c) {
+                    const uint32_t e0 = e1;
+                    e1 = ebase + __shfl_sync(0xffffffffu, hw, c);
                     if (e0 == e1 || (p.debug & 4u)) continue;
+                    if (c < 4) CTRACE(16 + 4 * c);
+                    // the first (up to) 64 entries of the sub-block are requested BEFORE the accumulator is staged: every step
+                    // of this chain (LDTM, STS, LDS.64, LDS, STG) has ~100 cycles of latency under load, and the entry fetch
+                    // does not depend on the staging image
+                    const uint32_t pg0 = e0 / kWListPage;
+                    ensure_page(pg0);
+                    const uint32_t pend0 = (pg0 + 1) * kWListPage;
+                    uint32_t seg0 = e1 < pend0 ? e1 : pend0;
+                    if (seg0 > e0 + 128u) seg0 = e0 + 128u;
+                    uint2 en0[4];
+                    {
+                        const uint2* lent = reinterpret_cast<const uint2*>(slot_addr(pg0 * kWListPage)) - (size_t)pg0 * kWListPage;   // lent[e] = slot e
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t ee = e0 + q * 32 + lane;
+                            en0[q] = lent[ee < seg0 ? ee : e0];
+                        }
+                    }
                     uint32_t v[32];
-                    const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * (SGP * kWSubRows) + col0 + c * 32u;
+                    const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * (SGP * kWSubRows) + col0 + c * kWSbRows;
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -354,43 +430,59 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                         : "r"(taddr));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (c < 4) CTRACE(17 + 4 * c);
                     // staging image [column = lane][row]: thread writes the 32 rows of its column
                     uint4* srow = reinterpret_cast<uint4*>(stg + lane * kWEpiRowWords);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) srow[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     __syncwarp();
-                    // the chunk's entries, page by page, four groups of 32 entries at a time
-                    for (uint32_t e = e0; e < e1;) {
+                    if (c < 4) CTRACE(18 + 4 * c);
+                    {
+                        float val[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            val[q] = (p.debug & 128u) ? __uint_as_float(en0[q].x) : *reinterpret_cast<const float*>(stg_bytes + en0[q].x);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (e0 + q * 32 + lane < seg0 && !(p.debug & 64u)) p.P[en0[q].y] = val[q];
+                    }
+                    // the rest of a long list (more than 128 entries, or a page boundary inside the first 128)
+                    for (uint32_t e = seg0; e < e1;) {
                         const uint32_t pg = e / kWListPage;
                         ensure_page(pg);
                         const uint32_t pend = (pg + 1) * kWListPage;
                         const uint32_t seg_end = e1 < pend ? e1 : pend;
-                        const uint2* lent = lpage + (pg & 1u) * kWListPage - (size_t)pg * kWListPage;   // lent[e] = entry e of the stream
-                        for (uint32_t eb = e; eb < seg_end; eb += 128) {
-                            uint2 en[4];
-                            float val[4];
+                        const uint2* lent = reinterpret_cast<const uint2*>(slot_addr(pg * kWListPage)) - (size_t)pg * kWListPage;
+                        for (uint32_t eb = e; eb < seg_end; eb += 64) {
+                            uint2 en[2];
+                            float val[2];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
+                            for (int q = 0; q < 2; ++q) {
                                 const uint32_t ee = eb + q * 32 + lane;
                                 en[q] = lent[ee < seg_end ? ee : e];
                             }
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) val[q] = *reinterpret_cast<const float*>(stg_bytes + en[q].x);
+                            for (int q = 0; q < 2; ++q)
+                                val[q] = (p.debug & 128u) ? __uint_as_float(en[q].x) : *reinterpret_cast<const float*>(stg_bytes + en[q].x);
 #pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                if (eb + q * 32 + lane < seg_end) p.P[en[q].y] = val[q];
+                            for (int q = 0; q < 2; ++q)
+                                if (eb + q * 32 + lane < seg_end && !(p.debug & 64u)) p.P[en[q].y] = val[q];
                         }
                         e = seg_end;
                     }
                     __syncwarp();
+                    if (c < 4) CTRACE(19 + 4 * c);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
                 if (ew == 0 && it < 2) WTRACE(11 + 2 * it);   // epilogue of tile 0 / 1 done
+                pos += (kWHeaderSlots + total + 7u) & ~7u;
             }
+            // every page that was requested must have landed before the ring is reused or the CTA exits
+            for (uint32_t pg = cur_page; pg < npages && pg < cur_page + (uint32_t)kWListPages; ++pg) wait_page(pg);
+            gp_base += npages;
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (ew == 0) WTRACE(14);                   // epilogue done
     }
 
@@ -494,6 +586,9 @@ int launch_wide(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, f
     static const bool fp32_maps = std::getenv("BSMR_WIDE_FP32_MAPS") != nullptr;   // experiment: truncating operands
     BSMR_TRY(make_row_gather_map(ctx, dA, plan->M, K, &map_a, !fp32_maps));
     BSMR_TRY(make_row_gather_map(ctx, dB, plan->N, K, &map_b, !fp32_maps));
+    CUtensorMap map_b32, map_b128;    // tiled loads of 32 / 128 consecutive columns of B
+    BSMR_TRY(make_row_gather_map(ctx, dB, plan->N, K, &map_b32, !fp32_maps, 32));
+    BSMR_TRY(make_row_gather_map(ctx, dB, plan->N, K, &map_b128, !fp32_maps, 128));
     WideParams p{};
     p.K = K; p.kchunks = kchunks; p.stages = stages; p.sgp = sgp;
     p.num_rows = static_cast<uint32_t>(plan->h_reordered_rows.size());
@@ -516,7 +611,7 @@ int launch_wide(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, f
         return BSMR_ERR_BAD_STATE;
     }
     const uint32_t grid = plan->w_grid;   // one CTA per SM
-    wide_sddmm_kernel<<<grid, kWThreads, smem, stream>>>(map_a, map_b, p);
+    wide_sddmm_kernel<<<grid, kWThreads, smem, stream>>>(map_a, map_b, map_b32, map_b128, p);
     ctx->launches++;
     BSMR_CUDA_OK(cudaGetLastError());
     return BSMR_OK;

@@ -48,13 +48,13 @@ def main():
         col = rel[:, i]
         print("%-10s min %6.2f  med %6.2f  max %6.2f us" % (n, np.nanmin(col), np.nanmedian(col), np.nanmax(col)))
     c = raw[used][:, 16:32].astype(np.float64)
-    ok = c[:, 0] > 0
+    ok = (c > 0).all(axis=1)
     c = c[ok]
-    lab = ["ldtm", "sts", "gather", "next"]
-    for j in range(3):
+    print("cycle stamps of tile 1 (epilogue warp 8), %d CTAs whose first four sub-blocks all have entries:" % len(c))
+    for j in range(4):
         d = [np.median(c[:, j * 4 + k + 1] - c[:, j * 4 + k]) for k in range(3)]
-        nxt = np.median(c[:, (j + 1) * 4] - c[:, j * 4 + 3]) if j < 2 else float("nan")
-        print("tile 1 chunk %d cycles: ldtm+wait %.0f  sts+sync %.0f  gather %.0f  to next chunk %.0f" % (j, d[0], d[1], d[2], nxt))
+        nxt = np.median(c[:, (j + 1) * 4] - c[:, j * 4 + 3]) if j < 3 else float("nan")
+        print("sub-block %d cycles: tcgen05.ld+wait %.0f  sts+syncwarp %.0f  entries %.0f  to next chunk %.0f" % (j, d[0], d[1], d[2], nxt))
 
 
 if __name__ == "__main__":
