@@ -195,9 +195,12 @@ def main():
     t0 = time.perf_counter()
     plan.reorder(ALPHA, DELTA)                     # block_size from calculateBlockSize, reference_compat reduction
     reorder_wall_ms = (time.perf_counter() - t0) * 1e3          # first call of the process: module load + allocations
-    t0 = time.perf_counter()
-    plan.reorder(ALPHA, DELTA)
-    reorder_warm_ms = (time.perf_counter() - t0) * 1e3          # scratch arena and plan buffers in place
+    reorder_warm_ms = None
+    for _ in range(3):                                          # the scratch arena settles at its high-water mark on the 2nd call
+        t0 = time.perf_counter()
+        plan.reorder(ALPHA, DELTA)
+        dt = (time.perf_counter() - t0) * 1e3
+        reorder_warm_ms = dt if reorder_warm_ms is None else min(reorder_warm_ms, dt)
     info = plan.info()
     shard_nnz = nnz
     if world > 1:
