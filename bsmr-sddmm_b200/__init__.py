@@ -105,6 +105,10 @@ def lib():
         L.bsmr_sddmm_host_wait.argtypes = [vp, C.c_uint64]
         L.bsmr_sddmm_batch.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint32, f32p]
         L.bsmr_sddmm_host_batch.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint32, f32p]
+        L.bsmr_plan_fingerprint.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.bsmr_plan_execution_choice.argtypes = [vp, C.c_uint32, u32p]
+        L.bsmr_plan_save_row_order.argtypes = [vp, C.c_char_p, C.c_float, C.c_uint32]
+        L.bsmr_plan_load_row_order.argtypes = [vp, C.c_char_p, C.c_float, C.c_uint32]
         L.bsmr_sddmm_profile.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_uint32, f32p, f32p]
         L.bsmr_sddmm_profile3.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_uint32, f32p, f32p, f32p]
         L.bsmr_plan_set_wide_ratio.argtypes = [vp, C.c_float]
@@ -116,6 +120,7 @@ def lib():
                      "bsmr_plan_vector_size", "bsmr_plan_vector_copy", "bsmr_plan_get_info", "bsmr_plan_set_shard",
                      "bsmr_sddmm", "bsmr_sddmm_host", "bsmr_sddmm_profile", "bsmr_sddmm_profile3",
                      "bsmr_sddmm_host_submit", "bsmr_sddmm_host_wait", "bsmr_sddmm_batch", "bsmr_sddmm_host_batch",
+                     "bsmr_plan_fingerprint", "bsmr_plan_save_row_order", "bsmr_plan_load_row_order", "bsmr_plan_execution_choice",
                      "bsmr_plan_set_wide_ratio", "bsmr_plan_evaluate"):
             getattr(L, name).restype = C.c_int
         _lib = L
@@ -270,6 +275,25 @@ class Plan:
         _check(lib().bsmr_sddmm_host(self._h, K, _ptr(hA), _ptr(hB), _ptr(hP), iterations, flags, C.byref(ms),
                                      C.byref(tot)))
         return hP, ms.value, tot.value
+
+    def execution_choice(self, K):
+        """SDDMM flags the default call settled on for this K (0 = three-kernel plan, NO_WIDE, NO_REORDER)."""
+        f = C.c_uint32(0)
+        _check(lib().bsmr_plan_execution_choice(self._h, K, C.byref(f)))
+        return f.value
+
+    def fingerprint(self):
+        """64-bit fingerprint of the sparsity pattern (key of the reorder cache)."""
+        h = C.c_uint64(0)
+        _check(lib().bsmr_plan_fingerprint(self._h, C.byref(h)))
+        return h.value
+
+    def save_row_order(self, path, alpha, flags=ROW_REFERENCE_COMPAT):
+        _check(lib().bsmr_plan_save_row_order(self._h, os.fsencode(path), alpha, flags))
+
+    def load_row_order(self, path, alpha, flags=ROW_REFERENCE_COMPAT):
+        """Install a saved row order (same pattern, alpha and flags, else BsmrError); then call col_reorder(delta)."""
+        _check(lib().bsmr_plan_load_row_order(self._h, os.fsencode(path), alpha, flags))
 
     def sddmm_host_submit(self, K, hA, hB, hP, flags=SDDMM_DEFAULT):
         """Pipelined host-data call (pinned host buffers): queues H2D -> kernels -> D2H and returns a ticket."""

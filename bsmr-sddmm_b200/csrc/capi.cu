@@ -3,6 +3,8 @@
 // rowreorder.cu.  Nothing here falls back to the CPU: without a device every call fails.
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -291,6 +293,7 @@ int bsmr_plan_col_reorder(bsmr_plan* plan, float delta) {
     BSMR_CUDA_OK(cudaSetDevice(plan->ctx->device));
     BSMR_TRY(col_reorder_and_format(plan, delta));
     plan->have_cols = plan->have_format = true;
+    plan->auto_flags.clear();
     reset_shard(plan);
     return BSMR_OK;
 }
@@ -298,6 +301,128 @@ int bsmr_plan_col_reorder(bsmr_plan* plan, float delta) {
 int bsmr_plan_reorder(bsmr_plan* plan, float alpha, float delta, uint32_t block_size, uint32_t flags) {
     BSMR_TRY(bsmr_plan_row_reorder(plan, alpha, block_size, flags));
     return bsmr_plan_col_reorder(plan, delta);
+}
+
+// ---- reorder cache ---------------------------------------------------
+// The row order is the expensive part of BSMR (the clustering chain: 20 ms on nips, seconds on 100 k rows) and it
+// depends only on the sparsity pattern, alpha, the block size and the reduction mode.  The reference recomputes it on
+// every run (src/sddmm.cu:10-39; sddmm_testMode only reuses it across deltas, :70-89).  Here it can be written to a
+// file keyed by a fingerprint of the pattern and read back into a plan of the same pattern; the column reorder and the
+// device format (about a millisecond) are then rebuilt from it.
+}  // extern "C"
+namespace {
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {   // splitmix64 finaliser
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27; x *= 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+// order-independent fingerprint: sum over i of mix(seed, i, a[i])
+__global__ void fingerprint_kernel(const uint32_t* __restrict__ a, uint64_t n, unsigned long long seed, unsigned long long* __restrict__ out) {
+    unsigned long long h = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        h += mix64(seed + i * 0x9E3779B97F4A7C15ull + a[i]);
+    for (int w = 16; w >= 1; w >>= 1) h += __shfl_xor_sync(0xffffffffu, h, w);
+    if ((threadIdx.x & 31) == 0 && h) atomicAdd(out, h);
+}
+struct ReorderFileHeader {
+    char magic[8];                 // "BSMRRO01"
+    uint32_t M, N, nnz, block_size;
+    uint64_t fingerprint;
+    float alpha;
+    uint32_t flags;
+    int32_t num_clusters, num_clusters_true;
+    uint32_t num_rows, reserved;
+};
+int pattern_fingerprint(bsmr_plan* p, uint64_t* out) {
+    bsmr_ctx* ctx = p->ctx;
+    DevBuf<unsigned long long> acc;
+    BSMR_TRY(acc.alloc(1));
+    BSMR_CUDA_OK(cudaMemsetAsync(acc.ptr, 0, 8, ctx->stream));
+    const int grid = ctx->sm_count * 4;
+    fingerprint_kernel<<<grid, 256, 0, ctx->stream>>>(p->row_offsets.ptr, static_cast<uint64_t>(p->M) + 1, 0x1234567ull, acc.ptr);
+    if (p->nnz) fingerprint_kernel<<<grid, 256, 0, ctx->stream>>>(p->col_indices.ptr, p->nnz, 0x89abcdefull, acc.ptr);
+    ctx->launches += 2;
+    unsigned long long h = 0;
+    BSMR_CUDA_OK(cudaMemcpyAsync(&h, acc.ptr, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    BSMR_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    *out = h ^ (static_cast<uint64_t>(p->M) << 40) ^ (static_cast<uint64_t>(p->N) << 20) ^ p->nnz;
+    return BSMR_OK;
+}
+}  // namespace
+extern "C" {
+
+int bsmr_plan_fingerprint(bsmr_plan* plan, uint64_t* fingerprint) {
+    if (!plan || !fingerprint) return BSMR_ERR_INVALID_ARGUMENT;
+    BSMR_CUDA_OK(cudaSetDevice(plan->ctx->device));
+    return pattern_fingerprint(plan, fingerprint);
+}
+
+int bsmr_plan_save_row_order(bsmr_plan* plan, const char* path, float alpha, uint32_t flags) {
+    if (!plan || !path) return BSMR_ERR_INVALID_ARGUMENT;
+    if (!plan->have_rows) {
+        set_error("bsmr_plan_save_row_order: the plan has no row order yet");
+        return BSMR_ERR_BAD_STATE;
+    }
+    BSMR_CUDA_OK(cudaSetDevice(plan->ctx->device));
+    ReorderFileHeader h{};
+    std::memcpy(h.magic, "BSMRRO01", 8);
+    h.M = plan->M; h.N = plan->N; h.nnz = plan->nnz; h.block_size = plan->block_size;
+    BSMR_TRY(pattern_fingerprint(plan, &h.fingerprint));
+    h.alpha = alpha; h.flags = flags;
+    h.num_clusters = plan->num_clusters; h.num_clusters_true = plan->num_clusters_true;
+    h.num_rows = static_cast<uint32_t>(plan->h_reordered_rows.size());
+    FILE* f = std::fopen(path, "wb");
+    if (!f) {
+        set_error("bsmr_plan_save_row_order: cannot open %s for writing", path);
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    const bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 &&
+                    (h.num_rows == 0 || std::fwrite(plan->h_reordered_rows.data(), 4, h.num_rows, f) == h.num_rows);
+    if (std::fclose(f) != 0 || !ok) {
+        set_error("bsmr_plan_save_row_order: short write to %s", path);
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    return BSMR_OK;
+}
+
+int bsmr_plan_load_row_order(bsmr_plan* plan, const char* path, float alpha, uint32_t flags) {
+    if (!plan || !path) return BSMR_ERR_INVALID_ARGUMENT;
+    BSMR_CUDA_OK(cudaSetDevice(plan->ctx->device));
+    FILE* f = std::fopen(path, "rb");
+    if (!f) {
+        set_error("bsmr_plan_load_row_order: cannot open %s", path);
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    ReorderFileHeader h{};
+    std::vector<uint32_t> rows;
+    bool ok = std::fread(&h, sizeof(h), 1, f) == 1 && std::memcmp(h.magic, "BSMRRO01", 8) == 0 && h.num_rows <= plan->M;
+    if (ok) {
+        rows.resize(h.num_rows);
+        ok = h.num_rows == 0 || std::fread(rows.data(), 4, h.num_rows, f) == h.num_rows;
+    }
+    std::fclose(f);
+    if (!ok) {
+        set_error("bsmr_plan_load_row_order: %s is not a row-order file of this library (or is truncated)", path);
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    uint64_t fp = 0;
+    BSMR_TRY(pattern_fingerprint(plan, &fp));
+    if (h.M != plan->M || h.N != plan->N || h.nnz != plan->nnz || h.fingerprint != fp) {
+        set_error("bsmr_plan_load_row_order: %s was computed for another sparsity pattern (%u x %u, nnz %u, fingerprint %016llx; "
+                  "this plan: %u x %u, nnz %u, %016llx)", path, h.M, h.N, h.nnz, (unsigned long long)h.fingerprint, plan->M, plan->N,
+                  plan->nnz, (unsigned long long)fp);
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    if (h.alpha != alpha || h.flags != flags) {
+        set_error("bsmr_plan_load_row_order: %s holds the order for alpha = %g, flags = %u, not alpha = %g, flags = %u", path, h.alpha,
+                  h.flags, alpha, flags);
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    BSMR_TRY(bsmr_plan_set_row_order(plan, rows.data(), h.num_rows));
+    plan->block_size = h.block_size;
+    plan->num_clusters = h.num_clusters;
+    plan->num_clusters_true = h.num_clusters_true;
+    return BSMR_OK;
 }
 
 // ---- accessors -----------------------------------------------------------------------
@@ -492,6 +617,7 @@ int bsmr_plan_set_shard(bsmr_plan* plan, uint32_t rank, uint32_t world, uint32_t
     }
     if (e < b) e = b;
     plan->sharded = world > 1;
+    plan->auto_flags.clear();   // the execution plan is chosen again for the shard
     plan->shard_first_panel = b;
     plan->shard_end_panel = e;
     plan->shard_res_begin = plan->h_sparse_value_offsets.empty() ? 0 : plan->h_sparse_value_offsets[b];
@@ -595,6 +721,37 @@ int bsmr_sddmm(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, fl
     BSMR_CUDA_OK(cudaSetDevice(ctx->device));
     if (ms_per_iteration) *ms_per_iteration = 0.f;
     if (plan->nnz == 0) return BSMR_OK;
+    // Execution plan per K, chosen by measurement on the first default call with that K: the three-kernel plan (wide
+    // groups + BSMR split), the BSMR split alone, or -- unsharded only -- the CSR-order residual kernel.  Which one wins
+    // depends on K as much as on the pattern (nips: CSR order at K = 32, the wide plan at K = 128); all of them
+    // compute the same P.  Two passes each, best of the second; the choice is kept with the plan's format.
+    if (flags == BSMR_SDDMM_DEFAULT && plan->have_format) {
+        auto it = plan->auto_flags.find(K);
+        if (it == plan->auto_flags.end()) {
+            static const bool no_auto = std::getenv("BSMR_NO_AUTOTUNE") != nullptr;
+            uint32_t best = BSMR_SDDMM_DEFAULT;
+            if (!no_auto) {
+                std::vector<uint32_t> cand{BSMR_SDDMM_DEFAULT};
+                if (plan->num_wide_tiles != 0 && wide_supports(K, dA, dB)) cand.push_back(BSMR_SDDMM_NO_WIDE);
+                if (!plan->sharded) cand.push_back(BSMR_SDDMM_NO_REORDER);
+                float best_ms = 0.f;
+                for (uint32_t f : cand) {
+                    if (f & BSMR_SDDMM_NO_REORDER) BSMR_TRY(ensure_identity_rows(plan));
+                    float ms = 0.f;
+                    for (int rep = 0; rep < 2; ++rep) {
+                        BSMR_CUDA_OK(cudaEventRecord(ctx->ev0, ctx->stream));
+                        BSMR_TRY(run_once(plan, K, dA, dB, dP, f));
+                        BSMR_CUDA_OK(cudaEventRecord(ctx->ev1, ctx->stream));
+                        BSMR_CUDA_OK(cudaEventSynchronize(ctx->ev1));
+                        BSMR_CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+                    }
+                    if (f == cand[0] || ms < best_ms) { best_ms = ms; best = f; }
+                }
+            }
+            it = plan->auto_flags.emplace(K, best).first;
+        }
+        flags = it->second;
+    }
     if (flags & BSMR_SDDMM_NO_REORDER) BSMR_TRY(ensure_identity_rows(plan));
     if (iterations <= 0) iterations = 1;
     if (ms_per_iteration) BSMR_CUDA_OK(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -606,6 +763,17 @@ int bsmr_sddmm(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, fl
         BSMR_CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         *ms_per_iteration = ms / static_cast<float>(iterations);
     }
+    return BSMR_OK;
+}
+
+int bsmr_plan_execution_choice(bsmr_plan* plan, uint32_t K, uint32_t* flags) {
+    if (!plan || !flags) return BSMR_ERR_INVALID_ARGUMENT;
+    auto it = plan->auto_flags.find(K);
+    if (it == plan->auto_flags.end()) {
+        set_error("bsmr_plan_execution_choice: no default SDDMM call with K = %u yet", K);
+        return BSMR_ERR_BAD_STATE;
+    }
+    *flags = it->second;
     return BSMR_OK;
 }
 

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -240,6 +241,9 @@ struct bsmr_plan {
     uint64_t num_res2 = 0;
     std::vector<uint64_t> h_rr2_group_off;    // per row group (+1): first entry of the group in rr2
     uint64_t num_block_values2 = 0;           // nnz of the dense-block tiles outside the wide groups
+
+    // ---- execution plan chosen per K on the first default SDDMM call (capi.cu: bsmr_sddmm) ----
+    std::map<uint32_t, uint32_t> auto_flags;
 
     // ---- identity ("no reorder") residual list, built lazily ----
     bsmr::DevBuf<uint32_t> csr_row_of_nnz;

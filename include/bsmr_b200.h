@@ -155,6 +155,16 @@ typedef struct {
 } bsmr_plan_info;
 int bsmr_plan_get_info(bsmr_plan* plan, bsmr_plan_info* info);
 
+/* ---- reorder cache (no counterpart: the reference recomputes the row order on every run, src/sddmm.cu:10-39) ----
+ * The row order depends only on the sparsity pattern, alpha, the block size and the reduction mode.  _save writes
+ * it (with numClusters and a 64-bit fingerprint of the pattern) to a file; _load checks the fingerprint, alpha and
+ * flags against the plan and installs the order like bsmr_plan_set_row_order; the caller then runs
+ * bsmr_plan_col_reorder(delta), which rebuilds the column vectors and the device format (about a millisecond).
+ * alpha / flags are the values the order was (or would be) computed with by bsmr_plan_row_reorder.           */
+int bsmr_plan_fingerprint(bsmr_plan* plan, uint64_t* fingerprint);
+int bsmr_plan_save_row_order(bsmr_plan* plan, const char* path, float alpha, uint32_t flags);
+int bsmr_plan_load_row_order(bsmr_plan* plan, const char* path, float alpha, uint32_t flags);
+
 /* ---- multi-GPU sharding (no counterpart in the reference, which is single-GPU) --------
  * Restrict the plan to the rank-th of world nnz-balanced contiguous ranges of reordered
  * row panels.  SDDMM calls then compute (and write) only the nnz of that range.
@@ -182,6 +192,13 @@ int bsmr_sddmm(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, fl
  * total_ms (may be NULL) covers copies + kernels.                                        */
 int bsmr_sddmm_host(bsmr_plan* plan, uint32_t K, const float* hA, const float* hB, float* hP,
                     int iterations, uint32_t flags, float* ms_per_iteration, float* total_ms);
+
+/* A call with BSMR_SDDMM_DEFAULT runs, per K, the fastest of three execution plans over the same nnz, chosen by
+ * measurement on the first such call (two passes each; that first call therefore synchronises): the three-kernel
+ * plan (wide row groups + BSMR split), the BSMR split alone (= BSMR_SDDMM_NO_WIDE), or, on an unsharded plan, the
+ * CSR-order residual kernel (= BSMR_SDDMM_NO_REORDER).  The choice is forgotten at the next column reorder /
+ * set_shard; environment BSMR_NO_AUTOTUNE pins the three-kernel plan.  _execution_choice returns the flags chosen. */
+int bsmr_plan_execution_choice(bsmr_plan* plan, uint32_t K, uint32_t* flags);
 
 /* Pipelined form of the host-data overload: the same H2D A,B -> zero P -> kernels -> D2H P, but the call returns as
  * soon as the work is queued.  Successive calls alternate between two slots of device buffers and three streams

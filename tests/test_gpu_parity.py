@@ -337,6 +337,60 @@ def test_sddmm_batch(pkg, ctx, oracle, host):
         assert oracle.check_data(oracle.sddmm_cpu(M, N, K, A[b], B[b], ro, ci), P[b]) == 0
 
 
+def test_row_order_cache_roundtrip(pkg, ctx, oracle, tmp_path):
+    """Reorder cache: the saved row order installs into a fresh plan of the same pattern, gives the same
+    column vectors and the same P; a different pattern, alpha or mode is refused."""
+    import torch
+    M, N, ro, ci = pkg.synth.block_structured(1000, 2000, seed=11, groups=12, cols_per_group=64)
+    K = 64
+    A, B = pkg.synth.make_ab(M, N, K)
+    plan = pkg.Plan(ctx, M, N, ro, ci)
+    plan.reorder(0.3, 0.3, block_size=16)
+    path = str(tmp_path / "rows.bsmr")
+    plan.save_row_order(path, 0.3)
+    plan2 = pkg.Plan(ctx, M, N, ro, ci)
+    assert plan2.fingerprint() == plan.fingerprint()
+    plan2.load_row_order(path, 0.3)
+    plan2.col_reorder(0.3)
+    assert np.array_equal(plan2.vector("reordered_rows"), plan.vector("reordered_rows"))
+    for v in COL_VECS:
+        assert np.array_equal(plan2.vector(v), plan.vector(v)), v
+    assert plan2.info()["num_clusters"] == plan.info()["num_clusters"]
+    dA, dB = torch_dev(A), torch_dev(B)
+    p1, p2 = torch.zeros(len(ci), device="cuda"), torch.zeros(len(ci), device="cuda")
+    plan.sddmm(K, dA, dB, p1)
+    plan2.sddmm(K, dA, dB, p2)
+    torch.cuda.synchronize()
+    assert oracle.check_data(oracle.sddmm_cpu(M, N, K, A, B, ro, ci), p2.cpu().numpy()) == 0
+    assert torch.equal(p1, p2)
+    with pytest.raises(pkg.BsmrError):
+        plan2.load_row_order(path, 0.5)                      # other alpha
+    M3, N3, ro3, ci3 = pkg.synth.block_structured(1000, 2000, seed=12, groups=12, cols_per_group=64)
+    plan3 = pkg.Plan(ctx, M3, N3, ro3, ci3)
+    assert plan3.fingerprint() != plan.fingerprint()
+    with pytest.raises(pkg.BsmrError):
+        plan3.load_row_order(path, 0.3)                      # other pattern
+
+
+@pytest.mark.parametrize("K", [32, 128, 256])
+def test_execution_plan_choice_keeps_results(pkg, ctx, oracle, K):
+    """The default call picks one of three execution plans per K by measurement; every one of them gives P within
+    tolerance, and the choice made is one of the candidates."""
+    import torch
+    M, N, ro, ci = pkg.synth.nips_like()
+    A, B = pkg.synth.make_ab(M, N, K)
+    want = oracle.sddmm_cpu(M, N, K, A, B, ro, ci)
+    plan = pkg.Plan(ctx, M, N, ro, ci)
+    plan.reorder(0.3, 0.3, flags=pkg.ROW_IDENTITY)
+    dA, dB = torch_dev(A), torch_dev(B)
+    for flags in (pkg.SDDMM_DEFAULT, pkg.SDDMM_NO_WIDE, pkg.SDDMM_NO_REORDER, pkg.SDDMM_DEFAULT):
+        dP = torch.full((len(ci),), -5.0, device="cuda")
+        plan.sddmm(K, dA, dB, dP, flags=flags)
+        torch.cuda.synchronize()
+        assert oracle.check_data(want, dP.cpu().numpy()) == 0, (K, flags)
+    assert plan.execution_choice(K) in (pkg.SDDMM_DEFAULT, pkg.SDDMM_NO_WIDE, pkg.SDDMM_NO_REORDER)
+
+
 def test_sddmm_linearity_and_idempotence(pkg, ctx):
     """Size-independent properties: SDDMM is linear in A and repeated calls give identical bits."""
     import torch
