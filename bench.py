@@ -26,6 +26,15 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# stdout carries exactly one JSON line: everything else that libraries write to fd 1 while the bench runs (NCCL prints
+# its version banner there) goes to stderr; emit() puts the line on the real stdout
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
@@ -142,7 +151,7 @@ def run_reference(args, rank, world):
             "config": workload_config(M, N, len(ci), K, source, args.gpus),
             "cpu_baseline": {"value": gflops, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": gflops, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(M, N, nnz, K, source, gpus):
@@ -204,7 +213,8 @@ def main():
     info = plan.info()
     shard_nnz = nnz
     if world > 1:
-        _, _, shard_nnz = plan.set_shard(rank, world)
+        p0s, p1s, shard_nnz = plan.set_shard(rank, world)
+        shard_panels = (p0s, p1s)
 
     dA = torch.from_numpy(A).cuda()
     dB = torch.empty((N, K), dtype=torch.float32, device="cuda")
@@ -243,6 +253,7 @@ def main():
         step_timed(e0, e1)
     barrier()
     launches = ctx.launch_count() - launches0
+    exec_choice = plan.execution_choice(K)
     clocks = sampler.stop() if rank == 0 else None
     total_ms = float(sum(e0.elapsed_time(e1) for e0, e1 in events))
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
@@ -333,7 +344,7 @@ def main():
     sv = plan.vector("sparse_values")
     svo = plan.vector("sparse_value_offsets")
     gw = plan.vector("group_wide").astype(bool)
-    p0, p1 = (0, info["num_row_panels"]) if world == 1 else plan.set_shard(rank, world)[:2]
+    p0, p1 = (0, info["num_row_panels"]) if world == 1 else shard_panels
     row_of = np.repeat(np.arange(M, dtype=np.int64), np.diff(ro.astype(np.int64)))
     pos_of_row = np.full(M, -1, dtype=np.int64)
     pos_of_row[rows] = np.arange(len(rows))
@@ -420,10 +431,10 @@ def main():
                                  "wide_format_ms": info["wide_format_ms"]},
                         "gflops_incl_reorder": 2.0 * nnz * K / ((ms_per_step + reorder_warm_ms) * 1e-3) / 1e9},
             "execution_plan": {0: "wide row groups + BSMR split (three kernels)", 4: "BSMR split (dense blocks + residual)",
-                               2: "CSR-order residual kernel"}.get(plan.execution_choice(K), "?") + " (chosen by measurement per K)",
+                               2: "CSR-order residual kernel"}.get(exec_choice, "?") + " (chosen by measurement per K)",
             "kernels": {"wide_ms_cold": wide_ms, "dense_ms_cold": dense_ms, "residual_ms_cold": res_ms, "step_ms_hot_l2": hot_ms,
                         "gflops_hot_l2": 2.0 * shard_nnz * K / (hot_ms * 1e-3) / 1e9}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -560,10 +560,22 @@ int build_wide_format(bsmr_plan* plan, Workspace* ws, const uint64_t* ukeys, con
     std::vector<uint4> h_meta;
     uint32_t seg = 0, col_total = 0;
     uint64_t wide_values = 0;
+    // Second tier: when the groups that pass the bar already hold >= 90 % of the nnz, the few that remain would cost two
+    // more kernel launches (dense-block + residual, ~10 us each however little they do) next to the wide kernel, which
+    // owns every SM while it runs; they go wide too if they pass 40 % of the bar.
+    auto bar = [&](uint32_t i) {
+        const uint32_t tiles = (h_gncols[i] + kWideCols - 1) / kWideCols;
+        return static_cast<double>(ratio) * (static_cast<double>(kWideCols) * tiles + kWideRows);
+    };
+    uint64_t nnz_all = 0, nnz_pass = 0;
+    for (uint32_t i = 0; i < num_g; ++i) {
+        nnz_all += h_gnnz[i];
+        if (h_gid[i] < G && static_cast<double>(h_gnnz[i]) >= bar(i)) nnz_pass += h_gnnz[i];
+    }
+    const double tier = (nnz_all > 0 && static_cast<double>(nnz_pass) >= 0.9 * static_cast<double>(nnz_all)) ? 0.4 : 1.0;
     for (uint32_t i = 0; i < num_g; ++i) {
         const uint32_t g = h_gid[i], nc = h_gncols[i];
-        const uint32_t tiles = (nc + kWideCols - 1) / kWideCols;
-        if (g < G && static_cast<double>(h_gnnz[i]) >= static_cast<double>(ratio) * (static_cast<double>(kWideCols) * tiles + kWideRows)) {
+        if (g < G && static_cast<double>(h_gnnz[i]) >= tier * bar(i)) {
             plan->h_group_wide[g] = 1;
             col_total = (col_total + 3u) & ~3u;   // the kernel reads a tile's column ids four at a time (16-byte loads)
             wg_group.push_back(g); wg_seg.push_back(seg); wg_ncols.push_back(nc); wg_col_off.push_back(col_total);
