@@ -24,7 +24,7 @@ BLOCK_COL_SIZE = 16
 NULL_VALUE = 0xFFFFFFFF
 
 ROW_REFERENCE_COMPAT, ROW_EXACT_REDUCE, ROW_IDENTITY = 0, 1, 2
-SDDMM_DEFAULT, SDDMM_RESIDUAL_ONLY, SDDMM_NO_REORDER, SDDMM_NO_WIDE = 0, 1, 2, 4
+SDDMM_DEFAULT, SDDMM_RESIDUAL_ONLY, SDDMM_NO_REORDER, SDDMM_NO_WIDE, SDDMM_THREE_KERNEL = 0, 1, 2, 4, 8
 TICKET_ALL = 0xFFFFFFFFFFFFFFFF
 WIDE_GROUP_ROWS, WIDE_TILE_COLS = 256, 128
 

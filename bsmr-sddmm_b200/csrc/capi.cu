@@ -752,6 +752,7 @@ int bsmr_sddmm(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, fl
         }
         flags = it->second;
     }
+    flags &= ~BSMR_SDDMM_THREE_KERNEL;     // = the default plan, minus the choice above
     if (flags & BSMR_SDDMM_NO_REORDER) BSMR_TRY(ensure_identity_rows(plan));
     if (iterations <= 0) iterations = 1;
     if (ms_per_iteration) BSMR_CUDA_OK(cudaEventRecord(ctx->ev0, ctx->stream));

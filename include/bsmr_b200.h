@@ -183,6 +183,7 @@ int bsmr_plan_set_shard(bsmr_plan* plan, uint32_t rank, uint32_t world,
 #define BSMR_SDDMM_RESIDUAL_ONLY  1u   /* every nnz through the CUDA-core kernel (delta > 1) */
 #define BSMR_SDDMM_NO_REORDER     2u   /* ignore the plan's reorder: CSR order, residual kernel */
 #define BSMR_SDDMM_NO_WIDE        4u   /* dense-block + residual kernels only, exactly the reference's split */
+#define BSMR_SDDMM_THREE_KERNEL   8u   /* the three-kernel plan (wide groups + BSMR split) without the per-K choice below */
 int bsmr_sddmm(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP,
                int iterations, uint32_t flags, float* ms_per_iteration);
 

@@ -185,7 +185,7 @@ def test_sddmm_dense_plus_residual(pkg, ctx, oracle, K, delta, wide):
     execution plan, in which row groups that are dense at 128-row scale run through the wide tcgen05 kernel."""
     worst = 0.0
     for name, M, N, ro, ci in small_cases(pkg):
-        plan, A, B, got = run_sddmm(pkg, ctx, M, N, ro, ci, K, 0.3, delta, flags=0 if wide else pkg.SDDMM_NO_WIDE)
+        plan, A, B, got = run_sddmm(pkg, ctx, M, N, ro, ci, K, 0.3, delta, flags=pkg.SDDMM_THREE_KERNEL if wide else pkg.SDDMM_NO_WIDE)
         want = oracle.sddmm_cpu(M, N, K, A, B, ro, ci)
         bad = oracle.check_data(want, got)
         rel = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-3)))
@@ -221,7 +221,7 @@ def test_sddmm_wide_row_groups(pkg, ctx, oracle, K):
         if K != 128 and name in ("mask98",):
             continue
         # mask98 (2 % fill) sits just below the default policy (ratio 5): lower the bar so that very sparse tiles are covered
-        plan, A, B, got = run_sddmm(pkg, ctx, M, N, ro, ci, K, 0.3, 0.3, row_flags=pkg.ROW_IDENTITY,
+        plan, A, B, got = run_sddmm(pkg, ctx, M, N, ro, ci, K, 0.3, 0.3, row_flags=pkg.ROW_IDENTITY, flags=pkg.SDDMM_THREE_KERNEL,
                                     wide_ratio=2.0 if name == "mask98" else None)
         info = plan.info()
         assert info["num_wide_groups"] > 0, (name, info)
@@ -358,8 +358,8 @@ def test_row_order_cache_roundtrip(pkg, ctx, oracle, tmp_path):
     assert plan2.info()["num_clusters"] == plan.info()["num_clusters"]
     dA, dB = torch_dev(A), torch_dev(B)
     p1, p2 = torch.zeros(len(ci), device="cuda"), torch.zeros(len(ci), device="cuda")
-    plan.sddmm(K, dA, dB, p1)
-    plan2.sddmm(K, dA, dB, p2)
+    plan.sddmm(K, dA, dB, p1, flags=pkg.SDDMM_THREE_KERNEL)
+    plan2.sddmm(K, dA, dB, p2, flags=pkg.SDDMM_THREE_KERNEL)
     torch.cuda.synchronize()
     assert oracle.check_data(oracle.sddmm_cpu(M, N, K, A, B, ro, ci), p2.cpu().numpy()) == 0
     assert torch.equal(p1, p2)
@@ -383,12 +383,42 @@ def test_execution_plan_choice_keeps_results(pkg, ctx, oracle, K):
     plan = pkg.Plan(ctx, M, N, ro, ci)
     plan.reorder(0.3, 0.3, flags=pkg.ROW_IDENTITY)
     dA, dB = torch_dev(A), torch_dev(B)
-    for flags in (pkg.SDDMM_DEFAULT, pkg.SDDMM_NO_WIDE, pkg.SDDMM_NO_REORDER, pkg.SDDMM_DEFAULT):
+    for flags in (pkg.SDDMM_DEFAULT, pkg.SDDMM_THREE_KERNEL, pkg.SDDMM_NO_WIDE, pkg.SDDMM_NO_REORDER, pkg.SDDMM_DEFAULT):
         dP = torch.full((len(ci),), -5.0, device="cuda")
         plan.sddmm(K, dA, dB, dP, flags=flags)
         torch.cuda.synchronize()
         assert oracle.check_data(want, dP.cpu().numpy()) == 0, (K, flags)
     assert plan.execution_choice(K) in (pkg.SDDMM_DEFAULT, pkg.SDDMM_NO_WIDE, pkg.SDDMM_NO_REORDER)
+
+
+def test_edge_cases_empty_and_ragged(pkg, ctx, oracle):
+    """Empty pattern, all-empty rows around a few entries, one dense row, K that no tensor-core path takes."""
+    import torch
+    # nnz == 0
+    M, N = 40, 50
+    ro = np.zeros(M + 1, dtype=np.uint32)
+    ci = np.zeros(0, dtype=np.uint32)
+    plan = pkg.Plan(ctx, M, N, ro, ci)
+    plan.reorder(0.3, 0.3)
+    assert len(plan.vector("reordered_rows")) == 0 and plan.info()["num_row_panels"] == 0
+    A, B = pkg.synth.make_ab(M, N, 32)
+    plan.sddmm(32, torch_dev(A), torch_dev(B), torch.zeros(1, device="cuda"))
+    # three entries in a 1000 x 1000 matrix, and one full row on top of an empty matrix
+    cases = []
+    ro = np.zeros(1001, dtype=np.uint32)
+    ro[501:] = 1
+    ro[778:] = 3
+    cases.append(("three_entries", 1000, 1000, ro, np.array([999, 0, 512], dtype=np.uint32)))
+    ro = np.zeros(301, dtype=np.uint32)
+    ro[151:] = 700
+    cases.append(("one_full_row", 300, 700, ro, np.arange(700, dtype=np.uint32)))
+    for name, M, N, ro, ci in cases:
+        for K in (32, 128, 20, 5):
+            for flags in (pkg.SDDMM_DEFAULT, pkg.SDDMM_THREE_KERNEL, pkg.SDDMM_NO_WIDE, pkg.SDDMM_NO_REORDER):
+                plan, A, B, got = run_sddmm(pkg, ctx, M, N, ro, ci, K, 0.3, 0.3, flags=flags)
+                assert oracle.check_data(oracle.sddmm_cpu(M, N, K, A, B, ro, ci), got) == 0, (name, K, flags)
+                if not (flags & pkg.SDDMM_NO_REORDER):
+                    assert sorted(plan.vector("reordered_rows").tolist()) == nonempty_rows(ro).tolist()
 
 
 def test_sddmm_linearity_and_idempotence(pkg, ctx):
