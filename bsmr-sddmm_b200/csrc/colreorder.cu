@@ -41,7 +41,6 @@ constexpr uint32_t kWideCols = BSMR_WIDE_TILE_COLS;
 constexpr uint32_t kWQ = kWideRows / 32;                       // 32-row quarters per tile (sub-group x TMEM lane quarter)
 constexpr uint32_t kWW = kWideCols / 32;                       // mask words per (tile, row) = 32-column chunks of a tile
 constexpr uint32_t kWH = kWideCols >= 128 ? kWideCols / 128 : 1;   // run starts per (tile, row): one per 128 columns
-constexpr uint32_t kWideStageRowWords = kWideStagePitchWords;
 
 inline int grid_for(uint64_t n, int per_cta, int sm_count) {
     uint64_t g = (n + per_cta - 1) / per_cta;
@@ -311,7 +310,34 @@ __global__ void fill_wide_kernel(uint32_t num_wide, const uint32_t* __restrict__
 }
 
 // The wide kernel computes the TRANSPOSED tile (lanes = the tile's 128 columns, TMEM columns = the group's 256 rows).  An
-// epilogue warp owns 32 tile columns (TMEM lane quarter j) and one half h of the group's rows, and handles them as
+// epilogue warp owns 32 tile columns (TMEM lane quarter j) and one half h of the group's rows.  What it needs per row
+// of the tile is one pair {mask of the row's nnz among the warp's 32 columns, CSR position of the first of them}: a
+// row's entries inside a column quarter are consecutive CSR positions in ascending column order, so lane c stores
+// its accumulator to P[base + popc(mask & ((1 << c) - 1))] when bit c is set.  Unit u = (tile, j, h): 128 pairs = 1 KB;
+// the units one warp touches while it walks a range of tiles are contiguous: index ((j * 2 + h) * #tiles + tile).
+constexpr uint32_t kWideStageRowWords = kWideStagePitchWords;
+constexpr uint32_t kWUnitRows = kWideRows / 2;                  // 128
+constexpr uint32_t kWUnitsPerTile = kWW * 2;
+
+// W2b: the row-meta pairs; one thread per (tile, column quarter, row)
+__global__ void wide_rowmeta_kernel(uint32_t wtiles, const uint32_t* __restrict__ mask, const uint32_t* __restrict__ base,
+                                    uint2* __restrict__ meta) {
+    const uint64_t total = (uint64_t)wtiles * kWW * kWideRows;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t row = (uint32_t)(i % kWideRows), j = (uint32_t)(i / kWideRows) % kWW, t = (uint32_t)(i / ((uint64_t)kWideRows * kWW));
+        const uint32_t m = mask[((size_t)t * kWW + j) * kWideRows + row];
+        uint32_t k = 0;
+        if (m) {
+            k = base[((size_t)t * kWH + (j >> 2)) * kWideRows + row];
+            for (uint32_t jj = j & ~3u; jj < j; ++jj) k += __popc(mask[((size_t)t * kWW + jj) * kWideRows + row]);
+        }
+        const uint32_t h = row / kWUnitRows;
+        meta[(((size_t)(j * 2 + h) * wtiles + t) * kWUnitRows) + row % kWUnitRows] = make_uint2(m, k);
+    }
+}
+
+// ---- list form of the epilogue's work (sparse tiles) ----
+// An epilogue warp owns 32 tile columns (TMEM lane quarter j) and one half h of the group's rows, and handles them as
 // kWUSB sub-blocks of 32 columns x 16 rows.  Unit u = (tile * kWW + j) * 2 + h; sub-block sbi = u * kWUSB + s.
 // The work lists are laid out by (j, h, tile): everything one epilogue warp consumes while it walks a range of tiles is
 // one contiguous stream of 8-byte slots, which it pages through shared memory with bulk copies.  A unit's list is
@@ -321,7 +347,6 @@ __global__ void fill_wide_kernel(uint32_t num_wide, const uint32_t* __restrict__
 constexpr uint32_t kWSbRows = kWideSbRows;
 constexpr uint32_t kWSbPerQ = 32 / kWSbRows;                    // sub-blocks per 32-row quarter
 constexpr uint32_t kWUSB = (kWideRows / 2) / kWSbRows;          // sub-blocks per unit: 8
-constexpr uint32_t kWUnitsPerTile = kWW * 2;
 constexpr uint32_t kWHeaderSlots = 4;
 __host__ __device__ inline uint64_t wide_unit_stream_index(uint64_t u, uint32_t wtiles) {
     return (u % kWUnitsPerTile) * wtiles + u / kWUnitsPerTile;
@@ -612,27 +637,40 @@ int build_wide_format(bsmr_plan* plan, Workspace* ws, const uint64_t* ukeys, con
         num_wide, d_wg_group.ptr, d_wg_col_off.ptr, d_wg_ncols.ptr, d_wg_tile_off.ptr, plan->reordered_rows.ptr, R,
         plan->row_offsets.ptr, plan->col_indices.ptr, plan->w_cols.ptr, plan->w_mask.ptr, plan->w_base.ptr, d_unsorted.ptr);
     ctx->launches += 2;
-    // the epilogue's work lists (64 sub-blocks of 32 columns x 16 rows per tile, 8 units per tile)
-    const uint32_t num_q = wtiles * kWQ * kWW;                 // (tile, column quarter, 32-row quarter)
-    const uint32_t num_units = wtiles * kWUnitsPerTile;
-    TmpBuf<uint32_t> sb_cnt(ws), u_tot(ws);
-    BSMR_TRY(sb_cnt.alloc(static_cast<size_t>(num_q) * kWSbPerQ));
-    BSMR_TRY(u_tot.alloc(static_cast<size_t>(num_units) + 1));
-    // w_sb_off[stream index of the unit] = first slot of the unit's list (+1 entry: the end); a unit takes 4 header
-    // slots + its entries, padded to 8
-    BSMR_TRY(plan->w_sb_off.alloc(static_cast<size_t>(num_units) + 1));
-    const size_t list_cap = static_cast<size_t>(wide_values) + (kWHeaderSlots + 8u) * num_units + 64;
-    BSMR_TRY(plan->w_entries.alloc(list_cap));
-    BSMR_CUDA_OK(cudaMemsetAsync(plan->w_entries.ptr, 0, plan->w_entries.bytes(), st));
-    BSMR_CUDA_OK(cudaMemsetAsync(u_tot.ptr + num_units, 0, 4, st));
-    wide_subblock_count_kernel<<<grid_for((uint64_t)num_q * 32, kThreads, sm), kThreads, 0, st>>>(num_q, plan->w_mask.ptr, sb_cnt.ptr);
-    wide_unit_totals_kernel<<<grid_for(num_units, kThreads, sm), kThreads, 0, st>>>(num_units, wtiles, sb_cnt.ptr, u_tot.ptr);
-    BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb, u_tot.ptr, plan->w_sb_off.ptr, static_cast<size_t>(num_units) + 1, st));
-    BSMR_TRY(ensure_temp(tb));
-    BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(temp.ptr, tb, u_tot.ptr, plan->w_sb_off.ptr, static_cast<size_t>(num_units) + 1, st));
-    wide_unit_header_kernel<<<grid_for(num_units, kThreads, sm), kThreads, 0, st>>>(num_units, wtiles, sb_cnt.ptr, plan->w_sb_off.ptr, plan->w_entries.ptr);
-    wide_subblock_fill_kernel<<<grid_for((uint64_t)num_q * 32, kThreads, sm), kThreads, 0, st>>>(
-        num_q, wtiles, plan->w_mask.ptr, plan->w_base.ptr, sb_cnt.ptr, plan->w_sb_off.ptr, plan->w_entries.ptr);
+    // Two forms of the epilogue's work (wide_tc.cu): per-entry lists for sparse tiles (instruction count follows the nnz;
+    // 2.5 us per 128 x 256 tile at 4 % fill against 3.2 us for the mask form), row masks for dense ones (cost per tile
+    // independent of the fill, stores of a row coalesce: 30 % fill runs 1.6x faster than through lists).
+    const double fill = static_cast<double>(wide_values) / (static_cast<double>(wtiles) * kWideCols * kWideRows);
+    static const char* force_form = std::getenv("BSMR_WIDE_EPILOGUE");      // "mask" / "list": experiments
+    plan->wide_mask_epilogue = force_form ? std::string(force_form) == "mask" : fill >= 0.08;
+    if (plan->wide_mask_epilogue) {
+        // row-meta pairs (8 units of 128 pairs per tile)
+        BSMR_TRY(plan->w_entries.alloc(static_cast<size_t>(wtiles) * kWUnitsPerTile * kWUnitRows));
+        wide_rowmeta_kernel<<<grid_for((uint64_t)wtiles * kWW * kWideRows, kThreads, sm), kThreads, 0, st>>>(
+            wtiles, plan->w_mask.ptr, plan->w_base.ptr, plan->w_entries.ptr);
+    } else {
+        // the epilogue's work lists (64 sub-blocks of 32 columns x 16 rows per tile, 8 units per tile)
+        const uint32_t num_q = wtiles * kWQ * kWW;                 // (tile, column quarter, 32-row quarter)
+        const uint32_t num_units = wtiles * kWUnitsPerTile;
+        TmpBuf<uint32_t> sb_cnt(ws), u_tot(ws);
+        BSMR_TRY(sb_cnt.alloc(static_cast<size_t>(num_q) * kWSbPerQ));
+        BSMR_TRY(u_tot.alloc(static_cast<size_t>(num_units) + 1));
+        // w_sb_off[stream index of the unit] = first slot of the unit's list (+1 entry: the end); a unit takes 4 header
+        // slots + its entries, padded to 8
+        BSMR_TRY(plan->w_sb_off.alloc(static_cast<size_t>(num_units) + 1));
+        const size_t list_cap = static_cast<size_t>(wide_values) + (kWHeaderSlots + 8u) * num_units + 64;
+        BSMR_TRY(plan->w_entries.alloc(list_cap));
+        BSMR_CUDA_OK(cudaMemsetAsync(plan->w_entries.ptr, 0, plan->w_entries.bytes(), st));
+        BSMR_CUDA_OK(cudaMemsetAsync(u_tot.ptr + num_units, 0, 4, st));
+        wide_subblock_count_kernel<<<grid_for((uint64_t)num_q * 32, kThreads, sm), kThreads, 0, st>>>(num_q, plan->w_mask.ptr, sb_cnt.ptr);
+        wide_unit_totals_kernel<<<grid_for(num_units, kThreads, sm), kThreads, 0, st>>>(num_units, wtiles, sb_cnt.ptr, u_tot.ptr);
+        BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb, u_tot.ptr, plan->w_sb_off.ptr, static_cast<size_t>(num_units) + 1, st));
+        BSMR_TRY(ensure_temp(tb));
+        BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(temp.ptr, tb, u_tot.ptr, plan->w_sb_off.ptr, static_cast<size_t>(num_units) + 1, st));
+        wide_unit_header_kernel<<<grid_for(num_units, kThreads, sm), kThreads, 0, st>>>(num_units, wtiles, sb_cnt.ptr, plan->w_sb_off.ptr, plan->w_entries.ptr);
+        wide_subblock_fill_kernel<<<grid_for((uint64_t)num_q * 32, kThreads, sm), kThreads, 0, st>>>(
+            num_q, wtiles, plan->w_mask.ptr, plan->w_base.ptr, sb_cnt.ptr, plan->w_sb_off.ptr, plan->w_entries.ptr);
+    }
     ctx->launches += 2;
     ctx->launches += 3;
     uint32_t unsorted = 0;

@@ -18,10 +18,11 @@ constexpr uint32_t kPanel = BSMR_ROW_PANEL_SIZE;    // rows per row panel
 constexpr uint32_t kBlockCols = BSMR_BLOCK_COL_SIZE;  // columns per reference dense block
 constexpr uint32_t kTileCols = 128;                   // dense columns per tcgen05 tile (UMMA M)
 constexpr uint32_t kNull = BSMR_NULL_VALUE;
-// wide kernel epilogue (wide_tc.cu) <-> its work-list builder (colreorder.cu): a sub-block is 32 tile columns x
+// wide kernel epilogue, list form (wide_tc.cu) <-> its work-list builder (colreorder.cu): a sub-block is 32 tile columns x
 // kWideSbRows group rows; the staging image [column][row] has a pitch of kWideSbRows + 4 words (conflict-free STS.128)
 constexpr uint32_t kWideSbRows = 32;
 constexpr uint32_t kWideStagePitchWords = kWideSbRows + 4;
+
 
 // ---- error plumbing: every ABI function returns a status and records a message ---------
 void set_error(const char* fmt, ...);
@@ -226,10 +227,12 @@ struct bsmr_plan {
     bsmr::DevBuf<uint32_t> w_cols;            // distinct columns of the wide groups, ascending inside a group
     bsmr::DevBuf<uint32_t> w_mask;            // [tile][8][128]
     bsmr::DevBuf<uint32_t> w_base;            // [tile][2][128]
-    bsmr::DevBuf<uint32_t> w_sb_off;          // [(column quarter * 2 + row half) * #tiles + tile] (+1): first 8-byte slot of the
-                                              // unit's work list in w_entries (a multiple of 8)
-    bsmr::DevBuf<uint2> w_entries;            // per unit: 4 header slots (8 cumulative sub-block counts), then the entries
-                                              // {byte offset inside the epilogue's staging image, CSR position}, padded to 8 slots
+    bool wide_mask_epilogue = false;          // which form of the epilogue's work the format holds (colreorder.cu: by tile fill)
+    bsmr::DevBuf<uint2> w_entries;            // mask form: row-meta pairs [(column quarter * 2 + row half) * #tiles + tile][128 rows]:
+                                              //   {mask of the row's nnz among the quarter's 32 columns, CSR position of the first}
+                                              // list form: per unit 4 header slots (cumulative sub-block counts), then the entries
+                                              //   {byte offset inside the epilogue's staging image, CSR position}, padded to 8 slots
+    bsmr::DevBuf<uint32_t> w_sb_off;          // list form: [(column quarter * 2 + row half) * #tiles + tile] (+1): first slot of the unit
     std::vector<uint32_t> h_wt_group;         // row group of every wide tile
     bsmr::DevBuf<uint32_t> w_cta_begin;       // CTA -> first tile, for tiles [w_part_begin, w_part_end) (wide_partition)
     uint32_t w_part_begin = 0, w_part_end = 0, w_grid = 0;

@@ -56,6 +56,7 @@ constexpr int kWMaxKChunks = 8;                       // K <= 256
 constexpr int kWTmemCols = 512;
 constexpr int kWMaxAccs = 4;
 constexpr uint32_t kNoCol = 0xFFFFFFFFu;
+// ---- epilogue, list form (sparse tiles)
 constexpr int kWSbRows = kWideSbRows;                          // rows of an epilogue sub-block (32 columns x 32 rows)
 static_assert(kWSbRows == 32, "the epilogue loads a sub-block with tcgen05.ld 32x32b.x32");
 constexpr int kWUSB = (kWGroupRows / 2) / kWSbRows;            // sub-blocks per unit (tile x column quarter x row half): 4
@@ -65,6 +66,13 @@ constexpr int kWListPage = 216;                                // 8-byte slots p
 constexpr int kWListPages = 2;                                 // pages in shared memory per epilogue warp (bulk-copy ring)
 constexpr int kWListBytes = kWListPages * kWListPage * 8;      // 1.7 KB per epilogue warp
 constexpr int kWHeaderSlots = 4;                               // a unit's list starts with 8 words: entries in sub-blocks 0..s
+// ---- epilogue, mask form (dense tiles)
+constexpr int kWUnitRows = kWGroupRows / 2;                    // rows of an epilogue unit (tile x column quarter x row half)
+constexpr int kWMetaPageBytes = kWUnitRows * 8;                // one unit = 128 row-meta pairs {mask, first CSR position} = 1 KB
+constexpr int kWMetaPages = 4;                                 // units in shared memory per epilogue warp (bulk-copy ring)
+constexpr int kWMetaBytes = kWMetaPages * kWMetaPageBytes;     // 4 KB per epilogue warp
+
+static_assert(kWListPages <= kWMetaPages, "l_full is sized for the larger ring");
 
 struct __align__(16) WideSmemTail {
     uint64_t b_full[kWMaxStages];    // TMA bytes of the stage landed
@@ -73,7 +81,7 @@ struct __align__(16) WideSmemTail {
     uint64_t a_free;                 // every MMA that reads the current A images has completed
     uint64_t tmem_full[kWMaxAccs];
     uint64_t tmem_empty[kWMaxAccs];  // the epilogue warps have read the accumulator
-    uint64_t l_full[kWEpiWarps][kWListPages];   // a page of an epilogue warp's list stream has landed (bulk copy)
+    uint64_t l_full[kWEpiWarps][kWMetaPages];   // a page of an epilogue warp's list / row-meta stream has landed (bulk copy)
     uint32_t tmem_base;
     uint32_t pad[3];
 };
@@ -87,8 +95,9 @@ struct WideParams {
     const uint4* tile_meta;          // {group, first column (offset into cols, multiple of 4), #columns, 0}
     const uint32_t* cols;            // distinct columns of the wide groups, ascending inside a group
     uint32_t num_tiles;              // wide tiles of the plan (stride of the per-quarter list streams)
-    const uint32_t* sb_off;          // [(column quarter * num_tiles + tile) * 9 + row quarter]: first work-list entry of a 32 x 32 sub-block
-    const uint2* entries;            // entry: {byte offset inside the staging image (column * 36 + row) * 4, CSR position}
+    const uint2* entries;            // mask form: row-meta pairs [(column quarter * 2 + row half) * num_tiles + tile][128]: {mask, first CSR
+                                     // position}; list form: the warps' list streams of 8-byte slots (colreorder.cu)
+    const uint32_t* sb_off;          // list form: [(column quarter * 2 + row half) * num_tiles + tile] (+1): first slot of the unit
     const uint32_t* reordered_rows;
     float* P;
     uint32_t* error_flag;
@@ -106,6 +115,7 @@ __device__ __forceinline__ unsigned long long gtime() {
         if (p.trace && lane == 0) p.trace[(size_t)blockIdx.x * 32 + (slot)] = gtime();        \
     } while (0)
 
+template <bool kMaskEpilogue>
 __global__ void __launch_bounds__(kWThreads, 1)
 wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_b32, const __grid_constant__ CUtensorMap map_b128, const WideParams p) {
@@ -116,9 +126,10 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint32_t KC = p.kchunks, S = p.stages, SGP = p.sgp;
     uint8_t* a_img = smem;                                                   // [KC][SGP] x 16 KB: per K-chunk one (SGP x 128)-row image
     uint8_t* b_ring = a_img + (size_t)SGP * KC * kWAImgBytes;                // S x 16 KB
-    uint8_t* epi_stage = b_ring + (size_t)S * kWBStageBytes;                 // 4 epilogue warps x 32 rows x 36 words
-    uint8_t* epi_lists = epi_stage + (size_t)kWEpiWarps * kWEpiStageBytes;   // 4 x 3 KB
-    WideSmemTail* tail = reinterpret_cast<WideSmemTail*>(epi_lists + (size_t)kWEpiWarps * kWListBytes);
+    // epilogue scratch: list form = staging images + list pages, mask form = row-meta pages
+    uint8_t* epi_stage = b_ring + (size_t)S * kWBStageBytes;
+    uint8_t* epi_lists = kMaskEpilogue ? epi_stage : epi_stage + (size_t)kWEpiWarps * kWEpiStageBytes;
+    WideSmemTail* tail = reinterpret_cast<WideSmemTail*>(epi_lists + (size_t)kWEpiWarps * (kMaskEpilogue ? kWMetaBytes : kWListBytes));
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t passes = kWSub / SGP;                  // K = 256: the tile range is walked once per sub-group
@@ -140,7 +151,7 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             mbar_init(&tail->tmem_empty[a], kWEpiWarps);
         }
         for (int w = 0; w < kWEpiWarps; ++w)
-            for (int k = 0; k < kWListPages; ++k) mbar_init(&tail->l_full[w][k], 1);
+            for (int k = 0; k < kWMetaPages; ++k) mbar_init(&tail->l_full[w][k], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -301,187 +312,279 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         WTRACE(9);                                 // last MMA issued
     } else {
         // ================= epilogue (warps 8..15) =================
-        // Warp = (TMEM lane quarter = 32 tile columns, row half of the group).  Per tile it walks 8 sub-blocks of 32 columns
-        // x 16 rows: tcgen05.ld 32x32b.x16 -> padded shared-memory staging image [column][row] (pitch 20 words:
-        // conflict-free STS.128) -> the sub-block's work list: one LDS.64 (entry), one LDS (value), one STG per entry, so
-        // the instruction count follows the nnz, not the tile area (a predicated store per accumulator element cost
-        // 4.6 us per 128 x 256 tile, measured).
-        // The lists of this warp's units, tile ascending, are ONE contiguous stream of 8-byte slots in global memory
-        // (colreorder.cu); the warp pages through it with cp.async.bulk into a ring of kWListPages pages, each with its
-        // own mbarrier.  (Paging with cp.async / LDG went through the LSU and whatever L1 the 227 KB of shared memory
-        // leave: every list access then waited ~700 cycles behind those loads -- measured with clock64 stamps.)
         const uint32_t ew = warp - kWEpiWarp0;
-        const uint32_t quarter = warp & 3;          // TMEM lanes [32*quarter, +32) = tile columns: fixed by warp id % 4
-        const uint32_t half = ew >> 2;              // rows [128*half, +128) of the group
-        float* stg = reinterpret_cast<float*>(epi_stage + (size_t)ew * kWEpiStageBytes);
-        const uint8_t* stg_bytes = reinterpret_cast<const uint8_t*>(stg);
-        const uint8_t* lring = epi_lists + (size_t)ew * kWListBytes;
-        const uint32_t lring_u32 = smem_u32(lring);
-        uint64_t* lfull = tail->l_full[ew];
-        const uint32_t* ustart = p.sb_off + (size_t)(quarter * 2 + half) * p.num_tiles;
-        uint32_t gp_base = 0;                       // pages issued in earlier passes (ring position of local page 0)
-        uint32_t it = 0;
-        for (uint32_t pass = 0; pass < passes; ++pass) {
-            // K = 256: one row half is resident per pass and only the warps of that half have work.  The others still take
-            // part in the accumulator hand-shake tile by tile: a warp that skipped ahead would test the parity of a phase
-            // the barrier has not reached yet (a parity wait can only tell the current phase from the previous one).
-            if (SGP == 1 && half != pass) {
+        if constexpr (kMaskEpilogue) {
+            // ---- mask form ----
+            // Warp = (TMEM lane quarter = 32 tile columns, row half of the group).  tcgen05.ld 32x32b.x32 gives lane c the
+            // accumulators of column c for 32 rows; per row the warp reads ONE pair {mask of the row's nnz among its 32
+            // columns, CSR position of the first} (a uniform-address LDS.64: a broadcast) and lane c stores its value to
+            // P[base + popc(mask & lanes below c)] when bit c is set: a row's entries inside a column quarter are consecutive
+            // CSR positions, so the stores of a row coalesce.  No staging of the accumulator tile through shared memory and
+            // no per-entry list: earlier versions moved the whole 128 KB tile through STS/LDS and walked {offset, position}
+            // lists (LDS.64 -> LDS -> STG per entry), which cost ~2.5 us per tile against ~1 us of MMAs -- every step of
+            // that chain has ~100 cycles of latency under load (clock64 stamps, tests/wide_trace.py).
+            // The pairs of a (tile, quarter, half) unit are 1 KB; the units a warp walks are contiguous in global memory and
+            // are pulled into a ring of kWMetaPages units with cp.async.bulk, kWMetaPages - 1 tiles ahead.
+            const uint32_t quarter = warp & 3;          // TMEM lanes [32*quarter, +32) = tile columns: fixed by warp id % 4
+            const uint32_t half = ew >> 2;              // rows [128*half, +128) of the group
+            const uint8_t* lring = epi_lists + (size_t)ew * kWMetaBytes;
+            const uint32_t lring_u32 = smem_u32(lring);
+            uint64_t* lfull = tail->l_full[ew];
+            const uint2* units = p.entries + (size_t)(quarter * 2 + half) * p.num_tiles * kWUnitRows;   // [tile][128]
+            const uint32_t lane_bit = 1u << lane, lanes_below = lane_bit - 1u;
+            float* const Pout = p.P;
+            uint32_t gp = 0;                            // units requested so far (ring position)
+            uint32_t it = 0;
+            for (uint32_t pass = 0; pass < passes; ++pass) {
+                // K = 256: one row half is resident per pass and only the warps of that half have work.  The others still take
+                // part in the accumulator hand-shake tile by tile: a warp that skipped ahead would test the parity of a phase
+                // the barrier has not reached yet (a parity wait can only tell the current phase from the previous one).
+                if (SGP == 1 && half != pass) {
+                    for (uint32_t t = my_begin; t < my_end; ++t, ++it) {
+                        const uint32_t acc = it % naccs, acc_phase = (it / naccs) & 1;
+                        mbar_wait(&tail->tmem_full[acc], acc_phase, p.error_flag, 19);
+                        if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
+                        __syncwarp();
+                    }
+                    continue;
+                }
+                const uint32_t col0 = SGP == 2 ? half * 128u : 0u;      // first accumulator column of this warp's rows
+                const uint32_t gp0 = gp;                                 // ring position of tile my_begin
+                auto issue_unit = [&](uint32_t t) {      // tile t -> ring buffer (gp0 + t - my_begin) % kWMetaPages
+                    if (lane == 0) {
+                        const uint32_t g = gp0 + (t - my_begin);
+                        uint64_t* bar = &lfull[g % kWMetaPages];
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer's last readers were generic-proxy loads
+                        mbar_arrive_expect_tx(bar, kWMetaPageBytes);
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(lring_u32 + (g % kWMetaPages) * kWMetaPageBytes), "l"(units + (size_t)t * kWUnitRows),
+                                       "r"((uint32_t)kWMetaPageBytes), "r"(smem_u32(bar))
+                                     : "memory");
+                    }
+                };
+                for (uint32_t t = my_begin; t < my_end && t < my_begin + (uint32_t)kWMetaPages; ++t) issue_unit(t);
                 for (uint32_t t = my_begin; t < my_end; ++t, ++it) {
                     const uint32_t acc = it % naccs, acc_phase = (it / naccs) & 1;
-                    mbar_wait(&tail->tmem_full[acc], acc_phase, p.error_flag, 19);
+                    const uint32_t g = gp0 + (t - my_begin);
+                    const uint8_t* page = lring + (g % kWMetaPages) * kWMetaPageBytes;
+                    mbar_wait(&lfull[g % kWMetaPages], (g / kWMetaPages) & 1, p.error_flag, 20);
+                    mbar_wait(&tail->tmem_full[acc], acc_phase, p.error_flag, 16);
+                    tc_fence_after();
+                    if (ew == 0 && it < 2) WTRACE(10 + 2 * it);   // accumulators of tile 0 / 1 complete
+                    // four sub-blocks of 32 rows; not unrolled (the body is ~250 instructions)
+    #pragma unroll 1
+                    for (uint32_t c = 0; c < 4 && !(p.debug & 4u); ++c) {
+                        const uint2* rows = reinterpret_cast<const uint2*>(page) + c * 32;
+                        uint32_t v[32];
+                        const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * (SGP * kWSubRows) + col0 + c * 32u;
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                            : "r"(taddr));
+                        // rows in two batches of 16 pairs (uniform address: one broadcast wavefront per two rows)
+                        uint2 mb[16];
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) mb[r] = rows[r];
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int r = 0; r < 16; ++r)
+                            if (mb[r].x & lane_bit) Pout[mb[r].y + __popc(mb[r].x & lanes_below)] = __uint_as_float(v[r]);
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) mb[r] = rows[16 + r];
+#pragma unroll
+                        for (int r = 0; r < 16; ++r)
+                            if (mb[r].x & lane_bit) Pout[mb[r].y + __popc(mb[r].x & lanes_below)] = __uint_as_float(v[16 + r]);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
                     if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
-                    __syncwarp();
+                    if (ew == 0 && it < 2) WTRACE(11 + 2 * it);   // epilogue of tile 0 / 1 done
+                    if (t + kWMetaPages < my_end) issue_unit(t + kWMetaPages);   // every lane is past its reads of this buffer
                 }
-                continue;
+                gp = gp0 + (my_end - my_begin);
             }
-            if (my_begin >= my_end) continue;
-            const uint32_t col0 = SGP == 2 ? half * 128u : 0u;      // first accumulator column of this warp's rows
-            const uint32_t s_begin = __ldg(ustart + my_begin), s_end = __ldg(ustart + my_end);   // slots of this warp's stream
-            const uint32_t npages = (s_end - s_begin + kWListPage - 1) / kWListPage;
-            auto issue_page = [&](uint32_t pg) {     // local page pg -> ring buffer (gp_base + pg) % kWListPages
-                if (lane == 0) {
+        } else {
+            // ---- list form ----
+            // Warp = (TMEM lane quarter = 32 tile columns, row half of the group).  Per tile it walks 8 sub-blocks of 32 columns
+            // x 16 rows: tcgen05.ld 32x32b.x16 -> padded shared-memory staging image [column][row] (pitch 20 words:
+            // conflict-free STS.128) -> the sub-block's work list: one LDS.64 (entry), one LDS (value), one STG per entry, so
+            // the instruction count follows the nnz, not the tile area (a predicated store per accumulator element cost
+            // 4.6 us per 128 x 256 tile, measured).
+            // The lists of this warp's units, tile ascending, are ONE contiguous stream of 8-byte slots in global memory
+            // (colreorder.cu); the warp pages through it with cp.async.bulk into a ring of kWListPages pages, each with its
+            // own mbarrier.  (Paging with cp.async / LDG went through the LSU and whatever L1 the 227 KB of shared memory
+            // leave: every list access then waited ~700 cycles behind those loads -- measured with clock64 stamps.)
+            const uint32_t quarter = warp & 3;          // TMEM lanes [32*quarter, +32) = tile columns: fixed by warp id % 4
+            const uint32_t half = ew >> 2;              // rows [128*half, +128) of the group
+            float* stg = reinterpret_cast<float*>(epi_stage + (size_t)ew * kWEpiStageBytes);
+            const uint8_t* stg_bytes = reinterpret_cast<const uint8_t*>(stg);
+            const uint8_t* lring = epi_lists + (size_t)ew * kWListBytes;
+            const uint32_t lring_u32 = smem_u32(lring);
+            uint64_t* lfull = tail->l_full[ew];
+            const uint32_t* ustart = p.sb_off + (size_t)(quarter * 2 + half) * p.num_tiles;
+            uint32_t gp_base = 0;                       // pages issued in earlier passes (ring position of local page 0)
+            uint32_t it = 0;
+            for (uint32_t pass = 0; pass < passes; ++pass) {
+                // K = 256: one row half is resident per pass and only the warps of that half have work.  The others still take
+                // part in the accumulator hand-shake tile by tile: a warp that skipped ahead would test the parity of a phase
+                // the barrier has not reached yet (a parity wait can only tell the current phase from the previous one).
+                if (SGP == 1 && half != pass) {
+                    for (uint32_t t = my_begin; t < my_end; ++t, ++it) {
+                        const uint32_t acc = it % naccs, acc_phase = (it / naccs) & 1;
+                        mbar_wait(&tail->tmem_full[acc], acc_phase, p.error_flag, 19);
+                        if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
+                        __syncwarp();
+                    }
+                    continue;
+                }
+                if (my_begin >= my_end) continue;
+                const uint32_t col0 = SGP == 2 ? half * 128u : 0u;      // first accumulator column of this warp's rows
+                const uint32_t s_begin = __ldg(ustart + my_begin), s_end = __ldg(ustart + my_end);   // slots of this warp's stream
+                const uint32_t npages = (s_end - s_begin + kWListPage - 1) / kWListPage;
+                auto issue_page = [&](uint32_t pg) {     // local page pg -> ring buffer (gp_base + pg) % kWListPages
+                    if (lane == 0) {
+                        const uint32_t g = gp_base + pg;
+                        const uint32_t first = pg * kWListPage;
+                        const uint32_t n = s_end - s_begin - first < (uint32_t)kWListPage ? s_end - s_begin - first : (uint32_t)kWListPage;
+                        uint64_t* bar = &lfull[g % kWListPages];
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer's last readers were generic-proxy loads
+                        mbar_arrive_expect_tx(bar, n * 8u);
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(lring_u32 + (g % kWListPages) * (kWListPage * 8)), "l"(p.entries + s_begin + first), "r"(n * 8u),
+                                       "r"(smem_u32(bar))
+                                     : "memory");
+                    }
+                };
+                auto wait_page = [&](uint32_t pg) {
                     const uint32_t g = gp_base + pg;
-                    const uint32_t first = pg * kWListPage;
-                    const uint32_t n = s_end - s_begin - first < (uint32_t)kWListPage ? s_end - s_begin - first : (uint32_t)kWListPage;
-                    uint64_t* bar = &lfull[g % kWListPages];
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer's last readers were generic-proxy loads
-                    mbar_arrive_expect_tx(bar, n * 8u);
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(lring_u32 + (g % kWListPages) * (kWListPage * 8)), "l"(p.entries + s_begin + first), "r"(n * 8u),
-                                   "r"(smem_u32(bar))
-                                 : "memory");
-                }
-            };
-            auto wait_page = [&](uint32_t pg) {
-                const uint32_t g = gp_base + pg;
-                mbar_wait(&lfull[g % kWListPages], (g / kWListPages) & 1, p.error_flag, 20);
-            };
-            for (uint32_t pg = 0; pg < npages && pg < (uint32_t)kWListPages; ++pg) issue_page(pg);
-            uint32_t cur_page = 0;
-            bool cur_landed = false;                 // cur_page has been waited for (an mbarrier poll costs ~200 cycles: only once per page)
-            auto ensure_page = [&](uint32_t pg) {    // pages are consumed in ascending order
-                if (pg == cur_page && cur_landed) return;
-                while (cur_page < pg) {
-                    // leaving cur_page: it has landed (it may never have been read), every lane is done with it, and its
-                    // buffer takes page cur_page + kWListPages
-                    if (!cur_landed) wait_page(cur_page);
-                    __syncwarp();
-                    if (cur_page + kWListPages < npages) issue_page(cur_page + kWListPages);
-                    ++cur_page;
-                    cur_landed = false;
-                }
-                wait_page(pg);
-                cur_landed = true;
-            };
-            // slot e of the stream (relative to s_begin) inside the ring
-            auto slot_addr = [&](uint32_t e) -> const uint8_t* {
-                const uint32_t pg = e / kWListPage;
-                return lring + ((gp_base + pg) % kWListPages) * (kWListPage * 8) + (e - pg * kWListPage) * 8;
-            };
-            uint32_t pos = 0;                        // first slot of the current unit
-            for (uint32_t t = my_begin; t < my_end; ++t, ++it) {
-                const uint32_t acc = it % naccs, acc_phase = (it / naccs) & 1;
-                // the unit's header: the cumulative sub-block counts (4 slots, never straddles a page: pages and units start
-                // at multiples of 8 slots)
-                ensure_page(pos / kWListPage);
-                const uint32_t hw = lane < 8u ? reinterpret_cast<const uint32_t*>(slot_addr(pos))[lane] : 0u;
-                const uint32_t ebase = pos + kWHeaderSlots;
-                const uint32_t total = __shfl_sync(0xffffffffu, hw, kWUSB - 1);
-                mbar_wait(&tail->tmem_full[acc], acc_phase, p.error_flag, 16);
-                tc_fence_after();
-                if (ew == 0 && it < 2) WTRACE(10 + 2 * it);   // accumulators of tile 0 / 1 complete
-                const bool ctr = p.trace && ew == 0 && it == 1 && lane == 0;   // cycle stamps of tile 1's sub-blocks (slots 16..31)
-#define CTRACE(slot) do { if (ctr) p.trace[(size_t)blockIdx.x * 32 + (slot)] = (unsigned long long)clock64(); } while (0)
-                // not unrolled: eight copies of this body are ~50 KB of SASS, and eight warps walking different copies kept
-                // missing the instruction cache (the body took >1000 cycles per sub-block, measured)
-                uint32_t e1 = ebase;
-#pragma unroll 1
-                for (uint32_t c = 0; c < (uint32_t)kWUSB; ++c) {
-                    const uint32_t e0 = e1;
-                    e1 = ebase + __shfl_sync(0xffffffffu, hw, c);
-                    if (e0 == e1 || (p.debug & 4u)) continue;
-                    if (c < 4) CTRACE(16 + 4 * c);
-                    // the first (up to) 64 entries of the sub-block are requested BEFORE the accumulator is staged: every step
-                    // of this chain (LDTM, STS, LDS.64, LDS, STG) has ~100 cycles of latency under load, and the entry fetch
-                    // does not depend on the staging image
-                    const uint32_t pg0 = e0 / kWListPage;
-                    ensure_page(pg0);
-                    const uint32_t pend0 = (pg0 + 1) * kWListPage;
-                    uint32_t seg0 = e1 < pend0 ? e1 : pend0;
-                    if (seg0 > e0 + 128u) seg0 = e0 + 128u;
-                    uint2 en0[4];
-                    {
-                        const uint2* lent = reinterpret_cast<const uint2*>(slot_addr(pg0 * kWListPage)) - (size_t)pg0 * kWListPage;   // lent[e] = slot e
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint32_t ee = e0 + q * 32 + lane;
-                            en0[q] = lent[ee < seg0 ? ee : e0];
-                        }
+                    mbar_wait(&lfull[g % kWListPages], (g / kWListPages) & 1, p.error_flag, 20);
+                };
+                for (uint32_t pg = 0; pg < npages && pg < (uint32_t)kWListPages; ++pg) issue_page(pg);
+                uint32_t cur_page = 0;
+                bool cur_landed = false;                 // cur_page has been waited for (an mbarrier poll costs ~200 cycles: only once per page)
+                auto ensure_page = [&](uint32_t pg) {    // pages are consumed in ascending order
+                    if (pg == cur_page && cur_landed) return;
+                    while (cur_page < pg) {
+                        // leaving cur_page: it has landed (it may never have been read), every lane is done with it, and its
+                        // buffer takes page cur_page + kWListPages
+                        if (!cur_landed) wait_page(cur_page);
+                        __syncwarp();
+                        if (cur_page + kWListPages < npages) issue_page(cur_page + kWListPages);
+                        ++cur_page;
+                        cur_landed = false;
                     }
-                    uint32_t v[32];
-                    const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * (SGP * kWSubRows) + col0 + c * kWSbRows;
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                        : "r"(taddr));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (c < 4) CTRACE(17 + 4 * c);
-                    // staging image [column = lane][row]: thread writes the 32 rows of its column
-                    uint4* srow = reinterpret_cast<uint4*>(stg + lane * kWEpiRowWords);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) srow[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    __syncwarp();
-                    if (c < 4) CTRACE(18 + 4 * c);
-                    {
-                        float val[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            val[q] = (p.debug & 128u) ? __uint_as_float(en0[q].x) : *reinterpret_cast<const float*>(stg_bytes + en0[q].x);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (e0 + q * 32 + lane < seg0 && !(p.debug & 64u)) p.P[en0[q].y] = val[q];
-                    }
-                    // the rest of a long list (more than 128 entries, or a page boundary inside the first 128)
-                    for (uint32_t e = seg0; e < e1;) {
-                        const uint32_t pg = e / kWListPage;
-                        ensure_page(pg);
-                        const uint32_t pend = (pg + 1) * kWListPage;
-                        const uint32_t seg_end = e1 < pend ? e1 : pend;
-                        const uint2* lent = reinterpret_cast<const uint2*>(slot_addr(pg * kWListPage)) - (size_t)pg * kWListPage;
-                        for (uint32_t eb = e; eb < seg_end; eb += 64) {
-                            uint2 en[2];
-                            float val[2];
-#pragma unroll
-                            for (int q = 0; q < 2; ++q) {
-                                const uint32_t ee = eb + q * 32 + lane;
-                                en[q] = lent[ee < seg_end ? ee : e];
+                    wait_page(pg);
+                    cur_landed = true;
+                };
+                // slot e of the stream (relative to s_begin) inside the ring
+                auto slot_addr = [&](uint32_t e) -> const uint8_t* {
+                    const uint32_t pg = e / kWListPage;
+                    return lring + ((gp_base + pg) % kWListPages) * (kWListPage * 8) + (e - pg * kWListPage) * 8;
+                };
+                uint32_t pos = 0;                        // first slot of the current unit
+                for (uint32_t t = my_begin; t < my_end; ++t, ++it) {
+                    const uint32_t acc = it % naccs, acc_phase = (it / naccs) & 1;
+                    // the unit's header: the cumulative sub-block counts (4 slots, never straddles a page: pages and units start
+                    // at multiples of 8 slots)
+                    ensure_page(pos / kWListPage);
+                    const uint32_t hw = lane < 8u ? reinterpret_cast<const uint32_t*>(slot_addr(pos))[lane] : 0u;
+                    const uint32_t ebase = pos + kWHeaderSlots;
+                    const uint32_t total = __shfl_sync(0xffffffffu, hw, kWUSB - 1);
+                    mbar_wait(&tail->tmem_full[acc], acc_phase, p.error_flag, 16);
+                    tc_fence_after();
+                    if (ew == 0 && it < 2) WTRACE(10 + 2 * it);   // accumulators of tile 0 / 1 complete
+                    // not unrolled: eight copies of this body are ~50 KB of SASS, and eight warps walking different copies kept
+                    // missing the instruction cache (the body took >1000 cycles per sub-block, measured)
+                    uint32_t e1 = ebase;
+    #pragma unroll 1
+                    for (uint32_t c = 0; c < (uint32_t)kWUSB; ++c) {
+                        const uint32_t e0 = e1;
+                        e1 = ebase + __shfl_sync(0xffffffffu, hw, c);
+                        if (e0 == e1 || (p.debug & 4u)) continue;
+                        // the first (up to) 64 entries of the sub-block are requested BEFORE the accumulator is staged: every step
+                        // of this chain (LDTM, STS, LDS.64, LDS, STG) has ~100 cycles of latency under load, and the entry fetch
+                        // does not depend on the staging image
+                        const uint32_t pg0 = e0 / kWListPage;
+                        ensure_page(pg0);
+                        const uint32_t pend0 = (pg0 + 1) * kWListPage;
+                        uint32_t seg0 = e1 < pend0 ? e1 : pend0;
+                        if (seg0 > e0 + 128u) seg0 = e0 + 128u;
+                        uint2 en0[4];
+                        {
+                            const uint2* lent = reinterpret_cast<const uint2*>(slot_addr(pg0 * kWListPage)) - (size_t)pg0 * kWListPage;   // lent[e] = slot e
+    #pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t ee = e0 + q * 32 + lane;
+                                en0[q] = lent[ee < seg0 ? ee : e0];
                             }
-#pragma unroll
-                            for (int q = 0; q < 2; ++q)
-                                val[q] = (p.debug & 128u) ? __uint_as_float(en[q].x) : *reinterpret_cast<const float*>(stg_bytes + en[q].x);
-#pragma unroll
-                            for (int q = 0; q < 2; ++q)
-                                if (eb + q * 32 + lane < seg_end && !(p.debug & 64u)) p.P[en[q].y] = val[q];
                         }
-                        e = seg_end;
+                        uint32_t v[32];
+                        const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * (SGP * kWSubRows) + col0 + c * kWSbRows;
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                            : "r"(taddr));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        // staging image [column = lane][row]: thread writes the 32 rows of its column
+                        uint4* srow = reinterpret_cast<uint4*>(stg + lane * kWEpiRowWords);
+    #pragma unroll
+                        for (int i = 0; i < 8; ++i) srow[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        __syncwarp();
+                        {
+                            float val[4];
+    #pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                val[q] = *reinterpret_cast<const float*>(stg_bytes + en0[q].x);
+    #pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (e0 + q * 32 + lane < seg0) p.P[en0[q].y] = val[q];
+                        }
+                        // the rest of a long list (more than 128 entries, or a page boundary inside the first 128)
+                        for (uint32_t e = seg0; e < e1;) {
+                            const uint32_t pg = e / kWListPage;
+                            ensure_page(pg);
+                            const uint32_t pend = (pg + 1) * kWListPage;
+                            const uint32_t seg_end = e1 < pend ? e1 : pend;
+                            const uint2* lent = reinterpret_cast<const uint2*>(slot_addr(pg * kWListPage)) - (size_t)pg * kWListPage;
+                            for (uint32_t eb = e; eb < seg_end; eb += 64) {
+                                uint2 en[2];
+                                float val[2];
+    #pragma unroll
+                                for (int q = 0; q < 2; ++q) {
+                                    const uint32_t ee = eb + q * 32 + lane;
+                                    en[q] = lent[ee < seg_end ? ee : e];
+                                }
+    #pragma unroll
+                                for (int q = 0; q < 2; ++q)
+                                    val[q] = *reinterpret_cast<const float*>(stg_bytes + en[q].x);
+    #pragma unroll
+                                for (int q = 0; q < 2; ++q)
+                                    if (eb + q * 32 + lane < seg_end) p.P[en[q].y] = val[q];
+                            }
+                            e = seg_end;
+                        }
+                        __syncwarp();
                     }
+                    tc_fence_before();
                     __syncwarp();
-                    if (c < 4) CTRACE(19 + 4 * c);
+                    if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
+                    if (ew == 0 && it < 2) WTRACE(11 + 2 * it);   // epilogue of tile 0 / 1 done
+                    pos += (kWHeaderSlots + total + 7u) & ~7u;
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
-                if (ew == 0 && it < 2) WTRACE(11 + 2 * it);   // epilogue of tile 0 / 1 done
-                pos += (kWHeaderSlots + total + 7u) & ~7u;
+                // every page that was requested must have landed before the ring is reused or the CTA exits
+                for (uint32_t pg = cur_page; pg < npages && pg < cur_page + (uint32_t)kWListPages; ++pg) wait_page(pg);
+                gp_base += npages;
             }
-            // every page that was requested must have landed before the ring is reused or the CTA exits
-            for (uint32_t pg = cur_page; pg < npages && pg < cur_page + (uint32_t)kWListPages; ++pg) wait_page(pg);
-            gp_base += npages;
         }
         if (ew == 0) WTRACE(14);                   // epilogue done
     }
@@ -565,7 +668,7 @@ int launch_wide(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, f
     // one sub-group is resident at a time and the CTA walks its tile range twice
     const uint32_t sgp = kchunks <= 4 ? 2u : 1u;
     const size_t max_smem = 232448;   // 227 KB per CTA on sm_100
-    const size_t fixed = 1024 + sizeof(WideSmemTail) + (size_t)kWEpiWarps * (kWEpiStageBytes + kWListBytes) +
+    const size_t fixed = 1024 + sizeof(WideSmemTail) + (size_t)kWEpiWarps * (plan->wide_mask_epilogue ? (size_t)kWMetaBytes : (size_t)(kWEpiStageBytes + kWListBytes)) +
                          (size_t)sgp * kchunks * kWAImgBytes;
     uint32_t stages = static_cast<uint32_t>((max_smem - fixed) / kWBStageBytes);
     static const uint32_t stage_cap = [] { const char* e = std::getenv("BSMR_WIDE_STAGES"); return e ? (uint32_t)std::atoi(e) : 0u; }();
@@ -574,7 +677,8 @@ int launch_wide(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, f
     const size_t smem = fixed + (size_t)stages * kWBStageBytes;
     static bool attr_set = false;
     if (!attr_set) {
-        BSMR_CUDA_OK(cudaFuncSetAttribute(wide_sddmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+        BSMR_CUDA_OK(cudaFuncSetAttribute(wide_sddmm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+        BSMR_CUDA_OK(cudaFuncSetAttribute(wide_sddmm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
         attr_set = true;
     }
     uint32_t* error_flag = kernel_error_flag();
@@ -597,8 +701,8 @@ int launch_wide(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, f
     p.tile_meta = plan->wt_meta.ptr;
     p.cols = plan->w_cols.ptr;
     p.num_tiles = plan->num_wide_tiles;
-    p.sb_off = plan->w_sb_off.ptr;
     p.entries = plan->w_entries.ptr;
+    p.sb_off = plan->w_sb_off.ptr;
     p.reordered_rows = plan->reordered_rows.ptr;
     p.P = dP;
     p.error_flag = error_flag;
@@ -611,7 +715,8 @@ int launch_wide(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, f
         return BSMR_ERR_BAD_STATE;
     }
     const uint32_t grid = plan->w_grid;   // one CTA per SM
-    wide_sddmm_kernel<<<grid, kWThreads, smem, stream>>>(map_a, map_b, map_b32, map_b128, p);
+    if (plan->wide_mask_epilogue) wide_sddmm_kernel<true><<<grid, kWThreads, smem, stream>>>(map_a, map_b, map_b32, map_b128, p);
+    else wide_sddmm_kernel<false><<<grid, kWThreads, smem, stream>>>(map_a, map_b, map_b32, map_b128, p);
     ctx->launches++;
     BSMR_CUDA_OK(cudaGetLastError());
     return BSMR_OK;

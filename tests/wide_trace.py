@@ -29,12 +29,12 @@ def main():
     dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
     dP = torch.zeros(len(ci), device="cuda")
     for _ in range(5):
-        plan.sddmm(K, dA, dB, dP)
+        plan.sddmm(K, dA, dB, dP, flags=pkg.SDDMM_THREE_KERNEL)
     trace = torch.zeros(148 * 32, dtype=torch.int64, device="cuda")
     lib = pkg.lib()
     lib.bsmr_debug_set_wide_trace.argtypes = [C.c_void_p]
     lib.bsmr_debug_set_wide_trace(trace.data_ptr())
-    ms = plan.sddmm(K, dA, dB, dP)
+    ms = plan.sddmm(K, dA, dB, dP, flags=pkg.SDDMM_THREE_KERNEL)
     torch.cuda.synchronize()
     raw = trace.cpu().numpy().reshape(148, 32)
     t = raw[:, :16].astype(np.float64)
@@ -47,14 +47,6 @@ def main():
     for i, n in enumerate(NAMES):
         col = rel[:, i]
         print("%-10s min %6.2f  med %6.2f  max %6.2f us" % (n, np.nanmin(col), np.nanmedian(col), np.nanmax(col)))
-    c = raw[used][:, 16:32].astype(np.float64)
-    ok = (c > 0).all(axis=1)
-    c = c[ok]
-    print("cycle stamps of tile 1 (epilogue warp 8), %d CTAs whose first four sub-blocks all have entries:" % len(c))
-    for j in range(4):
-        d = [np.median(c[:, j * 4 + k + 1] - c[:, j * 4 + k]) for k in range(3)]
-        nxt = np.median(c[:, (j + 1) * 4] - c[:, j * 4 + 3]) if j < 3 else float("nan")
-        print("sub-block %d cycles: tcgen05.ld+wait %.0f  sts+syncwarp %.0f  entries %.0f  to next chunk %.0f" % (j, d[0], d[1], d[2], nxt))
 
 
 if __name__ == "__main__":
