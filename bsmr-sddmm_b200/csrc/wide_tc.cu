@@ -1,7 +1,7 @@
 // Wide row-group SDDMM kernel for sm_100a.  A 256-row group of the reordered matrix stays resident in shared memory as
-// two 128-row M operands of tcgen05.mma (TF32, fp32 accumulators in TMEM); the group's distinct B columns stream past
-// them 128 at a time as the N operand (one B stage feeds both sub-groups); the epilogue keeps only the accumulator
-// elements S has, driven by per-sub-block work lists.
+// the N operand of tcgen05.mma (TF32, fp32 accumulators in TMEM); the group's distinct B columns stream past it 128 at a
+// time as the M operand (transposed product: TMEM lanes = tile columns, TMEM columns = group rows); the epilogue keeps
+// only the accumulator elements S has.
 //
 // Why it exists (no counterpart in the reference, whose only tensor-core unit is the 16 x 16 block of
 // src/sddmmKernel.cu:213-351): on matrices that are dense-ish at the scale of a row group (the nips example is 4 %
@@ -13,19 +13,23 @@
 // other group keeps the BSMR dense-block + residual kernels.
 //
 // Pipeline (17 warps, one CTA per SM, persistent over a contiguous range of tiles of one row group):
-//   warps 0-7   TMA producers: cp.async.bulk.tensor.2d tile::gather4 (4 arbitrary rows of the [N x K] / [M x K] tensor
-//               per request, SWIZZLE_128B K-major image, 32 floats of K per stage); first the A images of the group
-//               ([sub-group][K-chunk] x 16 KB), then the B ring (S x 16 KB)
-//   warps 12-15 converters: cvt.rna.tf32.f32 in place on every landed image (tcgen05 kind::tf32 truncates, the reference
-//               rounds to nearest), fence.proxy.async, mbarrier
-//   warp  16    TMEM allocator (512 columns) + single-lane MMA issuer: per B stage 4 MMAs (M=128, N<=128, K=8) per
-//               resident sub-group; accumulator sets rotate so that the epilogue of tile i overlaps the MMAs of tile i+1
-//   warps 8-11  epilogue (TMEM lane quarter = warp % 4): tcgen05.ld 32x32b.x32 -> padded staging -> work list -> P
-// Shared memory (K = 128): 128 KB A + 4 x 16 KB B ring + 18 KB staging + 14 KB lists.  A first version staged the
-// operands with LDG -> cvt -> STS from producer warps (no converter pass, less shared-memory traffic): every load in
+//   warps 0-7   TMA producers: the A images of the group ([K-chunk][sub-group] x 16 KB, tile::gather4 of the reordered
+//               rows), then the B ring (S x 16 KB, 32 floats of K per stage): one tiled load per run of consecutive
+//               columns (whole tile or 32-column quarter), tile::gather4 (4 arbitrary rows per request) otherwise.  The
+//               tensor maps are CU_TENSOR_MAP_DATA_TYPE_TFLOAT32: the TMA unit rounds fp32 -> TF32 to nearest on the way in
+//               (tcgen05 kind::tf32 alone truncates; the reference rounds: src/sddmmKernel.cu:317-322)
+//   warp  16    TMEM allocator (512 columns) + single-lane MMA issuer: per B stage 4 MMAs (M = 128 tile columns,
+//               N = 256 resident rows, K = 8); two accumulator sets rotate so that the epilogue of tile i overlaps the
+//               MMAs of tile i+1.  K = 256: one 128-row half resident at a time, the tile range is walked twice
+//   warps 8-15  epilogue (TMEM lane quarter = warp % 4, row half = (warp - 8) / 4), in one of two forms chosen per plan by
+//               the fill of the tiles (template parameter): per-entry lists through a staged accumulator image, or row
+//               masks with direct stores; both stream their metadata with cp.async.bulk rings (see the epilogue section)
+// Shared memory (K = 128): 128 KB A + 16 KB B stages (2 with lists: 36 KB staging + 27 KB list pages; 4 with masks:
+// 32 KB row-meta pages).  A first version staged the operands with LDG -> cvt -> STS from producer warps: every load in
 // flight held an L1 line, L1 is what shared memory leaves over, and the epilogue's LDS/STG queued behind the loads in
 // the LSU; measured slower at every depth of prefetch.  TMA does not touch the LSU / L1 miss path at all.
-// Roofline: HBM on the compulsory bytes of the step; inside, L2 -> SM traffic (distinct columns x K x 4 per group).
+// Roofline: HBM on the compulsory bytes of the step; inside, L2 -> SM traffic (distinct columns x K x 4 per group) and
+// the shared-memory / issue cost of the epilogue.
 #include <cstdlib>
 #include <vector>
 
