@@ -217,11 +217,16 @@ int bsmr_plan_create(bsmr_ctx* ctx, uint32_t M, uint32_t N, uint32_t nnz, const 
     return BSMR_OK;
 }
 
+static int queue_copy_out(bsmr_plan* plan, bsmr_plan::HostSlot& s);
+
 int bsmr_plan_destroy(bsmr_plan* plan) {
     if (!plan) return BSMR_OK;
     cudaSetDevice(plan->ctx->device);
     for (bsmr_plan::HostSlot& s : plan->host_slots)       // pipelined host-data calls still in flight use the plan's buffers
-        if (s.in_flight) cudaEventSynchronize(s.d2h_done);
+        if (s.in_flight) {
+            queue_copy_out(plan, s);
+            cudaEventSynchronize(s.d2h_done);
+        }
     delete plan;
     return BSMR_OK;
 }
@@ -876,10 +881,14 @@ int bsmr_sddmm_host(bsmr_plan* plan, uint32_t K, const float* hA, const float* h
 }
 
 // ---- pipelined host-data SDDMM --------------------------------------------------------------------------------
-// A call = H2D A,B -> zero P -> kernels -> D2H P, exactly what bsmr_sddmm_host does, but the three phases run on
-// three streams (copy-in, the context's stream, copy-out) and successive calls alternate between two slots of device
-// buffers: while call i computes, call i + 1 copies in and call i - 1 copies out (PCIe is full duplex, the copy
-// engines run next to the SMs).  Ordering is carried by the slot's events only; the host blocks only in _wait.
+// A call = H2D A,B -> zero P -> kernels -> D2H P, exactly what bsmr_sddmm_host does, but asynchronous: successive calls
+// alternate between two slots of device buffers, the kernels run on the context's stream and the copies on a copy
+// stream, ordered by the slots' events; the host blocks only in _wait.
+// Copy order.  The copy-out of call i is queued BEHIND the copy-in of call i + 1 (it is held back until the next submit
+// or until somebody waits for it): on one in-order copy stream that gives H2D(i+1) | kernels(i) in parallel, then
+// D2H(i), and never two copies in opposite directions at once.  Measured on this pool's B200 hosts, a 6.4 MB H2D and a
+// 3 MB D2H running concurrently drop to ~12 GB/s each on some boxes (53 GB/s alone; tests/pcie_probe.py), which made
+// the two-stream variant (environment BSMR_HOST_PIPE_DUPLEX) anything between 146 and 390 us per nips step.
 static int ensure_host_pipeline(bsmr_plan* plan) {
     bsmr_ctx* ctx = plan->ctx;
     if (!ctx->copy_in_stream) BSMR_CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_in_stream, cudaStreamNonBlocking));
@@ -889,6 +898,23 @@ static int ensure_host_pipeline(bsmr_plan* plan) {
         if (!s.compute_done) BSMR_CUDA_OK(cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming));
         if (!s.d2h_done) BSMR_CUDA_OK(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
     }
+    return BSMR_OK;
+}
+
+static bool host_pipe_duplex() {
+    static const bool v = std::getenv("BSMR_HOST_PIPE_DUPLEX") != nullptr;
+    return v;
+}
+
+// queue the copy-out of a slot whose kernels have been issued
+static int queue_copy_out(bsmr_plan* plan, bsmr_plan::HostSlot& s) {
+    if (s.d2h_queued) return BSMR_OK;
+    bsmr_ctx* ctx = plan->ctx;
+    cudaStream_t cs = host_pipe_duplex() ? ctx->copy_out_stream : ctx->copy_in_stream;
+    BSMR_CUDA_OK(cudaStreamWaitEvent(cs, s.compute_done, 0));
+    if (plan->nnz) BSMR_CUDA_OK(cudaMemcpyAsync(s.hP, s.dP.ptr, s.dP.bytes(), cudaMemcpyDeviceToHost, cs));
+    BSMR_CUDA_OK(cudaEventRecord(s.d2h_done, cs));
+    s.d2h_queued = true;
     return BSMR_OK;
 }
 
@@ -907,7 +933,9 @@ int bsmr_sddmm_host_submit(bsmr_plan* plan, uint32_t K, const float* hA, const f
     BSMR_TRY(ensure_host_pipeline(plan));
     const uint64_t id = plan->host_submits;
     bsmr_plan::HostSlot& s = plan->host_slots[id % bsmr_plan::kHostSlots];
+    bsmr_plan::HostSlot& prev = plan->host_slots[(id + bsmr_plan::kHostSlots - 1) % bsmr_plan::kHostSlots];
     const size_t na = static_cast<size_t>(plan->M) * K, nb = static_cast<size_t>(plan->N) * K;
+    if (s.in_flight) BSMR_TRY(queue_copy_out(plan, s));       // (two slots: already queued by the previous submit)
     if (s.in_flight && (na > s.dA.capacity || nb > s.dB.capacity || plan->nnz > s.dP.capacity))
         BSMR_CUDA_OK(cudaEventSynchronize(s.d2h_done));      // the buffers are about to be reallocated
     BSMR_TRY(s.dA.alloc(na));
@@ -918,17 +946,18 @@ int bsmr_sddmm_host_submit(bsmr_plan* plan, uint32_t K, const float* hA, const f
     BSMR_CUDA_OK(cudaMemcpyAsync(s.dA.ptr, hA, na * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in_stream));
     BSMR_CUDA_OK(cudaMemcpyAsync(s.dB.ptr, hB, nb * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in_stream));
     BSMR_CUDA_OK(cudaEventRecord(s.h2d_done, ctx->copy_in_stream));
+    // the copy-out of the previous call goes behind this copy-in
+    if (&prev != &s && prev.in_flight) BSMR_TRY(queue_copy_out(plan, prev));
     // kernels: after the copy-in, and after the slot's previous copy-out has read dP
     BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->stream, s.h2d_done, 0));
     if (s.in_flight) BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->stream, s.d2h_done, 0));
     if (plan->nnz) BSMR_CUDA_OK(cudaMemsetAsync(s.dP.ptr, 0, s.dP.bytes(), ctx->stream));   // src/sddmmKernel.cu:2525
     BSMR_TRY(bsmr_sddmm(plan, K, s.dA.ptr, s.dB.ptr, s.dP.ptr, 1, flags, nullptr));
     BSMR_CUDA_OK(cudaEventRecord(s.compute_done, ctx->stream));
-    // copy-out
-    BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->copy_out_stream, s.compute_done, 0));
-    if (plan->nnz) BSMR_CUDA_OK(cudaMemcpyAsync(hP, s.dP.ptr, s.dP.bytes(), cudaMemcpyDeviceToHost, ctx->copy_out_stream));
-    BSMR_CUDA_OK(cudaEventRecord(s.d2h_done, ctx->copy_out_stream));
+    s.hP = hP;
+    s.d2h_queued = false;
     s.in_flight = true;
+    if (host_pipe_duplex()) BSMR_TRY(queue_copy_out(plan, s));   // two copy streams: nothing to hold back
     plan->host_submits = id + 1;
     if (ticket) *ticket = id;
     return BSMR_OK;
@@ -939,7 +968,10 @@ int bsmr_sddmm_host_wait(bsmr_plan* plan, uint64_t ticket) {
     BSMR_CUDA_OK(cudaSetDevice(plan->ctx->device));
     if (ticket == BSMR_TICKET_ALL) {
         for (bsmr_plan::HostSlot& s : plan->host_slots)
-            if (s.in_flight) BSMR_CUDA_OK(cudaEventSynchronize(s.d2h_done));
+            if (s.in_flight) {
+                BSMR_TRY(queue_copy_out(plan, s));
+                BSMR_CUDA_OK(cudaEventSynchronize(s.d2h_done));
+            }
         return BSMR_OK;
     }
     if (ticket >= plan->host_submits) {
@@ -948,7 +980,10 @@ int bsmr_sddmm_host_wait(bsmr_plan* plan, uint64_t ticket) {
     }
     // a ticket older than the slot's latest call completed before that call's kernels started
     bsmr_plan::HostSlot& s = plan->host_slots[ticket % bsmr_plan::kHostSlots];
-    if (s.in_flight) BSMR_CUDA_OK(cudaEventSynchronize(s.d2h_done));
+    if (s.in_flight) {
+        BSMR_TRY(queue_copy_out(plan, s));
+        BSMR_CUDA_OK(cudaEventSynchronize(s.d2h_done));
+    }
     return BSMR_OK;
 }
 

@@ -269,6 +269,8 @@ struct bsmr_plan {
         bsmr::DevBuf<float> dA, dB, dP;
         cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
         bool in_flight = false;
+        float* hP = nullptr;          // where the slot's result goes (its copy-out may still be waiting to be queued)
+        bool d2h_queued = true;
     };
     static constexpr int kHostSlots = 2;
     HostSlot host_slots[kHostSlots];

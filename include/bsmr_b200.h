@@ -202,11 +202,13 @@ int bsmr_sddmm_host(bsmr_plan* plan, uint32_t K, const float* hA, const float* h
 int bsmr_plan_execution_choice(bsmr_plan* plan, uint32_t K, uint32_t* flags);
 
 /* Pipelined form of the host-data overload: the same H2D A,B -> zero P -> kernels -> D2H P, but the call returns as
- * soon as the work is queued.  Successive calls alternate between two slots of device buffers and three streams
- * (copy-in, the context's stream, copy-out), so the copy-in of call i+1 and the copy-out of call i-1 overlap the
- * kernels of call i.  hA / hB must stay valid and hP must not be read until bsmr_sddmm_host_wait(plan, ticket)
- * returns (BSMR_TICKET_ALL: every call submitted so far); pinned host memory is needed for the copies to be
- * asynchronous.  One caller thread per plan, as everywhere in this ABI.                                    */
+ * soon as the work is queued.  Successive calls alternate between two slots of device buffers; the kernels run on the
+ * context's stream, the copies on a copy stream, so the copy-in of call i+1 overlaps the kernels of call i.  The
+ * copy-out of a call is queued behind the copy-in of the next one (or by _wait): copies in opposite directions never
+ * run at the same time, which on some hosts of this pool costs 4x in rate (environment BSMR_HOST_PIPE_DUPLEX = two
+ * copy streams, copy-out queued at once).  hA / hB must stay valid and hP must not be read until
+ * bsmr_sddmm_host_wait(plan, ticket) returns (BSMR_TICKET_ALL: every call submitted so far); pinned host memory is
+ * needed for the copies to be asynchronous.  One caller thread per plan, as everywhere in this ABI.          */
 #define BSMR_TICKET_ALL 0xFFFFFFFFFFFFFFFFull
 int bsmr_sddmm_host_submit(bsmr_plan* plan, uint32_t K, const float* hA, const float* hB, float* hP,
                            uint32_t flags, uint64_t* ticket);
