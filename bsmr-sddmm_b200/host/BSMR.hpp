@@ -118,6 +118,19 @@ public:
     float reorderingTime() const { return rowReorderingTime_ + colReorderingTime_; }
 
     // additions
+    // Reorder cache (no counterpart in the reference, which reclusters on every run): the row order of this pattern for
+    // (similarityThreshold, row flags), written to / read from a file keyed by a fingerprint of the pattern.
+    // loadRowOrder() replaces rowReordering(); colReordering() then rebuilds the column vectors and the device format.
+    bool saveRowOrder(const std::string& path, const float similarityThreshold) const {
+        return handle_ && bsmr_host::ok(bsmr_plan_save_row_order(handle_->plan, path.c_str(), similarityThreshold, rowFlags_), "save row order");
+    }
+    bool loadRowOrder(const std::string& path, const float similarityThreshold, const sparseMatrix::CSR<float>& matrix) {
+        if (!ensurePlan(matrix)) return false;
+        if (!bsmr_host::ok(bsmr_plan_load_row_order(handle_->plan, path.c_str(), similarityThreshold, rowFlags_), "load row order")) return false;
+        rowReorderingTime_ = 0.0f;
+        refreshRows();
+        return true;
+    }
     void setBlockSize(UIN blockSize) { blockSize_ = blockSize; }           // pin the clustering block size (0 = calculateBlockSize)
     void setRowFlags(uint32_t flags) { rowFlags_ = flags; }               // BSMR_ROW_REFERENCE_COMPAT / EXACT_REDUCE / IDENTITY
     float formatBuildTime() const { return formatBuildTime_; }

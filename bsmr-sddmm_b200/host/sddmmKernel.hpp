@@ -1,5 +1,5 @@
-// sddmm_gpu entry points with the reference's signatures (include/sddmmKernel.cuh:19-39,
-// src/sddmmKernel.cu:2518-2762).  They forward to bsmr_sddmm / bsmr_sddmm_host.
+// sddmm_gpu entry points with the reference's signatures (include/sddmmKernel.cuh:19-47,
+// src/sddmmKernel.cu:2518-2848).  They forward to bsmr_sddmm / bsmr_sddmm_host / bsmr_sddmm_batch.
 #pragma once
 
 #include "BSMR.hpp"
@@ -54,4 +54,19 @@ inline void sddmm_gpu(const Matrix<float>& matrixA, const Matrix<float>& matrixB
     logger.blockDim_dense_.x = 544;
     logger.gridDim_sparse_.x = static_cast<unsigned>((info.num_sparse_values + 255) / 256);
     logger.blockDim_sparse_.x = 256;
+}
+
+// numBatch (A, B, P) triples on one pattern, device pointers strided by M*K, N*K and nnz; `time` = total ms of the batch
+// (include/sddmmKernel.cuh:41-47, src/sddmmKernel.cu:2764-2848).
+inline void sddmm_gpu_batch(const UIN numBatch, const UIN M, const UIN N, const UIN K, const UIN nnz, const float* matrixA,
+                            const float* matrixB, const RPHM& rphm, float* matrixP, float& time) {
+    (void)M;
+    (void)N;
+    (void)nnz;
+    time = 0.0f;
+    if (!rphm.plan()) {
+        fprintf(stderr, "sddmm_gpu_batch: RPHM has no device format\n");
+        return;
+    }
+    bsmr_host::ok(bsmr_sddmm_batch(rphm.plan(), numBatch, K, matrixA, matrixB, matrixP, BSMR_SDDMM_DEFAULT, &time), "sddmm_gpu_batch");
 }
