@@ -884,11 +884,11 @@ int bsmr_sddmm_host(bsmr_plan* plan, uint32_t K, const float* hA, const float* h
 // A call = H2D A,B -> zero P -> kernels -> D2H P, exactly what bsmr_sddmm_host does, but asynchronous: successive calls
 // alternate between two slots of device buffers, the kernels run on the context's stream and the copies on a copy
 // stream, ordered by the slots' events; the host blocks only in _wait.
-// Copy order.  The copy-out of call i is queued BEHIND the copy-in of call i + 1 (it is held back until the next submit
-// or until somebody waits for it): on one in-order copy stream that gives H2D(i+1) | kernels(i) in parallel, then
-// D2H(i), and never two copies in opposite directions at once.  Measured on this pool's B200 hosts, a 6.4 MB H2D and a
-// 3 MB D2H running concurrently drop to ~12 GB/s each on some boxes (53 GB/s alone; tests/pcie_probe.py), which made
-// the two-stream variant (environment BSMR_HOST_PIPE_DUPLEX) anything between 146 and 390 us per nips step.
+// Copy order, half-duplex mode.  The copy-out of call i is queued BEHIND the copy-in of call i + 1 (it is held back until
+// the next submit or until somebody waits for it): on one in-order copy stream that gives H2D(i+1) | kernels(i) in
+// parallel, then D2H(i), and never two copies in opposite directions at once.  Duplex mode: two copy streams, the
+// copy-out queued at once.  Which of the two a host gets is measured (probe_duplex below).
+static int probe_duplex(bsmr_ctx* ctx);
 static int ensure_host_pipeline(bsmr_plan* plan) {
     bsmr_ctx* ctx = plan->ctx;
     if (!ctx->copy_in_stream) BSMR_CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_in_stream, cudaStreamNonBlocking));
@@ -898,13 +898,99 @@ static int ensure_host_pipeline(bsmr_plan* plan) {
         if (!s.compute_done) BSMR_CUDA_OK(cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming));
         if (!s.d2h_done) BSMR_CUDA_OK(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
     }
-    return BSMR_OK;
+    return probe_duplex(ctx);
 }
 
-static bool host_pipe_duplex() {
-    static const bool v = std::getenv("BSMR_HOST_PIPE_DUPLEX") != nullptr;
+// Copies between pinned host memory and the device: cudaMemcpyAsync, or -- for copies of at most
+// BSMR_HOST_COPY_KERNEL_MAX bytes whose host side is mapped into the device's address space (cudaHostAlloc /
+// cudaHostRegister memory under UVA) -- a kernel that reads or writes the host memory directly over PCIe.  Off by
+// default (threshold 0): measured on the nips step, 200 us with the copy engines, 204 with A through the kernel, 212
+// with everything through kernels (tests/e2e_probe.py).
+}  // extern "C"
+namespace {
+__global__ void copy16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n16) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+size_t copy_kernel_max_bytes() {
+    static const size_t v = [] { const char* e = std::getenv("BSMR_HOST_COPY_KERNEL_MAX"); return e ? (size_t)std::atoll(e) : (size_t)0; }();
     return v;
 }
+// device-side alias of a pinned host pointer, or nullptr
+void* mapped_alias(const void* host) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+int copy_async(bsmr_ctx* ctx, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream) {
+    if (bytes == 0) return BSMR_OK;
+    const void* host = kind == cudaMemcpyHostToDevice ? src : dst;
+    if (bytes <= copy_kernel_max_bytes() && bytes % 16 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+        if (void* alias = mapped_alias(host)) {
+            const void* s = kind == cudaMemcpyHostToDevice ? alias : src;
+            void* d = kind == cudaMemcpyHostToDevice ? dst : alias;
+            const size_t n16 = bytes / 16;
+            const unsigned grid = static_cast<unsigned>(std::min<size_t>((n16 + 255) / 256, static_cast<size_t>(ctx->sm_count) * 4));
+            copy16_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(s), static_cast<uint4*>(d), n16);
+            ctx->launches++;
+            BSMR_CUDA_OK(cudaGetLastError());
+            return BSMR_OK;
+        }
+    }
+    BSMR_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, kind, stream));
+    return BSMR_OK;
+}
+}  // namespace
+extern "C" {
+
+// Whether copies in opposite directions may run at the same time.  On some hosts of this pool a 6.4 MB H2D and a 3 MB D2H
+// in flight together drop to ~12 GB/s each (53 GB/s alone), on others they overlap perfectly (140 instead of 200 us per
+// nips step).  Decided once per process by timing 2 MB each way, back to back and concurrently (about a millisecond);
+// environment BSMR_HOST_PIPE_DUPLEX = 0 / 1 overrides.
+static int g_duplex = -1;
+static int probe_duplex(bsmr_ctx* ctx) {
+    if (g_duplex >= 0) return BSMR_OK;
+    if (const char* e = std::getenv("BSMR_HOST_PIPE_DUPLEX")) {
+        g_duplex = std::atoi(e) != 0 ? 1 : 0;
+        return BSMR_OK;
+    }
+    const size_t bytes = 2u << 20;
+    void *h = nullptr, *d = nullptr;
+    if (cudaHostAlloc(&h, 2 * bytes, cudaHostAllocDefault) != cudaSuccess || cudaMalloc(&d, 2 * bytes) != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (h) cudaFreeHost(h);
+        g_duplex = 0;
+        return BSMR_OK;
+    }
+    char* hb = static_cast<char*>(h);
+    char* db = static_cast<char*>(d);
+    auto run = [&](bool duplex) -> double {
+        double best = 1e30;
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaStreamSynchronize(ctx->copy_in_stream);
+            cudaStreamSynchronize(ctx->copy_out_stream);
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int i = 0; i < 3; ++i) {
+                cudaMemcpyAsync(db, hb, bytes, cudaMemcpyHostToDevice, ctx->copy_in_stream);
+                cudaMemcpyAsync(hb + bytes, db + bytes, bytes, cudaMemcpyDeviceToHost, duplex ? ctx->copy_out_stream : ctx->copy_in_stream);
+            }
+            cudaStreamSynchronize(ctx->copy_in_stream);
+            cudaStreamSynchronize(ctx->copy_out_stream);
+            const double t = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+            if (rep > 0 && t < best) best = t;
+        }
+        return best;
+    };
+    const double t_seq = run(false), t_dup = run(true);
+    g_duplex = t_dup < 0.8 * t_seq ? 1 : 0;
+    cudaFree(d);
+    cudaFreeHost(h);
+    (void)cudaGetLastError();
+    return BSMR_OK;
+}
+static bool host_pipe_duplex() { return g_duplex == 1; }
 
 // queue the copy-out of a slot whose kernels have been issued
 static int queue_copy_out(bsmr_plan* plan, bsmr_plan::HostSlot& s) {
@@ -912,7 +998,7 @@ static int queue_copy_out(bsmr_plan* plan, bsmr_plan::HostSlot& s) {
     bsmr_ctx* ctx = plan->ctx;
     cudaStream_t cs = host_pipe_duplex() ? ctx->copy_out_stream : ctx->copy_in_stream;
     BSMR_CUDA_OK(cudaStreamWaitEvent(cs, s.compute_done, 0));
-    if (plan->nnz) BSMR_CUDA_OK(cudaMemcpyAsync(s.hP, s.dP.ptr, s.dP.bytes(), cudaMemcpyDeviceToHost, cs));
+    BSMR_TRY(copy_async(ctx, s.hP, s.dP.ptr, s.dP.bytes(), cudaMemcpyDeviceToHost, cs));
     BSMR_CUDA_OK(cudaEventRecord(s.d2h_done, cs));
     s.d2h_queued = true;
     return BSMR_OK;
@@ -943,8 +1029,8 @@ int bsmr_sddmm_host_submit(bsmr_plan* plan, uint32_t K, const float* hA, const f
     BSMR_TRY(s.dP.alloc(plan->nnz));
     // copy-in: the slot's previous kernels must be done with dA / dB
     if (s.in_flight) BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->copy_in_stream, s.compute_done, 0));
-    BSMR_CUDA_OK(cudaMemcpyAsync(s.dA.ptr, hA, na * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in_stream));
-    BSMR_CUDA_OK(cudaMemcpyAsync(s.dB.ptr, hB, nb * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in_stream));
+    BSMR_TRY(copy_async(ctx, s.dA.ptr, hA, na * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in_stream));
+    BSMR_TRY(copy_async(ctx, s.dB.ptr, hB, nb * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in_stream));
     BSMR_CUDA_OK(cudaEventRecord(s.h2d_done, ctx->copy_in_stream));
     // the copy-out of the previous call goes behind this copy-in
     if (&prev != &s && prev.in_flight) BSMR_TRY(queue_copy_out(plan, prev));

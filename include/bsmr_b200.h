@@ -203,10 +203,10 @@ int bsmr_plan_execution_choice(bsmr_plan* plan, uint32_t K, uint32_t* flags);
 
 /* Pipelined form of the host-data overload: the same H2D A,B -> zero P -> kernels -> D2H P, but the call returns as
  * soon as the work is queued.  Successive calls alternate between two slots of device buffers; the kernels run on the
- * context's stream, the copies on a copy stream, so the copy-in of call i+1 overlaps the kernels of call i.  The
- * copy-out of a call is queued behind the copy-in of the next one (or by _wait): copies in opposite directions never
- * run at the same time, which on some hosts of this pool costs 4x in rate (environment BSMR_HOST_PIPE_DUPLEX = two
- * copy streams, copy-out queued at once).  hA / hB must stay valid and hP must not be read until
+ * context's stream, the copies on copy streams, so the copy-in of call i+1 overlaps the kernels of call i.  Whether
+ * copies in opposite directions may overlap is measured once per process (on some hosts of this pool that costs 4x in
+ * rate, on others it is free): if not, the copy-out of a call is queued behind the copy-in of the next one (or by
+ * _wait) on one copy stream; environment BSMR_HOST_PIPE_DUPLEX = 0 / 1 overrides.  hA / hB must stay valid and hP must not be read until
  * bsmr_sddmm_host_wait(plan, ticket) returns (BSMR_TICKET_ALL: every call submitted so far); pinned host memory is
  * needed for the copies to be asynchronous.  One caller thread per plan, as everywhere in this ABI.          */
 #define BSMR_TICKET_ALL 0xFFFFFFFFFFFFFFFFull
