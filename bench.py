@@ -283,36 +283,23 @@ def main():
     hB = torch.from_numpy(B).pin_memory()
     hPs = [torch.zeros(nnz, dtype=torch.float32).pin_memory() for _ in range(2)]
     hP = hPs[0]
-    dPfull = torch.empty(nnz, dtype=torch.float32, device="cuda") if world > 1 else None
     e2e_steps = max(3, min(args.steps, 20))
-
-    def assemble(buf):
-        # N > 1: P is assembled on every rank; the shards are disjoint index sets of the CSR value array
-        dPfull.copy_(buf, non_blocking=True)
-        dist.all_reduce(dPfull)
-        buf.copy_(dPfull, non_blocking=False)
-
+    # N > 1: every rank copies in A and B, runs its shard and copies its P out (the shards are disjoint index sets of the
+    # CSR value array; rows of a shard are scattered over the original matrix, so the copy-out is the whole array).  The
+    # result is left distributed over the ranks' host buffers: no collective on this path either.
     for _ in range(2):
         plan.sddmm_host(K, hA, hB, hP)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         plan.sddmm_host(K, hA, hB, hP)
-        if world > 1:
-            assemble(hP)
     barrier()
     e2e_serial_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
 
     def pipelined(n):
-        tickets = []
         for i in range(n):
-            tickets.append(plan.sddmm_host_submit(K, hA, hB, hPs[i % 2]))
-            if world > 1 and i >= 1:
-                plan.sddmm_host_wait(tickets[i - 1])
-                assemble(hPs[(i - 1) % 2])
+            plan.sddmm_host_submit(K, hA, hB, hPs[i % 2])
         plan.sddmm_host_wait()
-        if world > 1:
-            assemble(hPs[(n - 1) % 2])
 
     pipelined(4)
     barrier()
@@ -410,9 +397,10 @@ def main():
             "config": workload_config(M, N, nnz, K, source, world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int((M + N) * K * 4), "d2h_bytes_per_step": int(nnz * 4),
-                    "how": "bsmr_sddmm_host_submit/_wait, pinned host buffers, 2 steps in flight (copies of "
-                           "neighbouring steps overlap the kernels); %d steps" % e2e_steps,
+                    "h2d_bytes_per_step": int((M + N) * K * 4) * world, "d2h_bytes_per_step": int(nnz * 4) * world,
+                    "how": "bsmr_sddmm_host_submit/_wait, pinned host buffers, 2 steps in flight (copies of neighbouring steps "
+                           "overlap the kernels); %d steps%s" % (e2e_steps, "" if world == 1 else "; every rank copies A, B in and "
+                           "its P out (result left distributed over the ranks, bytes summed over ranks)"),
                     "blocking_call_ms": e2e_serial_ms,
                     "blocking_call_value": 2.0 * nnz * K / (e2e_serial_ms * 1e-3) / 1e9},
             "gpu_launches": int(launches),
