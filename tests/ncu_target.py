@@ -18,7 +18,7 @@ def main():
     identity = "identity" in sys.argv[4:]
     nowide = "nowide" in sys.argv[4:]          # force the reference's split: dense-block + residual kernels only
     s = pkg.synth
-    gen = {"nips": lambda: s.nips_like(), "graph17": lambda: s.rmat(17, 3_000_000, 17),
+    gen = {"nips": lambda: s.nips_like(), "graph17": lambda: s.rmat(17, 3_000_000, 17), "graph20": lambda: s.rmat(20, 30_000_000, 20),
            "blocks16k": lambda: s.block_structured(16000, 16000, seed=5, groups=200, cols_per_group=96, noise=0.001),
            "mask90": lambda: s.dlmc_mask(0.90)}[name]
     M, N, ro, ci = gen()

@@ -1,4 +1,4 @@
-"""B200 box: per-CTA time stamps of the wide kernel (not a pytest test).  python tests/wide_trace.py [K] [workload]"""
+"""B200 box: per-CTA time stamps of the wide kernel (not a pytest test).  python tests/wide_trace.py [K] [workload] [cold]"""
 import ctypes as C
 import os
 import sys
@@ -34,6 +34,8 @@ def main():
     lib = pkg.lib()
     lib.bsmr_debug_set_wide_trace.argtypes = [C.c_void_p]
     lib.bsmr_debug_set_wide_trace(trace.data_ptr())
+    if "cold" in sys.argv:      # L2 flushed before the traced launch, like a timed step of bench.py
+        torch.empty(512 << 20, dtype=torch.uint8, device="cuda").fill_(1)
     ms = plan.sddmm(K, dA, dB, dP, flags=pkg.SDDMM_THREE_KERNEL)
     torch.cuda.synchronize()
     raw = trace.cpu().numpy().reshape(148, 32)
