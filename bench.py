@@ -418,7 +418,7 @@ def main():
                                  "residual_nnz_outside_wide": int(info["num_residual_values"]),
                                  "wide_format_ms": info["wide_format_ms"]},
                         "gflops_incl_reorder": 2.0 * nnz * K / ((ms_per_step + reorder_warm_ms) * 1e-3) / 1e9},
-            "execution_plan": {0: "wide row groups + BSMR split (three kernels)", 4: "BSMR split (dense blocks + residual)",
+            "execution_plan": ("pinned by BSMR_NO_AUTOTUNE: " if os.environ.get("BSMR_NO_AUTOTUNE") else "") + {0: "wide row groups + BSMR split (three kernels)", 4: "BSMR split (dense blocks + residual)",
                                2: "CSR-order residual kernel"}.get(exec_choice, "?") + " (chosen by measurement per K)",
             "kernels": {"wide_ms_cold": wide_ms, "dense_ms_cold": dense_ms, "residual_ms_cold": res_ms, "step_ms_hot_l2": hot_ms,
                         "gflops_hot_l2": 2.0 * shard_nnz * K / (hot_ms * 1e-3) / 1e9}}

@@ -23,7 +23,8 @@ def main():
         agg[n][0] += 1
         agg[n][1] += v
     tot = sum(v[1] for v in agg.values())
-    print("# ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv python bench.py --steps 5 --warmup 3   (B200, after the same command exited 0 without ncu)")
+    print("# BSMR_NO_AUTOTUNE=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv python bench.py --steps 5 --warmup 3   (B200, after the same command exited 0 without ncu)")
+    print("# (BSMR_NO_AUTOTUNE pins the execution plan: under ncu every launch is serialised and replayed, which distorts the timing the per-K choice is made on)")
     print("# full list: %s.  Times are ns, cold-cache and serialised: compare shares." % sys.argv[1])
     print("# The timed step of bench.py launches ONE kernel on the nips workload (wide_sddmm_kernel: all six row groups are wide), so its share of the step is 100 %.")
     print("# Everything else below is the reorder (4 calls: first + 3 warm; bsa_cluster_kernel is the clustering chain), the L2 flush (FillFunctor),")
