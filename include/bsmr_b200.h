@@ -195,7 +195,7 @@ int bsmr_sddmm_host(bsmr_plan* plan, uint32_t K, const float* hA, const float* h
                     int iterations, uint32_t flags, float* ms_per_iteration, float* total_ms);
 
 /* A call with BSMR_SDDMM_DEFAULT runs, per K, the fastest of three execution plans over the same nnz, chosen by
- * measurement on the first such call (two passes each; that first call therefore synchronises): the three-kernel
+ * measurement on the first such call (four passes each; that first call therefore synchronises): the three-kernel
  * plan (wide row groups + BSMR split), the BSMR split alone (= BSMR_SDDMM_NO_WIDE), or, on an unsharded plan, the
  * CSR-order residual kernel (= BSMR_SDDMM_NO_REORDER).  The choice is forgotten at the next column reorder /
  * set_shard; environment BSMR_NO_AUTOTUNE pins the three-kernel plan.  _execution_choice returns the flags chosen. */
