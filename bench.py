@@ -358,12 +358,15 @@ def main():
     dom, dom_ms, dom_bytes = max(parts, key=lambda x: x[1])
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     # DRAM bytes per launch of that kernel from the committed ncu --set full capture of this workload, if any
-    traffic = None
+    traffic = tensor_pct = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath) and world == 1:
-        traffic = json.load(open(tpath)).get("K%d" % K, {}).get(dom.split(" ")[0])
+        committed = json.load(open(tpath))
+        traffic = committed.get("K%d" % K, {}).get(dom.split(" ")[0])
+        tensor_pct = committed.get("tensor_pipe_active_pct_K%d" % K, {}).get(dom.split(" ")[0])
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "tensor_pipe_active_pct": tensor_pct,     # sm__pipe_tensor_cycles_active of the committed ncu capture (profiles/)
                 "algorithmic_bytes_per_launch": int(dom_bytes), "kernel_ms": dom_ms,
                 "other_kernels_ms": {n: ms for n, ms, _ in parts if n != dom},
                 "step": {"algorithmic_bytes": int(step_bytes), "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,

@@ -59,6 +59,8 @@ def main():
                 return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
             try:
                 traffic.setdefault("K%d" % K, {})[short] = int(num("dram__bytes_read.sum") + num("dram__bytes_write.sum"))
+                traffic.setdefault("tensor_pipe_active_pct_K%d" % K, {})[short] = round(
+                    float(r[col["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]]), 2)
             except (KeyError, ValueError):
                 pass
         with open(os.path.join(HERE, "%s_ncu_full_%s.txt" % (tag, name.replace("prof_%s_" % tag, ""))), "w") as f:
