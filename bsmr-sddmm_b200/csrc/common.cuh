@@ -235,6 +235,8 @@ struct bsmr_plan {
     bsmr::DevBuf<uint32_t> w_sb_off;          // list form: [(column quarter * 2 + row half) * #tiles + tile] (+1): first slot of the unit
     std::vector<uint32_t> h_wt_group;         // row group of every wide tile
     bsmr::DevBuf<uint32_t> w_cta_begin;       // CTA -> first tile, for tiles [w_part_begin, w_part_end) (wide_partition)
+    bsmr::DevBuf<uint4> w_cta_rec;            // per CTA two words: {first tile, end tile, group of the first tile, its first column id},
+                                              // {the first tile's wt_meta}: everything the kernel needs to issue its first loads
     uint32_t w_part_begin = 0, w_part_end = 0, w_grid = 0;
     // dense-block tiles and residual entries of the groups that are NOT wide (what runs next to the wide kernel)
     bsmr::DevBuf<uint32_t> tile_list2;        // tile ids (ascending)

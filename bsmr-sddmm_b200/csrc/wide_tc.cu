@@ -95,7 +95,7 @@ struct WideParams {
     uint32_t sgp;                    // sub-groups per pass: 2 (A images of the whole group resident, K <= 128) or 1 (K = 256)
     uint32_t num_rows;               // reordered (non-empty) rows
     uint32_t M, N;                   // out-of-bounds coordinates for missing rows / columns (TMA zero fill)
-    const uint32_t* cta_begin;       // gridDim.x + 1 tile indices: CTA b owns tiles [cta_begin[b], cta_begin[b + 1])
+    const uint4* cta_rec;            // per CTA: {first tile, end tile, group of the first tile, its first column id}, {its tile_meta}
     const uint4* tile_meta;          // {group, first column (offset into cols, multiple of 4), #columns, 0}
     const uint32_t* cols;            // distinct columns of the wide groups, ascending inside a group
     uint32_t num_tiles;              // wide tiles of the plan (stride of the per-quarter list streams)
@@ -139,7 +139,8 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint32_t passes = kWSub / SGP;                  // K = 256: the tile range is walked once per sub-group
     const uint32_t naccs = kWTmemCols / (kWCols * SGP);   // accumulator sets in rotation (one set = SGP x 128 columns)
     // tile range of this CTA (host-side partition: CTAs do not straddle row groups when there are enough of them)
-    const uint32_t my_begin = __ldg(p.cta_begin + blockIdx.x), my_end = __ldg(p.cta_begin + blockIdx.x + 1);
+    const uint4 rec0 = __ldg(p.cta_rec + 2 * blockIdx.x), rec1 = __ldg(p.cta_rec + 2 * blockIdx.x + 1);
+    const uint32_t my_begin = rec0.x, my_end = rec0.y;
 
     if (warp == 0 && lane == 0) {
         for (uint32_t s = 0; s < S; ++s) {
@@ -184,7 +185,7 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // of its warp's scheduler, and with 32 of them per stage the epilogue warps' LDS / STS waited ~700-1000 cycles
         // behind them (measured with clock64 stamps).
         auto fetch_cols = [&](uint32_t t, uint32_t& ncols, uint32_t& flags, int4& cols) {
-            const uint4 m = __ldg(p.tile_meta + t);
+            const uint4 m = t == my_begin ? rec1 : __ldg(p.tile_meta + t);      // the first tile's meta came with the start record
             ncols = m.z;
             flags = (p.debug & 256u) ? 0u : m.w;
             cols = make_int4((int)p.N, (int)p.N, (int)p.N, (int)p.N);
@@ -204,7 +205,7 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (my_begin < my_end) fetch_cols(my_begin, ncols, flags, cols);
             for (uint32_t t = my_begin; t < my_end; ++t) {
                 if (t + 1 < my_end) fetch_cols(t + 1, ncols_next, flags_next, cols_next);   // indices of the next tile: off the critical path
-                const uint32_t g = __ldg(p.tile_meta + t).x;
+                const uint32_t g = t == my_begin ? rec0.z : __ldg(p.tile_meta + t).x;
                 const uint32_t key = g * 2 + pass;
                 const bool new_key = key != cur_key;
                 int4 arows[2];
@@ -260,7 +261,11 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         else mbar_arrive(&tail->b_full[stage]);
                     }
                     uint8_t* bst = b_ring + (size_t)stage * kWBStageBytes;
-                    if (do_whole) tma_load_2d(&map_b128, &tail->b_full[stage], bst, (int)(kc * kWChunk), cols.x);
+                    if (do_whole) {
+                        // the first tile's first column id came with the start record: no wait for the column list
+                        if (t == my_begin) tma_load_2d(&map_b128, &tail->b_full[stage], bst, (int)(kc * kWChunk), (int)rec0.w);
+                        else tma_load_2d(&map_b128, &tail->b_full[stage], bst, (int)(kc * kWChunk), cols.x);
+                    }
                     if (do_qrun) tma_load_2d(&map_b32, &tail->b_full[stage], bst + myq * 4096, (int)(kc * kWChunk), cols.x);
                     if (do_gather) tma_gather4(&map_b, &tail->b_full[stage], bst + rq * 512, (int)(kc * kWChunk), cols);
                     if (++stage == S) { stage = 0; phase ^= 1; }
@@ -604,6 +609,20 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
 }  // namespace
 
+namespace {
+// start records: one dependent load instead of three (CTA range -> tile -> column ids) before a CTA's first TMA request;
+// with a cold L2 every link of that chain is a DRAM round trip
+__global__ void wide_cta_rec_kernel(uint32_t ctas, const uint32_t* __restrict__ cta_begin, const uint4* __restrict__ meta,
+                                    const uint32_t* __restrict__ cols, uint4* __restrict__ rec) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= ctas) return;
+    const uint32_t t0 = cta_begin[b], t1 = cta_begin[b + 1];
+    const uint4 m = t0 < t1 ? meta[t0] : make_uint4(0, 0, 0, 0);
+    rec[2 * b] = make_uint4(t0, t1, m.x, (t0 < t1 && m.z) ? cols[m.y] : 0u);
+    rec[2 * b + 1] = m;
+}
+}  // namespace
+
 // CTA -> tile range table for the wide kernel over tiles [tile_begin, tile_end).  When there are at least as many
 // CTAs as row groups no CTA straddles a group (an A reload in mid-range costs K/32 serial L2 round trips): every
 // group first gets one CTA, the remaining CTAs go one by one to the group with the most tiles per CTA, and a group's
@@ -647,6 +666,11 @@ int wide_partition(bsmr_plan* plan, uint32_t tile_begin, uint32_t tile_end) {
     plan->w_grid = static_cast<uint32_t>(table.size()) - 1;
     BSMR_TRY(plan->w_cta_begin.alloc(table.size()));
     BSMR_CUDA_OK(cudaMemcpyAsync(plan->w_cta_begin.ptr, table.data(), table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    BSMR_TRY(plan->w_cta_rec.alloc(static_cast<size_t>(plan->w_grid) * 2));
+    wide_cta_rec_kernel<<<(plan->w_grid + 127) / 128, 128, 0, ctx->stream>>>(plan->w_grid, plan->w_cta_begin.ptr, plan->wt_meta.ptr, plan->w_cols.ptr,
+                                                                           plan->w_cta_rec.ptr);
+    ctx->launches++;
+    BSMR_CUDA_OK(cudaGetLastError());
     BSMR_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     return BSMR_OK;
 }
@@ -701,7 +725,7 @@ int launch_wide(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, f
     p.K = K; p.kchunks = kchunks; p.stages = stages; p.sgp = sgp;
     p.num_rows = static_cast<uint32_t>(plan->h_reordered_rows.size());
     p.M = plan->M; p.N = plan->N;
-    p.cta_begin = plan->w_cta_begin.ptr;
+    p.cta_rec = plan->w_cta_rec.ptr;
     p.tile_meta = plan->wt_meta.ptr;
     p.cols = plan->w_cols.ptr;
     p.num_tiles = plan->num_wide_tiles;
