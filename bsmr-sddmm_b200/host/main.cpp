@@ -1,34 +1,48 @@
-// BSMR-sddmm command line, same flags / flow / log keys as the reference's src/main.cu:6-42.
-//   BSMR-sddmm -f matrix.mtx -k 128 -a 0.3 -d 0.3 [-t 1 -l logdir/] [-b blockSize]
-// Define VALIDATE (make VALIDATE=1) to run check_rphm + checkSddmm after the SDDMM like the reference's
-// compile-time self-check (src/sddmm.cu:7,35-38).
+// Command-line front end of the B200 path: the flags, exit codes and log keys of the reference's binary
+// (`-f matrix -k K -a alpha -d delta [-t 1 -l logdir/]`, src/main.cu), driven through the host mirror in this directory.
+//   make VALIDATE=1 additionally runs check_rphm + checkSddmm after the SDDMM (the reference's compile-time self-check,
+//   src/sddmm.cu:7,35-38).
+#include <cstdio>
+
 #include "sddmm.hpp"
 
-int main(int argc, char* argv[]) {
-    Options options(argc, argv);
+namespace {
 
-    sparseMatrix::CSR<float> matrixS;
-    if (!matrixS.initializeFromMatrixFile(options.inputFile())) {
+// the dense operands of one run: A is M x K row-major, B is K x N column-major, both from makeData()
+struct Operands {
+    Matrix<float> lhs, rhs;
+    Operands(size_t rows, size_t cols, size_t depth)
+        : lhs(rows, depth, MatrixStorageOrder::row_major), rhs(depth, cols, MatrixStorageOrder::col_major) {
+        lhs.makeData();
+        rhs.makeData();
+    }
+};
+
+// one SDDMM on the pattern: reorder, compute, print the log
+int run_single(const Options& opts, const sparseMatrix::CSR<float>& pattern) {
+    Operands ab(pattern.row(), pattern.col(), opts.K());
+    Logger log;
+    log.getInformation(opts);
+    log.getInformation(pattern);
+    log.getInformation(ab.lhs, ab.rhs);
+    sparseMatrix::CSR<float> result(pattern);          // carries the pattern in, the values out
+    sddmm(opts, ab.lhs, ab.rhs, result, log);
+    log.printLogInformation();
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+    const Options opts(argc, argv);
+    sparseMatrix::CSR<float> pattern;
+    if (!pattern.initializeFromMatrixFile(opts.inputFile())) {
         fprintf(stderr, "Error, matrix S initialize failed.\n");
         return -1;
     }
-    if (options.testMode()) {
-        sddmm_testMode(options, matrixS);
+    if (opts.testMode()) {                              // the sweep that produced the reference's published logs
+        sddmm_testMode(opts, pattern);
         return 0;
     }
-    const size_t K = options.K();
-    Matrix<float> matrixA(matrixS.row(), K, MatrixStorageOrder::row_major);
-    matrixA.makeData();
-    Matrix<float> matrixB(K, matrixS.col(), MatrixStorageOrder::col_major);
-    matrixB.makeData();
-
-    Logger logger;
-    logger.getInformation(options);
-    logger.getInformation(matrixS);
-    logger.getInformation(matrixA, matrixB);
-
-    sparseMatrix::CSR<float> matrixP(matrixS);
-    sddmm(options, matrixA, matrixB, matrixP, logger);
-    logger.printLogInformation();
-    return 0;
+    return run_single(opts, pattern);
 }

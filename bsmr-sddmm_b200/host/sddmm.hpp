@@ -12,92 +12,104 @@
 #include "host.hpp"
 #include "sddmmKernel.hpp"
 
-inline void fillDeviceName(Logger& logger) {
+namespace bsmr_host {
+
+// name of the device the context runs on, for the log's "GPU" key
+inline void noteDevice(Logger& log) {
     char name[256] = "";
-    bsmr_ctx* ctx = bsmr_host::context();
-    if (ctx && bsmr_ctx_device_name(ctx, name, sizeof(name)) == BSMR_OK) logger.gpu_ = name;
+    bsmr_ctx* ctx = context();
+    if (ctx && bsmr_ctx_device_name(ctx, name, sizeof(name)) == BSMR_OK) log.gpu_ = name;
 }
 
-// BSMR reorder -> RPHM -> sddmm_gpu -> evaluationReordering (src/sddmm.cu:10-39).  P carries S's pattern in
-// and the result values out.
+// what a reorder contributes to a log record
+inline void noteReorder(Logger& log, const BSMR& order) {
+    log.rowReorderingTime_ = order.rowReorderingTime();
+    log.colReorderingTime_ = order.colReorderingTime();
+    log.reorderingTime_ = order.reorderingTime();
+    log.formatBuildTime_ = order.formatBuildTime();
+    log.numRowPanels_ = order.numRowPanels();
+    log.numClusters_ = order.numClusters();
+    noteDevice(log);
+}
+
+// device format + SDDMM + density statistics for an order that is already in place; the result lands in `pattern`
+inline void computeAndEvaluate(const Matrix<float>& lhs, const Matrix<float>& rhs, const BSMR& order, sparseMatrix::CSR<float>& pattern,
+                               Logger& log) {
+    const RPHM format(pattern, order);
+    sddmm_gpu(lhs, rhs, format, pattern, log);
+    evaluationReordering(pattern, order, log);
+}
+
+// file name of one record of the test-mode sweep (src/sddmm.cu:107-110: BSMR_k_<K>_a_<alpha>_d_<delta>.log)
+inline std::string sweepLogName(const Options& opts, UIN k, float alpha, float delta) {
+    return opts.outputLogDirectory() + "BSMR_k_" + util::to_trimmed_string(k) + "_a_" + util::to_trimmed_string(alpha) + "_d_" +
+           util::to_trimmed_string(delta) + ".log";
+}
+
+}  // namespace bsmr_host
+
+// The reference's entry point (include/sddmm.hpp:8-12, src/sddmm.cu:10-39): BSMR reorder with the options' alpha and delta,
+// device format, SDDMM, density statistics.  P carries S's pattern in and the result values out.
 inline void sddmm(const Options& options, const Matrix<float>& matrixA, const Matrix<float>& matrixB, sparseMatrix::CSR<float>& matrixP,
                   Logger& logger) {
-    BSMR bsmr;
-    bsmr.setBlockSize(options.blockSize());
-    bsmr.rowReordering(options.similarityThresholdAlpha(), matrixP, 1);
-    bsmr.colReordering(options.blockDensityThresholdDelta(), matrixP, std::vector<UIN>(), 1);
-    logger.rowReorderingTime_ = bsmr.rowReorderingTime();
-    logger.colReorderingTime_ = bsmr.colReorderingTime();
-    logger.reorderingTime_ = bsmr.reorderingTime();
-    logger.formatBuildTime_ = bsmr.formatBuildTime();
-    logger.numRowPanels_ = bsmr.numRowPanels();
-    logger.numClusters_ = bsmr.numClusters();
-    fillDeviceName(logger);
-
-    RPHM rphm(matrixP, bsmr);
-    sddmm_gpu(matrixA, matrixB, rphm, matrixP, logger);
-    evaluationReordering(matrixP, bsmr, logger);
+    BSMR order;
+    order.setBlockSize(options.blockSize());
+    order.rowReordering(options.similarityThresholdAlpha(), matrixP, 1);
+    order.colReordering(options.blockDensityThresholdDelta(), matrixP, std::vector<UIN>(), 1);
+    bsmr_host::noteReorder(logger, order);
+    bsmr_host::computeAndEvaluate(matrixA, matrixB, order, matrixP, logger);
 #ifdef VALIDATE
-    check_rphm(matrixP, bsmr, rphm, options.blockDensityThresholdDelta());
+    check_rphm(matrixP, order, RPHM(matrixP, order), options.blockDensityThresholdDelta());
     checkSddmm(matrixA, matrixB, matrixP, matrixP);
 #endif
 }
 
-// GPU result vs the host computation, reference tolerance (src/sddmm.cu:41-59)
+// GPU result against the host computation under the reference's tolerance (include/sddmm.hpp:18-21, src/sddmm.cu:41-59;
+// same two lines of output)
 inline bool checkSddmm(const Matrix<float>& matrixA, const Matrix<float>& matrixB, const sparseMatrix::CSR<float>& matrixS,
                        const sparseMatrix::CSR<float>& matrixP) {
-    sparseMatrix::CSR<float> cpu(matrixS);
-    sddmm_cpu(matrixA, matrixB, matrixS, cpu);
+    sparseMatrix::CSR<float> expected(matrixS);
+    sddmm_cpu(matrixA, matrixB, matrixS, expected);
     printf("check cpu sddmm and BSMR sddmm: \n");
-    size_t numError = 0;
-    if (!checkData(cpu.values(), matrixP.values(), numError)) {
-        printf("[checkData : NO PASS Error rate : %2.2f%%]\n", static_cast<float>(numError) / static_cast<float>(matrixP.values().size()) * 100);
-        return false;
-    }
-    return true;
+    size_t wrong = 0;
+    const bool pass = checkData(expected.values(), matrixP.values(), wrong);
+    if (!pass) printf("[checkData : NO PASS Error rate : %2.2f%%]\n", 100.0f * static_cast<float>(wrong) / static_cast<float>(matrixP.values().size()));
+    return pass;
 }
 
-// alpha x delta x K sweep, one appended log record per configuration (src/sddmm.cu:62-118)
+// `-t 1` (include/sddmm.hpp:14-16, src/sddmm.cu:62-118): the alpha x delta x K grid the reference's published logs come
+// from, one record appended per point to <logdir>/BSMR_k_*_a_*_d_*.log.  The row order is computed once per alpha and
+// shared by all deltas and Ks, the column order once per (alpha, delta).
 inline void sddmm_testMode(const Options& options, sparseMatrix::CSR<float>& matrixP) {
-    const std::vector<float> alphas = {0.1f, 0.3f, 0.5f, 0.7f, 0.9f};
-    const std::vector<float> deltas = {0.0f, 0.1f, 0.3f, 0.5f, 0.7f, 0.9f, 1.1f};
-    const std::vector<UIN> Ks = {32, 64, 128, 256};
-    BSMR bsmr;
-    bsmr.setBlockSize(options.blockSize());
-    for (const float alpha : alphas) {
-        bsmr.rowReordering(alpha, matrixP);
-        for (const float delta : deltas) {
-            for (const UIN k : Ks) {
-                Matrix<float> matrixA(matrixP.row(), k, row_major);
-                matrixA.makeData();
-                Matrix<float> matrixB(k, matrixP.col(), col_major);
-                matrixB.makeData();
-                Logger logger;
-                logger.getInformation(options);
-                logger.getInformation(matrixP);
-                logger.getInformation(matrixA, matrixB);
-                logger.alpha_ = alpha;
-                logger.delta_ = delta;
-                fillDeviceName(logger);
-                bsmr.colReordering(delta, matrixP);
-                logger.rowReorderingTime_ = bsmr.rowReorderingTime();
-                logger.colReorderingTime_ = bsmr.colReorderingTime();
-                logger.reorderingTime_ = bsmr.reorderingTime();
-                logger.formatBuildTime_ = bsmr.formatBuildTime();
-                logger.numRowPanels_ = bsmr.numRowPanels();
-                logger.numClusters_ = bsmr.numClusters();
-                RPHM rphm(matrixP, bsmr);
-                sddmm_gpu(matrixA, matrixB, rphm, matrixP, logger);
-                evaluationReordering(matrixP, bsmr, logger);
-                const std::string logFile = options.outputLogDirectory() + "BSMR_k_" + util::to_trimmed_string(k) + "_a_" +
-                                            util::to_trimmed_string(alpha) + "_d_" + util::to_trimmed_string(delta) + ".log";
-                std::ofstream fout(logFile, std::ios::app);
-                if (fout.fail()) {
-                    fprintf(stderr, "Error, failed to open log file: %s\n", logFile.c_str());
+    static const float kAlphas[] = {0.1f, 0.3f, 0.5f, 0.7f, 0.9f};
+    static const float kDeltas[] = {0.0f, 0.1f, 0.3f, 0.5f, 0.7f, 0.9f, 1.1f};
+    static const UIN kDepths[] = {32, 64, 128, 256};
+    BSMR order;
+    order.setBlockSize(options.blockSize());
+    for (const float alpha : kAlphas) {
+        order.rowReordering(alpha, matrixP);
+        for (const float delta : kDeltas) {
+            for (const UIN depth : kDepths) {
+                Matrix<float> lhs(matrixP.row(), depth, row_major), rhs(depth, matrixP.col(), col_major);
+                lhs.makeData();
+                rhs.makeData();
+                Logger record;
+                record.getInformation(options);
+                record.getInformation(matrixP);
+                record.getInformation(lhs, rhs);
+                record.alpha_ = alpha;
+                record.delta_ = delta;
+                order.colReordering(delta, matrixP);        // per point, like the reference (its time is part of the record)
+                bsmr_host::noteReorder(record, order);
+                bsmr_host::computeAndEvaluate(lhs, rhs, order, matrixP, record);
+                const std::string path = bsmr_host::sweepLogName(options, depth, alpha, delta);
+                std::ofstream out(path, std::ios::app);
+                if (!out) {
+                    fprintf(stderr, "Error, failed to open log file: %s\n", path.c_str());
                     return;
                 }
-                fout << "\n---New data---\n";
-                logger.printLogInformation(fout);
+                out << "\n---New data---\n";
+                record.printLogInformation(out);
             }
         }
     }
