@@ -48,6 +48,9 @@ inline std::string sweepLogName(const Options& opts, UIN k, float alpha, float d
 
 }  // namespace bsmr_host
 
+inline bool checkSddmm(const Matrix<float>& matrixA, const Matrix<float>& matrixB, const sparseMatrix::CSR<float>& matrixS,
+                       const sparseMatrix::CSR<float>& matrixP);
+
 // The reference's entry point (include/sddmm.hpp:8-12, src/sddmm.cu:10-39): BSMR reorder with the options' alpha and delta,
 // device format, SDDMM, density statistics.  P carries S's pattern in and the result values out.
 inline void sddmm(const Options& options, const Matrix<float>& matrixA, const Matrix<float>& matrixB, sparseMatrix::CSR<float>& matrixP,
