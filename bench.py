@@ -212,9 +212,13 @@ def main():
         reorder_warm_ms = dt if reorder_warm_ms is None else min(reorder_warm_ms, dt)
     info = plan.info()
     shard_nnz = nnz
+    shard_sizes = None
     if world > 1:
         p0s, p1s, shard_nnz = plan.set_shard(rank, world)
         shard_panels = (p0s, p1s)
+        sizes = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([p1s - p0s, shard_nnz], dtype=torch.int64, device="cuda"))
+        shard_sizes = [[int(x[0]), int(x[1])] for x in sizes]
 
     dA = torch.from_numpy(A).cuda()
     dB = torch.empty((N, K), dtype=torch.float32, device="cuda")
@@ -257,7 +261,11 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     total_ms = float(sum(e0.elapsed_time(e1) for e0, e1 in events))
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    per_rank_ms = [total_ms / args.steps]
     if world > 1:
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        per_rank_ms = [float(x.item()) / args.steps for x in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
@@ -407,6 +415,8 @@ def main():
                     "blocking_call_ms": e2e_serial_ms,
                     "blocking_call_value": 2.0 * nnz * K / (e2e_serial_ms * 1e-3) / 1e9},
             "gpu_launches": int(launches),
+            "ms_per_step_by_rank": per_rank_ms,
+            "shards_panels_nnz": shard_sizes,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "reorder": {"row_ms": info["row_reordering_ms"], "col_ms": info["col_reordering_ms"],

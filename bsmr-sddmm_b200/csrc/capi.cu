@@ -596,9 +596,26 @@ int bsmr_plan_set_shard(bsmr_plan* plan, uint32_t rank, uint32_t world, uint32_t
         set_error("bsmr_plan_set_shard: reorder first");
         return BSMR_ERR_BAD_STATE;
     }
-    // contiguous ranges of reordered row panels, boundaries where the nnz prefix crosses rank * total / world
-    const std::vector<uint64_t>& pre = plan->h_panel_nnz_prefix;  // size panels + 1
+    // contiguous ranges of reordered row panels, boundaries where the work prefix crosses rank * total / world.
+    // Work of a panel = its nnz, plus, inside a wide row group, its share of the group's tiles: a wide tile costs about
+    // as much as 900 nnz whatever its fill (measured on the wide kernel: ~1.5 us per tile + ~1.7 ns per nnz).  Balancing
+    // on nnz alone gave the ranks between 2 and 10 row groups of an 8-way sharded stack of nips blocks (clustering puts
+    // the dense rows together), 20 to 33 us per step.
+    const std::vector<uint64_t>& nnz_pre = plan->h_panel_nnz_prefix;  // size panels + 1
     const uint32_t panels = plan->num_row_panels;
+    const uint32_t ppg = BSMR_WIDE_GROUP_ROWS / kPanel;
+    std::vector<uint64_t> work_pre;
+    if (plan->num_wide_tiles && !nnz_pre.empty()) {
+        constexpr uint64_t kTileWork = 900;
+        work_pre.assign(nnz_pre.size(), 0);
+        for (uint32_t q = 0; q < panels; ++q) {
+            const uint32_t g = q / ppg;
+            const uint64_t tiles = g + 1 < plan->h_wt_group_off.size() && plan->h_group_wide[g] ? plan->h_wt_group_off[g + 1] - plan->h_wt_group_off[g] : 0;
+            const uint32_t in_group = std::min(ppg, panels - g * ppg);
+            work_pre[q + 1] = work_pre[q] + (nnz_pre[q + 1] - nnz_pre[q]) + kTileWork * tiles / in_group;
+        }
+    }
+    const std::vector<uint64_t>& pre = work_pre.empty() ? nnz_pre : work_pre;
     const uint64_t total = pre.empty() ? 0 : pre[panels];
     auto boundary = [&](uint32_t r) -> uint32_t {
         if (r == 0) return 0;
@@ -609,9 +626,8 @@ int bsmr_plan_set_shard(bsmr_plan* plan, uint32_t rank, uint32_t world, uint32_t
     uint32_t b = boundary(rank), e = boundary(rank + 1);
     if (b > panels) b = panels;
     if (e > panels) e = panels;
-    const uint32_t ppg = BSMR_WIDE_GROUP_ROWS / kPanel;
     if (plan->num_wide_tiles) {
-        // a wide row group (8 panels) is one unit of work: move the boundaries to the nearest group boundary
+        // a wide row group (16 panels) is one unit of work: move the boundaries to the nearest group boundary
         auto snap = [&](uint32_t q) -> uint32_t {
             if (q >= panels) return panels;
             const uint32_t r = (q + ppg / 2) / ppg * ppg;
@@ -646,7 +662,7 @@ int bsmr_plan_set_shard(bsmr_plan* plan, uint32_t rank, uint32_t world, uint32_t
     }
     if (first_panel) *first_panel = b;
     if (end_panel) *end_panel = e;
-    if (shard_nnz) *shard_nnz = pre.empty() ? 0 : pre[e] - pre[b];
+    if (shard_nnz) *shard_nnz = nnz_pre.empty() ? 0 : nnz_pre[e] - nnz_pre[b];
     return BSMR_OK;
 }
 
