@@ -597,16 +597,16 @@ int bsmr_plan_set_shard(bsmr_plan* plan, uint32_t rank, uint32_t world, uint32_t
         return BSMR_ERR_BAD_STATE;
     }
     // contiguous ranges of reordered row panels, boundaries where the work prefix crosses rank * total / world.
-    // Work of a panel = its nnz, plus, inside a wide row group, its share of the group's tiles: a wide tile costs about
-    // as much as 900 nnz whatever its fill (measured on the wide kernel: ~1.5 us per tile + ~1.7 ns per nnz).  Balancing
-    // on nnz alone gave the ranks between 2 and 10 row groups of an 8-way sharded stack of nips blocks (clustering puts
-    // the dense rows together), 20 to 33 us per step.
+    // Work of a panel = its nnz, plus, inside a wide row group, its share of the group's tiles at 3000 nnz-equivalents
+    // per tile: the wide kernel's time follows the tile count far more than the nnz.  Measured on an 8-way sharded stack
+    // of nips blocks (clustering puts the dense rows together, so row groups differ 5x in nnz): balanced on nnz alone
+    // the ranks got 2 to 10 row groups and took 20 to 33 us per step; at 900 per tile 18.5 to 28.9 us.
     const std::vector<uint64_t>& nnz_pre = plan->h_panel_nnz_prefix;  // size panels + 1
     const uint32_t panels = plan->num_row_panels;
     const uint32_t ppg = BSMR_WIDE_GROUP_ROWS / kPanel;
     std::vector<uint64_t> work_pre;
     if (plan->num_wide_tiles && !nnz_pre.empty()) {
-        constexpr uint64_t kTileWork = 900;
+        constexpr uint64_t kTileWork = 3000;
         work_pre.assign(nnz_pre.size(), 0);
         for (uint32_t q = 0; q < panels; ++q) {
             const uint32_t g = q / ppg;
