@@ -8,7 +8,7 @@ Workload (config.workload): the nips-shaped matrix of BASELINE.json configs[1] a
 alpha=0.3, delta=0.3.  dataset/nips.mtx is not in the reference tree, so a seeded synthetic
 of the same shape / nnz is used (bsmr-sddmm_b200/synth.py) unless dataset/nips.mtx exists.
 At N GPUs the job is N such row blocks stacked into one matrix, reordered globally and sharded
-over the ranks by nnz-balanced ranges of reordered row panels (bsmr_plan_set_shard): weak scaling,
+over the ranks by work-balanced ranges of reordered row panels (bsmr_plan_set_shard: nnz plus tile count): weak scaling,
 per-GPU work fixed, no collective on the data path (B is replicated before the clock starts).
 
 A "step" = one pass of the hot path (wide row-group tcgen05 kernel + dense-block tcgen05 kernel +
@@ -157,7 +157,7 @@ def run_reference(args, rank, world):
 def workload_config(M, N, nnz, K, source, gpus):
     return {"workload": "nips K=%d alpha=%.1f delta=%.1f (BASELINE.json configs[1]); %s" % (K, ALPHA, DELTA, source),
             "M": int(M), "N": int(N), "nnz": int(nnz), "K": int(K), "alpha": ALPHA, "delta": DELTA,
-            "blocks": max(1, gpus), "sharding": "nnz-balanced reordered row-panel ranges" if gpus > 1 else "none",
+            "blocks": max(1, gpus), "sharding": "work-balanced (nnz + wide tiles) reordered row-panel ranges" if gpus > 1 else "none",
             "l2": "flushed between timed steps (512 MB buffer rewritten outside the event pairs)"}
 
 

@@ -166,8 +166,10 @@ int bsmr_plan_save_row_order(bsmr_plan* plan, const char* path, float alpha, uin
 int bsmr_plan_load_row_order(bsmr_plan* plan, const char* path, float alpha, uint32_t flags);
 
 /* ---- multi-GPU sharding (no counterpart in the reference, which is single-GPU) --------
- * Restrict the plan to the rank-th of world nnz-balanced contiguous ranges of reordered
- * row panels.  SDDMM calls then compute (and write) only the nnz of that range.
+ * Restrict the plan to the rank-th of world contiguous ranges of reordered row panels, balanced on
+ * the work of the panels: their nnz, plus inside a wide row group the group's tiles (3000 nnz-equivalents
+ * each: the wide kernel's time follows the tile count); boundaries fall on row-group boundaries when the
+ * plan has wide groups.  SDDMM calls then compute (and write) only the nnz of that range.
  * first_panel / last_panel (exclusive) / shard_nnz are outputs (may be NULL).            */
 int bsmr_plan_set_shard(bsmr_plan* plan, uint32_t rank, uint32_t world,
                         uint32_t* first_panel, uint32_t* end_panel, uint64_t* shard_nnz);

@@ -1,4 +1,4 @@
-"""CPU, world_size 2 over gloo: the host-side logic of the multi-GPU path -- nnz-balanced contiguous panel ranges,
+"""CPU, world_size 2 over gloo: the host-side logic of the multi-GPU path -- work-balanced contiguous panel ranges,
 disjoint cover of the CSR value array, assembly of P by an all-reduce -- with the oracle standing in for the kernels
 (no GPU in this container).  The same range arithmetic is what bsmr_plan_set_shard implements on the device side
 (tests/test_gpu_parity.py::test_shards_partition_the_nnz checks that one on a B200)."""
@@ -92,3 +92,24 @@ def test_shard_bounds_cover_and_balance():
         assert b[0] == 0 and b[-1] == 1000 and all(x <= y for x, y in zip(b, b[1:]))
         shares = [prefix[b[i + 1]] - prefix[b[i]] for i in range(world)]
         assert max(shares) - min(shares) <= 2 * nnz.max()
+
+
+def test_work_prefix_balances_tiles_not_only_nnz():
+    """bsmr_plan_set_shard balances on nnz + 3000 per wide tile (csrc/capi.cu): with row groups that differ 5x in nnz but
+    not in tiles, the nnz prefix gives some rank several times the tiles of another, the work prefix does not."""
+    rng = np.random.default_rng(1)
+    groups, ppg, tiles_per_group = 48, 16, 97
+    nnz_g = np.where(rng.random(groups) < 0.25, 400_000, 80_000) + rng.integers(0, 5000, groups)
+    panel_nnz = np.repeat(nnz_g // ppg, ppg)
+    panel_work = panel_nnz + 3000 * tiles_per_group // ppg
+    for world in (2, 4, 8):
+        cover = {}
+        for name, per_panel in (("nnz", panel_nnz), ("work", panel_work)):
+            prefix = np.concatenate([[0], np.cumsum(per_panel)])
+            b = [(x + ppg // 2) // ppg * ppg for x in shard_bounds(prefix, world)]      # snapped to row-group boundaries
+            b[0], b[-1] = 0, groups * ppg
+            assert all(b[i] <= b[i + 1] for i in range(world)), (name, b)
+            cover[name] = [(b[i + 1] - b[i]) // ppg for i in range(world)]              # row groups (= tiles / 97) per rank
+            assert sum(cover[name]) == groups
+        assert max(cover["work"]) - min(cover["work"]) <= max(cover["nnz"]) - min(cover["nnz"])
+        assert max(cover["work"]) <= 1.5 * groups / world + 1
