@@ -1,9 +1,9 @@
-"""Small pass over every kernel for compute-sanitizer (B200 box): python tests/sanitize_target.py
+"""Small pass over every kernel (B200 box, not a pytest test): python tests/sanitize_target.py
 
-    compute-sanitizer --tool memcheck python tests/sanitize_target.py
-
-One reorder (row clustering, column reorder, both forms of the wide format) and one SDDMM per execution plan on small
-matrices; prints the worst mismatch count against the oracle (0 expected)."""
+Meant as the target of `compute-sanitizer --tool memcheck` (closed on this pool's boxes in round 1, so it has only been
+run plain): one reorder (row clustering, column reorder, wide format with the bar lowered so that small matrices have
+wide groups) and one SDDMM per execution plan and K on small matrices; prints the mismatch count against the oracle
+(0 expected).  BSMR_WIDE_EPILOGUE=list|mask forces either form of the wide epilogue."""
 import os
 import sys
 
