@@ -369,7 +369,7 @@ void oracle_row_reordering(uint32_t M, uint32_t N, const uint32_t* row_offsets, 
     uint32_t* rep = (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)nb + 1));
     oracle_dispersion(M, N, row_offsets, col_indices, block_size, enc, disp);
     stable_argsort_u32(disp, M, asc, NULL);
-    for (uint32_t i = 0; i < M; ++i) cid[i] = ORACLE_NULL_VALUE;
+    memset(cid, 0xFF, sizeof(uint32_t) * ((size_t)M + 1));   /* ORACLE_NULL_VALUE everywhere */
 
     uint32_t zero_row_idx = 0;
     while (zero_row_idx < M && disp[asc[zero_row_idx]] == 0) { cid[zero_row_idx] = 0; zero_row_idx++; }
