@@ -112,6 +112,7 @@ def lib():
         L.bsmr_sddmm_profile.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_uint32, f32p, f32p]
         L.bsmr_sddmm_profile3.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_uint32, f32p, f32p, f32p]
         L.bsmr_plan_set_wide_ratio.argtypes = [vp, C.c_float]
+        L.bsmr_plan_set_l2_policy.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32]
         L.bsmr_plan_evaluate.argtypes = [vp, C.c_float, C.POINTER(ReorderStats)]
         L.bsmr_debug_set_dense_smem_dump.argtypes = [vp]
         for name in ("bsmr_ctx_create", "bsmr_ctx_destroy", "bsmr_ctx_synchronize", "bsmr_ctx_device_name",
@@ -121,7 +122,7 @@ def lib():
                      "bsmr_sddmm", "bsmr_sddmm_host", "bsmr_sddmm_profile", "bsmr_sddmm_profile3",
                      "bsmr_sddmm_host_submit", "bsmr_sddmm_host_wait", "bsmr_sddmm_batch", "bsmr_sddmm_host_batch",
                      "bsmr_plan_fingerprint", "bsmr_plan_save_row_order", "bsmr_plan_load_row_order", "bsmr_plan_execution_choice",
-                     "bsmr_plan_set_wide_ratio", "bsmr_plan_evaluate"):
+                     "bsmr_plan_set_wide_ratio", "bsmr_plan_set_l2_policy", "bsmr_plan_evaluate"):
             getattr(L, name).restype = C.c_int
         _lib = L
     return _lib
@@ -213,6 +214,10 @@ class Plan:
     def set_wide_ratio(self, ratio):
         """Policy of the wide row-group path, applied at the next column reorder (<= 0 disables it)."""
         _check(lib().bsmr_plan_set_wide_ratio(self._h, ratio))
+
+    def set_l2_policy(self, hot_budget_mb=64, min_b_mb=2048, cold_first=True):
+        """Residual kernel: keep the hub columns' K-vectors (up to hot_budget_mb MiB) in L2 when B exceeds min_b_mb MiB."""
+        _check(lib().bsmr_plan_set_l2_policy(self._h, hot_budget_mb, min_b_mb, int(cold_first)))
 
     def col_reorder(self, delta):
         _check(lib().bsmr_plan_col_reorder(self._h, delta))

@@ -253,6 +253,15 @@ int bsmr_plan_set_wide_ratio(bsmr_plan* plan, float ratio) {
     return BSMR_OK;
 }
 
+int bsmr_plan_set_l2_policy(bsmr_plan* plan, uint32_t hot_budget_mb, uint32_t min_b_mb, uint32_t cold_first) {
+    if (!plan) return BSMR_ERR_INVALID_ARGUMENT;
+    plan->l2_hot_budget_mb = hot_budget_mb;
+    plan->l2_hot_min_b_mb = min_b_mb;
+    plan->l2_cold_first = cold_first ? 1u : 0u;
+    plan->auto_flags.clear();               // the per-K execution plan was measured under the old policy
+    return BSMR_OK;
+}
+
 int bsmr_plan_row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flags) {
     if (!plan) return BSMR_ERR_INVALID_ARGUMENT;
     BSMR_CUDA_OK(cudaSetDevice(plan->ctx->device));
@@ -679,9 +688,13 @@ static int ensure_identity_rows(bsmr_plan* p) {
 // both are persistent-style grids that fill the machine on their own.
 static int run_once(bsmr_plan* p, uint32_t K, const float* dA, const float* dB, float* dP, uint32_t flags) {
     bsmr_ctx* ctx = p->ctx;
+    // B far larger than L2: the residual kernel asks L2 to keep the hub columns (nullptr otherwise; residual.cu)
+    const uint32_t* hot = nullptr;
+    uint32_t cold_first = 0;
+    BSMR_TRY(hot_columns(p, K, &hot, &cold_first));
     if (flags & BSMR_SDDMM_NO_REORDER) {
         // CSR order: A row from the expanded row list, B column = CSR column, P index = position
-        return launch_residual(ctx, K, dA, dB, dP, p->csr_row_of_nnz.ptr, p->col_indices.ptr, nullptr, 0, p->nnz);
+        return launch_residual(ctx, K, dA, dB, dP, p->csr_row_of_nnz.ptr, p->col_indices.ptr, nullptr, 0, p->nnz, hot, cold_first);
     }
     if ((flags & BSMR_SDDMM_RESIDUAL_ONLY) && p->num_tiles != 0) {
         set_error("BSMR_SDDMM_RESIDUAL_ONLY needs a plan whose column reorder ran with delta > 1 (no dense tiles); "
@@ -705,7 +718,7 @@ static int run_once(bsmr_plan* p, uint32_t K, const float* dA, const float* dB, 
     if (kinds <= 1) {
         if (do_wide) return launch_wide(p, K, dA, dB, dP, wt_b, wt_e, ctx->stream);
         if (do_dense) return launch_dense(p, K, dA, dB, dP, tl_b, tl_e, tile_list, ctx->stream);
-        return launch_residual(ctx, K, dA, dB, dP, rr_row, rr_col, rr_out, rs_b, rs_e);
+        return launch_residual(ctx, K, dA, dB, dP, rr_row, rr_col, rr_out, rs_b, rs_e, hot, cold_first);
     }
     BSMR_CUDA_OK(cudaEventRecord(ctx->ev_fork, ctx->stream));
     if (do_wide) {
@@ -717,12 +730,12 @@ static int run_once(bsmr_plan* p, uint32_t K, const float* dA, const float* dB, 
         BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
         BSMR_TRY(launch_dense(p, K, dA, dB, dP, tl_b, tl_e, tile_list, ctx->side_stream));
         BSMR_CUDA_OK(cudaEventRecord(ctx->ev_join, ctx->side_stream));
-        BSMR_TRY(launch_residual(ctx, K, dA, dB, dP, rr_row, rr_col, rr_out, rs_b, rs_e));
+        BSMR_TRY(launch_residual(ctx, K, dA, dB, dP, rr_row, rr_col, rr_out, rs_b, rs_e, hot, cold_first));
         BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     } else if (do_dense) {
         BSMR_TRY(launch_dense(p, K, dA, dB, dP, tl_b, tl_e, tile_list, ctx->stream));
     } else if (do_res) {
-        BSMR_TRY(launch_residual(ctx, K, dA, dB, dP, rr_row, rr_col, rr_out, rs_b, rs_e));
+        BSMR_TRY(launch_residual(ctx, K, dA, dB, dP, rr_row, rr_col, rr_out, rs_b, rs_e, hot, cold_first));
     }
     if (do_wide) BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));
     return BSMR_OK;

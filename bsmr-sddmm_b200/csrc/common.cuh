@@ -253,6 +253,16 @@ struct bsmr_plan {
     // ---- identity ("no reorder") residual list, built lazily ----
     bsmr::DevBuf<uint32_t> csr_row_of_nnz;
 
+    // ---- hub columns the residual kernel keeps in L2 when B does not fit (residual.cu: hot_columns) ----
+    // Defaults from the sweep in profiles/r01h_l2_policy_sweep.md: the policy pays only when the gather is DRAM-bound
+    // (B = 4.3 / 8.6 GB: -5 / -7 %); at B = 537 MB (L2 hit rate 70 % without it) it costs 10 %.
+    uint32_t l2_hot_budget_mb = 64;           // bytes of hub-column K-vectors marked evict_last; 0 = policy off
+    uint32_t l2_hot_min_b_mb = 2048;          // smaller B: plain kernel
+    uint32_t l2_cold_first = 1;               // 1: the other columns carry evict_first instead of the default priority
+    bsmr::DevBuf<uint32_t> col_degree, col_hot;
+    uint32_t hot_K = 0, hot_budget_mb = 0, hot_threshold = 0;
+    uint64_t hot_count = 0;
+
     // ---- shard (multi-GPU) ----
     uint32_t shard_first_panel = 0, shard_end_panel = 0;
     uint64_t shard_res_begin = 0, shard_res_end = 0;
@@ -291,7 +301,8 @@ namespace bsmr {
 // ---- kernels' host launchers (defined in the .cu files) ---------------------------------
 int launch_residual(bsmr_ctx* ctx, uint32_t K, const float* dA, const float* dB, float* dP,
                     const uint32_t* res_row, const uint32_t* res_col, const uint32_t* res_out,
-                    uint64_t begin, uint64_t end);
+                    uint64_t begin, uint64_t end, const uint32_t* col_hot = nullptr, uint32_t cold_first = 0);
+int hot_columns(bsmr_plan* plan, uint32_t K, const uint32_t** bitmap, uint32_t* cold_first);
 int launch_expand_rows(bsmr_ctx* ctx, uint32_t M, uint32_t nnz, const uint32_t* row_offsets, uint32_t* row_of_nnz);
 
 int col_reorder_and_format(bsmr_plan* plan, float delta);

@@ -25,6 +25,7 @@
 // Roofline: HBM-bound on compulsory traffic; what it actually stresses is L2 -> SM gather
 // bandwidth (K*4 bytes of B per nnz), see DESIGN.md.
 #include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 
@@ -42,6 +43,37 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
     acc = fmaf(a.z, b.z, acc);
     acc = fmaf(a.w, b.w, acc);
     return acc;
+}
+
+// ---- L2 eviction priorities for gathers that do not fit in L2 (HINT variants) ----------------------------------
+// On a power-law pattern whose B is far larger than L2 (R-MAT 2^22, K = 256: B = 4.3 GB) the residual kernel runs at
+// DRAM speed (ncu profiles/r01h_*: 5.5 TB/s, L2 hit rate 36 %): every K-vector of a cold column that passes through
+// L2 pushes out a hub column that would have been hit again.  The plan marks the highest-degree columns whose
+// K-vectors fit an L2 budget in a bitmap (hot_columns below); their loads carry evict_last, the A rows, the index
+// lists and P (each touched once) carry evict_first / streaming, the cold columns evict_first or the default.
+// Measured (profiles/r01h_l2_policy_sweep.md): -5 % at B = 4.3 GB, -7 % at 8.6 GB with evict_first on the cold columns;
+// evict_last alone (cold columns on the default priority) is slower than no hints, and at B = 537 MB (70 % L2 hit rate
+// as it is) every variant costs 10 % -- so the policy is on only above 2 GiB of B.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ldg4_hint(const float* p, uint64_t policy) {
+    float4 v;
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy));
+    return v;
 }
 
 // LPN: lanes per nnz.  KV: number of float4 pieces per lane (K == LPN*4*KV); KV == 0 -> runtime loop.
@@ -122,12 +154,14 @@ residual_sddmm_kernel(const uint32_t K, const float* __restrict__ A, const float
 }
 
 // Row-sorted fast path.  LPN lanes per entry, KV float4 pieces per lane: K == LPN * 4 * KV.
-template <int LPN, int KV>
+// HINT: col_hot is the bitmap of the columns to keep in L2 (bit c of word c / 32), cold_first the policy of the others.
+template <int LPN, int KV, bool HINT = false>
 __global__ void __launch_bounds__(kResThreads, 3)
 residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const float* __restrict__ B,
                      float* __restrict__ P, const uint32_t* __restrict__ res_row,
                      const uint32_t* __restrict__ res_col, const uint32_t* __restrict__ res_out,
-                     const uint64_t begin, const uint64_t end) {
+                     const uint64_t begin, const uint64_t end,
+                     const uint32_t* __restrict__ col_hot = nullptr, const uint32_t cold_first = 0) {
     constexpr int G = 32 / LPN;      // entries in flight per warp instruction
     constexpr int UNROLL = KV >= 4 ? 2 : 4;
     const uint32_t lane = threadIdx.x & 31;
@@ -141,14 +175,28 @@ residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const float*
     float4 a_cur[KV];
 #pragma unroll
     for (int v = 0; v < KV; ++v) a_cur[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint64_t pol_hot = 0, pol_cold = 0, pol_stream = 0;
+    if constexpr (HINT) {
+        pol_hot = l2_policy_evict_last();
+        pol_stream = l2_policy_evict_first();
+        pol_cold = cold_first ? pol_stream : l2_policy_evict_normal();
+    }
 
     for (uint64_t chunk = warp_global; chunk < num_chunks; chunk += warp_stride) {
         const uint64_t e = begin + chunk * 32 + lane;
         const bool valid = e < end;
         const uint64_t es = valid ? e : begin;       // idle lanes recompute entry `begin`; never stored
-        const uint32_t my_row = __ldg(res_row + es);
-        const uint32_t my_col = __ldg(res_col + es);
-        const uint32_t my_out = res_out ? __ldg(res_out + es) : (uint32_t)es;   // NULL = identity (CSR order)
+        uint32_t my_row, my_col, my_out, my_hot = 0;
+        if constexpr (HINT) {
+            my_row = __ldcs(res_row + es);
+            my_col = __ldcs(res_col + es);
+            my_out = res_out ? __ldcs(res_out + es) : (uint32_t)es;
+            my_hot = (__ldg(col_hot + (my_col >> 5)) >> (my_col & 31)) & 1u;
+        } else {
+            my_row = __ldg(res_row + es);
+            my_col = __ldg(res_col + es);
+            my_out = res_out ? __ldg(res_out + es) : (uint32_t)es;   // NULL = identity (CSR order)
+        }
         // Pass s (s = 0..ITERS-1, entries in list order so that the A row in registers is reused) fills
         // accumulator slot it(s) = (s >> 1) + (s & 1) * H: the two passes of a pair (i, i + H) are adjacent,
         // and the first butterfly step (offset H) is folded in as soon as both are known, which keeps only
@@ -167,8 +215,17 @@ residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const float*
                 rows_u[u] = __shfl_sync(0xffffffffu, my_row, j);
                 const uint32_t col = __shfl_sync(0xffffffffu, my_col, j);
                 const float* bp = B + (size_t)col * K + sl * 4;
+                if constexpr (HINT) {
+                    // the policy operand travels in a uniform register: one priority per warp instruction (with LPN < 32
+                    // the G entries of a pass share it: hot if any of them is)
+                    const uint32_t hot_j = __shfl_sync(0xffffffffu, my_hot, j);
+                    const uint64_t pol = (LPN == 32 ? hot_j != 0 : __any_sync(0xffffffffu, hot_j != 0)) ? pol_hot : pol_cold;
 #pragma unroll
-                for (int v = 0; v < KV; ++v) bv[u][v] = ldg4(bp + v * LPN * 4);
+                    for (int v = 0; v < KV; ++v) bv[u][v] = ldg4_hint(bp + v * LPN * 4, pol);
+                } else {
+#pragma unroll
+                    for (int v = 0; v < KV; ++v) bv[u][v] = ldg4(bp + v * LPN * 4);
+                }
             }
             float d[UNROLL];
 #pragma unroll
@@ -176,7 +233,7 @@ residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const float*
                 if (rows_u[u] != cur_row) {              // uniform inside the group (warp-uniform for LPN == 32)
                     const float* ap = A + (size_t)rows_u[u] * K + sl * 4;
 #pragma unroll
-                    for (int v = 0; v < KV; ++v) a_cur[v] = ldg4(ap + v * LPN * 4);
+                    for (int v = 0; v < KV; ++v) a_cur[v] = HINT ? ldg4_hint(ap + v * LPN * 4, pol_stream) : ldg4(ap + v * LPN * 4);
                     cur_row = rows_u[u];
                 }
                 float acc = 0.f;
@@ -208,7 +265,10 @@ residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const float*
         const int mine = (int)((2 * (sl % H) + sl / H) * G + sub);
         const uint32_t out = __shfl_sync(0xffffffffu, my_out, mine);
         const bool ok = __shfl_sync(0xffffffffu, (int)valid, mine) != 0;
-        if (ok) P[out] = q[0];
+        if (ok) {
+            if constexpr (HINT) __stcs(P + out, q[0]);
+            else P[out] = q[0];
+        }
     }
 }
 
@@ -390,6 +450,42 @@ __global__ void expand_rows_kernel(const uint32_t M, const uint32_t* __restrict_
     }
 }
 
+// ---- hub columns (HINT variant of residual_rows_kernel) ----
+constexpr int kDegBins = 4096;                // degrees are capped at kDegBins - 1 for the threshold search
+
+__global__ void col_degree_kernel(const uint32_t* __restrict__ col, const uint64_t nnz, uint32_t* __restrict__ deg) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(deg + __ldg(col + i), 1u);
+}
+
+__global__ void degree_hist_kernel(const uint32_t* __restrict__ deg, const uint32_t N, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t h[kDegBins];
+    for (int i = threadIdx.x; i < kDegBins; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < N; c += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t d = __ldg(deg + c);
+        atomicAdd(&h[d < kDegBins ? d : kDegBins - 1], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kDegBins; i += blockDim.x)
+        if (h[i]) atomicAdd(hist + i, h[i]);
+}
+
+// bit c of word c / 32 = (degree of column c >= threshold); one warp per word
+__global__ void hot_bitmap_kernel(const uint32_t* __restrict__ deg, const uint32_t N, const uint32_t threshold,
+                                  uint32_t* __restrict__ bitmap) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t words = ((uint64_t)N + 31) / 32;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t w = warp; w < words; w += stride) {
+        const uint64_t c = w * 32 + lane;
+        const bool hot = c < N && __ldg(deg + c) >= threshold;
+        const uint32_t bits = __ballot_sync(0xffffffffu, hot);
+        if (lane == 0) bitmap[w] = bits;
+    }
+}
+
 template <int LPN, int KV, int UNROLL>
 void launch_one(bsmr_ctx* ctx, int grid, uint32_t K, const float* dA, const float* dB, float* dP,
                 const uint32_t* rr, const uint32_t* rc, const uint32_t* ro, uint64_t begin, uint64_t end) {
@@ -400,7 +496,7 @@ void launch_one(bsmr_ctx* ctx, int grid, uint32_t K, const float* dA, const floa
 
 int launch_residual(bsmr_ctx* ctx, uint32_t K, const float* dA, const float* dB, float* dP,
                     const uint32_t* res_row, const uint32_t* res_col, const uint32_t* res_out,
-                    uint64_t begin, uint64_t end) {
+                    uint64_t begin, uint64_t end, const uint32_t* col_hot, uint32_t cold_first) {
     if (end <= begin) return BSMR_OK;
     if (K == 0) {
         set_error("K must be positive");
@@ -433,6 +529,13 @@ int launch_residual(bsmr_ctx* ctx, uint32_t K, const float* dA, const float* dB,
         else if (K == 256) st = launch_async<32, 2, 7>(ctx, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
         else st = launch_async<32, 4, 3>(ctx, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
         BSMR_TRY(st);
+    } else if (fast_k && col_hot) {
+        // hub columns pinned in L2 (hot_columns below): same kernel, loads and stores carry L2 eviction priorities
+        if (K == 32) residual_rows_kernel<8, 1, true><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end, col_hot, cold_first);
+        else if (K == 64) residual_rows_kernel<16, 1, true><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end, col_hot, cold_first);
+        else if (K == 128) residual_rows_kernel<32, 1, true><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end, col_hot, cold_first);
+        else if (K == 256) residual_rows_kernel<32, 2, true><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end, col_hot, cold_first);
+        else residual_rows_kernel<32, 4, true><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end, col_hot, cold_first);
     } else if (K == 32) {
         residual_rows_kernel<8, 1><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end);
     } else if (K == 64) {
@@ -452,6 +555,56 @@ int launch_residual(bsmr_ctx* ctx, uint32_t K, const float* dA, const float* dB,
     }
     ctx->launches++;
     BSMR_CUDA_OK(cudaGetLastError());
+    return BSMR_OK;
+}
+
+// The columns whose K-vectors the residual kernel asks L2 to keep: the highest-degree columns (degree >= 2) that fit
+// plan->l2_hot_budget_mb, as a bitmap; *bitmap = nullptr when B fits the budget anyway (every small workload), when
+// the policy is switched off (budget 0) or when K has no fast path.  Built once per (plan, K, budget): a degree count
+// over the CSR column indices (once per plan), a capped degree histogram and a threshold chosen on the host.
+int hot_columns(bsmr_plan* p, uint32_t K, const uint32_t** bitmap, uint32_t* cold_first) {
+    *bitmap = nullptr;
+    *cold_first = p->l2_cold_first;
+    const uint64_t b_bytes = (uint64_t)p->N * K * sizeof(float);
+    const bool fast_k = K == 32 || K == 64 || K == 128 || K == 256 || K == 512;
+    if (!fast_k || p->l2_hot_budget_mb == 0 || p->nnz == 0 || b_bytes <= ((uint64_t)p->l2_hot_min_b_mb << 20)) return BSMR_OK;
+    if (p->hot_K == K && p->hot_budget_mb == p->l2_hot_budget_mb && p->col_hot.ptr) {
+        *bitmap = p->col_hot.ptr;
+        return BSMR_OK;
+    }
+    bsmr_ctx* ctx = p->ctx;
+    const int grid = ctx->sm_count * 8;
+    if (!p->col_degree.ptr) {
+        BSMR_TRY(p->col_degree.alloc(p->N));
+        BSMR_CUDA_OK(cudaMemsetAsync(p->col_degree.ptr, 0, p->col_degree.bytes(), ctx->stream));
+        col_degree_kernel<<<grid, 256, 0, ctx->stream>>>(p->col_indices.ptr, p->nnz, p->col_degree.ptr);
+        ctx->launches++;
+    }
+    bsmr::DevBuf<uint32_t> d_hist;
+    BSMR_TRY(d_hist.alloc(kDegBins));
+    BSMR_CUDA_OK(cudaMemsetAsync(d_hist.ptr, 0, d_hist.bytes(), ctx->stream));
+    degree_hist_kernel<<<grid, 256, 0, ctx->stream>>>(p->col_degree.ptr, p->N, d_hist.ptr);
+    ctx->launches++;
+    std::vector<uint32_t> hist(kDegBins);
+    BSMR_CUDA_OK(cudaMemcpyAsync(hist.data(), d_hist.ptr, d_hist.bytes(), cudaMemcpyDeviceToHost, ctx->stream));
+    BSMR_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    const uint64_t max_cols = ((uint64_t)p->l2_hot_budget_mb << 20) / ((uint64_t)K * sizeof(float));
+    uint64_t count = 0;
+    uint32_t threshold = kDegBins;           // nothing hot unless a class fits
+    for (int d = kDegBins - 1; d >= 2; --d) {
+        if (count + hist[d] > max_cols) break;
+        count += hist[d];
+        threshold = (uint32_t)d;
+    }
+    BSMR_TRY(p->col_hot.alloc(((size_t)p->N + 31) / 32));
+    hot_bitmap_kernel<<<grid, 256, 0, ctx->stream>>>(p->col_degree.ptr, p->N, threshold, p->col_hot.ptr);
+    ctx->launches++;
+    BSMR_CUDA_OK(cudaGetLastError());
+    p->hot_K = K;
+    p->hot_budget_mb = p->l2_hot_budget_mb;
+    p->hot_threshold = threshold;
+    p->hot_count = count;
+    *bitmap = p->col_hot.ptr;
     return BSMR_OK;
 }
 

@@ -8,6 +8,11 @@ THE GPU with torch (the numpy generator of `synth.rmat` needs minutes of host ti
 column reorder + format build at delta = 0.3, then `bsmr_sddmm` at K.  Prints one JSON line: reorder / format times, the
 split, ms per SDDMM, GFLOPS, the fraction of the HBM roofline on SURVEY section 8(d)'s algorithmic bytes, and a sampled
 check of the values against an fp64 dot product of the same rows (size-independent parity at the full size).
+
+Under torchrun (`python -m torch.distributed.run --nproc-per-node N ... tests/graph8m_probe.py ...`) every rank builds
+the same plan (same seed), takes the rank-th of N work-balanced shards of row panels (`bsmr_plan_set_shard`) and times
+its own shard; rank 0 prints the line with the per-rank times and GFLOPS over the slowest rank (strong scaling: the
+matrix is fixed).  A and B are replicated, P stays distributed, there is no collective in the timed region.
 """
 import json
 import os
@@ -46,6 +51,39 @@ def rmat_device(torch, scale, edges, seed, a=0.57, b=0.19, c=0.19):
     return n, ro.to(torch.int32), ci, rows
 
 
+def sharded(torch, pkg, plan, out, world, rank, K, dA, dB, dP, ro, ci, rows, g):
+    import torch.distributed as dist
+    nnz = ci.numel()
+    first_panel, end_panel, shard_nnz = plan.set_shard(rank, world)
+    plan.sddmm(K, dA, dB, dP, iterations=1)                    # execution-plan choice on the shard
+    dP.zero_()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = min(plan.sddmm(K, dA, dB, dP, iterations=3) for _ in range(3))
+    # the shard's entries: identity row order -> reordered row i is the i-th non-empty row, 16 rows per panel
+    nz_rows = torch.nonzero(ro[1:] != ro[:-1]).flatten()
+    r0 = int(nz_rows[first_panel * 16])
+    r1 = int(nz_rows[min(end_panel * 16, nz_rows.numel()) - 1]) + 1
+    e0, e1 = int(ro[r0]), int(ro[r1])
+    idx = torch.randint(e0, e1, (1 << 17,), device="cuda", generator=g)
+    ref = (dA[rows[idx]].double() * dB[ci[idx].long()].double()).sum(-1)
+    rel = ((dP[idx].double() - ref).abs() / ref.abs().clamp_min(1e-30)).max().item()
+    written = int((dP != 0).sum())
+    ok = rel <= 1e-3 and written == shard_nnz == e1 - e0
+    mine = torch.tensor([ms, float(shard_nnz), float(end_panel - first_panel), rel, float(ok)], dtype=torch.float64, device="cuda")
+    allr = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allr, mine)
+    if rank == 0:
+        t = max(float(a[0]) for a in allr)
+        out.update({"n_gpus": world, "scaling": "strong", "ms_by_rank": [float(a[0]) for a in allr],
+                    "shard_nnz": [int(a[1]) for a in allr], "shard_panels": [int(a[2]) for a in allr],
+                    "sample_max_rel_err": max(float(a[3]) for a in allr), "parity_ok": all(float(a[4]) == 1.0 for a in allr),
+                    "covered_nnz": sum(int(a[1]) for a in allr), "sddmm_ms": t, "gflops": 2.0 * nnz * K / t / 1e6})
+        print(json.dumps(out), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     import torch
     pkg = entry.load_package()
@@ -60,9 +98,14 @@ def main():
         pass
     bw = float(peaks.get("hbm_gbs", 6552.3))
 
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    ctx = pkg.Context(0, stream.cuda_stream)
+    ctx = pkg.Context(local, stream.cuda_stream)
     t0 = time.perf_counter()
     n, ro, ci, rows = rmat_device(torch, scale, edges, seed=scale)
     torch.cuda.synchronize()
@@ -85,7 +128,8 @@ def main():
                                      "num_row_groups", "num_wide_groups", "num_wide_tiles")})
     out.update({k: int(info[k]) for k in ("num_dense_values", "num_sparse_values", "num_wide_values", "num_block_values",
                                           "num_residual_values")})
-    print(json.dumps(out), file=sys.stderr, flush=True)
+    if rank == 0:
+        print(json.dumps(out), file=sys.stderr, flush=True)
 
     g = torch.Generator(device="cuda")
     g.manual_seed(5489)
@@ -95,6 +139,10 @@ def main():
     torch.cuda.synchronize()
     out["hbm_used_gb"] = torch.cuda.mem_get_info()[1] / 1e9 - torch.cuda.mem_get_info()[0] / 1e9
 
+    if world > 1:
+        sharded(torch, pkg, plan, out, world, rank, K, dA, dB, dP, ro, ci, rows, g)
+        plan.close()
+        return
     first = plan.sddmm(K, dA, dB, dP, iterations=1)           # includes the execution-plan choice
     ms = min(plan.sddmm(K, dA, dB, dP, iterations=3) for _ in range(3))
     out["first_call_ms"] = first
@@ -118,6 +166,19 @@ def main():
     got = dP[idx].double()
     out["csr_order_ms"] = ms_csr
     out["csr_order_max_rel_err"] = ((got - ref).abs() / ref.abs().clamp_min(1e-30)).max().item()
+
+    # L2 policy of the residual kernel (bsmr_plan_set_l2_policy): hub-column budget in MiB x priority of the other columns
+    sweep = []
+    keep = dP.clone()
+    for budget, cold_first in ((0, 0), (32, 0), (64, 0), (96, 0), (32, 1), (64, 1), (96, 1)):
+        plan.set_l2_policy(budget, 96, bool(cold_first))     # 96 MiB floor: the sweep also covers B = 537 MB
+        dP.zero_()
+        csr = min(plan.sddmm(K, dA, dB, dP, iterations=3, flags=pkg.SDDMM_NO_REORDER) for _ in range(2))
+        same = bool(torch.equal(dP, keep))
+        split = min(plan.sddmm(K, dA, dB, dP, iterations=3, flags=pkg.SDDMM_NO_WIDE) for _ in range(2))
+        sweep.append({"hot_mb": budget, "cold_first": cold_first, "csr_order_ms": csr, "bsmr_split_ms": split, "bit_identical": same})
+    out["l2_policy_sweep"] = sweep
+    plan.set_l2_policy()
     print(json.dumps(out), flush=True)
     plan.close()
 

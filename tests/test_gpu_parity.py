@@ -167,6 +167,33 @@ def test_sddmm_csr_order_residual_kernel(pkg, ctx, oracle, K):
         assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-3)) < 2e-5, (name, K)
 
 
+@pytest.mark.parametrize("K", [32, 64, 128, 256, 512, 40])
+def test_residual_l2_policy_is_bit_identical(pkg, ctx, oracle, K):
+    """bsmr_plan_set_l2_policy: the hub-column variant of the residual kernel (L2 eviction priorities on the loads,
+    forced here on small inputs with min_b_mb = 0) computes exactly what the plain kernel computes."""
+    import torch
+    for name, M, N, ro, ci in small_cases(pkg):
+        if name not in ("blocks_1000x2000", "uniform_200x333_ragged", "single_row", "tall_2500x64"):
+            continue
+        A, B = pkg.synth.make_ab(M, N, K)
+        dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+        plan = pkg.Plan(ctx, M, N, ro, ci)
+        plan.reorder(0.3, 0.3)
+        want = oracle.sddmm_cpu(M, N, K, A, B, ro, ci)
+        for flags in (pkg.SDDMM_NO_REORDER, pkg.SDDMM_NO_WIDE):
+            outs = []
+            for budget, min_b, cold_first in ((0, 96, False), (1, 0, False), (1, 0, True), (4096, 0, False)):
+                plan.set_l2_policy(budget, min_b, cold_first)
+                dP = torch.full((len(ci),), -7.0, dtype=torch.float32, device="cuda")
+                plan.sddmm(K, dA, dB, dP, iterations=1, flags=flags)
+                torch.cuda.synchronize()
+                outs.append(dP.cpu().numpy())
+            assert oracle.check_data(want, outs[0]) == 0, (name, K, flags)
+            for o in outs[1:]:
+                assert np.array_equal(o, outs[0]), (name, K, flags)
+        plan.close()
+
+
 @pytest.mark.parametrize("K", [32, 128, 40])
 def test_sddmm_all_residual_after_reorder(pkg, ctx, oracle, K):
     """delta > 1: nothing is dense, every nnz goes through the residual kernel in RPHM order."""
