@@ -28,7 +28,7 @@ int run_single(const Options& opts, const sparseMatrix::CSR<float>& pattern) {
     sparseMatrix::CSR<float> result(pattern);          // carries the pattern in, the values out
     sddmm(opts, ab.lhs, ab.rhs, result, log);
     log.printLogInformation();
-    return 0;
+    return bsmr_host::validationFailures() ? 1 : 0;     // non-zero only in VALIDATE builds
 }
 
 }  // namespace
@@ -38,6 +38,10 @@ int main(int argc, char* argv[]) {
     sparseMatrix::CSR<float> pattern;
     if (!pattern.initializeFromMatrixFile(opts.inputFile())) {
         fprintf(stderr, "Error, matrix S initialize failed.\n");
+        return -1;
+    }
+    if (!bsmr_host::context()) {                        // no CPU path: without a usable device there is nothing to run
+        fprintf(stderr, "Error, no usable CUDA device for libbsmr_b200.\n");
         return -1;
     }
     if (opts.testMode()) {                              // the sweep that produced the reference's published logs

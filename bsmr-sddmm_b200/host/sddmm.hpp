@@ -40,6 +40,13 @@ inline void computeAndEvaluate(const Matrix<float>& lhs, const Matrix<float>& rh
     evaluationReordering(pattern, order, log);
 }
 
+// VALIDATE builds: how many of the post-SDDMM self-checks failed so far (the CLI turns it into its exit code; the
+// reference only prints, src/sddmm.cu:35-38)
+inline int& validationFailures() {
+    static int failures = 0;
+    return failures;
+}
+
 // file name of one record of the test-mode sweep (src/sddmm.cu:107-110: BSMR_k_<K>_a_<alpha>_d_<delta>.log)
 inline std::string sweepLogName(const Options& opts, UIN k, float alpha, float delta) {
     return opts.outputLogDirectory() + "BSMR_k_" + util::to_trimmed_string(k) + "_a_" + util::to_trimmed_string(alpha) + "_d_" +
@@ -62,8 +69,8 @@ inline void sddmm(const Options& options, const Matrix<float>& matrixA, const Ma
     bsmr_host::noteReorder(logger, order);
     bsmr_host::computeAndEvaluate(matrixA, matrixB, order, matrixP, logger);
 #ifdef VALIDATE
-    check_rphm(matrixP, order, RPHM(matrixP, order), options.blockDensityThresholdDelta());
-    checkSddmm(matrixA, matrixB, matrixP, matrixP);
+    if (!check_rphm(matrixP, order, RPHM(matrixP, order), options.blockDensityThresholdDelta())) ++bsmr_host::validationFailures();
+    if (!checkSddmm(matrixA, matrixB, matrixP, matrixP)) ++bsmr_host::validationFailures();
 #endif
 }
 

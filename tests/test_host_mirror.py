@@ -153,3 +153,44 @@ def test_sddmm_cpu_and_check_data(pkg, oracle, harness, tmp_path):
     r = harness("check", str(tmp_path / "a.bin"), str(tmp_path / "b.bin"))
     errors = int(r.stdout.strip().splitlines()[-1].split("=")[1])
     assert errors == oracle.check_data(a, b.astype(np.float32)) and 0 < errors < len(a)
+
+
+# ---- the CLI (bsmr-sddmm_b200/host/main.cpp): same flags, exit codes and log keys as the reference's binary ----
+CLI = os.path.join(HOST_DIR, "BSMR-sddmm-validate")      # built with -DVALIDATE: check_rphm + checkSddmm after the SDDMM
+LOG_KEYS = ["[File : ", "[K : ", "[NNZ : ", "[NumRowPanel : ", "[bsmr_alpha : ", "[bsmr_delta : ", "[bsmr_numClusters : ",
+            "[bsmr_numDenseBlock : ", "[bsmr_rowReordering : ", "[bsmr_colReordering : ", "[bsmr_gflops : ", "[bsmr_sddmm : "]
+
+
+def run_cli(*args):
+    return subprocess.run([CLI, *map(str, args)], capture_output=True, text=True, timeout=300)
+
+
+def test_cli_rejects_bad_input_and_has_no_cpu_path(pkg, tmp_path):
+    import torch
+    assert os.path.exists(CLI), "run __graft_entry__.build()"
+    r = run_cli("-f", str(tmp_path / "missing.mtx"), "-k", 32)
+    assert r.returncode == 255 and "matrix S initialize failed" in r.stderr          # main returns -1 (src/main.cu:20-23)
+    if torch.cuda.is_available():
+        return
+    M, N, ro, ci = pkg.synth.block_structured(64, 96, seed=2)
+    p = str(tmp_path / "s.mtx")
+    pkg.synth.write_mtx(p, M, N, ro, ci)
+    r = run_cli("-f", p, "-k", 32)
+    assert r.returncode == 255 and "no CPU fallback" in r.stderr and "[bsmr_gflops" not in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,alpha,delta", [(32, 0.3, 0.3), (128, 0.3, 0.3), (64, 0.5, 0.0), (256, 0.1, 1.1)])
+def test_cli_validate_run(pkg, tmp_path, K, alpha, delta):
+    """The reference's own end-to-end self-check (VALIDATE build, src/sddmm.cu:35-38) through the host mirror on the B200:
+    .mtx loader -> makeData -> BSMR -> RPHM -> sddmm_gpu -> check_rphm + checkSddmm (sddmm_cpu, 1e-3 tolerance)."""
+    M, N, ro, ci = pkg.synth.block_structured(300, 520, seed=7)
+    p = str(tmp_path / "s.mtx")
+    pkg.synth.write_mtx(p, M, N, ro, ci, shuffle_seed=1)
+    r = run_cli("-f", p, "-k", K, "-a", alpha, "-d", delta)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Pass! Result validates successfully." in r.stdout and "No Pass" not in r.stdout
+    assert "incorrect" not in r.stderr
+    for key in LOG_KEYS:
+        assert key in r.stdout, key
+    assert "[K : %d]" % K in r.stdout and "[NNZ : %d]" % len(ci) in r.stdout and "[M : 300], [N : 520]" in r.stdout
