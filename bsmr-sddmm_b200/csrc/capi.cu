@@ -827,6 +827,9 @@ int bsmr_sddmm_profile3(bsmr_plan* plan, uint32_t K, const float* dA, const floa
     const bool wide = p->num_wide_tiles != 0 && !(flags & BSMR_SDDMM_NO_WIDE) && wide_supports(K, dA, dB);
     const uint32_t tl_b = wide ? p->shard_tile2_begin : p->shard_tile_begin, tl_e = wide ? p->shard_tile2_end : p->shard_tile_end;
     const uint64_t rs_b = wide ? p->shard_res2_begin : p->shard_res_begin, rs_e = wide ? p->shard_res2_end : p->shard_res_end;
+    const uint32_t* hot = nullptr;           // the residual kernel's L2 policy, as in run_once (built before the clock starts)
+    uint32_t cold_first = 0;
+    BSMR_TRY(hot_columns(p, K, &hot, &cold_first));
     cudaEvent_t mid0, mid;
     BSMR_CUDA_OK(cudaEventCreate(&mid0));
     BSMR_CUDA_OK(cudaEventCreate(&mid));
@@ -838,7 +841,7 @@ int bsmr_sddmm_profile3(bsmr_plan* plan, uint32_t K, const float* dA, const floa
     cudaEventRecord(mid, ctx->stream);
     if (s == BSMR_OK)
         s = launch_residual(ctx, K, dA, dB, dP, wide ? p->rr2_row.ptr : p->rr_row.ptr, wide ? p->rr2_col.ptr : p->rr_col.ptr,
-                            wide ? p->rr2_out.ptr : p->rr_out.ptr, rs_b, rs_e);
+                            wide ? p->rr2_out.ptr : p->rr_out.ptr, rs_b, rs_e, hot, cold_first);
     cudaEventRecord(ctx->ev1, ctx->stream);
     cudaError_t e = cudaEventSynchronize(ctx->ev1);
     float w = 0.f, a = 0.f, b = 0.f;
