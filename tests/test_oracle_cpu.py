@@ -138,3 +138,24 @@ def test_block_size_and_blockdim_rules(oracle):
     assert oracle.clustering_blockdim(256) == 64
     assert oracle.clustering_blockdim(777) == 224
     assert oracle.clustering_blockdim(6133) == 1024
+
+
+def test_randomised_shapes_against_reference(pkg, oracle, ref):
+    """40 seeded random shapes (tiny to a few thousand nnz, ragged panels, N not a multiple of 16, K not a multiple of 4):
+    column reorder vectors and sddmm_cpu of the oracle are bit-identical to the reference's CPU code."""
+    rng = np.random.default_rng(2024)
+    for case in range(40):
+        M = int(rng.integers(1, 400))
+        N = int(rng.integers(2, 700))
+        nnz = int(rng.integers(2, max(3, min(M * N, 6000))))
+        _, _, ro, ci = pkg.synth.random_uniform(M, N, nnz, seed=1000 + case)
+        rows = nonempty_rows(ro)
+        rows = rows[rng.permutation(len(rows))]
+        delta = float(rng.choice([0.0, 0.05, 0.3, 0.6, 1.0, 1.1]))
+        a = oracle.col_reordering(M, N, ro, ci, rows, delta)
+        b = ref.col_reordering_cpu(M, N, ro, ci, rows, delta)
+        for k in COL_VECS:
+            assert np.array_equal(a[k], b[k]), (case, M, N, nnz, delta, k)
+        K = int(rng.choice([1, 3, 32, 50, 64]))
+        A, B = pkg.synth.make_ab(M, N, K, seed=case)
+        assert np.array_equal(oracle.sddmm_cpu(M, N, K, A, B, ro, ci), ref.sddmm_cpu(M, N, K, A, B, ro, ci)), (case, K)
