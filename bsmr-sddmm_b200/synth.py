@@ -18,7 +18,7 @@ def csr_from_rows_cols(M, N, rows, cols):
     r = (key // N).astype(np.int64)
     c = (key % N).astype(np.uint32)
     ro = np.zeros(M + 1, dtype=np.int64)
-    np.add.at(ro, r + 1, 1)
+    ro[1:] = np.bincount(r, minlength=M)
     return M, N, np.cumsum(ro).astype(np.uint32), c
 
 
@@ -92,7 +92,7 @@ def rmat(scale, edges, seed, a=0.57, b=0.19, c=0.19):
         keys = np.sort(rng.choice(keys, size=edges, replace=False))
     rows = keys // n
     ro = np.zeros(n + 1, dtype=np.int64)
-    np.add.at(ro, rows + 1, 1)
+    ro[1:] = np.bincount(rows, minlength=n)
     return n, n, np.cumsum(ro).astype(np.uint32), (keys % n).astype(np.uint32)
 
 
