@@ -4,7 +4,9 @@
 #pragma once
 
 #include <algorithm>
+#include <cerrno>
 #include <cstdint>
+#include <cstdlib>
 #include <fstream>
 #include <iostream>
 #include <numeric>
@@ -190,27 +192,76 @@ inline std::vector<UIN> rowOffsetsFromSortedRows(UIN rows, const std::vector<UIN
     for (UIN r = 0; r < rows; ++r) off[r + 1] += off[r];
     return off;
 }
-// stable sort by row only: the order inside a row stays the file order (src/Matrix.cpp:467-470)
+// stable sort by row only: the order inside a row stays the file order (src/Matrix.cpp:467-470).
+// Counting sort over the row index: O(nnz + rows), stable by construction (the reference's std::stable_sort over
+// tuples is O(nnz log nnz) with a large constant -- minutes on the 2.5e8-nnz graphs).  max_row_hint = number of rows
+// when the caller knows it (all indices already validated to be below it), 0 = take it from the data.
 template <typename T>
-inline void stableSortByRow(std::vector<UIN>& rows, std::vector<UIN>& cols, std::vector<T>& vals) {
-    std::vector<size_t> order(rows.size());
-    std::iota(order.begin(), order.end(), size_t(0));
-    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return rows[a] < rows[b]; });
-    std::vector<UIN> r2(rows.size()), c2(cols.size());
-    std::vector<T> v2(vals.size());
-    for (size_t i = 0; i < order.size(); ++i) {
-        r2[i] = rows[order[i]];
-        c2[i] = cols[order[i]];
-        v2[i] = vals[order[i]];
+inline void stableSortByRow(std::vector<UIN>& rows, std::vector<UIN>& cols, std::vector<T>& vals, UIN max_row_hint = 0) {
+    const size_t n = rows.size();
+    if (n == 0) return;
+    size_t buckets = max_row_hint;
+    if (buckets == 0) buckets = static_cast<size_t>(*std::max_element(rows.begin(), rows.end())) + 1;
+    std::vector<size_t> start(buckets + 1, 0);
+    for (size_t i = 0; i < n; ++i) ++start[static_cast<size_t>(rows[i]) + 1];
+    for (size_t b = 0; b < buckets; ++b) start[b + 1] += start[b];
+    std::vector<UIN> r2(n), c2(n);
+    std::vector<T> v2(n);
+    for (size_t i = 0; i < n; ++i) {
+        const size_t dst = start[rows[i]]++;
+        r2[dst] = rows[i];
+        c2[dst] = cols[i];
+        v2[dst] = vals[i];
     }
     rows.swap(r2);
     cols.swap(c2);
     vals.swap(v2);
 }
+// One word of plain decimal digits (at most 9, so that it is inside std::stoi's range) ending at a separator or at the
+// end of the line, parsed in place; `pos` then skips the separators like util::iterateOneWordFromLine.  Anything else
+// (sign, blanks first, letters, more digits) returns false and leaves `pos` alone: the caller takes the std::stoi path,
+// which accepts or throws exactly as the reference does.
+inline bool fastUnsignedWord(const char* s, int& pos, UIN& out) {
+    int p = pos, digits = 0;
+    UIN value = 0;
+    while (s[p] >= '0' && s[p] <= '9' && digits < 10) {
+        value = value * 10 + static_cast<UIN>(s[p] - '0');
+        ++p;
+        ++digits;
+    }
+    if (digits == 0 || digits > 9) return false;
+    if (s[p] != '\0' && s[p] != ' ' && s[p] != '\t' && s[p] != '\r') return false;
+    while (s[p] == ' ' || s[p] == '\t' || s[p] == '\r') ++p;
+    pos = p;
+    out = value;
+    return true;
+}
+// "a b [v]" of one line (src/Matrix.cpp:421-438 reads three words with std::stoi / std::stoi / std::stod).  The common
+// case -- two digit words and a number strtod understands -- is parsed in place without a substring per word.
 template <typename T>
 inline bool readThree(const std::string& line, UIN& a, UIN& b, T& v) {
     if (line.empty()) return false;
+    const char* s = line.c_str();
     int pos = 0;
+    UIN fa = 0, fb = 0;
+    if (fastUnsignedWord(s, pos, fa) && fastUnsignedWord(s, pos, fb)) {
+        if (s[pos] == '\0') {
+            a = fa;
+            b = fb;
+            v = static_cast<T>(0);
+            return true;
+        }
+        char* end = nullptr;
+        errno = 0;
+        const double d = std::strtod(s + pos, &end);
+        if (end != s + pos) {                       // std::stod would have converted the same prefix
+            a = fa;
+            b = fb;
+            v = errno == ERANGE ? static_cast<T>(0) : static_cast<T>(d);
+            return true;
+        }
+    }
+    pos = 0;
     a = static_cast<UIN>(std::stoi(util::iterateOneWordFromLine(line, pos)));
     b = static_cast<UIN>(std::stoi(util::iterateOneWordFromLine(line, pos)));
     const std::string w = util::iterateOneWordFromLine(line, pos);
@@ -294,7 +345,7 @@ public:
             std::cerr << "Warning, file " << file << " nnz is 1, this is not a valid matrix!" << std::endl;
             return false;
         }
-        detail::stableSortByRow(rows, cols, vals);
+        detail::stableSortByRow(rows, cols, vals, row_);
         rowOffsets_ = detail::rowOffsetsFromSortedRows(row_, rows);
         colIndices_.swap(cols);
         values_.swap(vals);
@@ -390,7 +441,7 @@ public:
             return false;
         }
         if (!validateCoordinates(file, rows, cols)) return false;
-        detail::stableSortByRow(rows, cols, vals);
+        detail::stableSortByRow(rows, cols, vals, row_);
         rowOffsets_ = detail::rowOffsetsFromSortedRows(row_, rows);
         colIndices_.swap(cols);
         values_.swap(vals);
@@ -421,7 +472,19 @@ private:
         col_ = c;
         nnz_ = n;
     }
+    // bounds + duplicate check of the loaders (src/Matrix.cpp:442-465: a std::set of pairs filled entry by entry).  A clean
+    // file is recognised with one pass and one sort of 64-bit keys; only a file that has a problem takes the entry-by-
+    // entry walk, so that the message names the first offending entry exactly as the reference does.
     bool validateCoordinates(const std::string& file, const std::vector<UIN>& rows, const std::vector<UIN>& cols) const {
+        bool clean = true;
+        for (size_t i = 0; i < rows.size() && clean; ++i) clean = rows[i] < row_ && cols[i] < col_;
+        if (clean) {
+            std::vector<uint64_t> keys(rows.size());
+            for (size_t i = 0; i < rows.size(); ++i) keys[i] = (static_cast<uint64_t>(rows[i]) << 32) | cols[i];
+            std::sort(keys.begin(), keys.end());
+            clean = std::adjacent_find(keys.begin(), keys.end()) == keys.end();
+        }
+        if (clean) return true;
         std::set<std::pair<UIN, UIN>> seen;
         for (size_t i = 0; i < rows.size(); ++i) {
             if (rows[i] >= row_ || cols[i] >= col_) {

@@ -5,6 +5,7 @@
 #define _GNU_SOURCE
 #include "bsmr_oracle.h"
 
+#include <errno.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -74,7 +75,12 @@ int oracle_load_mtx(const char* path, oracle_csr* out) {
         p = next_word(p, w, sizeof w); const uint32_t r = (uint32_t)atoi(w);
         p = next_word(p, w, sizeof w); const uint32_t c = (uint32_t)atoi(w);
         p = next_word(p, w, sizeof w);
-        const float v = w[0] ? (float)strtod(w, NULL) : 0.0f;
+        float v = 0.0f;
+        if (w[0]) { /* std::stod throws out_of_range on ERANGE and the reference then stores 0 (:383-388) */
+            errno = 0;
+            const double d = strtod(w, NULL);
+            v = errno == ERANGE ? 0.0f : (float)d;
+        }
         if (idx >= nnz) { ok = 0; break; }
         ri[idx] = r - 1; ci[idx] = c - 1; va[idx] = v; ++idx;
     }

@@ -79,6 +79,22 @@ def test_mtx_loader_rejections(oracle, harness, tmp_path):
     assert load(harness, str(tmp_path / "m.bin2"), tmp_path) is None        # unsupported suffix
 
 
+def test_mtx_loader_token_forms(oracle, harness, tmp_path, request):
+    """Separators, line endings and number spellings the in-place parser must read exactly like std::stoi / std::stod:
+    tabs, CRLF, exponents, signs, an explicit '+' on an index (std::stoi path), a value out of double range (-> 0)."""
+    text = ("%%MatrixMarket matrix coordinate real general\r\n% c\r\n4 5 7\r\n"
+            "1\t2\t1.5e0\r\n2 3 -2.25\r\n+3 4 7\r\n4  1   1e999\r\n1 5 .5\r\n2 1 3.\r\n4 5\r\n")
+    p = str(tmp_path / "forms.mtx")
+    open(p, "w", newline="").write(text)
+    got, want = load(harness, p, tmp_path), oracle.load_mtx(p)
+    assert got is not None and want is not None and same_csr(got, want)
+    assert list(got[2]) == [0, 2, 4, 5, 7] and list(got[3]) == [1, 4, 2, 0, 3, 0, 4]
+    assert list(got[4]) == [1.5, 0.5, -2.25, 3.0, 7.0, 0.0, 0.0]
+    from oracle.bindings import Ref, REF_SO
+    if os.path.exists(REF_SO):
+        assert same_csr(got, Ref().load_matrix_file(p))
+
+
 def test_smtx_and_edge_list_loaders(ref, harness, tmp_path):
     """The other two loaders of initializeFromMatrixFile (src/Matrix.cpp:296-371, 482-585) against the reference."""
     smtx = str(tmp_path / "mask.smtx")
