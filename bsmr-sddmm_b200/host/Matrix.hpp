@@ -375,19 +375,27 @@ public:
         rowOffsets_.assign(static_cast<size_t>(row_) + 1, 0);
         colIndices_.assign(nnz_, 0);
         values_.assign(nnz_, static_cast<T>(1));
+        // one line of row offsets, one line of column indices (millions of words on the DLMC masks): digits in place,
+        // std::stoi for anything else
+        const auto readWords = [&line, &pos](std::vector<UIN>& dst) {
+            const char* text = line.c_str();
+            for (auto& x : dst)
+                if (!detail::fastUnsignedWord(text, pos, x)) x = static_cast<UIN>(std::stoi(util::iterateOneWordFromLine(line, pos)));
+        };
         std::getline(in, line);
         pos = 0;
-        for (auto& o : rowOffsets_) o = static_cast<UIN>(std::stoi(util::iterateOneWordFromLine(line, pos)));
+        readWords(rowOffsets_);
         std::getline(in, line);
         pos = 0;
-        for (auto& ci : colIndices_) ci = static_cast<UIN>(std::stoi(util::iterateOneWordFromLine(line, pos)));
+        readWords(colIndices_);
+        std::vector<UIN> sorted_row;                 // duplicate columns inside a row (an unordered_set per row in the reference)
         for (UIN row = 0; row < row_; ++row) {
-            std::unordered_set<UIN> seen;
-            for (UIN k = rowOffsets_[row]; k < rowOffsets_[row + 1]; ++k)
-                if (!seen.insert(colIndices_[k]).second) {
-                    std::cerr << "Error, matrix has duplicate data!" << std::endl;
-                    return false;
-                }
+            sorted_row.assign(colIndices_.begin() + rowOffsets_[row], colIndices_.begin() + rowOffsets_[row + 1]);
+            std::sort(sorted_row.begin(), sorted_row.end());
+            if (std::adjacent_find(sorted_row.begin(), sorted_row.end()) != sorted_row.end()) {
+                std::cerr << "Error, matrix has duplicate data!" << std::endl;
+                return false;
+            }
         }
         return true;
     }
