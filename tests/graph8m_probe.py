@@ -12,7 +12,10 @@ check of the values against an fp64 dot product of the same rows (size-independe
 Under torchrun (`python -m torch.distributed.run --nproc-per-node N ... tests/graph8m_probe.py ...`) every rank builds
 the same plan (same seed), takes the rank-th of N work-balanced shards of row panels (`bsmr_plan_set_shard`) and times
 its own shard; rank 0 prints the line with the per-rank times and GFLOPS over the slowest rank (strong scaling: the
-matrix is fixed).  A and B are replicated, P stays distributed, there is no collective in the timed region.
+matrix is fixed).  A and B are replicated and there is no collective in the timed SDDMM; afterwards P is assembled on
+every rank by one NCCL all-reduce of the disjoint shards, timed separately (`assemble_p_nccl_allreduce_ms`) and checked
+on entries sampled from the whole matrix (the assembly step was added after the r01h runs of profiles/ and has not run
+on a GPU box yet).
 """
 import json
 import os
@@ -70,7 +73,21 @@ def sharded(torch, pkg, plan, out, world, rank, K, dA, dB, dP, ro, ci, rows, g):
     rel = ((dP[idx].double() - ref).abs() / ref.abs().clamp_min(1e-30)).max().item()
     written = int((dP != 0).sum())
     ok = rel <= 1e-3 and written == shard_nnz == e1 - e0
-    mine = torch.tensor([ms, float(shard_nnz), float(end_panel - first_panel), rel, float(ok)], dtype=torch.float64, device="cuda")
+    # assembly of P over NCCL: the shards are disjoint index sets of the CSR value array and dP is zero elsewhere, so an
+    # all-reduce(sum) leaves the complete result on every rank (timed on the device, outside the SDDMM time above)
+    dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    dist.all_reduce(dP)
+    ev1.record()
+    torch.cuda.synchronize()
+    assemble_ms = ev0.elapsed_time(ev1)
+    idx_all = torch.randint(0, nnz, (1 << 17,), device="cuda", generator=g)
+    ref_all = (dA[rows[idx_all]].double() * dB[ci[idx_all].long()].double()).sum(-1)
+    rel_all = ((dP[idx_all].double() - ref_all).abs() / ref_all.abs().clamp_min(1e-30)).max().item()
+    ok = ok and rel_all <= 1e-3 and int((dP == 0).sum()) == 0
+    rel = max(rel, rel_all)
+    mine = torch.tensor([ms, float(shard_nnz), float(end_panel - first_panel), rel, float(ok), assemble_ms], dtype=torch.float64, device="cuda")
     allr = [torch.zeros_like(mine) for _ in range(world)]
     dist.all_gather(allr, mine)
     if rank == 0:
@@ -78,7 +95,8 @@ def sharded(torch, pkg, plan, out, world, rank, K, dA, dB, dP, ro, ci, rows, g):
         out.update({"n_gpus": world, "scaling": "strong", "ms_by_rank": [float(a[0]) for a in allr],
                     "shard_nnz": [int(a[1]) for a in allr], "shard_panels": [int(a[2]) for a in allr],
                     "sample_max_rel_err": max(float(a[3]) for a in allr), "parity_ok": all(float(a[4]) == 1.0 for a in allr),
-                    "covered_nnz": sum(int(a[1]) for a in allr), "sddmm_ms": t, "gflops": 2.0 * nnz * K / t / 1e6})
+                    "covered_nnz": sum(int(a[1]) for a in allr), "sddmm_ms": t, "gflops": 2.0 * nnz * K / t / 1e6,
+                    "assemble_p_nccl_allreduce_ms": max(float(a[5]) for a in allr)})
         print(json.dumps(out), flush=True)
     dist.barrier()
     dist.destroy_process_group()
