@@ -53,6 +53,10 @@ def main():
                 d["K"], d["ms"], d["gflops"], d["row_ms"], d["col_ms"], d["clusters"], d["mismatches"]))
     out += ["", "The reference's K > 32 kernels produce no output on sm_100 (`1 << tId` shuffle mask, `src/sddmmKernel.cu:2096`; DESIGN.md §4), "
             "hence 0 GFLOP/s and every value mismatching at K = 128.", ""]
+    out += ["## Graphs far larger than L2 (r01h): see `profiles/r01h_l2_policy_sweep.md`", "",
+            "R-MAT 2²³ rows, 2.5·10⁸ nnz, K=256 (BASELINE configs[4]): 27.95 ms = 4.58 TFLOP/s on one B200 (L2 policy on; 30.41 ms",
+            "without), 15.38 / 7.64 ms on 2 / 4 GPUs (98.8 / 99.6 % of linear).  Residual kernel on R-MAT 2²², K=256 under ncu:",
+            "5.49 TB/s of DRAM traffic = 84 % of the measured copy peak.", ""]
     open(os.path.join(HERE, "r01_results.md"), "w").write("\n".join(out))
 
 
