@@ -26,6 +26,7 @@ NULL_VALUE = 0xFFFFFFFF
 ROW_REFERENCE_COMPAT, ROW_EXACT_REDUCE, ROW_IDENTITY = 0, 1, 2
 SDDMM_DEFAULT, SDDMM_RESIDUAL_ONLY, SDDMM_NO_REORDER, SDDMM_NO_WIDE, SDDMM_THREE_KERNEL = 0, 1, 2, 4, 8
 TICKET_ALL = 0xFFFFFFFFFFFFFFFF
+CUDA_STREAM_LEGACY = 1          # cudaStreamLegacy: the legacy default stream as an explicit handle
 WIDE_GROUP_ROWS, WIDE_TILE_COLS = 256, 128
 
 VEC = dict(reordered_rows=0, dense_cols=1, dense_col_offsets=2, sparse_cols=3, sparse_col_offsets=4,
@@ -54,6 +55,13 @@ class PlanInfo(C.Structure):
                 ("num_residual_values", C.c_uint64), ("wide_format_ms", C.c_float)]
 
 
+class ShardTimes(C.Structure):
+    _fields_ = [("h2d_a_ms", C.c_float), ("h2d_b_ms", C.c_float), ("allgather_b_ms", C.c_float), ("kernel_ms", C.c_float),
+                ("pack_ms", C.c_float), ("gather_p_ms", C.c_float), ("unpermute_ms", C.c_float), ("d2h_ms", C.c_float),
+                ("total_ms", C.c_float), ("shard_nnz", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("allgather_b_bytes", C.c_uint64), ("gather_p_bytes", C.c_uint64)]
+
+
 class ReorderStats(C.Structure):
     _fields_ = [("num_dense_blocks", C.c_int32), ("average_density", C.c_float),
                 ("num_dense_thread_blocks", C.c_int32), ("num_sparse_thread_blocks", C.c_int32),
@@ -73,11 +81,13 @@ def lib():
     """The loaded C-ABI library.  Raises (never falls back) when it has not been built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        # BSMR_B200_LIB: another build of the same library (the -DBSMR_DEBUG build with the probe hooks, make DEBUG=1)
+        path = os.environ.get("BSMR_B200_LIB", LIB_PATH)
+        if not os.path.exists(path):
             raise FileNotFoundError(
-                LIB_PATH + " is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                path + " is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU fallback)")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         vp, cp = C.c_void_p, C.c_char_p
         L.bsmr_version.restype = cp
         L.bsmr_last_error.restype = cp
@@ -114,7 +124,20 @@ def lib():
         L.bsmr_plan_set_wide_ratio.argtypes = [vp, C.c_float]
         L.bsmr_plan_set_l2_policy.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32]
         L.bsmr_plan_evaluate.argtypes = [vp, C.c_float, C.POINTER(ReorderStats)]
-        L.bsmr_debug_set_dense_smem_dump.argtypes = [vp]
+        L.bsmr_plan_autotune.argtypes = [vp, C.c_uint32, vp, vp, vp, u32p]
+        L.bsmr_plan_set_execution_choice.argtypes = [vp, C.c_uint32, C.c_uint32]
+        L.bsmr_plan_fit_tile_work.argtypes = [vp, C.c_uint32, vp, vp, vp, f32p]
+        L.bsmr_plan_set_tile_work.argtypes = [vp, C.c_float]
+        L.bsmr_batched_transpose.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]
+        L.bsmr_convert_f32_to_f16.argtypes = [vp, vp, vp, C.c_uint64]
+        L.bsmr_sddmm_f16b.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_int, C.c_uint32, f32p]
+        L.bsmr_comm_unique_id.argtypes = [vp]
+        L.bsmr_ctx_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+        L.bsmr_ctx_comm_destroy.argtypes = [vp]
+        L.bsmr_ctx_comm_bcast.argtypes = [vp, vp, C.c_uint64, C.c_int]
+        L.bsmr_plan_bcast_row_order.argtypes = [vp, C.c_int]
+        L.bsmr_sddmm_sharded.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_uint32, C.c_int, C.POINTER(ShardTimes)]
+        L.bsmr_sddmm_sharded_host.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_uint32, C.c_int, C.POINTER(ShardTimes)]
         for name in ("bsmr_ctx_create", "bsmr_ctx_destroy", "bsmr_ctx_synchronize", "bsmr_ctx_device_name",
                      "bsmr_ctx_launch_count", "bsmr_calculate_block_size", "bsmr_plan_create", "bsmr_plan_destroy",
                      "bsmr_plan_row_reorder", "bsmr_plan_set_row_order", "bsmr_plan_col_reorder", "bsmr_plan_reorder",
@@ -122,7 +145,11 @@ def lib():
                      "bsmr_sddmm", "bsmr_sddmm_host", "bsmr_sddmm_profile", "bsmr_sddmm_profile3",
                      "bsmr_sddmm_host_submit", "bsmr_sddmm_host_wait", "bsmr_sddmm_batch", "bsmr_sddmm_host_batch",
                      "bsmr_plan_fingerprint", "bsmr_plan_save_row_order", "bsmr_plan_load_row_order", "bsmr_plan_execution_choice",
-                     "bsmr_plan_set_wide_ratio", "bsmr_plan_set_l2_policy", "bsmr_plan_evaluate"):
+                     "bsmr_plan_set_wide_ratio", "bsmr_plan_set_l2_policy", "bsmr_plan_evaluate", "bsmr_plan_autotune",
+                     "bsmr_plan_set_execution_choice", "bsmr_plan_fit_tile_work", "bsmr_plan_set_tile_work",
+                     "bsmr_batched_transpose", "bsmr_convert_f32_to_f16", "bsmr_sddmm_f16b", "bsmr_comm_unique_id",
+                     "bsmr_ctx_comm_init", "bsmr_ctx_comm_destroy", "bsmr_ctx_comm_bcast", "bsmr_plan_bcast_row_order",
+                     "bsmr_sddmm_sharded", "bsmr_sddmm_sharded_host"):
             getattr(L, name).restype = C.c_int
         _lib = L
     return _lib
@@ -148,6 +175,15 @@ class Context:
     """One device + one stream (bsmr_ctx)."""
 
     def __init__(self, device=0, stream=None):
+        """stream: a cudaStream_t address.  None -> torch's current stream on that device when torch is imported and has
+        a GPU (work queued by torch before a call is then ordered before it, and vice versa); a stream owned by the
+        context otherwise."""
+        if stream is None:
+            import sys
+            torch = sys.modules.get("torch")
+            if torch is not None and torch.cuda.is_available():
+                # torch's legacy default stream has handle 0, which the C ABI reads as "own stream": name it explicitly
+                stream = torch.cuda.current_stream(device).cuda_stream or CUDA_STREAM_LEGACY
         self._h = C.c_void_p()
         _check(lib().bsmr_ctx_create(device, stream, C.byref(self._h)))
         self.device = device
@@ -176,6 +212,32 @@ class Context:
         out = C.c_uint32()
         _check(lib().bsmr_calculate_block_size(self._h, M, N, free_mem_bytes, C.byref(out)))
         return out.value
+
+    def batched_transpose(self, width, height, num_batches, d_in, d_out):
+        """batchedMatrixTranspose: every batch element height x width row-major -> width x height."""
+        _check(lib().bsmr_batched_transpose(self._h, width, height, num_batches, _ptr(d_in), _ptr(d_out)))
+
+    def convert_f32_to_f16(self, d_src, d_dst, count):
+        _check(lib().bsmr_convert_f32_to_f16(self._h, _ptr(d_src), _ptr(d_dst), count))
+
+    # ---- multi-GPU data plane (NCCL) ----
+    def comm_init(self, unique_id, rank, world):
+        """unique_id: the 128 bytes rank 0 got from comm_unique_id()."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        _check(lib().bsmr_ctx_comm_init(self._h, buf, rank, world))
+
+    def comm_destroy(self):
+        _check(lib().bsmr_ctx_comm_destroy(self._h))
+
+    def comm_bcast(self, d_tensor, nbytes, root=0):
+        _check(lib().bsmr_ctx_comm_bcast(self._h, _ptr(d_tensor), nbytes, root))
+
+
+def comm_unique_id():
+    """Rank 0: a fresh NCCL unique id (128 bytes) to hand to Context.comm_init on every rank."""
+    buf = C.create_string_buffer(128)
+    _check(lib().bsmr_comm_unique_id(buf))
+    return buf.raw
 
 
 class Plan:
@@ -282,10 +344,48 @@ class Plan:
         return hP, ms.value, tot.value
 
     def execution_choice(self, K):
-        """SDDMM flags the default call settled on for this K (0 = three-kernel plan, NO_WIDE, NO_REORDER)."""
+        """SDDMM flags a default call runs for this K (0 = three-kernel plan, unless autotune / set_execution_choice installed another)."""
         f = C.c_uint32(0)
         _check(lib().bsmr_plan_execution_choice(self._h, K, C.byref(f)))
         return f.value
+
+    def autotune(self, K, dA, dB, dP):
+        """Explicit measurement of the execution plans for this K (synchronises, writes P); installs and returns the winner."""
+        f = C.c_uint32(0)
+        _check(lib().bsmr_plan_autotune(self._h, K, _ptr(dA), _ptr(dB), _ptr(dP), C.byref(f)))
+        return f.value
+
+    def set_execution_choice(self, K, flags):
+        _check(lib().bsmr_plan_set_execution_choice(self._h, K, flags))
+
+    def fit_tile_work(self, K, dA, dB, dP):
+        v = C.c_float(0)
+        _check(lib().bsmr_plan_fit_tile_work(self._h, K, _ptr(dA), _ptr(dB), _ptr(dP), C.byref(v)))
+        return v.value
+
+    def set_tile_work(self, v):
+        _check(lib().bsmr_plan_set_tile_work(self._h, v))
+
+    def sddmm_f16b(self, K, dA, dB_f16, dP, iterations=1, flags=SDDMM_DEFAULT, timed=True):
+        """B stored as fp16 ([N, K] halves), A fp32, fp32 accumulate; every nnz through the CUDA-core kernel."""
+        ms = C.c_float(0)
+        _check(lib().bsmr_sddmm_f16b(self._h, K, _ptr(dA), _ptr(dB_f16), _ptr(dP), iterations, flags,
+                                     C.byref(ms) if timed else None))
+        return ms.value
+
+    # ---- multi-GPU data plane ----
+    def bcast_row_order(self, root=0):
+        _check(lib().bsmr_plan_bcast_row_order(self._h, root))
+
+    def sddmm_sharded(self, K, dA, dB, dP_root, flags=SDDMM_DEFAULT, root=0, timed=True):
+        t = ShardTimes()
+        _check(lib().bsmr_sddmm_sharded(self._h, K, _ptr(dA), _ptr(dB), _ptr(dP_root), flags, root, C.byref(t) if timed else None))
+        return {k: getattr(t, k) for k, _ in ShardTimes._fields_}
+
+    def sddmm_sharded_host(self, K, hA, hB, hP, flags=SDDMM_DEFAULT, root=0):
+        t = ShardTimes()
+        _check(lib().bsmr_sddmm_sharded_host(self._h, K, _ptr(hA), _ptr(hB), _ptr(hP), flags, root, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in ShardTimes._fields_}
 
     def fingerprint(self):
         """64-bit fingerprint of the sparsity pattern (key of the reorder cache)."""

@@ -7,6 +7,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cub/cub.cuh>
+
 #include "common.cuh"
 
 namespace bsmr {
@@ -20,7 +22,7 @@ static uint32_t* g_flag_dev = nullptr;
 uint32_t* kernel_error_flag() {
     if (!g_flag_dev) {
         void* h = nullptr;
-        if (cudaHostAlloc(&h, sizeof(uint32_t), cudaHostAllocMapped) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+        if (cudaHostAlloc(&h, sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
         g_flag_host = static_cast<uint32_t*>(h);
         *g_flag_host = 0;
         void* d = nullptr;
@@ -177,6 +179,85 @@ int bsmr_calculate_block_size(bsmr_ctx* ctx, uint32_t M, uint32_t N, uint64_t fr
 }
 
 // ------------------------------------------------------------------------------- plan
+}  // extern "C"
+namespace {
+// The checks the reference's loaders make before a matrix reaches any kernel (src/Matrix.cpp:442-465: entry count,
+// bounds, duplicate coordinates), for patterns that arrive through the C ABI instead of a loader.  One warp per row:
+// bit 0 = offsets not monotone / beyond nnz, bit 1 = column >= N, bit 2 = a row whose columns are not strictly
+// ascending (then duplicates have to be looked for by sorting, below).
+__global__ void validate_csr_kernel(uint32_t M, uint32_t N, uint32_t nnz, const uint32_t* __restrict__ ro, const uint32_t* __restrict__ ci,
+                                    uint32_t* __restrict__ flags) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    uint32_t f = 0;
+    if (warp == 0 && lane == 0 && ro[0] != 0) f |= 1u;
+    for (uint64_t r = warp; r < M; r += stride) {
+        const uint32_t b = ro[r], e = ro[r + 1];
+        if (b > e || e > nnz) { f |= 1u; continue; }
+        for (uint32_t k = b + lane; k < e; k += 32) {
+            const uint32_t c = ci[k];
+            if (c >= N) f |= 2u;
+            if (k > b && ci[k - 1] >= c) f |= 4u;
+        }
+    }
+    f = __reduce_or_sync(0xffffffffu, f);
+    if (lane == 0 && f) atomicOr(flags, f);
+}
+__global__ void row_col_keys_kernel(uint32_t M, const uint32_t* __restrict__ ro, const uint32_t* __restrict__ ci, uint64_t* __restrict__ keys) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < M; r += stride)
+        for (uint32_t k = ro[r] + lane; k < ro[r + 1]; k += 32) keys[k] = (r << 32) | ci[k];
+}
+__global__ void adjacent_equal_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ flags) {
+    uint32_t f = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        if (keys[i] == keys[i - 1]) f = 8u;
+    f = __reduce_or_sync(0xffffffffu, f);
+    if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
+}
+int validate_pattern(bsmr_plan* p) {
+    bsmr_ctx* ctx = p->ctx;
+    DevBuf<uint32_t> d_flags;
+    BSMR_TRY(d_flags.alloc(1));
+    BSMR_CUDA_OK(cudaMemsetAsync(d_flags.ptr, 0, 4, ctx->stream));
+    const int grid = ctx->sm_count * 8;
+    validate_csr_kernel<<<grid, 256, 0, ctx->stream>>>(p->M, p->N, p->nnz, p->row_offsets.ptr, p->col_indices.ptr, d_flags.ptr);
+    ctx->launches++;
+    uint32_t f = 0;
+    BSMR_CUDA_OK(cudaMemcpyAsync(&f, d_flags.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    BSMR_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    if ((f & 3u) == 0 && (f & 4u) && p->nnz > 1) {
+        // some row is not in ascending column order (the .mtx loader keeps file order: src/Matrix.cpp:467-470), so a
+        // repeated coordinate need not be adjacent: sort (row, column) keys and compare neighbours
+        DevBuf<uint64_t> ka, kb;
+        DevBuf<uint8_t> tmp;
+        BSMR_TRY(ka.alloc(p->nnz));
+        BSMR_TRY(kb.alloc(p->nnz));
+        row_col_keys_kernel<<<grid, 256, 0, ctx->stream>>>(p->M, p->row_offsets.ptr, p->col_indices.ptr, ka.ptr);
+        cub::DoubleBuffer<uint64_t> dk(ka.ptr, kb.ptr);
+        size_t tb = 0;
+        int end_bit = 33;
+        while (end_bit < 64 && ((uint64_t)p->M >> (end_bit - 32)) != 0) ++end_bit;
+        BSMR_CUDA_OK(cub::DeviceRadixSort::SortKeys(nullptr, tb, dk, static_cast<int64_t>(p->nnz), 0, end_bit, ctx->stream));
+        BSMR_TRY(tmp.alloc(tb + 256));
+        BSMR_CUDA_OK(cub::DeviceRadixSort::SortKeys(tmp.ptr, tb, dk, static_cast<int64_t>(p->nnz), 0, end_bit, ctx->stream));
+        adjacent_equal_kernel<<<grid, 256, 0, ctx->stream>>>(dk.Current(), p->nnz, d_flags.ptr);
+        ctx->launches += 3;
+        BSMR_CUDA_OK(cudaMemcpyAsync(&f, d_flags.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        BSMR_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    }
+    BSMR_CUDA_OK(cudaGetLastError());
+    if (f & 1u) { set_error("bsmr_plan_create: row_offsets is not a non-decreasing sequence from 0 to nnz"); return BSMR_ERR_INVALID_ARGUMENT; }
+    if (f & 2u) { set_error("bsmr_plan_create: a column index is >= N = %u (the reference's loaders reject this: src/Matrix.cpp:452)", p->N); return BSMR_ERR_INVALID_ARGUMENT; }
+    if (f & 8u) { set_error("bsmr_plan_create: a (row, column) coordinate appears twice (the reference's loaders reject this: src/Matrix.cpp:457)"); return BSMR_ERR_INVALID_ARGUMENT; }
+    return BSMR_OK;
+}
+}  // namespace
+extern "C" {
+
 int bsmr_plan_create(bsmr_ctx* ctx, uint32_t M, uint32_t N, uint32_t nnz, const uint32_t* row_offsets,
                      const uint32_t* col_indices, int on_device, bsmr_plan** out) {
     if (!ctx || !out || !row_offsets || (nnz && !col_indices)) {
@@ -213,6 +294,15 @@ int bsmr_plan_create(bsmr_ctx* ctx, uint32_t M, uint32_t N, uint32_t nnz, const 
         delete p;
         return BSMR_ERR_INVALID_ARGUMENT;
     }
+    // ... and the rest of the loaders' checks: offsets monotone, columns in range, no coordinate twice.  Anything else
+    // would reach the kernels as out-of-bounds reads of B or as a (panel, column) run longer than 16.
+    {
+        const int vs = validate_pattern(p);
+        if (vs != BSMR_OK) {
+            delete p;
+            return vs;
+        }
+    }
     *out = p;
     return BSMR_OK;
 }
@@ -233,6 +323,9 @@ int bsmr_plan_destroy(bsmr_plan* plan) {
 
 static void reset_shard(bsmr_plan* p) {
     p->sharded = false;
+    p->shard_rank = 0;
+    p->shard_world = 1;
+    p->h_shard_bounds.assign({0u, p->num_row_panels});
     p->shard_first_panel = 0;
     p->shard_end_panel = p->num_row_panels;
     p->shard_res_begin = 0;
@@ -245,6 +338,12 @@ static void reset_shard(bsmr_plan* p) {
     p->shard_tile2_end = p->num_tiles2;
     p->shard_res2_begin = 0;
     p->shard_res2_end = p->num_res2;
+}
+
+int bsmr_plan_set_tile_work(bsmr_plan* plan, float nnz_equivalents_per_tile) {
+    if (!plan || !(nnz_equivalents_per_tile >= 0.f)) return BSMR_ERR_INVALID_ARGUMENT;
+    plan->tile_work = nnz_equivalents_per_tile;
+    return BSMR_OK;
 }
 
 int bsmr_plan_set_wide_ratio(bsmr_plan* plan, float ratio) {
@@ -265,7 +364,7 @@ int bsmr_plan_set_l2_policy(bsmr_plan* plan, uint32_t hot_budget_mb, uint32_t mi
 int bsmr_plan_row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flags) {
     if (!plan) return BSMR_ERR_INVALID_ARGUMENT;
     BSMR_CUDA_OK(cudaSetDevice(plan->ctx->device));
-    plan->have_cols = plan->have_format = false;
+    plan->have_cols = plan->have_format = plan->have_flat = false;
     BSMR_TRY(row_reorder(plan, alpha, block_size, flags));
     plan->have_rows = true;
     return BSMR_OK;
@@ -277,10 +376,17 @@ int bsmr_plan_set_row_order(bsmr_plan* plan, const uint32_t* reordered_rows, uin
         set_error("bsmr_plan_set_row_order: %u rows given but the matrix has %u", count, plan->M);
         return BSMR_ERR_INVALID_ARGUMENT;
     }
-    for (uint32_t i = 0; i < count; ++i) {
-        if (reordered_rows[i] >= plan->M) {
-            set_error("bsmr_plan_set_row_order: row %u out of range", reordered_rows[i]);
-            return BSMR_ERR_INVALID_ARGUMENT;
+    {
+        std::vector<uint8_t> seen(plan->M, 0);
+        for (uint32_t i = 0; i < count; ++i) {
+            if (reordered_rows[i] >= plan->M) {
+                set_error("bsmr_plan_set_row_order: row %u out of range", reordered_rows[i]);
+                return BSMR_ERR_INVALID_ARGUMENT;
+            }
+            if (seen[reordered_rows[i]]++) {
+                set_error("bsmr_plan_set_row_order: row %u is listed twice", reordered_rows[i]);
+                return BSMR_ERR_INVALID_ARGUMENT;
+            }
         }
     }
     BSMR_CUDA_OK(cudaSetDevice(plan->ctx->device));
@@ -294,7 +400,7 @@ int bsmr_plan_set_row_order(bsmr_plan* plan, const uint32_t* reordered_rows, uin
     // numRowPanels_ = ceil(size / ROW_PANEL_SIZE)   (src/BSMR.cpp:57)
     plan->num_row_panels = (count + kPanel - 1) / kPanel;
     plan->have_rows = true;
-    plan->have_cols = plan->have_format = false;
+    plan->have_cols = plan->have_format = plan->have_flat = false;
     return BSMR_OK;
 }
 
@@ -606,22 +712,23 @@ int bsmr_plan_set_shard(bsmr_plan* plan, uint32_t rank, uint32_t world, uint32_t
         return BSMR_ERR_BAD_STATE;
     }
     // contiguous ranges of reordered row panels, boundaries where the work prefix crosses rank * total / world.
-    // Work of a panel = its nnz, plus, inside a wide row group, its share of the group's tiles at 3000 nnz-equivalents
-    // per tile: the wide kernel's time follows the tile count far more than the nnz.  Measured on an 8-way sharded stack
-    // of nips blocks (clustering puts the dense rows together, so row groups differ 5x in nnz): balanced on nnz alone
-    // the ranks got 2 to 10 row groups and took 20 to 33 us per step; at 900 per tile 18.5 to 28.9 us.
+    // Work of a panel = its nnz, plus, inside a wide row group, its share of the group's tiles at `tile_work`
+    // nnz-equivalents per tile: the wide kernel's time follows the tile count far more than the nnz.  tile_work is a
+    // property of the plan: the default (3000) was fitted by hand on an 8-way sharded stack of nips blocks (clustering
+    // puts the dense rows together, so row groups differ 5x in nnz: balanced on nnz alone the ranks took 20 to 33 us per
+    // step); bsmr_plan_fit_tile_work measures it for this plan and K from the kernels' own times.
     const std::vector<uint64_t>& nnz_pre = plan->h_panel_nnz_prefix;  // size panels + 1
     const uint32_t panels = plan->num_row_panels;
     const uint32_t ppg = BSMR_WIDE_GROUP_ROWS / kPanel;
     std::vector<uint64_t> work_pre;
     if (plan->num_wide_tiles && !nnz_pre.empty()) {
-        constexpr uint64_t kTileWork = 3000;
+        const double tile_work = plan->tile_work;
         work_pre.assign(nnz_pre.size(), 0);
         for (uint32_t q = 0; q < panels; ++q) {
             const uint32_t g = q / ppg;
             const uint64_t tiles = g + 1 < plan->h_wt_group_off.size() && plan->h_group_wide[g] ? plan->h_wt_group_off[g + 1] - plan->h_wt_group_off[g] : 0;
             const uint32_t in_group = std::min(ppg, panels - g * ppg);
-            work_pre[q + 1] = work_pre[q] + (nnz_pre[q + 1] - nnz_pre[q]) + kTileWork * tiles / in_group;
+            work_pre[q + 1] = work_pre[q] + (nnz_pre[q + 1] - nnz_pre[q]) + static_cast<uint64_t>(tile_work * static_cast<double>(tiles) / in_group);
         }
     }
     const std::vector<uint64_t>& pre = work_pre.empty() ? nnz_pre : work_pre;
@@ -630,21 +737,22 @@ int bsmr_plan_set_shard(bsmr_plan* plan, uint32_t rank, uint32_t world, uint32_t
         if (r == 0) return 0;
         if (r >= world) return panels;
         const uint64_t target = total / world * r + (total % world) * r / world;
-        return static_cast<uint32_t>(std::lower_bound(pre.begin(), pre.end(), target) - pre.begin());
+        uint32_t q = static_cast<uint32_t>(std::lower_bound(pre.begin(), pre.end(), target) - pre.begin());
+        if (q > panels) q = panels;
+        if (plan->num_wide_tiles) {
+            // a wide row group (16 panels) is one unit of work: move the boundary to the nearest group boundary
+            const uint32_t snapped = (q + ppg / 2) / ppg * ppg;
+            q = snapped > panels ? panels : snapped;
+        }
+        return q;
     };
-    uint32_t b = boundary(rank), e = boundary(rank + 1);
-    if (b > panels) b = panels;
-    if (e > panels) e = panels;
-    if (plan->num_wide_tiles) {
-        // a wide row group (16 panels) is one unit of work: move the boundaries to the nearest group boundary
-        auto snap = [&](uint32_t q) -> uint32_t {
-            if (q >= panels) return panels;
-            const uint32_t r = (q + ppg / 2) / ppg * ppg;
-            return r > panels ? panels : r;
-        };
-        b = rank == 0 ? 0 : snap(b);
-        e = rank + 1 == world ? panels : snap(e);
-    }
+    // every rank computes every boundary (the sharded data plane needs the other ranks' ranges: comm.cu)
+    plan->h_shard_bounds.assign(static_cast<size_t>(world) + 1, 0);
+    for (uint32_t r = 0; r <= world; ++r) plan->h_shard_bounds[r] = boundary(r);
+    for (uint32_t r = 1; r <= world; ++r) plan->h_shard_bounds[r] = std::max(plan->h_shard_bounds[r], plan->h_shard_bounds[r - 1]);
+    uint32_t b = plan->h_shard_bounds[rank], e = plan->h_shard_bounds[rank + 1];
+    plan->shard_rank = rank;
+    plan->shard_world = world;
     if (e < b) e = b;
     plan->sharded = world > 1;
     plan->auto_flags.clear();   // the execution plan is chosen again for the shard
@@ -682,19 +790,86 @@ static int ensure_identity_rows(bsmr_plan* p) {
     return launch_expand_rows(p->ctx, p->M, p->nnz, p->row_offsets.ptr, p->csr_row_of_nnz.ptr);
 }
 
-// One SDDMM pass = dense-block kernel over the (sharded) tile range + residual kernel over the
-// (sharded) residual range.  The reference runs the two on separate streams
-// (src/sddmmKernel.cu:2555-2559); here they are issued back to back on the context's stream --
-// both are persistent-style grids that fill the machine on their own.
-static int run_once(bsmr_plan* p, uint32_t K, const float* dA, const float* dB, float* dP, uint32_t flags) {
+// The whole pattern as ONE row-sorted list in reordered-row order: entry e = (A row, B column, CSR position), rows in
+// the order of reorderedRows, a row's entries in CSR order.  Panel q owns [h_panel_nnz_prefix[q], h_panel_nnz_prefix[q+1]),
+// so a shard (a range of reordered row panels) is one contiguous range of it.  Built on first use; it is what the
+// residual kernel walks when an operand has no tensor-core path (K % 4 != 0, unaligned A / B, fp16 B), and the
+// order in which the sharded data plane (comm.cu) packs a rank's slice of P.
+}  // extern "C"
+namespace {
+__global__ void reordered_row_len_kernel(uint32_t n, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ ro, uint32_t* __restrict__ len) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = rows[i];
+        len[i] = ro[r + 1] - ro[r];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) len[n] = 0;
+}
+__global__ void flat_expand_kernel(uint32_t n, const uint32_t* __restrict__ rows, const uint32_t* __restrict__ ro, const uint32_t* __restrict__ ci,
+                                   const uint32_t* __restrict__ off, uint32_t* __restrict__ frow, uint32_t* __restrict__ fcol,
+                                   uint32_t* __restrict__ fout) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t i = warp; i < n; i += stride) {
+        const uint32_t r = rows[i], b = ro[r], e = ro[r + 1], o = off[i];
+        for (uint32_t k = b + lane; k < e; k += 32) {
+            frow[o + (k - b)] = r;
+            fcol[o + (k - b)] = ci[k];
+            fout[o + (k - b)] = k;
+        }
+    }
+}
+}  // namespace
+namespace bsmr {
+int ensure_flat_list(bsmr_plan* p) {
+    if (p->have_flat || p->nnz == 0) return BSMR_OK;
     bsmr_ctx* ctx = p->ctx;
+    const uint32_t n = static_cast<uint32_t>(p->h_reordered_rows.size());
+    DevBuf<uint32_t> len, off;
+    DevBuf<uint8_t> tmp;
+    BSMR_TRY(len.alloc(static_cast<size_t>(n) + 1));
+    BSMR_TRY(off.alloc(static_cast<size_t>(n) + 1));
+    BSMR_TRY(p->flat_row.alloc(p->nnz));
+    BSMR_TRY(p->flat_col.alloc(p->nnz));
+    BSMR_TRY(p->flat_out.alloc(p->nnz));
+    const int grid = ctx->sm_count * 8;
+    reordered_row_len_kernel<<<grid, 256, 0, ctx->stream>>>(n, p->reordered_rows.ptr, p->row_offsets.ptr, len.ptr);
+    size_t tb = 0;
+    BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb, len.ptr, off.ptr, static_cast<size_t>(n) + 1, ctx->stream));
+    BSMR_TRY(tmp.alloc(tb + 256));
+    BSMR_CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp.ptr, tb, len.ptr, off.ptr, static_cast<size_t>(n) + 1, ctx->stream));
+    flat_expand_kernel<<<grid, 256, 0, ctx->stream>>>(n, p->reordered_rows.ptr, p->row_offsets.ptr, p->col_indices.ptr, off.ptr,
+                                                      p->flat_row.ptr, p->flat_col.ptr, p->flat_out.ptr);
+    ctx->launches += 3;
+    BSMR_CUDA_OK(cudaGetLastError());
+    BSMR_CUDA_OK(cudaStreamSynchronize(ctx->stream));      // the scratch above goes out of scope
+    p->have_flat = true;
+    return BSMR_OK;
+}
+}  // namespace bsmr
+extern "C" {
+
+// One SDDMM pass over the (sharded) plan for `batch` (A, B, P) triples on the same pattern (batch element b at
+// A + b*M*K, B + b*N*K, P + b*nnz: sddmm_gpu_batch's strides, src/sddmmKernel.cu:2764-2848; batch = 1: sddmm_gpu).
+// The reference runs its two kernels on separate streams (:2555-2559) and folds the batch into gridDim.z; here up to
+// three kernels over disjoint sets of nnz run on three streams of the context, each launched ONCE for the whole batch
+// (wide: the persistent CTAs walk their tile range once per element, metadata reused; dense: work item = (element,
+// tile); residual: gridDim.y = element).
+// b_half: B holds fp16 (bsmr_sddmm_f16b); only the CUDA-core kernel reads that, so every nnz goes through it.
+static int run_pass(bsmr_plan* p, uint32_t K, const float* dA, const void* dBv, bool b_half, float* dP, uint32_t flags, uint32_t batch) {
+    bsmr_ctx* ctx = p->ctx;
+    const float* dB = static_cast<const float*>(dBv);
     // B far larger than L2: the residual kernel asks L2 to keep the hub columns (nullptr otherwise; residual.cu)
     const uint32_t* hot = nullptr;
     uint32_t cold_first = 0;
-    BSMR_TRY(hot_columns(p, K, &hot, &cold_first));
+    BSMR_TRY(hot_columns(p, K, &hot, &cold_first, b_half ? 2 : 4));
+    ResidualArgs ra{};
+    ra.K = K; ra.A = dA; ra.B = dBv; ra.b_half = b_half; ra.P = dP; ra.col_hot = hot; ra.cold_first = cold_first;
+    ra.batch = batch; ra.stride_a = (size_t)p->M * K; ra.stride_b = (size_t)p->N * K; ra.stride_p = p->nnz; ra.stream = ctx->stream;
     if (flags & BSMR_SDDMM_NO_REORDER) {
         // CSR order: A row from the expanded row list, B column = CSR column, P index = position
-        return launch_residual(ctx, K, dA, dB, dP, p->csr_row_of_nnz.ptr, p->col_indices.ptr, nullptr, 0, p->nnz, hot, cold_first);
+        ra.row = p->csr_row_of_nnz.ptr; ra.col = p->col_indices.ptr; ra.out = nullptr; ra.begin = 0; ra.end = p->nnz;
+        return launch_residual(ctx, ra);
     }
     if ((flags & BSMR_SDDMM_RESIDUAL_ONLY) && p->num_tiles != 0) {
         set_error("BSMR_SDDMM_RESIDUAL_ONLY needs a plan whose column reorder ran with delta > 1 (no dense tiles); "
@@ -705,40 +880,53 @@ static int run_once(bsmr_plan* p, uint32_t K, const float* dA, const float* dB, 
     // (side stream; launched before the residual kernel so that its CTAs take their shared memory / TMEM slots) and
     // the residual kernel (main stream), joined on the main stream.  Without wide groups -- or when the caller asks
     // for the reference's split, or K does not fit the wide kernel -- the full BSMR lists are used.
-    const bool wide = p->num_wide_tiles != 0 && !(flags & BSMR_SDDMM_NO_WIDE) && wide_supports(K, dA, dB);
+    const bool wide = p->num_wide_tiles != 0 && !(flags & BSMR_SDDMM_NO_WIDE) && !b_half && wide_supports(K, dA, dB);
     const uint32_t wt_b = wide ? p->shard_wt_begin : 0, wt_e = wide ? p->shard_wt_end : 0;
     const uint32_t tl_b = wide ? p->shard_tile2_begin : p->shard_tile_begin, tl_e = wide ? p->shard_tile2_end : p->shard_tile_end;
     const uint64_t rs_b = wide ? p->shard_res2_begin : p->shard_res_begin, rs_e = wide ? p->shard_res2_end : p->shard_res_end;
     const uint32_t* tile_list = wide ? p->tile_list2.ptr : nullptr;
-    const uint32_t* rr_row = wide ? p->rr2_row.ptr : p->rr_row.ptr;
-    const uint32_t* rr_col = wide ? p->rr2_col.ptr : p->rr_col.ptr;
-    const uint32_t* rr_out = wide ? p->rr2_out.ptr : p->rr_out.ptr;
+    ra.row = wide ? p->rr2_row.ptr : p->rr_row.ptr;
+    ra.col = wide ? p->rr2_col.ptr : p->rr_col.ptr;
+    ra.out = wide ? p->rr2_out.ptr : p->rr_out.ptr;
+    ra.begin = rs_b; ra.end = rs_e;
     const bool do_wide = wt_e > wt_b, do_dense = tl_e > tl_b, do_res = rs_e > rs_b;
+    if (b_half || (do_dense && !dense_supports(K, dA, dB))) {
+        // no tensor-core path for these operands (fp16 B, K % 4 != 0, unaligned pointers): every nnz of the shard through
+        // the CUDA-core kernel, rows in reordered order (the TMA row stride must be a multiple of 16 bytes)
+        BSMR_TRY(ensure_flat_list(p));
+        ra.row = p->flat_row.ptr; ra.col = p->flat_col.ptr; ra.out = p->flat_out.ptr;
+        ra.begin = p->h_panel_nnz_prefix.empty() ? 0 : p->h_panel_nnz_prefix[p->shard_first_panel];
+        ra.end = p->h_panel_nnz_prefix.empty() ? 0 : p->h_panel_nnz_prefix[p->shard_end_panel];
+        return launch_residual(ctx, ra);
+    }
     const int kinds = (int)do_wide + (int)do_dense + (int)do_res;
     if (kinds <= 1) {
-        if (do_wide) return launch_wide(p, K, dA, dB, dP, wt_b, wt_e, ctx->stream);
-        if (do_dense) return launch_dense(p, K, dA, dB, dP, tl_b, tl_e, tile_list, ctx->stream);
-        return launch_residual(ctx, K, dA, dB, dP, rr_row, rr_col, rr_out, rs_b, rs_e, hot, cold_first);
+        if (do_wide) return launch_wide(p, K, dA, dB, dP, wt_b, wt_e, ctx->stream, batch);
+        if (do_dense) return launch_dense(p, K, dA, dB, dP, tl_b, tl_e, tile_list, ctx->stream, batch);
+        return launch_residual(ctx, ra);
     }
     BSMR_CUDA_OK(cudaEventRecord(ctx->ev_fork, ctx->stream));
     if (do_wide) {
         BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->side_stream2, ctx->ev_fork, 0));
-        BSMR_TRY(launch_wide(p, K, dA, dB, dP, wt_b, wt_e, ctx->side_stream2));
+        BSMR_TRY(launch_wide(p, K, dA, dB, dP, wt_b, wt_e, ctx->side_stream2, batch));
         BSMR_CUDA_OK(cudaEventRecord(ctx->ev_join2, ctx->side_stream2));
     }
     if (do_dense && do_res) {
         BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
-        BSMR_TRY(launch_dense(p, K, dA, dB, dP, tl_b, tl_e, tile_list, ctx->side_stream));
+        BSMR_TRY(launch_dense(p, K, dA, dB, dP, tl_b, tl_e, tile_list, ctx->side_stream, batch));
         BSMR_CUDA_OK(cudaEventRecord(ctx->ev_join, ctx->side_stream));
-        BSMR_TRY(launch_residual(ctx, K, dA, dB, dP, rr_row, rr_col, rr_out, rs_b, rs_e, hot, cold_first));
+        BSMR_TRY(launch_residual(ctx, ra));
         BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     } else if (do_dense) {
-        BSMR_TRY(launch_dense(p, K, dA, dB, dP, tl_b, tl_e, tile_list, ctx->stream));
+        BSMR_TRY(launch_dense(p, K, dA, dB, dP, tl_b, tl_e, tile_list, ctx->stream, batch));
     } else if (do_res) {
-        BSMR_TRY(launch_residual(ctx, K, dA, dB, dP, rr_row, rr_col, rr_out, rs_b, rs_e, hot, cold_first));
+        BSMR_TRY(launch_residual(ctx, ra));
     }
     if (do_wide) BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));
     return BSMR_OK;
+}
+static int run_once(bsmr_plan* p, uint32_t K, const float* dA, const float* dB, float* dP, uint32_t flags, uint32_t batch = 1) {
+    return run_pass(p, K, dA, dB, false, dP, flags, batch);
 }
 
 int bsmr_sddmm(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP, int iterations, uint32_t flags,
@@ -755,40 +943,14 @@ int bsmr_sddmm(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, fl
     BSMR_CUDA_OK(cudaSetDevice(ctx->device));
     if (ms_per_iteration) *ms_per_iteration = 0.f;
     if (plan->nnz == 0) return BSMR_OK;
-    // Execution plan per K, chosen by measurement on the first default call with that K: the three-kernel plan (wide
-    // groups + BSMR split), the BSMR split alone, or -- unsharded only -- the CSR-order residual kernel.  Which one wins
-    // depends on K as much as on the pattern (nips: CSR order at K = 32, the wide plan at K = 128); all of them
-    // compute the same P.  One warm-up pass and the best of three timed ones each; the choice is kept with the plan's format.
+    // Execution plan of a default call: the three-kernel plan, unless the caller asked for a measured choice for this K
+    // (bsmr_plan_autotune) or installed one (bsmr_plan_set_execution_choice).  Nothing is measured, synchronised or
+    // written here: the call stays asynchronous and stream-capturable, and gives the same bits on every run and rank.
     if (flags == BSMR_SDDMM_DEFAULT && plan->have_format) {
         auto it = plan->auto_flags.find(K);
-        if (it == plan->auto_flags.end()) {
-            static const bool no_auto = std::getenv("BSMR_NO_AUTOTUNE") != nullptr;
-            uint32_t best = BSMR_SDDMM_DEFAULT;
-            if (!no_auto) {
-                std::vector<uint32_t> cand{BSMR_SDDMM_DEFAULT};
-                if (plan->num_wide_tiles != 0 && wide_supports(K, dA, dB)) cand.push_back(BSMR_SDDMM_NO_WIDE);
-                if (!plan->sharded) cand.push_back(BSMR_SDDMM_NO_REORDER);
-                float best_ms = 0.f;
-                for (uint32_t f : cand) {
-                    if (f & BSMR_SDDMM_NO_REORDER) BSMR_TRY(ensure_identity_rows(plan));
-                    float ms = 0.f;
-                    for (int rep = 0; rep < 4; ++rep) {          // one warm-up pass, then the best of three
-                        float t = 0.f;
-                        BSMR_CUDA_OK(cudaEventRecord(ctx->ev0, ctx->stream));
-                        BSMR_TRY(run_once(plan, K, dA, dB, dP, f));
-                        BSMR_CUDA_OK(cudaEventRecord(ctx->ev1, ctx->stream));
-                        BSMR_CUDA_OK(cudaEventSynchronize(ctx->ev1));
-                        BSMR_CUDA_OK(cudaEventElapsedTime(&t, ctx->ev0, ctx->ev1));
-                        if (rep == 1 || (rep > 1 && t < ms)) ms = t;
-                    }
-                    if (f == cand[0] || ms < best_ms) { best_ms = ms; best = f; }
-                }
-            }
-            it = plan->auto_flags.emplace(K, best).first;
-        }
-        flags = it->second;
+        if (it != plan->auto_flags.end()) flags = it->second;
     }
-    flags &= ~BSMR_SDDMM_THREE_KERNEL;     // = the default plan, minus the choice above
+    flags &= ~BSMR_SDDMM_THREE_KERNEL;     // = the default plan, whatever choice is installed
     if (flags & BSMR_SDDMM_NO_REORDER) BSMR_TRY(ensure_identity_rows(plan));
     if (iterations <= 0) iterations = 1;
     if (ms_per_iteration) BSMR_CUDA_OK(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -806,11 +968,70 @@ int bsmr_sddmm(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, fl
 int bsmr_plan_execution_choice(bsmr_plan* plan, uint32_t K, uint32_t* flags) {
     if (!plan || !flags) return BSMR_ERR_INVALID_ARGUMENT;
     auto it = plan->auto_flags.find(K);
-    if (it == plan->auto_flags.end()) {
-        set_error("bsmr_plan_execution_choice: no default SDDMM call with K = %u yet", K);
+    *flags = it == plan->auto_flags.end() ? BSMR_SDDMM_DEFAULT : it->second;
+    return BSMR_OK;
+}
+
+int bsmr_plan_set_execution_choice(bsmr_plan* plan, uint32_t K, uint32_t flags) {
+    if (!plan || K == 0) return BSMR_ERR_INVALID_ARGUMENT;
+    if (flags != BSMR_SDDMM_DEFAULT && flags != BSMR_SDDMM_NO_WIDE && flags != BSMR_SDDMM_NO_REORDER && flags != BSMR_SDDMM_THREE_KERNEL) {
+        set_error("bsmr_plan_set_execution_choice: flags %u is not one of DEFAULT / THREE_KERNEL / NO_WIDE / NO_REORDER", flags);
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    if ((flags & BSMR_SDDMM_NO_REORDER) && plan->sharded) {
+        set_error("bsmr_plan_set_execution_choice: the CSR-order kernel is not shard-aware");
         return BSMR_ERR_BAD_STATE;
     }
-    *flags = it->second;
+    if (flags == BSMR_SDDMM_DEFAULT || flags == BSMR_SDDMM_THREE_KERNEL) plan->auto_flags.erase(K);
+    else plan->auto_flags[K] = flags;
+    return BSMR_OK;
+}
+
+// Explicit measurement of the execution plans for one K (a tool, not part of the default call: it synchronises, writes
+// P four times per candidate and its outcome depends on timing).  Candidates: the three-kernel plan, the BSMR split
+// alone and -- unsharded -- the CSR-order residual kernel; one warm-up pass and the best of three timed ones each, on
+// private events.  The winner is installed for default calls with this K until the next column reorder / set_shard.
+// Numerics differ between the candidates (TF32 tensor-core tiles ~1.5e-4 relative, fp32 residual ~1e-6): callers that
+// need identical bits across ranks agree on one choice with bsmr_plan_set_execution_choice.
+int bsmr_plan_autotune(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP, uint32_t* chosen_flags) {
+    if (!plan || !dA || !dB || (plan->nnz && !dP) || K == 0) {
+        set_error("bsmr_plan_autotune: NULL pointer or K == 0");
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    if (!plan->have_format) {
+        set_error("bsmr_plan_autotune: the plan has no reorder/format yet (call bsmr_plan_reorder)");
+        return BSMR_ERR_BAD_STATE;
+    }
+    bsmr_ctx* ctx = plan->ctx;
+    BSMR_CUDA_OK(cudaSetDevice(ctx->device));
+    uint32_t best = BSMR_SDDMM_DEFAULT;
+    if (plan->nnz) {
+        std::vector<uint32_t> cand{BSMR_SDDMM_DEFAULT};
+        if (plan->num_wide_tiles != 0 && wide_supports(K, dA, dB)) cand.push_back(BSMR_SDDMM_NO_WIDE);
+        if (!plan->sharded) cand.push_back(BSMR_SDDMM_NO_REORDER);
+        cudaEvent_t t0, t1;
+        BSMR_CUDA_OK(cudaEventCreate(&t0));
+        BSMR_CUDA_OK(cudaEventCreate(&t1));
+        struct Guard { cudaEvent_t a, b; ~Guard() { cudaEventDestroy(a); cudaEventDestroy(b); } } guard{t0, t1};
+        float best_ms = 0.f;
+        for (uint32_t f : cand) {
+            if (f & BSMR_SDDMM_NO_REORDER) BSMR_TRY(ensure_identity_rows(plan));
+            float ms = 0.f;
+            for (int rep = 0; rep < 4; ++rep) {
+                float t = 0.f;
+                BSMR_CUDA_OK(cudaEventRecord(t0, ctx->stream));
+                BSMR_TRY(run_once(plan, K, dA, dB, dP, f));
+                BSMR_CUDA_OK(cudaEventRecord(t1, ctx->stream));
+                BSMR_CUDA_OK(cudaEventSynchronize(t1));
+                BSMR_CUDA_OK(cudaEventElapsedTime(&t, t0, t1));
+                if (rep == 1 || (rep > 1 && t < ms)) ms = t;
+            }
+            if (f == cand[0] || ms < best_ms) { best_ms = ms; best = f; }
+        }
+    }
+    if (best == BSMR_SDDMM_DEFAULT) plan->auto_flags.erase(K);
+    else plan->auto_flags[K] = best;
+    if (chosen_flags) *chosen_flags = best;
     return BSMR_OK;
 }
 
@@ -860,6 +1081,33 @@ int bsmr_sddmm_profile3(bsmr_plan* plan, uint32_t K, const float* dA, const floa
     if (dense_ms) *dense_ms = a;
     if (residual_ms) *residual_ms = b;
     return s;
+}
+
+// Fit of the shard balance's tile weight for this plan and K from the kernels' own times (unsharded plan): one wide
+// tile costs wide_ms / #tiles, one nnz outside the wide groups (dense_ms + residual_ms) / nnz there.  Timing-dependent:
+// in a multi-rank run one rank measures and every rank installs the same value (bsmr_plan_set_tile_work) BEFORE
+// bsmr_plan_set_shard, or the ranks' ranges would not partition the panels.
+int bsmr_plan_fit_tile_work(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP, float* nnz_equivalents_per_tile) {
+    if (!plan || !nnz_equivalents_per_tile) return BSMR_ERR_INVALID_ARGUMENT;
+    *nnz_equivalents_per_tile = static_cast<float>(plan->tile_work);
+    if (plan->sharded) {
+        set_error("bsmr_plan_fit_tile_work: measure on the unsharded plan (before bsmr_plan_set_shard)");
+        return BSMR_ERR_BAD_STATE;
+    }
+    const uint64_t outside = plan->num_block_values2 + plan->num_res2;
+    if (plan->num_wide_tiles == 0 || outside == 0) return BSMR_OK;      // nothing to weigh against each other
+    float best_w = 0.f, best_o = 0.f;
+    for (int rep = 0; rep < 4; ++rep) {
+        float w = 0.f, a = 0.f, b = 0.f;
+        BSMR_TRY(bsmr_sddmm_profile3(plan, K, dA, dB, dP, BSMR_SDDMM_THREE_KERNEL, &w, &a, &b));
+        if (rep == 1 || (rep > 1 && w < best_w)) best_w = w;
+        if (rep == 1 || (rep > 1 && a + b < best_o)) best_o = a + b;
+    }
+    if (best_w > 0.f && best_o > 0.f) {
+        const double per_tile = best_w / plan->num_wide_tiles, per_nnz = best_o / static_cast<double>(outside);
+        *nnz_equivalents_per_tile = static_cast<float>(per_tile / per_nnz);
+    }
+    return BSMR_OK;
 }
 
 int bsmr_sddmm_profile(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP, uint32_t flags,
@@ -981,13 +1229,12 @@ extern "C" {
 
 // Whether copies in opposite directions may run at the same time.  On some hosts of this pool a 6.4 MB H2D and a 3 MB D2H
 // in flight together drop to ~12 GB/s each (53 GB/s alone), on others they overlap perfectly (140 instead of 200 us per
-// nips step).  Decided once per process by timing 2 MB each way, back to back and concurrently (about a millisecond);
+// nips step).  Decided once per context (= per device) by timing 2 MB each way, back to back and concurrently (about a millisecond);
 // environment BSMR_HOST_PIPE_DUPLEX = 0 / 1 overrides.
-static int g_duplex = -1;
 static int probe_duplex(bsmr_ctx* ctx) {
-    if (g_duplex >= 0) return BSMR_OK;
+    if (ctx->duplex >= 0) return BSMR_OK;
     if (const char* e = std::getenv("BSMR_HOST_PIPE_DUPLEX")) {
-        g_duplex = std::atoi(e) != 0 ? 1 : 0;
+        ctx->duplex = std::atoi(e) != 0 ? 1 : 0;
         return BSMR_OK;
     }
     const size_t bytes = 2u << 20;
@@ -995,7 +1242,7 @@ static int probe_duplex(bsmr_ctx* ctx) {
     if (cudaHostAlloc(&h, 2 * bytes, cudaHostAllocDefault) != cudaSuccess || cudaMalloc(&d, 2 * bytes) != cudaSuccess) {
         (void)cudaGetLastError();
         if (h) cudaFreeHost(h);
-        g_duplex = 0;
+        ctx->duplex = 0;
         return BSMR_OK;
     }
     char* hb = static_cast<char*>(h);
@@ -1018,19 +1265,19 @@ static int probe_duplex(bsmr_ctx* ctx) {
         return best;
     };
     const double t_seq = run(false), t_dup = run(true);
-    g_duplex = t_dup < 0.8 * t_seq ? 1 : 0;
+    ctx->duplex = t_dup < 0.8 * t_seq ? 1 : 0;
     cudaFree(d);
     cudaFreeHost(h);
     (void)cudaGetLastError();
     return BSMR_OK;
 }
-static bool host_pipe_duplex() { return g_duplex == 1; }
+static bool host_pipe_duplex(const bsmr_ctx* ctx) { return ctx->duplex == 1; }
 
 // queue the copy-out of a slot whose kernels have been issued
 static int queue_copy_out(bsmr_plan* plan, bsmr_plan::HostSlot& s) {
     if (s.d2h_queued) return BSMR_OK;
     bsmr_ctx* ctx = plan->ctx;
-    cudaStream_t cs = host_pipe_duplex() ? ctx->copy_out_stream : ctx->copy_in_stream;
+    cudaStream_t cs = host_pipe_duplex(ctx) ? ctx->copy_out_stream : ctx->copy_in_stream;
     BSMR_CUDA_OK(cudaStreamWaitEvent(cs, s.compute_done, 0));
     BSMR_TRY(copy_async(ctx, s.hP, s.dP.ptr, s.dP.bytes(), cudaMemcpyDeviceToHost, cs));
     BSMR_CUDA_OK(cudaEventRecord(s.d2h_done, cs));
@@ -1077,7 +1324,7 @@ int bsmr_sddmm_host_submit(bsmr_plan* plan, uint32_t K, const float* hA, const f
     s.hP = hP;
     s.d2h_queued = false;
     s.in_flight = true;
-    if (host_pipe_duplex()) BSMR_TRY(queue_copy_out(plan, s));   // two copy streams: nothing to hold back
+    if (host_pipe_duplex(ctx)) BSMR_TRY(queue_copy_out(plan, s));   // two copy streams: nothing to hold back
     plan->host_submits = id + 1;
     if (ticket) *ticket = id;
     return BSMR_OK;
@@ -1109,29 +1356,158 @@ int bsmr_sddmm_host_wait(bsmr_plan* plan, uint64_t ticket) {
 
 // sddmm_gpu_batch (include/sddmmKernel.cuh:41-47, src/sddmmKernel.cu:2764-2848): numBatch (A, B, P) triples on one
 // pattern, batch b at A + b*M*K, B + b*N*K, P + b*nnz.  The reference folds the batch into gridDim.z of its two
-// kernels; here every batch element is one pass of the plan's kernels, issued back to back (asynchronously) on the
-// context's streams.
+// kernels; here every kernel of the plan is launched ONCE for the whole batch (run_once): the wide kernel's persistent
+// CTAs walk their tile range once per element with the tile metadata in place, the dense-block kernel's work items are
+// (element, tile) pairs, the residual kernel takes the element from gridDim.y -- one launch + one tail per kernel
+// instead of one per element.  The stacked operands are addressed through one tensor map with batch*M / batch*N rows:
+// batches beyond the 31-bit TMA coordinate range are cut into sub-batches.
 int bsmr_sddmm_batch(bsmr_plan* plan, uint32_t num_batch, uint32_t K, const float* dA, const float* dB, float* dP,
                      uint32_t flags, float* total_ms) {
     if (!plan || !dA || !dB || (plan->nnz && !dP) || K == 0) {
         set_error("bsmr_sddmm_batch: NULL pointer or K == 0");
         return BSMR_ERR_INVALID_ARGUMENT;
     }
+    if (!(flags & BSMR_SDDMM_NO_REORDER) && !plan->have_format) {
+        set_error("bsmr_sddmm_batch: the plan has no reorder/format yet (call bsmr_plan_reorder)");
+        return BSMR_ERR_BAD_STATE;
+    }
     bsmr_ctx* ctx = plan->ctx;
     BSMR_CUDA_OK(cudaSetDevice(ctx->device));
+    if (total_ms) *total_ms = 0.f;
+    if (plan->nnz == 0 || num_batch == 0) return BSMR_OK;
+    if (flags == BSMR_SDDMM_DEFAULT && plan->have_format) {
+        auto it = plan->auto_flags.find(K);
+        if (it != plan->auto_flags.end()) flags = it->second;
+    }
+    flags &= ~BSMR_SDDMM_THREE_KERNEL;
+    if (flags & BSMR_SDDMM_NO_REORDER) BSMR_TRY(ensure_identity_rows(plan));
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
     if (total_ms) {
-        *total_ms = 0.f;
-        BSMR_CUDA_OK(cudaEventRecord(ctx->ev0, ctx->stream));
+        BSMR_CUDA_OK(cudaEventCreate(&t0));
+        BSMR_CUDA_OK(cudaEventCreate(&t1));
+        BSMR_CUDA_OK(cudaEventRecord(t0, ctx->stream));
     }
     const size_t sa = static_cast<size_t>(plan->M) * K, sb = static_cast<size_t>(plan->N) * K;
-    for (uint32_t b = 0; b < num_batch; ++b)
-        BSMR_TRY(bsmr_sddmm(plan, K, dA + b * sa, dB + b * sb, dP + static_cast<size_t>(b) * plan->nnz, 1, flags, nullptr));
+    const uint64_t big = std::max<uint64_t>(std::max(plan->M, plan->N), 1);
+    const uint32_t chunk = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(num_batch, 0x7FFFFFFFull / big)));
+    int s = BSMR_OK;
+    for (uint32_t b = 0; b < num_batch && s == BSMR_OK; b += chunk)
+        s = run_once(plan, K, dA + b * sa, dB + b * sb, dP + static_cast<size_t>(b) * plan->nnz, flags, std::min(chunk, num_batch - b));
     if (total_ms) {
-        BSMR_CUDA_OK(cudaEventRecord(ctx->ev1, ctx->stream));
-        BSMR_CUDA_OK(cudaEventSynchronize(ctx->ev1));
-        BSMR_CUDA_OK(cudaEventElapsedTime(total_ms, ctx->ev0, ctx->ev1));
+        cudaError_t e = cudaEventRecord(t1, ctx->stream);
+        if (e == cudaSuccess) e = cudaEventSynchronize(t1);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(total_ms, t0, t1);
+        cudaEventDestroy(t0);
+        cudaEventDestroy(t1);
+        if (s == BSMR_OK && e != cudaSuccess) {
+            set_error("bsmr_sddmm_batch: %s", cudaGetErrorString(e));
+            s = BSMR_ERR_CUDA;
+        }
     }
+    return s;
+}
+
+// batchedMatrixTranspose (include/sddmmKernel.cuh:49-51, src/sddmmKernel.cu:2486-2515, 2852-2869): every batch element
+// is a height x width row-major matrix, written back as width x height; elements are width*height apart.  (The
+// reference takes int strides; 64-bit here.)  This is how a caller turns row-major B matrices [K x N] into the
+// column-major operand the SDDMM kernels read.
+}  // extern "C"
+namespace {
+__global__ void __launch_bounds__(256) batched_transpose_kernel(uint32_t width, uint32_t height, uint32_t batches, const float* __restrict__ in,
+                                                                 float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // 32 x 8 threads, 4 rows each
+    const uint32_t tw = (width + 31) / 32, th = (height + 31) / 32;
+    const uint64_t per = (uint64_t)tw * th, total = per * batches;
+    const size_t mat = (size_t)width * height;
+    for (uint64_t w = blockIdx.x; w < total; w += gridDim.x) {
+        const uint32_t b = (uint32_t)(w / per);
+        const uint32_t r = (uint32_t)(w - (uint64_t)b * per);
+        const uint32_t by = r / tw, bx = r - by * tw;
+        const float* src = in + b * mat;
+        float* dst = out + b * mat;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t x = bx * 32 + tx, y = by * 32 + ty + 8 * j;
+            if (x < width && y < height) tile[ty + 8 * j][tx] = src[(size_t)y * width + x];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t x = by * 32 + tx, y = bx * 32 + ty + 8 * j;        // output: row y (an input column), column x
+            if (x < height && y < width) dst[(size_t)y * height + x] = tile[tx][ty + 8 * j];
+        }
+        __syncthreads();
+    }
+}
+}  // namespace
+extern "C" {
+
+int bsmr_batched_transpose(bsmr_ctx* ctx, uint32_t width, uint32_t height, uint32_t num_batches, const float* d_input, float* d_output) {
+    if (!ctx || (!d_input || !d_output)) {
+        set_error("bsmr_batched_transpose: NULL argument");
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    if (width == 0 || height == 0 || num_batches == 0) return BSMR_OK;
+    BSMR_CUDA_OK(cudaSetDevice(ctx->device));
+    const uint64_t tiles = (uint64_t)((width + 31) / 32) * ((height + 31) / 32) * num_batches;
+    const uint64_t cap = (uint64_t)ctx->sm_count * 8;
+    batched_transpose_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, ctx->stream>>>(width, height, num_batches, d_input, d_output);
+    ctx->launches++;
+    BSMR_CUDA_OK(cudaGetLastError());
     return BSMR_OK;
+}
+
+// ---- fp16 storage of B (the reference sketches half operands in include/TensorCoreConfig.cuh:22-56) ----
+int bsmr_convert_f32_to_f16(bsmr_ctx* ctx, const float* d_src, void* d_dst, uint64_t count) {
+    if (!ctx || (count && (!d_src || !d_dst))) return BSMR_ERR_INVALID_ARGUMENT;
+    BSMR_CUDA_OK(cudaSetDevice(ctx->device));
+    return launch_f32_to_f16(ctx, d_src, d_dst, count, ctx->stream);
+}
+
+int bsmr_sddmm_f16b(bsmr_plan* plan, uint32_t K, const float* dA, const void* dB_f16, float* dP, int iterations, uint32_t flags,
+                    float* ms_per_iteration) {
+    if (!plan || !dA || !dB_f16 || (plan->nnz && !dP) || K == 0) {
+        set_error("bsmr_sddmm_f16b: NULL pointer or K == 0");
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    if (flags != BSMR_SDDMM_DEFAULT && flags != BSMR_SDDMM_NO_REORDER) {
+        set_error("bsmr_sddmm_f16b: flags must be BSMR_SDDMM_DEFAULT (reordered row order) or BSMR_SDDMM_NO_REORDER (CSR order)");
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    if (!(flags & BSMR_SDDMM_NO_REORDER) && !plan->have_format) {
+        set_error("bsmr_sddmm_f16b: the plan has no reorder/format yet (call bsmr_plan_reorder)");
+        return BSMR_ERR_BAD_STATE;
+    }
+    bsmr_ctx* ctx = plan->ctx;
+    BSMR_CUDA_OK(cudaSetDevice(ctx->device));
+    if (ms_per_iteration) *ms_per_iteration = 0.f;
+    if (plan->nnz == 0) return BSMR_OK;
+    if (flags & BSMR_SDDMM_NO_REORDER) BSMR_TRY(ensure_identity_rows(plan));
+    else BSMR_TRY(ensure_flat_list(plan));
+    if (iterations <= 0) iterations = 1;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (ms_per_iteration) {
+        BSMR_CUDA_OK(cudaEventCreate(&t0));
+        BSMR_CUDA_OK(cudaEventCreate(&t1));
+        BSMR_CUDA_OK(cudaEventRecord(t0, ctx->stream));
+    }
+    int s = BSMR_OK;
+    for (int it = 0; it < iterations && s == BSMR_OK; ++it) s = run_pass(plan, K, dA, dB_f16, true, dP, flags, 1);
+    if (ms_per_iteration) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventRecord(t1, ctx->stream);
+        if (e == cudaSuccess) e = cudaEventSynchronize(t1);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, t0, t1);
+        cudaEventDestroy(t0);
+        cudaEventDestroy(t1);
+        if (s == BSMR_OK && e != cudaSuccess) {
+            set_error("bsmr_sddmm_f16b: %s", cudaGetErrorString(e));
+            s = BSMR_ERR_CUDA;
+        }
+        *ms_per_iteration = ms / static_cast<float>(iterations);
+    }
+    return s;
 }
 
 // The batch with host data: one pipelined host-data call per batch element (copy-in of element b + 1 and copy-out of

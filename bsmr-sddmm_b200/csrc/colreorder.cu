@@ -97,7 +97,9 @@ __global__ void run_keys_kernel(const uint64_t* __restrict__ ukeys, const uint32
         const bool valid = u < num_runs;
         const uint32_t panel = valid ? (uint32_t)(ukeys[u] >> cbits) : 0xFFFFFFFFu;
         if (valid) {
-            key2[u] = (panel << 4) | (16u - counts[u]);
+            // a (panel, column) run holds at most 16 entries on a valid pattern (bsmr_plan_create rejects repeated
+            // coordinates, set_row_order repeated rows); clamped so that a broken invariant cannot reach the panel bits
+            key2[u] = (panel << 4) | (16u - min(counts[u], 16u));
             iota[u] = (uint32_t)u;
         }
         const uint32_t peers = __match_any_sync(0xffffffffu, panel);

@@ -1,0 +1,412 @@
+// Multi-GPU data plane of the sharded SDDMM: NCCL over NVLink 5 / NVSwitch, one process per GPU.
+//
+// No counterpart in the reference (single process, device 0 only: include/Logger.hpp:23-25).  The path shards by
+// contiguous ranges of REORDERED row panels balanced on work (bsmr_plan_set_shard); output entries are independent, so
+// the only exchanges are the two the problem has:
+//   before the kernels   B (K x N, read by every rank): every rank uploads 1/world of it over its own PCIe link and an
+//                        in-place ncclAllGather replicates it (world x the host->device rate of a root upload +
+//                        ncclBroadcast); A follows the panels: a rank uploads only the rows of its shard
+//   after the kernels    P: the kernels write CSR positions; a rank's entries are ONE contiguous range of the pattern
+//                        in reordered-row order (ensure_flat_list), so a pack kernel makes its slice contiguous, the
+//                        slices go to the root with grouped ncclSend / ncclRecv (a gather-v: 4 * nnz bytes in total,
+//                        not an all-reduce of nnz-length arrays), and one kernel on the root un-permutes to CSR order
+// The row order is global (clustering sees every row) and is the cost centre: it is computed on one rank and broadcast
+// (bsmr_plan_bcast_row_order); the column reorder + format build (integer only, deterministic) is recomputed on every
+// rank concurrently, which is cheaper than shipping the format.
+// NCCL is resolved at run time (dlopen of libnccl.so.2: inside a PyTorch process that is the copy torch already
+// loaded), so libbsmr_b200.so has no link-time dependency on it and single-GPU users never load it.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace bsmr {
+namespace {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+NcclApi& nccl() {
+    static NcclApi api = [] {
+        NcclApi a;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            a.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (a.handle) break;
+        }
+        if (!a.handle) return a;
+        auto sym = [&](const char* n) { return dlsym(a.handle, n); };
+        a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(sym("ncclGetUniqueId"));
+        a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(sym("ncclCommInitRank"));
+        a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
+        a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(sym("ncclBroadcast"));
+        a.AllGather = reinterpret_cast<decltype(a.AllGather)>(sym("ncclAllGather"));
+        a.Send = reinterpret_cast<decltype(a.Send)>(sym("ncclSend"));
+        a.Recv = reinterpret_cast<decltype(a.Recv)>(sym("ncclRecv"));
+        a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(sym("ncclGroupStart"));
+        a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
+        a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.Broadcast && a.AllGather && a.Send && a.Recv && a.GroupStart &&
+               a.GroupEnd && a.GetErrorString;
+        return a;
+    }();
+    return api;
+}
+
+#define BSMR_NCCL_OK(expr)                                                                         \
+    do {                                                                                           \
+        ncclResult_t _r = (expr);                                                                  \
+        if (_r != ncclSuccess) {                                                                   \
+            ::bsmr::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, nccl().GetErrorString(_r)); \
+            return BSMR_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+int need_nccl() {
+    if (!nccl().ok) {
+        set_error("NCCL is not available (dlopen of libnccl.so.2 failed: %s)", dlerror() ? dlerror() : "symbols missing");
+        return BSMR_ERR_UNSUPPORTED;
+    }
+    return BSMR_OK;
+}
+int need_comm(const bsmr_ctx* ctx, const char* who) {
+    if (!ctx->nccl_comm) {
+        set_error("%s: the context has no communicator (call bsmr_ctx_comm_init on every rank first)", who);
+        return BSMR_ERR_BAD_STATE;
+    }
+    return BSMR_OK;
+}
+ncclComm_t comm_of(const bsmr_ctx* ctx) { return static_cast<ncclComm_t>(ctx->nccl_comm); }
+
+// rows of A that a shard reads, straight from (mapped, pinned) host memory into their place in the device copy of A:
+// one warp per row, 16-byte pieces; the reads are PCIe bursts of a whole K-vector
+__global__ void upload_rows_kernel(const float* __restrict__ host_a, float* __restrict__ dev_a, const uint32_t* __restrict__ rows,
+                                   uint32_t n, uint32_t K) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t k4 = K / 4;
+    for (uint64_t i = warp; i < n; i += stride) {
+        const size_t off = (size_t)rows[i] * K;
+        const float4* src = reinterpret_cast<const float4*>(host_a + off);
+        float4* dst = reinterpret_cast<float4*>(dev_a + off);
+        for (uint32_t k = lane; k < k4; k += 32) dst[k] = src[k];
+        for (uint32_t k = k4 * 4 + lane; k < K; k += 32) dev_a[off + k] = host_a[off + k];
+    }
+}
+
+// slice[e - begin] = P[flat_out[e]]  (a rank's entries made contiguous, in reordered-row order)
+__global__ void pack_p_kernel(const float* __restrict__ P, const uint32_t* __restrict__ flat_out, uint64_t begin, uint64_t end,
+                              float* __restrict__ slice) {
+    for (uint64_t e = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < end; e += (uint64_t)gridDim.x * blockDim.x)
+        slice[e - begin] = P[__ldg(flat_out + e)];
+}
+// P[flat_out[e]] = assembled[e]  (root: back to CSR order)
+__global__ void unpack_p_kernel(const float* __restrict__ assembled, const uint32_t* __restrict__ flat_out, uint64_t begin, uint64_t end,
+                                float* __restrict__ P) {
+    for (uint64_t e = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < end; e += (uint64_t)gridDim.x * blockDim.x)
+        P[__ldg(flat_out + e)] = assembled[e];
+}
+
+const float* mapped_host_alias(const float* host) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? static_cast<const float*>(a.devicePointer) : nullptr;
+}
+
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() {
+        if (a) cudaEventDestroy(a);
+        if (b) cudaEventDestroy(b);
+    }
+};
+
+// kernels of the shard + pack + gather-v to root + un-permute; P of the whole pattern lands in dP_root (root only)
+int assemble_sharded(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP_root, uint32_t flags, int root,
+                     bsmr_shard_times* times, cudaEvent_t* stamps /* 5 events or nullptr */) {
+    bsmr_ctx* ctx = plan->ctx;
+    const int rank = ctx->comm_rank, world = ctx->comm_world;
+    if (!plan->sharded || plan->shard_world != (uint32_t)world || plan->shard_rank != (uint32_t)rank) {
+        set_error("sharded SDDMM: call bsmr_plan_set_shard(rank = %d, world = %d) with the communicator's rank / size first", rank, world);
+        return BSMR_ERR_BAD_STATE;
+    }
+    BSMR_TRY(ensure_flat_list(plan));
+    const std::vector<uint64_t>& pre = plan->h_panel_nnz_prefix;
+    const std::vector<uint32_t>& bounds = plan->h_shard_bounds;     // world + 1 panel boundaries
+    const uint64_t e0 = pre[bounds[rank]], e1 = pre[bounds[rank + 1]];
+    BSMR_TRY(plan->shard_p.alloc(plan->nnz));                        // this rank's P in CSR positions (only its entries are defined)
+    BSMR_TRY(plan->shard_slice.alloc(rank == root ? plan->nnz : (size_t)(e1 - e0)));
+    if (stamps) BSMR_CUDA_OK(cudaEventRecord(stamps[0], ctx->stream));
+    BSMR_TRY(bsmr_sddmm(plan, K, dA, dB, plan->shard_p.ptr, 1, flags, nullptr));
+    if (stamps) BSMR_CUDA_OK(cudaEventRecord(stamps[1], ctx->stream));
+    const int grid = ctx->sm_count * 8;
+    // the root's own slice is packed straight into its place in the assembled array
+    float* slice = rank == root ? plan->shard_slice.ptr + e0 : plan->shard_slice.ptr;
+    if (e1 > e0) {
+        pack_p_kernel<<<grid, 256, 0, ctx->stream>>>(plan->shard_p.ptr, plan->flat_out.ptr, e0, e1, slice);
+        ctx->launches++;
+    }
+    if (stamps) BSMR_CUDA_OK(cudaEventRecord(stamps[2], ctx->stream));
+    NcclApi& n = nccl();
+    BSMR_NCCL_OK(n.GroupStart());
+    if (rank == root) {
+        for (int r = 0; r < world; ++r) {
+            const uint64_t b = pre[bounds[r]], e = pre[bounds[r + 1]];
+            if (r != root && e > b) BSMR_NCCL_OK(n.Recv(plan->shard_slice.ptr + b, e - b, ncclFloat32, r, comm_of(ctx), ctx->stream));
+        }
+    } else if (e1 > e0) {
+        BSMR_NCCL_OK(n.Send(slice, e1 - e0, ncclFloat32, root, comm_of(ctx), ctx->stream));
+    }
+    BSMR_NCCL_OK(n.GroupEnd());
+    if (stamps) BSMR_CUDA_OK(cudaEventRecord(stamps[3], ctx->stream));
+    if (rank == root && plan->nnz) {
+        if (!dP_root) {
+            set_error("sharded SDDMM: the root needs an output buffer");
+            return BSMR_ERR_INVALID_ARGUMENT;
+        }
+        unpack_p_kernel<<<grid, 256, 0, ctx->stream>>>(plan->shard_slice.ptr, plan->flat_out.ptr, 0, plan->nnz, dP_root);
+        ctx->launches++;
+    }
+    if (stamps) BSMR_CUDA_OK(cudaEventRecord(stamps[4], ctx->stream));
+    BSMR_CUDA_OK(cudaGetLastError());
+    if (times) {
+        times->shard_nnz = e1 - e0;
+        times->gather_p_bytes = rank == root ? (plan->nnz - (e1 - e0)) * 4ull : (e1 - e0) * 4ull;
+    }
+    return BSMR_OK;
+}
+
+}  // namespace
+}  // namespace bsmr
+
+using namespace bsmr;
+
+extern "C" {
+
+int bsmr_comm_unique_id(void* id_out) {
+    if (!id_out) return BSMR_ERR_INVALID_ARGUMENT;
+    BSMR_TRY(need_nccl());
+    ncclUniqueId id;
+    BSMR_NCCL_OK(nccl().GetUniqueId(&id));
+    static_assert(sizeof(id) == BSMR_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    std::memcpy(id_out, &id, sizeof(id));
+    return BSMR_OK;
+}
+
+int bsmr_ctx_comm_init(bsmr_ctx* ctx, const void* unique_id, int rank, int world) {
+    if (!ctx || !unique_id || world < 1 || rank < 0 || rank >= world) {
+        set_error("bsmr_ctx_comm_init: bad arguments (rank %d, world %d)", rank, world);
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    BSMR_TRY(need_nccl());
+    BSMR_CUDA_OK(cudaSetDevice(ctx->device));
+    if (ctx->nccl_comm) BSMR_TRY(bsmr_ctx_comm_destroy(ctx));
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id, sizeof(id));
+    ncclComm_t comm = nullptr;
+    BSMR_NCCL_OK(nccl().CommInitRank(&comm, world, id, rank));
+    ctx->nccl_comm = comm;
+    ctx->comm_rank = rank;
+    ctx->comm_world = world;
+    return BSMR_OK;
+}
+
+int bsmr_ctx_comm_destroy(bsmr_ctx* ctx) {
+    if (!ctx) return BSMR_ERR_INVALID_ARGUMENT;
+    if (ctx->nccl_comm) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        nccl().CommDestroy(comm_of(ctx));
+        ctx->nccl_comm = nullptr;
+        ctx->comm_rank = 0;
+        ctx->comm_world = 1;
+    }
+    return BSMR_OK;
+}
+
+int bsmr_ctx_comm_bcast(bsmr_ctx* ctx, void* device_ptr, uint64_t bytes, int root) {
+    if (!ctx || (bytes && !device_ptr)) return BSMR_ERR_INVALID_ARGUMENT;
+    BSMR_TRY(need_comm(ctx, "bsmr_ctx_comm_bcast"));
+    BSMR_CUDA_OK(cudaSetDevice(ctx->device));
+    if (bytes) BSMR_NCCL_OK(nccl().Broadcast(device_ptr, device_ptr, bytes, ncclUint8, root, comm_of(ctx), ctx->stream));
+    return BSMR_OK;
+}
+
+// The row order is computed on `root` (bsmr_plan_row_reorder there; the other ranks skip it) and installed on every
+// rank like bsmr_plan_set_row_order; each rank then runs bsmr_plan_col_reorder(delta) itself.
+int bsmr_plan_bcast_row_order(bsmr_plan* plan, int root) {
+    if (!plan) return BSMR_ERR_INVALID_ARGUMENT;
+    bsmr_ctx* ctx = plan->ctx;
+    BSMR_TRY(need_comm(ctx, "bsmr_plan_bcast_row_order"));
+    BSMR_CUDA_OK(cudaSetDevice(ctx->device));
+    const bool is_root = ctx->comm_rank == root;
+    if (is_root && !plan->have_rows) {
+        set_error("bsmr_plan_bcast_row_order: the root has no row order yet");
+        return BSMR_ERR_BAD_STATE;
+    }
+    // header: {count, num_clusters, num_clusters_true, block_size}
+    DevBuf<uint32_t> hdr, rows;
+    BSMR_TRY(hdr.alloc(4));
+    uint32_t h[4] = {0, 0, 0, 0};
+    if (is_root) {
+        h[0] = static_cast<uint32_t>(plan->h_reordered_rows.size());
+        h[1] = static_cast<uint32_t>(plan->num_clusters);
+        h[2] = static_cast<uint32_t>(plan->num_clusters_true);
+        h[3] = plan->block_size;
+        BSMR_CUDA_OK(cudaMemcpyAsync(hdr.ptr, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    BSMR_NCCL_OK(nccl().Broadcast(hdr.ptr, hdr.ptr, sizeof(h), ncclUint8, root, comm_of(ctx), ctx->stream));
+    BSMR_CUDA_OK(cudaMemcpyAsync(h, hdr.ptr, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    BSMR_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    if (h[0] > plan->M) {
+        set_error("bsmr_plan_bcast_row_order: the root announced %u rows for a matrix with %u", h[0], plan->M);
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    BSMR_TRY(rows.alloc(h[0] ? h[0] : 1));
+    if (is_root && h[0]) BSMR_CUDA_OK(cudaMemcpyAsync(rows.ptr, plan->reordered_rows.ptr, (size_t)h[0] * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (h[0]) BSMR_NCCL_OK(nccl().Broadcast(rows.ptr, rows.ptr, (size_t)h[0] * 4, ncclUint8, root, comm_of(ctx), ctx->stream));
+    if (!is_root) {
+        std::vector<uint32_t> host_rows(h[0]);
+        if (h[0]) BSMR_CUDA_OK(cudaMemcpyAsync(host_rows.data(), rows.ptr, (size_t)h[0] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        BSMR_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+        BSMR_TRY(bsmr_plan_set_row_order(plan, host_rows.data(), h[0]));
+        plan->num_clusters = static_cast<int>(h[1]);
+        plan->num_clusters_true = static_cast<int>(h[2]);
+        plan->block_size = h[3];
+    } else {
+        BSMR_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    }
+    return BSMR_OK;
+}
+
+int bsmr_sddmm_sharded(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP_root, uint32_t flags, int root,
+                       bsmr_shard_times* times) {
+    if (!plan || !dA || !dB || K == 0) {
+        set_error("bsmr_sddmm_sharded: NULL pointer or K == 0");
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    bsmr_ctx* ctx = plan->ctx;
+    BSMR_TRY(need_comm(ctx, "bsmr_sddmm_sharded"));
+    BSMR_CUDA_OK(cudaSetDevice(ctx->device));
+    if (times) std::memset(times, 0, sizeof(*times));
+    if (!times) return assemble_sharded(plan, K, dA, dB, dP_root, flags, root, nullptr, nullptr);
+    cudaEvent_t ev[5];
+    for (auto& e : ev) BSMR_CUDA_OK(cudaEventCreate(&e));
+    int s = assemble_sharded(plan, K, dA, dB, dP_root, flags, root, times, ev);
+    if (s == BSMR_OK) {
+        cudaError_t e = cudaEventSynchronize(ev[4]);
+        if (e != cudaSuccess) {
+            set_error("bsmr_sddmm_sharded: %s", cudaGetErrorString(e));
+            s = BSMR_ERR_CUDA;
+        } else {
+            cudaEventElapsedTime(&times->kernel_ms, ev[0], ev[1]);
+            cudaEventElapsedTime(&times->pack_ms, ev[1], ev[2]);
+            cudaEventElapsedTime(&times->gather_p_ms, ev[2], ev[3]);
+            cudaEventElapsedTime(&times->unpermute_ms, ev[3], ev[4]);
+            cudaEventElapsedTime(&times->total_ms, ev[0], ev[4]);
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return s;
+}
+
+int bsmr_sddmm_sharded_host(bsmr_plan* plan, uint32_t K, const float* hA, const float* hB, float* hP, uint32_t flags, int root,
+                            bsmr_shard_times* times) {
+    if (!plan || !hA || !hB || K == 0) {
+        set_error("bsmr_sddmm_sharded_host: NULL pointer or K == 0");
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    bsmr_ctx* ctx = plan->ctx;
+    BSMR_TRY(need_comm(ctx, "bsmr_sddmm_sharded_host"));
+    BSMR_CUDA_OK(cudaSetDevice(ctx->device));
+    const int rank = ctx->comm_rank, world = ctx->comm_world;
+    if (rank == root && plan->nnz && !hP) {
+        set_error("bsmr_sddmm_sharded_host: the root needs an output buffer");
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    if (!plan->sharded || plan->shard_world != (uint32_t)world || plan->shard_rank != (uint32_t)rank) {
+        set_error("bsmr_sddmm_sharded_host: call bsmr_plan_set_shard(rank = %d, world = %d) first", rank, world);
+        return BSMR_ERR_BAD_STATE;
+    }
+    bsmr_shard_times local{};
+    bsmr_shard_times* t = times ? times : &local;
+    std::memset(t, 0, sizeof(*t));
+    const size_t na = (size_t)plan->M * K;
+    // B is padded to world equal slices of whole columns (ncclAllGather wants equal counts)
+    const uint32_t cols_per = (plan->N + world - 1) / world;
+    const size_t nb_padded = (size_t)cols_per * world * K;
+    BSMR_TRY(plan->dA.alloc(na));
+    BSMR_TRY(plan->dB.alloc(nb_padded));
+    BSMR_TRY(plan->dP.alloc(rank == root ? plan->nnz : 1));
+    cudaEvent_t ev[9];
+    for (auto& e : ev) BSMR_CUDA_OK(cudaEventCreate(&e));
+    struct Guard { cudaEvent_t* e; ~Guard() { for (int i = 0; i < 9; ++i) cudaEventDestroy(e[i]); } } guard{ev};
+    cudaStream_t st = ctx->stream;
+    BSMR_CUDA_OK(cudaEventRecord(ev[0], st));
+    // ---- A: only the rows of this rank's panels ----
+    const uint32_t r0 = plan->shard_first_panel * kPanel;
+    const uint32_t r1 = std::min<uint32_t>(plan->shard_end_panel * kPanel, static_cast<uint32_t>(plan->h_reordered_rows.size()));
+    const float* hA_dev = (K % 4 == 0) ? mapped_host_alias(hA) : nullptr;
+    if (r1 > r0) {
+        if (hA_dev) {
+            upload_rows_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(hA_dev, plan->dA.ptr, plan->reordered_rows.ptr + r0, r1 - r0, K);
+            ctx->launches++;
+            t->h2d_bytes += (uint64_t)(r1 - r0) * K * 4;
+        } else {
+            // pageable / unmapped host memory: the rows cannot be gathered over PCIe by a kernel, the whole matrix goes up
+            BSMR_CUDA_OK(cudaMemcpyAsync(plan->dA.ptr, hA, na * sizeof(float), cudaMemcpyHostToDevice, st));
+            t->h2d_bytes += na * 4;
+        }
+    }
+    BSMR_CUDA_OK(cudaEventRecord(ev[1], st));
+    // ---- B: 1/world of the columns per rank, then all-gather in place ----
+    const uint32_t c0 = std::min<uint32_t>(plan->N, cols_per * rank), c1 = std::min<uint32_t>(plan->N, c0 + cols_per);
+    if (c1 > c0) {
+        BSMR_CUDA_OK(cudaMemcpyAsync(plan->dB.ptr + (size_t)c0 * K, hB + (size_t)c0 * K, (size_t)(c1 - c0) * K * sizeof(float), cudaMemcpyHostToDevice, st));
+        t->h2d_bytes += (uint64_t)(c1 - c0) * K * 4;
+    }
+    BSMR_CUDA_OK(cudaEventRecord(ev[2], st));
+    if (world > 1)
+        BSMR_NCCL_OK(nccl().AllGather(plan->dB.ptr + (size_t)cols_per * rank * K, plan->dB.ptr, (size_t)cols_per * K, ncclFloat32, comm_of(ctx), st));
+    t->allgather_b_bytes = world > 1 ? (uint64_t)cols_per * K * 4 * (world - 1) : 0;
+    BSMR_CUDA_OK(cudaEventRecord(ev[3], st));
+    // ---- kernels, pack, gather-v, un-permute ----
+    BSMR_TRY(assemble_sharded(plan, K, plan->dA.ptr, plan->dB.ptr, plan->dP.ptr, flags, root, t, ev + 3));   // stamps 3..7
+    // ---- P: root copies the assembled result out ----
+    if (rank == root && plan->nnz) {
+        BSMR_CUDA_OK(cudaMemcpyAsync(hP, plan->dP.ptr, (size_t)plan->nnz * sizeof(float), cudaMemcpyDeviceToHost, st));
+        t->d2h_bytes = (uint64_t)plan->nnz * 4;
+    }
+    BSMR_CUDA_OK(cudaEventRecord(ev[8], st));
+    BSMR_CUDA_OK(cudaEventSynchronize(ev[8]));
+    cudaEventElapsedTime(&t->h2d_a_ms, ev[0], ev[1]);
+    cudaEventElapsedTime(&t->h2d_b_ms, ev[1], ev[2]);
+    cudaEventElapsedTime(&t->allgather_b_ms, ev[2], ev[3]);
+    cudaEventElapsedTime(&t->kernel_ms, ev[3], ev[4]);
+    cudaEventElapsedTime(&t->pack_ms, ev[4], ev[5]);
+    cudaEventElapsedTime(&t->gather_p_ms, ev[5], ev[6]);
+    cudaEventElapsedTime(&t->unpermute_ms, ev[6], ev[7]);
+    cudaEventElapsedTime(&t->d2h_ms, ev[7], ev[8]);
+    cudaEventElapsedTime(&t->total_ms, ev[0], ev[8]);
+    return BSMR_OK;
+}
+
+}  // extern "C"

@@ -169,6 +169,13 @@ struct bsmr_ctx {
     // tensor-map encoder resolved at runtime (no link-time dependency on libcuda)
     void* encode_tiled = nullptr;
     bsmr::Workspace ws;     // scratch of the reorder passes
+    // per-context (= per-device) one-time state: cudaFuncSetAttribute is a property of a function ON a device, and
+    // whether the host's copies in opposite directions may overlap belongs to the device's PCIe path
+    bool attr_dense = false, attr_wide = false;
+    int duplex = -1;        // -1 unknown, 0 half-duplex copy order, 1 two copy streams
+    // multi-GPU data plane (csrc/comm.cu): NCCL communicator of the ranks that share a sharded plan
+    void* nccl_comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
 };
 
 struct bsmr_plan {
@@ -252,6 +259,9 @@ struct bsmr_plan {
 
     // ---- identity ("no reorder") residual list, built lazily ----
     bsmr::DevBuf<uint32_t> csr_row_of_nnz;
+    // ---- the whole pattern as one row-sorted list in reordered-row order, built lazily (capi.cu: ensure_flat_list) ----
+    bsmr::DevBuf<uint32_t> flat_row, flat_col, flat_out;
+    bool have_flat = false;
 
     // ---- hub columns the residual kernel keeps in L2 when B does not fit (residual.cu: hot_columns) ----
     // Defaults from the sweep in profiles/r01h_l2_policy_sweep.md: the policy pays only when the gather is DRAM-bound
@@ -260,10 +270,14 @@ struct bsmr_plan {
     uint32_t l2_hot_min_b_mb = 2048;          // smaller B: plain kernel
     uint32_t l2_cold_first = 1;               // 1: the other columns carry evict_first instead of the default priority
     bsmr::DevBuf<uint32_t> col_degree, col_hot;
-    uint32_t hot_K = 0, hot_budget_mb = 0, hot_threshold = 0;
+    uint32_t hot_K = 0, hot_budget_mb = 0, hot_threshold = 0, hot_elem = 0;
     uint64_t hot_count = 0;
 
     // ---- shard (multi-GPU) ----
+    uint32_t shard_rank = 0, shard_world = 1;
+    std::vector<uint32_t> h_shard_bounds;                 // world + 1 panel boundaries (every rank knows every range)
+    double tile_work = 3000.0;                            // nnz-equivalents of one wide tile in the shard balance
+    bsmr::DevBuf<float> shard_p, shard_slice;             // comm.cu: the rank's P in CSR positions / its contiguous slice (root: all slices)
     uint32_t shard_first_panel = 0, shard_end_panel = 0;
     uint64_t shard_res_begin = 0, shard_res_end = 0;
     uint32_t shard_tile_begin = 0, shard_tile_end = 0;
@@ -299,21 +313,39 @@ struct bsmr_plan {
 namespace bsmr {
 
 // ---- kernels' host launchers (defined in the .cu files) ---------------------------------
+struct ResidualArgs {
+    uint32_t K = 0;
+    const float* A = nullptr;
+    const void* B = nullptr;        // fp32, or fp16 when b_half
+    bool b_half = false;
+    float* P = nullptr;
+    const uint32_t *row = nullptr, *col = nullptr, *out = nullptr;   // out == nullptr: P index = list position
+    uint64_t begin = 0, end = 0;
+    const uint32_t* col_hot = nullptr;
+    uint32_t cold_first = 0;
+    uint32_t batch = 1;             // batch elements (gridDim.y); strides in elements of A / B / P
+    size_t stride_a = 0, stride_b = 0, stride_p = 0;
+    cudaStream_t stream = nullptr;
+};
+int launch_residual(bsmr_ctx* ctx, const ResidualArgs& args);
+int launch_f32_to_f16(bsmr_ctx* ctx, const float* src, void* dst, size_t n, cudaStream_t stream);
 int launch_residual(bsmr_ctx* ctx, uint32_t K, const float* dA, const float* dB, float* dP,
                     const uint32_t* res_row, const uint32_t* res_col, const uint32_t* res_out,
                     uint64_t begin, uint64_t end, const uint32_t* col_hot = nullptr, uint32_t cold_first = 0);
-int hot_columns(bsmr_plan* plan, uint32_t K, const uint32_t** bitmap, uint32_t* cold_first);
+int hot_columns(bsmr_plan* plan, uint32_t K, const uint32_t** bitmap, uint32_t* cold_first, uint32_t b_elem_bytes = 4);
+int ensure_flat_list(bsmr_plan* plan);
 int launch_expand_rows(bsmr_ctx* ctx, uint32_t M, uint32_t nnz, const uint32_t* row_offsets, uint32_t* row_of_nnz);
 
 int col_reorder_and_format(bsmr_plan* plan, float delta);
 int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flags);
 // tile_list != nullptr: positions [tile_begin, tile_end) of that list of tile ids; else the tile ids themselves
 int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP,
-                 uint32_t tile_begin, uint32_t tile_end, const uint32_t* tile_list, cudaStream_t stream);
+                 uint32_t tile_begin, uint32_t tile_end, const uint32_t* tile_list, cudaStream_t stream, uint32_t batch = 1);
+bool dense_supports(uint32_t K, const float* dA, const float* dB);
 bool wide_supports(uint32_t K, const float* dA, const float* dB);
 int wide_partition(bsmr_plan* plan, uint32_t tile_begin, uint32_t tile_end);
 int launch_wide(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP,
-                uint32_t tile_begin, uint32_t tile_end, cudaStream_t stream);
+                uint32_t tile_begin, uint32_t tile_end, cudaStream_t stream, uint32_t batch = 1);
 int evaluate_reordering(bsmr_plan* plan, float delta, bsmr_reorder_stats* stats);
 
 }  // namespace bsmr

@@ -83,7 +83,14 @@ struct DenseParams {
     const uint32_t* tile_list;   // optional: [tile_begin, tile_end) index this list of tile ids (groups on the wide path removed)
     float* P;
     uint32_t* error_flag;
+    // batch (sddmm_gpu_batch, src/sddmmKernel.cu:2764-2848): work item w = batch element * #tiles + tile; the batch's A
+    // matrices are one [batch * M, K] tensor, its B matrices one [batch * N, K] tensor (the reference's strides M*K / N*K)
+    uint32_t batch;
+    uint32_t oob_row, oob_col;   // out-of-bounds coordinates of those tensors: batch * M, batch * N
+    size_t stride_p;             // nnz
+#ifdef BSMR_DEBUG
     uint32_t* debug_smem;    // optional: raw copy of stage 0 of the first tile (probe / tests)
+#endif
 };
 
 __global__ void __launch_bounds__(kDenseThreads, 2)
@@ -98,6 +105,8 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t num_chunks = (p.K + kChunk - 1) / kChunk;
+    const uint32_t ntiles = p.tile_end - p.tile_begin;
+    const uint32_t total = ntiles * p.batch;           // work items: (batch element, tile)
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -131,30 +140,39 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         // of a stage needed ~1.7 us per stage, four warps ~0.6 us.  (One lane issuing 8 requests from straight-line code
         // was slower still: measured.)
         uint32_t stage = 0, phase = 0;
-        auto fetch = [&](uint32_t ti, uint32_t& nc, int4& cols, int4& rows) {
+        auto fetch = [&](uint32_t w, uint32_t& nc, int4& cols, int4& rows) {
+            const uint32_t be = w / ntiles, ti = p.tile_begin + (w - be * ntiles);
             const uint32_t t = p.tile_list ? __ldg(p.tile_list + ti) : ti;
             const uint4 m = __ldg(p.tile_meta + t);
             nc = m.z;
-            cols = make_int4((int)p.N, (int)p.N, (int)p.N, (int)p.N);
+            const int oc = (int)p.oob_col, orow = (int)p.oob_row;
+            cols = make_int4(oc, oc, oc, oc);
             const uint32_t c0 = warp * kColsPerProducer + lane * 4;      // first dense column of this lane's request
-            if (lane < kReqPerProducer && c0 < nc) cols = __ldg(reinterpret_cast<const int4*>(p.dense_cols + m.y + c0));
-            rows = make_int4((int)p.M, (int)p.M, (int)p.M, (int)p.M);
+            if (lane < kReqPerProducer && c0 < nc) {
+                const int4 raw = __ldg(reinterpret_cast<const int4*>(p.dense_cols + m.y + c0));
+                const int cb = (int)(be * p.N);          // sentinel columns (index N, the reference's padding) stay out of bounds
+                cols.x = (uint32_t)raw.x < p.N ? raw.x + cb : oc;
+                cols.y = (uint32_t)raw.y < p.N ? raw.y + cb : oc;
+                cols.z = (uint32_t)raw.z < p.N ? raw.z + cb : oc;
+                cols.w = (uint32_t)raw.w < p.N ? raw.w + cb : oc;
+            }
+            rows = make_int4(orow, orow, orow, orow);
             if (warp == kProducerWarps - 1 && lane >= 4 && lane < 8) {
                 const uint32_t r0 = m.x * kPanel + (lane - 4) * 4;
                 int* rp = reinterpret_cast<int*>(&rows);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (r0 + j < p.num_rows) rp[j] = (int)__ldg(p.reordered_rows + r0 + j);
+                    if (r0 + j < p.num_rows) rp[j] = (int)(__ldg(p.reordered_rows + r0 + j) + be * p.M);
             }
         };
         uint32_t nc = 0, nc_next = 0;
         int4 cols, rows, cols_next, rows_next;
         cols = rows = cols_next = rows_next = make_int4(0, 0, 0, 0);
-        uint32_t t = p.tile_begin + blockIdx.x;
-        if (t < p.tile_end) fetch(t, nc, cols, rows);
-        for (; t < p.tile_end; t += gridDim.x) {
+        uint32_t t = blockIdx.x;
+        if (t < total) fetch(t, nc, cols, rows);
+        for (; t < total; t += gridDim.x) {
             // indices of the next tile are fetched while this one streams (dependent L2/DRAM loads off the critical path)
-            if (t + gridDim.x < p.tile_end) fetch(t + gridDim.x, nc_next, cols_next, rows_next);
+            if (t + gridDim.x < total) fetch(t + gridDim.x, nc_next, cols_next, rows_next);
             const bool has_cols = lane < kReqPerProducer && warp * kColsPerProducer + lane * 4 < nc;
             const bool has_rows = warp == kProducerWarps - 1 && lane >= 4 && lane < 8;
             const uint32_t tx_bytes = (nc / 4) * 512u + kATileBytes;
@@ -181,7 +199,7 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         // ================= MMA issuer =================
         const uint32_t idesc = make_idesc_tf32(kTileCols, kPanel);
         uint32_t stage = 0, phase = 0, it = 0;
-        for (uint32_t t = p.tile_begin + blockIdx.x; t < p.tile_end; t += gridDim.x, ++it) {
+        for (uint32_t t = blockIdx.x; t < total; t += gridDim.x, ++it) {
             const uint32_t acc = it % kAccs, acc_phase = (it / kAccs) & 1;
             mbar_wait(&tail->tmem_empty[acc], acc_phase ^ 1, p.error_flag, 2);
             tc_fence_after();
@@ -189,7 +207,8 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             for (uint32_t kc = 0; kc < num_chunks; ++kc) {
                 mbar_wait<false>(&tail->full[stage], phase, p.error_flag, 3);
                 tc_fence_after();
-                if (p.debug_smem && t == p.tile_begin && kc == 0 && blockIdx.x == 0) {
+#ifdef BSMR_DEBUG
+                if (p.debug_smem && t == 0 && kc == 0 && blockIdx.x == 0) {
                     // probe: raw image of stage 0 (B-column tile then A-row tile)
                     const uint32_t* src_b = reinterpret_cast<const uint32_t*>(b_tiles);
                     const uint32_t* src_a = reinterpret_cast<const uint32_t*>(a_tiles);
@@ -197,6 +216,7 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     for (uint32_t i = lane; i < kATileBytes / 4; i += 32) p.debug_smem[kBTileBytes / 4 + i] = src_a[i];
                     __syncwarp();
                 }
+#endif
                 if (lane == 0) {
                     const uint64_t da = make_smem_desc(smem_u32(b_tiles + (size_t)stage * kBTileBytes));
                     const uint64_t db = make_smem_desc(smem_u32(a_tiles + (size_t)stage * kATileBytes));
@@ -217,7 +237,9 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const uint32_t quarter = warp & 3;              // TMEM lanes [32*quarter, 32*quarter + 32)
         const uint32_t c = quarter * 32 + lane;         // dense column of the tile owned by this thread
         uint32_t it = 0;
-        for (uint32_t ti = p.tile_begin + blockIdx.x; ti < p.tile_end; ti += gridDim.x, ++it) {
+        for (uint32_t w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+            const uint32_t be = w / ntiles, ti = p.tile_begin + (w - be * ntiles);
+            float* const Pb = p.P + be * p.stride_p;
             const uint32_t t = p.tile_list ? __ldg(p.tile_list + ti) : ti;
             const uint32_t acc = it % kAccs, acc_phase = (it / kAccs) & 1;
             const uint32_t nc = __ldg(p.tile_meta + t).z;
@@ -247,7 +269,7 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             if (active) {
 #pragma unroll
                 for (int r = 0; r < (int)kPanel; ++r)
-                    if (idx[r] != kNull) p.P[idx[r]] = __uint_as_float(v[r]);
+                    if (idx[r] != kNull) Pb[idx[r]] = __uint_as_float(v[r]);
             }
         }
     }
@@ -262,26 +284,33 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
 }  // namespace
 
-// test hook: when set, the next dense launch copies the first tile's stage-0 smem image here
+#ifdef BSMR_DEBUG
+// probe hook (debug builds only): when set, the next dense launch copies the first tile's stage-0 smem image here
 static uint32_t* g_debug_smem = nullptr;
 extern "C" void bsmr_debug_set_dense_smem_dump(uint32_t* device_buffer) { g_debug_smem = device_buffer; }
+#endif
 
 int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP, uint32_t tile_begin, uint32_t tile_end,
-                 const uint32_t* tile_list, cudaStream_t stream) {
+                 const uint32_t* tile_list, cudaStream_t stream, uint32_t batch) {
     bsmr_ctx* ctx = plan->ctx;
-    if (tile_end <= tile_begin) return BSMR_OK;
-    if (K % 4 != 0 || (reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(dB)) % 16 != 0) {
+    if (tile_end <= tile_begin || batch == 0) return BSMR_OK;
+    if (!dense_supports(K, dA, dB)) {
         set_error("dense-block path needs K %% 4 == 0 and 16-byte aligned A/B (TMA row stride); K = %u", K);
         return BSMR_ERR_UNSUPPORTED;
     }
+    if ((uint64_t)plan->M * batch > 0x7FFFFFFFull || (uint64_t)plan->N * batch > 0x7FFFFFFFull ||
+        (uint64_t)(tile_end - tile_begin) * batch > 0xFFFFFFFFull) {
+        set_error("dense-block path: batch %u x (%u rows, %u columns) exceeds the 31-bit TMA coordinates", batch, plan->M, plan->N);
+        return BSMR_ERR_UNSUPPORTED;
+    }
     CUtensorMap map_a, map_b;
-    BSMR_TRY(make_row_gather_map(ctx, dA, plan->M, K, &map_a, true));   // TFLOAT32 maps: the TMA unit rounds to TF32
-    BSMR_TRY(make_row_gather_map(ctx, dB, plan->N, K, &map_b, true));
+    // TFLOAT32 maps: the TMA unit rounds to TF32.  The batch's matrices are contiguous (stride M*K / N*K): one tensor each.
+    BSMR_TRY(make_row_gather_map(ctx, dA, plan->M * batch, K, &map_a, true));
+    BSMR_TRY(make_row_gather_map(ctx, dB, plan->N * batch, K, &map_b, true));
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->attr_dense) {       // per context = per device: the attribute is a property of the function ON a device
         BSMR_CUDA_OK(cudaFuncSetAttribute(dense_sddmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseSmemBytes));
-        attr_set = true;
+        ctx->attr_dense = true;
     }
     uint32_t* error_flag = kernel_error_flag();
     if (!error_flag) {
@@ -302,15 +331,25 @@ int launch_dense(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, 
     p.tile_list = tile_list;
     p.P = dP;
     p.error_flag = error_flag;
+    p.batch = batch;
+    p.oob_row = plan->M * batch;
+    p.oob_col = plan->N * batch;
+    p.stride_p = plan->nnz;
+#ifdef BSMR_DEBUG
     p.debug_smem = g_debug_smem;
     g_debug_smem = nullptr;
-    const uint32_t tiles = tile_end - tile_begin;
+#endif
+    const uint64_t items = (uint64_t)(tile_end - tile_begin) * batch;
     const uint32_t max_ctas = static_cast<uint32_t>(ctx->sm_count) * 2;  // 2 CTAs (2 x 94 KB smem, 2 x 32 TMEM columns) per SM
-    const uint32_t grid = tiles < max_ctas ? tiles : max_ctas;
+    const uint32_t grid = items < max_ctas ? (uint32_t)items : max_ctas;
     dense_sddmm_kernel<<<grid, kDenseThreads, kDenseSmemBytes, stream>>>(map_a, map_b, p);
     ctx->launches++;
     BSMR_CUDA_OK(cudaGetLastError());
     return BSMR_OK;
+}
+
+bool dense_supports(uint32_t K, const float* dA, const float* dB) {
+    return K % 4 == 0 && (reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(dB)) % 16 == 0;
 }
 
 }  // namespace bsmr

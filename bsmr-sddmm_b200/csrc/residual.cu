@@ -24,6 +24,8 @@
 //
 // Roofline: HBM-bound on compulsory traffic; what it actually stresses is L2 -> SM gather
 // bandwidth (K*4 bytes of B per nnz), see DESIGN.md.
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 #include <vector>
 
@@ -76,13 +78,43 @@ __device__ __forceinline__ float4 ldg4_hint(const float* p, uint64_t policy) {
     return v;
 }
 
+// B may be stored as fp16 (bsmr_sddmm_f16b: 11 significant bits like the TF32 operands of the tensor-core kernels, fp32
+// products and accumulation): four k of a column are then one 8-byte load, and a K-vector is half the bytes at every
+// level of the gather (L1 wavefronts, L2 -> SM, DRAM).
+template <typename BT> __device__ __forceinline__ float4 ldb4(const BT* p);
+template <> __device__ __forceinline__ float4 ldb4<float>(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+template <> __device__ __forceinline__ float4 ldb4<__half>(const __half* p) {
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+template <typename BT> __device__ __forceinline__ float4 ldb4_hint(const BT* p, uint64_t policy);
+template <> __device__ __forceinline__ float4 ldb4_hint<float>(const float* p, uint64_t policy) { return ldg4_hint(p, policy); }
+template <> __device__ __forceinline__ float4 ldb4_hint<__half>(const __half* p, uint64_t policy) {
+    uint2 raw;
+    asm("ld.global.nc.L2::cache_hint.v2.b32 {%0, %1}, [%2], %3;" : "=r"(raw.x), "=r"(raw.y) : "l"(p), "l"(policy));
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+// Batch (sddmm_gpu_batch, src/sddmmKernel.cu:2764-2848: the reference folds the batch into gridDim.z of its kernels):
+// blockIdx.y = batch element; A, B, P advance by whole matrices, the index lists are shared.
+struct BatchStride {
+    size_t a, b, p;      // elements between consecutive batch elements of A, B, P (0 for a single SDDMM)
+};
+
 // LPN: lanes per nnz.  KV: number of float4 pieces per lane (K == LPN*4*KV); KV == 0 -> runtime loop.
-template <int LPN, int KV, int UNROLL>
+template <int LPN, int KV, int UNROLL, typename BT>
 __global__ void __launch_bounds__(kResThreads)
-residual_sddmm_kernel(const uint32_t K, const float* __restrict__ A, const float* __restrict__ B,
+residual_sddmm_kernel(const uint32_t K, const float* __restrict__ A, const BT* __restrict__ B,
                       float* __restrict__ P, const uint32_t* __restrict__ res_row,
                       const uint32_t* __restrict__ res_col, const uint32_t* __restrict__ res_out,
-                      const uint64_t begin, const uint64_t end) {
+                      const uint64_t begin, const uint64_t end, const BatchStride bs) {
+    A += blockIdx.y * bs.a;
+    B += blockIdx.y * bs.b;
+    P += blockIdx.y * bs.p;
     constexpr int G = 32 / LPN;     // entries processed concurrently by one warp
     constexpr int ITERS = 32 / G;   // passes to cover the warp's 32 entries
     const uint32_t lane = threadIdx.x & 31;
@@ -113,11 +145,11 @@ residual_sddmm_kernel(const uint32_t K, const float* __restrict__ A, const float
                     const uint32_t row = __shfl_sync(0xffffffffu, my_row, j);
                     const uint32_t col = __shfl_sync(0xffffffffu, my_col, j);
                     const float* ap = A + (size_t)row * K + sl * 4;
-                    const float* bp = B + (size_t)col * K + sl * 4;
+                    const BT* bp = B + (size_t)col * K + sl * 4;
 #pragma unroll
                     for (int v = 0; v < KV; ++v) {
                         av[u][v] = ldg4(ap + v * LPN * 4);
-                        bv[u][v] = ldg4(bp + v * LPN * 4);
+                        bv[u][v] = ldb4<BT>(bp + v * LPN * 4);
                     }
                 }
 #pragma unroll
@@ -133,9 +165,9 @@ residual_sddmm_kernel(const uint32_t K, const float* __restrict__ A, const float
                     const uint32_t row = __shfl_sync(0xffffffffu, my_row, j);
                     const uint32_t col = __shfl_sync(0xffffffffu, my_col, j);
                     const float* ap = A + (size_t)row * K;
-                    const float* bp = B + (size_t)col * K;
+                    const BT* bp = B + (size_t)col * K;
                     float s = 0.f;
-                    for (uint32_t k = sl * 4; k < K; k += LPN * 4) s = dot4(ldg4(ap + k), ldg4(bp + k), s);
+                    for (uint32_t k = sl * 4; k < K; k += LPN * 4) s = dot4(ldg4(ap + k), ldb4<BT>(bp + k), s);
                     acc[u] = s;
                 }
             }
@@ -155,13 +187,16 @@ residual_sddmm_kernel(const uint32_t K, const float* __restrict__ A, const float
 
 // Row-sorted fast path.  LPN lanes per entry, KV float4 pieces per lane: K == LPN * 4 * KV.
 // HINT: col_hot is the bitmap of the columns to keep in L2 (bit c of word c / 32), cold_first the policy of the others.
-template <int LPN, int KV, bool HINT = false>
+template <int LPN, int KV, bool HINT, typename BT>
 __global__ void __launch_bounds__(kResThreads, 3)
-residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const float* __restrict__ B,
+residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const BT* __restrict__ B,
                      float* __restrict__ P, const uint32_t* __restrict__ res_row,
                      const uint32_t* __restrict__ res_col, const uint32_t* __restrict__ res_out,
-                     const uint64_t begin, const uint64_t end,
-                     const uint32_t* __restrict__ col_hot = nullptr, const uint32_t cold_first = 0) {
+                     const uint64_t begin, const uint64_t end, const BatchStride bs,
+                     const uint32_t* __restrict__ col_hot, const uint32_t cold_first) {
+    A += blockIdx.y * bs.a;
+    B += blockIdx.y * bs.b;
+    P += blockIdx.y * bs.p;
     constexpr int G = 32 / LPN;      // entries in flight per warp instruction
     constexpr int UNROLL = KV >= 4 ? 2 : 4;
     const uint32_t lane = threadIdx.x & 31;
@@ -214,17 +249,17 @@ residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const float*
                 const int j = s_pass * G + sub;           // entry handled by this group in that pass
                 rows_u[u] = __shfl_sync(0xffffffffu, my_row, j);
                 const uint32_t col = __shfl_sync(0xffffffffu, my_col, j);
-                const float* bp = B + (size_t)col * K + sl * 4;
+                const BT* bp = B + (size_t)col * K + sl * 4;
                 if constexpr (HINT) {
                     // the policy operand travels in a uniform register: one priority per warp instruction (with LPN < 32
                     // the G entries of a pass share it: hot if any of them is)
                     const uint32_t hot_j = __shfl_sync(0xffffffffu, my_hot, j);
                     const uint64_t pol = (LPN == 32 ? hot_j != 0 : __any_sync(0xffffffffu, hot_j != 0)) ? pol_hot : pol_cold;
 #pragma unroll
-                    for (int v = 0; v < KV; ++v) bv[u][v] = ldg4_hint(bp + v * LPN * 4, pol);
+                    for (int v = 0; v < KV; ++v) bv[u][v] = ldb4_hint<BT>(bp + v * LPN * 4, pol);
                 } else {
 #pragma unroll
-                    for (int v = 0; v < KV; ++v) bv[u][v] = ldg4(bp + v * LPN * 4);
+                    for (int v = 0; v < KV; ++v) bv[u][v] = ldb4<BT>(bp + v * LPN * 4);
                 }
             }
             float d[UNROLL];
@@ -272,166 +307,24 @@ residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const float*
     }
 }
 
-// ---- residual_async_kernel: the same computation with the B columns staged through shared memory by cp.async ----
-// EXPERIMENT (opt-in, BSMR_RESIDUAL=async; measured slower than residual_rows_kernel, kept for the record).
-// residual_rows_kernel keeps every in-flight B piece in a register, so the bytes in flight per SM are bounded by the
-// register file (ncu on the nips-shaped matrix, K = 128: 24 warps x 4 x 512 B = 49 KB in flight, L2->L1 9.2 TB/s, LSU
-// 46 %, L2 39 % -- latency bound, nothing saturated).  Here each lane copies its own 16-byte pieces with
-// cp.async.cg (LDGSTS, L1 bypass) into a per-warp ring of 4 groups x 8 entries and reads them back with LDS.128 when
-// their group is complete: a lane only ever reads what it copied itself, so cp.async.wait_group is the only
-// synchronisation, and 3 groups (24 entries x K*4 bytes) per warp are always in flight -- ~170 KB per SM at K = 128.
-// Steady state per group: wait_group 3 -> 8 dot products from shared memory (A row in registers) -> re-issue the
-// group's slots with the next chunk's entries.
-template <int LPN, int KV, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
-residual_async_kernel(const uint32_t K, const float* __restrict__ A, const float* __restrict__ B,
-                      float* __restrict__ P, const uint32_t* __restrict__ res_row,
-                      const uint32_t* __restrict__ res_col, const uint32_t* __restrict__ res_out,
-                      const uint64_t begin, const uint64_t end) {
-    extern __shared__ __align__(16) uint8_t ring_smem[];
-    constexpr int G = 32 / LPN;                 // entries per warp instruction
-    constexpr int H = LPN / 2;
-    constexpr int kEntryBytes = LPN * KV * 16;  // K * 4
-    constexpr int kGroups = 4, kGroupEntries = 8;
-    constexpr int kPassesPerGroup = kGroupEntries / G;
-    static_assert(kPassesPerGroup % 2 == 0, "pairs of passes are folded together");
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t sub = lane / LPN;
-    const uint32_t sl = lane % LPN;
-    uint8_t* ring = ring_smem + (size_t)(threadIdx.x >> 5) * 32 * kEntryBytes;
-    const uint32_t ring_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(ring));
-    const uint64_t num_chunks = (end - begin + 31) / 32;
-    const uint64_t warp_stride = (uint64_t)gridDim.x * WARPS;
-    uint64_t chunk = (uint64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
-    if (chunk >= num_chunks) return;
-
-    uint32_t my_row, my_col, my_out, nx_row = 0, nx_col = 0, nx_out = 0;
-    bool my_valid, nx_valid = false;
-    auto load_meta = [&](uint64_t c, uint32_t& row, uint32_t& col, uint32_t& out, bool& valid) {
-        const uint64_t e = begin + c * 32 + lane;
-        valid = e < end;
-        const uint64_t es = valid ? e : begin;   // idle lanes recompute entry `begin`; never stored
-        row = __ldg(res_row + es);
-        col = __ldg(res_col + es);
-        out = res_out ? __ldg(res_out + es) : (uint32_t)es;
-    };
-    // copy the B pieces of group g (entries 8g .. 8g+7 of the chunk whose columns are in `col_reg`) into their slots
-    auto issue_group = [&](int g, uint32_t col_reg) {
-#pragma unroll
-        for (int it = 0; it < kPassesPerGroup; ++it) {
-            const int j = (g * kPassesPerGroup + it) * G + sub;
-            const uint32_t col = __shfl_sync(0xffffffffu, col_reg, j);
-            const float* src = B + (size_t)col * K + sl * 4;
-            const uint32_t dst = ring_u32 + j * kEntryBytes + sl * 16;
-#pragma unroll
-            for (int v = 0; v < KV; ++v)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + v * LPN * 16), "l"(src + v * LPN * 4) : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
-    load_meta(chunk, my_row, my_col, my_out, my_valid);
-#pragma unroll
-    for (int g = 0; g < kGroups; ++g) issue_group(g, my_col);
-
-    uint32_t cur_row = 0xFFFFFFFFu;
-    float4 a_cur[KV];
-#pragma unroll
-    for (int v = 0; v < KV; ++v) a_cur[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool upper0 = (sl & H) != 0;
-
-    for (;;) {
-        const uint64_t next = chunk + warp_stride;
-        const bool has_next = next < num_chunks;
-        if (has_next) load_meta(next, nx_row, nx_col, nx_out, nx_valid);   // in flight while this chunk is computed
-        float q[H];
-#pragma unroll
-        for (int g = 0; g < kGroups; ++g) {
-            asm volatile("cp.async.wait_group 3;" ::: "memory");           // the oldest outstanding group (this one) has landed
-#pragma unroll
-            for (int it = 0; it < kPassesPerGroup; it += 2) {
-                float d[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int pass = g * kPassesPerGroup + it + u;
-                    const int j = pass * G + sub;
-                    const uint32_t row = __shfl_sync(0xffffffffu, my_row, j);
-                    if (row != cur_row) {                    // uniform inside the group (warp-uniform for LPN == 32)
-                        const float* ap = A + (size_t)row * K + sl * 4;
-#pragma unroll
-                        for (int v = 0; v < KV; ++v) a_cur[v] = ldg4(ap + v * LPN * 4);
-                        cur_row = row;
-                    }
-                    const float4* bp = reinterpret_cast<const float4*>(ring + j * kEntryBytes + sl * 16);
-                    float acc = 0.f;
-#pragma unroll
-                    for (int v = 0; v < KV; ++v) acc = dot4(a_cur[v], bp[v * LPN], acc);
-                    d[u] = acc;
-                }
-                // slots i (pass 2i) and i + H (pass 2i + 1): first butterfly step folded in
-                const float send = upper0 ? d[0] : d[1];
-                const float keep = upper0 ? d[1] : d[0];
-                q[(g * kPassesPerGroup + it) / 2] = keep + __shfl_xor_sync(0xffffffffu, send, H);
-            }
-            // the group's slots are free again (their contents were consumed into d[]): refill with the next chunk
-            if (has_next) issue_group(g, nx_col);
-            else asm volatile("cp.async.commit_group;" ::: "memory");      // keeps the group count uniform
-        }
-#pragma unroll
-        for (int h = H / 2; h >= 1; h >>= 1) {
-            const bool upper = (sl & h) != 0;
-#pragma unroll
-            for (int i = 0; i < h; ++i) {
-                const float send = upper ? q[i] : q[i + h];
-                const float keep = upper ? q[i + h] : q[i];
-                q[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
-            }
-        }
-        const int mine = (int)((2 * (sl % H) + sl / H) * G + sub);
-        const uint32_t out = __shfl_sync(0xffffffffu, my_out, mine);
-        const bool ok = __shfl_sync(0xffffffffu, (int)my_valid, mine) != 0;
-        if (ok) P[out] = q[0];
-        if (!has_next) break;
-        chunk = next;
-        my_row = nx_row; my_col = nx_col; my_out = nx_out; my_valid = nx_valid;
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
-
-template <int LPN, int KV, int WARPS>
-int launch_async(bsmr_ctx* ctx, uint32_t K, const float* dA, const float* dB, float* dP, const uint32_t* rr, const uint32_t* rc,
-                 const uint32_t* ro, uint64_t begin, uint64_t end) {
-    constexpr size_t smem = (size_t)WARPS * 32 * LPN * KV * 16;
-    static bool configured = false;
-    static int per_sm = 1;
-    if (!configured) {
-        BSMR_CUDA_OK(cudaFuncSetAttribute(residual_async_kernel<LPN, KV, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        BSMR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, residual_async_kernel<LPN, KV, WARPS>, WARPS * 32, smem));
-        if (per_sm < 1) per_sm = 1;
-        configured = true;
-    }
-    const uint64_t chunks = (end - begin + 31) / 32;
-    const uint64_t need = (chunks + WARPS - 1) / WARPS;
-    const uint64_t cap = (uint64_t)ctx->sm_count * per_sm;      // persistent: exactly the resident CTAs
-    const int grid = (int)(need < cap ? need : cap);
-    residual_async_kernel<LPN, KV, WARPS><<<grid, WARPS * 32, smem, ctx->stream>>>(K, dA, dB, dP, rr, rc, ro, begin, end);
-    return BSMR_OK;
-}
-
 // Any K (no alignment assumption): one lane group of 32, scalar loads.
+template <typename BT>
 __global__ void __launch_bounds__(kResThreads)
-residual_sddmm_generic_kernel(const uint32_t K, const float* __restrict__ A, const float* __restrict__ B,
+residual_sddmm_generic_kernel(const uint32_t K, const float* __restrict__ A, const BT* __restrict__ B,
                               float* __restrict__ P, const uint32_t* __restrict__ res_row,
                               const uint32_t* __restrict__ res_col, const uint32_t* __restrict__ res_out,
-                              const uint64_t begin, const uint64_t end) {
+                              const uint64_t begin, const uint64_t end, const BatchStride bs) {
+    A += blockIdx.y * bs.a;
+    B += blockIdx.y * bs.b;
+    P += blockIdx.y * bs.p;
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp_global = (uint64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     const uint64_t warp_stride = (uint64_t)gridDim.x * kWarpsPerCta;
     for (uint64_t e = begin + warp_global; e < end; e += warp_stride) {
         const float* ap = A + (size_t)__ldg(res_row + e) * K;
-        const float* bp = B + (size_t)__ldg(res_col + e) * K;
+        const BT* bp = B + (size_t)__ldg(res_col + e) * K;
         float s = 0.f;
-        for (uint32_t k = lane; k < K; k += 32) s = fmaf(__ldg(ap + k), __ldg(bp + k), s);
+        for (uint32_t k = lane; k < K; k += 32) s = fmaf(__ldg(ap + k), static_cast<float>(__ldg(bp + k)), s);
 #pragma unroll
         for (int w = 16; w >= 1; w >>= 1) s += __shfl_xor_sync(0xffffffffu, s, w);
         if (lane == 0) P[res_out ? __ldg(res_out + e) : (uint32_t)e] = s;
@@ -486,73 +379,107 @@ __global__ void hot_bitmap_kernel(const uint32_t* __restrict__ deg, const uint32
     }
 }
 
-template <int LPN, int KV, int UNROLL>
-void launch_one(bsmr_ctx* ctx, int grid, uint32_t K, const float* dA, const float* dB, float* dP,
-                const uint32_t* rr, const uint32_t* rc, const uint32_t* ro, uint64_t begin, uint64_t end) {
-    residual_sddmm_kernel<LPN, KV, UNROLL><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, rr, rc, ro, begin, end);
-}
-
-}  // namespace
-
-int launch_residual(bsmr_ctx* ctx, uint32_t K, const float* dA, const float* dB, float* dP,
-                    const uint32_t* res_row, const uint32_t* res_col, const uint32_t* res_out,
-                    uint64_t begin, uint64_t end, const uint32_t* col_hot, uint32_t cold_first) {
-    if (end <= begin) return BSMR_OK;
-    if (K == 0) {
-        set_error("K must be positive");
-        return BSMR_ERR_INVALID_ARGUMENT;
-    }
+template <typename BT>
+int launch_residual_t(bsmr_ctx* ctx, const ResidualArgs& r) {
+    const uint32_t K = r.K;
+    const float* dA = r.A;
+    const BT* dB = static_cast<const BT*>(r.B);
+    const uint64_t begin = r.begin, end = r.end;
     const uint64_t chunks = (end - begin + 31) / 32;
     const uint64_t ctas_needed = (chunks + kWarpsPerCta - 1) / kWarpsPerCta;
     // 8 CTAs of 256 threads = 64 warps = a full SM; grid is a multiple of the SM count
     const uint64_t max_ctas = (uint64_t)ctx->sm_count * 8;
     const bool fast_k = K == 32 || K == 64 || K == 128 || K == 256 || K == 512;
-    // default: the register-staged kernel.  BSMR_RESIDUAL=async selects the cp.async-staged variant, which keeps 3.5x
-    // more bytes in flight per SM but measured SLOWER on B200 (graph17 K=128: 164 us vs 127 us; nips K=256: 79 vs 50 us):
-    // the gather is not limited by bytes in flight.
-    static const bool use_rows_kernel = [] { const char* e = std::getenv("BSMR_RESIDUAL"); return !(e && e[0] == 'a'); }();
     // residual_rows_kernel: 3 resident CTAs per SM (register budget), persistent grid-stride over the chunks
     const uint64_t cap = fast_k ? (uint64_t)ctx->sm_count * 3 : max_ctas;
-    const int grid = (int)(ctas_needed < cap ? ctas_needed : cap);
-    const bool aligned = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(dB)) % 16 == 0);
-
+    const uint32_t batch = r.batch ? r.batch : 1u;
+    const BatchStride bs{r.stride_a, r.stride_b, r.stride_p};
+    const dim3 grid((unsigned)(ctas_needed < cap ? ctas_needed : cap), batch);
+    // 128-bit loads of A, 128-bit (fp32) / 64-bit (fp16) loads of B: every batch element must keep that alignment
+    const size_t b_align = sizeof(BT) * 4;
+    const bool aligned = (K % 4 == 0) && (reinterpret_cast<uintptr_t>(dA) % 16 == 0) && (reinterpret_cast<uintptr_t>(dB) % b_align == 0) &&
+                         (batch == 1 || ((r.stride_a * sizeof(float)) % 16 == 0 && (r.stride_b * sizeof(BT)) % b_align == 0));
+    cudaStream_t st = r.stream;
+#define BSMR_ROWS(LPN, KV, HINT) \
+    residual_rows_kernel<LPN, KV, HINT, BT><<<grid, kResThreads, 0, st>>>(K, dA, dB, r.P, r.row, r.col, r.out, begin, end, bs, r.col_hot, r.cold_first)
     if (!aligned) {
-        const uint64_t warps = end - begin;
-        const uint64_t need = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
-        const int g = (int)(need < max_ctas ? need : max_ctas);
-        residual_sddmm_generic_kernel<<<g, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end);
-    } else if (fast_k && !use_rows_kernel) {
-        int st = BSMR_OK;
-        if (K == 32) st = launch_async<8, 1, 8>(ctx, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
-        else if (K == 64) st = launch_async<16, 1, 8>(ctx, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
-        else if (K == 128) st = launch_async<32, 1, 7>(ctx, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
-        else if (K == 256) st = launch_async<32, 2, 7>(ctx, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
-        else st = launch_async<32, 4, 3>(ctx, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
-        BSMR_TRY(st);
-    } else if (fast_k && col_hot) {
+        const uint64_t need = (end - begin + kWarpsPerCta - 1) / kWarpsPerCta;
+        const dim3 g((unsigned)(need < max_ctas ? need : max_ctas), batch);
+        residual_sddmm_generic_kernel<BT><<<g, kResThreads, 0, st>>>(K, dA, dB, r.P, r.row, r.col, r.out, begin, end, bs);
+    } else if (fast_k && r.col_hot) {
         // hub columns pinned in L2 (hot_columns below): same kernel, loads and stores carry L2 eviction priorities
-        if (K == 32) residual_rows_kernel<8, 1, true><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end, col_hot, cold_first);
-        else if (K == 64) residual_rows_kernel<16, 1, true><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end, col_hot, cold_first);
-        else if (K == 128) residual_rows_kernel<32, 1, true><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end, col_hot, cold_first);
-        else if (K == 256) residual_rows_kernel<32, 2, true><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end, col_hot, cold_first);
-        else residual_rows_kernel<32, 4, true><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end, col_hot, cold_first);
+        if (K == 32) BSMR_ROWS(8, 1, true);
+        else if (K == 64) BSMR_ROWS(16, 1, true);
+        else if (K == 128) BSMR_ROWS(32, 1, true);
+        else if (K == 256) BSMR_ROWS(32, 2, true);
+        else BSMR_ROWS(32, 4, true);
     } else if (K == 32) {
-        residual_rows_kernel<8, 1><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+        BSMR_ROWS(8, 1, false);
     } else if (K == 64) {
-        residual_rows_kernel<16, 1><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+        BSMR_ROWS(16, 1, false);
     } else if (K == 128) {
-        residual_rows_kernel<32, 1><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+        BSMR_ROWS(32, 1, false);
     } else if (K == 256) {
-        residual_rows_kernel<32, 2><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+        BSMR_ROWS(32, 2, false);
     } else if (K == 512) {
-        residual_rows_kernel<32, 4><<<grid, kResThreads, 0, ctx->stream>>>(K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+        BSMR_ROWS(32, 4, false);
     } else if (K < 64) {
-        launch_one<8, 0, 2>(ctx, grid, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+        residual_sddmm_kernel<8, 0, 2, BT><<<grid, kResThreads, 0, st>>>(K, dA, dB, r.P, r.row, r.col, r.out, begin, end, bs);
     } else if (K < 128) {
-        launch_one<16, 0, 2>(ctx, grid, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+        residual_sddmm_kernel<16, 0, 2, BT><<<grid, kResThreads, 0, st>>>(K, dA, dB, r.P, r.row, r.col, r.out, begin, end, bs);
     } else {
-        launch_one<32, 0, 2>(ctx, grid, K, dA, dB, dP, res_row, res_col, res_out, begin, end);
+        residual_sddmm_kernel<32, 0, 2, BT><<<grid, kResThreads, 0, st>>>(K, dA, dB, r.P, r.row, r.col, r.out, begin, end, bs);
     }
+#undef BSMR_ROWS
+    ctx->launches++;
+    BSMR_CUDA_OK(cudaGetLastError());
+    return BSMR_OK;
+}
+
+}  // namespace
+
+int launch_residual(bsmr_ctx* ctx, const ResidualArgs& r) {
+    if (r.end <= r.begin) return BSMR_OK;
+    if (r.K == 0) {
+        set_error("K must be positive");
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    return r.b_half ? launch_residual_t<__half>(ctx, r) : launch_residual_t<float>(ctx, r);
+}
+
+int launch_residual(bsmr_ctx* ctx, uint32_t K, const float* dA, const float* dB, float* dP,
+                    const uint32_t* res_row, const uint32_t* res_col, const uint32_t* res_out,
+                    uint64_t begin, uint64_t end, const uint32_t* col_hot, uint32_t cold_first) {
+    ResidualArgs r{};
+    r.K = K; r.A = dA; r.B = dB; r.P = dP; r.row = res_row; r.col = res_col; r.out = res_out;
+    r.begin = begin; r.end = end; r.col_hot = col_hot; r.cold_first = cold_first; r.stream = ctx->stream;
+    return launch_residual(ctx, r);
+}
+
+// fp32 -> fp16 conversion of an operand (round to nearest even), the converter behind bsmr_convert_f32_to_f16
+namespace {
+__global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+    const size_t n4 = n / 4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+        const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&lo);
+        o.y = *reinterpret_cast<const uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(dst)[i] = o;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < n % 4) dst[n4 * 4 + threadIdx.x] = __float2half_rn(src[n4 * 4 + threadIdx.x]);
+}
+}  // namespace
+int launch_f32_to_f16(bsmr_ctx* ctx, const float* src, void* dst, size_t n, cudaStream_t stream) {
+    if (n == 0) return BSMR_OK;
+    if ((reinterpret_cast<uintptr_t>(src) % 16) || (reinterpret_cast<uintptr_t>(dst) % 8)) {
+        set_error("fp32 -> fp16 conversion needs a 16-byte aligned source and an 8-byte aligned destination");
+        return BSMR_ERR_INVALID_ARGUMENT;
+    }
+    const size_t blocks = (n / 4 + 255) / 256;
+    const size_t cap = (size_t)ctx->sm_count * 16;
+    f32_to_f16_kernel<<<(unsigned)(blocks < cap ? (blocks ? blocks : 1) : cap), 256, 0, stream>>>(src, static_cast<__half*>(dst), n);
     ctx->launches++;
     BSMR_CUDA_OK(cudaGetLastError());
     return BSMR_OK;
@@ -562,13 +489,13 @@ int launch_residual(bsmr_ctx* ctx, uint32_t K, const float* dA, const float* dB,
 // plan->l2_hot_budget_mb, as a bitmap; *bitmap = nullptr when B fits the budget anyway (every small workload), when
 // the policy is switched off (budget 0) or when K has no fast path.  Built once per (plan, K, budget): a degree count
 // over the CSR column indices (once per plan), a capped degree histogram and a threshold chosen on the host.
-int hot_columns(bsmr_plan* p, uint32_t K, const uint32_t** bitmap, uint32_t* cold_first) {
+int hot_columns(bsmr_plan* p, uint32_t K, const uint32_t** bitmap, uint32_t* cold_first, uint32_t b_elem_bytes) {
     *bitmap = nullptr;
     *cold_first = p->l2_cold_first;
-    const uint64_t b_bytes = (uint64_t)p->N * K * sizeof(float);
+    const uint64_t b_bytes = (uint64_t)p->N * K * b_elem_bytes;
     const bool fast_k = K == 32 || K == 64 || K == 128 || K == 256 || K == 512;
     if (!fast_k || p->l2_hot_budget_mb == 0 || p->nnz == 0 || b_bytes <= ((uint64_t)p->l2_hot_min_b_mb << 20)) return BSMR_OK;
-    if (p->hot_K == K && p->hot_budget_mb == p->l2_hot_budget_mb && p->col_hot.ptr) {
+    if (p->hot_K == K && p->hot_elem == b_elem_bytes && p->hot_budget_mb == p->l2_hot_budget_mb && p->col_hot.ptr) {
         *bitmap = p->col_hot.ptr;
         return BSMR_OK;
     }
@@ -588,9 +515,9 @@ int hot_columns(bsmr_plan* p, uint32_t K, const uint32_t** bitmap, uint32_t* col
     std::vector<uint32_t> hist(kDegBins);
     BSMR_CUDA_OK(cudaMemcpyAsync(hist.data(), d_hist.ptr, d_hist.bytes(), cudaMemcpyDeviceToHost, ctx->stream));
     BSMR_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-    const uint64_t max_cols = ((uint64_t)p->l2_hot_budget_mb << 20) / ((uint64_t)K * sizeof(float));
+    const uint64_t max_cols = ((uint64_t)p->l2_hot_budget_mb << 20) / ((uint64_t)K * b_elem_bytes);
     uint64_t count = 0;
-    uint32_t threshold = kDegBins;           // nothing hot unless a class fits
+    uint32_t threshold = 0xFFFFFFFFu;        // nothing hot unless a degree class fits the budget
     for (int d = kDegBins - 1; d >= 2; --d) {
         if (count + hist[d] > max_cols) break;
         count += hist[d];
@@ -601,6 +528,7 @@ int hot_columns(bsmr_plan* p, uint32_t K, const uint32_t** bitmap, uint32_t* col
     ctx->launches++;
     BSMR_CUDA_OK(cudaGetLastError());
     p->hot_K = K;
+    p->hot_elem = b_elem_bytes;
     p->hot_budget_mb = p->l2_hot_budget_mb;
     p->hot_threshold = threshold;
     p->hot_count = count;

@@ -94,7 +94,11 @@ struct WideParams {
     uint32_t K, kchunks, stages;
     uint32_t sgp;                    // sub-groups per pass: 2 (A images of the whole group resident, K <= 128) or 1 (K = 256)
     uint32_t num_rows;               // reordered (non-empty) rows
-    uint32_t M, N;                   // out-of-bounds coordinates for missing rows / columns (TMA zero fill)
+    uint32_t M, N;                   // rows of one A / columns of one B (row / column offset of a batch element)
+    uint32_t oob_row, oob_col;       // out-of-bounds coordinates for missing rows / columns (TMA zero fill): batch * M, batch * N
+    uint32_t batch;                  // batch elements: the CTA walks its tile range once per (element, pass); the batch's A / B
+                                     // matrices are one [batch * M, K] / [batch * N, K] tensor (sddmm_gpu_batch's strides)
+    size_t stride_p;                 // nnz: P of batch element b starts at P + b * stride_p
     const uint4* cta_rec;            // per CTA: {first tile, end tile, group of the first tile, its first column id}, {its tile_meta}
     const uint4* tile_meta;          // {group, first column (offset into cols, multiple of 4), #columns, 0}
     const uint32_t* cols;            // distinct columns of the wide groups, ascending inside a group
@@ -105,8 +109,9 @@ struct WideParams {
     const uint32_t* reordered_rows;
     float* P;
     uint32_t* error_flag;
-    uint32_t debug;                  // timing experiments only (BSMR_WIDE_DEBUG): 4 = epilogue skips every chunk (wrong results)
-    unsigned long long* trace;       // optional (tests/perf probes): 32 time stamps per CTA
+#ifdef BSMR_DEBUG
+    unsigned long long* trace;       // probe builds only (tests/wide_trace.py): 32 time stamps per CTA
+#endif
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -114,10 +119,14 @@ __device__ __forceinline__ unsigned long long gtime() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+#ifdef BSMR_DEBUG
 #define WTRACE(slot)                                                                          \
     do {                                                                                      \
         if (p.trace && lane == 0) p.trace[(size_t)blockIdx.x * 32 + (slot)] = gtime();        \
     } while (0)
+#else
+#define WTRACE(slot) do { } while (0)
+#endif
 
 template <bool kMaskEpilogue>
 __global__ void __launch_bounds__(kWThreads, 1)
@@ -137,6 +146,7 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t passes = kWSub / SGP;                  // K = 256: the tile range is walked once per sub-group
+    const uint32_t rounds = p.batch * passes;             // ... and once per batch element: round r = (element r / passes, pass r % passes)
     const uint32_t naccs = kWTmemCols / (kWCols * SGP);   // accumulator sets in rotation (one set = SGP x 128 columns)
     // tile range of this CTA (host-side partition: CTAs do not straddle row groups when there are enough of them)
     const uint4 rec0 = __ldg(p.cta_rec + 2 * blockIdx.x), rec1 = __ldg(p.cta_rec + 2 * blockIdx.x + 1);
@@ -184,32 +194,38 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // 32-column quarter, or per tile, instead of 8 / 32 gather4 requests: every request passes through the MIO queue
         // of its warp's scheduler, and with 32 of them per stage the epilogue warps' LDS / STS waited ~700-1000 cycles
         // behind them (measured with clock64 stamps).
+        uint32_t col_off = 0, row_off = 0;           // column / row offset of the current batch element in the stacked tensors
         auto fetch_cols = [&](uint32_t t, uint32_t& ncols, uint32_t& flags, int4& cols) {
             const uint4 m = t == my_begin ? rec1 : __ldg(p.tile_meta + t);      // the first tile's meta came with the start record
             ncols = m.z;
-            flags = (p.debug & 256u) ? 0u : m.w;
-            cols = make_int4((int)p.N, (int)p.N, (int)p.N, (int)p.N);
+            flags = m.w;
+            const int oc = (int)p.oob_col;
+            cols = make_int4(oc, oc, oc, oc);
             const uint32_t c0 = rq * 4;
             if (issuer && c0 < m.z) {
                 cols = __ldg(reinterpret_cast<const int4*>(p.cols + m.y + c0));
-                if (c0 + 1 >= m.z) cols.y = (int)p.N;
-                if (c0 + 2 >= m.z) cols.z = (int)p.N;
-                if (c0 + 3 >= m.z) cols.w = (int)p.N;
+                cols.x += (int)col_off;
+                cols.y = c0 + 1 >= m.z ? oc : cols.y + (int)col_off;
+                cols.z = c0 + 2 >= m.z ? oc : cols.z + (int)col_off;
+                cols.w = c0 + 3 >= m.z ? oc : cols.w + (int)col_off;
             }
         };
         const uint32_t myq = warp >> 1;              // 32-column quarter of the tile this warp's requests belong to
         uint32_t stage = 0, phase = 0, a_loads = 0, cur_key = kNoCol;
-        for (uint32_t pass = 0; pass < passes; ++pass) {
+        for (uint32_t round = 0; round < rounds; ++round) {
+            const uint32_t be = round / passes, pass = round - be * passes;
+            col_off = be * p.N;
+            row_off = be * p.M;
             uint32_t ncols = 0, ncols_next = 0, flags = 0, flags_next = 0;
             int4 cols = make_int4(0, 0, 0, 0), cols_next = make_int4(0, 0, 0, 0);
             if (my_begin < my_end) fetch_cols(my_begin, ncols, flags, cols);
             for (uint32_t t = my_begin; t < my_end; ++t) {
                 if (t + 1 < my_end) fetch_cols(t + 1, ncols_next, flags_next, cols_next);   // indices of the next tile: off the critical path
                 const uint32_t g = t == my_begin ? rec0.z : __ldg(p.tile_meta + t).x;
-                const uint32_t key = g * 2 + pass;
+                const uint32_t key = g * rounds + round;          // one A image per (row group, batch element, pass)
                 const bool new_key = key != cur_key;
                 int4 arows[2];
-                arows[0] = arows[1] = make_int4((int)p.M, (int)p.M, (int)p.M, (int)p.M);
+                arows[0] = arows[1] = make_int4((int)p.oob_row, (int)p.oob_row, (int)p.oob_row, (int)p.oob_row);
                 if (new_key) {
                     // (re)load the A images, [sub-group of the pass][K-chunk] x 32 requests, interleaved with the B stages of
                     // this tile: chunk kc of A, then stage kc of B, so that the first MMAs start after one chunk has landed
@@ -221,7 +237,7 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             int* rp = reinterpret_cast<int*>(&arows[sg]);
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
-                                if (r0 + j < p.num_rows) rp[j] = (int)__ldg(p.reordered_rows + r0 + j);
+                                if (r0 + j < p.num_rows) rp[j] = (int)(__ldg(p.reordered_rows + r0 + j) + row_off);
                         }
                     }
                     cur_key = key;
@@ -263,7 +279,7 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     uint8_t* bst = b_ring + (size_t)stage * kWBStageBytes;
                     if (do_whole) {
                         // the first tile's first column id came with the start record: no wait for the column list
-                        if (t == my_begin) tma_load_2d(&map_b128, &tail->b_full[stage], bst, (int)(kc * kWChunk), (int)rec0.w);
+                        if (t == my_begin) tma_load_2d(&map_b128, &tail->b_full[stage], bst, (int)(kc * kWChunk), (int)(rec0.w + col_off));
                         else tma_load_2d(&map_b128, &tail->b_full[stage], bst, (int)(kc * kWChunk), cols.x);
                     }
                     if (do_qrun) tma_load_2d(&map_b32, &tail->b_full[stage], bst + myq * 4096, (int)(kc * kWChunk), cols.x);
@@ -278,11 +294,11 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     } else if (warp == kWMmaWarp) {
         // ================= MMA issuer =================
         uint32_t stage = 0, phase = 0, it = 0, a_idx = 0, cur_key = kNoCol;
-        for (uint32_t pass = 0; pass < passes; ++pass) {
+        for (uint32_t round = 0; round < rounds; ++round) {
             for (uint32_t t = my_begin; t < my_end; ++t, ++it) {
                 const uint4 m = __ldg(p.tile_meta + t);
                 const uint32_t acc = it % naccs, acc_phase = (it / naccs) & 1;
-                const uint32_t key = m.x * 2 + pass;
+                const uint32_t key = m.x * rounds + round;
                 const bool new_key = key != cur_key;
                 cur_key = key;
                 const bool last_of_key = (t + 1 == my_end) || (__ldg(p.tile_meta + t + 1).x != m.x);
@@ -300,11 +316,9 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     if (lane == 0) {
                         const uint64_t da = make_smem_desc(smem_u32(b_ring + (size_t)stage * kWBStageBytes));
                         const uint64_t db = make_smem_desc(smem_u32(a_img + (size_t)kc * SGP * kWAImgBytes));
-                        if (!(p.debug & 16u)) {
 #pragma unroll
-                            for (uint32_t k = 0; k < kWChunk / 8; ++k)
-                                umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
-                        }
+                        for (uint32_t k = 0; k < kWChunk / 8; ++k)
+                            umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
                         umma_commit(&tail->b_empty[stage]);
                         if (it == 0 && kc == 0) WTRACE(8);             // first MMAs issued
                         if (kc + 1 == KC) {
@@ -341,10 +355,11 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             uint64_t* lfull = tail->l_full[ew];
             const uint2* units = p.entries + (size_t)(quarter * 2 + half) * p.num_tiles * kWUnitRows;   // [tile][128]
             const uint32_t lane_bit = 1u << lane, lanes_below = lane_bit - 1u;
-            float* const Pout = p.P;
             uint32_t gp = 0;                            // units requested so far (ring position)
             uint32_t it = 0;
-            for (uint32_t pass = 0; pass < passes; ++pass) {
+            for (uint32_t round = 0; round < rounds; ++round) {
+                const uint32_t be = round / passes, pass = round - be * passes;
+                float* const Pout = p.P + be * p.stride_p;
                 // K = 256: one row half is resident per pass and only the warps of that half have work.  The others still take
                 // part in the accumulator hand-shake tile by tile: a warp that skipped ahead would test the parity of a phase
                 // the barrier has not reached yet (a parity wait can only tell the current phase from the previous one).
@@ -382,7 +397,7 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     if (ew == 0 && it < 2) WTRACE(10 + 2 * it);   // accumulators of tile 0 / 1 complete
                     // four sub-blocks of 32 rows; not unrolled (the body is ~250 instructions)
     #pragma unroll 1
-                    for (uint32_t c = 0; c < 4 && !(p.debug & 4u); ++c) {
+                    for (uint32_t c = 0; c < 4; ++c) {
                         const uint2* rows = reinterpret_cast<const uint2*>(page) + c * 32;
                         uint32_t v[32];
                         const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * (SGP * kWSubRows) + col0 + c * 32u;
@@ -438,7 +453,9 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint32_t* ustart = p.sb_off + (size_t)(quarter * 2 + half) * p.num_tiles;
             uint32_t gp_base = 0;                       // pages issued in earlier passes (ring position of local page 0)
             uint32_t it = 0;
-            for (uint32_t pass = 0; pass < passes; ++pass) {
+            for (uint32_t round = 0; round < rounds; ++round) {
+                const uint32_t be = round / passes, pass = round - be * passes;
+                float* const Pout = p.P + be * p.stride_p;
                 // K = 256: one row half is resident per pass and only the warps of that half have work.  The others still take
                 // part in the accumulator hand-shake tile by tile: a warp that skipped ahead would test the parity of a phase
                 // the barrier has not reached yet (a parity wait can only tell the current phase from the previous one).
@@ -514,7 +531,7 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     for (uint32_t c = 0; c < (uint32_t)kWUSB; ++c) {
                         const uint32_t e0 = e1;
                         e1 = ebase + __shfl_sync(0xffffffffu, hw, c);
-                        if (e0 == e1 || (p.debug & 4u)) continue;
+                        if (e0 == e1) continue;
                         // the first (up to) 64 entries of the sub-block are requested BEFORE the accumulator is staged: every step
                         // of this chain (LDTM, STS, LDS.64, LDS, STG) has ~100 cycles of latency under load, and the entry fetch
                         // does not depend on the staging image
@@ -556,7 +573,7 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                                 val[q] = *reinterpret_cast<const float*>(stg_bytes + en0[q].x);
     #pragma unroll
                             for (int q = 0; q < 4; ++q)
-                                if (e0 + q * 32 + lane < seg0) p.P[en0[q].y] = val[q];
+                                if (e0 + q * 32 + lane < seg0) Pout[en0[q].y] = val[q];
                         }
                         // the rest of a long list (more than 128 entries, or a page boundary inside the first 128)
                         for (uint32_t e = seg0; e < e1;) {
@@ -578,7 +595,7 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                                     val[q] = *reinterpret_cast<const float*>(stg_bytes + en[q].x);
     #pragma unroll
                                 for (int q = 0; q < 2; ++q)
-                                    if (eb + q * 32 + lane < seg_end) p.P[en[q].y] = val[q];
+                                    if (eb + q * 32 + lane < seg_end) Pout[en[q].y] = val[q];
                             }
                             e = seg_end;
                         }
@@ -675,8 +692,10 @@ int wide_partition(bsmr_plan* plan, uint32_t tile_begin, uint32_t tile_end) {
     return BSMR_OK;
 }
 
+#ifdef BSMR_DEBUG
 static unsigned long long* g_wide_trace = nullptr;
 extern "C" void bsmr_debug_set_wide_trace(unsigned long long* device_buffer) { g_wide_trace = device_buffer; }
+#endif
 
 bool wide_supports(uint32_t K, const float* dA, const float* dB) {
     return K >= 32 && K % kWChunk == 0 && K / kWChunk <= kWMaxKChunks &&
@@ -684,9 +703,13 @@ bool wide_supports(uint32_t K, const float* dA, const float* dB) {
 }
 
 int launch_wide(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP, uint32_t tile_begin, uint32_t tile_end,
-                cudaStream_t stream) {
+                cudaStream_t stream, uint32_t batch) {
     bsmr_ctx* ctx = plan->ctx;
-    if (tile_end <= tile_begin) return BSMR_OK;
+    if (tile_end <= tile_begin || batch == 0) return BSMR_OK;
+    if ((uint64_t)plan->M * batch > 0x7FFFFFFFull || (uint64_t)plan->N * batch > 0x7FFFFFFFull) {
+        set_error("wide row-group path: batch %u x (%u rows, %u columns) exceeds the 31-bit TMA coordinates", batch, plan->M, plan->N);
+        return BSMR_ERR_UNSUPPORTED;
+    }
     if (!wide_supports(K, dA, dB)) {
         set_error("wide row-group path needs K %% 32 == 0, K <= 256 and 16-byte aligned A/B; K = %u", K);
         return BSMR_ERR_UNSUPPORTED;
@@ -699,32 +722,32 @@ int launch_wide(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, f
     const size_t fixed = 1024 + sizeof(WideSmemTail) + (size_t)kWEpiWarps * (plan->wide_mask_epilogue ? (size_t)kWMetaBytes : (size_t)(kWEpiStageBytes + kWListBytes)) +
                          (size_t)sgp * kchunks * kWAImgBytes;
     uint32_t stages = static_cast<uint32_t>((max_smem - fixed) / kWBStageBytes);
-    static const uint32_t stage_cap = [] { const char* e = std::getenv("BSMR_WIDE_STAGES"); return e ? (uint32_t)std::atoi(e) : 0u; }();
-    if (stage_cap && stages > stage_cap) stages = stage_cap;
     if (stages > (uint32_t)kWMaxStages) stages = kWMaxStages;
     const size_t smem = fixed + (size_t)stages * kWBStageBytes;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->attr_wide) {        // per context = per device: the attribute is a property of the function ON a device
         BSMR_CUDA_OK(cudaFuncSetAttribute(wide_sddmm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
         BSMR_CUDA_OK(cudaFuncSetAttribute(wide_sddmm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-        attr_set = true;
+        ctx->attr_wide = true;
     }
     uint32_t* error_flag = kernel_error_flag();
     if (!error_flag) {
         set_error("no mapped host memory for the kernels' error flag");
         return BSMR_ERR_CUDA;
     }
+    // TFLOAT32 maps (the TMA unit rounds to nearest); the batch's matrices are contiguous (stride M*K / N*K): one tensor each
     CUtensorMap map_a, map_b;
-    static const bool fp32_maps = std::getenv("BSMR_WIDE_FP32_MAPS") != nullptr;   // experiment: truncating operands
-    BSMR_TRY(make_row_gather_map(ctx, dA, plan->M, K, &map_a, !fp32_maps));
-    BSMR_TRY(make_row_gather_map(ctx, dB, plan->N, K, &map_b, !fp32_maps));
+    BSMR_TRY(make_row_gather_map(ctx, dA, (uint64_t)plan->M * batch, K, &map_a, true));
+    BSMR_TRY(make_row_gather_map(ctx, dB, (uint64_t)plan->N * batch, K, &map_b, true));
     CUtensorMap map_b32, map_b128;    // tiled loads of 32 / 128 consecutive columns of B
-    BSMR_TRY(make_row_gather_map(ctx, dB, plan->N, K, &map_b32, !fp32_maps, 32));
-    BSMR_TRY(make_row_gather_map(ctx, dB, plan->N, K, &map_b128, !fp32_maps, 128));
+    BSMR_TRY(make_row_gather_map(ctx, dB, (uint64_t)plan->N * batch, K, &map_b32, true, 32));
+    BSMR_TRY(make_row_gather_map(ctx, dB, (uint64_t)plan->N * batch, K, &map_b128, true, 128));
     WideParams p{};
     p.K = K; p.kchunks = kchunks; p.stages = stages; p.sgp = sgp;
     p.num_rows = static_cast<uint32_t>(plan->h_reordered_rows.size());
     p.M = plan->M; p.N = plan->N;
+    p.oob_row = plan->M * batch; p.oob_col = plan->N * batch;
+    p.batch = batch;
+    p.stride_p = plan->nnz;
     p.cta_rec = plan->w_cta_rec.ptr;
     p.tile_meta = plan->wt_meta.ptr;
     p.cols = plan->w_cols.ptr;
@@ -734,10 +757,10 @@ int launch_wide(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, f
     p.reordered_rows = plan->reordered_rows.ptr;
     p.P = dP;
     p.error_flag = error_flag;
-    static const uint32_t dbg = [] { const char* e = std::getenv("BSMR_WIDE_DEBUG"); return e ? (uint32_t)std::atoi(e) : 0u; }();
-    p.debug = dbg;
+#ifdef BSMR_DEBUG
     p.trace = g_wide_trace;
     g_wide_trace = nullptr;
+#endif
     if (plan->w_part_begin != tile_begin || plan->w_part_end != tile_end || plan->w_grid == 0) {
         set_error("launch_wide: no CTA partition for tiles [%u, %u)", tile_begin, tile_end);
         return BSMR_ERR_BAD_STATE;

@@ -16,11 +16,14 @@
 
 namespace bsmr_host {
 
-// One context per process and device, created on first use (the reference implicitly uses device 0).
+// One context per process, created on first use on device 0 and on the LEGACY DEFAULT STREAM (cudaStreamLegacy = 0x1),
+// which is what the reference implicitly uses everywhere (include/Logger.hpp:23-25; kernels launched without a stream
+// argument): device pointers a caller prepared on the default stream are ordered before our kernels and our results
+// before whatever the caller launches next, exactly as with the reference's code.
 inline bsmr_ctx* context(int device = 0) {
     static bsmr_ctx* ctx = nullptr;
     if (!ctx) {
-        if (bsmr_ctx_create(device, nullptr, &ctx) != BSMR_OK) {
+        if (bsmr_ctx_create(device, reinterpret_cast<void*>(0x1), &ctx) != BSMR_OK) {
             fprintf(stderr, "bsmr_b200: %s\n", bsmr_last_error());
             return nullptr;
         }

@@ -10,7 +10,7 @@
 #include "Options.hpp"
 #include "checkData.hpp"
 #include "host.hpp"
-#include "sddmmKernel.hpp"
+#include "sddmmKernel.cuh"
 
 namespace bsmr_host {
 

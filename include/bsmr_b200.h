@@ -15,7 +15,9 @@
  *     gives the text for the most recent failure on the calling thread
  *   - indices are uint32_t ("UIN", include/TensorCoreConfig.cuh:10), values are fp32
  *   - A is M x K row-major (ld = K), B is K x N column-major (ld = K)  (src/main.cu:25-29)
- *   - one context = one device + one stream; one caller thread per context
+ *   - one context = one device + one stream; one caller thread per context.  A process may hold contexts on several
+ *     devices: everything that is a property of a device (kernel attributes, the copy-order probe, the NCCL
+ *     communicator) lives in the context
  *   - there is NO CPU fallback: without a usable sm_100 device every compute call fails
  *     with BSMR_ERR_NO_DEVICE
  */
@@ -74,6 +76,9 @@ int bsmr_calculate_block_size(bsmr_ctx* ctx, uint32_t M, uint32_t N, uint64_t fr
  * The CSR pattern is copied to the device (values of S are never used: the reference does
  * not multiply by them, src/host.cpp:62-73).  `on_device` != 0 -> the two arrays are device
  * pointers on ctx's device.                                                              */
+/* The pattern is validated on the device like the reference's loaders validate a file (src/Matrix.cpp:442-465):
+ * row_offsets non-decreasing from 0 to nnz, every column < N, no (row, column) coordinate twice; anything else ->
+ * BSMR_ERR_INVALID_ARGUMENT (columns inside a row need not be sorted: the .mtx loader keeps file order).            */
 int bsmr_plan_create(bsmr_ctx* ctx, uint32_t M, uint32_t N, uint32_t nnz,
                      const uint32_t* row_offsets, const uint32_t* col_indices, int on_device,
                      bsmr_plan** out);
@@ -93,7 +98,7 @@ int bsmr_plan_destroy(bsmr_plan* plan);
 int bsmr_plan_row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flags);
 
 /* BSMR::colReordering(delta, matrix, reorderedRows) with a caller-supplied row order
- * (src/BSMR.cpp:52-59; host pointer).                                                    */
+ * (src/BSMR.cpp:52-59; host pointer).  Row ids out of range or listed twice are rejected.  */
 int bsmr_plan_set_row_order(bsmr_plan* plan, const uint32_t* reordered_rows, uint32_t count);
 
 /* BSMR::colReordering -> colReordering_cpu semantics, computed on the GPU
@@ -173,6 +178,60 @@ int bsmr_plan_load_row_order(bsmr_plan* plan, const char* path, float alpha, uin
  * first_panel / last_panel (exclusive) / shard_nnz are outputs (may be NULL).            */
 int bsmr_plan_set_shard(bsmr_plan* plan, uint32_t rank, uint32_t world,
                         uint32_t* first_panel, uint32_t* end_panel, uint64_t* shard_nnz);
+/* The tile weight of that balance (nnz-equivalents of one wide tile; default 3000, fitted by hand on stacked nips
+ * blocks).  _fit measures it for this plan and K on the unsharded plan from the kernels' own times (wide kernel per
+ * tile against dense-block + residual kernels per nnz; synchronises, writes P); every rank of a multi-rank run must
+ * install the SAME value with _set before bsmr_plan_set_shard, or the ranks' ranges would not partition the panels. */
+int bsmr_plan_fit_tile_work(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP,
+                            float* nnz_equivalents_per_tile);
+int bsmr_plan_set_tile_work(bsmr_plan* plan, float nnz_equivalents_per_tile);
+
+/* ---- multi-GPU data plane: NCCL over NVLink / NVSwitch, one process per GPU (no counterpart in the reference) ----
+ * The communicator belongs to the context; collectives are queued on the context's stream.  NCCL is resolved at run
+ * time (dlopen of libnccl.so.2), single-GPU users never load it.
+ *   rank 0:      bsmr_comm_unique_id(id)  -> ship the 128 bytes to the other ranks (a file, MPI, torch.distributed ...)
+ *   every rank:  bsmr_ctx_comm_init(ctx, id, rank, world)
+ *   reorder:     bsmr_plan_row_reorder on the root only (clustering is global and the cost centre), then
+ *                bsmr_plan_bcast_row_order(plan, root) on every rank, then bsmr_plan_col_reorder(delta) on every rank
+ *                (integer-only and deterministic: recomputing it concurrently is cheaper than shipping the format)
+ *   shard:       bsmr_plan_set_shard(plan, rank, world, ...)
+ *   SDDMM:       bsmr_sddmm_sharded (A, B resident on every rank) or bsmr_sddmm_sharded_host (host buffers)          */
+#define BSMR_NCCL_UNIQUE_ID_BYTES 128
+int bsmr_comm_unique_id(void* id_out);
+int bsmr_ctx_comm_init(bsmr_ctx* ctx, const void* unique_id, int rank, int world);
+int bsmr_ctx_comm_destroy(bsmr_ctx* ctx);
+int bsmr_ctx_comm_bcast(bsmr_ctx* ctx, void* device_ptr, uint64_t bytes, int root);   /* ncclBroadcast, in place */
+int bsmr_plan_bcast_row_order(bsmr_plan* plan, int root);
+
+typedef struct {
+    float h2d_a_ms;        /* host path: upload of the shard's A rows                                   */
+    float h2d_b_ms;        /* host path: upload of this rank's 1/world of B                             */
+    float allgather_b_ms;  /* host path: ncclAllGather that replicates B                                */
+    float kernel_ms;       /* SDDMM kernels of the shard                                                */
+    float pack_ms;         /* the shard's entries made contiguous (reordered-row order)                 */
+    float gather_p_ms;     /* grouped ncclSend / ncclRecv of the slices to the root                     */
+    float unpermute_ms;    /* root: back to CSR order                                                   */
+    float d2h_ms;          /* host path, root: P to the host                                            */
+    float total_ms;
+    uint64_t shard_nnz;
+    uint64_t h2d_bytes, d2h_bytes;       /* this rank */
+    uint64_t allgather_b_bytes;          /* received by this rank */
+    uint64_t gather_p_bytes;             /* sent (non-root) or received (root) by this rank */
+} bsmr_shard_times;
+
+/* One SDDMM over a sharded plan with the result assembled on `root`: every rank runs the kernels of its range of
+ * reordered row panels (dA: at least the rows of the shard valid; dB: complete), packs its entries into one contiguous
+ * slice, the slices go to the root (a gather-v: 4 * nnz bytes over NVLink in total) and the root un-permutes them into
+ * dP_root (CSR order, length nnz; ignored on the other ranks, may be NULL there).  Asynchronous on the context's stream
+ * when times == NULL.                                                                                              */
+int bsmr_sddmm_sharded(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP_root, uint32_t flags, int root,
+                       bsmr_shard_times* times);
+/* The same from host buffers (the sharded form of the host-data sddmm_gpu overload, src/sddmmKernel.cu:2518-2538):
+ * hA, hB valid on every rank, hP on the root.  Every rank uploads only the A rows of its shard (straight out of the
+ * host buffer when that is pinned + mapped memory and K % 4 == 0, else all of A) and 1/world of B, which an in-place
+ * ncclAllGather replicates; then as above, and the root copies P out.  Synchronous; times (may be NULL) is filled.    */
+int bsmr_sddmm_sharded_host(bsmr_plan* plan, uint32_t K, const float* hA, const float* hB, float* hP, uint32_t flags, int root,
+                            bsmr_shard_times* times);
 
 /* ---- SDDMM ---------------------------------------------------------------------------
  * sddmm_gpu(M, N, K, dA, dB, rphm, dP, logger) (include/sddmmKernel.cuh:25-30,
@@ -185,7 +244,11 @@ int bsmr_plan_set_shard(bsmr_plan* plan, uint32_t rank, uint32_t world,
 #define BSMR_SDDMM_RESIDUAL_ONLY  1u   /* every nnz through the CUDA-core kernel (delta > 1) */
 #define BSMR_SDDMM_NO_REORDER     2u   /* ignore the plan's reorder: CSR order, residual kernel */
 #define BSMR_SDDMM_NO_WIDE        4u   /* dense-block + residual kernels only, exactly the reference's split */
-#define BSMR_SDDMM_THREE_KERNEL   8u   /* the three-kernel plan (wide groups + BSMR split) without the per-K choice below */
+#define BSMR_SDDMM_THREE_KERNEL   8u   /* the three-kernel plan (wide groups + BSMR split), whatever choice is installed for K */
+/* A default call runs the three-kernel plan: the wide row-group kernel on the groups that qualify, the dense-block and
+ * residual kernels on the rest.  Operands without a tensor-core path (K % 4 != 0, A / B not 16-byte aligned) go through
+ * the CUDA-core kernel entirely, rows in reordered order.  Nothing is measured or synchronised behind the caller's
+ * back: with ms_per_iteration == NULL the call is asynchronous and stream-capturable.                               */
 int bsmr_sddmm(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP,
                int iterations, uint32_t flags, float* ms_per_iteration);
 
@@ -196,11 +259,15 @@ int bsmr_sddmm(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, fl
 int bsmr_sddmm_host(bsmr_plan* plan, uint32_t K, const float* hA, const float* hB, float* hP,
                     int iterations, uint32_t flags, float* ms_per_iteration, float* total_ms);
 
-/* A call with BSMR_SDDMM_DEFAULT runs, per K, the fastest of three execution plans over the same nnz, chosen by
- * measurement on the first such call (four passes each; that first call therefore synchronises): the three-kernel
- * plan (wide row groups + BSMR split), the BSMR split alone (= BSMR_SDDMM_NO_WIDE), or, on an unsharded plan, the
- * CSR-order residual kernel (= BSMR_SDDMM_NO_REORDER).  The choice is forgotten at the next column reorder /
- * set_shard; environment BSMR_NO_AUTOTUNE pins the three-kernel plan.  _execution_choice returns the flags chosen. */
+/* Measured choice of the execution plan for one K -- an explicit tool, not part of bsmr_sddmm: _autotune times the
+ * three-kernel plan, the BSMR split alone (= BSMR_SDDMM_NO_WIDE) and, on an unsharded plan, the CSR-order residual
+ * kernel (= BSMR_SDDMM_NO_REORDER) on the caller's operands (one warm-up pass + best of three each; synchronises,
+ * writes P) and installs the winner for default calls with this K until the next column reorder / set_shard.  The
+ * candidates differ in numerics (TF32 tiles ~1.5e-4 relative, fp32 residual ~1e-6) and the outcome depends on timing:
+ * ranks that must agree install one choice with _set_execution_choice.  _execution_choice returns what a default call
+ * with this K runs (BSMR_SDDMM_DEFAULT = the three-kernel plan).                                                    */
+int bsmr_plan_autotune(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP, uint32_t* chosen_flags);
+int bsmr_plan_set_execution_choice(bsmr_plan* plan, uint32_t K, uint32_t flags);
 int bsmr_plan_execution_choice(bsmr_plan* plan, uint32_t K, uint32_t* flags);
 
 /* Pipelined form of the host-data overload: the same H2D A,B -> zero P -> kernels -> D2H P, but the call returns as
@@ -218,7 +285,8 @@ int bsmr_sddmm_host_wait(bsmr_plan* plan, uint64_t ticket);
 
 /* sddmm_gpu_batch(numBatch, M, N, K, nnz, dA, dB, rphm, dP, time) (include/sddmmKernel.cuh:41-47,
  * src/sddmmKernel.cu:2764-2848): num_batch (A, B, P) triples on the plan's pattern, device pointers, batch b at
- * dA + b*M*K (row-major M x K), dB + b*N*K (column-major K x N) and dP + b*nnz (CSR order).  total_ms (may be NULL:
+ * dA + b*M*K (row-major M x K), dB + b*N*K (column-major K x N) and dP + b*nnz (CSR order).  Every kernel of the plan
+ * is launched once for the whole batch (the reference folds the batch into gridDim.z).  total_ms (may be NULL:
  * then the call is asynchronous on the context's stream) = Logger-style total time of the batch.           */
 int bsmr_sddmm_batch(bsmr_plan* plan, uint32_t num_batch, uint32_t K, const float* dA, const float* dB, float* dP,
                      uint32_t flags, float* total_ms);
@@ -226,6 +294,23 @@ int bsmr_sddmm_batch(bsmr_plan* plan, uint32_t num_batch, uint32_t K, const floa
  * every P has landed.  total_ms (may be NULL) = wall time of the call.                                      */
 int bsmr_sddmm_host_batch(bsmr_plan* plan, uint32_t num_batch, uint32_t K, const float* hA, const float* hB, float* hP,
                           uint32_t flags, float* total_ms);
+
+/* batchedMatrixTranspose(width, height, numBatches, d_input, d_output) (include/sddmmKernel.cuh:49-51,
+ * src/sddmmKernel.cu:2486-2515, 2852-2869): every batch element is a height x width row-major matrix, written back as
+ * width x height; elements are width*height apart.  Queued on the context's stream.                          */
+int bsmr_batched_transpose(bsmr_ctx* ctx, uint32_t width, uint32_t height, uint32_t num_batches,
+                           const float* d_input, float* d_output);
+
+/* ---- fp16 storage of B (the reference sketches half operands in include/TensorCoreConfig.cuh:22-56) ----
+ * On graph-shaped patterns the time goes into one K-vector of B per nnz; stored as fp16 (11 significant bits, what the
+ * TF32 tensor-core operands keep as well) the vector is half the bytes at every level of the gather.  A stays fp32,
+ * products and sums are fp32.  Tolerance of this entry point: the reference's checkData (|d| < 1e-5 or relative
+ * < 1e-3; measured ~2e-4).  Every nnz goes through the CUDA-core kernel, rows in reordered order (flags =
+ * BSMR_SDDMM_DEFAULT, shard-aware) or CSR order (BSMR_SDDMM_NO_REORDER).
+ * _convert: count fp32 values -> fp16, round to nearest even, on the context's stream.                        */
+int bsmr_convert_f32_to_f16(bsmr_ctx* ctx, const float* d_src, void* d_dst_f16, uint64_t count);
+int bsmr_sddmm_f16b(bsmr_plan* plan, uint32_t K, const float* dA, const void* dB_f16, float* dP,
+                    int iterations, uint32_t flags, float* ms_per_iteration);
 
 /* One pass with the two kernels timed separately (CUDA events on the context's stream):
  * what bench.py's roofline block reports per kernel.  Either output may be NULL.          */

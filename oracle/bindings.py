@@ -93,6 +93,9 @@ class Oracle:
         lib.oracle_similarity.argtypes = [u32p, u32p, C.c_uint32, C.c_uint32, C.c_int]
         lib.oracle_row_reordering.argtypes = [C.c_uint32, C.c_uint32, u32p, u32p, C.c_float, C.c_uint32, C.c_int,
                                               u32p, u32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.oracle_row_reordering_indexed.argtypes = [C.c_uint32, C.c_uint32, u32p, u32p, C.c_float, C.c_uint32, C.c_int, C.c_int,
+                                                      u32p, u32p, C.POINTER(C.c_int), C.POINTER(C.c_int), u32p,
+                                                      C.POINTER(C.c_uint64)]
         lib.oracle_col_reordering.argtypes = [C.c_uint32, C.c_uint32, u32p, u32p, u32p, C.c_uint32, C.c_float,
                                               C.POINTER(_ColReorder)]
         lib.oracle_free_colreorder.argtypes = [C.POINTER(_ColReorder)]
@@ -151,6 +154,22 @@ class Oracle:
         self.lib.oracle_row_reordering(M, N, _p(ro, u32p), _p(ci, u32p), alpha, block_size, int(exact),
                                        _p(perm, u32p), C.byref(n), C.byref(cc), C.byref(ct))
         return perm[:n.value].copy(), cc.value, ct.value
+
+    def row_reordering_indexed(self, M, N, row_offsets, col_indices, alpha, block_size, exact=False, use_filter=True,
+                               with_stats=False):
+        """Same permutation as row_reordering, on sparse encodings with the rows filed per column block (graph scale)."""
+        ro, ci = _u32(row_offsets), _u32(col_indices)
+        perm = np.zeros(max(M, 1), dtype=np.uint32)
+        n = C.c_uint32(0)
+        cc, ct = C.c_int(0), C.c_int(0)
+        stats = (C.c_uint64 * 4)()
+        self.lib.oracle_row_reordering_indexed(M, N, _p(ro, u32p), _p(ci, u32p), alpha, block_size, int(exact),
+                                               int(use_filter), _p(perm, u32p), C.byref(n), C.byref(cc), C.byref(ct),
+                                               None, stats)
+        out = (perm[:n.value].copy(), cc.value, ct.value)
+        if with_stats:
+            out += (dict(evaluations=int(stats[0]), joins=int(stats[1]), filed=int(stats[2]), runs=int(stats[3])),)
+        return out
 
     def col_reordering(self, M, N, row_offsets, col_indices, rows, delta, with_rphm=False):
         ro, ci, rows = _u32(row_offsets), _u32(col_indices), _u32(rows)

@@ -332,6 +332,11 @@ float oracle_similarity(const uint32_t* enc_rep, const uint32_t* enc_cmp, uint32
     return min_sum / max_sum;
 }
 
+static int cmp_u32_fwd(const void* a, const void* b) {
+    const uint32_t x = *(const uint32_t*)a, y = *(const uint32_t*)b;
+    return x < y ? -1 : (x > y);
+}
+
 /* stable ascending argsort on u32 keys (thrust host sort_by_key == stable) */
 typedef struct { uint32_t key, pos; } kp_t;
 static int cmp_kp(const void* a, const void* b) {
@@ -414,6 +419,298 @@ void oracle_row_reordering(uint32_t M, uint32_t N, const uint32_t* row_offsets, 
     *num_out = M - first;
     memcpy(perm_out, perm + first, sizeof(uint32_t) * (M - first));
     free(enc); free(disp); free(asc); free(cid); free(rep); free(indices); free(sorted); free(perm);
+}
+
+/* ===================================================================================== */
+/* a4-a6 at graph scale: the SAME sequential semantics as oracle_row_reordering, restated    */
+/* on sparse encodings so that it finishes on 10^6-row inputs (the dense rows x nb matrix    */
+/* of the reference, src/rowReordering.cu:1040-1043, is 25 GB at 2^20 rows).                 */
+/*   - similarity: every float operation of calculate_similarity_norm_weighted_jaccard        */
+/*     (:235-293) in the same order -- thread t sums the terms i = t, t+bd, ... ascending;    */
+/*     zero terms add +0.0f exactly, so only threads that own a non-zero block of the          */
+/*     candidate are recomputed, the others keep the representative-only partial sums          */
+/*   - candidates: a row sharing no kept block with the representative has min-sum 0, i.e.     */
+/*     sim = 0 <= alpha (alpha >= 0), and  sim <= (nnz of the row in shared kept blocks) /     */
+/*     (nnz of the row in kept blocks).  Every row is therefore filed only under a subset      */
+/*     of its blocks chosen so that the blocks left out hold less than (alpha - 1e-3) of its   */
+/*     nnz (use_filter != 0; the most popular blocks are left out first); a representative     */
+/*     that contains none of the filed blocks cannot be joined by the row.  The sweep of a     */
+/*     cluster visits, in position order, the unassigned rows filed under a block of the       */
+/*     representative; a block that enters the representative at a join contributes its rows   */
+/*     behind the join position only (earlier ones were passed while their similarity was 0). */
+/*   - rows whose (possibly lossy) sum of squares is 0 join exactly the representatives whose  */
+/*     sum is 0 too (:258-263): they are filed under one pseudo block.                         */
+/* ===================================================================================== */
+typedef struct { uint32_t* a; size_t n, cap; } u32heap;
+static void heap_push(u32heap* h, uint32_t v) {
+    if (h->n == h->cap) { h->cap = h->cap ? h->cap * 2 : 1024; h->a = (uint32_t*)realloc(h->a, h->cap * sizeof(uint32_t)); }
+    size_t i = h->n++;
+    while (i > 0) {
+        const size_t p = (i - 1) / 2;
+        if (h->a[p] <= v) break;
+        h->a[i] = h->a[p];
+        i = p;
+    }
+    h->a[i] = v;
+}
+static uint32_t heap_pop(u32heap* h) {
+    const uint32_t top = h->a[0];
+    const uint32_t v = h->a[--h->n];
+    size_t i = 0;
+    for (;;) {
+        size_t c = 2 * i + 1;
+        if (c >= h->n) break;
+        if (c + 1 < h->n && h->a[c + 1] < h->a[c]) ++c;
+        if (h->a[c] >= v) break;
+        h->a[i] = h->a[c];
+        i = c;
+    }
+    if (h->n) h->a[i] = v;
+    return top;
+}
+typedef struct { uint32_t pop, blk, cnt; } pbc_t;
+static int cmp_pbc_desc(const void* a, const void* b) {
+    const pbc_t* x = (const pbc_t*)a; const pbc_t* y = (const pbc_t*)b;
+    if (x->pop != y->pop) return x->pop > y->pop ? -1 : 1;
+    return x->blk < y->blk ? -1 : (x->blk > y->blk);
+}
+/* shared-memory tree of include/cudaUtil.cuh:37-43 over per-warp values */
+static float warp_tree_f32(const float* wv, uint32_t nw, uint32_t first_stride) {
+    float shm[64];
+    for (uint32_t i = 0; i < 64; ++i) shm[i] = i < nw ? wv[i] : 0.0f;
+    for (uint32_t s = first_stride; s >= 1; s >>= 1)
+        for (uint32_t w = 0; w < s; ++w) shm[w] = shm[w] + shm[w + s];
+    return shm[0];
+}
+static float butterfly32(const float* in) {
+    float v[32], t[32];
+    memcpy(v, in, sizeof v);
+    for (uint32_t x = 1; x < 32; x <<= 1) {
+        for (uint32_t l = 0; l < 32; ++l) t[l] = v[l] + v[l ^ x];
+        memcpy(v, t, sizeof v);
+    }
+    return v[0];
+}
+
+void oracle_row_reordering_indexed(uint32_t M, uint32_t N, const uint32_t* row_offsets, const uint32_t* col_indices,
+                                   float alpha, uint32_t block_size, int exact, int use_filter,
+                                   uint32_t* perm_out, uint32_t* num_out, int* clusters_compat, int* clusters_true,
+                                   uint32_t* cluster_ids_by_pos, uint64_t* stats /* [4]: evaluations, joins, filed entries, runs */) {
+    const uint32_t nb = (uint32_t)ceilf((float)N / (float)block_size);
+    const uint32_t bd = oracle_clustering_blockdim(nb);
+    const uint32_t nw = bd / 32;
+    uint32_t first_stride = nw / 2;
+    if (exact) { uint32_t p = 1; while (p < nw) p <<= 1; first_stride = p / 2; }
+    uint32_t kept_mask = 0;
+    {   /* which warps the tree keeps (every warp at most once) */
+        uint32_t contrib[64];
+        for (uint32_t w = 0; w < 64; ++w) contrib[w] = w < nw ? (1u << w) : 0u;
+        for (uint32_t s = first_stride; s >= 1; s >>= 1)
+            for (uint32_t w = 0; w < s; ++w) contrib[w] |= contrib[w + s];
+        kept_mask = contrib[0];
+    }
+#define KEPT(blk) ((kept_mask >> (((blk) % bd) >> 5)) & 1u)
+    const uint32_t nnz = row_offsets[M];
+    /* ---- sparse encodings (:49-93) ---- */
+    uint32_t* enc_ptr = (uint32_t*)calloc((size_t)M + 1, sizeof(uint32_t));
+    uint32_t* enc_blk = (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)nnz + 1));
+    uint32_t* enc_cnt = (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)nnz + 1));
+    uint32_t* disp = (uint32_t*)calloc((size_t)M + 1, sizeof(uint32_t));
+    uint32_t* row_sq = (uint32_t*)calloc((size_t)M + 1, sizeof(uint32_t));
+    uint32_t* pop = (uint32_t*)calloc((size_t)nb + 2, sizeof(uint32_t));
+    uint32_t* tmpb = (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)N + 1));
+    uint32_t runs = 0;
+    for (uint32_t r = 0; r < M; ++r) {
+        const uint32_t b = row_offsets[r], e = row_offsets[r + 1];
+        enc_ptr[r] = runs;
+        if (e == b) continue;
+        for (uint32_t k = b; k < e; ++k) tmpb[k - b] = col_indices[k] / block_size;
+        qsort(tmpb, e - b, sizeof(uint32_t), cmp_u32_fwd);
+        uint32_t res = 0, sq = 0;
+        const uint32_t first = runs;
+        for (uint32_t k = 0; k < e - b;) {
+            uint32_t k2 = k;
+            while (k2 < e - b && tmpb[k2] == tmpb[k]) ++k2;
+            enc_blk[runs] = tmpb[k]; enc_cnt[runs] = k2 - k; ++runs;
+            res += block_size - (k2 - k);
+            if (KEPT(tmpb[k])) sq += (k2 - k) * (k2 - k);
+            pop[tmpb[k]]++;
+            k = k2;
+        }
+        disp[r] = res + (e - b) * (runs - first);
+        row_sq[r] = sq;
+    }
+    enc_ptr[M] = runs;
+    free(tmpb);
+    uint32_t* asc = (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)M + 1));
+    uint32_t* cid = (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)M + 1));
+    stable_argsort_u32(disp, M, asc, NULL);
+    memset(cid, 0xFF, sizeof(uint32_t) * ((size_t)M + 1));
+    uint32_t zero_row_idx = 0;
+    while (zero_row_idx < M && disp[asc[zero_row_idx]] == 0) { cid[zero_row_idx] = 0; zero_row_idx++; }
+
+    /* ---- the rows filed per block (pseudo block nb: rows whose sum of squares is 0) ---- */
+    const float bound = alpha - 1e-3f;
+    uint8_t* filed = (uint8_t*)calloc((size_t)runs + 1, 1);
+    uint32_t* inv_ptr = (uint32_t*)calloc((size_t)nb + 3, sizeof(uint32_t));
+    pbc_t* srt = (pbc_t*)malloc(sizeof(pbc_t) * ((size_t)nb + 1));
+    uint64_t filed_total = 0;
+    for (uint32_t p = zero_row_idx; p < M; ++p) {
+        const uint32_t r = asc[p], b = enc_ptr[r], e = enc_ptr[r + 1];
+        if (row_sq[r] == 0) { inv_ptr[nb + 1]++; filed_total++; continue; }
+        uint32_t n = 0, tot = 0;
+        for (uint32_t j = b; j < e; ++j)
+            if (KEPT(enc_blk[j])) { srt[n].pop = pop[enc_blk[j]]; srt[n].blk = j; srt[n].cnt = enc_cnt[j]; ++n; tot += enc_cnt[j]; }
+        if (use_filter && bound > 0.0f) qsort(srt, n, sizeof(pbc_t), cmp_pbc_desc);
+        uint32_t left_out = 0;
+        for (uint32_t k = 0; k < n; ++k) {
+            if (use_filter && bound > 0.0f && (float)(left_out + srt[k].cnt) < bound * (float)tot) { left_out += srt[k].cnt; continue; }
+            filed[srt[k].blk] = 1;
+            inv_ptr[enc_blk[srt[k].blk] + 1]++;
+            filed_total++;
+        }
+    }
+    free(srt);
+    for (uint32_t b = 0; b <= nb; ++b) inv_ptr[b + 1] += inv_ptr[b];
+    uint32_t* inv = (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)filed_total + 1));
+    uint32_t* fillp = (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)nb + 2));
+    memcpy(fillp, inv_ptr, sizeof(uint32_t) * ((size_t)nb + 1));
+    for (uint32_t p = zero_row_idx; p < M; ++p) {          /* ascending positions -> every list is sorted */
+        const uint32_t r = asc[p];
+        if (row_sq[r] == 0) { inv[fillp[nb]++] = p; continue; }
+        for (uint32_t j = enc_ptr[r]; j < enc_ptr[r + 1]; ++j)
+            if (filed[j]) inv[fillp[enc_blk[j]]++] = p;
+    }
+    free(fillp); free(filed);
+
+    /* ---- the sweep ---- */
+    uint32_t* rep = (uint32_t*)calloc((size_t)nb + 1, sizeof(uint32_t));
+    float* repn = (float*)calloc((size_t)nb + 1, sizeof(float));
+    uint32_t* candv = (uint32_t*)calloc((size_t)nb + 1, sizeof(uint32_t));
+    uint32_t* rep_blocks = (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)nb + 1));
+    uint32_t* merged = (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)nb + 1));
+    uint32_t* stamp = (uint32_t*)calloc((size_t)M + 1, sizeof(uint32_t));
+    float part_max[1024], warp_max[32];
+    uint8_t thr_touched[1024];
+    memset(thr_touched, 0, sizeof thr_touched);
+    u32heap heap = {0, 0, 0};
+    uint64_t n_eval = 0, n_join = 0;
+    uint32_t cluster = 0, start = zero_row_idx;
+    while (start < M) {
+        ++cluster;
+        cid[start] = cluster;
+        uint32_t n_rep_blocks = 0, s_rep = 0;
+        float n_rep = 0.0f;
+        heap.n = 0;
+        uint32_t last_pos = start;
+        /* absorb the rows of `pos` into the representative and refresh everything derived from it */
+#define ABSORB(pos)                                                                                        \
+        do {                                                                                               \
+            const uint32_t r_ = asc[(pos)], b_ = enc_ptr[r_], e_ = enc_ptr[r_ + 1];                        \
+            uint32_t i_ = 0, j_ = b_, m_ = 0;                                                              \
+            while (i_ < n_rep_blocks || j_ < e_) {                                                         \
+                if (j_ >= e_ || (i_ < n_rep_blocks && rep_blocks[i_] < enc_blk[j_])) merged[m_++] = rep_blocks[i_++]; \
+                else if (i_ >= n_rep_blocks || enc_blk[j_] < rep_blocks[i_]) {                             \
+                    const uint32_t nbk_ = enc_blk[j_];                                                     \
+                    merged[m_++] = nbk_;                                                                   \
+                    if (KEPT(nbk_)) {   /* a block new to the representative: its rows behind this position */ \
+                        uint32_t lo_ = inv_ptr[nbk_], hi_ = inv_ptr[nbk_ + 1];                             \
+                        while (lo_ < hi_) { const uint32_t mid_ = (lo_ + hi_) / 2; if (inv[mid_] <= (pos)) lo_ = mid_ + 1; else hi_ = mid_; } \
+                        for (uint32_t q_ = lo_; q_ < inv_ptr[nbk_ + 1]; ++q_) {                            \
+                            const uint32_t cp_ = inv[q_];                                                  \
+                            if (cid[cp_] == ORACLE_NULL_VALUE && stamp[cp_] != cluster) { stamp[cp_] = cluster; heap_push(&heap, cp_); } \
+                        }                                                                                  \
+                    }                                                                                      \
+                    ++j_;                                                                                  \
+                } else { merged[m_++] = rep_blocks[i_++]; ++j_; }                                          \
+            }                                                                                              \
+            for (uint32_t j2_ = b_; j2_ < e_; ++j2_) rep[enc_blk[j2_]] += enc_cnt[j2_];                    \
+            memcpy(rep_blocks, merged, sizeof(uint32_t) * m_);                                             \
+            n_rep_blocks = m_;                                                                             \
+            s_rep = 0;                                                                                     \
+            for (uint32_t k_ = 0; k_ < n_rep_blocks; ++k_)                                                 \
+                if (KEPT(rep_blocks[k_])) s_rep += rep[rep_blocks[k_]] * rep[rep_blocks[k_]];              \
+            n_rep = sqrtf((float)s_rep);                                                                   \
+            for (uint32_t t_ = 0; t_ < bd; ++t_) part_max[t_] = 0.0f;                                      \
+            for (uint32_t k_ = 0; k_ < n_rep_blocks; ++k_) {   /* ascending i -> ascending inside every thread */ \
+                const uint32_t i2_ = rep_blocks[k_];                                                       \
+                repn[i2_] = (float)rep[i2_] / n_rep;                                                       \
+                part_max[i2_ % bd] = part_max[i2_ % bd] + repn[i2_];                                       \
+            }                                                                                              \
+            for (uint32_t w_ = 0; w_ < nw; ++w_) warp_max[w_] = butterfly32(part_max + 32 * w_);           \
+        } while (0)
+        ABSORB(start);
+        if (s_rep == 0) {
+            /* a representative without a kept block: exactly the rows of the same kind can join (:258-260) */
+            uint32_t lo = inv_ptr[nb], hi = inv_ptr[nb + 1];
+            while (lo < hi) { const uint32_t mid = (lo + hi) / 2; if (inv[mid] <= start) lo = mid + 1; else hi = mid; }
+            for (uint32_t q = lo; q < inv_ptr[nb + 1]; ++q)
+                if (cid[inv[q]] == ORACLE_NULL_VALUE && stamp[inv[q]] != cluster) { stamp[inv[q]] = cluster; heap_push(&heap, inv[q]); }
+        }
+        while (heap.n) {
+            const uint32_t p = heap_pop(&heap);
+            if (p <= last_pos || cid[p] != ORACLE_NULL_VALUE) continue;
+            last_pos = p;
+            const uint32_t r = asc[p], b = enc_ptr[r], e = enc_ptr[r + 1];
+            const uint32_t s_cmp = row_sq[r];
+            ++n_eval;
+            float sim;
+            if (s_rep == 0 && s_cmp == 0) sim = 1.0f;
+            else if (s_rep == 0 || s_cmp == 0) sim = 0.0f;
+            else {
+                const float n_cmp = sqrtf((float)s_cmp);
+                float wmin[32], wmax[32];
+                uint32_t touched_warps = 0;
+                for (uint32_t j = b; j < e; ++j) { candv[enc_blk[j]] = enc_cnt[j]; thr_touched[enc_blk[j] % bd] = 1; touched_warps |= 1u << ((enc_blk[j] % bd) >> 5); }
+                for (uint32_t w = 0; w < nw; ++w) {
+                    if (!((touched_warps >> w) & 1u)) { wmin[w] = 0.0f; wmax[w] = warp_max[w]; continue; }
+                    float lmin[32], lmax[32];
+                    for (uint32_t l = 0; l < 32; ++l) {
+                        const uint32_t t = 32 * w + l;
+                        if (!thr_touched[t]) { lmin[l] = 0.0f; lmax[l] = part_max[t]; continue; }
+                        float mn = 0.0f, mx = 0.0f;
+                        for (uint32_t i = t; i < nb; i += bd) {
+                            const float a = repn[i];
+                            const float c = (float)candv[i] / n_cmp;
+                            mn = mn + fminf(a, c);
+                            mx = mx + fmaxf(a, c);
+                        }
+                        lmin[l] = mn; lmax[l] = mx;
+                    }
+                    wmin[w] = butterfly32(lmin);
+                    wmax[w] = butterfly32(lmax);
+                }
+                for (uint32_t j = b; j < e; ++j) { candv[enc_blk[j]] = 0; thr_touched[enc_blk[j] % bd] = 0; }
+                sim = warp_tree_f32(wmin, nw, first_stride) / warp_tree_f32(wmax, nw, first_stride);
+            }
+            if (sim > alpha) {
+                cid[p] = cluster;
+                ++n_join;
+                ABSORB(p);
+            }
+        }
+        for (uint32_t k = 0; k < n_rep_blocks; ++k) { rep[rep_blocks[k]] = 0; repn[rep_blocks[k]] = 0.0f; }
+        while (start < M && cid[start] != ORACLE_NULL_VALUE) ++start;
+    }
+#undef ABSORB
+#undef KEPT
+    if (stats) { stats[0] = n_eval; stats[1] = n_join; stats[2] = filed_total; stats[3] = runs; }
+    if (cluster_ids_by_pos) memcpy(cluster_ids_by_pos, cid, sizeof(uint32_t) * M);
+
+    uint32_t* indices = (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)M + 1));
+    uint32_t* sorted = (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)M + 1));
+    stable_argsort_u32(cid, M, indices, sorted);
+    uint32_t* perm = (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)M + 1));
+    for (uint32_t i = 0; i < M; ++i) perm[i] = asc[indices[i]];
+    if (clusters_compat) *clusters_compat = M ? (int)sorted[indices[M - 1]] + (zero_row_idx != 0) : 0;
+    if (clusters_true) *clusters_true = (zero_row_idx < M) ? (int)cluster : 0;
+    uint32_t first = 0;
+    while (first < M && row_offsets[perm[first] + 1] - row_offsets[perm[first]] == 0) ++first;
+    *num_out = M - first;
+    memcpy(perm_out, perm + first, sizeof(uint32_t) * (M - first));
+    free(enc_ptr); free(enc_blk); free(enc_cnt); free(disp); free(row_sq); free(pop); free(asc); free(cid);
+    free(inv_ptr); free(inv); free(rep); free(repn); free(candv); free(rep_blocks); free(merged); free(stamp);
+    free(heap.a); free(indices); free(sorted); free(perm);
 }
 
 /* ===================================================================================== */

@@ -72,6 +72,15 @@ void oracle_row_reordering(uint32_t M, uint32_t N, const uint32_t* row_offsets, 
                            uint32_t* perm_out, uint32_t* num_out,
                            int* clusters_compat, int* clusters_true);
 
+/* The same permutation computed on sparse encodings with the rows filed per column block, so that it
+ * finishes on 10^6-row inputs (see the comment at the definition): the checker for the product at graph
+ * scale, itself checked against oracle_row_reordering on every small case.  use_filter = 0 files every row
+ * under all of its blocks.  stats (optional, 4 words): evaluations, joins, filed entries, encoding runs.   */
+void oracle_row_reordering_indexed(uint32_t M, uint32_t N, const uint32_t* row_offsets, const uint32_t* col_indices,
+                                   float alpha, uint32_t block_size, int exact_reduce, int use_filter,
+                                   uint32_t* perm_out, uint32_t* num_out, int* clusters_compat, int* clusters_true,
+                                   uint32_t* cluster_ids_by_pos, uint64_t* stats);
+
 /* ---- a8: colReordering_cpu (src/colReordering.cu:274-404, 244-271) -------------------- */
 typedef struct {
     uint32_t num_row_panels;

@@ -93,6 +93,7 @@ def main():
             plan.col_reorder(0.3)
             info = plan.info()
             dump = torch.zeros(16384 // 4 + 2048 // 4, dtype=torch.int32, device="cuda")
+            pkg.lib().bsmr_debug_set_dense_smem_dump.argtypes = [__import__('ctypes').c_void_p]   # debug build only (make DEBUG=1, BSMR_B200_LIB)
             pkg.lib().bsmr_debug_set_dense_smem_dump(dump.data_ptr())
             dP = torch.full((nnz,), -7.0, device="cuda")
             ms = plan.sddmm(K, dA, dB, dP, iterations=1)
