@@ -1,19 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- SDDMM GFLOPS (2*nnz*K / time) of the BSMR hot path on B200, one JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--quick]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (config.workload): the nips-shaped matrix of BASELINE.json configs[1] at K=128,
-alpha=0.3, delta=0.3.  dataset/nips.mtx is not in the reference tree, so a seeded synthetic
-of the same shape / nnz is used (bsmr-sddmm_b200/synth.py) unless dataset/nips.mtx exists.
-At N GPUs the job is N such row blocks stacked into one matrix, reordered globally and sharded
-over the ranks by work-balanced ranges of reordered row panels (bsmr_plan_set_shard: nnz plus tile count): weak scaling,
-per-GPU work fixed, no collective on the data path (B is replicated before the clock starts).
+N = 1 (the headline line).  Workload (config.workload): the nips-shaped matrix of BASELINE.json configs[1] at K=128,
+alpha=0.3, delta=0.3.  dataset/nips.mtx is not in the reference tree, so a seeded synthetic of the same shape / nnz is
+used (bsmr-sddmm_b200/synth.py) unless dataset/nips.mtx exists.  A "step" = one pass of the hot path over the matrix;
+the inputs (27 MB) fit in L2, so L2 is flushed (a 512 MB buffer is rewritten) between timed steps, outside the event
+pairs.  Times are CUDA events on the stream the kernels run on.  The same run also measures, and reports under
+`configs`, every other configuration BASELINE.json names -- nips K=32 / 256, the DLMC masks at K=64, the 2^20-row graph at
+K=128 with the real BSMR row order (reorder time included), the 2^23-row graph at K=256 on this one GPU -- plus the batched
+entry point and the fp16-B path, and under `comparators` cuSPARSE SDDMM and the reference's own sm_80-style kernels
+rebuilt for sm_100 (oracle/_ref, each in a child process).
 
-A "step" = one pass of the hot path (wide row-group tcgen05 kernel + dense-block tcgen05 kernel +
-residual kernel, each over its share of the nnz) over the matrix.  The inputs (27 MB) fit in L2, so L2 is flushed (a 512 MB buffer is rewritten) between
-timed steps, outside the event pairs.  Times are CUDA events on the stream the kernels run on.
+N > 1.  Workload: BASELINE.json configs[4], the fixed 2^23-row / 2.5e8-nnz R-MAT graph at K=256 (STRONG scaling; it
+fits one GPU, and rank 0 also times the unsharded pass in the same run: `single_gpu`).  Work is partitioned by
+nnz-balanced ranges of reordered row panels; `value` times, with A and B resident on every rank, the kernels of every
+shard PLUS the assembly of P on rank 0 (pack -> grouped ncclSend/ncclRecv over NVLink -> un-permute: bsmr_sddmm_sharded);
+`e2e` times bsmr_sddmm_sharded_host from pinned host buffers: every rank uploads the A rows of its shard and 1/N of B,
+ncclAllGather replicates B, kernels, gather of P, D2H on rank 0.  The inputs (17 GB) are far larger than L2.
 """
 import argparse
 import json
@@ -35,34 +41,32 @@ os.dup2(2, 1)
 def emit(line):
     sys.stdout.flush()
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
 K_DEFAULT, ALPHA, DELTA = 128, 0.3, 0.3
 METRIC, UNIT = "sddmm_gflops", "GFLOP/s"
+GRAPH8M = dict(scale=23, edges=250_000_000, K=256)
+GRAPH1M = dict(scale=20, edges=30_000_000, K=128)
+PLAN_NAMES = {0: "wide row groups + BSMR split (three kernels)", 4: "BSMR split (dense blocks + residual)", 2: "CSR-order residual kernel"}
 
 
-def load_workload(pkg, blocks):
-    """`blocks` nips-shaped row blocks stacked vertically (blocks == 1: the nips config itself)."""
+def log(msg):
+    print("[bench %.1fs] %s" % (time.perf_counter() - _T0, msg), file=sys.stderr, flush=True)
+
+
+_T0 = time.perf_counter()
+
+
+def load_nips(pkg):
     path = os.path.join(ROOT, "dataset", "nips.mtx")
-    parts = []
-    source = "synthetic nips-shaped (1500x12419, nnz 746316), seed 1500+i"
-    for i in range(blocks):
-        if i == 0 and os.path.exists(path):
-            M, N, ro, ci = pkg.synth.read_mtx(path)
-            source = "dataset/nips.mtx + synthetic blocks"
-        else:
-            M, N, ro, ci = pkg.synth.nips_like(seed=1500 + i)
-        parts.append((M, N, ro.astype(np.int64), ci))
-    N = parts[0][1]
-    ro = [np.zeros(1, dtype=np.int64)]
-    off = 0
-    for _, _, r, c in parts:
-        ro.append(r[1:] + off)
-        off += len(c)
-    ro = np.concatenate(ro).astype(np.uint32)
-    ci = np.concatenate([p[3] for p in parts])
-    return sum(p[0] for p in parts), N, ro, ci, source
+    if os.path.exists(path):
+        M, N, ro, ci = pkg.synth.read_mtx(path)
+        return M, N, ro, ci, "dataset/nips.mtx"
+    M, N, ro, ci = pkg.synth.nips_like(seed=1500)
+    return M, N, ro, ci, "synthetic nips-shaped (1500x12419, nnz 746316), seed 1500"
 
 
 class ClockSampler:
@@ -119,52 +123,431 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_impl():
+    from oracle.bindings import Oracle, Ref, REF_SO
+    if os.path.exists(REF_SO):
+        return Ref(), "reference"
+    return Oracle(), "port"
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path (sddmm_cpu, OpenMP, all host
-    threads) from oracle/_ref; the oracle port when that library did not travel.  Rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path (sddmm_cpu, OpenMP, all host threads) from
+    oracle/_ref; the oracle port when that library did not travel.  Rank 0 only."""
     if rank != 0:
         return
     pkg = entry.load_package()
-    from oracle.bindings import Oracle, Ref, REF_SO
-    M, N, ro, ci, source = load_workload(pkg, max(1, args.gpus))
-    K = args.k
-    A, B = pkg.synth.make_ab(M, N, K)
-    # all the host threads the box offers: torchrun exports OMP_NUM_THREADS=1, which would otherwise pin the
-    # reference's OpenMP loop to one core (the harness calls omp_set_num_threads(threads) around the call)
+    impl, kind = cpu_impl()
     threads = host_threads()
-    if os.path.exists(REF_SO):
-        impl, kind = Ref(), "reference"
+    if args.gpus <= 1:
+        M, N, ro, ci, source = load_nips(pkg)
+        K = args.k
+        config = nips_config(M, N, len(ci), K, source)
+        sample = "whole workload (%d nnz, K=%d) per step" % (len(ci), K)
+        scaling = "weak"
     else:
-        impl, kind = Oracle(), "port"
-    steps = max(1, min(args.steps, 20))
-    for _ in range(max(1, min(args.warmup, 2))):
+        # configs[4] is 128 GFLOP per pass (~30 s of sddmm_cpu on 16 cores): each step is a bounded sample of it, the
+        # 2^19-row R-MAT graph of the same generator at the same K (1.5e7 nnz, 6 % of the work); GFLOP/s is scale free
+        K = GRAPH8M["K"]
+        M, N, ro, ci = pkg.synth.rmat(19, 15_000_000, 19)
+        config = graph8m_config(args.gpus)
+        sample = "bounded sample per step: R-MAT 2^19 rows / 1.5e7 nnz (same generator, same edges per row, same K=%d) instead of 2^23 rows / 2.5e8 nnz" % K
+        scaling = "strong"
+    A, B = pkg.synth.make_ab(M, N, K)
+    steps = max(1, min(args.steps, 20 if args.gpus <= 1 else 3))
+    for _ in range(max(1, min(args.warmup, 2 if args.gpus <= 1 else 1))):
         impl.sddmm_cpu(M, N, K, A, B, ro, ci, num_threads=threads)
     t0 = time.perf_counter()
     for _ in range(steps):
         impl.sddmm_cpu(M, N, K, A, B, ro, ci, num_threads=threads)
     dt = (time.perf_counter() - t0) / steps
     gflops = 2.0 * len(ci) * K / dt / 1e9
-    sample = "whole workload (%d nnz, K=%d) per step, %d steps" % (len(ci), K, steps)
     line = {"impl": "reference", "metric": METRIC, "value": gflops, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(M, N, len(ci), K, source, args.gpus),
-            "cpu_baseline": {"value": gflops, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": gflops, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample + ", %d steps" % steps},
             "e2e": {"value": gflops, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
-def workload_config(M, N, nnz, K, source, gpus):
+def nips_config(M, N, nnz, K, source):
     return {"workload": "nips K=%d alpha=%.1f delta=%.1f (BASELINE.json configs[1]); %s" % (K, ALPHA, DELTA, source),
             "M": int(M), "N": int(N), "nnz": int(nnz), "K": int(K), "alpha": ALPHA, "delta": DELTA,
-            "blocks": max(1, gpus), "sharding": "work-balanced (nnz + wide tiles) reordered row-panel ranges" if gpus > 1 else "none",
-            "l2": "flushed between timed steps (512 MB buffer rewritten outside the event pairs)"}
+            "sharding": "none", "l2": "flushed between timed steps (512 MB buffer rewritten outside the event pairs)"}
 
 
-def kernel_alg_bytes(K, rows_touched, cols_touched, nnz, extra_index_bytes_per_nnz=0):
-    return 4 * K * (rows_touched + cols_touched) + (8 + extra_index_bytes_per_nnz) * nnz
+def graph8m_config(gpus):
+    return {"workload": "R-MAT power-law graph 2^23 rows, 2.5e8 nnz, K=256 (BASELINE.json configs[4]); seed 23, generated on the GPU",
+            "M": 1 << 23, "N": 1 << 23, "nnz": GRAPH8M["edges"], "K": GRAPH8M["K"], "alpha": ALPHA, "delta": DELTA,
+            "row_order": "identity (clustering at 2^23 rows: see configs / DESIGN.md section 3.4)",
+            "sharding": "nnz-balanced ranges of reordered row panels over %d ranks; B replicated, P gathered to rank 0 over NCCL" % gpus,
+            "l2": "inputs (17 GB) far larger than L2"}
 
 
+def alg_bytes(K, rows_touched, cols_touched, nnz, M=None, b_elem=4):
+    return 4 * K * rows_touched + b_elem * K * cols_touched + 8 * nnz + (4 * (M + 1) if M is not None else 0)
+
+
+# ------------------------------------------------------------------------------------------------ comparators
+COMPARATOR_CHILD = r"""
+import sys, json, numpy as np
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, %(root)r + "/tests")
+import __graft_entry__ as entry
+from oracle.bindings import Ref, Oracle
+from cases import named_case
+pkg = entry.load_package()
+what, K, mode = %(what)r, %(K)d, %(mode)r
+_, M, N, ro, ci = named_case(pkg, what)
+A, B = pkg.synth.make_ab(M, N, K)
+ref = Ref()
+out = {"workload": what, "K": K, "comparator": mode, "nnz": int(len(ci))}
+if mode == "cusparse":
+    P, ms = ref.cusparse_sddmm(M, N, K, ro, ci, A, B, iters=20)
+    out["ms"] = ms
+else:
+    r = ref.bsmr_sddmm_gpu(M, N, K, ro, ci, A, B, 0.3, 0.3, 16, iters=10)
+    P = r["P"]
+    out.update(ms=r["sddmm_ms"], row_reorder_ms=r["row_ms"], col_reorder_ms=r["col_ms"])
+want = Oracle().sddmm_cpu(M, N, K, A, B, ro, ci)
+out["mismatches_vs_sddmm_cpu"] = int(Oracle().check_data(want, P))
+out["gflops"] = 2.0 * len(ci) * K / (out["ms"] * 1e-3) / 1e9 if out["ms"] > 0 else 0.0
+print("RESULT " + json.dumps(out))
+"""
+
+
+def run_comparators(points, timeout=600):
+    """cuSPARSE SDDMM (cusparseSDDMM, CSR fp32, ALG_DEFAULT, preprocess + 20 timed iterations back to back) and the
+    reference's own BSMR pipeline rebuilt for sm_100 (bsa_rowReordering_gpu -> colReordering_cpu -> RPHM -> sddmm_gpu,
+    10 iterations back to back, its own timing), each in a child process: the reference changes device-wide limits and
+    its K > 32 kernels write nothing on sm_100 (reported as mismatches)."""
+    from oracle.bindings import REF_SO
+    if not os.path.exists(REF_SO):
+        return {"unavailable": "oracle/_ref/libbsmr_ref.so was not built (needs /root/reference at build time)"}
+    out = []
+    for what, K, mode in points:
+        code = COMPARATOR_CHILD % dict(root=ROOT, what=what, K=K, mode=mode)
+        try:
+            p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=timeout)
+            res = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
+            if res:
+                out.append(json.loads(res[-1][7:]))
+            else:
+                out.append({"workload": what, "K": K, "comparator": mode, "rc": p.returncode,
+                            "tail": (p.stdout + p.stderr).strip().splitlines()[-2:]})
+        except subprocess.TimeoutExpired:
+            out.append({"workload": what, "K": K, "comparator": mode, "error": "timeout"})
+        log("comparator %s %s K=%d done" % (mode, what, K))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ one configuration
+def measure_config(torch, pkg, ctx, stream, flush, name, M, N, ro, ci, K, row_flags, on_device, peak, steps=10, fp16=False, e2e_host=None):
+    """Reorder + every execution plan of one configuration, cold (L2 flushed between passes, CUDA events) and hot."""
+    nnz = int(ci.numel()) if on_device else int(len(ci))
+    plan = pkg.Plan(ctx, M, N, ro, ci, on_device=on_device)
+    t0 = time.perf_counter()
+    plan.row_reorder(ALPHA, flags=row_flags)
+    row_wall = (time.perf_counter() - t0) * 1e3
+    info_r = plan.info()
+    plan.col_reorder(DELTA)
+    t0 = time.perf_counter()
+    plan.col_reorder(DELTA)                                     # second call: scratch arena warm
+    col_wall = (time.perf_counter() - t0) * 1e3
+    info = plan.info()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5489)
+    dA = torch.rand((M, K), device="cuda", generator=g) * 2
+    dB = torch.rand((N, K), device="cuda", generator=g) * 2
+    dP = torch.full((nnz,), float("nan"), device="cuda")
+    chosen = plan.autotune(K, dA, dB, dP)
+
+    def timed(fn, n):
+        ts = []
+        for _ in range(n):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
+
+    plans = {}
+    for flags, tag in ((pkg.SDDMM_THREE_KERNEL, "three_kernel"), (pkg.SDDMM_NO_WIDE, "bsmr_split"), (pkg.SDDMM_NO_REORDER, "csr_order")):
+        plans[tag + "_ms_cold"] = timed(lambda: plan.sddmm(K, dA, dB, dP, flags=flags, timed=False), max(3, steps // 2))
+    dP.fill_(float("nan"))
+    ms_cold = timed(lambda: plan.sddmm(K, dA, dB, dP, timed=False), steps)
+    written = not bool(torch.isnan(dP).any())
+    ms_hot = plan.sddmm(K, dA, dB, dP, iterations=20 if nnz < 10_000_000 else 3)
+    # size-independent check of what was timed: sampled entries against fp64 dot products
+    ro_d = ro if on_device else torch.from_numpy(ro.astype(np.int64)).cuda()
+    ci_d = ci if on_device else torch.from_numpy(ci.astype(np.int64)).cuda()
+    gi = torch.Generator(device="cuda")
+    gi.manual_seed(11)
+    idx = torch.randint(0, nnz, (min(nnz, 1 << 16),), device="cuda", generator=gi)
+    rows = torch.searchsorted(ro_d.long(), idx, right=True) - 1
+    ref64 = (dA[rows].double() * dB[ci_d[idx].long()].double()).sum(-1)
+    rel = float(((dP[idx].double() - ref64).abs() / ref64.abs().clamp_min(1e-3)).max())
+    m_nz = int((ro_d[1:] != ro_d[:-1]).sum())
+    n_nz = int(torch.unique(ci_d).numel())
+    bytes_alg = alg_bytes(K, m_nz, n_nz, nnz, M)
+    w, a, b = plan.sddmm_profile3(K, dA, dB, dP)
+    out = {"name": name, "M": int(M), "N": int(N), "nnz": nnz, "K": K,
+           "value": 2.0 * nnz * K / (ms_cold * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_cold,
+           "ms_hot_l2": ms_hot, "gflops_hot_l2": 2.0 * nnz * K / (ms_hot * 1e-3) / 1e9,
+           "execution_plan": PLAN_NAMES.get(chosen, "?") + " (bsmr_plan_autotune)", **plans,
+           "roofline": {"bound": "hbm", "algorithmic_bytes": int(bytes_alg), "achieved": bytes_alg / (ms_cold * 1e-3) / 1e9, "peak": peak,
+                        "frac": bytes_alg / (ms_cold * 1e-3) / 1e9 / peak, "traffic": None},
+           "reorder": {"row_order": {0: "BSMR clustering (reference_compat)", 2: "identity"}[row_flags], "row_ms": info_r["row_reordering_ms"],
+                       "row_wall_ms": row_wall, "cluster_kernel_ms": info_r["cluster_kernel_ms"], "clusters": info_r["num_clusters_true"],
+                       "block_size": info_r["block_size"], "col_ms": info["col_reordering_ms"], "format_ms": info["format_build_ms"],
+                       "col_wall_ms": col_wall,
+                       "gflops_incl_reorder": 2.0 * nnz * K / ((ms_cold + info_r["row_reordering_ms"] + info["col_reordering_ms"] + info["format_build_ms"]) * 1e-3) / 1e9},
+           "split": {"dense_nnz": int(info["num_dense_values"]), "residual_nnz": int(info["num_sparse_values"]),
+                     "wide_groups": info["num_wide_groups"], "row_groups": info["num_row_groups"], "wide_tiles": info["num_wide_tiles"],
+                     "wide_nnz": int(info["num_wide_values"]), "block_tiles": info["num_block_tiles"], "block_nnz": int(info["num_block_values"]),
+                     "residual_nnz_outside_wide": int(info["num_residual_values"])},
+           "three_kernel_profile_ms": {"wide": w, "dense_block": a, "residual": b},
+           "check": {"every_entry_written": written, "max_rel_err_sampled_vs_fp64": rel, "samples": int(idx.numel())}}
+    if fp16:
+        dBh = torch.empty((N, K), dtype=torch.float16, device="cuda")
+        ctx.convert_f32_to_f16(dB, dBh, N * K)
+        dP.fill_(float("nan"))
+        ms16 = timed(lambda: plan.sddmm_f16b(K, dA, dBh, dP, timed=False), steps)
+        rel16 = float(((dP[idx].double() - ref64).abs() / ref64.abs().clamp_min(1e-3)).max())
+        b16 = alg_bytes(K, m_nz, n_nz, nnz, M, b_elem=2)
+        out["fp16_b"] = {"ms_per_step": ms16, "value": 2.0 * nnz * K / (ms16 * 1e-3) / 1e9, "max_rel_err_sampled_vs_fp64": rel16,
+                         "algorithmic_bytes": int(b16), "roofline_frac": b16 / (ms16 * 1e-3) / 1e9 / peak,
+                         "roofline_frac_on_fp32_bytes": bytes_alg / (ms16 * 1e-3) / 1e9 / peak,
+                         "how": "bsmr_sddmm_f16b: B stored as fp16, A fp32, fp32 accumulate; every nnz through the CUDA-core kernel in reordered-row order"}
+        del dBh
+    if e2e_host:
+        hA = torch.empty((M, K), dtype=torch.float32, pin_memory=True)
+        hB = torch.empty((N, K), dtype=torch.float32, pin_memory=True)
+        hP = torch.empty(nnz, dtype=torch.float32, pin_memory=True)
+        hA.copy_(dA)
+        hB.copy_(dB)
+        plan.sddmm_host(K, hA, hB, hP)
+        t0 = time.perf_counter()
+        for _ in range(e2e_host):
+            plan.sddmm_host(K, hA, hB, hP)
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_host
+        out["e2e"] = {"ms_per_step": e2e_ms, "value": 2.0 * nnz * K / (e2e_ms * 1e-3) / 1e9, "h2d_bytes_per_step": int((M + N) * K * 4),
+                      "d2h_bytes_per_step": nnz * 4, "how": "blocking bsmr_sddmm_host, pinned host buffers, %d steps" % e2e_host}
+        del hA, hB, hP
+    plan.close()
+    del dA, dB, dP
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_batch(torch, pkg, ctx, stream, flush, M, N, ro, ci, K, nb):
+    """sddmm_gpu_batch: one launch per kernel for the whole batch against nb single calls (the attention-mask use case)."""
+    nnz = len(ci)
+    plan = pkg.Plan(ctx, M, N, ro, ci)
+    plan.reorder(ALPHA, DELTA)
+    dA = torch.rand((nb, M, K), device="cuda") * 2
+    dB = torch.rand((nb, N, K), device="cuda") * 2
+    dP = torch.zeros((nb, nnz), device="cuda")
+    dP2 = torch.zeros((nb, nnz), device="cuda")
+
+    def loop():
+        for b in range(nb):
+            plan.sddmm(K, dA[b], dB[b], dP[b], timed=False)
+
+    def timed(fn):
+        ts = []
+        for _ in range(7):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
+
+    t_loop = timed(loop)
+    t_batch = timed(lambda: plan.sddmm_batch(nb, K, dA, dB, dP2, timed=False))
+    same = bool(torch.equal(dP, dP2))
+    plan.close()
+    return {"workload": "mask90 K=%d x %d (A, B, P) triples" % (K, nb), "loop_of_single_calls_ms": t_loop, "batched_ms": t_batch,
+            "speedup": t_loop / t_batch, "gflops_batched": 2.0 * nnz * K * nb / (t_batch * 1e-3) / 1e9, "bit_identical_to_loop": same,
+            "l2": "flushed before each timed batch"}
+
+
+# ------------------------------------------------------------------------------------------------ N > 1
+def run_sharded(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from graph8m_probe import rmat_device
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = entry.load_package()
+    scale, edges, K = GRAPH8M["scale"], GRAPH8M["edges"], GRAPH8M["K"]
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = pkg.Context(local_rank, stream.cuda_stream)
+    ident = [pkg.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ident, src=0)
+    ctx.comm_init(ident[0], rank, world)
+    n, ro, ci, rows = rmat_device(torch, scale, edges, seed=scale)      # same seed -> the same matrix on every rank
+    del rows
+    nnz = edges
+    plan = pkg.Plan(ctx, n, n, ro, ci, on_device=True)
+    # row order: the clustering of a 2^23-row graph takes tens of minutes (DESIGN.md 3.4): identity order on the root,
+    # shipped with the same call a clustered order would take
+    if rank == 0:
+        plan.row_reorder(ALPHA, flags=pkg.ROW_IDENTITY)
+    t0 = time.perf_counter()
+    plan.bcast_row_order(0)
+    bcast_ms = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    plan.col_reorder(DELTA)
+    col_wall_ms = (time.perf_counter() - t0) * 1e3
+    info = plan.info()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5489)
+    dA = torch.rand((n, K), device="cuda", generator=g) * 2
+    dB = torch.rand((n, K), device="cuda", generator=g) * 2
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- single-GPU baseline of the same matrix, in the same run (rank 0) ----
+    single = None
+    if rank == 0:
+        dP1 = torch.full((nnz,), float("nan"), device="cuda")
+        plan.sddmm(K, dA, dB, dP1)
+        ts = [plan.sddmm(K, dA, dB, dP1) for _ in range(3)]
+        single = {"ms_per_step": float(np.median(ts)), "value": 2.0 * nnz * K / (float(np.median(ts)) * 1e-3) / 1e9}
+    barrier()
+    p0, p1, shard_nnz = plan.set_shard(rank, world)
+    sizes = [None] * world
+    dist.all_gather_object(sizes, [int(p1 - p0), int(shard_nnz)])
+    dP = torch.full((nnz,), float("nan"), device="cuda") if rank == 0 else None
+    for _ in range(max(3, args.warmup)):
+        plan.sddmm_sharded(K, dA, dB, dP, timed=False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    steps = args.steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(steps):
+        plan.sddmm_sharded(K, dA, dB, dP, timed=False)
+    e1.record(stream)
+    barrier()
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    every = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(every, t)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / steps
+    breakdown = plan.sddmm_sharded(K, dA, dB, dP, timed=True)
+    parts = [None] * world
+    dist.all_gather_object(parts, {k: v for k, v in breakdown.items()})
+    # ---- check of what was timed (root): every entry written, sampled entries against fp64 ----
+    check = None
+    if rank == 0:
+        written = not bool(torch.isnan(dP).any())
+        gi = torch.Generator(device="cuda")
+        gi.manual_seed(11)
+        idx = torch.randint(0, nnz, (1 << 17,), device="cuda", generator=gi)
+        rws = torch.searchsorted(ro.long(), idx, right=True) - 1
+        ref64 = (dA[rws].double() * dB[ci[idx].long()].double()).sum(-1)
+        rel = float(((dP[idx].double() - ref64).abs() / ref64.abs().clamp_min(1e-3)).max())
+        check = {"every_entry_written": written, "max_rel_err_sampled_vs_fp64": rel, "samples": 1 << 17}
+        if not written or rel > 1e-3:
+            raise SystemExit("bench: sharded result wrong (written %s, rel err %g)" % (written, rel))
+    # ---- e2e: pinned host buffers through bsmr_sddmm_sharded_host ----
+    hA = torch.empty((n, K), dtype=torch.float32, pin_memory=True)
+    hB = torch.empty((n, K), dtype=torch.float32, pin_memory=True)
+    hA.copy_(dA)
+    hB.copy_(dB)
+    hP = torch.empty(nnz, dtype=torch.float32, pin_memory=True) if rank == 0 else None
+    del dA, dB
+    torch.cuda.empty_cache()
+    e2e_steps = max(2, min(args.steps, 5))
+    plan.sddmm_sharded_host(K, hA, hB, hP)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        et = plan.sddmm_sharded_host(K, hA, hB, hP)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_parts = [None] * world
+    dist.all_gather_object(e2e_parts, et)
+    if rank == 0:
+        gi = torch.Generator(device="cuda")
+        gi.manual_seed(11)
+        idx = torch.randint(0, nnz, (1 << 17,), device="cuda", generator=gi).cpu()
+        if not bool(torch.isfinite(hP[idx]).all()):
+            raise SystemExit("bench: e2e result has unwritten entries")
+        peak, peak_src = peak_hbm()
+        m_nz = int((ro[1:] != ro[:-1]).sum())
+        n_nz = int(torch.unique(ci).numel())
+        bytes_alg = alg_bytes(K, m_nz, n_nz, nnz, n)
+        kern = max(p["kernel_ms"] for p in parts)
+        gather = parts[0]
+        h2d = sum(p["h2d_bytes"] for p in e2e_parts)
+        line = {"metric": METRIC, "value": 2.0 * nnz * K / (ms_per_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32 (CUDA-core residual kernel; tf32 tcgen05 tiles where the plan has any), f32 accumulate",
+                "data": "synthetic", "config": graph8m_config(world), "clocks": clocks,
+                "e2e": {"value": 2.0 * nnz * K / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(nnz * 4),
+                        "how": "bsmr_sddmm_sharded_host, pinned host buffers, %d steps: every rank uploads the A rows of its shard and 1/N of B, "
+                               "ncclAllGather replicates B, kernels, gather-v of P to rank 0, D2H on rank 0 (bytes summed over ranks)" % e2e_steps,
+                        "by_rank_ms": [{k: round(v, 3) for k, v in p.items() if k.endswith("_ms")} for p in e2e_parts],
+                        "allgather_b": {"bytes_received_per_rank": int(e2e_parts[0]["allgather_b_bytes"]), "ms": max(p["allgather_b_ms"] for p in e2e_parts),
+                                        "GB_per_s_per_rank": e2e_parts[0]["allgather_b_bytes"] / (max(p["allgather_b_ms"] for p in e2e_parts) * 1e-3) / 1e9}},
+                "gpu_launches": int(launches),
+                "single_gpu": single,
+                "speedup_vs_single_gpu_same_run": single["ms_per_step"] / ms_per_step,
+                "ms_total_by_rank": [float(x.item()) / steps for x in every],
+                "shards_panels_nnz": sizes,
+                "collective": {"what": "gather-v of P to rank 0: grouped ncclSend / ncclRecv of each rank's contiguous slice (reordered-row order)",
+                               "bytes_into_root": int(gather["gather_p_bytes"]), "ms": gather["gather_p_ms"],
+                               "GB_per_s_into_root": gather["gather_p_bytes"] / (gather["gather_p_ms"] * 1e-3) / 1e9 if gather["gather_p_ms"] > 0 else None,
+                               "pack_ms": max(p["pack_ms"] for p in parts), "unpermute_ms_root": gather["unpermute_ms"]},
+                "breakdown_by_rank_ms": [{k: round(v, 3) for k, v in p.items() if k.endswith("_ms")} for p in parts],
+                "roofline": {"bound": "hbm", "kernel": "residual_rows_kernel (slowest shard)", "algorithmic_bytes_per_launch": int(bytes_alg / world),
+                             "achieved": bytes_alg / world / (kern * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": bytes_alg / world / (kern * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "kernel_ms": kern, "note": "algorithmic bytes of the whole matrix / N over the slowest shard's kernel time"},
+                "cpu_baseline": None,
+                "reorder": {"row_order": "identity, broadcast from rank 0 (%.1f ms)" % bcast_ms, "col_reorder_wall_ms_per_rank": col_wall_ms,
+                            "col_ms": info["col_reordering_ms"], "format_ms": info["format_build_ms"],
+                            "why_recomputed_per_rank": "integer-only and deterministic: %.0f ms on every rank concurrently; shipping the device format "
+                                                       "(~%.1f GB) from one rank would cost that rank's %.0f ms plus the broadcast" %
+                                                       (info["col_reordering_ms"] + info["format_build_ms"], nnz * 33 / 1e9, info["col_reordering_ms"] + info["format_build_ms"]),
+                            "dense_nnz": int(info["num_dense_values"]), "residual_nnz": int(info["num_sparse_values"])},
+                "check": check}
+        emit(line)
+    ctx.comm_destroy()
+    dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ N = 1
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -172,6 +555,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--k", type=int, default=K_DEFAULT)
+    ap.add_argument("--quick", action="store_true", help="headline line only: skip the other configs, the batch and the comparators")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -180,18 +564,19 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if world > 1:
+        run_sharded(args, rank, world, local_rank)
+        return
 
     import torch
-    import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pkg = entry.load_package()
     K = args.k
+    peak, peak_src = peak_hbm()
 
-    M, N, ro, ci, source = load_workload(pkg, world)
+    M, N, ro, ci, source = load_nips(pkg)
     nnz = len(ci)
     A, B = pkg.synth.make_ab(M, N, K)
     # an explicit (non-default) stream shared by torch and the library: the CUDA events below must be
@@ -211,31 +596,13 @@ def main():
         dt = (time.perf_counter() - t0) * 1e3
         reorder_warm_ms = dt if reorder_warm_ms is None else min(reorder_warm_ms, dt)
     info = plan.info()
-    shard_nnz = nnz
-    shard_sizes = None
-    if world > 1:
-        p0s, p1s, shard_nnz = plan.set_shard(rank, world)
-        shard_panels = (p0s, p1s)
-        sizes = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(world)]
-        dist.all_gather(sizes, torch.tensor([p1s - p0s, shard_nnz], dtype=torch.int64, device="cuda"))
-        shard_sizes = [[int(x[0]), int(x[1])] for x in sizes]
 
     dA = torch.from_numpy(A).cuda()
-    dB = torch.empty((N, K), dtype=torch.float32, device="cuda")
-    if world > 1:
-        # B is replicated: produced on rank 0, broadcast over NCCL/NVLink before the clock starts
-        if rank == 0:
-            dB.copy_(torch.from_numpy(B))
-        dist.broadcast(dB, src=0)
-    else:
-        dB.copy_(torch.from_numpy(B))
+    dB = torch.from_numpy(B).cuda()
     dP = torch.zeros(nnz, dtype=torch.float32, device="cuda")
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    # the execution plan for this K is chosen by an explicit measurement (a default call measures nothing)
+    exec_choice = plan.autotune(K, dA, dB, dP)
 
     def step_timed(ev0, ev1):
         flush.fill_(1)                              # L2 flush, outside the timed pair
@@ -246,28 +613,18 @@ def main():
     for _ in range(max(3, args.warmup)):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         step_timed(e0, e1)
-    barrier()
+    torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.start()
     launches0 = ctx.launch_count()
     events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
+    torch.cuda.synchronize()
     for e0, e1 in events:
         step_timed(e0, e1)
-    barrier()
+    torch.cuda.synchronize()
     launches = ctx.launch_count() - launches0
-    exec_choice = plan.execution_choice(K)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
     total_ms = float(sum(e0.elapsed_time(e1) for e0, e1 in events))
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    per_rank_ms = [total_ms / args.steps]
-    if world > 1:
-        every = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(every, t)
-        per_rank_ms = [float(x.item()) / args.steps for x in every]
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
     value = 2.0 * nnz * K / (ms_per_step * 1e-3) / 1e9
 
@@ -292,16 +649,13 @@ def main():
     hPs = [torch.zeros(nnz, dtype=torch.float32).pin_memory() for _ in range(2)]
     hP = hPs[0]
     e2e_steps = max(3, min(args.steps, 20))
-    # N > 1: every rank copies in A and B, runs its shard and copies its P out (the shards are disjoint index sets of the
-    # CSR value array; rows of a shard are scattered over the original matrix, so the copy-out is the whole array).  The
-    # result is left distributed over the ranks' host buffers: no collective on this path either.
     for _ in range(2):
         plan.sddmm_host(K, hA, hB, hP)
-    barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         plan.sddmm_host(K, hA, hB, hP)
-    barrier()
+    torch.cuda.synchronize()
     e2e_serial_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
 
     def pipelined(n):
@@ -310,65 +664,49 @@ def main():
         plan.sddmm_host_wait()
 
     pipelined(4)
-    barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     pipelined(e2e_steps)
-    barrier()
+    torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    t = torch.tensor([e2e_ms, e2e_serial_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms, e2e_serial_ms = float(t[0].item()), float(t[1].item())
     e2e_value = 2.0 * nnz * K / (e2e_ms * 1e-3) / 1e9
     hP = hPs[(e2e_steps - 1) % 2]
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline (rank 0's shard when N > 1) ---------------------------------------------------
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    # which nnz each of the three kernels computes (rank 0's shard when N > 1): the wide kernel owns whole row groups
-    # (256 reordered rows = 16 panels); outside them the BSMR split applies (residual list / dense blocks)
+    # ---- roofline ---------------------------------------------------------------------------------
+    # which nnz each of the three kernels computes: the wide kernel owns whole row groups (256 reordered rows = 16
+    # panels); outside them the BSMR split applies (residual list / dense blocks)
     rows = plan.vector("reordered_rows")
     sv = plan.vector("sparse_values")
-    svo = plan.vector("sparse_value_offsets")
     gw = plan.vector("group_wide").astype(bool)
-    p0, p1 = (0, info["num_row_panels"]) if world == 1 else shard_panels
     row_of = np.repeat(np.arange(M, dtype=np.int64), np.diff(ro.astype(np.int64)))
     pos_of_row = np.full(M, -1, dtype=np.int64)
     pos_of_row[rows] = np.arange(len(rows))
     pos = pos_of_row[row_of]                                   # reordered position of every nnz's row
-    in_shard = (pos >= p0 * 16) & (pos < p1 * 16)
+    use_wide = exec_choice == 0 and info["num_wide_tiles"]
     is_wide = np.zeros(nnz, dtype=bool)
-    if info["num_wide_tiles"]:
-        is_wide = in_shard & gw[np.clip(pos // pkg.WIDE_GROUP_ROWS, 0, len(gw) - 1)]
+    if use_wide:
+        is_wide = gw[np.clip(pos // pkg.WIDE_GROUP_ROWS, 0, len(gw) - 1)]
     is_res = np.zeros(nnz, dtype=bool)
-    is_res[sv[svo[p0]:svo[p1]]] = True
+    is_res[sv] = True
     is_res &= ~is_wide
-    is_blk = in_shard & ~is_wide & ~is_res
+    is_blk = ~is_wide & ~is_res
 
     def part_bytes(mask, extra):
         n = int(mask.sum())
         if n == 0:
             return 0
-        return kernel_alg_bytes(K, len(np.unique(row_of[mask])), len(np.unique(ci[mask])), n, extra)
+        return alg_bytes(K, len(np.unique(row_of[mask])), len(np.unique(ci[mask])), n) + extra * n
 
     parts = [("wide_sddmm_kernel (tcgen05, 256-row groups)", wide_ms, part_bytes(is_wide, 0)),
              ("dense_sddmm_kernel (tcgen05, 16x16 blocks)", dense_ms, part_bytes(is_blk, 0)),
              ("residual_rows_kernel", res_ms, part_bytes(is_res, 8))]
-    step_bytes = pkg.synth.algorithmic_bytes(M, N, K, ro, ci) if world == 1 else sum(x[2] for x in parts)
+    step_bytes = pkg.synth.algorithmic_bytes(M, N, K, ro, ci)
     dom, dom_ms, dom_bytes = max(parts, key=lambda x: x[1])
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     # DRAM bytes per launch of that kernel from the committed ncu --set full capture of this workload, if any
     traffic = tensor_pct = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath) and world == 1:
+    if os.path.exists(tpath):
         committed = json.load(open(tpath))
         traffic = committed.get("K%d" % K, {}).get(dom.split(" ")[0])
         tensor_pct = committed.get("tensor_pipe_active_pct_K%d" % K, {}).get(dom.split(" ")[0])
@@ -380,43 +718,74 @@ def main():
                 "step": {"algorithmic_bytes": int(step_bytes), "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
                          "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak}}
 
-    # ---- CPU baseline: the reference's sddmm_cpu on this box's host cores (rank 0, N = 1 only) ----
-    cpu_baseline = None
-    if world == 1:
-        from oracle.bindings import Oracle, Ref, REF_SO
-        threads = host_threads()
-        if os.path.exists(REF_SO):
-            impl, kind = Ref(), "reference"
-        else:
-            impl, kind = Oracle(), "port"
-        impl.sddmm_cpu(M, N, K, A, B, ro, ci, num_threads=threads)
-        reps = 5
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            Pcpu = impl.sddmm_cpu(M, N, K, A, B, ro, ci, num_threads=threads)
-        cpu_dt = (time.perf_counter() - t0) / reps
-        cpu_baseline = {"value": 2.0 * nnz * K / cpu_dt / 1e9, "unit": UNIT, "cores": threads, "kind": kind,
-                        "sample": "whole workload, %d passes after 1 warm-up (%.1f ms per pass)" % (reps, cpu_dt * 1e3)}
-        # the bench also checks what it timed
-        bad = Oracle().check_data(Pcpu, hP.numpy())
-        if bad:
-            raise SystemExit("bench: %d of %d values outside the reference tolerance" % (bad, nnz))
+    # ---- CPU baseline: the reference's sddmm_cpu on this box's host cores --------------------------
+    from oracle.bindings import Oracle
+    impl, kind = cpu_impl()
+    threads = host_threads()
+    impl.sddmm_cpu(M, N, K, A, B, ro, ci, num_threads=threads)
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        Pcpu = impl.sddmm_cpu(M, N, K, A, B, ro, ci, num_threads=threads)
+    cpu_dt = (time.perf_counter() - t0) / reps
+    cpu_baseline = {"value": 2.0 * nnz * K / cpu_dt / 1e9, "unit": UNIT, "cores": threads, "kind": kind,
+                    "sample": "whole workload, %d passes after 1 warm-up (%.1f ms per pass)" % (reps, cpu_dt * 1e3)}
+    # the bench also checks what it timed
+    bad = Oracle().check_data(Pcpu, hP.numpy())
+    if bad:
+        raise SystemExit("bench: %d of %d values outside the reference tolerance" % (bad, nnz))
+    plan.close()
+    del dA, dB, dP
+    log("headline done: %.1f us per step" % (ms_per_step * 1e3))
+
+    # ---- the other BASELINE configurations, the batch, the comparators ------------------------------
+    configs, batch, comparators = [], None, None
+    if not args.quick:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from graph8m_probe import rmat_device
+        for k in (32, 256):
+            configs.append(measure_config(torch, pkg, ctx, stream, flush, "nips K=%d (configs[%d])" % (k, 0 if k == 32 else 1), M, N, ro, ci, k,
+                                          pkg.ROW_REFERENCE_COMPAT, False, peak))
+            log(configs[-1]["name"])
+        for s in (70, 90, 98):
+            Mm, Nm, rom, cim = pkg.synth.dlmc_mask(s / 100.0)
+            configs.append(measure_config(torch, pkg, ctx, stream, flush, "mask %d %% K=64 (configs[2])" % s, Mm, Nm, rom, cim, 64,
+                                          pkg.ROW_REFERENCE_COMPAT, False, peak))
+            log(configs[-1]["name"])
+            if s == 90:
+                batch = measure_batch(torch, pkg, ctx, stream, flush, Mm, Nm, rom, cim, 64, 16)
+                log("batch")
+        n, rog, cig, rws = rmat_device(torch, GRAPH1M["scale"], GRAPH1M["edges"], seed=GRAPH1M["scale"])
+        del rws
+        configs.append(measure_config(torch, pkg, ctx, stream, flush, "graph 2^20 rows, 3e7 nnz, K=128 (configs[3]), BSMR row order", n, n, rog, cig,
+                                      GRAPH1M["K"], pkg.ROW_REFERENCE_COMPAT, True, peak, steps=6, fp16=True))
+        log(configs[-1]["name"])
+        del rog, cig
+        torch.cuda.empty_cache()
+        n, rog, cig, rws = rmat_device(torch, GRAPH8M["scale"], GRAPH8M["edges"], seed=GRAPH8M["scale"])
+        del rws
+        configs.append(measure_config(torch, pkg, ctx, stream, flush, "graph 2^23 rows, 2.5e8 nnz, K=256 (configs[4]) on 1 GPU, identity row order", n, n,
+                                      rog, cig, GRAPH8M["K"], pkg.ROW_IDENTITY, True, peak, steps=4, fp16=True, e2e_host=2))
+        log(configs[-1]["name"])
+        del rog, cig
+        torch.cuda.empty_cache()
+        pts = [("nips", 32, "cusparse"), ("nips", 32, "bsmr_ref"), ("nips", 128, "cusparse"), ("nips", 128, "bsmr_ref"),
+               ("nips", 256, "cusparse"), ("mask70", 64, "cusparse"), ("mask90", 64, "cusparse"), ("mask90", 64, "bsmr_ref"),
+               ("mask98", 64, "cusparse")]
+        comparators = run_comparators(pts)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "tf32 (tcgen05 wide groups and dense blocks) / f32 (residual), f32 accumulate", "data": "synthetic",
-            "config": workload_config(M, N, nnz, K, source, world),
+            "config": nips_config(M, N, nnz, K, source),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int((M + N) * K * 4) * world, "d2h_bytes_per_step": int(nnz * 4) * world,
+                    "h2d_bytes_per_step": int((M + N) * K * 4), "d2h_bytes_per_step": int(nnz * 4),
                     "how": "bsmr_sddmm_host_submit/_wait, pinned host buffers, 2 steps in flight (copies of neighbouring steps "
-                           "overlap the kernels); %d steps%s" % (e2e_steps, "" if world == 1 else "; every rank copies A, B in and "
-                           "its P out (result left distributed over the ranks, bytes summed over ranks)"),
+                           "overlap the kernels); %d steps" % e2e_steps,
                     "blocking_call_ms": e2e_serial_ms,
                     "blocking_call_value": 2.0 * nnz * K / (e2e_serial_ms * 1e-3) / 1e9},
             "gpu_launches": int(launches),
-            "ms_per_step_by_rank": per_rank_ms,
-            "shards_panels_nnz": shard_sizes,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "reorder": {"row_ms": info["row_reordering_ms"], "col_ms": info["col_reordering_ms"],
@@ -431,13 +800,13 @@ def main():
                                  "residual_nnz_outside_wide": int(info["num_residual_values"]),
                                  "wide_format_ms": info["wide_format_ms"]},
                         "gflops_incl_reorder": 2.0 * nnz * K / ((ms_per_step + reorder_warm_ms) * 1e-3) / 1e9},
-            "execution_plan": ("pinned by BSMR_NO_AUTOTUNE: " if os.environ.get("BSMR_NO_AUTOTUNE") else "") + {0: "wide row groups + BSMR split (three kernels)", 4: "BSMR split (dense blocks + residual)",
-                               2: "CSR-order residual kernel"}.get(exec_choice, "?") + " (chosen by measurement per K)",
+            "execution_plan": PLAN_NAMES.get(exec_choice, "?") + " (chosen by bsmr_plan_autotune, an explicit measurement before the clock starts)",
             "kernels": {"wide_ms_cold": wide_ms, "dense_ms_cold": dense_ms, "residual_ms_cold": res_ms, "step_ms_hot_l2": hot_ms,
-                        "gflops_hot_l2": 2.0 * shard_nnz * K / (hot_ms * 1e-3) / 1e9}}
+                        "gflops_hot_l2": 2.0 * nnz * K / (hot_ms * 1e-3) / 1e9},
+            "configs": configs,
+            "batch": batch,
+            "comparators": comparators}
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import __graft_entry__ as entry  # noqa: E402
-from cases import small_cases  # noqa: E402
+from cases import named_case  # noqa: E402
 from oracle.bindings import Ref  # noqa: E402
 
 
@@ -21,7 +21,7 @@ def main():
     case, K, alpha, delta, bs, out = sys.argv[1], int(sys.argv[2]), float(sys.argv[3]), float(sys.argv[4]), int(sys.argv[5]), sys.argv[6]
     rows_only = len(sys.argv) > 7
     pkg = entry.load_package()
-    name, M, N, ro, ci = [c for c in small_cases(pkg) if c[0] == case][0]
+    name, M, N, ro, ci = named_case(pkg, case)
     ref = Ref()
     if rows_only:
         perm, clusters, ms = ref.row_reordering_gpu(M, N, ro, ci, alpha, bs)
