@@ -144,7 +144,7 @@ int assemble_sharded(bsmr_plan* plan, uint32_t K, const float* dA, const float* 
                      bsmr_shard_times* times, cudaEvent_t* stamps /* 5 events or nullptr */) {
     bsmr_ctx* ctx = plan->ctx;
     const int rank = ctx->comm_rank, world = ctx->comm_world;
-    if (!plan->sharded || plan->shard_world != (uint32_t)world || plan->shard_rank != (uint32_t)rank) {
+    if (!plan->have_format || plan->shard_world != (uint32_t)world || plan->shard_rank != (uint32_t)rank) {
         set_error("sharded SDDMM: call bsmr_plan_set_shard(rank = %d, world = %d) with the communicator's rank / size first", rank, world);
         return BSMR_ERR_BAD_STATE;
     }
@@ -342,7 +342,7 @@ int bsmr_sddmm_sharded_host(bsmr_plan* plan, uint32_t K, const float* hA, const 
         set_error("bsmr_sddmm_sharded_host: the root needs an output buffer");
         return BSMR_ERR_INVALID_ARGUMENT;
     }
-    if (!plan->sharded || plan->shard_world != (uint32_t)world || plan->shard_rank != (uint32_t)rank) {
+    if (!plan->have_format || plan->shard_world != (uint32_t)world || plan->shard_rank != (uint32_t)rank) {
         set_error("bsmr_sddmm_sharded_host: call bsmr_plan_set_shard(rank = %d, world = %d) first", rank, world);
         return BSMR_ERR_BAD_STATE;
     }

@@ -187,8 +187,14 @@ residual_sddmm_kernel(const uint32_t K, const float* __restrict__ A, const BT* _
 
 // Row-sorted fast path.  LPN lanes per entry, KV float4 pieces per lane: K == LPN * 4 * KV.
 // HINT: col_hot is the bitmap of the columns to keep in L2 (bit c of word c / 32), cold_first the policy of the others.
+#ifndef BSMR_RES_OCC
+#define BSMR_RES_OCC 3      // resident CTAs per SM the register budget is set for (probe builds override it)
+#endif
+#ifndef BSMR_RES_UNROLL
+#define BSMR_RES_UNROLL 4   // entries in flight per lane group for KV < 4
+#endif
 template <int LPN, int KV, bool HINT, typename BT>
-__global__ void __launch_bounds__(kResThreads, 3)
+__global__ void __launch_bounds__(kResThreads, BSMR_RES_OCC)
 residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const BT* __restrict__ B,
                      float* __restrict__ P, const uint32_t* __restrict__ res_row,
                      const uint32_t* __restrict__ res_col, const uint32_t* __restrict__ res_out,
@@ -198,7 +204,7 @@ residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const BT* __
     B += blockIdx.y * bs.b;
     P += blockIdx.y * bs.p;
     constexpr int G = 32 / LPN;      // entries in flight per warp instruction
-    constexpr int UNROLL = KV >= 4 ? 2 : 4;
+    constexpr int UNROLL = KV >= 4 ? 2 : BSMR_RES_UNROLL;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t sub = lane / LPN;
     const uint32_t sl = lane % LPN;
@@ -391,7 +397,7 @@ int launch_residual_t(bsmr_ctx* ctx, const ResidualArgs& r) {
     const uint64_t max_ctas = (uint64_t)ctx->sm_count * 8;
     const bool fast_k = K == 32 || K == 64 || K == 128 || K == 256 || K == 512;
     // residual_rows_kernel: 3 resident CTAs per SM (register budget), persistent grid-stride over the chunks
-    const uint64_t cap = fast_k ? (uint64_t)ctx->sm_count * 3 : max_ctas;
+    const uint64_t cap = fast_k ? (uint64_t)ctx->sm_count * BSMR_RES_OCC : max_ctas;
     const uint32_t batch = r.batch ? r.batch : 1u;
     const BatchStride bs{r.stride_a, r.stride_b, r.stride_p};
     const dim3 grid((unsigned)(ctas_needed < cap ? ctas_needed : cap), batch);

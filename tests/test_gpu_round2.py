@@ -31,6 +31,22 @@ def blocks_case(pkg):
     return pkg.synth.block_structured(1000, 2000, seed=11, groups=12, cols_per_group=64)
 
 
+def three_kernel_case(pkg):
+    """300 rows at 12 % density (a wide row group) on top of 1000 block-structured rows (dense 16 x 16 blocks + residual
+    after clustering): the default plan runs all three kernels on it."""
+    rng = np.random.default_rng(21)
+    N = 3000
+    top = []
+    for r in range(300):
+        n = max(1, int(rng.binomial(N, 0.12)))
+        top.append(np.sort(rng.choice(N, size=n, replace=False)).astype(np.uint32))
+    M2, _, ro2, ci2 = pkg.synth.block_structured(1000, N, seed=11, groups=12, cols_per_group=64, noise=0.002)
+    ro = np.zeros(300 + M2 + 1, dtype=np.int64)
+    ro[1:301] = np.cumsum([len(r) for r in top])
+    ro[301:] = ro[300] + ro2[1:].astype(np.int64)
+    return 300 + M2, N, ro.astype(np.uint32), np.concatenate(top + [ci2])
+
+
 def rel_err(got, want):
     return float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-3)))
 
@@ -150,17 +166,16 @@ def test_batched_launch_is_bit_identical_to_single_calls(pkg, ctx, oracle, K, fl
     single calls; element 3 is also checked against the oracle."""
     import torch
     flags = getattr(pkg, flags_name)
-    M, N, ro, ci = blocks_case(pkg)
+    M, N, ro, ci = three_kernel_case(pkg)
     nb = 9
     rng = np.random.Generator(np.random.Philox(77))
     A = (rng.random((nb, M, K), dtype=np.float32) * 2).astype(np.float32)
     B = (rng.random((nb, N, K), dtype=np.float32) * 2).astype(np.float32)
     plan = pkg.Plan(ctx, M, N, ro, ci)
-    plan.set_wide_ratio(1.0)                   # small matrix: lower the bar so that all three kernels have work
     plan.reorder(0.3, 0.3, block_size=16)
     info = plan.info()
     if flags == pkg.SDDMM_THREE_KERNEL and K % 32 == 0:
-        assert info["num_wide_tiles"] > 0 and info["num_block_tiles"] > 0 and info["num_residual_values"] > 0
+        assert info["num_wide_tiles"] > 0 and info["num_block_tiles"] > 0 and info["num_residual_values"] > 0, info
     dA, dB = torch_dev(A), torch_dev(B)
     nnz = len(ci)
     single = torch.full((nb, nnz), float("nan"), device="cuda")
