@@ -52,6 +52,14 @@ def main():
                 d["d%02d_%s" % (int(delta * 10), k)] = c[k]
         np.savez_compressed(os.path.join(out, name + ".npz"), **d)
         print("wrote", name, "gpu" if gpu else "cpu-only")
+    if gpu:
+        # BASELINE configs[0]/[1] at full size: nb = 777 column blocks -> 7 warps in the reference's clustering CTA, the
+        # lossy block reduction.  Only the outputs are stored; the input is synth.nips_like().
+        M, N, ro, ci = pkg.synth.nips_like()
+        perm, clusters, _ = ref.row_reordering_gpu(M, N, ro, ci, alpha, block_size)
+        np.savez_compressed(os.path.join(out, "nips_perm_ref_gpu.npz"), perm_ref_gpu=perm, num_clusters=clusters, alpha=alpha,
+                            block_size=block_size, input_checksum=np.uint64(int(ci.astype(np.uint64).sum()) * 1000003 + int(ro.astype(np.uint64).sum())))
+        print("wrote nips_perm_ref_gpu")
 
 
 if __name__ == "__main__":

@@ -86,7 +86,7 @@ def test_mtx_loader_rejections(oracle, ref, tmp_path):
 
 def test_golden_fixtures(pkg, oracle, golden_dir):
     """Fixtures produced by the reference library (tests/golden/make_golden.py); they travel to the GPU box."""
-    files = sorted(f for f in os.listdir(golden_dir) if f.endswith(".npz"))
+    files = sorted(f for f in os.listdir(golden_dir) if f.endswith(".npz") and f != "nips_perm_ref_gpu.npz")
     assert files, "no golden fixtures committed"
     for f in files:
         g = np.load(os.path.join(golden_dir, f))
@@ -159,3 +159,30 @@ def test_randomised_shapes_against_reference(pkg, oracle, ref):
         K = int(rng.choice([1, 3, 32, 50, 64]))
         A, B = pkg.synth.make_ab(M, N, K, seed=case)
         assert np.array_equal(oracle.sddmm_cpu(M, N, K, A, B, ro, ci), ref.sddmm_cpu(M, N, K, A, B, ro, ci)), (case, K)
+
+
+def test_indexed_restatement_equals_dense_restatement(pkg, oracle):
+    """oracle_row_reordering_indexed (sparse encodings, rows filed per column block: the checker at graph scale) gives the
+    permutation of oracle_row_reordering (the dense restatement pinned to the reference) -- with and without the filter
+    that leaves the most popular blocks out, lossy and exact reduction."""
+    for name, M, N, ro, ci in small_cases(pkg):
+        for alpha in (0.1, 0.3, 0.7):
+            for bs in (16, 37):
+                for exact in (False, True):
+                    want = oracle.row_reordering(M, N, ro, ci, alpha, bs, exact)
+                    for filt in (True, False):
+                        got = oracle.row_reordering_indexed(M, N, ro, ci, alpha, bs, exact, filt)
+                        assert np.array_equal(got[0], want[0]) and got[1:] == want[1:], (name, alpha, bs, exact, filt)
+
+
+def test_nips_permutation_golden(pkg, oracle, golden_dir):
+    """The row permutation the reference's own GPU code produced on a B200 for the nips-shaped matrix (nb = 777 column
+    blocks -> 7 warps -> the lossy reduction of include/cudaUtil.cuh:27-45), against the sparse restatement of the oracle."""
+    path = os.path.join(golden_dir, "nips_perm_ref_gpu.npz")
+    if not os.path.exists(path):
+        pytest.skip("nips_perm_ref_gpu.npz not generated yet (tests/golden/make_golden.py --gpu on the B200 box)")
+    g = np.load(path)
+    M, N, ro, ci = pkg.synth.nips_like()
+    assert int(g["input_checksum"]) == int(ci.astype(np.uint64).sum()) * 1000003 + int(ro.astype(np.uint64).sum())
+    perm, compat, _ = oracle.row_reordering_indexed(M, N, ro, ci, float(g["alpha"]), int(g["block_size"]))
+    assert np.array_equal(perm, g["perm_ref_gpu"]) and compat == int(g["num_clusters"])
