@@ -88,6 +88,23 @@ def lib():
                 path + " is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU fallback)")
         L = C.CDLL(path)
+        if path != LIB_PATH:
+            # a probe build may predate part of the ABI (A/B runs against an older library): missing entry points raise
+            # when they are called, not when the library is loaded
+            class _Tolerant:
+                def __init__(self, lib):
+                    object.__setattr__(self, "_lib", lib)
+
+                def __getattr__(self, name):
+                    try:
+                        return getattr(self._lib, name)
+                    except AttributeError:
+                        def missing(*a, **k):
+                            raise AttributeError(path + " does not export " + name)
+                        missing.argtypes = missing.restype = None
+                        object.__setattr__(self, name, missing)
+                        return missing
+            L = _Tolerant(L)
         vp, cp = C.c_void_p, C.c_char_p
         L.bsmr_version.restype = cp
         L.bsmr_last_error.restype = cp

@@ -188,11 +188,46 @@ residual_sddmm_kernel(const uint32_t K, const float* __restrict__ A, const BT* _
 // Row-sorted fast path.  LPN lanes per entry, KV float4 pieces per lane: K == LPN * 4 * KV.
 // HINT: col_hot is the bitmap of the columns to keep in L2 (bit c of word c / 32), cold_first the policy of the others.
 #ifndef BSMR_RES_OCC
-#define BSMR_RES_OCC 3      // resident CTAs per SM the register budget is set for (probe builds override it)
+#define BSMR_RES_OCC 4      // resident CTAs per SM the register budget is set for (64 registers; measured against 3 and 5)
 #endif
 #ifndef BSMR_RES_UNROLL
 #define BSMR_RES_UNROLL 4   // entries in flight per lane group for KV < 4
 #endif
+#ifndef BSMR_RES_K128_LPN
+#define BSMR_RES_K128_LPN 32   // lanes per entry of the fp32 kernel at K = 128 (32: one 16-byte piece per lane; 16: two)
+#endif
+
+// One 16-byte piece of a B column per lane: 4 fp32 or 8 fp16 values.
+template <typename BT> struct BPiece;
+template <> struct BPiece<float> {
+    static constexpr int EP = 4;                  // elements of K per piece
+    using Raw = float4;
+    static __device__ __forceinline__ Raw load(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+    static __device__ __forceinline__ Raw load_hint(const float* p, uint64_t pol) { return ldg4_hint(p, pol); }
+    static __device__ __forceinline__ float dot(const float4* a, const Raw& b, float acc) { return dot4(a[0], b, acc); }
+};
+template <> struct BPiece<__half> {
+    static constexpr int EP = 8;
+    using Raw = uint4;
+    static __device__ __forceinline__ Raw load(const __half* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+    static __device__ __forceinline__ Raw load_hint(const __half* p, uint64_t pol) {
+        uint4 v;
+        asm("ld.global.nc.L2::cache_hint.v4.b32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+        return v;
+    }
+    static __device__ __forceinline__ float dot(const float4* a, const Raw& b, float acc) {
+        const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&b.x)), b1 = __half22float2(*reinterpret_cast<const __half2*>(&b.y));
+        const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&b.z)), b3 = __half22float2(*reinterpret_cast<const __half2*>(&b.w));
+        acc = dot4(a[0], make_float4(b0.x, b0.y, b1.x, b1.y), acc);
+        return dot4(a[1], make_float4(b2.x, b2.y, b3.x, b3.y), acc);
+    }
+};
+
+// Row-sorted fast path.  LPN lanes per entry, KV 16-byte pieces of the B column per lane: K == LPN * EP * KV with EP = 4
+// (fp32 B) or 8 (fp16 B) elements per piece.  The kernel is bound by instruction issue as much as by the gather (ncu:
+// no unit above 66 %, 13 cycles per entry and SM at K = 128), so the fewer lanes an entry takes the better: at K = 128 a
+// 16-lane group (two fp32 pieces, or one fp16 piece per lane) handles two entries per warp instruction.
+// HINT: col_hot is the bitmap of the columns to keep in L2 (bit c of word c / 32), cold_first the policy of the others.
 template <int LPN, int KV, bool HINT, typename BT>
 __global__ void __launch_bounds__(kResThreads, BSMR_RES_OCC)
 residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const BT* __restrict__ B,
@@ -203,8 +238,13 @@ residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const BT* __
     A += blockIdx.y * bs.a;
     B += blockIdx.y * bs.b;
     P += blockIdx.y * bs.p;
+    using BP = BPiece<BT>;
+    constexpr int EP = BP::EP;
+    constexpr int AP = EP / 4;       // float4 pieces of the A row per piece of B
     constexpr int G = 32 / LPN;      // entries in flight per warp instruction
-    constexpr int UNROLL = KV >= 4 ? 2 : BSMR_RES_UNROLL;
+    constexpr int H = LPN / 2;
+    constexpr int UNROLL0 = KV * AP >= 4 ? 2 : BSMR_RES_UNROLL;
+    constexpr int UNROLL = UNROLL0 > 2 * H ? 2 * H : UNROLL0;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t sub = lane / LPN;
     const uint32_t sl = lane % LPN;
@@ -213,9 +253,11 @@ residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const BT* __
     const uint64_t warp_stride = (uint64_t)gridDim.x * kWarpsPerCta;
 
     uint32_t cur_row = 0xFFFFFFFFu;
-    float4 a_cur[KV];
+    float4 a_cur[KV][AP];
 #pragma unroll
-    for (int v = 0; v < KV; ++v) a_cur[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int v = 0; v < KV; ++v)
+#pragma unroll
+        for (int j = 0; j < AP; ++j) a_cur[v][j] = make_float4(0.f, 0.f, 0.f, 0.f);
     uint64_t pol_hot = 0, pol_cold = 0, pol_stream = 0;
     if constexpr (HINT) {
         pol_hot = l2_policy_evict_last();
@@ -238,16 +280,15 @@ residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const BT* __
             my_col = __ldg(res_col + es);
             my_out = res_out ? __ldg(res_out + es) : (uint32_t)es;   // NULL = identity (CSR order)
         }
-        // Pass s (s = 0..ITERS-1, entries in list order so that the A row in registers is reused) fills
+        // Pass s (s = 0..LPN-1, entries in list order so that the A row in registers is reused) fills
         // accumulator slot it(s) = (s >> 1) + (s & 1) * H: the two passes of a pair (i, i + H) are adjacent,
         // and the first butterfly step (offset H) is folded in as soon as both are known, which keeps only
         // H accumulators live.
-        constexpr int H = LPN / 2;
         float q[H];
         const bool upper0 = (sl & H) != 0;
 #pragma unroll
         for (int i0 = 0; i0 < H; i0 += UNROLL / 2) {
-            float4 bv[UNROLL][KV];
+            typename BP::Raw bv[UNROLL][KV];
             uint32_t rows_u[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
@@ -255,31 +296,34 @@ residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const BT* __
                 const int j = s_pass * G + sub;           // entry handled by this group in that pass
                 rows_u[u] = __shfl_sync(0xffffffffu, my_row, j);
                 const uint32_t col = __shfl_sync(0xffffffffu, my_col, j);
-                const BT* bp = B + (size_t)col * K + sl * 4;
+                const BT* bp = B + (size_t)col * K + sl * EP;
                 if constexpr (HINT) {
                     // the policy operand travels in a uniform register: one priority per warp instruction (with LPN < 32
                     // the G entries of a pass share it: hot if any of them is)
                     const uint32_t hot_j = __shfl_sync(0xffffffffu, my_hot, j);
                     const uint64_t pol = (LPN == 32 ? hot_j != 0 : __any_sync(0xffffffffu, hot_j != 0)) ? pol_hot : pol_cold;
 #pragma unroll
-                    for (int v = 0; v < KV; ++v) bv[u][v] = ldb4_hint<BT>(bp + v * LPN * 4, pol);
+                    for (int v = 0; v < KV; ++v) bv[u][v] = BP::load_hint(bp + v * LPN * EP, pol);
                 } else {
 #pragma unroll
-                    for (int v = 0; v < KV; ++v) bv[u][v] = ldb4<BT>(bp + v * LPN * 4);
+                    for (int v = 0; v < KV; ++v) bv[u][v] = BP::load(bp + v * LPN * EP);
                 }
             }
             float d[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 if (rows_u[u] != cur_row) {              // uniform inside the group (warp-uniform for LPN == 32)
-                    const float* ap = A + (size_t)rows_u[u] * K + sl * 4;
+                    const float* ap = A + (size_t)rows_u[u] * K + sl * EP;
 #pragma unroll
-                    for (int v = 0; v < KV; ++v) a_cur[v] = HINT ? ldg4_hint(ap + v * LPN * 4, pol_stream) : ldg4(ap + v * LPN * 4);
+                    for (int v = 0; v < KV; ++v)
+#pragma unroll
+                        for (int j = 0; j < AP; ++j)
+                            a_cur[v][j] = HINT ? ldg4_hint(ap + v * LPN * EP + 4 * j, pol_stream) : ldg4(ap + v * LPN * EP + 4 * j);
                     cur_row = rows_u[u];
                 }
                 float acc = 0.f;
 #pragma unroll
-                for (int v = 0; v < KV; ++v) acc = dot4(a_cur[v], bv[u][v], acc);
+                for (int v = 0; v < KV; ++v) acc = BP::dot(a_cur[v], bv[u][v], acc);
                 d[u] = acc;
             }
 #pragma unroll
@@ -402,33 +446,40 @@ int launch_residual_t(bsmr_ctx* ctx, const ResidualArgs& r) {
     const BatchStride bs{r.stride_a, r.stride_b, r.stride_p};
     const dim3 grid((unsigned)(ctas_needed < cap ? ctas_needed : cap), batch);
     // 128-bit loads of A, 128-bit (fp32) / 64-bit (fp16) loads of B: every batch element must keep that alignment
-    const size_t b_align = sizeof(BT) * 4;
-    const bool aligned = (K % 4 == 0) && (reinterpret_cast<uintptr_t>(dA) % 16 == 0) && (reinterpret_cast<uintptr_t>(dB) % b_align == 0) &&
+    const size_t b_align = 16;
+    const bool aligned = (K % (16 / sizeof(BT)) == 0 || !fast_k) && (K % 4 == 0) && (reinterpret_cast<uintptr_t>(dA) % 16 == 0) && (reinterpret_cast<uintptr_t>(dB) % b_align == 0) &&
                          (batch == 1 || ((r.stride_a * sizeof(float)) % 16 == 0 && (r.stride_b * sizeof(BT)) % b_align == 0));
     cudaStream_t st = r.stream;
 #define BSMR_ROWS(LPN, KV, HINT) \
     residual_rows_kernel<LPN, KV, HINT, BT><<<grid, kResThreads, 0, st>>>(K, dA, dB, r.P, r.row, r.col, r.out, begin, end, bs, r.col_hot, r.cold_first)
+    // lanes per entry x 16-byte pieces per lane: K = LPN * EP * KV (EP = 4 fp32 / 8 fp16 elements per piece).  As few lanes
+    // per entry as keeps a piece a full 16 bytes: more entries per warp instruction (the kernel is issue-bound at small K)
+    constexpr bool kHalf = sizeof(BT) == 2;
+#define BSMR_ROWS_K(HINT)                                                                  \
+    do {                                                                                   \
+        if constexpr (kHalf) {                                                             \
+            if (K == 32) BSMR_ROWS(4, 1, HINT);                                            \
+            else if (K == 64) BSMR_ROWS(8, 1, HINT);                                       \
+            else if (K == 128) BSMR_ROWS(16, 1, HINT);                                     \
+            else if (K == 256) BSMR_ROWS(32, 1, HINT);                                     \
+            else BSMR_ROWS(32, 2, HINT);                                                   \
+        } else {                                                                           \
+            if (K == 32) BSMR_ROWS(8, 1, HINT);                                            \
+            else if (K == 64) BSMR_ROWS(16, 1, HINT);                                      \
+            else if (K == 128) BSMR_ROWS(BSMR_RES_K128_LPN, 128 / (BSMR_RES_K128_LPN * 4), HINT); \
+            else if (K == 256) BSMR_ROWS(32, 2, HINT);                                     \
+            else BSMR_ROWS(32, 4, HINT);                                                   \
+        }                                                                                  \
+    } while (0)
     if (!aligned) {
         const uint64_t need = (end - begin + kWarpsPerCta - 1) / kWarpsPerCta;
         const dim3 g((unsigned)(need < max_ctas ? need : max_ctas), batch);
         residual_sddmm_generic_kernel<BT><<<g, kResThreads, 0, st>>>(K, dA, dB, r.P, r.row, r.col, r.out, begin, end, bs);
     } else if (fast_k && r.col_hot) {
         // hub columns pinned in L2 (hot_columns below): same kernel, loads and stores carry L2 eviction priorities
-        if (K == 32) BSMR_ROWS(8, 1, true);
-        else if (K == 64) BSMR_ROWS(16, 1, true);
-        else if (K == 128) BSMR_ROWS(32, 1, true);
-        else if (K == 256) BSMR_ROWS(32, 2, true);
-        else BSMR_ROWS(32, 4, true);
-    } else if (K == 32) {
-        BSMR_ROWS(8, 1, false);
-    } else if (K == 64) {
-        BSMR_ROWS(16, 1, false);
-    } else if (K == 128) {
-        BSMR_ROWS(32, 1, false);
-    } else if (K == 256) {
-        BSMR_ROWS(32, 2, false);
-    } else if (K == 512) {
-        BSMR_ROWS(32, 4, false);
+        BSMR_ROWS_K(true);
+    } else if (fast_k) {
+        BSMR_ROWS_K(false);
     } else if (K < 64) {
         residual_sddmm_kernel<8, 0, 2, BT><<<grid, kResThreads, 0, st>>>(K, dA, dB, r.P, r.row, r.col, r.out, begin, end, bs);
     } else if (K < 128) {
@@ -436,6 +487,7 @@ int launch_residual_t(bsmr_ctx* ctx, const ResidualArgs& r) {
     } else {
         residual_sddmm_kernel<32, 0, 2, BT><<<grid, kResThreads, 0, st>>>(K, dA, dB, r.P, r.row, r.col, r.out, begin, end, bs);
     }
+#undef BSMR_ROWS_K
 #undef BSMR_ROWS
     ctx->launches++;
     BSMR_CUDA_OK(cudaGetLastError());

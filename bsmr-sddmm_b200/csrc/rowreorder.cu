@@ -66,18 +66,15 @@ __global__ void enc_keys_kernel(uint32_t M, const uint32_t* __restrict__ row_off
 }
 
 // enc_blk[u] = column block of run u; runs per row counted with one atomic per (warp, distinct row)
-__global__ void runs_split_kernel(const uint64_t* __restrict__ ukeys, const uint32_t* __restrict__ counts, uint32_t num_runs,
-                                  uint32_t* __restrict__ enc_blk, uint2* __restrict__ enc_pair, uint32_t* __restrict__ runs_per_row) {
+__global__ void runs_split_kernel(const uint64_t* __restrict__ ukeys, uint32_t num_runs, uint32_t* __restrict__ enc_blk,
+                                  uint32_t* __restrict__ runs_per_row) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t n32 = ((uint64_t)num_runs + 31) & ~31ull;
     for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n32; u += (uint64_t)gridDim.x * blockDim.x) {
         const bool valid = u < num_runs;
         const uint64_t key = valid ? ukeys[u] : ~0ull;
         const uint32_t row = (uint32_t)(key >> 32);
-        if (valid) {
-            enc_blk[u] = (uint32_t)(key & 0xffffffffull);
-            enc_pair[u] = make_uint2((uint32_t)(key & 0xffffffffull), counts[u]);    // what the clustering kernel stages per candidate
-        }
+        if (valid) enc_blk[u] = (uint32_t)(key & 0xffffffffull);
         const uint32_t peers = __match_any_sync(0xffffffffu, row);
         if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(runs_per_row + row, (uint32_t)__popc(peers));
     }
@@ -171,8 +168,6 @@ struct ClusterParams {
     const uint32_t* enc_ptr;   // row -> first run
     const uint32_t* enc_blk;   // run -> column block (ascending inside a row)
     const uint32_t* counts;    // run -> nnz in the block
-    const uint2* enc_pair;     // run -> {column block, nnz in the block}: the two arrays above interleaved (staged with cp.async)
-    uint32_t stage_entries;    // runs of every candidate of a step prefetched into shared memory (0 = no staging)
     const uint32_t* row_sq;    // row -> (lossy) sum of squares
     const uint4* pos_info;     // position -> {row, first run, end run, (lossy) sum of squares}
     uint32_t* cluster_ids;     // position -> cluster id (pre-set: 0 for empty rows, NULL otherwise)
@@ -234,18 +229,13 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
 // A candidate that shares no column block with the representative has min-sum 0, i.e. similarity 0 <= alpha, and is
 // rejected after one pass over its block list (alpha >= 0 only).
 __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(ClusterParams p) {
-    extern __shared__ __align__(16) uint32_t smem[];
+    extern __shared__ uint32_t smem[];
     uint32_t* rep = smem;                                        // [nb]  representative encoding
     float* repn = reinterpret_cast<float*>(smem + p.nb);         // [nb]  (float)rep / norm_rep
     float* part_max = repn + p.nb;                               // [1024] per-reference-thread max partial of the representative alone
     float* warp_max = part_max + 1024;                           // [32]  the same after the warp butterfly
     // per evaluating warp: the candidate's encoding expanded to nb 16-bit counts (only when p.scratch != 0)
     uint16_t* scratch = reinterpret_cast<uint16_t*>(warp_max + 32) + (size_t)(threadIdx.x >> 5) * p.scratch;
-    // per evaluating warp: the first stage_entries {block, count} runs of each of the (up to kMaxCpw) candidates of a step,
-    // fetched with cp.async BEFORE any of them is evaluated.  Without it a warp walked its candidates one global round
-    // trip after the other (measured at 2^20 rows: 5 000 cycles per candidate, 64 s for 3.5e5 clusters); with it the loads
-    // of a whole step are one round trip.  (Registers cannot hold them: 1024 threads leave 64 each.)
-    uint2* stage_base = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(warp_max + 32) + (size_t)32 * p.scratch);
     __shared__ uint32_t s_sq_rep;
     __shared__ unsigned long long s_ctrl;
     __shared__ uint32_t s_joined[2][8];    // bit k: candidate k of the step joins (up to 256 candidates); double buffered
@@ -261,7 +251,6 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
     const float bound = p.alpha - 1e-3f;
     constexpr uint32_t kMaxCpw = 8;
     constexpr uint32_t kWarps = kClusterThreads / 32;
-    uint2* const stage = p.stage_entries ? stage_base + (size_t)wid * kMaxCpw * p.stage_entries : nullptr;
 
     // everything derived from `rep`; called by the whole CTA after rep changed (rep complete and visible on entry)
     auto refresh = [&]() {
@@ -306,7 +295,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
     // run of consecutive joins.
     uint32_t c_idx = 0xFFFFFFFFu, c_touched = 0, c_pos = 0;
     uint4 c_info = make_uint4(0, 0, 0, 0);
-    auto evaluate = [&](const uint4 info, const uint32_t x, const uint2* __restrict__ st) -> bool {
+    auto evaluate = [&](const uint4 info, const uint32_t x) -> bool {
         const uint32_t b = info.y, e = info.z, s_cmp = info.w;
         const uint32_t s_rep = s_sq_rep;
         if (s_rep == 0 && s_cmp == 0) return 1.0f > p.alpha;       // :258-260
@@ -317,11 +306,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
         if (n <= 32) {
             // ---- short block list: patch only the reference threads that own one of the row's blocks ----
             const bool valid = lane < n;
-            uint32_t blk = 0u, cnt = 0u;
-            if (valid) {
-                if (st) { const uint2 pr = st[lane]; blk = pr.x; cnt = pr.y; }
-                else { blk = p.enc_blk[b + lane]; cnt = p.counts[b + lane]; }
-            }
+            const uint32_t blk = valid ? p.enc_blk[b + lane] : 0u;
+            const uint32_t cnt = valid ? p.counts[b + lane] : 0u;
             const uint32_t t = blk % p.bd;
             const bool kept = valid && ((p.kept_mask >> (t >> 5)) & 1u);
             if (prune) {
@@ -396,14 +382,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {                // four independent loads in flight per array
                     const uint32_t j = j0 + 32 * u;
-                    if (st && j - b < p.stage_entries) {       // staged before the step's evaluations started
-                        const uint2 pr = j < e ? st[j - b] : make_uint2(0xFFFFFFFFu, 0u);
-                        blk4[u] = pr.x;
-                        cnt4[u] = pr.y;
-                    } else {
-                        blk4[u] = j < e ? __ldg(p.enc_blk + j) : 0xFFFFFFFFu;
-                        cnt4[u] = j < e ? __ldg(p.counts + j) : 0u;
-                    }
+                    blk4[u] = j < e ? __ldg(p.enc_blk + j) : 0xFFFFFFFFu;
+                    cnt4[u] = j < e ? __ldg(p.counts + j) : 0u;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -623,26 +603,11 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
 #pragma unroll
             for (uint32_t q = 0; q < kMaxCpw; ++q)
                 if (my_pos[q] != 0xFFFFFFFFu) my_info[q] = (q == 0 && hit0) ? c_info : __ldg(p.pos_info + my_pos[q]);
-            if (stage) {
-#pragma unroll
-                for (uint32_t q = 0; q < kMaxCpw; ++q) {
-                    if (my_pos[q] != 0xFFFFFFFFu) {
-                        const uint32_t b = my_info[q].y;
-                        const uint32_t n = min(my_info[q].z - b, p.stage_entries);
-                        for (uint32_t i = lane; i < n; i += 32)
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(stage + q * p.stage_entries + i)),
-                                         "l"(p.enc_pair + b + i) : "memory");
-                    }
-                }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                __syncwarp();
-            }
 #pragma unroll
             for (uint32_t q = 0; q < kMaxCpw; ++q) {
                 if (my_pos[q] != 0xFFFFFFFFu) {
                     const uint32_t k = q * kWarps + k0;
-                    const bool joins = evaluate(my_info[q], cursor + k, stage ? stage + q * p.stage_entries : nullptr);
+                    const bool joins = evaluate(my_info[q], cursor + k);
                     if (c_idx == cursor + k) {                 // evaluate() left this candidate in the scratch
                         c_pos = my_pos[q];
                         c_info = my_info[q];
@@ -810,13 +775,8 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
         const uint32_t scratch_entries = (nb + 7u) & ~7u;
         const size_t base_smem = (static_cast<size_t>(nb) * 2 + 1024 + 32) * 4;
         const bool use_scratch = block_size <= 65535u && base_smem + static_cast<size_t>(scratch_entries) * 2 * 32 <= 200 * 1024;
-        const size_t smem_wo_stage = base_smem + (use_scratch ? static_cast<size_t>(scratch_entries) * 2 * 32 : 0);
-        // staged candidate runs: 32 warps x 8 candidates x stage_entries x 8 bytes (128 KB at 64 entries), when they fit
-        uint32_t stage_entries = 0;
-        for (uint32_t cand : {64u, 32u})
-            if (stage_entries == 0 && smem_wo_stage + static_cast<size_t>(32) * 8 * cand * 8 <= 224 * 1024) stage_entries = cand;
-        const size_t smem = smem_wo_stage + static_cast<size_t>(32) * 8 * stage_entries * 8;
-        if (smem_wo_stage > 200 * 1024) {
+        const size_t smem = base_smem + (use_scratch ? static_cast<size_t>(scratch_entries) * 2 * 32 : 0);
+        if (smem > 200 * 1024) {
             set_error("row reorder: %u column blocks need %zu bytes of shared memory; raise block_size", nb, smem);
             return BSMR_ERR_UNSUPPORTED;
         }
@@ -829,7 +789,6 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
         // ---- sparse encodings ----
         TmpBuf<uint64_t> keys_a(ws), keys_b(ws), ukeys(ws);
         TmpBuf<uint32_t> counts(ws), num_runs_d(ws), runs_per_row(ws), enc_ptr(ws), disp(ws), row_sq(ws), enc_blk(ws);
-        TmpBuf<uint2> enc_pair(ws);
         BSMR_TRY(runs_per_row.alloc(static_cast<size_t>(M) + 1));
         BSMR_TRY(enc_ptr.alloc(static_cast<size_t>(M) + 1));
         BSMR_TRY(disp.alloc(M ? M : 1));
@@ -857,8 +816,7 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
             BSMR_CUDA_OK(cudaMemcpyAsync(&num_runs, num_runs_d.ptr, 4, cudaMemcpyDeviceToHost, st));
             BSMR_CUDA_OK(cudaStreamSynchronize(st));
             BSMR_TRY(enc_blk.alloc(num_runs));
-            BSMR_TRY(enc_pair.alloc(num_runs));
-            runs_split_kernel<<<grid_for(num_runs, kThreads, sm), kThreads, 0, st>>>(ukeys.ptr, counts.ptr, num_runs, enc_blk.ptr, enc_pair.ptr, runs_per_row.ptr);
+            runs_split_kernel<<<grid_for(num_runs, kThreads, sm), kThreads, 0, st>>>(ukeys.ptr, num_runs, enc_blk.ptr, runs_per_row.ptr);
             ctx->launches++;
         }
         {
@@ -936,7 +894,6 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
             cp.M = M; cp.nb = nb; cp.bd = bd; cp.first_stride = first_stride; cp.zero_rows = zero_rows; cp.alpha = alpha;
             cp.list_cap = list_cap; cp.num_slots = num_slots;
             cp.asc = asc; cp.enc_ptr = enc_ptr.ptr; cp.enc_blk = enc_blk.ptr; cp.counts = counts.ptr; cp.row_sq = row_sq.ptr;
-            cp.enc_pair = enc_pair.ptr; cp.stage_entries = stage_entries;
             cp.cluster_ids = cluster_ids.ptr; cp.lists = lists.ptr; cp.ctrl = ctrl.ptr; cp.status = status.ptr;
             void* args[] = {&cp};
             BSMR_CUDA_OK(cudaEventRecord(ctx->ev0, st));

@@ -172,6 +172,7 @@ def test_batched_launch_is_bit_identical_to_single_calls(pkg, ctx, oracle, K, fl
     A = (rng.random((nb, M, K), dtype=np.float32) * 2).astype(np.float32)
     B = (rng.random((nb, N, K), dtype=np.float32) * 2).astype(np.float32)
     plan = pkg.Plan(ctx, M, N, ro, ci)
+    plan.set_wide_ratio(8.0)                   # the 12 % rows qualify for the wide kernel, the block-structured rows do not
     plan.reorder(0.3, 0.3, block_size=16)
     info = plan.info()
     if flags == pkg.SDDMM_THREE_KERNEL and K % 32 == 0:
@@ -237,7 +238,7 @@ def test_sddmm_f16b_within_the_reference_tolerance(pkg, ctx, oracle, K):
         plan.sddmm(K, dA, dBq, p32, flags=pkg.SDDMM_NO_REORDER)
         plan.sddmm_f16b(K, dA, dBq.half(), p16, flags=pkg.SDDMM_NO_REORDER)
         torch.cuda.synchronize()
-        assert torch.equal(p32, p16), (name, K)
+        assert float((p32 - p16).abs().max() / p32.abs().max()) < 2e-6, (name, K)    # same products, other summation tree (8 instead of 4 k per lane)
         plan.close()
 
 
