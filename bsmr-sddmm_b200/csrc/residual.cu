@@ -194,7 +194,11 @@ residual_sddmm_kernel(const uint32_t K, const float* __restrict__ A, const BT* _
 #define BSMR_RES_UNROLL 4   // entries in flight per lane group for KV < 4
 #endif
 #ifndef BSMR_RES_K128_LPN
-#define BSMR_RES_K128_LPN 32   // lanes per entry of the fp32 kernel at K = 128 (32: one 16-byte piece per lane; 16: two)
+#define BSMR_RES_K128_LPN 16   // lanes per entry of the fp32 kernel at K = 128: two 16-byte pieces per lane (measured against 32 x one:
+                               // 1.20 against 1.35 ms on the 2^20-row graph, 34.8 against 38.9 us on nips)
+#endif
+#ifndef BSMR_RES_HALVE_LANES
+#define BSMR_RES_HALVE_LANES 0  // probe builds: 1 = half the lanes / twice the pieces per lane at the other K as well
 #endif
 
 // One 16-byte piece of a B column per lane: 4 fp32 or 8 fp16 values.
@@ -459,15 +463,15 @@ int launch_residual_t(bsmr_ctx* ctx, const ResidualArgs& r) {
     do {                                                                                   \
         if constexpr (kHalf) {                                                             \
             if (K == 32) BSMR_ROWS(4, 1, HINT);                                            \
-            else if (K == 64) BSMR_ROWS(8, 1, HINT);                                       \
+            else if (K == 64) { if (BSMR_RES_HALVE_LANES) BSMR_ROWS(4, 2, HINT); else BSMR_ROWS(8, 1, HINT); } \
             else if (K == 128) BSMR_ROWS(16, 1, HINT);                                     \
-            else if (K == 256) BSMR_ROWS(32, 1, HINT);                                     \
+            else if (K == 256) { if (BSMR_RES_HALVE_LANES) BSMR_ROWS(16, 2, HINT); else BSMR_ROWS(32, 1, HINT); } \
             else BSMR_ROWS(32, 2, HINT);                                                   \
         } else {                                                                           \
-            if (K == 32) BSMR_ROWS(8, 1, HINT);                                            \
-            else if (K == 64) BSMR_ROWS(16, 1, HINT);                                      \
+            if (K == 32) { if (BSMR_RES_HALVE_LANES) BSMR_ROWS(4, 2, HINT); else BSMR_ROWS(8, 1, HINT); } \
+            else if (K == 64) { if (BSMR_RES_HALVE_LANES) BSMR_ROWS(8, 2, HINT); else BSMR_ROWS(16, 1, HINT); } \
             else if (K == 128) BSMR_ROWS(BSMR_RES_K128_LPN, 128 / (BSMR_RES_K128_LPN * 4), HINT); \
-            else if (K == 256) BSMR_ROWS(32, 2, HINT);                                     \
+            else if (K == 256) { if (BSMR_RES_HALVE_LANES) BSMR_ROWS(16, 4, HINT); else BSMR_ROWS(32, 2, HINT); } \
             else BSMR_ROWS(32, 4, HINT);                                                   \
         }                                                                                  \
     } while (0)

@@ -224,20 +224,25 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const uint32_t g = t == my_begin ? rec0.z : __ldg(p.tile_meta + t).x;
                 const uint32_t key = g * rounds + round;          // one A image per (row group, batch element, pass)
                 const bool new_key = key != cur_key;
-                int4 arows[2];
-                arows[0] = arows[1] = make_int4((int)p.oob_row, (int)p.oob_row, (int)p.oob_row, (int)p.oob_row);
+                // (two named vectors, not an array indexed by the sub-group: an indexed array ends up in local memory)
+                int4 arows0 = make_int4((int)p.oob_row, (int)p.oob_row, (int)p.oob_row, (int)p.oob_row), arows1 = arows0;
                 if (new_key) {
                     // (re)load the A images, [sub-group of the pass][K-chunk] x 32 requests, interleaved with the B stages of
                     // this tile: chunk kc of A, then stage kc of B, so that the first MMAs start after one chunk has landed
                     // instead of after the whole 128 KB image
                     if (a_loads > 0) mbar_wait(&tail->a_free, (a_loads - 1) & 1, p.error_flag, 11);
                     if (issuer) {
-                        for (uint32_t sg = 0; sg < SGP; ++sg) {
-                            const uint32_t r0 = g * kWGroupRows + (pass * SGP + sg) * kWSubRows + rq * 4;
-                            int* rp = reinterpret_cast<int*>(&arows[sg]);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (r0 + j < p.num_rows) rp[j] = (int)(__ldg(p.reordered_rows + r0 + j) + row_off);
+                        const uint32_t r0 = g * kWGroupRows + pass * SGP * kWSubRows + rq * 4;
+                        if (r0 + 0 < p.num_rows) arows0.x = (int)(__ldg(p.reordered_rows + r0 + 0) + row_off);
+                        if (r0 + 1 < p.num_rows) arows0.y = (int)(__ldg(p.reordered_rows + r0 + 1) + row_off);
+                        if (r0 + 2 < p.num_rows) arows0.z = (int)(__ldg(p.reordered_rows + r0 + 2) + row_off);
+                        if (r0 + 3 < p.num_rows) arows0.w = (int)(__ldg(p.reordered_rows + r0 + 3) + row_off);
+                        if (SGP == 2) {
+                            const uint32_t r1 = r0 + kWSubRows;
+                            if (r1 + 0 < p.num_rows) arows1.x = (int)(__ldg(p.reordered_rows + r1 + 0) + row_off);
+                            if (r1 + 1 < p.num_rows) arows1.y = (int)(__ldg(p.reordered_rows + r1 + 1) + row_off);
+                            if (r1 + 2 < p.num_rows) arows1.z = (int)(__ldg(p.reordered_rows + r1 + 2) + row_off);
+                            if (r1 + 3 < p.num_rows) arows1.w = (int)(__ldg(p.reordered_rows + r1 + 3) + row_off);
                         }
                     }
                     cur_key = key;
@@ -263,9 +268,9 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     if (new_key) {
                         if (warp == 0 && lane == 0) mbar_arrive_expect_tx(&tail->a_full[kc], SGP * kWAImgBytes);
                         if (issuer) {
-                            for (uint32_t sg = 0; sg < SGP; ++sg)
-                                tma_gather4(&map_a, &tail->a_full[kc], a_img + ((size_t)kc * SGP + sg) * kWAImgBytes + rq * 512,
-                                            (int)(kc * kWChunk), arows[sg]);
+                            tma_gather4(&map_a, &tail->a_full[kc], a_img + (size_t)kc * SGP * kWAImgBytes + rq * 512, (int)(kc * kWChunk), arows0);
+                            if (SGP == 2)
+                                tma_gather4(&map_a, &tail->a_full[kc], a_img + ((size_t)kc * SGP + 1) * kWAImgBytes + rq * 512, (int)(kc * kWChunk), arows1);
                         }
                     }
                     mbar_wait(&tail->b_empty[stage], phase ^ 1, p.error_flag, 12);

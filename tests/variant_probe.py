@@ -71,7 +71,7 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
         return
-    libs = [None] + sorted(glob.glob(os.path.join(ROOT, "bsmr-sddmm_b200", "lib", "_variants", "*.so")))
+    libs = [None] + sorted(l for l in glob.glob(os.path.join(ROOT, "bsmr-sddmm_b200", "lib", "_variants", "*.so")) if "r01" not in l)
     for lib in libs:
         env = dict(os.environ)
         if lib:
