@@ -239,7 +239,8 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         uint32_t it = 0;
         for (uint32_t w = blockIdx.x; w < total; w += gridDim.x, ++it) {
             const uint32_t be = w / ntiles, ti = p.tile_begin + (w - be * ntiles);
-            float* const Pb = p.P + be * p.stride_p;
+            float* Pb = p.P + be * p.stride_p;
+            asm volatile("" : "+l"(Pb));        // one register pair per work item: not re-derived per store
             const uint32_t t = p.tile_list ? __ldg(p.tile_list + ti) : ti;
             const uint32_t acc = it % kAccs, acc_phase = (it / kAccs) & 1;
             const uint32_t nc = __ldg(p.tile_meta + t).z;
@@ -269,7 +270,7 @@ dense_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             if (active) {
 #pragma unroll
                 for (int r = 0; r < (int)kPanel; ++r)
-                    if (idx[r] != kNull) Pb[idx[r]] = __uint_as_float(v[r]);
+                    st_global_if(Pb, idx[r] != kNull ? idx[r] : 0u, v[r], idx[r] != kNull);
             }
         }
     }

@@ -151,5 +151,19 @@ inline int make_row_gather_map(bsmr_ctx* ctx, const float* base, uint64_t rows, 
 }
 
 
+// Predicated 4-byte store P[idx] = bits.  The epilogues store one accumulator per (row, lane) where S has an entry; written
+// as `if (...) P[i] = v` the compiler turns each of them into a divergent branch (BSSY / BSYNC per row) as soon as the
+// address takes more than an IMAD.WIDE off a kernel parameter -- measured: the mask-form epilogue of the wide kernel went
+// from 20 to 35 us per DLMC mask when P became a per-batch-element pointer.  The predicate is explicit here.
+__device__ __forceinline__ void st_global_if(float* base, uint32_t idx, uint32_t bits, bool pred) {
+    asm volatile(
+        "{\n"
+        "  .reg .pred p;\n"
+        "  setp.ne.b32 p, %2, 0;\n"
+        "  @p st.global.b32 [%0], %1;\n"
+        "}\n" ::"l"(base + idx), "r"(bits), "r"((uint32_t)pred)
+        : "memory");
+}
+
 }  // namespace tc
 }  // namespace bsmr

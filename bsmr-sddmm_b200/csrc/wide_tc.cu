@@ -364,7 +364,8 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             uint32_t it = 0;
             for (uint32_t round = 0; round < rounds; ++round) {
                 const uint32_t be = round / passes, pass = round - be * passes;
-                float* const Pout = p.P + be * p.stride_p;
+                float* Pout = p.P + be * p.stride_p;
+                asm volatile("" : "+l"(Pout));      // one register pair for the whole round: not re-derived from (element, stride) per store
                 // K = 256: one row half is resident per pass and only the warps of that half have work.  The others still take
                 // part in the accumulator hand-shake tile by tile: a warp that skipped ahead would test the parity of a phase
                 // the barrier has not reached yet (a parity wait can only tell the current phase from the previous one).
@@ -422,12 +423,12 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                         for (int r = 0; r < 16; ++r)
-                            if (mb[r].x & lane_bit) Pout[mb[r].y + __popc(mb[r].x & lanes_below)] = __uint_as_float(v[r]);
+                            st_global_if(Pout, mb[r].y + __popc(mb[r].x & lanes_below), v[r], (mb[r].x & lane_bit) != 0);
 #pragma unroll
                         for (int r = 0; r < 16; ++r) mb[r] = rows[16 + r];
 #pragma unroll
                         for (int r = 0; r < 16; ++r)
-                            if (mb[r].x & lane_bit) Pout[mb[r].y + __popc(mb[r].x & lanes_below)] = __uint_as_float(v[16 + r]);
+                            st_global_if(Pout, mb[r].y + __popc(mb[r].x & lanes_below), v[16 + r], (mb[r].x & lane_bit) != 0);
                     }
                     tc_fence_before();
                     __syncwarp();
@@ -460,7 +461,8 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             uint32_t it = 0;
             for (uint32_t round = 0; round < rounds; ++round) {
                 const uint32_t be = round / passes, pass = round - be * passes;
-                float* const Pout = p.P + be * p.stride_p;
+                float* Pout = p.P + be * p.stride_p;
+                asm volatile("" : "+l"(Pout));      // one register pair for the whole round: not re-derived from (element, stride) per store
                 // K = 256: one row half is resident per pass and only the warps of that half have work.  The others still take
                 // part in the accumulator hand-shake tile by tile: a warp that skipped ahead would test the parity of a phase
                 // the barrier has not reached yet (a parity wait can only tell the current phase from the previous one).
@@ -578,7 +580,7 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                                 val[q] = *reinterpret_cast<const float*>(stg_bytes + en0[q].x);
     #pragma unroll
                             for (int q = 0; q < 4; ++q)
-                                if (e0 + q * 32 + lane < seg0) Pout[en0[q].y] = val[q];
+                                st_global_if(Pout, en0[q].y, __float_as_uint(val[q]), e0 + q * 32 + lane < seg0);
                         }
                         // the rest of a long list (more than 128 entries, or a page boundary inside the first 128)
                         for (uint32_t e = seg0; e < e1;) {
@@ -600,7 +602,7 @@ wide_sddmm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                                     val[q] = *reinterpret_cast<const float*>(stg_bytes + en[q].x);
     #pragma unroll
                                 for (int q = 0; q < 2; ++q)
-                                    if (eb + q * 32 + lane < seg_end) Pout[en[q].y] = val[q];
+                                    st_global_if(Pout, en[q].y, __float_as_uint(val[q]), eb + q * 32 + lane < seg_end);
                             }
                             e = seg_end;
                         }
