@@ -83,33 +83,39 @@ __global__ void runs_split_kernel(const uint64_t* __restrict__ ukeys, uint32_t n
 // dispersion (src/rowReordering.cu:78-92) and the row's (possibly lossy) sum of squares, one warp per row
 __global__ void dispersion_kernel(uint32_t M, const uint32_t* __restrict__ row_offsets, const uint32_t* __restrict__ enc_ptr,
                                   const uint32_t* __restrict__ enc_blk, const uint32_t* __restrict__ counts, uint32_t block_size,
-                                  uint32_t bd, uint32_t kept_mask, uint32_t* __restrict__ dispersion, uint32_t* __restrict__ row_sq) {
+                                  uint32_t bd, uint32_t kept_mask, uint32_t* __restrict__ dispersion, uint32_t* __restrict__ row_sq,
+                                  uint32_t* __restrict__ row_tot) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t r = warp; r < M; r += stride) {
         const uint32_t nz = row_offsets[r + 1] - row_offsets[r];
         const uint32_t b = enc_ptr[r], e = enc_ptr[r + 1];
-        uint32_t res = 0, sq = 0;
+        uint32_t res = 0, sq = 0, tot = 0;
         for (uint32_t j = b + lane; j < e; j += 32) {
             const uint32_t c = counts[j];
             res += block_size - c;
-            if ((kept_mask >> ((enc_blk[j] % bd) >> 5)) & 1u) sq += c * c;
+            if ((kept_mask >> ((enc_blk[j] % bd) >> 5)) & 1u) {
+                sq += c * c;
+                tot += c;
+            }
         }
         res = __reduce_add_sync(0xffffffffu, res);
         sq = __reduce_add_sync(0xffffffffu, sq);
+        tot = __reduce_add_sync(0xffffffffu, tot);
         if (lane == 0) {
             dispersion[r] = nz ? res + nz * (e - b) : 0u;
             row_sq[r] = sq;
+            row_tot[r] = tot;          // nnz of the row in the blocks the reference's reduction keeps
         }
     }
 }
 
 __global__ void pos_info_kernel(uint32_t M, const uint32_t* __restrict__ asc, const uint32_t* __restrict__ enc_ptr,
-                                const uint32_t* __restrict__ row_sq, uint4* __restrict__ info) {
+                                const uint32_t* __restrict__ row_sq, const uint32_t* __restrict__ row_tot, uint4* __restrict__ info) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t r = asc[i];
-        info[i] = make_uint4(r, enc_ptr[r], enc_ptr[r + 1], row_sq[r]);
+        info[i] = make_uint4(row_tot[r], enc_ptr[r], enc_ptr[r + 1], row_sq[r]);
     }
 }
 
@@ -169,13 +175,15 @@ struct ClusterParams {
     const uint32_t* enc_blk;   // run -> column block (ascending inside a row)
     const uint32_t* counts;    // run -> nnz in the block
     const uint32_t* row_sq;    // row -> (lossy) sum of squares
-    const uint4* pos_info;     // position -> {row, first run, end run, (lossy) sum of squares}
+    const uint4* pos_info;     // position -> {nnz in kept blocks, first run, end run, (lossy) sum of squares}
+    uint32_t bd_mask;          // bd - 1 when bd is a power of two (block % bd without a division), else 0
     uint32_t* cluster_ids;     // position -> cluster id (pre-set: 0 for empty rows, NULL otherwise)
     uint32_t* lists;           // num_slots x list_cap positions; list of cluster c lives in slot c % num_slots
     unsigned long long* ctrl;  // per slot: list id << 33 | entries << 1 | producer-done   (single writer, release-published)
     uint32_t* status;          // [0] = number of clusters (set once), [1] = finished flag, [2] = abort (watchdog)
     unsigned long long* trace_ts; // optional: per cluster {start, first publish, end} in ns (globaltimer)
     unsigned long long* trace; // [0] steps [1] candidates [2] joins [3] polls [4] poll cycles [5] eval cycles [6] update cycles [7] busy cycles
+                               // [8] candidates rejected by the size bound alone (no block list read)
 };
 
 // block reduction with the reference's structure, executed by threads [0, bd) of the CTA
@@ -236,7 +244,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
     float* warp_max = part_max + 1024;                           // [32]  the same after the warp butterfly
     // per evaluating warp: the candidate's encoding expanded to nb 16-bit counts (only when p.scratch != 0)
     uint16_t* scratch = reinterpret_cast<uint16_t*>(warp_max + 32) + (size_t)(threadIdx.x >> 5) * p.scratch;
-    __shared__ uint32_t s_sq_rep;
+    __shared__ uint32_t s_sq_rep, s_tot_rep;
+    __shared__ float s_l1_rep;             // sum of the representative's normalised kept entries = s_tot_rep / sqrt(s_sq_rep)
     __shared__ unsigned long long s_ctrl;
     __shared__ uint32_t s_joined[2][8];    // bit k: candidate k of the step joins (up to 256 candidates); double buffered
     __shared__ uint32_t s_inscratch[2][8]; // bit k: ... and its encoding is expanded in the evaluating warp's scratch
@@ -254,18 +263,20 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
 
     // everything derived from `rep`; called by the whole CTA after rep changed (rep complete and visible on entry)
     auto refresh = [&]() {
-        if (tid == 0) s_sq_rep = 0;
+        if (tid == 0) { s_sq_rep = 0; s_tot_rep = 0; }
         __syncthreads();
         // sum of squares: thread t of the reference CTA owns blocks t, t+bd, ...; int e*e wraps (:241-249).  Integer
         // sums are order independent, so the reference's tree (which keeps each warp at most once) is the sum of the
         // warp sums of the kept warps.
-        uint32_t sq = 0;
+        uint32_t sq = 0, tt = 0;
         if (tid < p.bd)
-            for (uint32_t i = tid; i < p.nb; i += p.bd) sq += rep[i] * rep[i];
+            for (uint32_t i = tid; i < p.nb; i += p.bd) { sq += rep[i] * rep[i]; tt += rep[i]; }
         sq = __reduce_add_sync(0xffffffffu, sq);
-        if (lane == 0 && tid < p.bd && ((p.kept_mask >> wid) & 1u)) atomicAdd(&s_sq_rep, sq);
+        tt = __reduce_add_sync(0xffffffffu, tt);
+        if (lane == 0 && tid < p.bd && ((p.kept_mask >> wid) & 1u)) { atomicAdd(&s_sq_rep, sq); atomicAdd(&s_tot_rep, tt); }
         __syncthreads();
         const float nr = sqrtf((float)s_sq_rep);
+        if (tid == 0) s_l1_rep = s_sq_rep ? (float)s_tot_rep / nr : 0.f;
         // normalised representative and, in the same pass, thread t's max partial of the representative alone (:273-282)
         float mx = 0.f;
         if (tid < p.bd) {
@@ -294,6 +305,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
     // (c_idx / c_touched, warp-uniform registers): no global loads, no refill -- this is what bounds the cost of a long
     // run of consecutive joins.
     uint32_t c_idx = 0xFFFFFFFFu, c_touched = 0, c_pos = 0;
+    unsigned long long size_rejects = 0;
+    auto mod_bd = [&](uint32_t blk) -> uint32_t { return p.bd_mask ? (blk & p.bd_mask) : blk % p.bd; };
     uint4 c_info = make_uint4(0, 0, 0, 0);
     auto evaluate = [&](const uint4 info, const uint32_t x) -> bool {
         const uint32_t b = info.y, e = info.z, s_cmp = info.w;
@@ -302,13 +315,20 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
         if (s_rep == 0 || s_cmp == 0) return 0.0f > p.alpha;       // :261-263
         const uint32_t n = e - b;
         const float nc = sqrtf((float)s_cmp);
+        if (prune) {
+            // size bound: min-sum <= the smaller of the two L1 norms of the normalised (kept) encodings, max-sum >= the larger,
+            // so sim <= smaller / larger.  Both norms are known without reading the row's block list: rows that are much
+            // longer or much shorter than the representative (most of a power-law graph, for most clusters) go in O(1).
+            const float lc = (float)info.x / nc, lr = s_l1_rep;
+            if (fminf(lc, lr) < bound * fmaxf(lc, lr)) { ++size_rejects; return false; }
+        }
         float my_min = 0.f, my_max = lane < nw ? warp_max[lane] : 0.f;  // lane w = reference warp w
         if (n <= 32) {
             // ---- short block list: patch only the reference threads that own one of the row's blocks ----
             const bool valid = lane < n;
             const uint32_t blk = valid ? p.enc_blk[b + lane] : 0u;
             const uint32_t cnt = valid ? p.counts[b + lane] : 0u;
-            const uint32_t t = blk % p.bd;
+            const uint32_t t = mod_bd(blk);
             const bool kept = valid && ((p.kept_mask >> (t >> 5)) & 1u);
             if (prune) {
                 const uint32_t sh = __reduce_add_sync(0xffffffffu, (kept && rep[blk] != 0) ? cnt : 0u);
@@ -388,7 +408,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (blk4[u] == 0xFFFFFFFFu) continue;
-                    const uint32_t w = (blk4[u] % p.bd) >> 5;
+                    const uint32_t w = mod_bd(blk4[u]) >> 5;
                     touched |= 1u << w;
                     if ((p.kept_mask >> w) & 1u) {
                         tot += cnt4[u];
@@ -535,6 +555,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
             atomicAdd(p.trace + 0, tr_steps); atomicAdd(p.trace + 1, tr_cand); atomicAdd(p.trace + 2, tr_joins);
             atomicAdd(p.trace + 3, tr_polls); atomicAdd(p.trace + 4, tr_poll_cyc); atomicAdd(p.trace + 5, tr_eval_cyc);
             atomicAdd(p.trace + 6, tr_upd_cyc); atomicAdd(p.trace + 7, (unsigned long long)(clock64() - tr_begin));
+            atomicAdd(p.trace + 8, size_rejects);
         }
     };
     for (uint32_t c = blockIdx.x + 1;; c += gridDim.x) {
@@ -788,11 +809,12 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
         };
         // ---- sparse encodings ----
         TmpBuf<uint64_t> keys_a(ws), keys_b(ws), ukeys(ws);
-        TmpBuf<uint32_t> counts(ws), num_runs_d(ws), runs_per_row(ws), enc_ptr(ws), disp(ws), row_sq(ws), enc_blk(ws);
+        TmpBuf<uint32_t> counts(ws), num_runs_d(ws), runs_per_row(ws), enc_ptr(ws), disp(ws), row_sq(ws), row_tot(ws), enc_blk(ws);
         BSMR_TRY(runs_per_row.alloc(static_cast<size_t>(M) + 1));
         BSMR_TRY(enc_ptr.alloc(static_cast<size_t>(M) + 1));
         BSMR_TRY(disp.alloc(M ? M : 1));
         BSMR_TRY(row_sq.alloc(M ? M : 1));
+        BSMR_TRY(row_tot.alloc(M ? M : 1));
         BSMR_CUDA_OK(cudaMemsetAsync(runs_per_row.ptr, 0, runs_per_row.bytes(), st));
         uint32_t num_runs = 0;
         if (nnz) {
@@ -834,7 +856,7 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
         uint32_t zero_rows = 0;
         if (M) {
             dispersion_kernel<<<grid_for((uint64_t)M * 32, kThreads, sm), kThreads, 0, st>>>(M, plan->row_offsets.ptr, enc_ptr.ptr, enc_blk.ptr, counts.ptr,
-                                                                             block_size, bd, kept_mask, disp.ptr, row_sq.ptr);
+                                                                             block_size, bd, kept_mask, disp.ptr, row_sq.ptr, row_tot.ptr);
             // stable ascending sort of the rows by dispersion (:1055-1062)
             BSMR_CUDA_OK(cudaMemcpyAsync(dk_a.ptr, disp.ptr, static_cast<size_t>(M) * 4, cudaMemcpyDeviceToDevice, st));
             iota_kernel<<<grid_for(M, kThreads, sm), kThreads, 0, st>>>(asc_a.ptr, M);
@@ -857,7 +879,7 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
         TmpBuf<uint4> pos_info(ws);
         TmpBuf<unsigned long long> trace(ws);
         const bool want_trace = std::getenv("BSMR_TRACE") != nullptr;
-        BSMR_TRY(trace.alloc(8));
+        BSMR_TRY(trace.alloc(9));
         BSMR_CUDA_OK(cudaMemsetAsync(trace.ptr, 0, trace.bytes(), st));
         TmpBuf<unsigned long long> trace_ts(ws);
         if (want_trace) {
@@ -885,11 +907,12 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
             init_cluster_state_kernel<<<grid_for(M, kThreads, sm), kThreads, 0, st>>>(
                 M, zero_rows, num_slots, cluster_ids.ptr, lists.ptr + static_cast<size_t>(1 % num_slots) * list_cap, ctrl.ptr, status.ptr);
             BSMR_TRY(pos_info.alloc(M));
-            pos_info_kernel<<<grid_for(M, kThreads, sm), kThreads, 0, st>>>(M, asc, enc_ptr.ptr, row_sq.ptr, pos_info.ptr);
+            pos_info_kernel<<<grid_for(M, kThreads, sm), kThreads, 0, st>>>(M, asc, enc_ptr.ptr, row_sq.ptr, row_tot.ptr, pos_info.ptr);
             ctx->launches++;
             ClusterParams cp{};
             cp.trace = want_trace ? trace.ptr : nullptr;
             cp.trace_ts = want_trace ? trace_ts.ptr : nullptr;
+            cp.bd_mask = (bd & (bd - 1)) == 0 ? bd - 1 : 0u;
             cp.kept_mask = kept_mask; cp.pos_info = pos_info.ptr; cp.scratch = use_scratch ? scratch_entries : 0u;
             cp.M = M; cp.nb = nb; cp.bd = bd; cp.first_stride = first_stride; cp.zero_rows = zero_rows; cp.alpha = alpha;
             cp.list_cap = list_cap; cp.num_slots = num_slots;
@@ -909,11 +932,11 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
             }
             clusters_true = h_status[0];
             if (want_trace) {
-                unsigned long long h_tr[8];
+                unsigned long long h_tr[9];
                 BSMR_CUDA_OK(cudaMemcpy(h_tr, trace.ptr, sizeof(h_tr), cudaMemcpyDeviceToHost));
                 fprintf(stderr, "[bsmr trace] clustering: rows %u nb %u bd %u grid %d scratch %d | clusters %u steps %llu candidates %llu joins %llu "
-                                "polls %llu | Mcycles: poll %.1f eval %.1f update %.1f busy(all CTAs) %.1f\n",
-                        M, nb, bd, grid, (int)use_scratch, clusters_true, h_tr[0], h_tr[1], h_tr[2], h_tr[3], h_tr[4] / 1e6, h_tr[5] / 1e6,
+                                "polls %llu size-bound rejects seen by warp 0 of every CTA %llu | Mcycles: poll %.1f eval %.1f update %.1f busy(all CTAs) %.1f\n",
+                        M, nb, bd, grid, (int)use_scratch, clusters_true, h_tr[0], h_tr[1], h_tr[2], h_tr[3], h_tr[8], h_tr[4] / 1e6, h_tr[5] / 1e6,
                         h_tr[6] / 1e6, h_tr[7] / 1e6);
                 const uint32_t nc = clusters_true < M ? clusters_true : M;
                 std::vector<unsigned long long> ts(3 * (static_cast<size_t>(nc) + 1));
