@@ -18,8 +18,8 @@ N > 1.  Workload: BASELINE.json configs[4], the fixed 2^23-row / 2.5e8-nnz R-MAT
 fits one GPU, and rank 0 also times the unsharded pass in the same run: `single_gpu`).  Work is partitioned by
 nnz-balanced ranges of reordered row panels; `value` times, with A and B resident on every rank, the kernels of every
 shard PLUS the assembly of P on rank 0 (pack -> grouped ncclSend/ncclRecv over NVLink -> un-permute: bsmr_sddmm_sharded);
-`e2e` times bsmr_sddmm_sharded_host from pinned host buffers: every rank uploads the A rows of its shard and 1/N of B,
-ncclAllGather replicates B, kernels, gather of P, D2H on rank 0.  The inputs (17 GB) are far larger than L2.
+`e2e` times bsmr_sddmm_sharded_host from pinned host buffers: every rank uploads the A rows of its shard and a slice of B,
+an all-gather-v over NCCL replicates B, kernels, gather of P, D2H on rank 0.  The inputs (17 GB) are far larger than L2.
 """
 import argparse
 import json
@@ -350,7 +350,7 @@ def measure_config(torch, pkg, ctx, stream, flush, name, M, N, ro, ci, K, row_fl
     return out
 
 
-def measure_batch(torch, pkg, ctx, stream, flush, M, N, ro, ci, K, nb):
+def measure_batch(torch, pkg, ctx, stream, flush, M, N, ro, ci, K, nb, name="mask90"):
     """sddmm_gpu_batch: one launch per kernel for the whole batch against nb single calls (the attention-mask use case)."""
     nnz = len(ci)
     plan = pkg.Plan(ctx, M, N, ro, ci)
@@ -380,7 +380,7 @@ def measure_batch(torch, pkg, ctx, stream, flush, M, N, ro, ci, K, nb):
     t_batch = timed(lambda: plan.sddmm_batch(nb, K, dA, dB, dP2, timed=False))
     same = bool(torch.equal(dP, dP2))
     plan.close()
-    return {"workload": "mask90 K=%d x %d (A, B, P) triples" % (K, nb), "loop_of_single_calls_ms": t_loop, "batched_ms": t_batch,
+    return {"workload": "%s K=%d x %d (A, B, P) triples" % (name, K, nb), "loop_of_single_calls_ms": t_loop, "batched_ms": t_batch,
             "speedup": t_loop / t_batch, "gflops_batched": 2.0 * nnz * K * nb / (t_batch * 1e-3) / 1e9, "bit_identical_to_loop": same,
             "l2": "flushed before each timed batch"}
 
@@ -515,8 +515,9 @@ def run_sharded(args, rank, world, local_rank):
                 "data": "synthetic", "config": graph8m_config(world), "clocks": clocks,
                 "e2e": {"value": 2.0 * nnz * K / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(nnz * 4),
-                        "how": "bsmr_sddmm_sharded_host, pinned host buffers, %d steps: every rank uploads the A rows of its shard and 1/N of B, "
-                               "ncclAllGather replicates B, kernels, gather-v of P to rank 0, D2H on rank 0 (bytes summed over ranks)" % e2e_steps,
+                        "how": "bsmr_sddmm_sharded_host, pinned host buffers, %d steps: every rank uploads the A rows of its shard and a slice of B "
+                               "(sized so that A rows + B columns per rank are equal), a grouped ncclBroadcast per rank (all-gather-v) replicates B, "
+                               "kernels, gather-v of P to rank 0, D2H on rank 0 (bytes summed over ranks)" % e2e_steps,
                         "by_rank_ms": [{k: round(v, 3) for k, v in p.items() if k.endswith("_ms")} for p in e2e_parts],
                         "allgather_b": {"bytes_received_per_rank": int(e2e_parts[0]["allgather_b_bytes"]), "ms": max(p["allgather_b_ms"] for p in e2e_parts),
                                         "GB_per_s_per_rank": e2e_parts[0]["allgather_b_bytes"] / (max(p["allgather_b_ms"] for p in e2e_parts) * 1e-3) / 1e9}},
@@ -752,8 +753,8 @@ def main():
             configs.append(measure_config(torch, pkg, ctx, stream, flush, "mask %d %% K=64 (configs[2])" % s, Mm, Nm, rom, cim, 64,
                                           pkg.ROW_REFERENCE_COMPAT, False, peak))
             log(configs[-1]["name"])
-            if s == 90:
-                batch = measure_batch(torch, pkg, ctx, stream, flush, Mm, Nm, rom, cim, 64, 16)
+            if s in (90, 98):
+                batch = (batch or []) + [measure_batch(torch, pkg, ctx, stream, flush, Mm, Nm, rom, cim, 64, 16, "mask%d" % s)]
                 log("batch")
         n, rog, cig, rws = rmat_device(torch, GRAPH1M["scale"], GRAPH1M["edges"], seed=GRAPH1M["scale"])
         del rws

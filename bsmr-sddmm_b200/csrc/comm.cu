@@ -3,9 +3,10 @@
 // No counterpart in the reference (single process, device 0 only: include/Logger.hpp:23-25).  The path shards by
 // contiguous ranges of REORDERED row panels balanced on work (bsmr_plan_set_shard); output entries are independent, so
 // the only exchanges are the two the problem has:
-//   before the kernels   B (K x N, read by every rank): every rank uploads 1/world of it over its own PCIe link and an
-//                        in-place ncclAllGather replicates it (world x the host->device rate of a root upload +
-//                        ncclBroadcast); A follows the panels: a rank uploads only the rows of its shard
+//   before the kernels   B (K x N, read by every rank): every rank uploads a slice of it over its own PCIe link and a grouped
+//                        ncclBroadcast per rank (an all-gather-v) replicates it -- world x the host->device rate of a root
+//                        upload + broadcast; A follows the panels: a rank uploads only the rows of its shard, and the
+//                        slices of B are sized so that A rows + B columns per rank come out equal
 //   after the kernels    P: the kernels write CSR positions; a rank's entries are ONE contiguous range of the pattern
 //                        in reordered-row order (ensure_flat_list), so a pack kernel makes its slice contiguous, the
 //                        slices go to the root with grouped ncclSend / ncclRecv (a gather-v: 4 * nnz bytes in total,
@@ -20,6 +21,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 
@@ -350,11 +352,39 @@ int bsmr_sddmm_sharded_host(bsmr_plan* plan, uint32_t K, const float* hA, const 
     bsmr_shard_times* t = times ? times : &local;
     std::memset(t, 0, sizeof(*t));
     const size_t na = (size_t)plan->M * K;
-    // B is padded to world equal slices of whole columns (ncclAllGather wants equal counts)
-    const uint32_t cols_per = (plan->N + world - 1) / world;
-    const size_t nb_padded = (size_t)cols_per * world * K;
+    // How B is split for the upload: rank r uploads columns [bcol[r], bcol[r+1]) and the slices are exchanged with a grouped
+    // ncclBroadcast per rank (an all-gather-v).  The slices are NOT equal: nnz-balanced shards differ a lot in their number
+    // of rows (on a power-law graph the first shard holds the hub rows: few rows, many nnz), and what a rank's PCIe link
+    // has to carry is its A rows PLUS its slice of B -- so B goes preferentially to the ranks with few A rows (water
+    // filling on rows of K floats; every rank computes the same split from the shard bounds it already knows).
+    std::vector<uint32_t> bcol(static_cast<size_t>(world) + 1, 0);
+    {
+        const uint32_t nrows = static_cast<uint32_t>(plan->h_reordered_rows.size());
+        std::vector<uint64_t> a_rows(world);
+        for (int r = 0; r < world; ++r) {
+            const uint64_t lo = std::min<uint64_t>((uint64_t)plan->h_shard_bounds[r] * kPanel, nrows);
+            const uint64_t hi = std::min<uint64_t>((uint64_t)plan->h_shard_bounds[r + 1] * kPanel, nrows);
+            a_rows[r] = hi - lo;
+        }
+        // level L such that sum_r max(0, L - a_rows[r]) = N  (bisection on integers)
+        uint64_t lo = 0, hi = (uint64_t)plan->N + *std::max_element(a_rows.begin(), a_rows.end());
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) / 2;
+            uint64_t got = 0;
+            for (int r = 0; r < world; ++r) got += mid > a_rows[r] ? mid - a_rows[r] : 0;
+            if (got >= plan->N) hi = mid; else lo = mid + 1;
+        }
+        uint64_t left = plan->N;
+        for (int r = 0; r < world; ++r) {
+            uint64_t take = lo > a_rows[r] ? lo - a_rows[r] : 0;
+            if (take > left || r + 1 == world) take = left;
+            bcol[r + 1] = bcol[r] + static_cast<uint32_t>(take);
+            left -= take;
+        }
+    }
+    const size_t nb_all = (size_t)plan->N * K;
     BSMR_TRY(plan->dA.alloc(na));
-    BSMR_TRY(plan->dB.alloc(nb_padded));
+    BSMR_TRY(plan->dB.alloc(nb_all));
     BSMR_TRY(plan->dP.alloc(rank == root ? plan->nnz : 1));
     cudaEvent_t ev[9];
     for (auto& e : ev) BSMR_CUDA_OK(cudaEventCreate(&e));
@@ -377,16 +407,23 @@ int bsmr_sddmm_sharded_host(bsmr_plan* plan, uint32_t K, const float* hA, const 
         }
     }
     BSMR_CUDA_OK(cudaEventRecord(ev[1], st));
-    // ---- B: 1/world of the columns per rank, then all-gather in place ----
-    const uint32_t c0 = std::min<uint32_t>(plan->N, cols_per * rank), c1 = std::min<uint32_t>(plan->N, c0 + cols_per);
+    // ---- B: this rank's slice, then the all-gather-v ----
+    const uint32_t c0 = bcol[rank], c1 = bcol[rank + 1];
     if (c1 > c0) {
         BSMR_CUDA_OK(cudaMemcpyAsync(plan->dB.ptr + (size_t)c0 * K, hB + (size_t)c0 * K, (size_t)(c1 - c0) * K * sizeof(float), cudaMemcpyHostToDevice, st));
         t->h2d_bytes += (uint64_t)(c1 - c0) * K * 4;
     }
     BSMR_CUDA_OK(cudaEventRecord(ev[2], st));
-    if (world > 1)
-        BSMR_NCCL_OK(nccl().AllGather(plan->dB.ptr + (size_t)cols_per * rank * K, plan->dB.ptr, (size_t)cols_per * K, ncclFloat32, comm_of(ctx), st));
-    t->allgather_b_bytes = world > 1 ? (uint64_t)cols_per * K * 4 * (world - 1) : 0;
+    if (world > 1) {
+        BSMR_NCCL_OK(nccl().GroupStart());
+        for (int r = 0; r < world; ++r)
+            if (bcol[r + 1] > bcol[r]) {
+                float* slice = plan->dB.ptr + (size_t)bcol[r] * K;
+                BSMR_NCCL_OK(nccl().Broadcast(slice, slice, (size_t)(bcol[r + 1] - bcol[r]) * K, ncclFloat32, r, comm_of(ctx), st));
+            }
+        BSMR_NCCL_OK(nccl().GroupEnd());
+    }
+    t->allgather_b_bytes = world > 1 ? (uint64_t)(plan->N - (c1 - c0)) * K * 4 : 0;
     BSMR_CUDA_OK(cudaEventRecord(ev[3], st));
     // ---- kernels, pack, gather-v, un-permute ----
     BSMR_TRY(assemble_sharded(plan, K, plan->dA.ptr, plan->dB.ptr, plan->dP.ptr, flags, root, t, ev + 3));   // stamps 3..7

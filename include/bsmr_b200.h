@@ -205,8 +205,8 @@ int bsmr_plan_bcast_row_order(bsmr_plan* plan, int root);
 
 typedef struct {
     float h2d_a_ms;        /* host path: upload of the shard's A rows                                   */
-    float h2d_b_ms;        /* host path: upload of this rank's 1/world of B                             */
-    float allgather_b_ms;  /* host path: ncclAllGather that replicates B                                */
+    float h2d_b_ms;        /* host path: upload of this rank's slice of B                               */
+    float allgather_b_ms;  /* host path: the all-gather-v (grouped ncclBroadcast) that replicates B     */
     float kernel_ms;       /* SDDMM kernels of the shard                                                */
     float pack_ms;         /* the shard's entries made contiguous (reordered-row order)                 */
     float gather_p_ms;     /* grouped ncclSend / ncclRecv of the slices to the root                     */
@@ -228,8 +228,9 @@ int bsmr_sddmm_sharded(bsmr_plan* plan, uint32_t K, const float* dA, const float
                        bsmr_shard_times* times);
 /* The same from host buffers (the sharded form of the host-data sddmm_gpu overload, src/sddmmKernel.cu:2518-2538):
  * hA, hB valid on every rank, hP on the root.  Every rank uploads only the A rows of its shard (straight out of the
- * host buffer when that is pinned + mapped memory and K % 4 == 0, else all of A) and 1/world of B, which an in-place
- * ncclAllGather replicates; then as above, and the root copies P out.  Synchronous; times (may be NULL) is filled.    */
+ * host buffer when that is pinned + mapped memory and K % 4 == 0, else all of A) and a slice of B sized so that every
+ * rank's PCIe link carries the same number of K-vectors (A rows + B columns); the slices are exchanged with a grouped
+ * ncclBroadcast per rank (an all-gather-v); then as above, and the root copies P out.  Synchronous; times is filled.  */
 int bsmr_sddmm_sharded_host(bsmr_plan* plan, uint32_t K, const float* hA, const float* hB, float* hP, uint32_t flags, int root,
                             bsmr_shard_times* times);
 
