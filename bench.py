@@ -524,6 +524,8 @@ def run_sharded(args, rank, world, local_rank):
                 "gpu_launches": int(launches),
                 "single_gpu": single,
                 "speedup_vs_single_gpu_same_run": single["ms_per_step"] / ms_per_step,
+                "scaling_note": "strong scaling of ONE fixed matrix (configs[4]); its one-GPU time is `single_gpu`, measured by rank 0 in this run. "
+                                "The N = 1 bench line is another workload (configs[1], the headline): do not divide this value by it.",
                 "ms_total_by_rank": [float(x.item()) / steps for x in every],
                 "shards_panels_nnz": sizes,
                 "collective": {"what": "gather-v of P to rank 0: grouped ncclSend / ncclRecv of each rank's contiguous slice (reordered-row order)",
@@ -756,6 +758,13 @@ def main():
             if s in (90, 98):
                 batch = (batch or []) + [measure_batch(torch, pkg, ctx, stream, flush, Mm, Nm, rom, cim, 64, 16, "mask%d" % s)]
                 log("batch")
+        # not a BASELINE.json configuration: the structure BSMR is built for (rows that share column supports in groups of
+        # ~80: dense 16 x 16 blocks after clustering, but no 256-row group dense enough for the wide kernel) -- the one
+        # workload here whose tensor-core work goes through the dense-block kernel
+        Mb, Nb, rob, cib = pkg.synth.block_structured(16000, 16000, seed=5, groups=200, cols_per_group=96, noise=0.001)
+        configs.append(measure_config(torch, pkg, ctx, stream, flush, "block-structured 16000^2, 200 column supports of 96, K=128 (extra: the dense-block kernel's case)",
+                                      Mb, Nb, rob, cib, 128, pkg.ROW_REFERENCE_COMPAT, False, peak))
+        log(configs[-1]["name"])
         n, rog, cig, rws = rmat_device(torch, GRAPH1M["scale"], GRAPH1M["edges"], seed=GRAPH1M["scale"])
         del rws
         configs.append(measure_config(torch, pkg, ctx, stream, flush, "graph 2^20 rows, 3e7 nnz, K=128 (configs[3]), BSMR row order", n, n, rog, cig,

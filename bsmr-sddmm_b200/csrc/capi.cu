@@ -701,6 +701,39 @@ int bsmr_plan_get_info(bsmr_plan* plan, bsmr_plan_info* info) {
     return BSMR_OK;
 }
 
+}  // extern "C"
+namespace bsmr {
+// The index ranges of the kernels' work lists that belong to the reordered row panels [b, e): residual entries, dense
+// tiles, and -- group aligned -- wide tiles.  (The wide kernel's CTA partition is NOT recomputed here: bsmr_plan_set_shard
+// does that; a caller that narrows the range temporarily, like the chunked sharded pass in comm.cu, does so only on plans
+// without wide tiles.)
+void apply_panel_range(bsmr_plan* plan, uint32_t b, uint32_t e) {
+    const uint32_t panels = plan->num_row_panels;
+    const uint32_t ppg = BSMR_WIDE_GROUP_ROWS / kPanel;
+    plan->shard_first_panel = b;
+    plan->shard_end_panel = e;
+    plan->shard_res_begin = plan->h_sparse_value_offsets.empty() ? 0 : plan->h_sparse_value_offsets[b];
+    plan->shard_res_end = plan->h_sparse_value_offsets.empty() ? 0 : plan->h_sparse_value_offsets[e];
+    // tiles are ordered by panel
+    const std::vector<uint32_t>& tp = plan->h_tile_panel;
+    plan->shard_tile_begin = static_cast<uint32_t>(std::lower_bound(tp.begin(), tp.end(), b) - tp.begin());
+    plan->shard_tile_end = static_cast<uint32_t>(std::lower_bound(tp.begin(), tp.end(), e) - tp.begin());
+    if (plan->num_wide_tiles) {
+        const uint32_t gb = (b + ppg - 1) / ppg, ge = e >= panels ? plan->num_groups : e / ppg;   // b, e are group aligned here
+        plan->shard_wt_begin = plan->h_wt_group_off[gb];
+        plan->shard_wt_end = plan->h_wt_group_off[ge];
+        plan->shard_res2_begin = plan->h_rr2_group_off[gb];
+        plan->shard_res2_end = plan->h_rr2_group_off[ge];
+        const std::vector<uint32_t>& tp2 = plan->h_tile2_panel;
+        plan->shard_tile2_begin = static_cast<uint32_t>(std::lower_bound(tp2.begin(), tp2.end(), b) - tp2.begin());
+        plan->shard_tile2_end = static_cast<uint32_t>(std::lower_bound(tp2.begin(), tp2.end(), e) - tp2.begin());
+    } else {
+        plan->shard_wt_begin = plan->shard_wt_end = 0;
+    }
+}
+}  // namespace bsmr
+extern "C" {
+
 int bsmr_plan_set_shard(bsmr_plan* plan, uint32_t rank, uint32_t world, uint32_t* first_panel, uint32_t* end_panel,
                         uint64_t* shard_nnz) {
     if (!plan || world == 0 || rank >= world) {
@@ -756,26 +789,9 @@ int bsmr_plan_set_shard(bsmr_plan* plan, uint32_t rank, uint32_t world, uint32_t
     if (e < b) e = b;
     plan->sharded = world > 1;
     plan->auto_flags.clear();   // the execution plan is chosen again for the shard
-    plan->shard_first_panel = b;
-    plan->shard_end_panel = e;
-    plan->shard_res_begin = plan->h_sparse_value_offsets.empty() ? 0 : plan->h_sparse_value_offsets[b];
-    plan->shard_res_end = plan->h_sparse_value_offsets.empty() ? 0 : plan->h_sparse_value_offsets[e];
-    // tiles are ordered by panel
-    const std::vector<uint32_t>& tp = plan->h_tile_panel;
-    plan->shard_tile_begin = static_cast<uint32_t>(std::lower_bound(tp.begin(), tp.end(), b) - tp.begin());
-    plan->shard_tile_end = static_cast<uint32_t>(std::lower_bound(tp.begin(), tp.end(), e) - tp.begin());
+    apply_panel_range(plan, b, e);
     if (plan->num_wide_tiles) {
-        const uint32_t gb = (b + ppg - 1) / ppg, ge = e >= panels ? plan->num_groups : e / ppg;   // b, e are group aligned here
-        plan->shard_wt_begin = plan->h_wt_group_off[gb];
-        plan->shard_wt_end = plan->h_wt_group_off[ge];
-        plan->shard_res2_begin = plan->h_rr2_group_off[gb];
-        plan->shard_res2_end = plan->h_rr2_group_off[ge];
-        const std::vector<uint32_t>& tp2 = plan->h_tile2_panel;
-        plan->shard_tile2_begin = static_cast<uint32_t>(std::lower_bound(tp2.begin(), tp2.end(), b) - tp2.begin());
-        plan->shard_tile2_end = static_cast<uint32_t>(std::lower_bound(tp2.begin(), tp2.end(), e) - tp2.begin());
         BSMR_TRY(wide_partition(plan, plan->shard_wt_begin, plan->shard_wt_end));
-    } else {
-        plan->shard_wt_begin = plan->shard_wt_end = 0;
     }
     if (first_panel) *first_panel = b;
     if (end_panel) *end_panel = e;

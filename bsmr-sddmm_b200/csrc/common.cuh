@@ -176,6 +176,8 @@ struct bsmr_ctx {
     // multi-GPU data plane (csrc/comm.cu): NCCL communicator of the ranks that share a sharded plan
     void* nccl_comm = nullptr;
     int comm_rank = 0, comm_world = 1;
+    cudaStream_t comm_stream = nullptr;          // the gather of P runs here, behind the kernels of the chunk it carries
+    cudaEvent_t comm_ev[9] = {};
 };
 
 struct bsmr_plan {
@@ -334,6 +336,7 @@ int launch_residual(bsmr_ctx* ctx, uint32_t K, const float* dA, const float* dB,
                     uint64_t begin, uint64_t end, const uint32_t* col_hot = nullptr, uint32_t cold_first = 0);
 int hot_columns(bsmr_plan* plan, uint32_t K, const uint32_t** bitmap, uint32_t* cold_first, uint32_t b_elem_bytes = 4);
 int ensure_flat_list(bsmr_plan* plan);
+void apply_panel_range(bsmr_plan* plan, uint32_t first_panel, uint32_t end_panel);
 int launch_expand_rows(bsmr_ctx* ctx, uint32_t M, uint32_t nnz, const uint32_t* row_offsets, uint32_t* row_of_nnz);
 
 int col_reorder_and_format(bsmr_plan* plan, float delta);

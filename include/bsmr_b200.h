@@ -208,8 +208,10 @@ typedef struct {
     float h2d_b_ms;        /* host path: upload of this rank's slice of B                               */
     float allgather_b_ms;  /* host path: the all-gather-v (grouped ncclBroadcast) that replicates B     */
     float kernel_ms;       /* SDDMM kernels of the shard                                                */
-    float pack_ms;         /* the shard's entries made contiguous (reordered-row order)                 */
-    float gather_p_ms;     /* grouped ncclSend / ncclRecv of the slices to the root                     */
+    float pack_ms;         /* 0: packing runs on the communication stream, inside gather_p_ms           */
+    float gather_p_ms;     /* pack + ncclSend / ncclRecv of the slices to the root that is NOT hidden   */
+                           /* behind the kernels (the shard is cut into chunks; chunk c travels while   */
+                           /* chunk c + 1 computes)                                                     */
     float unpermute_ms;    /* root: back to CSR order                                                   */
     float d2h_ms;          /* host path, root: P to the host                                            */
     float total_ms;
@@ -220,8 +222,9 @@ typedef struct {
 } bsmr_shard_times;
 
 /* One SDDMM over a sharded plan with the result assembled on `root`: every rank runs the kernels of its range of
- * reordered row panels (dA: at least the rows of the shard valid; dB: complete), packs its entries into one contiguous
- * slice, the slices go to the root (a gather-v: 4 * nnz bytes over NVLink in total) and the root un-permutes them into
+ * reordered row panels (dA: at least the rows of the shard valid; dB: complete) in a few chunks, packs the entries of a
+ * finished chunk into a contiguous slice and sends it to the root while the next chunk computes (a gather-v: 4 * nnz
+ * bytes over NVLink in total, on a communication stream of the context), and the root un-permutes them into
  * dP_root (CSR order, length nnz; ignored on the other ranks, may be NULL there).  Asynchronous on the context's stream
  * when times == NULL.                                                                                              */
 int bsmr_sddmm_sharded(bsmr_plan* plan, uint32_t K, const float* dA, const float* dB, float* dP_root, uint32_t flags, int root,
