@@ -184,7 +184,9 @@ int assemble_sharded(bsmr_plan* plan, uint32_t K, const float* dA, const float* 
     // the root's own slice is packed straight into its place in the assembled array
     float* slice0 = rank == root ? plan->shard_slice.ptr : plan->shard_slice.ptr - e0;     // slice0 + e = home of entry e
     const int grid = ctx->sm_count * 8;
-    const int chunks = (world > 1 && plan->num_wide_tiles == 0) ? kGatherChunks : 1;
+    // measured on configs[4]: at 2 ranks the transfer is 8 % of the step and chunking costs more than it hides (15.4 -> 17.6 ms:
+    // four launches with four tails, NCCL's copy kernels next to the gather kernel); from 4 ranks on the transfer is a third
+    const int chunks = (world >= 4 && plan->num_wide_tiles == 0) ? kGatherChunks : 1;
     NcclApi& n = nccl();
     cudaStream_t cs = ctx->comm_stream;
     if (stamps) BSMR_CUDA_OK(cudaEventRecord(stamps[0], ctx->stream));

@@ -193,6 +193,9 @@ residual_sddmm_kernel(const uint32_t K, const float* __restrict__ A, const BT* _
 #ifndef BSMR_RES_UNROLL
 #define BSMR_RES_UNROLL 4   // entries in flight per lane group for KV < 4
 #endif
+#ifndef BSMR_RES_PREFETCH
+#define BSMR_RES_PREFETCH 0    // probe builds: 1 = the index triples of a chunk are fetched one chunk ahead
+#endif
 #ifndef BSMR_RES_K128_LPN
 #define BSMR_RES_K128_LPN 16   // lanes per entry of the fp32 kernel at K = 128: two 16-byte pieces per lane (measured against 32 x one:
                                // 1.20 against 1.35 ms on the 2^20-row graph, 34.8 against 38.9 us on nips)
@@ -269,21 +272,35 @@ residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const BT* __
         pol_cold = cold_first ? pol_stream : l2_policy_evict_normal();
     }
 
-    for (uint64_t chunk = warp_global; chunk < num_chunks; chunk += warp_stride) {
+    auto load_idx = [&](uint64_t chunk, uint32_t& row, uint32_t& col, uint32_t& out, bool& valid) {
         const uint64_t e = begin + chunk * 32 + lane;
-        const bool valid = e < end;
+        valid = e < end;
         const uint64_t es = valid ? e : begin;       // idle lanes recompute entry `begin`; never stored
-        uint32_t my_row, my_col, my_out, my_hot = 0;
         if constexpr (HINT) {
-            my_row = __ldcs(res_row + es);
-            my_col = __ldcs(res_col + es);
-            my_out = res_out ? __ldcs(res_out + es) : (uint32_t)es;
-            my_hot = (__ldg(col_hot + (my_col >> 5)) >> (my_col & 31)) & 1u;
+            row = __ldcs(res_row + es);
+            col = __ldcs(res_col + es);
+            out = res_out ? __ldcs(res_out + es) : (uint32_t)es;
         } else {
-            my_row = __ldg(res_row + es);
-            my_col = __ldg(res_col + es);
-            my_out = res_out ? __ldg(res_out + es) : (uint32_t)es;   // NULL = identity (CSR order)
+            row = __ldg(res_row + es);
+            col = __ldg(res_col + es);
+            out = res_out ? __ldg(res_out + es) : (uint32_t)es;   // NULL = identity (CSR order)
         }
+    };
+    constexpr bool kPrefetch = BSMR_RES_PREFETCH != 0;
+    uint32_t nx_row = 0, nx_col = 0, nx_out = 0;
+    bool nx_valid = false;
+    if (kPrefetch && warp_global < num_chunks) load_idx(warp_global, nx_row, nx_col, nx_out, nx_valid);
+    for (uint64_t chunk = warp_global; chunk < num_chunks; chunk += warp_stride) {
+        uint32_t my_row, my_col, my_out;
+        bool valid;
+        if constexpr (kPrefetch) {
+            my_row = nx_row; my_col = nx_col; my_out = nx_out; valid = nx_valid;
+            if (chunk + warp_stride < num_chunks) load_idx(chunk + warp_stride, nx_row, nx_col, nx_out, nx_valid);
+        } else {
+            load_idx(chunk, my_row, my_col, my_out, valid);
+        }
+        uint32_t my_hot = 0;
+        if constexpr (HINT) my_hot = (__ldg(col_hot + (my_col >> 5)) >> (my_col & 31)) & 1u;
         // Pass s (s = 0..LPN-1, entries in list order so that the A row in registers is reused) fills
         // accumulator slot it(s) = (s >> 1) + (s & 1) * H: the two passes of a pair (i, i + H) are adjacent,
         // and the first butterfly step (offset H) is folded in as soon as both are known, which keeps only
