@@ -28,6 +28,7 @@ SDDMM_DEFAULT, SDDMM_RESIDUAL_ONLY, SDDMM_NO_REORDER, SDDMM_NO_WIDE, SDDMM_THREE
 TICKET_ALL = 0xFFFFFFFFFFFFFFFF
 CUDA_STREAM_LEGACY = 1          # cudaStreamLegacy: the legacy default stream as an explicit handle
 WIDE_GROUP_ROWS, WIDE_TILE_COLS = 256, 128
+WIDE_EPILOGUE_AUTO, WIDE_EPILOGUE_LIST, WIDE_EPILOGUE_MASK = 0, 1, 2
 
 VEC = dict(reordered_rows=0, dense_cols=1, dense_col_offsets=2, sparse_cols=3, sparse_col_offsets=4,
            sparse_value_offsets=5, block_offsets=6, block_values=7, sparse_values=8,
@@ -145,6 +146,8 @@ def lib():
         L.bsmr_plan_set_execution_choice.argtypes = [vp, C.c_uint32, C.c_uint32]
         L.bsmr_plan_fit_tile_work.argtypes = [vp, C.c_uint32, vp, vp, vp, f32p]
         L.bsmr_plan_set_tile_work.argtypes = [vp, C.c_float]
+        L.bsmr_plan_set_wide_epilogue.argtypes = [vp, C.c_int]
+        L.bsmr_ctx_set_host_copy_duplex.argtypes = [vp, C.c_int]
         L.bsmr_batched_transpose.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]
         L.bsmr_convert_f32_to_f16.argtypes = [vp, vp, vp, C.c_uint64]
         L.bsmr_sddmm_f16b.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_int, C.c_uint32, f32p]
@@ -164,6 +167,7 @@ def lib():
                      "bsmr_plan_fingerprint", "bsmr_plan_save_row_order", "bsmr_plan_load_row_order", "bsmr_plan_execution_choice",
                      "bsmr_plan_set_wide_ratio", "bsmr_plan_set_l2_policy", "bsmr_plan_evaluate", "bsmr_plan_autotune",
                      "bsmr_plan_set_execution_choice", "bsmr_plan_fit_tile_work", "bsmr_plan_set_tile_work",
+                     "bsmr_plan_set_wide_epilogue", "bsmr_ctx_set_host_copy_duplex",
                      "bsmr_batched_transpose", "bsmr_convert_f32_to_f16", "bsmr_sddmm_f16b", "bsmr_comm_unique_id",
                      "bsmr_ctx_comm_init", "bsmr_ctx_comm_destroy", "bsmr_ctx_comm_bcast", "bsmr_plan_bcast_row_order",
                      "bsmr_sddmm_sharded", "bsmr_sddmm_sharded_host"):
@@ -293,6 +297,10 @@ class Plan:
     def set_wide_ratio(self, ratio):
         """Policy of the wide row-group path, applied at the next column reorder (<= 0 disables it)."""
         _check(lib().bsmr_plan_set_wide_ratio(self._h, ratio))
+
+    def set_wide_epilogue(self, form):
+        """0 = by the fill of the wide tiles, 1 = per-entry lists, 2 = row masks; applied at the next column reorder."""
+        _check(lib().bsmr_plan_set_wide_epilogue(self._h, form))
 
     def set_l2_policy(self, hot_budget_mb=64, min_b_mb=2048, cold_first=True):
         """Residual kernel: keep the hub columns' K-vectors (up to hot_budget_mb MiB) in L2 when B exceeds min_b_mb MiB."""

@@ -346,6 +346,18 @@ int bsmr_plan_set_tile_work(bsmr_plan* plan, float nnz_equivalents_per_tile) {
     return BSMR_OK;
 }
 
+int bsmr_plan_set_wide_epilogue(bsmr_plan* plan, int form) {
+    if (!plan || form < BSMR_WIDE_EPILOGUE_AUTO || form > BSMR_WIDE_EPILOGUE_MASK) return BSMR_ERR_INVALID_ARGUMENT;
+    plan->wide_epilogue_form = form;
+    return BSMR_OK;
+}
+
+int bsmr_ctx_set_host_copy_duplex(bsmr_ctx* ctx, int mode) {
+    if (!ctx || mode < -1 || mode > 1) return BSMR_ERR_INVALID_ARGUMENT;
+    ctx->duplex = mode;
+    return BSMR_OK;
+}
+
 int bsmr_plan_set_wide_ratio(bsmr_plan* plan, float ratio) {
     if (!plan) return BSMR_ERR_INVALID_ARGUMENT;
     plan->wide_ratio = ratio;
@@ -1199,44 +1211,10 @@ static int ensure_host_pipeline(bsmr_plan* plan) {
     return probe_duplex(ctx);
 }
 
-// Copies between pinned host memory and the device: cudaMemcpyAsync, or -- for copies of at most
-// BSMR_HOST_COPY_KERNEL_MAX bytes whose host side is mapped into the device's address space (cudaHostAlloc /
-// cudaHostRegister memory under UVA) -- a kernel that reads or writes the host memory directly over PCIe.  Off by
-// default (threshold 0): measured on the nips step, 200 us with the copy engines, 204 with A through the kernel, 212
-// with everything through kernels (tests/e2e_probe.py).
 }  // extern "C"
 namespace {
-__global__ void copy16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n16) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
-}
-size_t copy_kernel_max_bytes() {
-    static const size_t v = [] { const char* e = std::getenv("BSMR_HOST_COPY_KERNEL_MAX"); return e ? (size_t)std::atoll(e) : (size_t)0; }();
-    return v;
-}
-// device-side alias of a pinned host pointer, or nullptr
-void* mapped_alias(const void* host) {
-    cudaPointerAttributes a{};
-    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
-        (void)cudaGetLastError();
-        return nullptr;
-    }
-    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
-}
-int copy_async(bsmr_ctx* ctx, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream) {
+int copy_async(bsmr_ctx*, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream) {
     if (bytes == 0) return BSMR_OK;
-    const void* host = kind == cudaMemcpyHostToDevice ? src : dst;
-    if (bytes <= copy_kernel_max_bytes() && bytes % 16 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
-        if (void* alias = mapped_alias(host)) {
-            const void* s = kind == cudaMemcpyHostToDevice ? alias : src;
-            void* d = kind == cudaMemcpyHostToDevice ? dst : alias;
-            const size_t n16 = bytes / 16;
-            const unsigned grid = static_cast<unsigned>(std::min<size_t>((n16 + 255) / 256, static_cast<size_t>(ctx->sm_count) * 4));
-            copy16_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(s), static_cast<uint4*>(d), n16);
-            ctx->launches++;
-            BSMR_CUDA_OK(cudaGetLastError());
-            return BSMR_OK;
-        }
-    }
     BSMR_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, kind, stream));
     return BSMR_OK;
 }
@@ -1246,13 +1224,9 @@ extern "C" {
 // Whether copies in opposite directions may run at the same time.  On some hosts of this pool a 6.4 MB H2D and a 3 MB D2H
 // in flight together drop to ~12 GB/s each (53 GB/s alone), on others they overlap perfectly (140 instead of 200 us per
 // nips step).  Decided once per context (= per device) by timing 2 MB each way, back to back and concurrently (about a millisecond);
-// environment BSMR_HOST_PIPE_DUPLEX = 0 / 1 overrides.
+// bsmr_ctx_set_host_copy_duplex overrides.
 static int probe_duplex(bsmr_ctx* ctx) {
     if (ctx->duplex >= 0) return BSMR_OK;
-    if (const char* e = std::getenv("BSMR_HOST_PIPE_DUPLEX")) {
-        ctx->duplex = std::atoi(e) != 0 ? 1 : 0;
-        return BSMR_OK;
-    }
     const size_t bytes = 2u << 20;
     void *h = nullptr, *d = nullptr;
     if (cudaHostAlloc(&h, 2 * bytes, cudaHostAllocDefault) != cudaSuccess || cudaMalloc(&d, 2 * bytes) != cudaSuccess) {

@@ -502,7 +502,6 @@ int h2d(T* dst, const std::vector<T>& src, cudaStream_t s) {
 
 float wide_ratio_of(const bsmr_plan* plan) {
     if (plan->wide_ratio >= 0.f) return plan->wide_ratio;
-    if (const char* e = std::getenv("BSMR_WIDE_RATIO")) return static_cast<float>(std::atof(e));
     return 5.0f;
 }
 
@@ -643,8 +642,7 @@ int build_wide_format(bsmr_plan* plan, Workspace* ws, const uint64_t* ukeys, con
     // 2.5 us per 128 x 256 tile at 4 % fill against 3.2 us for the mask form), row masks for dense ones (cost per tile
     // independent of the fill, stores of a row coalesce: 30 % fill runs 1.6x faster than through lists).
     const double fill = static_cast<double>(wide_values) / (static_cast<double>(wtiles) * kWideCols * kWideRows);
-    static const char* force_form = std::getenv("BSMR_WIDE_EPILOGUE");      // "mask" / "list": experiments
-    plan->wide_mask_epilogue = force_form ? std::string(force_form) == "mask" : fill >= 0.08;
+    plan->wide_mask_epilogue = plan->wide_epilogue_form ? plan->wide_epilogue_form == BSMR_WIDE_EPILOGUE_MASK : fill >= 0.08;   // bsmr_plan_set_wide_epilogue
     if (plan->wide_mask_epilogue) {
         // row-meta pairs (8 units of 128 pairs per tile)
         BSMR_TRY(plan->w_entries.alloc(static_cast<size_t>(wtiles) * kWUnitsPerTile * kWUnitRows));

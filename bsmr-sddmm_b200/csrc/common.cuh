@@ -236,6 +236,7 @@ struct bsmr_plan {
     bsmr::DevBuf<uint32_t> w_cols;            // distinct columns of the wide groups, ascending inside a group
     bsmr::DevBuf<uint32_t> w_mask;            // [tile][8][128]
     bsmr::DevBuf<uint32_t> w_base;            // [tile][2][128]
+    int wide_epilogue_form = 0;               // BSMR_WIDE_EPILOGUE_AUTO / _LIST / _MASK (bsmr_plan_set_wide_epilogue)
     bool wide_mask_epilogue = false;          // which form of the epilogue's work the format holds (colreorder.cu: by tile fill)
     bsmr::DevBuf<uint2> w_entries;            // mask form: row-meta pairs [(column quarter * 2 + row half) * #tiles + tile][128 rows]:
                                               //   {mask of the row's nnz among the quarter's 32 columns, CSR position of the first}

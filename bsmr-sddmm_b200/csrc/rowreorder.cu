@@ -878,7 +878,11 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
         TmpBuf<unsigned long long> ctrl(ws);
         TmpBuf<uint4> pos_info(ws);
         TmpBuf<unsigned long long> trace(ws);
-        const bool want_trace = std::getenv("BSMR_TRACE") != nullptr;
+#ifdef BSMR_DEBUG
+        const bool want_trace = std::getenv("BSMR_TRACE") != nullptr;     // probe builds (make DEBUG=1): per-cluster time stamps and counters
+#else
+        const bool want_trace = false;
+#endif
         BSMR_TRY(trace.alloc(9));
         BSMR_CUDA_OK(cudaMemsetAsync(trace.ptr, 0, trace.bytes(), st));
         TmpBuf<unsigned long long> trace_ts(ws);

@@ -136,8 +136,7 @@ inline int make_row_gather_map(bsmr_ctx* ctx, const float* base, uint64_t rows, 
     const cuuint64_t strides[1] = {K * sizeof(float)};
     const cuuint32_t box[2] = {32, box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    static const bool tf32_env = std::getenv("BSMR_TMA_TF32") != nullptr;
-    const bool tf32_map = tf32_rounding || tf32_env;
+    const bool tf32_map = tf32_rounding;
     CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
         out, tf32_map ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -279,13 +279,14 @@ int bsmr_plan_execution_choice(bsmr_plan* plan, uint32_t K, uint32_t* flags);
  * context's stream, the copies on copy streams, so the copy-in of call i+1 overlaps the kernels of call i.  Whether
  * copies in opposite directions may overlap is measured once per process (on some hosts of this pool that costs 4x in
  * rate, on others it is free): if not, the copy-out of a call is queued behind the copy-in of the next one (or by
- * _wait) on one copy stream; environment BSMR_HOST_PIPE_DUPLEX = 0 / 1 overrides.  hA / hB must stay valid and hP must not be read until
+ * _wait) on one copy stream; bsmr_ctx_set_host_copy_duplex(ctx, 0 / 1; -1 = measure) overrides.  hA / hB must stay valid and hP must not be read until
  * bsmr_sddmm_host_wait(plan, ticket) returns (BSMR_TICKET_ALL: every call submitted so far); pinned host memory is
  * needed for the copies to be asynchronous.  One caller thread per plan, as everywhere in this ABI.          */
 #define BSMR_TICKET_ALL 0xFFFFFFFFFFFFFFFFull
 int bsmr_sddmm_host_submit(bsmr_plan* plan, uint32_t K, const float* hA, const float* hB, float* hP,
                            uint32_t flags, uint64_t* ticket);
 int bsmr_sddmm_host_wait(bsmr_plan* plan, uint64_t ticket);
+int bsmr_ctx_set_host_copy_duplex(bsmr_ctx* ctx, int mode);
 
 /* sddmm_gpu_batch(numBatch, M, N, K, nnz, dA, dB, rphm, dP, time) (include/sddmmKernel.cuh:41-47,
  * src/sddmmKernel.cu:2764-2848): num_batch (A, B, P) triples on the plan's pattern, device pointers, batch b at
@@ -327,9 +328,15 @@ int bsmr_sddmm_profile3(bsmr_plan* plan, uint32_t K, const float* dA, const floa
 /* Wide-path policy of a plan, applied at the next column reorder: a row group goes wide when
  * nnz(group) >= ratio * (128 * tiles(group) + 256).  ratio <= 0 disables the wide path; the default
  * is 5.0, i.e. ~2 % fill of a 256 x 128 tile: below that the residual kernel's one K-vector
- * of B per nnz is cheaper than streaming the tile (measured on R-MAT hub groups; environment override:
- * BSMR_WIDE_RATIO).                                              */
+ * of B per nnz is cheaper than streaming the tile (measured on R-MAT hub groups).                          */
 int bsmr_plan_set_wide_ratio(bsmr_plan* plan, float ratio);
+/* Form of the wide kernel's epilogue, applied at the next column reorder: per-entry lists (instruction count follows
+ * the nnz), row masks with predicated stores (cost per tile independent of the fill), or chosen by the fill of the
+ * wide tiles (>= 8 % -> masks).  Both forms compute the same bits.                                             */
+#define BSMR_WIDE_EPILOGUE_AUTO 0
+#define BSMR_WIDE_EPILOGUE_LIST 1
+#define BSMR_WIDE_EPILOGUE_MASK 2
+int bsmr_plan_set_wide_epilogue(bsmr_plan* plan, int form);
 
 /* L2 policy of the residual kernel for operands that do not fit in L2 (no counterpart in the reference, whose sparse
  * kernels read B through __ldg with the default policy, src/sddmmKernel.cu:2043-2060).  When B (N * K * 4 bytes) is

@@ -3,7 +3,7 @@
 Meant as the target of `compute-sanitizer --tool memcheck` (closed on this pool's boxes in round 1, so it has only been
 run plain): one reorder (row clustering, column reorder, wide format with the bar lowered so that small matrices have
 wide groups) and one SDDMM per execution plan and K on small matrices; prints the mismatch count against the oracle
-(0 expected).  BSMR_WIDE_EPILOGUE=list|mask forces either form of the wide epilogue."""
+(0 expected).  Both forms of the wide epilogue are forced in turn (bsmr_plan_set_wide_epilogue)."""
 import os
 import sys
 
@@ -31,13 +31,15 @@ def main():
             want = oracle.sddmm_cpu(M, N, K, A, B, ro, ci)
             plan = pkg.Plan(ctx, M, N, ro, ci)
             plan.set_wide_ratio(1.0)
-            plan.reorder(0.3, 0.3, block_size=16)
             dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
-            for flags in (pkg.SDDMM_THREE_KERNEL, pkg.SDDMM_NO_WIDE, pkg.SDDMM_NO_REORDER):
-                dP = torch.zeros(len(ci), device="cuda")
-                plan.sddmm(K, dA, dB, dP, flags=flags)
-                torch.cuda.synchronize()
-                bad += oracle.check_data(want, dP.cpu().numpy())
+            for form in (pkg.WIDE_EPILOGUE_LIST, pkg.WIDE_EPILOGUE_MASK):
+                plan.set_wide_epilogue(form)
+                plan.reorder(0.3, 0.3, block_size=16)
+                for flags in (pkg.SDDMM_THREE_KERNEL, pkg.SDDMM_NO_WIDE, pkg.SDDMM_NO_REORDER):
+                    dP = torch.zeros(len(ci), device="cuda")
+                    plan.sddmm(K, dA, dB, dP, flags=flags)
+                    torch.cuda.synchronize()
+                    bad += oracle.check_data(want, dP.cpu().numpy())
             print(name, K, plan.info()["num_wide_groups"], "wide groups, mismatches so far", bad, flush=True)
             plan.close()
     print("total mismatches", bad)
