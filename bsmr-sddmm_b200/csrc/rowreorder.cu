@@ -66,7 +66,8 @@ __global__ void enc_keys_kernel(uint32_t M, const uint32_t* __restrict__ row_off
 }
 
 // enc_blk[u] = column block of run u; runs per row counted with one atomic per (warp, distinct row)
-__global__ void runs_split_kernel(const uint64_t* __restrict__ ukeys, uint32_t num_runs, uint32_t* __restrict__ enc_blk,
+__global__ void runs_split_kernel(const uint64_t* __restrict__ ukeys, const uint32_t* __restrict__ counts, uint32_t num_runs, uint32_t bd,
+                                  uint32_t kept_mask, uint32_t* __restrict__ enc_blk, uint2* __restrict__ enc_pair,
                                   uint32_t* __restrict__ runs_per_row) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t n32 = ((uint64_t)num_runs + 31) & ~31ull;
@@ -74,7 +75,13 @@ __global__ void runs_split_kernel(const uint64_t* __restrict__ ukeys, uint32_t n
         const bool valid = u < num_runs;
         const uint64_t key = valid ? ukeys[u] : ~0ull;
         const uint32_t row = (uint32_t)(key >> 32);
-        if (valid) enc_blk[u] = (uint32_t)(key & 0xffffffffull);
+        if (valid) {
+            const uint32_t blk = (uint32_t)(key & 0xffffffffull);
+            enc_blk[u] = blk;
+            // {block, count | kept << 31}: what the per-thread walk of the clustering kernel reads -- whether the reference's
+            // (lossy) reduction keeps the block's warp is decided here, once, instead of with a division per visit
+            enc_pair[u] = make_uint2(blk, counts[u] | (((kept_mask >> ((blk % bd) >> 5)) & 1u) << 31));
+        }
         const uint32_t peers = __match_any_sync(0xffffffffu, row);
         if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(runs_per_row + row, (uint32_t)__popc(peers));
     }
@@ -174,6 +181,8 @@ struct ClusterParams {
     const uint32_t* enc_ptr;   // row -> first run
     const uint32_t* enc_blk;   // run -> column block (ascending inside a row)
     const uint32_t* counts;    // run -> nnz in the block
+    const uint2* enc_pair;     // run -> {column block, nnz | kept << 31}
+    uint32_t thread_prune;     // 1: one THREAD per candidate for the cheap rejections, warps only for the survivors (see the step loop)
     const uint32_t* row_sq;    // row -> (lossy) sum of squares
     const uint4* pos_info;     // position -> {nnz in kept blocks, first run, end run, (lossy) sum of squares}
     uint32_t bd_mask;          // bd - 1 when bd is a power of two (block % bd without a division), else 0
@@ -250,6 +259,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
     __shared__ uint32_t s_joined[2][8];    // bit k: candidate k of the step joins (up to 256 candidates); double buffered
     __shared__ uint32_t s_inscratch[2][8]; // bit k: ... and its encoding is expanded in the evaluating warp's scratch
     __shared__ uint32_t s_stop;
+    __shared__ uint32_t s_maybe[2][32];    // thread-prune steps: bit l of word w = candidate 32 w + l survived the cheap tests; double buffered
+    __shared__ uint32_t s_first_join[2];   // ... first candidate of the step that joins (atomicMin), double buffered
     __shared__ uint32_t s_cpw;             // candidates per warp of the next step (thread 0 decides from the step's duration)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -510,6 +521,25 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
         const float sim = __shfl_sync(0xffffffffu, my_min, 0) / __shfl_sync(0xffffffffu, my_max, 0);
         return sim > p.alpha;
     };
+    // Cheap part of a similarity decision, for ONE candidate per THREAD: the zero cases, the size bound, and -- for rows of at
+    // most kWalkMax blocks -- the bound  sim <= (nnz in blocks shared with the representative) / (nnz in kept blocks),
+    // evaluated by walking the row's runs serially.  Same integers and the same float comparison as the warp path's prune,
+    // so the same candidates are rejected; false = rejected for sure, true = a warp has to evaluate it in full.
+    constexpr uint32_t kWalkMax = 64;
+    auto cheap_maybe = [&](const uint4 info) -> bool {
+        if (!prune) return true;
+        const uint32_t s_rep = s_sq_rep, s_cmp = info.w;
+        if (s_rep == 0 || s_cmp == 0) return s_rep == 0 && s_cmp == 0;    // one zero: sim = 0 <= alpha; both: sim = 1, the warp path decides
+        const float lc = (float)info.x / sqrtf((float)s_cmp), lr = s_l1_rep;
+        if (fminf(lc, lr) < bound * fmaxf(lc, lr)) return false;
+        if (info.z - info.y > kWalkMax) return true;
+        uint32_t sh = 0;
+        for (uint32_t j = info.y; j < info.z; ++j) {
+            const uint2 pr = __ldg(p.enc_pair + j);
+            if ((pr.y >> 31) && rep[pr.x] != 0) sh += pr.y & 0x7FFFFFFFu;
+        }
+        return !(sh == 0 || (float)sh < bound * (float)info.x);
+    };
     unsigned long long s_ctrl_copy = 0;
     // thread 0 polls the control word of list `id` until it belongs to that list and (has > have entries or is done);
     // returns false when the run is over (no such list will ever exist) or the watchdog fired
@@ -546,6 +576,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
         s_joined[tid >> 3][tid & 7] = 0;
         s_inscratch[tid >> 3][tid & 7] = 0;
     }
+    if (tid < 2) s_first_join[tid] = 0xFFFFFFFFu;
+    uint32_t par_a = 0, par_b = 0;
     uint32_t parity = 0;
     unsigned long long tr_steps = 0, tr_cand = 0, tr_joins = 0, tr_polls = 0, tr_poll_cyc = 0, tr_eval_cyc = 0, tr_upd_cyc = 0;
     const long long tr_begin = clock64();
@@ -591,7 +623,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
             __syncthreads();
             refresh();
         }
-        uint32_t cursor = 1, produced = 0, cpw = 1;
+        uint32_t cursor = 1, produced = 0, cpw = 1, published = 0;
         c_idx = 0xFFFFFFFFu;                                   // list indices of the previous cluster mean nothing here
         for (;;) {
             if (cursor >= avail) {
@@ -605,6 +637,80 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
                 }
                 avail = (uint32_t)((s_ctrl_copy >> 1) & 0xFFFFFFFFu);
                 in_done = (s_ctrl_copy & 1ull) != 0;
+                continue;
+            }
+            if (p.thread_prune) {
+                // ---- thread-prune step: up to 1024 candidates, one per thread ------------------------------------------------
+                // Measured on R-MAT graphs (ncu, profiles/r02d_*): the warp-per-candidate step spends ~300 warp instructions
+                // on a (cluster, row) pair that the bounds reject anyway -- 99.9 % of the pairs -- and the whole pipeline runs
+                // at the pace of that bookkeeping.  Here a THREAD applies the bounds to its candidate (the size bound in O(1),
+                // the shared-nnz bound by walking the row's <= 64 runs); warps evaluate only the survivors, in order, up to the
+                // first that joins.  The rejections are the same integers and comparisons, so the permutation is unchanged.
+                constexpr uint32_t kCpwB = 2;                               // survivors a warp evaluates per step
+                const uint32_t take = min(avail - cursor, (uint32_t)kClusterThreads);
+                ++tr_steps;
+                tr_cand += take;
+                uint32_t pos1 = 0xFFFFFFFFu;
+                bool maybe = false;
+                if (tid < take) {
+                    pos1 = __ldcg(in + cursor + tid);
+                    maybe = cheap_maybe(__ldg(p.pos_info + pos1));
+                }
+                const uint32_t mb = __ballot_sync(0xffffffffu, maybe);
+                if (lane == 0) s_maybe[par_a][wid] = mb;
+                __syncthreads();                                  // S1: verdicts in; the rejected rows stored by earlier steps are ordered before it
+                if (tid == 0 && produced != published) st_release_u64(out_ctrl, make_ctrl(c + 1, produced, 0));
+                published = produced;
+                const uint32_t wmask = s_maybe[par_a][lane];
+                par_a ^= 1;
+                uint32_t pre = __popc(wmask);                     // inclusive prefix of the survivors over the 32 words
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, pre, d);
+                    if ((int)lane >= d) pre += t;
+                }
+                const uint32_t total_maybe = __shfl_sync(0xffffffffu, pre, 31);
+                if (total_maybe == 0) {                           // the common step: nothing survives, everything moves on to the child
+                    if (tid < take) out[produced + tid] = pos1;
+                    produced += take;
+                    cursor += take;
+                    continue;
+                }
+                // index (within the step) of the survivor with rank r
+                auto nth_maybe = [&](uint32_t r) -> uint32_t {
+                    const uint32_t w = __ffs(__ballot_sync(0xffffffffu, pre > r)) - 1;      // first word whose prefix passes r
+                    const uint32_t before = __shfl_sync(0xffffffffu, pre - __popc(wmask), w);
+                    const uint32_t bits = __shfl_sync(0xffffffffu, wmask, w);
+                    return w * 32 + __fns(bits, 0, (int)(r - before) + 1);
+                };
+                const uint32_t evaluated = min(total_maybe, kWarps * kCpwB);
+                const uint32_t take_eff = total_maybe > evaluated ? nth_maybe(evaluated) : take;    // later survivors wait for the next step
+#pragma unroll 1
+                for (uint32_t q = 0; q < kCpwB; ++q) {
+                    const uint32_t r = q * kWarps + wid;
+                    if (r < evaluated) {                          // warp-uniform
+                        const uint32_t k = nth_maybe(r);
+                        const uint32_t kpos = __ldcg(in + cursor + k);
+                        if (evaluate(__ldg(p.pos_info + kpos), cursor + k) && lane == 0) atomicMin(&s_first_join[par_b], k);
+                    }
+                }
+                __syncthreads();                                  // S2: every survivor decided
+                const uint32_t fj = s_first_join[par_b];
+                par_b ^= 1;
+                if (tid == 0) s_first_join[par_b] = 0xFFFFFFFFu;   // last read two survivor steps ago; visible at the next S1
+                const uint32_t n_rej = fj == 0xFFFFFFFFu ? take_eff : fj;
+                if (tid < n_rej) out[produced + tid] = pos1;
+                produced += n_rej;
+                if (fj == 0xFFFFFFFFu) {
+                    cursor += take_eff;
+                } else {
+                    if (tid == fj) p.cluster_ids[pos1] = c;
+                    const uint4 ji = __ldg(p.pos_info + __ldcg(in + cursor + fj));
+                    absorb(ji.y, ji.z, false);
+                    refresh();                                    // its first barrier also closes the absorb
+                    cursor += fj + 1;
+                    ++tr_joins;
+                }
                 continue;
             }
             const uint32_t take = min(avail - cursor, kWarps * cpw);
@@ -810,6 +916,7 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
         // ---- sparse encodings ----
         TmpBuf<uint64_t> keys_a(ws), keys_b(ws), ukeys(ws);
         TmpBuf<uint32_t> counts(ws), num_runs_d(ws), runs_per_row(ws), enc_ptr(ws), disp(ws), row_sq(ws), row_tot(ws), enc_blk(ws);
+        TmpBuf<uint2> enc_pair(ws);
         BSMR_TRY(runs_per_row.alloc(static_cast<size_t>(M) + 1));
         BSMR_TRY(enc_ptr.alloc(static_cast<size_t>(M) + 1));
         BSMR_TRY(disp.alloc(M ? M : 1));
@@ -838,7 +945,9 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
             BSMR_CUDA_OK(cudaMemcpyAsync(&num_runs, num_runs_d.ptr, 4, cudaMemcpyDeviceToHost, st));
             BSMR_CUDA_OK(cudaStreamSynchronize(st));
             BSMR_TRY(enc_blk.alloc(num_runs));
-            runs_split_kernel<<<grid_for(num_runs, kThreads, sm), kThreads, 0, st>>>(ukeys.ptr, num_runs, enc_blk.ptr, runs_per_row.ptr);
+            BSMR_TRY(enc_pair.alloc(num_runs));
+            runs_split_kernel<<<grid_for(num_runs, kThreads, sm), kThreads, 0, st>>>(ukeys.ptr, counts.ptr, num_runs, bd, kept_mask, enc_blk.ptr, enc_pair.ptr,
+                                                                                runs_per_row.ptr);
             ctx->launches++;
         }
         {
@@ -921,6 +1030,10 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
             cp.M = M; cp.nb = nb; cp.bd = bd; cp.first_stride = first_stride; cp.zero_rows = zero_rows; cp.alpha = alpha;
             cp.list_cap = list_cap; cp.num_slots = num_slots;
             cp.asc = asc; cp.enc_ptr = enc_ptr.ptr; cp.enc_blk = enc_blk.ptr; cp.counts = counts.ptr; cp.row_sq = row_sq.ptr;
+            cp.enc_pair = enc_pair.ptr;
+            // the thread-prune step pays where most pairs are rejected by the bounds (graphs: many column blocks, short rows);
+            // where rows are long (nips: 777 blocks each) every candidate needs a warp anyway and the scratch path is faster
+            cp.thread_prune = (flags & BSMR_ROW_THREAD_PRUNE_ON) ? 1u : (flags & BSMR_ROW_THREAD_PRUNE_OFF) ? 0u : (use_scratch ? 0u : 1u);
             cp.cluster_ids = cluster_ids.ptr; cp.lists = lists.ptr; cp.ctrl = ctrl.ptr; cp.status = status.ptr;
             void* args[] = {&cp};
             BSMR_CUDA_OK(cudaEventRecord(ctx->ev0, st));

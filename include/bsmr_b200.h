@@ -90,6 +90,11 @@ int bsmr_plan_destroy(bsmr_plan* plan);
 #define BSMR_ROW_EXACT_REDUCE     1u  /* sum every warp (mathematically intended Jaccard)  */
 #define BSMR_ROW_IDENTITY         2u  /* noReorderRow (src/rowReordering.cu:15-46): keep the
                                          original order, only strip empty rows              */
+/* or-ed in: which step the clustering kernel runs.  Default: chosen from the number of column blocks (thread-prune on
+ * graph-shaped inputs, the warp-per-candidate step with its per-warp scratch where rows are long).  Same permutation
+ * either way (tests run both on every case).                                                                      */
+#define BSMR_ROW_THREAD_PRUNE_ON  4u
+#define BSMR_ROW_THREAD_PRUNE_OFF 8u
 
 /* BSMR::rowReordering -> bsa_rowReordering_gpu (src/BSMR.cpp:27-50,
  * src/rowReordering.cu:1027-1095): dispersion scores, stable sort, BSA clustering with

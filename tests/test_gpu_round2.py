@@ -377,16 +377,52 @@ def test_dlmc_masks_full_size(pkg, ctx, oracle, sparsity):
         assert oracle.check_data(cpu, dP.cpu().numpy()) == 0, (sparsity, flags)
 
 
+@pytest.mark.parametrize("alpha", [0.1, 0.3, 0.5, 0.7, 0.9])
+def test_row_reorder_both_clustering_steps_vs_oracle(pkg, ctx, oracle, alpha):
+    """The clustering kernel has two step forms -- a warp per candidate (with per-warp scratch; the default where rows are
+    long) and a thread per candidate for the cheap rejections with warps only for the survivors (the default on graph-shaped
+    inputs).  Both must give the oracle's permutation on every small case, lossy and exact reduction."""
+    for name, M, N, ro, ci in small_cases(pkg):
+        for block_size in (16, 37):
+            for mode in (pkg.ROW_REFERENCE_COMPAT, pkg.ROW_EXACT_REDUCE):
+                want, want_compat, want_true = oracle.row_reordering(M, N, ro, ci, alpha, block_size, exact=(mode == pkg.ROW_EXACT_REDUCE))
+                for step in (pkg.ROW_THREAD_PRUNE_ON, pkg.ROW_THREAD_PRUNE_OFF):
+                    plan = pkg.Plan(ctx, M, N, ro, ci)
+                    plan.row_reorder(alpha, block_size=block_size, flags=mode | step)
+                    assert np.array_equal(plan.vector("reordered_rows"), want), (name, alpha, block_size, mode, step)
+                    info = plan.info()
+                    assert info["num_clusters"] == want_compat and info["num_clusters_true"] == want_true, (name, alpha, block_size, mode, step)
+                    plan.close()
+
+
+def test_nips_and_mask_clustering_with_the_thread_prune_step(pkg, ctx, oracle, golden_dir):
+    """Full-size inputs through the step form that is NOT their default: nips against the reference's GPU permutation
+    (golden), the 98 % mask (4095 clusters) against the sparse oracle."""
+    _, M, N, ro, ci = named_case(pkg, "nips")
+    plan = pkg.Plan(ctx, M, N, ro, ci)
+    plan.row_reorder(0.3, block_size=16, flags=pkg.ROW_THREAD_PRUNE_ON)
+    g = np.load(os.path.join(golden_dir, "nips_perm_ref_gpu.npz"))
+    assert np.array_equal(plan.vector("reordered_rows"), g["perm_ref_gpu"]) and plan.info()["num_clusters"] == int(g["num_clusters"])
+    _, M, N, ro, ci = named_case(pkg, "mask98")
+    perm, compat, _ = oracle.row_reordering_indexed(M, N, ro, ci, 0.3, 16)
+    for step in (pkg.ROW_THREAD_PRUNE_ON, pkg.ROW_THREAD_PRUNE_OFF):
+        plan = pkg.Plan(ctx, M, N, ro, ci)
+        plan.row_reorder(0.3, block_size=16, flags=step)
+        assert np.array_equal(plan.vector("reordered_rows"), perm) and plan.info()["num_clusters"] == compat, step
+
+
 def test_graph_clustering_vs_sparse_oracle(pkg, ctx, oracle):
     """8 192-row R-MAT graph (234 k nnz): the clustering pipeline against the sparse restatement of the oracle (itself pinned to the
     dense restatement and the reference on every small case).  Larger graphs: tests/cluster_scale_probe.py (timing)."""
     _, M, N, ro, ci = named_case(pkg, "graph13")
     bs = ctx.calculate_block_size(M, N)
-    plan = pkg.Plan(ctx, M, N, ro, ci)
-    plan.row_reorder(0.3, block_size=bs)
     perm, compat, true = oracle.row_reordering_indexed(M, N, ro, ci, 0.3, bs)
-    assert np.array_equal(plan.vector("reordered_rows"), perm)
-    assert plan.info()["num_clusters"] == compat and plan.info()["num_clusters_true"] == true
+    for step in (pkg.ROW_THREAD_PRUNE_ON, pkg.ROW_THREAD_PRUNE_OFF):
+        plan = pkg.Plan(ctx, M, N, ro, ci)
+        plan.row_reorder(0.3, block_size=bs, flags=step)
+        assert np.array_equal(plan.vector("reordered_rows"), perm), step
+        assert plan.info()["num_clusters"] == compat and plan.info()["num_clusters_true"] == true, step
+        plan.close()
 
 
 def sampled_check(torch, dA, dB, dP, ro_dev, ci_dev, nnz, n=1 << 17, seed=3):
