@@ -193,9 +193,6 @@ residual_sddmm_kernel(const uint32_t K, const float* __restrict__ A, const BT* _
 #ifndef BSMR_RES_UNROLL
 #define BSMR_RES_UNROLL 4   // entries in flight per lane group for KV < 4
 #endif
-#ifndef BSMR_RES_PREFETCH
-#define BSMR_RES_PREFETCH 0    // probe builds: 1 = the index triples of a chunk are fetched one chunk ahead
-#endif
 #ifndef BSMR_RES_K128_LPN
 #define BSMR_RES_K128_LPN 16   // lanes per entry of the fp32 kernel at K = 128: two 16-byte pieces per lane (measured against 32 x one:
                                // 1.20 against 1.35 ms on the 2^20-row graph, 34.8 against 38.9 us on nips)
@@ -286,19 +283,10 @@ residual_rows_kernel(const uint32_t K, const float* __restrict__ A, const BT* __
             out = res_out ? __ldg(res_out + es) : (uint32_t)es;   // NULL = identity (CSR order)
         }
     };
-    constexpr bool kPrefetch = BSMR_RES_PREFETCH != 0;
-    uint32_t nx_row = 0, nx_col = 0, nx_out = 0;
-    bool nx_valid = false;
-    if (kPrefetch && warp_global < num_chunks) load_idx(warp_global, nx_row, nx_col, nx_out, nx_valid);
     for (uint64_t chunk = warp_global; chunk < num_chunks; chunk += warp_stride) {
         uint32_t my_row, my_col, my_out;
         bool valid;
-        if constexpr (kPrefetch) {
-            my_row = nx_row; my_col = nx_col; my_out = nx_out; valid = nx_valid;
-            if (chunk + warp_stride < num_chunks) load_idx(chunk + warp_stride, nx_row, nx_col, nx_out, nx_valid);
-        } else {
-            load_idx(chunk, my_row, my_col, my_out, valid);
-        }
+        load_idx(chunk, my_row, my_col, my_out, valid);     // (fetching them one chunk ahead was measured slower: registers)
         uint32_t my_hot = 0;
         if constexpr (HINT) my_hot = (__ldg(col_hot + (my_col >> 5)) >> (my_col & 31)) & 1u;
         // Pass s (s = 0..LPN-1, entries in list order so that the A row in registers is reused) fills
@@ -486,7 +474,7 @@ int launch_residual_t(bsmr_ctx* ctx, const ResidualArgs& r) {
             else BSMR_ROWS(32, 2, HINT);                                                   \
         } else {                                                                           \
             if (K == 32) { if (BSMR_RES_HALVE_LANES) BSMR_ROWS(4, 2, HINT); else BSMR_ROWS(8, 1, HINT); } \
-            else if (K == 64) { if (BSMR_RES_HALVE_LANES) BSMR_ROWS(8, 2, HINT); else BSMR_ROWS(16, 1, HINT); } \
+            else if (K == 64) BSMR_ROWS(8, 2, HINT);       /* measured: mask 98 % 10.6 against 12.4 us hot (16 x 1) */ \
             else if (K == 128) BSMR_ROWS(BSMR_RES_K128_LPN, 128 / (BSMR_RES_K128_LPN * 4), HINT); \
             else if (K == 256) { if (BSMR_RES_HALVE_LANES) BSMR_ROWS(16, 4, HINT); else BSMR_ROWS(32, 2, HINT); } \
             else BSMR_ROWS(32, 4, HINT);                                                   \
