@@ -644,9 +644,9 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
                 // Measured on R-MAT graphs (ncu, profiles/r02d_*): the warp-per-candidate step spends ~300 warp instructions
                 // on a (cluster, row) pair that the bounds reject anyway -- 99.9 % of the pairs -- and the whole pipeline runs
                 // at the pace of that bookkeeping.  Here a THREAD applies the bounds to its candidate (the size bound in O(1),
-                // the shared-nnz bound by walking the row's <= 64 runs); warps evaluate only the survivors, in order, up to the
-                // first that joins.  The rejections are the same integers and comparisons, so the permutation is unchanged.
-                constexpr uint32_t kCpwB = 2;                               // survivors a warp evaluates per step
+                // the shared-nnz bound by walking the row's <= 64 runs); warps look only at the survivors -- longer rows first through
+                // the same bound with the lanes over the runs -- and evaluate in full what is left, up to the first that joins.  The rejections are the same integers and comparisons, so the permutation is unchanged.
+                constexpr uint32_t kCpwB = 8;                               // survivors a warp looks at per step
                 const uint32_t take = min(avail - cursor, (uint32_t)kClusterThreads);
                 ++tr_steps;
                 tr_cand += take;
@@ -691,7 +691,20 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
                     if (r < evaluated) {                          // warp-uniform
                         const uint32_t k = nth_maybe(r);
                         const uint32_t kpos = __ldcg(in + cursor + k);
-                        if (evaluate(__ldg(p.pos_info + kpos), cursor + k) && lane == 0) atomicMin(&s_first_join[par_b], k);
+                        const uint4 ki = __ldg(p.pos_info + kpos);
+                        // a row too long for a thread's walk got here on the size bound alone: the shared-nnz bound first, with
+                        // the warp's lanes over the runs (coalesced, ~40 instructions) -- most of them end here
+                        bool alive = true;
+                        if (prune && ki.z - ki.y > kWalkMax && s_sq_rep != 0 && ki.w != 0) {
+                            uint32_t sh = 0;
+                            for (uint32_t j = ki.y + lane; j < ki.z; j += 32) {
+                                const uint2 pr = __ldg(p.enc_pair + j);
+                                if ((pr.y >> 31) && rep[pr.x] != 0) sh += pr.y & 0x7FFFFFFFu;
+                            }
+                            sh = __reduce_add_sync(0xffffffffu, sh);
+                            alive = !(sh == 0 || (float)sh < bound * (float)ki.x);
+                        }
+                        if (alive && evaluate(ki, cursor + k) && lane == 0) atomicMin(&s_first_join[par_b], k);
                     }
                 }
                 __syncthreads();                                  // S2: every survivor decided
