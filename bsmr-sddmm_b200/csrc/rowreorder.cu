@@ -522,10 +522,10 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
         return sim > p.alpha;
     };
     // Cheap part of a similarity decision, for ONE candidate per THREAD: the zero cases, the size bound, and -- for rows of at
-    // most kWalkMax blocks -- the bound  sim <= (nnz in blocks shared with the representative) / (nnz in kept blocks),
+    // most kWalkMax (256) blocks -- the bound  sim <= (nnz in blocks shared with the representative) / (nnz in kept blocks),
     // evaluated by walking the row's runs serially.  Same integers and the same float comparison as the warp path's prune,
     // so the same candidates are rejected; false = rejected for sure, true = a warp has to evaluate it in full.
-    constexpr uint32_t kWalkMax = 64;
+    constexpr uint32_t kWalkMax = 256;
     auto cheap_maybe = [&](const uint4 info) -> bool {
         if (!prune) return true;
         const uint32_t s_rep = s_sq_rep, s_cmp = info.w;
@@ -644,9 +644,11 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
                 // Measured on R-MAT graphs (ncu, profiles/r02d_*): the warp-per-candidate step spends ~300 warp instructions
                 // on a (cluster, row) pair that the bounds reject anyway -- 99.9 % of the pairs -- and the whole pipeline runs
                 // at the pace of that bookkeeping.  Here a THREAD applies the bounds to its candidate (the size bound in O(1),
-                // the shared-nnz bound by walking the row's <= 64 runs); warps look only at the survivors -- longer rows first through
+                // the shared-nnz bound by walking the row's <= 256 runs); warps look only at the survivors -- longer rows first through
                 // the same bound with the lanes over the runs -- and evaluate in full what is left, up to the first that joins.  The rejections are the same integers and comparisons, so the permutation is unchanged.
-                constexpr uint32_t kCpwB = 8;                               // survivors a warp looks at per step
+                // (measured on the 2^20-row graph: walks of up to 64 runs with 2 survivors per warp and step 38.8 s; the same with
+                // 8 survivors per warp 67.9 s -- a warp's survivors are serial round trips and a long step starves the children)
+                constexpr uint32_t kCpwB = 2;                               // survivors a warp looks at per step
                 const uint32_t take = min(avail - cursor, (uint32_t)kClusterThreads);
                 ++tr_steps;
                 tr_cand += take;
