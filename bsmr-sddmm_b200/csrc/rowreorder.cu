@@ -522,10 +522,10 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
         return sim > p.alpha;
     };
     // Cheap part of a similarity decision, for ONE candidate per THREAD: the zero cases, the size bound, and -- for rows of at
-    // most kWalkMax (256) blocks -- the bound  sim <= (nnz in blocks shared with the representative) / (nnz in kept blocks),
+    // most kWalkMax blocks -- the bound  sim <= (nnz in blocks shared with the representative) / (nnz in kept blocks),
     // evaluated by walking the row's runs serially.  Same integers and the same float comparison as the warp path's prune,
     // so the same candidates are rejected; false = rejected for sure, true = a warp has to evaluate it in full.
-    constexpr uint32_t kWalkMax = 256;
+    constexpr uint32_t kWalkMax = 64;
     auto cheap_maybe = [&](const uint4 info) -> bool {
         if (!prune) return true;
         const uint32_t s_rep = s_sq_rep, s_cmp = info.w;
@@ -644,11 +644,12 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
                 // Measured on R-MAT graphs (ncu, profiles/r02d_*): the warp-per-candidate step spends ~300 warp instructions
                 // on a (cluster, row) pair that the bounds reject anyway -- 99.9 % of the pairs -- and the whole pipeline runs
                 // at the pace of that bookkeeping.  Here a THREAD applies the bounds to its candidate (the size bound in O(1),
-                // the shared-nnz bound by walking the row's <= 256 runs); warps look only at the survivors -- longer rows first through
-                // the same bound with the lanes over the runs -- and evaluate in full what is left, up to the first that joins.  The rejections are the same integers and comparisons, so the permutation is unchanged.
-                // (measured on the 2^20-row graph: walks of up to 64 runs with 2 survivors per warp and step 38.8 s; the same with
-                // 8 survivors per warp 67.9 s -- a warp's survivors are serial round trips and a long step starves the children)
-                constexpr uint32_t kCpwB = 2;                               // survivors a warp looks at per step
+                // the shared-nnz bound by walking the row's <= 64 runs); warps evaluate only the survivors, in order, up to the
+                // first that joins.  The rejections are the same integers and comparisons, so the permutation is unchanged.
+                // (variants measured on the 2^20-row graph, profiles/r02m_*, r02n_*: 8 survivors per warp with a warp-wide prune for the
+                // long rows 67.9 s, walks of up to 256 runs 45.9 s, this one 38.8 s: a warp's survivors are serial round trips, a
+                // long walk idles 31 lanes, and either way a longer step starves the children)
+                constexpr uint32_t kCpwB = 2;                               // survivors a warp evaluates per step
                 const uint32_t take = min(avail - cursor, (uint32_t)kClusterThreads);
                 ++tr_steps;
                 tr_cand += take;
@@ -693,20 +694,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
                     if (r < evaluated) {                          // warp-uniform
                         const uint32_t k = nth_maybe(r);
                         const uint32_t kpos = __ldcg(in + cursor + k);
-                        const uint4 ki = __ldg(p.pos_info + kpos);
-                        // a row too long for a thread's walk got here on the size bound alone: the shared-nnz bound first, with
-                        // the warp's lanes over the runs (coalesced, ~40 instructions) -- most of them end here
-                        bool alive = true;
-                        if (prune && ki.z - ki.y > kWalkMax && s_sq_rep != 0 && ki.w != 0) {
-                            uint32_t sh = 0;
-                            for (uint32_t j = ki.y + lane; j < ki.z; j += 32) {
-                                const uint2 pr = __ldg(p.enc_pair + j);
-                                if ((pr.y >> 31) && rep[pr.x] != 0) sh += pr.y & 0x7FFFFFFFu;
-                            }
-                            sh = __reduce_add_sync(0xffffffffu, sh);
-                            alive = !(sh == 0 || (float)sh < bound * (float)ki.x);
-                        }
-                        if (alive && evaluate(ki, cursor + k) && lane == 0) atomicMin(&s_first_join[par_b], k);
+                        if (evaluate(__ldg(p.pos_info + kpos), cursor + k) && lane == 0) atomicMin(&s_first_join[par_b], k);
                     }
                 }
                 __syncthreads();                                  // S2: every survivor decided
@@ -1048,7 +1036,10 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
             cp.enc_pair = enc_pair.ptr;
             // the thread-prune step pays where most pairs are rejected by the bounds (graphs: many column blocks, short rows);
             // where rows are long (nips: 777 blocks each) every candidate needs a warp anyway and the scratch path is faster
-            cp.thread_prune = (flags & BSMR_ROW_THREAD_PRUNE_ON) ? 1u : (flags & BSMR_ROW_THREAD_PRUNE_OFF) ? 0u : (use_scratch ? 0u : 1u);
+            // Measured (R-MAT, profiles/r02e_* against r02l_*): 2^20 rows 61.4 -> 38.8 s, 2^19 rows 16.0 -> 14.2 s, but 2^17 rows
+            // 1.8 -> 3.6 s (three barriers per step instead of two, and the pipeline is latency-bound there): on from 2^18 rows.
+            const bool graph_sized = !use_scratch && (M - zero_rows) >= (1u << 18);
+            cp.thread_prune = (flags & BSMR_ROW_THREAD_PRUNE_ON) ? 1u : (flags & BSMR_ROW_THREAD_PRUNE_OFF) ? 0u : (graph_sized ? 1u : 0u);
             cp.cluster_ids = cluster_ids.ptr; cp.lists = lists.ptr; cp.ctrl = ctrl.ptr; cp.status = status.ptr;
             void* args[] = {&cp};
             BSMR_CUDA_OK(cudaEventRecord(ctx->ev0, st));
