@@ -649,6 +649,9 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
                 // (variants measured on the 2^20-row graph, profiles/r02m_*, r02n_*: 8 survivors per warp with a warp-wide prune for the
                 // long rows 67.9 s, walks of up to 256 runs 45.9 s, this one 38.8 s: a warp's survivors are serial round trips, a
                 // long walk idles 31 lanes, and either way a longer step starves the children)
+                // (variants measured on the 2^20-row graph, profiles/r02m_*, r02n_*: 8 survivors per warp with a warp-wide prune for
+                // the long rows 67.9 s, walks of up to 256 runs 45.9 s, this one 38.8 s: a warp's survivors are serial round trips, a
+                // long walk idles 31 lanes, and either way a longer step starves the children)
                 constexpr uint32_t kCpwB = 2;                               // survivors a warp evaluates per step
                 const uint32_t take = min(avail - cursor, (uint32_t)kClusterThreads);
                 ++tr_steps;
