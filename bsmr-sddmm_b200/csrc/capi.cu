@@ -128,6 +128,7 @@ int bsmr_ctx_create(int device, void* cuda_stream, bsmr_ctx** out) {
 int bsmr_ctx_destroy(bsmr_ctx* ctx) {
     if (!ctx) return BSMR_OK;
     cudaSetDevice(ctx->device);
+    if (ctx->nccl_comm) bsmr_ctx_comm_destroy(ctx);       // communicator, its stream and events (comm.cu)
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);

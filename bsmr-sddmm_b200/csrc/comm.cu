@@ -181,8 +181,8 @@ int assemble_sharded(bsmr_plan* plan, uint32_t K, const float* dA, const float* 
     const uint64_t e0 = pre[pb], e1 = pre[pe];
     BSMR_TRY(plan->shard_p.alloc(plan->nnz));                        // this rank's P in CSR positions (only its entries are defined)
     BSMR_TRY(plan->shard_slice.alloc(rank == root ? plan->nnz : (size_t)(e1 - e0)));
-    // the root's own slice is packed straight into its place in the assembled array
-    float* slice0 = rank == root ? plan->shard_slice.ptr : plan->shard_slice.ptr - e0;     // slice0 + e = home of entry e
+    // the root's own slice is packed straight into its place in the assembled array; elsewhere the buffer holds the shard only
+    const uint64_t slice_base = rank == root ? 0 : e0;             // entry e lives at shard_slice[e - slice_base]
     const int grid = ctx->sm_count * 8;
     // measured on configs[4]: at 2 ranks the transfer is 8 % of the step and chunking costs more than it hides (15.4 -> 17.6 ms:
     // four launches with four tails, NCCL's copy kernels next to the gather kernel); from 4 ranks on the transfer is a third
@@ -194,6 +194,10 @@ int assemble_sharded(bsmr_plan* plan, uint32_t K, const float* dA, const float* 
     BSMR_CUDA_OK(cudaStreamWaitEvent(cs, ctx->comm_ev[8], 0));      // the buffers' previous readers (last call's un-permute) are done
     std::vector<std::vector<uint32_t>> cb(world);
     for (int r = 0; r < world; ++r) cb[r] = chunk_bounds(plan, r, chunks);
+    struct RangeGuard {       // whatever happens below, the plan keeps the rank's whole shard
+        bsmr_plan* plan; uint32_t b, e; bool on;
+        ~RangeGuard() { if (on) apply_panel_range(plan, b, e); }
+    } range_guard{plan, pb, pe, chunks > 1};
     int status = BSMR_OK;
     for (int c = 0; c < chunks && status == BSMR_OK; ++c) {
         const uint32_t qb = cb[rank][c], qe = cb[rank][c + 1];
@@ -205,7 +209,7 @@ int assemble_sharded(bsmr_plan* plan, uint32_t K, const float* dA, const float* 
         BSMR_CUDA_OK(cudaStreamWaitEvent(cs, ctx->comm_ev[c], 0));
         const uint64_t s0 = pre[qb], s1 = pre[qe];
         if (s1 > s0) {
-            pack_p_kernel<<<grid, 256, 0, cs>>>(plan->shard_p.ptr, plan->flat_out.ptr, s0, s1, slice0 + s0);
+            pack_p_kernel<<<grid, 256, 0, cs>>>(plan->shard_p.ptr, plan->flat_out.ptr, s0, s1, plan->shard_slice.ptr + (s0 - slice_base));
             ctx->launches++;
         }
         if (world > 1) {
@@ -216,7 +220,7 @@ int assemble_sharded(bsmr_plan* plan, uint32_t K, const float* dA, const float* 
                     if (r != root && e > b) nr = n.Recv(plan->shard_slice.ptr + b, e - b, ncclFloat32, r, comm_of(ctx), cs);
                 }
             } else if (s1 > s0) {
-                nr = n.Send(slice0 + s0, s1 - s0, ncclFloat32, root, comm_of(ctx), cs);
+                nr = n.Send(plan->shard_slice.ptr + (s0 - slice_base), s1 - s0, ncclFloat32, root, comm_of(ctx), cs);
             }
             const ncclResult_t ne = n.GroupEnd();
             if (nr != ncclSuccess || ne != ncclSuccess) {
@@ -225,7 +229,6 @@ int assemble_sharded(bsmr_plan* plan, uint32_t K, const float* dA, const float* 
             }
         }
     }
-    if (chunks > 1) apply_panel_range(plan, pb, pe);                 // the plan keeps the rank's whole shard
     BSMR_TRY(status);
     BSMR_CUDA_OK(cudaEventRecord(ctx->comm_ev[7], cs));
     BSMR_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->comm_ev[7], 0));      // join: every slice has arrived / left
