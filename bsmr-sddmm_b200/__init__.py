@@ -25,6 +25,7 @@ NULL_VALUE = 0xFFFFFFFF
 
 ROW_REFERENCE_COMPAT, ROW_EXACT_REDUCE, ROW_IDENTITY = 0, 1, 2
 ROW_THREAD_PRUNE_ON, ROW_THREAD_PRUNE_OFF = 4, 8      # or-ed in: which step form the clustering kernel runs (default: by shape)
+ROW_STAGE_ON, ROW_STAGE_OFF = 16, 32                   # or-ed in: the 32-clusters-per-CTA stage kernel or the cluster-per-CTA kernel (default: by shape)
 SDDMM_DEFAULT, SDDMM_RESIDUAL_ONLY, SDDMM_NO_REORDER, SDDMM_NO_WIDE, SDDMM_THREE_KERNEL = 0, 1, 2, 4, 8
 TICKET_ALL = 0xFFFFFFFFFFFFFFFF
 CUDA_STREAM_LEGACY = 1          # cudaStreamLegacy: the legacy default stream as an explicit handle

@@ -186,6 +186,7 @@ struct ClusterParams {
     const uint32_t* row_sq;    // row -> (lossy) sum of squares
     const uint4* pos_info;     // position -> {nnz in kept blocks, first run, end run, (lossy) sum of squares}
     uint32_t bd_mask;          // bd - 1 when bd is a power of two (block % bd without a division), else 0
+    uint32_t* repd;            // stage kernel: per CTA 32 dense representatives of nb u32 counts
     uint32_t* cluster_ids;     // position -> cluster id (pre-set: 0 for empty rows, NULL otherwise)
     uint32_t* lists;           // num_slots x list_cap positions; list of cluster c lives in slot c % num_slots
     unsigned long long* ctrl;  // per slot: list id << 33 | entries << 1 | producer-done   (single writer, release-published)
@@ -825,6 +826,851 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
     }
 }
 
+// ---- the stage kernel: one CTA per RUN of kStageReps consecutive clusters ---------------------------------------------
+//
+// Same pipeline between the CTAs as bsa_cluster_kernel (lists in rotation, release-published control words, cooperative
+// launch), but the unit that owns a list is a STAGE: clusters (s-1)*32+1 .. s*32.  Row-major view of the reference's
+// semantics: a row walks the clusters in ascending order, joins the first whose (current) representative accepts it, and
+// founds the next cluster when none does.  A stage therefore keeps 32 representatives; a row is tested against all of them
+// while its pos_info / block list is in the thread's registers, and is forwarded ONCE to the next stage -- the list traffic,
+// the polls and the pipeline hops of 32 clusters collapse into one.
+//   * the stage's representatives live as (a) `slots`: one word per column block, bit r = representative r has nnz in the
+//     block (shared memory), (b) dense u32 count vectors in global memory (L2; only the full evaluation reads them),
+//     (c) the per-reference-thread / per-reference-warp partial sums of the representative alone (shared memory)
+//   * streaming step: up to 1024 rows, one per THREAD.  Size bound against the 32 representatives (two compares each), then
+//     ONE walk over the row's runs accumulates the nnz shared with all 32 representatives at once in bit-sliced counters
+//     (8 planes of 32 bits: plane q holds bit q of the 32 sums; adding a run's count under the slot word is a ripple of
+//     AND / XOR), and a bit-sliced compare against the row's threshold gives the mask of representatives the row may still
+//     join.  Rows with an empty mask (99.9 % on graphs) are forwarded; the others get a warp each that evaluates the
+//     reference's similarity (same float operations in the same order as bsa_cluster_kernel) against the set bits in
+//     ascending order.  The first row that joins ends the step: its representative is refreshed, the rows behind it are redone.
+//   * founding: while the stage has fewer than 32 representatives the stream is consumed row by row: the row joins the first
+//     existing representative that accepts it (the candidates are evaluated by different warps at once) or founds the next.
+// All bounds are exact (they only skip pairs whose similarity cannot exceed alpha), so the permutation is the reference's.
+constexpr uint32_t kStageReps = 32;
+constexpr uint32_t kStageTerms = 8;    // column blocks per reference thread the stage kernel takes: nb <= 8 * bd
+
+__global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterParams p) {
+    extern __shared__ uint32_t smem[];
+    const uint32_t nbp = (p.nb + 3u) & ~3u;
+    uint32_t* slots = smem;                                                    // [nb]   bit r: representative r has nnz in the block
+    float* part_max = reinterpret_cast<float*>(smem + nbp);                    // [32][1024] per-reference-thread max partial
+    float* warp_max = part_max + kStageReps * 1024;                            // [32][32]   the same after the warp butterfly
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(warp_max + kStageReps * 32);   // [1024] this step's verdict masks
+    uint16_t* scratch = reinterpret_cast<uint16_t*>(s_mask + 1024);               // [nb] one long row, expanded (zero between uses)
+    __shared__ uint32_t sq_s[kStageReps];      // (lossy) sum of squares of representative r
+    __shared__ uint32_t tot_s[kStageReps];     // (lossy) sum of its counts
+    __shared__ uint32_t s_sh[kStageReps];      // shared_mask_scratch: nnz the row shares with representative r
+    __shared__ uint32_t s_fpos[32];            // founding: the next rows of the input, fetched together ...
+    __shared__ uint4 s_finfo[32];              // ... their pos_info ...
+    __shared__ uint2 s_fruns[32 * 32];         // ... and the runs of those with at most 32
+    __shared__ float nr_s[kStageReps];         // its square root
+    __shared__ float2 l_s[kStageReps];         // {L1 norm of the normalised kept entries, bound * that}
+    __shared__ uint32_t s_nz;                  // bit r: sq_s[r] != 0
+    __shared__ float s_blr_min, s_lr_max;      // over the representatives with sq != 0: min of l_s.y, max of l_s.x
+    __shared__ uint32_t s_red[2];
+    __shared__ uint32_t s_ev[2][32];
+    __shared__ uint32_t s_long[2][32];         // bit: the event row still needs the warp-level shared-nnz bound
+    __shared__ uint32_t s_first[2];
+    __shared__ float s_fv[32];
+    __shared__ uint32_t s_qmask[64];           // per event row of the step: representatives left for the scratch pass (rows of > 32 runs)
+    __shared__ uint32_t s_touched;             // reference warps that own a block of the row in the scratch
+    __shared__ float2 s_res[kStageReps * 32];  // scratch pass: per (representative, reference warp) the {min, max} sums
+    __shared__ unsigned long long s_ctrl;
+    __shared__ uint32_t s_stop;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t nw = p.bd >> 5;
+    const float bound = p.alpha - 1e-3f;
+    constexpr uint32_t kWarps = kClusterThreads / 32;
+    constexpr uint32_t kWalkMax = 64;
+    constexpr uint32_t kNone = 0xFFFFFFFFu;
+    uint32_t* const repd = p.repd + (size_t)blockIdx.x * kStageReps * p.nb;     // dense representatives of this CTA
+    auto mod_bd = [&](uint32_t blk) -> uint32_t { return p.bd_mask ? (blk & p.bd_mask) : blk % p.bd; };
+
+    // add the row's runs to representative r (dense counts + slot bits); the caller's next barrier closes it
+    auto absorb = [&](const uint4 info, uint32_t r) {
+        uint32_t* rd = repd + (size_t)r * p.nb;
+        for (uint32_t j = info.y + tid; j < info.z; j += kClusterThreads) {
+            const uint32_t blk = __ldg(p.enc_blk + j);
+            rd[blk] = __ldcg(rd + blk) + __ldg(p.counts + j);          // a row's runs are distinct blocks: no conflicts
+            atomicOr(&slots[blk], 1u << r);
+        }
+    };
+    // everything derived from representative r; called by the whole CTA after an absorb
+    auto refresh = [&](uint32_t r, uint32_t nrep_now) {
+        const uint32_t* rd = repd + (size_t)r * p.nb;
+        if (tid == 0) { s_red[0] = 0; s_red[1] = 0; }
+        __syncthreads();                                   // closes the absorb
+        uint32_t sq = 0, tt = 0;
+        if (tid < p.bd)
+            for (uint32_t i = tid; i < p.nb; i += p.bd) { const uint32_t v = __ldcg(rd + i); sq += v * v; tt += v; }
+        sq = __reduce_add_sync(0xffffffffu, sq);
+        tt = __reduce_add_sync(0xffffffffu, tt);
+        if (lane == 0 && tid < p.bd && ((p.kept_mask >> wid) & 1u)) { atomicAdd(&s_red[0], sq); atomicAdd(&s_red[1], tt); }
+        __syncthreads();
+        const uint32_t sqr = s_red[0], ttr = s_red[1];
+        const float nr = sqrtf((float)sqr);
+        float mx = 0.f;
+        if (tid < p.bd) {
+            for (uint32_t i = tid; i < p.nb; i += p.bd) mx += (float)__ldcg(rd + i) / nr;
+            part_max[r * 1024 + tid] = mx;
+        }
+#pragma unroll
+        for (int w = 1; w < 32; w <<= 1) mx += __shfl_xor_sync(0xffffffffu, mx, w);
+        if (lane == 0) warp_max[r * 32 + wid] = tid < p.bd ? mx : 0.f;
+        if (tid == 0) {
+            sq_s[r] = sqr;
+            tot_s[r] = ttr;
+            nr_s[r] = nr;
+            const float l1 = sqr ? (float)ttr / nr : 0.f;
+            l_s[r] = make_float2(l1, bound * l1);
+            if (sqr) s_nz |= 1u << r;
+        }
+        __syncthreads();
+        if (wid == 0) {
+            const bool on = lane < nrep_now && ((s_nz >> lane) & 1u);
+            float lo = on ? l_s[lane].y : INFINITY, hi = on ? l_s[lane].x : 0.f;
+#pragma unroll
+            for (int w = 1; w < 32; w <<= 1) {
+                lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, w));
+                hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, w));
+            }
+            if (lane == 0) { s_blr_min = lo; s_lr_max = hi; s_red[0] = 0; s_red[1] = 0; }
+        }
+        __syncthreads();
+    };
+    // Which of the first `nrep` representatives can this row still join?  Exact bounds only (a cleared bit = similarity
+    // cannot exceed alpha); one thread, no synchronisation.
+    // the zero cases and the size bound: which of the first `nrep` representatives are still possible (no block list read)
+    auto size_mask = [&](const uint4 info, uint32_t nrep) -> uint32_t {
+        const uint32_t live = nrep >= 32 ? 0xFFFFFFFFu : ((1u << nrep) - 1u);
+        const uint32_t nz = s_nz;
+        if (info.w == 0) return live & ~nz;        // zero (kept) encoding: similarity 1 with an all-zero representative, 0 otherwise (:258-263)
+        const float lc = (float)info.x / sqrtf((float)info.w);
+        const float blc = bound * lc;
+        if (lc < s_blr_min || s_lr_max < blc) return 0u;
+        uint32_t alive = 0;
+        if (nrep >= 32) {
+#pragma unroll
+            for (uint32_t r = 0; r < 32; ++r) {
+                const float2 l = l_s[r];
+                alive |= (uint32_t)(lc >= l.y && l.x >= blc) << r;
+            }
+        } else {
+            for (uint32_t r = 0; r < nrep; ++r) {
+                const float2 l = l_s[r];
+                alive |= (uint32_t)(lc >= l.y && l.x >= blc) << r;
+            }
+        }
+        return alive & nz & live;
+    };
+    // One WARP, any row length: lane r sums the row's (kept) nnz in the blocks it shares with representative r; returns the
+    // representatives of `alive` that pass  shared >= 1 and shared >= bound * (kept nnz of the row).  Not for info.w == 0.
+    auto warp_shared_mask = [&](const uint4 info, uint32_t alive, const uint2* sruns) -> uint32_t {
+        uint32_t sh = 0;
+        for (uint32_t j0 = info.y; j0 < info.z; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            const uint2 pr = j < info.z ? (sruns ? sruns[lane] : __ldg(p.enc_pair + j)) : make_uint2(0u, 0u);   // sruns: rows of <= 32 runs
+            const uint32_t m = (pr.y >> 31) ? (slots[pr.x] & alive) : 0u;
+            const uint32_t cnt = pr.y & 0x7FFFFFFFu;
+            uint32_t hit = __ballot_sync(0xffffffffu, m != 0);
+            while (hit) {
+                const int i = __ffs(hit) - 1;
+                hit &= hit - 1;
+                const uint32_t mi = __shfl_sync(0xffffffffu, m, i);
+                const uint32_t ci = __shfl_sync(0xffffffffu, cnt, i);
+                if ((mi >> lane) & 1u) sh += ci;
+            }
+        }
+        const bool ok = sh != 0 && !((float)sh < bound * (float)info.x);
+        return __ballot_sync(0xffffffffu, ok) & alive;
+    };
+    // One THREAD per row: size bound, then (rows of at most kWalkMax runs and fewer than 256 kept nnz) the shared-nnz bound
+    // for all representatives at once in bit-sliced counters.  Longer rows come back with is_long set and the size mask: a
+    // warp finishes them with warp_shared_mask.
+    auto bounds_mask = [&](const uint4 info, uint32_t nrep, bool& is_long) -> uint32_t {
+        is_long = false;
+        const uint32_t alive = size_mask(info, nrep);
+        if (alive == 0 || info.w == 0) return alive;
+        if (info.z - info.y > kWalkMax || info.x >= 256u) { is_long = true; return alive; }
+        uint32_t S[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) S[q] = 0;
+        for (uint32_t j = info.y; j < info.z; ++j) {
+            const uint2 pr = __ldg(p.enc_pair + j);
+            if (pr.y >> 31) {
+                const uint32_t m = slots[pr.x] & alive;
+                if (m) {
+                    const uint32_t cnt = pr.y & 0x7FFFFFFFu;            // < 256: the row's kept nnz are
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if ((cnt >> k) & 1u) {
+                            uint32_t carry = m;
+#pragma unroll
+                            for (int q = k; q < 8; ++q) {
+                                const uint32_t t = S[q] & carry;
+                                S[q] ^= carry;
+                                carry = t;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // survive iff sh >= 1 and (float)sh >= bound * tot, i.e. sh >= T (sums below 2^24 convert exactly)
+        const float thr = bound * (float)info.x;
+        uint32_t T = thr > 0.f ? (uint32_t)ceilf(thr) : 0u;
+        if (T == 0) T = 1;
+        if (T > 255u) return 0u;                                       // sh <= tot < 256
+        uint32_t ge = 0xFFFFFFFFu;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ge = ((T >> q) & 1u) ? (S[q] & ge) : (S[q] | ge);
+        return ge & alive;
+    };
+    // does the row join representative r?  One warp; the float operations of calculate_similarity_norm_weighted_jaccard
+    // in the reference's order (see bsa_cluster_kernel::evaluate; here the normalised representative is recomputed from
+    // the dense counts: the same division on the same operands)
+    auto evaluate_pair = [&](const uint4 info, const uint32_t r, const uint2* sruns) -> bool {
+        const uint32_t b = info.y, e = info.z, s_cmp = info.w;
+        const uint32_t s_rep = sq_s[r];
+        if (s_rep == 0 && s_cmp == 0) return 1.0f > p.alpha;
+        if (s_rep == 0 || s_cmp == 0) return 0.0f > p.alpha;
+        const uint32_t* rd = repd + (size_t)r * p.nb;
+        const float* pm = part_max + r * 1024;
+        const float nr = nr_s[r];
+        const uint32_t n = e - b;
+        const float nc = sqrtf((float)s_cmp);
+        float my_min = 0.f, my_max = lane < nw ? warp_max[r * 32 + lane] : 0.f;
+        {   // n <= 32 (longer rows: evaluate_scratch): patch only the reference threads that own one of the row's blocks
+            const bool valid = lane < n;
+            const uint2 spr = (valid && sruns) ? sruns[lane] : make_uint2(0u, 0u);
+            const uint32_t blk = valid ? (sruns ? spr.x : __ldg(p.enc_blk + b + lane)) : 0u;
+            const uint32_t cnt = valid ? (sruns ? (spr.y & 0x7FFFFFFFu) : __ldg(p.counts + b + lane)) : 0u;
+            const uint32_t t = mod_bd(blk);
+            const bool kept = valid && ((p.kept_mask >> (t >> 5)) & 1u);
+            {
+                const uint32_t sh = __reduce_add_sync(0xffffffffu, (kept && ((slots[blk] >> r) & 1u)) ? cnt : 0u);
+                const uint32_t tot = __reduce_add_sync(0xffffffffu, kept ? cnt : 0u);
+                if (sh == 0 || (float)sh < bound * (float)tot) return false;
+            }
+            const uint32_t peers = __match_any_sync(0xffffffffu, valid ? t : 0xFFFF0000u + lane);
+            const bool leader = valid && lane == (uint32_t)(__ffs(peers) - 1);
+            uint32_t rest = peers;
+            float pmin = 0.f, pmax = 0.f;
+            for (uint32_t m = 0; m * p.bd < p.nb; ++m) {
+                const uint32_t i = t + m * p.bd;
+                const int q = rest ? __ffs(rest) - 1 : 0;
+                const uint32_t blk_q = __shfl_sync(0xffffffffu, blk, q);
+                const uint32_t cnt_q = __shfl_sync(0xffffffffu, cnt, q);
+                if (leader && i < p.nb) {
+                    const float a = (float)__ldcg(rd + i) / nr;
+                    if (rest && blk_q == i) {
+                        const float c = (float)cnt_q / nc;
+                        pmin += fminf(a, c);
+                        pmax += fmaxf(a, c);
+                        rest &= rest - 1;
+                    } else {
+                        pmax += a;
+                    }
+                }
+            }
+            uint32_t touched = __reduce_or_sync(0xffffffffu, leader ? 1u << (t >> 5) : 0u);
+            while (touched) {
+                const uint32_t w = __ffs(touched) - 1;
+                touched &= touched - 1;
+                float leaf_min = 0.f, leaf_max = pm[(w << 5) + lane];
+                uint32_t sel = __ballot_sync(0xffffffffu, leader && (t >> 5) == w);
+                while (sel) {
+                    const int src = __ffs(sel) - 1;
+                    sel &= sel - 1;
+                    const uint32_t tl = __shfl_sync(0xffffffffu, t & 31u, src);
+                    const float vmin = __shfl_sync(0xffffffffu, pmin, src);
+                    const float vmax = __shfl_sync(0xffffffffu, pmax, src);
+                    if (lane == tl) {
+                        leaf_min = vmin;
+                        leaf_max = vmax;
+                    }
+                }
+#pragma unroll
+                for (int x = 1; x < 32; x <<= 1) {
+                    leaf_min += __shfl_xor_sync(0xffffffffu, leaf_min, x);
+                    leaf_max += __shfl_xor_sync(0xffffffffu, leaf_max, x);
+                }
+                if (lane == w) {
+                    my_min = leaf_min;
+                    my_max = leaf_max;
+                }
+            }
+        }
+        for (uint32_t stride = p.first_stride; stride >= 1; stride >>= 1) {
+            const float tmin = __shfl_down_sync(0xffffffffu, my_min, stride);
+            const float tmax = __shfl_down_sync(0xffffffffu, my_max, stride);
+            if (lane < stride && lane + stride < 32) {
+                my_min += tmin;
+                my_max += tmax;
+            }
+        }
+        const float sim = __shfl_sync(0xffffffffu, my_min, 0) / __shfl_sync(0xffffffffu, my_max, 0);
+        return sim > p.alpha;
+    };
+    // Rows of more than 32 runs: the row is expanded ONCE into the CTA's dense scratch (16-bit counts: a count never exceeds
+    // the block size) and up to 32 warps evaluate it against 32 representatives at the same time -- every term of every
+    // touched reference thread is one shared-memory read and one coalesced read of the dense representative, no search.
+    auto expand_row = [&](const uint4 info) {
+        uint32_t touched = 0;
+        for (uint32_t j = info.y + tid; j < info.z; j += kClusterThreads) {
+            const uint32_t blk = __ldg(p.enc_blk + j);
+            scratch[blk] = (uint16_t)__ldg(p.counts + j);
+            touched |= 1u << (mod_bd(blk) >> 5);
+        }
+        touched = __reduce_or_sync(0xffffffffu, touched);
+        if (lane == 0 && touched) atomicOr(&s_touched, touched);
+    };
+    auto clear_row = [&](const uint4 info) {
+        for (uint32_t j = info.y + tid; j < info.z; j += kClusterThreads) scratch[__ldg(p.enc_blk + j)] = 0;
+        if (tid == 0) s_touched = 0;
+    };
+    // The whole CTA, after expand_row + barrier: does the row in the scratch join one of the representatives `mk`?  CTA warp w
+    // plays REFERENCE warp w for every candidate representative: the row's terms of reference thread t = 32 w + lane are read
+    // from the scratch once; per representative the thread's sums are recomputed from the dense counts only where the row
+    // has a block (others: the representative's own partial sum), two representatives per iteration so that their loads
+    // overlap; butterfly; the per-warp pairs go to s_res.  After a barrier one warp per representative runs the reference's
+    // tree over the 32 pairs and records an acceptance as key | r in s_first.  Ends with a barrier.
+    auto scratch_pass = [&](const uint4 info, const uint32_t mk, const uint32_t key, uint32_t* first) {
+        const uint32_t touched = s_touched;
+        const float nc = sqrtf((float)info.w);
+        if (wid < nw && ((touched >> wid) & 1u)) {
+            const uint32_t t = (wid << 5) + lane;
+            float cf[kStageTerms];                              // the row's normalised count per term, 0 = no block
+            bool mine = false;
+#pragma unroll
+            for (uint32_t m = 0; m < kStageTerms; ++m) {
+                const uint32_t i = t + m * p.bd;
+                const uint32_t cnt = i < p.nb ? scratch[i] : 0u;
+                cf[m] = cnt ? (float)cnt / nc : 0.f;
+                mine |= cnt != 0;
+            }
+            auto one = [&](const uint32_t r, float& amin, float& amax) {
+                const uint32_t* rd = repd + (size_t)r * p.nb;
+                const float nr = nr_s[r];
+                amin = 0.f;
+                if (!mine) { amax = part_max[r * 1024 + t]; return; }
+                uint32_t v[kStageTerms];
+#pragma unroll
+                for (uint32_t m = 0; m < kStageTerms; ++m) {
+                    const uint32_t i = t + m * p.bd;
+                    v[m] = i < p.nb ? __ldcg(rd + i) : 0u;
+                }
+                amax = 0.f;
+#pragma unroll
+                for (uint32_t m = 0; m < kStageTerms; ++m) {
+                    if (t + m * p.bd < p.nb) {
+                        const float a = (float)v[m] / nr;
+                        if (cf[m] != 0.f) {
+                            amin += fminf(a, cf[m]);
+                            amax += fmaxf(a, cf[m]);
+                        } else {
+                            amax += a;
+                        }
+                    }
+                }
+            };
+            uint32_t rest = mk;
+            while (rest) {
+                const uint32_t ra = __ffs(rest) - 1;
+                rest &= rest - 1;
+                const uint32_t rb = rest ? __ffs(rest) - 1 : ra;
+                rest &= rest - 1;                               // (0 & anything = 0)
+                float amin, amax, bmin, bmax;
+                one(ra, amin, amax);
+                one(rb, bmin, bmax);
+#pragma unroll
+                for (int x = 1; x < 32; x <<= 1) {
+                    amin += __shfl_xor_sync(0xffffffffu, amin, x);
+                    amax += __shfl_xor_sync(0xffffffffu, amax, x);
+                    bmin += __shfl_xor_sync(0xffffffffu, bmin, x);
+                    bmax += __shfl_xor_sync(0xffffffffu, bmax, x);
+                }
+                if (lane == 0) {
+                    s_res[ra * 32 + wid] = make_float2(amin, amax);
+                    s_res[rb * 32 + wid] = make_float2(bmin, bmax);
+                }
+            }
+        }
+        __syncthreads();
+        if (wid < __popc(mk)) {
+            const uint32_t r = __fns(mk, 0, (int)wid + 1);
+            const uint32_t s_rep = sq_s[r], s_cmp = info.w;
+            bool joins;
+            if (s_rep == 0 && s_cmp == 0) joins = 1.0f > p.alpha;
+            else if (s_rep == 0 || s_cmp == 0) joins = 0.0f > p.alpha;
+            else {
+                float my_min = 0.f, my_max = 0.f;               // lane = reference warp
+                if (lane < nw) {
+                    if ((touched >> lane) & 1u) {
+                        const float2 v = s_res[r * 32 + lane];
+                        my_min = v.x;
+                        my_max = v.y;
+                    } else {
+                        my_max = warp_max[r * 32 + lane];
+                    }
+                }
+                for (uint32_t stride = p.first_stride; stride >= 1; stride >>= 1) {
+                    const float tmin = __shfl_down_sync(0xffffffffu, my_min, stride);
+                    const float tmax = __shfl_down_sync(0xffffffffu, my_max, stride);
+                    if (lane < stride && lane + stride < 32) {
+                        my_min += tmin;
+                        my_max += tmax;
+                    }
+                }
+                const float sim = __shfl_sync(0xffffffffu, my_min, 0) / __shfl_sync(0xffffffffu, my_max, 0);
+                joins = sim > p.alpha;
+            }
+            if (joins && lane == 0) atomicMin(first, key | r);
+        }
+        __syncthreads();
+    };
+    // The whole CTA, row expanded in the scratch (barrier done): the shared-nnz bound of warp_shared_mask without touching
+    // global memory -- every thread looks at its column blocks.  Two barriers; every thread returns the same mask.
+    auto shared_mask_scratch = [&](const uint4 info, uint32_t alive) -> uint32_t {
+        if (tid < kStageReps) s_sh[tid] = 0;
+        __syncthreads();
+        for (uint32_t blk = tid; blk < p.nb; blk += kClusterThreads) {
+            const uint32_t cnt = scratch[blk];
+            if (cnt && ((p.kept_mask >> (mod_bd(blk) >> 5)) & 1u)) {
+                uint32_t m = slots[blk] & alive;
+                while (m) {
+                    atomicAdd(&s_sh[__ffs(m) - 1], cnt);
+                    m &= m - 1;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t sh = s_sh[lane];
+        const bool ok = sh != 0 && !((float)sh < bound * (float)info.x);
+        return __ballot_sync(0xffffffffu, ok) & alive;
+    };
+    // A row joins representative r: absorb + refresh in one, with the integer sums updated from the row's blocks alone
+    // (sum of squares += (old + cnt)^2 - old^2 over the kept blocks, wrapping like the reference's) and ONE dense pass.
+    auto join_absorb_refresh = [&](const uint4 info, uint32_t r, uint32_t nrep_now, const uint2* sruns) {
+        uint32_t* rd = repd + (size_t)r * p.nb;
+        uint32_t dsq = 0, dtot = 0;
+        for (uint32_t j = info.y + tid; j < info.z; j += kClusterThreads) {
+            const uint2 pr = sruns ? sruns[tid] : __ldg(p.enc_pair + j);
+            const uint32_t cnt = pr.y & 0x7FFFFFFFu;
+            const uint32_t old = __ldcg(rd + pr.x);
+            rd[pr.x] = old + cnt;
+            atomicOr(&slots[pr.x], 1u << r);
+            if (pr.y >> 31) {
+                dsq += (old + cnt) * (old + cnt) - old * old;
+                dtot += cnt;
+            }
+        }
+        dsq = __reduce_add_sync(0xffffffffu, dsq);
+        dtot = __reduce_add_sync(0xffffffffu, dtot);
+        if (lane == 0 && (dsq | dtot)) { atomicAdd(&s_red[0], dsq); atomicAdd(&s_red[1], dtot); }     // s_red is zero between uses
+        __syncthreads();
+        const uint32_t sqr = sq_s[r] + s_red[0], ttr = tot_s[r] + s_red[1];
+        const float nr = sqrtf((float)sqr);
+        float mx = 0.f;
+        if (tid < p.bd) {
+            for (uint32_t i = tid; i < p.nb; i += p.bd) mx += (float)__ldcg(rd + i) / nr;
+            part_max[r * 1024 + tid] = mx;
+        }
+#pragma unroll
+        for (int w = 1; w < 32; w <<= 1) mx += __shfl_xor_sync(0xffffffffu, mx, w);
+        if (lane == 0) warp_max[r * 32 + wid] = tid < p.bd ? mx : 0.f;
+        __syncthreads();
+        if (tid == 0) {
+            sq_s[r] = sqr;
+            tot_s[r] = ttr;
+            nr_s[r] = nr;
+            const float l1 = sqr ? (float)ttr / nr : 0.f;
+            l_s[r] = make_float2(l1, bound * l1);
+            if (sqr) s_nz |= 1u << r;
+            s_red[0] = 0;
+            s_red[1] = 0;
+        }
+        __syncthreads();
+        if (wid == 0) {
+            const bool on = lane < nrep_now && ((s_nz >> lane) & 1u);
+            float lo = on ? l_s[lane].y : INFINITY, hi = on ? l_s[lane].x : 0.f;
+#pragma unroll
+            for (int w = 1; w < 32; w <<= 1) {
+                lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, w));
+                hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, w));
+            }
+            if (lane == 0) { s_blr_min = lo; s_lr_max = hi; }
+        }
+        __syncthreads();
+    };
+    // A row founds representative r: everything refresh() derives, computed by WARP 0 from the row's runs alone (the dense
+    // sums over a single row are sums over its runs: zero terms add 0.f).  part_max / warp_max of r are zero on entry (stage
+    // start).  Also refreshes the size-bound summary for `nrep_now` representatives.  The caller's next barrier publishes it.
+    auto found_sparse = [&](const uint4 info, uint32_t r, uint32_t nrep_now, const uint2* sruns) {
+        float* pm = part_max + r * 1024;
+        const float nr = sqrtf((float)info.w);
+        uint32_t touched = 0;
+        for (uint32_t j0 = info.y; j0 < info.z; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            const bool valid = j < info.z;
+            const uint2 spr = (valid && sruns) ? sruns[lane] : make_uint2(0u, 0u);
+            const uint32_t blk = valid ? (sruns ? spr.x : __ldg(p.enc_blk + j)) : 0u;
+            const uint32_t cnt = valid ? (sruns ? (spr.y & 0x7FFFFFFFu) : __ldg(p.counts + j)) : 0u;
+            const uint32_t t = mod_bd(blk);
+            s_fv[lane] = (float)cnt / nr;
+            __syncwarp();
+            // runs of the same reference thread (blk = t, t + bd, ...) are added in ascending block order = ascending lane
+            const uint32_t peers = __match_any_sync(0xffffffffu, valid ? t : 0xFFFF0000u + lane);
+            if (valid && lane == (uint32_t)(__ffs(peers) - 1)) {
+                float acc = pm[t];
+                for (uint32_t rest = peers; rest; rest &= rest - 1) acc += s_fv[__ffs(rest) - 1];
+                pm[t] = acc;
+                touched |= 1u << (t >> 5);
+            }
+            __syncwarp();
+        }
+        touched = __reduce_or_sync(0xffffffffu, touched);
+        while (touched) {
+            const uint32_t w = __ffs(touched) - 1;
+            touched &= touched - 1;
+            float mx = pm[(w << 5) + lane];
+#pragma unroll
+            for (int x = 1; x < 32; x <<= 1) mx += __shfl_xor_sync(0xffffffffu, mx, x);
+            if (lane == 0) warp_max[r * 32 + w] = mx;
+        }
+        if (lane == 0) {
+            sq_s[r] = info.w;
+            tot_s[r] = info.x;
+            nr_s[r] = nr;
+            const float l1 = info.w ? (float)info.x / nr : 0.f;
+            l_s[r] = make_float2(l1, bound * l1);
+            if (info.w) s_nz |= 1u << r;
+        }
+        __syncwarp();
+        const bool on = lane < nrep_now && ((s_nz >> lane) & 1u);
+        float lo = on ? l_s[lane].y : INFINITY, hi = on ? l_s[lane].x : 0.f;
+#pragma unroll
+        for (int x = 1; x < 32; x <<= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, x));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, x));
+        }
+        if (lane == 0) { s_blr_min = lo; s_lr_max = hi; }
+    };
+    unsigned long long s_ctrl_copy = 0;
+    auto poll = [&](uint32_t id, uint32_t have) -> bool {
+        if (tid == 0) {
+            const unsigned long long* cw = p.ctrl + (id % p.num_slots);
+            uint32_t spins = 0;
+            unsigned long long v, t0 = 0;
+            uint32_t stop = 0;
+            for (;;) {
+                v = ld_acquire_u64(cw);
+                if ((uint32_t)(v >> 33) == id && ((uint32_t)((v >> 1) & 0xFFFFFFFFu) > have || (v & 1ull))) break;
+                if (((volatile uint32_t*)p.status)[1] | ((volatile uint32_t*)p.status)[2]) { stop = 1; break; }
+                if ((++spins & 1023u) == 0) {
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t0 == 0) t0 = now;
+                    if (now - t0 > 120ull * 1000000000ull) { atomicExch(p.status + 2, 1u); stop = 1; break; }
+                }
+                __nanosleep(spins < 64 ? 20 : 200);
+            }
+            s_ctrl = v;
+            s_stop = stop;
+        }
+        __syncthreads();
+        const bool ok = s_stop == 0;
+        const unsigned long long v = s_ctrl;
+        __syncthreads();
+        s_ctrl_copy = v;
+        return ok;
+    };
+
+    if (tid < 2) s_first[tid] = kNone;
+    if (tid == 0) { s_touched = 0; s_red[0] = 0; s_red[1] = 0; }
+    for (uint32_t i = tid; i < (nbp >> 1); i += kClusterThreads) reinterpret_cast<uint32_t*>(scratch)[i] = 0;
+    uint32_t par_a = 0, par_b = 0;
+    auto now_ns = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    unsigned long long tr_steps = 0, tr_cand = 0, tr_joins = 0, tr_polls = 0, tr_events = 0, tr_found = 0;
+    unsigned long long tr_long = 0, tr_poll_cyc = 0, tr_found_cyc = 0, tr_event_cyc = 0, tr_long_cyc = 0;
+    const long long tr_begin = clock64();
+    auto flush_trace = [&]() {
+        if (tid == 0 && p.trace) {
+            atomicAdd(p.trace + 0, tr_steps); atomicAdd(p.trace + 1, tr_cand); atomicAdd(p.trace + 2, tr_joins);
+            atomicAdd(p.trace + 3, tr_polls); atomicAdd(p.trace + 4, tr_events); atomicAdd(p.trace + 5, tr_found);
+            atomicAdd(p.trace + 6, tr_long); atomicAdd(p.trace + 7, (unsigned long long)(clock64() - tr_begin));
+            atomicAdd(p.trace + 8, tr_poll_cyc); atomicAdd(p.trace + 9, tr_found_cyc); atomicAdd(p.trace + 10, tr_event_cyc);
+            atomicAdd(p.trace + 11, tr_long_cyc);
+        }
+    };
+    for (uint32_t s = blockIdx.x + 1;; s += gridDim.x) {
+        const uint32_t* in = p.lists + (size_t)(s % p.num_slots) * p.list_cap;
+        uint32_t* out = p.lists + (size_t)((s + 1) % p.num_slots) * p.list_cap;
+        unsigned long long* out_ctrl = p.ctrl + ((s + 1) % p.num_slots);
+        // reset the stage's state while the input is on its way
+        for (uint32_t i = tid; i < nbp; i += kClusterThreads) slots[i] = 0;
+        for (uint32_t i = tid; i < kStageReps * p.nb; i += kClusterThreads) repd[i] = 0;
+        for (uint32_t i = tid; i < kStageReps * (1024 + 32); i += kClusterThreads) part_max[i] = 0.f;     // part_max and warp_max
+        if (tid == 0) { s_nz = 0; s_blr_min = INFINITY; s_lr_max = 0.f; }
+        ++tr_polls;
+        {
+            const long long t0 = clock64();
+            const bool ok = poll(s, 0);
+            tr_poll_cyc += clock64() - t0;
+            if (!ok) { flush_trace(); return; }
+        }
+        uint32_t avail = (uint32_t)((s_ctrl_copy >> 1) & 0xFFFFFFFFu);
+        bool in_done = (s_ctrl_copy & 1ull) != 0;
+        if (avail == 0) {                       // the previous stage forwarded nothing (it has recorded the cluster count): the run is over
+            if (tid == 0) atomicExch(p.status + 1, 1u);
+            flush_trace();
+            return;
+        }
+        if (tid == 0) st_release_u64(out_ctrl, make_ctrl(s + 1, 0, 0));
+        if (tid == 0 && p.trace_ts && s <= p.M) { p.trace_ts[3 * s] = now_ns(); p.trace_ts[3 * s + 1] = 0; }
+        const uint32_t base = (s - 1) * kStageReps + 1;      // cluster id of representative 0
+        uint32_t cursor = 0, produced = 0, published = 0, nrep = 0;
+        uint32_t fb_base = 0, fb_n = 0;                      // founding: the rows fetched into s_fpos / s_finfo / s_fruns
+        uint32_t fresh_steps = 0;                            // streaming steps since the 32nd representative
+        for (;;) {
+            if (cursor >= avail) {
+                if (in_done) break;
+                ++tr_polls;
+                {
+                    const long long t0 = clock64();
+                    const bool ok = poll(s, cursor);
+                    tr_poll_cyc += clock64() - t0;
+                    if (!ok) { flush_trace(); return; }
+                }
+                avail = (uint32_t)((s_ctrl_copy >> 1) & 0xFFFFFFFFu);
+                in_done = (s_ctrl_copy & 1ull) != 0;
+                continue;
+            }
+            if (nrep < kStageReps) {
+                // ---- founding: one row; joins the first representative that accepts it, else founds the next ----
+                // The stage forwards nothing until it has its 32 representatives, so this loop is the critical path of the whole
+                // pipeline: the next 32 rows' positions, pos_info and (rows of at most 32 runs) block lists are fetched together
+                // into shared memory, so that a row costs shared-memory work plus the reads of the dense representative.
+                const long long tf0 = clock64();
+                if (cursor >= fb_base + fb_n) {
+                    fb_base = cursor;
+                    fb_n = min(32u, avail - cursor);
+                    if (tid < fb_n) {
+                        const uint32_t ps = __ldcg(in + cursor + tid);
+                        s_fpos[tid] = ps;
+                        s_finfo[tid] = __ldg(p.pos_info + ps);
+                    }
+                    __syncthreads();
+                    if (wid < fb_n) {
+                        const uint4 fi = s_finfo[wid];
+                        const uint32_t fn = fi.z - fi.y;
+                        if (fn <= 32 && lane < fn) s_fruns[wid * 32 + lane] = __ldg(p.enc_pair + fi.y + lane);
+                    }
+                    __syncthreads();
+                }
+                const uint32_t fk = cursor - fb_base;
+                const uint32_t pos = s_fpos[fk];
+                const uint4 info = s_finfo[fk];
+                const bool big = info.z - info.y > 32;
+                const uint2* sruns = big ? nullptr : s_fruns + fk * 32;
+                uint32_t M = nrep ? size_mask(info, nrep) : 0u;    // uniform: every thread computes the same mask
+                bool expanded = false;
+                if (M && info.w) {
+                    if (!big) {
+                        M = warp_shared_mask(info, M, sruns);
+                    } else {
+                        expand_row(info);
+                        expanded = true;
+                        __syncthreads();
+                        M = shared_mask_scratch(info, M);
+                    }
+                }
+                uint32_t jr = kNone;
+                if (M) {                                           // (uniform) candidates: the first that accepts wins
+                    if (big) {
+                        if (!expanded) {
+                            expand_row(info);
+                            expanded = true;
+                            __syncthreads();
+                        }
+                        scratch_pass(info, M, 0u, &s_first[par_b]);
+                    } else {
+                        if (wid < __popc(M)) {
+                            const uint32_t r = __fns(M, 0, (int)wid + 1);
+                            if (evaluate_pair(info, r, sruns) && lane == 0) atomicMin(&s_first[par_b], r);
+                        }
+                        __syncthreads();
+                    }
+                    jr = s_first[par_b];
+                    par_b ^= 1;
+                    if (tid == 0) s_first[par_b] = kNone;          // visible after the barrier(s) below
+                } else {
+                    __syncthreads();                               // every warp has read the stage's state before it changes
+                }
+                if (expanded) clear_row(info);                     // closed by the barrier(s) below
+                const uint32_t r = jr != kNone ? jr : nrep;
+                if (tid == 0) p.cluster_ids[pos] = base + r;
+                if (jr == kNone) {
+                    ++nrep;
+                    ++tr_found;
+                    if (!big) {
+                        if (wid == 1 && lane < info.z - info.y) {   // the representative was all zero: plain stores
+                            const uint2 pr = sruns[lane];
+                            repd[(size_t)r * p.nb + pr.x] = pr.y & 0x7FFFFFFFu;
+                            atomicOr(&slots[pr.x], 1u << r);
+                        }
+                        if (wid == 0) found_sparse(info, r, nrep, sruns);
+                        __syncthreads();
+                    } else {
+                        absorb(info, r);
+                        refresh(r, nrep);
+                    }
+                    if (nrep == kStageReps) {
+                        fresh_steps = 0;
+                        if (tid == 0 && p.trace_ts && s <= p.M) p.trace_ts[3 * s + 1] = now_ns();
+                    }
+                } else {
+                    ++tr_joins;
+                    join_absorb_refresh(info, r, nrep, sruns);
+                }
+                cursor += 1;
+                ++tr_steps;
+                ++tr_cand;
+                tr_found_cyc += clock64() - tf0;
+                continue;
+            }
+            // ---- streaming step: up to 1024 rows, one per thread, against all 32 representatives ----
+            constexpr uint32_t kCpwB = 2;                       // event rows a warp evaluates per step
+            // the first steps after the founding are short and publish at once: the next stage is waiting for its first rows
+            const bool fresh = fresh_steps < 3;
+            ++fresh_steps;
+            const uint32_t take = min(avail - cursor, fresh ? 128u : (uint32_t)kClusterThreads);
+            ++tr_steps;
+            tr_cand += take;
+            uint32_t pos1 = kNone, M = 0;
+            bool is_long = false;
+            if (tid < take) {
+                pos1 = __ldcg(in + cursor + tid);
+                M = bounds_mask(__ldg(p.pos_info + pos1), kStageReps, is_long);
+            }
+            s_mask[tid] = M;
+            const uint32_t evb = __ballot_sync(0xffffffffu, M != 0);
+            const uint32_t lgb = __ballot_sync(0xffffffffu, is_long);
+            if (lane == 0) { s_ev[par_a][wid] = evb; s_long[par_a][wid] = lgb; }
+            __syncthreads();                                  // S1: verdicts in; the rows stored by earlier steps are ordered before it
+            if (tid == 0 && produced != published) st_release_u64(out_ctrl, make_ctrl(s + 1, produced, 0));
+            published = produced;
+            const uint32_t wmask = s_ev[par_a][lane];
+            const uint32_t* longs = s_long[par_a];
+            par_a ^= 1;
+            uint32_t pre = __popc(wmask);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, pre, d);
+                if ((int)lane >= d) pre += t;
+            }
+            const uint32_t total_ev = __shfl_sync(0xffffffffu, pre, 31);
+            if (total_ev == 0) {
+                if (tid < take) out[produced + tid] = pos1;
+                produced += take;
+                cursor += take;
+                if (fresh) {
+                    __syncthreads();
+                    if (tid == 0) st_release_u64(out_ctrl, make_ctrl(s + 1, produced, 0));
+                    published = produced;
+                }
+                continue;
+            }
+            auto nth_ev = [&](uint32_t rk) -> uint32_t {
+                const uint32_t w = __ffs(__ballot_sync(0xffffffffu, pre > rk)) - 1;
+                const uint32_t before = __shfl_sync(0xffffffffu, pre - __popc(wmask), w);
+                const uint32_t bits = __shfl_sync(0xffffffffu, wmask, w);
+                return w * 32 + __fns(bits, 0, (int)(rk - before) + 1);
+            };
+            const uint32_t evaluated = min(total_ev, kWarps * kCpwB);
+            const uint32_t take_eff = total_ev > evaluated ? nth_ev(evaluated) : take;
+            tr_events += evaluated;
+            const long long te0 = clock64();
+#pragma unroll 1
+            for (uint32_t q = 0; q < kCpwB; ++q) {
+                const uint32_t rk = q * kWarps + wid;
+                if (rk < evaluated) {                          // warp-uniform
+                    const uint32_t k = nth_ev(rk);
+                    const uint4 kinfo = __ldg(p.pos_info + __ldcg(in + cursor + k));
+                    uint32_t mk = s_mask[k];
+                    if ((longs[k >> 5] >> (k & 31)) & 1u) mk = warp_shared_mask(kinfo, mk, nullptr);
+                    if (kinfo.z - kinfo.y > 32) {              // left for the scratch pass below
+                        if (lane == 0) s_qmask[rk] = mk;
+                        continue;
+                    }
+                    if (lane == 0) s_qmask[rk] = 0;
+                    while (mk) {
+                        const uint32_t r = __ffs(mk) - 1;
+                        mk &= mk - 1;
+                        if (evaluate_pair(kinfo, r, nullptr)) {
+                            if (lane == 0) atomicMin(&s_first[par_b], (k << 5) | r);
+                            break;
+                        }
+                    }
+                }
+            }
+            __syncthreads();                                  // S2: every short event row decided, the long ones queued
+            const long long te1 = clock64();
+            // the long event rows, one at a time in list order: expanded once, evaluated against their candidates by a warp each
+#pragma unroll 1
+            for (uint32_t rk = 0; rk < evaluated; ++rk) {
+                const uint32_t mk = s_qmask[rk];
+                if (mk == 0) continue;                         // uniform
+                const uint32_t k = nth_ev(rk);
+                const uint32_t fcur = s_first[par_b];
+                if (fcur != kNone && (fcur >> 5) < k) break;   // an earlier row joins: this one is redone anyway
+                const uint4 kinfo = __ldg(p.pos_info + __ldcg(in + cursor + k));
+                expand_row(kinfo);
+                __syncthreads();
+                scratch_pass(kinfo, mk, k << 5, &s_first[par_b]);
+                clear_row(kinfo);
+                __syncthreads();
+                ++tr_long;
+            }
+            tr_event_cyc += te1 - te0;
+            tr_long_cyc += clock64() - te1;
+            const uint32_t fv = s_first[par_b];
+            par_b ^= 1;
+            if (tid == 0) s_first[par_b] = kNone;
+            const uint32_t fj = fv == kNone ? kNone : fv >> 5;
+            const uint32_t n_rej = fj == kNone ? take_eff : fj;
+            if (tid < n_rej) out[produced + tid] = pos1;
+            produced += n_rej;
+            if (fresh && n_rej) {
+                __syncthreads();
+                if (tid == 0) st_release_u64(out_ctrl, make_ctrl(s + 1, produced, 0));
+                published = produced;
+            }
+            if (fj == kNone) {
+                cursor += take_eff;
+            } else {
+                const uint32_t jr = fv & 31u;
+                if (tid == fj) p.cluster_ids[pos1] = base + jr;
+                join_absorb_refresh(__ldg(p.pos_info + __ldcg(in + cursor + fj)), jr, kStageReps, nullptr);
+                cursor += fj + 1;
+                ++tr_joins;
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && p.trace_ts && s <= p.M) p.trace_ts[3 * s + 2] = now_ns();
+        if (tid == 0) {
+            if (produced == 0) {                 // nothing left for a next stage: this one holds the last cluster
+                p.status[0] = base + nrep - 1;
+                __threadfence();
+                atomicExch(p.status + 1, 1u);
+            }
+            st_release_u64(out_ctrl, make_ctrl(s + 1, produced, 1));
+        }
+    }
+}
+
 __global__ void init_cluster_state_kernel(uint32_t M, uint32_t zero_rows, uint32_t num_slots, uint32_t* cluster_ids, uint32_t* list1,
                                           unsigned long long* ctrl, uint32_t* status) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -908,9 +1754,9 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
         const uint32_t scratch_entries = (nb + 7u) & ~7u;
         const size_t base_smem = (static_cast<size_t>(nb) * 2 + 1024 + 32) * 4;
         const bool use_scratch = block_size <= 65535u && base_smem + static_cast<size_t>(scratch_entries) * 2 * 32 <= 200 * 1024;
-        const size_t smem = base_smem + (use_scratch ? static_cast<size_t>(scratch_entries) * 2 * 32 : 0);
-        if (smem > 200 * 1024) {
-            set_error("row reorder: %u column blocks need %zu bytes of shared memory; raise block_size", nb, smem);
+        const size_t cluster_smem = base_smem + (use_scratch ? static_cast<size_t>(scratch_entries) * 2 * 32 : 0);
+        if (cluster_smem > 200 * 1024) {
+            set_error("row reorder: %u column blocks need %zu bytes of shared memory; raise block_size", nb, cluster_smem);
             return BSMR_ERR_UNSUPPORTED;
         }
 
@@ -998,7 +1844,7 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
 #else
         const bool want_trace = false;
 #endif
-        BSMR_TRY(trace.alloc(9));
+        BSMR_TRY(trace.alloc(12));
         BSMR_CUDA_OK(cudaMemsetAsync(trace.ptr, 0, trace.bytes(), st));
         TmpBuf<unsigned long long> trace_ts(ws);
         if (want_trace) {
@@ -1008,10 +1854,20 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
         BSMR_TRY(cluster_ids.alloc(M ? M : 1));
         BSMR_TRY(status.alloc(4));
         uint32_t clusters_true = 0;
+        // Which kernel: graph-shaped inputs (many short rows, no per-warp scratch) run the stage kernel -- 32 consecutive
+        // clusters per CTA -- everything else the cluster-per-CTA kernel.  BSMR_ROW_STAGE_ON / _OFF force either (same permutation).
+        const size_t stage_smem = (static_cast<size_t>((nb + 3u) & ~3u) + kStageReps * 1024 + kStageReps * 32 + 1024) * 4 + static_cast<size_t>((nb + 3u) & ~3u) * 2;
+        const bool stage_fits = stage_smem <= 220 * 1024 && alpha >= 0.0f && block_size <= 65535u && nb <= kStageTerms * bd;
+        const bool graph_sized = !use_scratch && (M - zero_rows) >= (1u << 15);
+        const bool use_stage = stage_fits && ((flags & BSMR_ROW_STAGE_ON) ? true : (flags & BSMR_ROW_STAGE_OFF) ? false
+                                              : (graph_sized && !(flags & (BSMR_ROW_THREAD_PRUNE_ON | BSMR_ROW_THREAD_PRUNE_OFF))));
+        void* const kernel_fn = use_stage ? reinterpret_cast<void*>(bsa_stage_kernel) : reinterpret_cast<void*>(bsa_cluster_kernel);
+        const size_t smem = use_stage ? stage_smem : cluster_smem;
+        TmpBuf<uint32_t> repd(ws);
         if (M > zero_rows) {
-            BSMR_CUDA_OK(cudaFuncSetAttribute(bsa_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            BSMR_CUDA_OK(cudaFuncSetAttribute(kernel_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             int per_sm = 0;
-            BSMR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bsa_cluster_kernel, kClusterThreads, smem));
+            BSMR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_fn, kClusterThreads, smem));
             if (per_sm < 1) {
                 set_error("row reorder: clustering kernel does not fit on an SM (smem %zu)", smem);
                 return BSMR_ERR_UNSUPPORTED;
@@ -1041,12 +1897,16 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
             // where rows are long (nips: 777 blocks each) every candidate needs a warp anyway and the scratch path is faster
             // Measured (R-MAT, profiles/r02e_* against r02l_*): 2^20 rows 61.4 -> 38.8 s, 2^19 rows 16.0 -> 14.2 s, but 2^17 rows
             // 1.8 -> 3.6 s (three barriers per step instead of two, and the pipeline is latency-bound there): on from 2^18 rows.
-            const bool graph_sized = !use_scratch && (M - zero_rows) >= (1u << 18);
-            cp.thread_prune = (flags & BSMR_ROW_THREAD_PRUNE_ON) ? 1u : (flags & BSMR_ROW_THREAD_PRUNE_OFF) ? 0u : (graph_sized ? 1u : 0u);
+            const bool prune_sized = !use_scratch && (M - zero_rows) >= (1u << 18);
+            cp.thread_prune = (flags & BSMR_ROW_THREAD_PRUNE_ON) ? 1u : (flags & BSMR_ROW_THREAD_PRUNE_OFF) ? 0u : (prune_sized ? 1u : 0u);
+            if (use_stage) {
+                BSMR_TRY(repd.alloc(static_cast<size_t>(grid) * kStageReps * nb));
+                cp.repd = repd.ptr;
+            }
             cp.cluster_ids = cluster_ids.ptr; cp.lists = lists.ptr; cp.ctrl = ctrl.ptr; cp.status = status.ptr;
             void* args[] = {&cp};
             BSMR_CUDA_OK(cudaEventRecord(ctx->ev0, st));
-            BSMR_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(bsa_cluster_kernel), dim3(grid), dim3(kClusterThreads), args, smem, st));
+            BSMR_CUDA_OK(cudaLaunchCooperativeKernel(kernel_fn, dim3(grid), dim3(kClusterThreads), args, smem, st));
             BSMR_CUDA_OK(cudaEventRecord(ctx->ev1, st));
             ctx->launches += 2;
             uint32_t h_status[4] = {0, 0, 0, 0};
@@ -1058,20 +1918,27 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
             }
             clusters_true = h_status[0];
             if (want_trace) {
-                unsigned long long h_tr[9];
+                unsigned long long h_tr[12];
                 BSMR_CUDA_OK(cudaMemcpy(h_tr, trace.ptr, sizeof(h_tr), cudaMemcpyDeviceToHost));
-                fprintf(stderr, "[bsmr trace] clustering: rows %u nb %u bd %u grid %d scratch %d | clusters %u steps %llu candidates %llu joins %llu "
+                if (use_stage)
+                    fprintf(stderr, "[bsmr trace] stage kernel: steps %llu rows-in-steps %llu joins %llu polls %llu event rows %llu founded %llu long rows through the scratch %llu | "
+                                    "Mcycles (thread 0 of every CTA): busy %.1f poll %.1f founding steps %.1f event phase A %.1f scratch pass %.1f\n",
+                            h_tr[0], h_tr[1], h_tr[2], h_tr[3], h_tr[4], h_tr[5], h_tr[6], h_tr[7] / 1e6, h_tr[8] / 1e6, h_tr[9] / 1e6, h_tr[10] / 1e6, h_tr[11] / 1e6);
+                else
+                fprintf(stderr, "[bsmr trace] clustering: stage kernel %d (then: Mcycles poll = events evaluated, eval = reps founded) rows %u nb %u bd %u grid %d scratch %d | clusters %u steps %llu candidates %llu joins %llu "
                                 "polls %llu size-bound rejects seen by warp 0 of every CTA %llu | Mcycles: poll %.1f eval %.1f update %.1f busy(all CTAs) %.1f\n",
-                        M, nb, bd, grid, (int)use_scratch, clusters_true, h_tr[0], h_tr[1], h_tr[2], h_tr[3], h_tr[8], h_tr[4] / 1e6, h_tr[5] / 1e6,
+                        (int)use_stage, M, nb, bd, grid, (int)use_scratch, clusters_true, h_tr[0], h_tr[1], h_tr[2], h_tr[3], h_tr[8], h_tr[4] / 1e6, h_tr[5] / 1e6,
                         h_tr[6] / 1e6, h_tr[7] / 1e6);
-                const uint32_t nc = clusters_true < M ? clusters_true : M;
+                const uint32_t nc = use_stage ? (clusters_true + kStageReps - 1) / kStageReps : (clusters_true < M ? clusters_true : M);
                 std::vector<unsigned long long> ts(3 * (static_cast<size_t>(nc) + 1));
                 BSMR_CUDA_OK(cudaMemcpy(ts.data(), trace_ts.ptr, ts.size() * 8, cudaMemcpyDeviceToHost));
                 if (nc >= 2) {
                     const unsigned long long t0 = ts[3];
                     auto us = [&](unsigned long long t) { return (double)(t - t0) / 1e3; };
                     fprintf(stderr, "[bsmr trace]   cluster: start / first publish / end (us)\n");
-                    for (uint32_t c = 1; c <= nc; c = c < 8 ? c + 1 : c + (nc / 12 ? nc / 12 : 1))
+                    const char* tv = std::getenv("BSMR_TRACE");
+                    const bool all = tv && tv[0] == 'a';
+                    for (uint32_t c = 1; c <= nc; c = (all || c < 8) ? c + 1 : c + (nc / 12 ? nc / 12 : 1))
                         fprintf(stderr, "[bsmr trace]   %6u: %10.1f %10.1f %10.1f\n", c, us(ts[3 * c]), us(ts[3 * c + 1]), us(ts[3 * c + 2]));
                     fprintf(stderr, "[bsmr trace]   %6u: %10.1f %10.1f %10.1f\n", nc, us(ts[3 * nc]), us(ts[3 * nc + 1]), us(ts[3 * nc + 2]));
                 }

@@ -95,6 +95,11 @@ int bsmr_plan_destroy(bsmr_plan* plan);
  * either way (tests run both on every case).                                                                      */
 #define BSMR_ROW_THREAD_PRUNE_ON  4u
 #define BSMR_ROW_THREAD_PRUNE_OFF 8u
+/* or-ed in: the stage kernel (one CTA per run of 32 consecutive clusters: a row is tested against 32 representatives at
+ * once and forwarded once) or the cluster-per-CTA kernel.  Default: the stage kernel on graph-shaped inputs (>= 2^15
+ * non-empty rows, no per-warp scratch).  Same permutation either way.                                              */
+#define BSMR_ROW_STAGE_ON         16u
+#define BSMR_ROW_STAGE_OFF        32u
 
 /* BSMR::rowReordering -> bsa_rowReordering_gpu (src/BSMR.cpp:27-50,
  * src/rowReordering.cu:1027-1095): dispersion scores, stable sort, BSA clustering with

@@ -379,14 +379,15 @@ def test_dlmc_masks_full_size(pkg, ctx, oracle, sparsity):
 
 @pytest.mark.parametrize("alpha", [0.1, 0.3, 0.5, 0.7, 0.9])
 def test_row_reorder_both_clustering_steps_vs_oracle(pkg, ctx, oracle, alpha):
-    """The clustering kernel has two step forms -- a warp per candidate (with per-warp scratch; the default where rows are
-    long) and a thread per candidate for the cheap rejections with warps only for the survivors (the default on graph-shaped
-    inputs).  Both must give the oracle's permutation on every small case, lossy and exact reduction."""
+    """Three forms of the clustering: the cluster-per-CTA kernel with a warp per candidate (per-warp scratch; the default where
+    rows are long), the same kernel with a thread per candidate for the cheap rejections, and the stage kernel (32 consecutive
+    clusters per CTA; the default on graph-shaped inputs).  All must give the oracle's permutation on every small case, lossy and
+    exact reduction."""
     for name, M, N, ro, ci in small_cases(pkg):
         for block_size in (16, 37):
             for mode in (pkg.ROW_REFERENCE_COMPAT, pkg.ROW_EXACT_REDUCE):
                 want, want_compat, want_true = oracle.row_reordering(M, N, ro, ci, alpha, block_size, exact=(mode == pkg.ROW_EXACT_REDUCE))
-                for step in (pkg.ROW_THREAD_PRUNE_ON, pkg.ROW_THREAD_PRUNE_OFF):
+                for step in (pkg.ROW_THREAD_PRUNE_ON, pkg.ROW_THREAD_PRUNE_OFF, pkg.ROW_STAGE_ON):
                     plan = pkg.Plan(ctx, M, N, ro, ci)
                     plan.row_reorder(alpha, block_size=block_size, flags=mode | step)
                     assert np.array_equal(plan.vector("reordered_rows"), want), (name, alpha, block_size, mode, step)
@@ -400,12 +401,13 @@ def test_nips_and_mask_clustering_with_the_thread_prune_step(pkg, ctx, oracle, g
     (golden), the 98 % mask (4095 clusters) against the sparse oracle."""
     _, M, N, ro, ci = named_case(pkg, "nips")
     plan = pkg.Plan(ctx, M, N, ro, ci)
-    plan.row_reorder(0.3, block_size=16, flags=pkg.ROW_THREAD_PRUNE_ON)
     g = np.load(os.path.join(golden_dir, "nips_perm_ref_gpu.npz"))
-    assert np.array_equal(plan.vector("reordered_rows"), g["perm_ref_gpu"]) and plan.info()["num_clusters"] == int(g["num_clusters"])
+    for step in (pkg.ROW_THREAD_PRUNE_ON, pkg.ROW_STAGE_ON):
+        plan.row_reorder(0.3, block_size=16, flags=step)
+        assert np.array_equal(plan.vector("reordered_rows"), g["perm_ref_gpu"]) and plan.info()["num_clusters"] == int(g["num_clusters"]), step
     _, M, N, ro, ci = named_case(pkg, "mask98")
     perm, compat, _ = oracle.row_reordering_indexed(M, N, ro, ci, 0.3, 16)
-    for step in (pkg.ROW_THREAD_PRUNE_ON, pkg.ROW_THREAD_PRUNE_OFF):
+    for step in (pkg.ROW_THREAD_PRUNE_ON, pkg.ROW_THREAD_PRUNE_OFF, pkg.ROW_STAGE_ON):
         plan = pkg.Plan(ctx, M, N, ro, ci)
         plan.row_reorder(0.3, block_size=16, flags=step)
         assert np.array_equal(plan.vector("reordered_rows"), perm) and plan.info()["num_clusters"] == compat, step
@@ -417,12 +419,29 @@ def test_graph_clustering_vs_sparse_oracle(pkg, ctx, oracle):
     _, M, N, ro, ci = named_case(pkg, "graph13")
     bs = ctx.calculate_block_size(M, N)
     perm, compat, true = oracle.row_reordering_indexed(M, N, ro, ci, 0.3, bs)
-    for step in (pkg.ROW_THREAD_PRUNE_ON, pkg.ROW_THREAD_PRUNE_OFF):
+    for step in (pkg.ROW_THREAD_PRUNE_ON, pkg.ROW_THREAD_PRUNE_OFF, pkg.ROW_STAGE_ON):
         plan = pkg.Plan(ctx, M, N, ro, ci)
         plan.row_reorder(0.3, block_size=bs, flags=step)
         assert np.array_equal(plan.vector("reordered_rows"), perm), step
         assert plan.info()["num_clusters"] == compat and plan.info()["num_clusters_true"] == true, step
         plan.close()
+
+
+@pytest.mark.parametrize("scale,alpha", [(15, 0.3), (16, 0.1), (16, 0.6), (17, 0.3)])
+def test_stage_kernel_equals_cluster_per_cta_kernel_on_graphs(pkg, ctx, scale, alpha):
+    """R-MAT graphs beyond what the CPU oracle finishes: the stage kernel (32 clusters per CTA, the default there) and the
+    cluster-per-CTA kernel (pinned to the oracle and the reference on everything smaller) must produce the same permutation and
+    cluster counts -- hub rows with thousands of column blocks, tens of thousands of clusters, joins in every phase."""
+    _, M, N, ro, ci = named_case(pkg, "graph%d" % scale)
+    out = []
+    for step in (pkg.ROW_STAGE_ON, pkg.ROW_STAGE_OFF):
+        plan = pkg.Plan(ctx, M, N, ro, ci)
+        plan.row_reorder(alpha, flags=step)
+        info = plan.info()
+        out.append((plan.vector("reordered_rows"), info["num_clusters"], info["num_clusters_true"]))
+        plan.close()
+    assert out[0][1:] == out[1][1:] and out[0][2] > 1000
+    assert np.array_equal(out[0][0], out[1][0])
 
 
 def sampled_check(torch, dA, dB, dP, ro_dev, ci_dev, nnz, n=1 << 17, seed=3):
