@@ -863,7 +863,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
     __shared__ uint32_t s_sh[kStageReps];      // shared_mask_scratch: nnz the row shares with representative r
     __shared__ uint32_t s_fpos[32];            // founding: the next rows of the input, fetched together ...
     __shared__ uint4 s_finfo[32];              // ... their pos_info ...
-    __shared__ uint2 s_fruns[32 * 32];         // ... and the runs of those with at most 32
+    __shared__ uint2 s_runs64[32 * 64];        // ... and the runs of those with at most 64; streaming: warp w stages a row of 33..64 runs at [w]
+    __shared__ uint32_t s_wbits[32 * 32];      // evaluate_medium, per warp: bit t = reference thread t already has its leader (zero between uses)
     __shared__ float nr_s[kStageReps];         // its square root
     __shared__ float2 l_s[kStageReps];         // {L1 norm of the normalised kept entries, bound * that}
     __shared__ uint32_t s_nz;                  // bit r: sq_s[r] != 0
@@ -942,6 +943,15 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
     };
     // Which of the first `nrep` representatives can this row still join?  Exact bounds only (a cleared bit = similarity
     // cannot exceed alpha); one thread, no synchronisation.
+    // Second shared-nnz bound.  max(a, c) = a + c - min(a, c) per block, so max-sum = L1(rep) + L1(row) - min-sum and
+    // sim = min-sum / (L1(rep) + L1(row) - min-sum), increasing in min-sum; min-sum <= U = the row's normalised nnz in the blocks
+    // it shares with the representative.  Reject when U / (L1(rep) + L1(row) - U) < alpha - 1e-3 (all sums over the kept blocks,
+    // like the reference's).  Against a representative much larger than the row this asks for nearly ALL of the row to be
+    // shared, where the first bound (U / L1(row)) only asks for 30 %.
+    auto keep_by_union = [&](uint32_t sh, float nc, float lc, uint32_t r) -> bool {
+        const float U = (float)sh / nc;
+        return !(U < bound * (l_s[r].x + lc - U));
+    };
     // the zero cases and the size bound: which of the first `nrep` representatives are still possible (no block list read)
     auto size_mask = [&](const uint4 info, uint32_t nrep) -> uint32_t {
         const uint32_t live = nrep >= 32 ? 0xFFFFFFFFu : ((1u << nrep) - 1u);
@@ -971,7 +981,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
         uint32_t sh = 0;
         for (uint32_t j0 = info.y; j0 < info.z; j0 += 32) {
             const uint32_t j = j0 + lane;
-            const uint2 pr = j < info.z ? (sruns ? sruns[lane] : __ldg(p.enc_pair + j)) : make_uint2(0u, 0u);   // sruns: rows of <= 32 runs
+            const uint2 pr = j < info.z ? (sruns ? sruns[j - info.y] : __ldg(p.enc_pair + j)) : make_uint2(0u, 0u);   // sruns: the row's runs in shared memory
             const uint32_t m = (pr.y >> 31) ? (slots[pr.x] & alive) : 0u;
             const uint32_t cnt = pr.y & 0x7FFFFFFFu;
             uint32_t hit = __ballot_sync(0xffffffffu, m != 0);
@@ -983,7 +993,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                 if ((mi >> lane) & 1u) sh += ci;
             }
         }
-        const bool ok = sh != 0 && !((float)sh < bound * (float)info.x);
+        const float nc = sqrtf((float)info.w);
+        const bool ok = sh != 0 && !((float)sh < bound * (float)info.x) && keep_by_union(sh, nc, (float)info.x / nc, lane);
         return __ballot_sync(0xffffffffu, ok) & alive;
     };
     // One THREAD per row: size bound, then (rows of at most kWalkMax runs and fewer than 256 kept nnz) the shared-nnz bound
@@ -1026,7 +1037,19 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
         uint32_t ge = 0xFFFFFFFFu;
 #pragma unroll
         for (int q = 0; q < 8; ++q) ge = ((T >> q) & 1u) ? (S[q] & ge) : (S[q] | ge);
-        return ge & alive;
+        uint32_t out = ge & alive;
+        if (out) {                                                      // the few survivors: the second bound, per representative
+            const float nc = sqrtf((float)info.w);
+            const float lc = (float)info.x / nc;
+            for (uint32_t rest = out; rest; rest &= rest - 1) {
+                const uint32_t r = __ffs(rest) - 1;
+                uint32_t sh = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) sh |= ((S[q] >> r) & 1u) << q;
+                if (!keep_by_union(sh, nc, lc, r)) out &= ~(1u << r);
+            }
+        }
+        return out;
     };
     // does the row join representative r?  One warp; the float operations of calculate_similarity_norm_weighted_jaccard
     // in the reference's order (see bsa_cluster_kernel::evaluate; here the normalised representative is recomputed from
@@ -1103,6 +1126,109 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                 }
             }
         }
+        for (uint32_t stride = p.first_stride; stride >= 1; stride >>= 1) {
+            const float tmin = __shfl_down_sync(0xffffffffu, my_min, stride);
+            const float tmax = __shfl_down_sync(0xffffffffu, my_max, stride);
+            if (lane < stride && lane + stride < 32) {
+                my_min += tmin;
+                my_max += tmax;
+            }
+        }
+        const float sim = __shfl_sync(0xffffffffu, my_min, 0) / __shfl_sync(0xffffffffu, my_max, 0);
+        return sim > p.alpha;
+    };
+    // Rows of 33..64 runs, one warp, runs staged in shared memory (`wr`, ascending blocks).  Same arithmetic as evaluate_pair;
+    // a lane holds two runs (lane, lane + 32).  The run that comes first among those of a reference thread t leads it (found
+    // with a match inside each half and a per-warp bitmap of the threads across the halves) and sums the thread's terms in
+    // ascending block order, finding the row's later blocks of that thread by walking on through the staged runs.
+    auto evaluate_medium = [&](const uint4 info, const uint32_t r, const uint2* wr, uint32_t* wbits) -> bool {
+        const uint32_t s_cmp = info.w, s_rep = sq_s[r];
+        if (s_rep == 0 && s_cmp == 0) return 1.0f > p.alpha;
+        if (s_rep == 0 || s_cmp == 0) return 0.0f > p.alpha;
+        const uint32_t* rd = repd + (size_t)r * p.nb;
+        const float* pm = part_max + r * 1024;
+        const float nr = nr_s[r];
+        const uint32_t n = info.z - info.y;
+        const float nc = sqrtf((float)s_cmp);
+        float my_min = 0.f, my_max = lane < nw ? warp_max[r * 32 + lane] : 0.f;
+        float pmn[2], pmx[2];
+        uint32_t tt[2];
+        bool lead[2];
+#pragma unroll
+        for (uint32_t h = 0; h < 2; ++h) {
+            const uint32_t j = h * 32 + lane;
+            const bool valid = j < n;
+            const uint32_t blk = valid ? wr[j].x : 0u;
+            const uint32_t t = mod_bd(blk);
+            tt[h] = t;
+            const uint32_t peers = __match_any_sync(0xffffffffu, valid ? t : 0xFFFF0000u + lane);
+            const bool first = valid && lane == (uint32_t)(__ffs(peers) - 1);
+            const bool ld = first && !((wbits[t >> 5] >> (t & 31u)) & 1u);       // no run of an earlier half belongs to t
+            __syncwarp();
+            if (ld) atomicOr(&wbits[t >> 5], 1u << (t & 31u));
+            __syncwarp();
+            lead[h] = ld;
+            float pmin = 0.f, pmax = 0.f;
+            if (ld) {
+                uint32_t v[kStageTerms];
+#pragma unroll
+                for (uint32_t m = 0; m < kStageTerms; ++m) {
+                    const uint32_t i = t + m * p.bd;
+                    v[m] = i < p.nb ? __ldcg(rd + i) : 0u;
+                }
+                uint32_t nxt = j;
+#pragma unroll
+                for (uint32_t m = 0; m < kStageTerms; ++m) {
+                    const uint32_t i = t + m * p.bd;
+                    if (i < p.nb) {
+                        const float a = (float)v[m] / nr;
+                        while (nxt < n && wr[nxt].x < i) ++nxt;
+                        if (nxt < n && wr[nxt].x == i) {
+                            const float c = (float)(wr[nxt].y & 0x7FFFFFFFu) / nc;
+                            pmin += fminf(a, c);
+                            pmax += fmaxf(a, c);
+                        } else {
+                            pmax += a;
+                        }
+                    }
+                }
+            }
+            pmn[h] = pmin;
+            pmx[h] = pmax;
+        }
+        uint32_t touched = __reduce_or_sync(0xffffffffu, (lead[0] ? 1u << (tt[0] >> 5) : 0u) | (lead[1] ? 1u << (tt[1] >> 5) : 0u));
+        while (touched) {
+            const uint32_t w = __ffs(touched) - 1;
+            touched &= touched - 1;
+            float leaf_min = 0.f, leaf_max = pm[(w << 5) + lane];
+#pragma unroll
+            for (uint32_t h = 0; h < 2; ++h) {
+                uint32_t sel = __ballot_sync(0xffffffffu, lead[h] && (tt[h] >> 5) == w);
+                while (sel) {
+                    const int src = __ffs(sel) - 1;
+                    sel &= sel - 1;
+                    const uint32_t tl = __shfl_sync(0xffffffffu, tt[h] & 31u, src);
+                    const float vmin = __shfl_sync(0xffffffffu, pmn[h], src);
+                    const float vmax = __shfl_sync(0xffffffffu, pmx[h], src);
+                    if (lane == tl) {
+                        leaf_min = vmin;
+                        leaf_max = vmax;
+                    }
+                }
+            }
+#pragma unroll
+            for (int x = 1; x < 32; x <<= 1) {
+                leaf_min += __shfl_xor_sync(0xffffffffu, leaf_min, x);
+                leaf_max += __shfl_xor_sync(0xffffffffu, leaf_max, x);
+            }
+            if (lane == w) {
+                my_min = leaf_min;
+                my_max = leaf_max;
+            }
+        }
+        __syncwarp();
+        wbits[lane] = 0;
+        __syncwarp();
         for (uint32_t stride = p.first_stride; stride >= 1; stride >>= 1) {
             const float tmin = __shfl_down_sync(0xffffffffu, my_min, stride);
             const float tmax = __shfl_down_sync(0xffffffffu, my_max, stride);
@@ -1248,7 +1374,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
         }
         __syncthreads();
         const uint32_t sh = s_sh[lane];
-        const bool ok = sh != 0 && !((float)sh < bound * (float)info.x);
+        const float nc = sqrtf((float)info.w);
+        const bool ok = sh != 0 && !((float)sh < bound * (float)info.x) && keep_by_union(sh, nc, (float)info.x / nc, lane);
         return __ballot_sync(0xffffffffu, ok) & alive;
     };
     // A row joins representative r: absorb + refresh in one, with the integer sums updated from the row's blocks alone
@@ -1315,7 +1442,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
         for (uint32_t j0 = info.y; j0 < info.z; j0 += 32) {
             const uint32_t j = j0 + lane;
             const bool valid = j < info.z;
-            const uint2 spr = (valid && sruns) ? sruns[lane] : make_uint2(0u, 0u);
+            const uint2 spr = (valid && sruns) ? sruns[j - info.y] : make_uint2(0u, 0u);
             const uint32_t blk = valid ? (sruns ? spr.x : __ldg(p.enc_blk + j)) : 0u;
             const uint32_t cnt = valid ? (sruns ? (spr.y & 0x7FFFFFFFu) : __ldg(p.counts + j)) : 0u;
             const uint32_t t = mod_bd(blk);
@@ -1390,6 +1517,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
 
     if (tid < 2) s_first[tid] = kNone;
     if (tid == 0) { s_touched = 0; s_red[0] = 0; s_red[1] = 0; }
+    s_wbits[tid] = 0;
     for (uint32_t i = tid; i < (nbp >> 1); i += kClusterThreads) reinterpret_cast<uint32_t*>(scratch)[i] = 0;
     uint32_t par_a = 0, par_b = 0;
     auto now_ns = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
@@ -1466,15 +1594,19 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                     if (wid < fb_n) {
                         const uint4 fi = s_finfo[wid];
                         const uint32_t fn = fi.z - fi.y;
-                        if (fn <= 32 && lane < fn) s_fruns[wid * 32 + lane] = __ldg(p.enc_pair + fi.y + lane);
+                        if (fn <= 64) {
+                            if (lane < fn) s_runs64[wid * 64 + lane] = __ldg(p.enc_pair + fi.y + lane);
+                            if (lane + 32 < fn) s_runs64[wid * 64 + lane + 32] = __ldg(p.enc_pair + fi.y + lane + 32);
+                        }
                     }
                     __syncthreads();
                 }
                 const uint32_t fk = cursor - fb_base;
                 const uint32_t pos = s_fpos[fk];
                 const uint4 info = s_finfo[fk];
-                const bool big = info.z - info.y > 32;
-                const uint2* sruns = big ? nullptr : s_fruns + fk * 32;
+                const uint32_t fn = info.z - info.y;
+                const bool big = fn > 64;                          // the CTA-wide scratch; up to 64 runs: warps, runs in shared memory
+                const uint2* sruns = big ? nullptr : s_runs64 + fk * 64;
                 uint32_t M = nrep ? size_mask(info, nrep) : 0u;    // uniform: every thread computes the same mask
                 bool expanded = false;
                 if (M && info.w) {
@@ -1499,7 +1631,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                     } else {
                         if (wid < __popc(M)) {
                             const uint32_t r = __fns(M, 0, (int)wid + 1);
-                            if (evaluate_pair(info, r, sruns) && lane == 0) atomicMin(&s_first[par_b], r);
+                            const bool joins = fn <= 32 ? evaluate_pair(info, r, sruns) : evaluate_medium(info, r, sruns, s_wbits + wid * 32);
+                            if (joins && lane == 0) atomicMin(&s_first[par_b], r);
                         }
                         __syncthreads();
                     }
@@ -1516,8 +1649,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                     ++nrep;
                     ++tr_found;
                     if (!big) {
-                        if (wid == 1 && lane < info.z - info.y) {   // the representative was all zero: plain stores
-                            const uint2 pr = sruns[lane];
+                        if (tid >= 32 && tid - 32 < fn) {          // the representative was all zero: plain stores
+                            const uint2 pr = sruns[tid - 32];
                             repd[(size_t)r * p.nb + pr.x] = pr.y & 0x7FFFFFFFu;
                             atomicOr(&slots[pr.x], 1u << r);
                         }
@@ -1601,15 +1734,23 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                     const uint4 kinfo = __ldg(p.pos_info + __ldcg(in + cursor + k));
                     uint32_t mk = s_mask[k];
                     if ((longs[k >> 5] >> (k & 31)) & 1u) mk = warp_shared_mask(kinfo, mk, nullptr);
-                    if (kinfo.z - kinfo.y > 32) {              // left for the scratch pass below
+                    const uint32_t kn = kinfo.z - kinfo.y;
+                    if (kn > 64) {                             // left for the scratch pass below
                         if (lane == 0) s_qmask[rk] = mk;
                         continue;
                     }
                     if (lane == 0) s_qmask[rk] = 0;
+                    uint2* wr = s_runs64 + wid * 64;
+                    if (kn > 32 && mk) {                       // 33..64 runs: staged once, evaluated by this warp
+                        __syncwarp();
+                        wr[lane] = __ldg(p.enc_pair + kinfo.y + lane);
+                        if (lane + 32 < kn) wr[lane + 32] = __ldg(p.enc_pair + kinfo.y + lane + 32);
+                        __syncwarp();
+                    }
                     while (mk) {
                         const uint32_t r = __ffs(mk) - 1;
                         mk &= mk - 1;
-                        if (evaluate_pair(kinfo, r, nullptr)) {
+                        if (kn <= 32 ? evaluate_pair(kinfo, r, nullptr) : evaluate_medium(kinfo, r, wr, s_wbits + wid * 32)) {
                             if (lane == 0) atomicMin(&s_first[par_b], (k << 5) | r);
                             break;
                         }
