@@ -846,6 +846,13 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
 //     ascending order.  The first row that joins ends the step: its representative is refreshed, the rows behind it are redone.
 //   * founding: while the stage has fewer than 32 representatives the stream is consumed row by row: the row joins the first
 //     existing representative that accepts it (the candidates are evaluated by different warps at once) or founds the next.
+//   * certain joins: a representative that holds a single column block b (count c) and a row whose only run is block b (count
+//     k): both normalise to exactly 1.0f in block b -- (float)c / sqrtf((float)(c * c)) == 1.0f for every c < 65536, checked
+//     exhaustively -- so the similarity is 1 and, after the join, the normalised representative, its L1 norm and its partial sums
+//     are bit-identical to what they were.  When the bounds leave such a row no other candidate, it joins without an
+//     evaluation and WITHOUT invalidating anything computed for the rows behind it: a step absorbs any number of them.  (On
+//     R-MAT graphs a third of the rows are single-run rows that pile into one cluster per hub block; handled one join per
+//     step they were 56 % of the 2^20-row run.)
 // All bounds are exact (they only skip pairs whose similarity cannot exceed alpha), so the permutation is the reference's.
 constexpr uint32_t kStageReps = 32;
 constexpr uint32_t kStageTerms = 8;    // column blocks per reference thread the stage kernel takes: nb <= 8 * bd
@@ -861,6 +868,10 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
     __shared__ uint32_t sq_s[kStageReps];      // (lossy) sum of squares of representative r
     __shared__ uint32_t tot_s[kStageReps];     // (lossy) sum of its counts
     __shared__ uint32_t s_sh[kStageReps];      // shared_mask_scratch: nnz the row shares with representative r
+    __shared__ uint32_t single_s[kStageReps];  // the one (kept) column block representative r consists of, else kNone
+    __shared__ uint32_t sc_s[kStageReps];      // ... and its count there
+    __shared__ uint32_t s_add[kStageReps];     // certain joins of the step: nnz added to representative r (zero between steps)
+    __shared__ uint32_t s_cj[2][32];           // bit: the row of the step is a certain join
     __shared__ uint32_t s_fpos[32];            // founding: the next rows of the input, fetched together ...
     __shared__ uint4 s_finfo[32];              // ... their pos_info ...
     __shared__ uint2 s_runs64[32 * 64];        // ... and the runs of those with at most 64; streaming: warp w stages a row of 33..64 runs at [w]
@@ -886,6 +897,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
     constexpr uint32_t kWarps = kClusterThreads / 32;
     constexpr uint32_t kWalkMax = 64;
     constexpr uint32_t kNone = 0xFFFFFFFFu;
+    const bool cj_on = p.alpha < 1.0f;         // similarity 1 must be an acceptance
     uint32_t* const repd = p.repd + (size_t)blockIdx.x * kStageReps * p.nb;     // dense representatives of this CTA
     auto mod_bd = [&](uint32_t blk) -> uint32_t { return p.bd_mask ? (blk & p.bd_mask) : blk % p.bd; };
 
@@ -1397,6 +1409,11 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
         dsq = __reduce_add_sync(0xffffffffu, dsq);
         dtot = __reduce_add_sync(0xffffffffu, dtot);
         if (lane == 0 && (dsq | dtot)) { atomicAdd(&s_red[0], dsq); atomicAdd(&s_red[1], dtot); }     // s_red is zero between uses
+        if (tid == 0 && single_s[r] != kNone) {                      // still a single block?
+            const uint2 pr0 = sruns ? sruns[0] : __ldg(p.enc_pair + info.y);
+            if (info.z - info.y == 1 && pr0.x == single_s[r]) sc_s[r] += pr0.y & 0x7FFFFFFFu;
+            else single_s[r] = kNone;
+        }
         __syncthreads();
         const uint32_t sqr = sq_s[r] + s_red[0], ttr = tot_s[r] + s_red[1];
         const float nr = sqrtf((float)sqr);
@@ -1542,6 +1559,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
         for (uint32_t i = tid; i < kStageReps * p.nb; i += kClusterThreads) repd[i] = 0;
         for (uint32_t i = tid; i < kStageReps * (1024 + 32); i += kClusterThreads) part_max[i] = 0.f;     // part_max and warp_max
         if (tid == 0) { s_nz = 0; s_blr_min = INFINITY; s_lr_max = 0.f; }
+        if (tid < kStageReps) { single_s[tid] = kNone; sc_s[tid] = 0; s_add[tid] = 0; }
         ++tr_polls;
         {
             const long long t0 = clock64();
@@ -1619,6 +1637,31 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                         M = shared_mask_scratch(info, M);
                     }
                 }
+                if (cj_on && M && !(M & (M - 1)) && fn == 1) {    // (uniform) certain join: see the kernel comment
+                    const uint32_t r = __ffs(M) - 1;
+                    const uint32_t sb = single_s[r];
+                    const uint2 pr = sruns[0];
+                    const uint32_t c = pr.y & 0x7FFFFFFFu;
+                    if (sb != kNone && pr.x == sb && (pr.y >> 31) && sc_s[r] + c <= 65535u) {
+                        __syncthreads();                           // every thread has read the stage's state
+                        if (tid == 0) {
+                            const uint32_t c2 = sc_s[r] + c;
+                            sc_s[r] = c2;
+                            repd[(size_t)r * p.nb + sb] = c2;
+                            sq_s[r] = c2 * c2;
+                            tot_s[r] = c2;
+                            nr_s[r] = sqrtf((float)(c2 * c2));
+                            p.cluster_ids[pos] = base + r;
+                        }
+                        __syncthreads();
+                        cursor += 1;
+                        ++tr_joins;
+                        ++tr_steps;
+                        ++tr_cand;
+                        tr_found_cyc += clock64() - tf0;
+                        continue;
+                    }
+                }
                 uint32_t jr = kNone;
                 if (M) {                                           // (uniform) candidates: the first that accepts wins
                     if (big) {
@@ -1655,6 +1698,10 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                             atomicOr(&slots[pr.x], 1u << r);
                         }
                         if (wid == 0) found_sparse(info, r, nrep, sruns);
+                        if (tid == 32 && fn == 1 && (sruns[0].y >> 31)) {      // a single kept block: certain joins possible
+                            single_s[r] = sruns[0].x;
+                            sc_s[r] = sruns[0].y & 0x7FFFFFFFu;
+                        }
                         __syncthreads();
                     } else {
                         absorb(info, r);
@@ -1682,32 +1729,84 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
             const uint32_t take = min(avail - cursor, fresh ? 128u : (uint32_t)kClusterThreads);
             ++tr_steps;
             tr_cand += take;
-            uint32_t pos1 = kNone, M = 0;
-            bool is_long = false;
+            uint32_t pos1 = kNone, M = 0, cj_r = 0, cj_cnt = 0;
+            bool is_long = false, cj = false;
             if (tid < take) {
                 pos1 = __ldcg(in + cursor + tid);
-                M = bounds_mask(__ldg(p.pos_info + pos1), kStageReps, is_long);
+                const uint4 info = __ldg(p.pos_info + pos1);
+                M = bounds_mask(info, kStageReps, is_long);
+                if (cj_on && M && !(M & (M - 1)) && info.z - info.y == 1) {       // certain join?  (see the kernel comment)
+                    const uint32_t r = __ffs(M) - 1;
+                    const uint32_t sb = single_s[r];
+                    if (sb != kNone && sc_s[r] <= 32767u) {                       // 1024 rows x 32 nnz keep the count below 65536
+                        const uint2 pr = __ldg(p.enc_pair + info.y);
+                        const uint32_t c = pr.y & 0x7FFFFFFFu;
+                        if (pr.x == sb && (pr.y >> 31) && c <= 32u) {
+                            cj = true;
+                            cj_r = r;
+                            cj_cnt = c;
+                            M = 0;
+                        }
+                    }
+                }
             }
             s_mask[tid] = M;
             const uint32_t evb = __ballot_sync(0xffffffffu, M != 0);
             const uint32_t lgb = __ballot_sync(0xffffffffu, is_long);
-            if (lane == 0) { s_ev[par_a][wid] = evb; s_long[par_a][wid] = lgb; }
+            const uint32_t cjb = __ballot_sync(0xffffffffu, cj);
+            if (lane == 0) { s_ev[par_a][wid] = evb; s_long[par_a][wid] = lgb; s_cj[par_a][wid] = cjb; }
             __syncthreads();                                  // S1: verdicts in; the rows stored by earlier steps are ordered before it
             if (tid == 0 && produced != published) st_release_u64(out_ctrl, make_ctrl(s + 1, produced, 0));
             published = produced;
             const uint32_t wmask = s_ev[par_a][lane];
+            const uint32_t cjw = s_cj[par_a][lane];
             const uint32_t* longs = s_long[par_a];
             par_a ^= 1;
-            uint32_t pre = __popc(wmask);
+            uint32_t pre = __popc(wmask), cpre = __popc(cjw);
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t t = __shfl_up_sync(0xffffffffu, pre, d);
-                if ((int)lane >= d) pre += t;
+                const uint32_t u = __shfl_up_sync(0xffffffffu, cpre, d);
+                if ((int)lane >= d) { pre += t; cpre += u; }
             }
             const uint32_t total_ev = __shfl_sync(0xffffffffu, pre, 31);
+            const uint32_t total_cj = __shfl_sync(0xffffffffu, cpre, 31);
+            // rows [0, limit) of the step are settled: the certain joins among them join, the others move on to the next stage
+            auto settle = [&](const uint32_t limit) {
+                uint32_t cj_lim = 0;
+                if (total_cj) {
+                    const uint32_t lw = limit >> 5;
+                    cj_lim = limit >= kClusterThreads ? total_cj
+                             : __shfl_sync(0xffffffffu, cpre - __popc(cjw), lw) + __popc(__shfl_sync(0xffffffffu, cjw, lw) & ((1u << (limit & 31u)) - 1u));
+                }
+                uint32_t before = 0;
+                if (total_cj) before = __shfl_sync(0xffffffffu, cpre - __popc(cjw), wid) + __popc(__shfl_sync(0xffffffffu, cjw, wid) & ((1u << lane) - 1u));
+                if (tid < limit) {
+                    if (cj) {
+                        atomicAdd(&s_add[cj_r], cj_cnt);
+                        p.cluster_ids[pos1] = base + cj_r;
+                    } else {
+                        out[produced + tid - before] = pos1;
+                    }
+                }
+                produced += limit - cj_lim;
+                if (cj_lim) {                                  // (uniform) the representatives' counts; nothing derived from them changes
+                    tr_joins += cj_lim;
+                    __syncthreads();
+                    if (tid < kStageReps && s_add[tid]) {
+                        const uint32_t c2 = sc_s[tid] + s_add[tid];
+                        s_add[tid] = 0;
+                        sc_s[tid] = c2;
+                        repd[(size_t)tid * p.nb + single_s[tid]] = c2;
+                        sq_s[tid] = c2 * c2;
+                        tot_s[tid] = c2;
+                        nr_s[tid] = sqrtf((float)(c2 * c2));
+                    }
+                    __syncthreads();
+                }
+            };
             if (total_ev == 0) {
-                if (tid < take) out[produced + tid] = pos1;
-                produced += take;
+                settle(take);
                 cursor += take;
                 if (fresh) {
                     __syncthreads();
@@ -1782,8 +1881,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
             if (tid == 0) s_first[par_b] = kNone;
             const uint32_t fj = fv == kNone ? kNone : fv >> 5;
             const uint32_t n_rej = fj == kNone ? take_eff : fj;
-            if (tid < n_rej) out[produced + tid] = pos1;
-            produced += n_rej;
+            settle(n_rej);
             if (fresh && n_rej) {
                 __syncthreads();
                 if (tid == 0) st_release_u64(out_ctrl, make_ctrl(s + 1, produced, 0));
