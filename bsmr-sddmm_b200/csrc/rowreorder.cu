@@ -192,6 +192,7 @@ struct ClusterParams {
     unsigned long long* ctrl;  // per slot: list id << 33 | entries << 1 | producer-done   (single writer, release-published)
     uint32_t* status;          // [0] = number of clusters (set once), [1] = finished flag, [2] = abort (watchdog)
     unsigned long long* trace_ts; // optional: per cluster {start, first publish, end} in ns (globaltimer)
+    unsigned long long* trace_stage; // optional (stage kernel): 8 counters per stage, stages <= 16384
     unsigned long long* trace; // [0] steps [1] candidates [2] joins [3] polls [4] poll cycles [5] eval cycles [6] update cycles [7] busy cycles
                                // [8] candidates rejected by the size bound alone (no block list read)
 };
@@ -872,6 +873,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
     __shared__ uint32_t sc_s[kStageReps];      // ... and its count there
     __shared__ uint32_t s_add[kStageReps];     // certain joins of the step: nnz added to representative r (zero between steps)
     __shared__ uint32_t s_cj[2][32];           // bit: the row of the step is a certain join
+    __shared__ uint32_t s_out[2][32];          // careful mode: what the round decided for the rows of the batch
     __shared__ uint32_t s_fpos[32];            // founding: the next rows of the input, fetched together ...
     __shared__ uint4 s_finfo[32];              // ... their pos_info ...
     __shared__ uint2 s_runs64[32 * 64];        // ... and the runs of those with at most 64; streaming: warp w stages a row of 33..64 runs at [w]
@@ -1148,6 +1150,41 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
         }
         const float sim = __shfl_sync(0xffffffffu, my_min, 0) / __shfl_sync(0xffffffffu, my_max, 0);
         return sim > p.alpha;
+    };
+    // Fast decision, one warp, a row of at most 64 runs staged in shared memory; lane = representative.  In real arithmetic
+    // max-sum = L1(rep) + L1(row) - min-sum (see keep_by_union), and min-sum only has terms in the row's blocks: n reads of the
+    // dense representative give the similarity to ~1e-6, all candidates of the row at once.  The reference's own value carries
+    // the rounding of its nb-term sums (< 4e-4 relative for nb <= 6144 + the division), so outside alpha +- 1e-3 -- the margin
+    // every bound of this file uses -- the decision is known; inside, `amb` sends the pair to the exact evaluation.
+    // acc / amb: bits of M that certainly join / that need the exact evaluation (every lane gets the same words).
+    auto fast_decide = [&](const uint4 info, const uint32_t M, const uint2* wr, uint32_t& acc, uint32_t& amb) {
+        const uint32_t n = info.z - info.y;
+        const float nc = sqrtf((float)info.w);
+        const float lc = (float)info.x / nc;
+        const bool mine = ((M >> lane) & 1u) && sq_s[lane] != 0 && info.w != 0;
+        const uint32_t* rd = repd + (size_t)lane * p.nb;
+        const float nr = nr_s[lane];
+        float msum = 0.f;
+        for (uint32_t i0 = 0; i0 < n; i0 += 8) {
+            uint32_t v[8];
+            float c[8];
+#pragma unroll
+            for (uint32_t u = 0; u < 8; ++u) {
+                const uint2 pr = i0 + u < n ? wr[i0 + u] : make_uint2(0u, 0u);      // broadcast read
+                const bool use = mine && (pr.y >> 31);
+                v[u] = use ? __ldcg(rd + pr.x) : 0u;
+                c[u] = (float)(pr.y & 0x7FFFFFFFu) / nc;
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < 8; ++u)
+                if (v[u]) msum += fminf((float)v[u] / nr, c[u]);
+        }
+        const float sim = msum / (l_s[lane].x + lc - msum);
+        const bool zero_case = ((M >> lane) & 1u) && !mine;               // a zero norm: the exact path knows the reference's rule
+        const bool yes = mine && sim > p.alpha + 1e-3f;
+        const bool no = mine && sim < bound;
+        acc = __ballot_sync(0xffffffffu, yes);
+        amb = __ballot_sync(0xffffffffu, zero_case || (mine && !yes && !no));
     };
     // Rows of 33..64 runs, one warp, runs staged in shared memory (`wr`, ascending blocks).  Same arithmetic as evaluate_pair;
     // a lane holds two runs (lane, lane + 32).  The run that comes first among those of a reference thread t leads it (found
@@ -1536,7 +1573,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
     if (tid == 0) { s_touched = 0; s_red[0] = 0; s_red[1] = 0; }
     s_wbits[tid] = 0;
     for (uint32_t i = tid; i < (nbp >> 1); i += kClusterThreads) reinterpret_cast<uint32_t*>(scratch)[i] = 0;
-    uint32_t par_a = 0, par_b = 0;
+    uint32_t par_a = 0, par_b = 0, par_c = 0;
     auto now_ns = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
     unsigned long long tr_steps = 0, tr_cand = 0, tr_joins = 0, tr_polls = 0, tr_events = 0, tr_found = 0;
     unsigned long long tr_long = 0, tr_poll_cyc = 0, tr_found_cyc = 0, tr_event_cyc = 0, tr_long_cyc = 0;
@@ -1580,6 +1617,10 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
         uint32_t cursor = 0, produced = 0, published = 0, nrep = 0;
         uint32_t fb_base = 0, fb_n = 0;                      // founding: the rows fetched into s_fpos / s_finfo / s_fruns
         uint32_t fresh_steps = 0;                            // streaming steps since the 32nd representative
+        bool careful = false;                                // 32 representatives, but joins are coming in bursts: rounds of 32 rows
+        uint32_t dbg_rounds = 0, dbg_rj_careful = 0, dbg_rj_stream = 0, dbg_cj = 0, dbg_steps = 0, dbg_solo = 0;   // (debug trace)
+        long long dbg_cyc_careful = 0, dbg_cyc_stream = 0;
+        uint32_t calm_rows = 0;                              // rows settled since the last join
         for (;;) {
             if (cursor >= avail) {
                 if (in_done) break;
@@ -1594,11 +1635,17 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                 in_done = (s_ctrl_copy & 1ull) != 0;
                 continue;
             }
-            if (nrep < kStageReps) {
-                // ---- founding: one row; joins the first representative that accepts it, else founds the next ----
-                // The stage forwards nothing until it has its 32 representatives, so this loop is the critical path of the whole
-                // pipeline: the next 32 rows' positions, pos_info and (rows of at most 32 runs) block lists are fetched together
-                // into shared memory, so that a row costs shared-memory work plus the reads of the dense representative.
+            if (nrep < kStageReps || careful) {
+                // ---- careful mode: rounds over a batch of 32 rows held in shared memory ----
+                // Used while the stage has fewer than 32 representatives (a row that joins nothing founds the next one, and nothing is
+                // forwarded before the 32nd: this is the critical path of the whole pipeline) and after a join in streaming mode (on
+                // graphs the joins come in bursts -- every row that holds a hub block joins that block's cluster -- and a join
+                // invalidates whatever was computed for the rows behind it: 1024-row steps would be thrown away 30 times over).
+                // The batch's positions, pos_info and block lists (rows of at most 64 runs) are fetched together.  A round: warp w
+                // decides row w of what is left of the batch against the current representatives; the first row that changes the
+                // stage (a join that is not a certain one, a founder, a row that needs the CTA-wide scratch) ends the round, everything
+                // before it is settled (certain joins, forwarded rows), the event is applied, and the next round re-decides only the
+                // rows behind it, out of shared memory.
                 const long long tf0 = clock64();
                 if (cursor >= fb_base + fb_n) {
                     fb_base = cursor;
@@ -1619,76 +1666,131 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                     }
                     __syncthreads();
                 }
-                const uint32_t fk = cursor - fb_base;
-                const uint32_t pos = s_fpos[fk];
-                const uint4 info = s_finfo[fk];
+                const uint32_t fk = cursor - fb_base;               // first undecided row of the batch
+                const uint32_t nrows = fb_n - fk;
+                constexpr uint32_t kReject = 0, kCertain = 1, kAccept = 2, kSolo = 3;
+                if (wid < nrows) {
+                    const uint32_t k = fk + wid;
+                    const uint4 info = s_finfo[k];
+                    const uint32_t fn = info.z - info.y;
+                    const uint2* sruns = fn <= 64 ? s_runs64 + k * 64 : nullptr;
+                    uint32_t M = nrep ? size_mask(info, nrep) : 0u;
+                    if (M && info.w) M = warp_shared_mask(info, M, sruns);
+                    uint32_t code = kReject;
+                    if (M) {
+                        if (fn > 64) {
+                            code = kSolo;
+                        } else {
+                            bool certain = false;
+                            if (cj_on && !(M & (M - 1)) && fn == 1) {
+                                const uint32_t r = __ffs(M) - 1;
+                                const uint2 pr = sruns[0];
+                                certain = single_s[r] != kNone && pr.x == single_s[r] && (pr.y >> 31) && (pr.y & 0x7FFFFFFFu) <= 32u && sc_s[r] <= 32767u;
+                                if (certain) code = kCertain | (r << 8);
+                            }
+                            if (!certain) {
+                                uint32_t acc, amb;
+                                fast_decide(info, M, sruns, acc, amb);
+                                uint32_t mk = acc | amb;
+                                while (mk) {
+                                    const uint32_t r = __ffs(mk) - 1;
+                                    mk &= mk - 1;
+                                    if (((acc >> r) & 1u) || (fn <= 32 ? evaluate_pair(info, r, sruns) : evaluate_medium(info, r, sruns, s_wbits + wid * 32))) {
+                                        code = kAccept | (r << 8);
+                                        break;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (lane == 0) s_out[par_c][k] = code;
+                }
+                __syncthreads();                                   // R1: every row of the round decided
+                if (tid == 0 && produced != published) st_release_u64(out_ctrl, make_ctrl(s + 1, produced, 0));
+                published = produced;
+                const uint32_t my_code = lane < nrows ? s_out[par_c][fk + lane] : kReject;
+                par_c ^= 1;
+                const uint32_t my_type = my_code & 0xFFu;
+                const bool founding = nrep < kStageReps;
+                const uint32_t evm = __ballot_sync(0xffffffffu, lane < nrows && (my_type == kAccept || my_type == kSolo || (my_type == kReject && founding)));
+                const uint32_t e = evm ? __ffs(evm) - 1 : nrows;    // the first row that changes the stage (relative to fk)
+                // settle the rows before it
+                const uint32_t cjm = __ballot_sync(0xffffffffu, lane < e && my_type == kCertain);
+                const uint32_t rjm = __ballot_sync(0xffffffffu, lane < e && my_type == kReject);     // (only with 32 representatives)
+                if (wid == 0 && lane < e) {
+                    const uint32_t ps = s_fpos[fk + lane];
+                    if (my_type == kCertain) {
+                        const uint32_t r = my_code >> 8;
+                        atomicAdd(&s_add[r], s_runs64[(fk + lane) * 64].y & 0x7FFFFFFFu);
+                        p.cluster_ids[ps] = base + r;
+                    } else {
+                        out[produced + __popc(rjm & ((1u << lane) - 1u))] = ps;
+                    }
+                }
+                produced += __popc(rjm);
+                calm_rows += e;
+                tr_joins += __popc(cjm);
+                tr_cand += e;
+                if (cjm) {                                         // (uniform)
+                    __syncthreads();
+                    if (tid < kStageReps && s_add[tid]) {
+                        const uint32_t c2 = sc_s[tid] + s_add[tid];
+                        s_add[tid] = 0;
+                        sc_s[tid] = c2;
+                        repd[(size_t)tid * p.nb + single_s[tid]] = c2;
+                        sq_s[tid] = c2 * c2;
+                        tot_s[tid] = c2;
+                        nr_s[tid] = sqrtf((float)(c2 * c2));
+                    }
+                    __syncthreads();
+                }
+                ++tr_steps;
+                ++dbg_rounds;
+                dbg_cj += __popc(cjm);
+                if (e == nrows) dbg_cyc_careful += clock64() - tf0;
+                if (e == nrows) {                                  // nothing changed the stage: the batch is used up
+                    cursor = fb_base + fb_n;
+                    if (!founding && calm_rows >= 64) careful = false;
+                    tr_found_cyc += clock64() - tf0;
+                    continue;
+                }
+                // ---- the event row ----
+                const uint32_t k = fk + e;
+                const uint32_t ecode = __shfl_sync(0xffffffffu, my_code, e);
+                const uint32_t pos = s_fpos[k];
+                const uint4 info = s_finfo[k];
                 const uint32_t fn = info.z - info.y;
-                const bool big = fn > 64;                          // the CTA-wide scratch; up to 64 runs: warps, runs in shared memory
-                const uint2* sruns = big ? nullptr : s_runs64 + fk * 64;
-                uint32_t M = nrep ? size_mask(info, nrep) : 0u;    // uniform: every thread computes the same mask
-                bool expanded = false;
-                if (M && info.w) {
-                    if (!big) {
-                        M = warp_shared_mask(info, M, sruns);
-                    } else {
-                        expand_row(info);
-                        expanded = true;
-                        __syncthreads();
-                        M = shared_mask_scratch(info, M);
-                    }
-                }
-                if (cj_on && M && !(M & (M - 1)) && fn == 1) {    // (uniform) certain join: see the kernel comment
-                    const uint32_t r = __ffs(M) - 1;
-                    const uint32_t sb = single_s[r];
-                    const uint2 pr = sruns[0];
-                    const uint32_t c = pr.y & 0x7FFFFFFFu;
-                    if (sb != kNone && pr.x == sb && (pr.y >> 31) && sc_s[r] + c <= 65535u) {
-                        __syncthreads();                           // every thread has read the stage's state
-                        if (tid == 0) {
-                            const uint32_t c2 = sc_s[r] + c;
-                            sc_s[r] = c2;
-                            repd[(size_t)r * p.nb + sb] = c2;
-                            sq_s[r] = c2 * c2;
-                            tot_s[r] = c2;
-                            nr_s[r] = sqrtf((float)(c2 * c2));
-                            p.cluster_ids[pos] = base + r;
-                        }
-                        __syncthreads();
-                        cursor += 1;
-                        ++tr_joins;
-                        ++tr_steps;
-                        ++tr_cand;
-                        tr_found_cyc += clock64() - tf0;
-                        continue;
-                    }
-                }
+                const bool big = fn > 64;
+                const uint2* sruns = big ? nullptr : s_runs64 + k * 64;
                 uint32_t jr = kNone;
-                if (M) {                                           // (uniform) candidates: the first that accepts wins
-                    if (big) {
-                        if (!expanded) {
-                            expand_row(info);
-                            expanded = true;
-                            __syncthreads();
-                        }
+                bool expanded = false;
+                if ((ecode & 0xFFu) == kAccept) {
+                    jr = ecode >> 8;
+                } else if ((ecode & 0xFFu) == kSolo) {
+                    // a row of more than 64 runs with candidates left: the CTA-wide scratch
+                    uint32_t M = size_mask(info, nrep);
+                    expand_row(info);
+                    expanded = true;
+                    __syncthreads();
+                    if (M && info.w) M = shared_mask_scratch(info, M);
+                    if (M) {
                         scratch_pass(info, M, 0u, &s_first[par_b]);
-                    } else {
-                        if (wid < __popc(M)) {
-                            const uint32_t r = __fns(M, 0, (int)wid + 1);
-                            const bool joins = fn <= 32 ? evaluate_pair(info, r, sruns) : evaluate_medium(info, r, sruns, s_wbits + wid * 32);
-                            if (joins && lane == 0) atomicMin(&s_first[par_b], r);
-                        }
-                        __syncthreads();
+                        jr = s_first[par_b];
+                        par_b ^= 1;
+                        if (tid == 0) s_first[par_b] = kNone;      // visible after the barrier(s) below
                     }
-                    jr = s_first[par_b];
-                    par_b ^= 1;
-                    if (tid == 0) s_first[par_b] = kNone;          // visible after the barrier(s) below
-                } else {
-                    __syncthreads();                               // every warp has read the stage's state before it changes
+                    clear_row(info);                               // closed by the barrier(s) below
                 }
-                if (expanded) clear_row(info);                     // closed by the barrier(s) below
-                const uint32_t r = jr != kNone ? jr : nrep;
-                if (tid == 0) p.cluster_ids[pos] = base + r;
-                if (jr == kNone) {
+                if ((ecode & 0xFFu) == kSolo) ++dbg_solo;
+                if (jr != kNone) {
+                    if (tid == 0) p.cluster_ids[pos] = base + jr;
+                    ++tr_joins;
+                    ++dbg_rj_careful;
+                    join_absorb_refresh(info, jr, nrep, sruns);
+                    calm_rows = 0;
+                } else if (founding) {
+                    const uint32_t r = nrep;
+                    if (tid == 0) p.cluster_ids[pos] = base + r;
                     ++nrep;
                     ++tr_found;
                     if (!big) {
@@ -1709,16 +1811,21 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                     }
                     if (nrep == kStageReps) {
                         fresh_steps = 0;
+                        careful = false;
                         if (tid == 0 && p.trace_ts && s <= p.M) p.trace_ts[3 * s + 1] = now_ns();
                     }
                 } else {
-                    ++tr_joins;
-                    join_absorb_refresh(info, r, nrep, sruns);
+                    // (a kSolo row that joined nothing, 32 representatives): it moves on
+                    if (tid == 0) out[produced] = pos;
+                    produced += 1;
+                    calm_rows += 1;
+                    __syncthreads();                               // closes clear_row
                 }
-                cursor += 1;
-                ++tr_steps;
+                (void)expanded;
+                cursor = fb_base + k + 1;
                 ++tr_cand;
                 tr_found_cyc += clock64() - tf0;
+                dbg_cyc_careful += clock64() - tf0;
                 continue;
             }
             // ---- streaming step: up to 1024 rows, one per thread, against all 32 representatives ----
@@ -1726,6 +1833,9 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
             // the first steps after the founding are short and publish at once: the next stage is waiting for its first rows
             const bool fresh = fresh_steps < 3;
             ++fresh_steps;
+            fb_n = 0;                                           // (the warps stage rows in s_runs64 below: the careful-mode batch is gone)
+            const long long ts0 = clock64();
+            ++dbg_steps;
             const uint32_t take = min(avail - cursor, fresh ? 128u : (uint32_t)kClusterThreads);
             ++tr_steps;
             tr_cand += take;
@@ -1792,6 +1902,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                 produced += limit - cj_lim;
                 if (cj_lim) {                                  // (uniform) the representatives' counts; nothing derived from them changes
                     tr_joins += cj_lim;
+                    dbg_cj += cj_lim;
                     __syncthreads();
                     if (tid < kStageReps && s_add[tid]) {
                         const uint32_t c2 = sc_s[tid] + s_add[tid];
@@ -1813,6 +1924,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                     if (tid == 0) st_release_u64(out_ctrl, make_ctrl(s + 1, produced, 0));
                     published = produced;
                 }
+                dbg_cyc_stream += clock64() - ts0;
                 continue;
             }
             auto nth_ev = [&](uint32_t rk) -> uint32_t {
@@ -1840,18 +1952,21 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                     }
                     if (lane == 0) s_qmask[rk] = 0;
                     uint2* wr = s_runs64 + wid * 64;
-                    if (kn > 32 && mk) {                       // 33..64 runs: staged once, evaluated by this warp
+                    if (mk) {                                  // the row's runs, staged once for this warp
                         __syncwarp();
-                        wr[lane] = __ldg(p.enc_pair + kinfo.y + lane);
+                        if (lane < kn) wr[lane] = __ldg(p.enc_pair + kinfo.y + lane);
                         if (lane + 32 < kn) wr[lane + 32] = __ldg(p.enc_pair + kinfo.y + lane + 32);
                         __syncwarp();
-                    }
-                    while (mk) {
-                        const uint32_t r = __ffs(mk) - 1;
-                        mk &= mk - 1;
-                        if (kn <= 32 ? evaluate_pair(kinfo, r, nullptr) : evaluate_medium(kinfo, r, wr, s_wbits + wid * 32)) {
-                            if (lane == 0) atomicMin(&s_first[par_b], (k << 5) | r);
-                            break;
+                        uint32_t acc, amb;
+                        fast_decide(kinfo, mk, wr, acc, amb);
+                        mk = acc | amb;
+                        while (mk) {
+                            const uint32_t r = __ffs(mk) - 1;
+                            mk &= mk - 1;
+                            if (((acc >> r) & 1u) || (kn <= 32 ? evaluate_pair(kinfo, r, wr) : evaluate_medium(kinfo, r, wr, s_wbits + wid * 32))) {
+                                if (lane == 0) atomicMin(&s_first[par_b], (k << 5) | r);
+                                break;
+                            }
                         }
                     }
                 }
@@ -1895,10 +2010,19 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                 join_absorb_refresh(__ldg(p.pos_info + __ldcg(in + cursor + fj)), jr, kStageReps, nullptr);
                 cursor += fj + 1;
                 ++tr_joins;
+                careful = true;                                // joins come in bursts: go on in rounds of 32 rows
+                calm_rows = 0;
+                ++dbg_rj_stream;
             }
+            dbg_cyc_stream += clock64() - ts0;
         }
         __syncthreads();
         if (tid == 0 && p.trace_ts && s <= p.M) p.trace_ts[3 * s + 2] = now_ns();
+        if (tid == 0 && p.trace_stage && s <= 16384) {
+            unsigned long long* d = p.trace_stage + 8 * (size_t)s;
+            d[0] = dbg_rounds; d[1] = dbg_rj_careful; d[2] = dbg_rj_stream; d[3] = dbg_cj; d[4] = dbg_steps; d[5] = dbg_solo;
+            d[6] = (unsigned long long)dbg_cyc_careful; d[7] = (unsigned long long)dbg_cyc_stream;
+        }
         if (tid == 0) {
             if (produced == 0) {                 // nothing left for a next stage: this one holds the last cluster
                 p.status[0] = base + nrep - 1;
@@ -2126,6 +2250,12 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
             ClusterParams cp{};
             cp.trace = want_trace ? trace.ptr : nullptr;
             cp.trace_ts = want_trace ? trace_ts.ptr : nullptr;
+            TmpBuf<unsigned long long> trace_stage(ws);
+            if (want_trace) {
+                BSMR_TRY(trace_stage.alloc(8 * 16385));
+                BSMR_CUDA_OK(cudaMemsetAsync(trace_stage.ptr, 0, trace_stage.bytes(), st));
+                cp.trace_stage = trace_stage.ptr;
+            }
             cp.bd_mask = (bd & (bd - 1)) == 0 ? bd - 1 : 0u;
             cp.kept_mask = kept_mask; cp.pos_info = pos_info.ptr; cp.scratch = use_scratch ? scratch_entries : 0u;
             cp.M = M; cp.nb = nb; cp.bd = bd; cp.first_stride = first_stride; cp.zero_rows = zero_rows; cp.alpha = alpha;
@@ -2175,6 +2305,14 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
                     const unsigned long long t0 = ts[3];
                     auto us = [&](unsigned long long t) { return (double)(t - t0) / 1e3; };
                     fprintf(stderr, "[bsmr trace]   cluster: start / first publish / end (us)\n");
+                    if (use_stage) {
+                        std::vector<unsigned long long> sd(8 * 16385);
+                        BSMR_CUDA_OK(cudaMemcpy(sd.data(), trace_stage.ptr, sd.size() * 8, cudaMemcpyDeviceToHost));
+                        fprintf(stderr, "[bsmr stage] stage: careful rounds / joins in careful / joins in streaming / certain joins / streaming steps / solo rows / Mcyc careful / Mcyc streaming\n");
+                        for (uint32_t c = 1; c <= nc && c <= 16384; c = c < 8 ? c + 1 : (c < 400 ? c + 8 : c + 500))
+                            fprintf(stderr, "[bsmr stage] %6u: %llu %llu %llu %llu %llu %llu %.1f %.1f\n", c, sd[8 * c], sd[8 * c + 1], sd[8 * c + 2], sd[8 * c + 3],
+                                    sd[8 * c + 4], sd[8 * c + 5], sd[8 * c + 6] / 1e6, sd[8 * c + 7] / 1e6);
+                    }
                     const char* tv = std::getenv("BSMR_TRACE");
                     const bool all = tv && tv[0] == 'a';
                     for (uint32_t c = 1; c <= nc; c = (all || c < 8) ? c + 1 : c + (nc / 12 ? nc / 12 : 1))
