@@ -886,8 +886,10 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
     __shared__ uint32_t s_ev[2][32];
     __shared__ uint32_t s_long[2][32];         // bit: the event row still needs the warp-level shared-nnz bound
     __shared__ uint32_t s_first[2];
-    __shared__ float s_fv[32];
-    __shared__ uint32_t s_qmask[64];           // per event row of the step: representatives left for the scratch pass (rows of > 32 runs)
+    __shared__ float s_fv[32 * 32];            // found_sparse: per warp, the normalised counts of a chunk of runs
+    __shared__ uint32_t s_pair[32];            // batch founding: bit i of word j = row j of the batch might join a cluster founded by row i
+    __shared__ uint8_t s_qun[128];             // ... and whether the shared-nnz bound is still to be applied (very long rows)
+    __shared__ uint32_t s_qmask[128];           // per event row of the step: representatives left for the scratch pass (rows of > 32 runs)
     __shared__ uint32_t s_touched;             // reference warps that own a block of the row in the scratch
     __shared__ float2 s_res[kStageReps * 32];  // scratch pass: per (representative, reference warp) the {min, max} sums
     __shared__ unsigned long long s_ctrl;
@@ -940,7 +942,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
             nr_s[r] = nr;
             const float l1 = sqr ? (float)ttr / nr : 0.f;
             l_s[r] = make_float2(l1, bound * l1);
-            if (sqr) s_nz |= 1u << r;
+            if (sqr) atomicOr(&s_nz, 1u << r);
         }
         __syncthreads();
         if (wid == 0) {
@@ -993,18 +995,26 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
     // representatives of `alive` that pass  shared >= 1 and shared >= bound * (kept nnz of the row).  Not for info.w == 0.
     auto warp_shared_mask = [&](const uint4 info, uint32_t alive, const uint2* sruns) -> uint32_t {
         uint32_t sh = 0;
-        for (uint32_t j0 = info.y; j0 < info.z; j0 += 32) {
-            const uint32_t j = j0 + lane;
-            const uint2 pr = j < info.z ? (sruns ? sruns[j - info.y] : __ldg(p.enc_pair + j)) : make_uint2(0u, 0u);   // sruns: the row's runs in shared memory
-            const uint32_t m = (pr.y >> 31) ? (slots[pr.x] & alive) : 0u;
-            const uint32_t cnt = pr.y & 0x7FFFFFFFu;
-            uint32_t hit = __ballot_sync(0xffffffffu, m != 0);
-            while (hit) {
-                const int i = __ffs(hit) - 1;
-                hit &= hit - 1;
-                const uint32_t mi = __shfl_sync(0xffffffffu, m, i);
-                const uint32_t ci = __shfl_sync(0xffffffffu, cnt, i);
-                if ((mi >> lane) & 1u) sh += ci;
+        for (uint32_t j0 = info.y; j0 < info.z; j0 += 128) {           // four chunks of 32 runs in flight (long rows: one round trip per 128 runs)
+            uint2 pr4[4];
+#pragma unroll
+            for (uint32_t u = 0; u < 4; ++u) {
+                const uint32_t j = j0 + 32 * u + lane;
+                pr4[u] = j < info.z ? (sruns ? sruns[j - info.y] : __ldg(p.enc_pair + j)) : make_uint2(0u, 0u);   // sruns: the row's runs in shared memory
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < 4; ++u) {
+                if (j0 + 32 * u >= info.z) break;                      // (uniform)
+                const uint32_t m = (pr4[u].y >> 31) ? (slots[pr4[u].x] & alive) : 0u;
+                const uint32_t cnt = pr4[u].y & 0x7FFFFFFFu;
+                uint32_t hit = __ballot_sync(0xffffffffu, m != 0);
+                while (hit) {
+                    const int i = __ffs(hit) - 1;
+                    hit &= hit - 1;
+                    const uint32_t mi = __shfl_sync(0xffffffffu, m, i);
+                    const uint32_t ci = __shfl_sync(0xffffffffu, cnt, i);
+                    if ((mi >> lane) & 1u) sh += ci;
+                }
             }
         }
         const float nc = sqrtf((float)info.w);
@@ -1302,8 +1312,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
         touched = __reduce_or_sync(0xffffffffu, touched);
         if (lane == 0 && touched) atomicOr(&s_touched, touched);
     };
-    auto clear_row = [&](const uint4 info) {
-        for (uint32_t j = info.y + tid; j < info.z; j += kClusterThreads) scratch[__ldg(p.enc_blk + j)] = 0;
+    auto clear_row = [&](const uint4) {
+        for (uint32_t i = tid; i < (nbp >> 1); i += kClusterThreads) reinterpret_cast<uint32_t*>(scratch)[i] = 0;     // 3 words per thread: cheaper than reading the row again
         if (tid == 0) s_touched = 0;
     };
     // The whole CTA, after expand_row + barrier: does the row in the scratch join one of the representatives `mk`?  CTA warp w
@@ -1469,7 +1479,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
             nr_s[r] = nr;
             const float l1 = sqr ? (float)ttr / nr : 0.f;
             l_s[r] = make_float2(l1, bound * l1);
-            if (sqr) s_nz |= 1u << r;
+            if (sqr) atomicOr(&s_nz, 1u << r);
             s_red[0] = 0;
             s_red[1] = 0;
         }
@@ -1500,13 +1510,14 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
             const uint32_t blk = valid ? (sruns ? spr.x : __ldg(p.enc_blk + j)) : 0u;
             const uint32_t cnt = valid ? (sruns ? (spr.y & 0x7FFFFFFFu) : __ldg(p.counts + j)) : 0u;
             const uint32_t t = mod_bd(blk);
-            s_fv[lane] = (float)cnt / nr;
+            float* fv = s_fv + wid * 32;
+            fv[lane] = (float)cnt / nr;
             __syncwarp();
             // runs of the same reference thread (blk = t, t + bd, ...) are added in ascending block order = ascending lane
             const uint32_t peers = __match_any_sync(0xffffffffu, valid ? t : 0xFFFF0000u + lane);
             if (valid && lane == (uint32_t)(__ffs(peers) - 1)) {
                 float acc = pm[t];
-                for (uint32_t rest = peers; rest; rest &= rest - 1) acc += s_fv[__ffs(rest) - 1];
+                for (uint32_t rest = peers; rest; rest &= rest - 1) acc += fv[__ffs(rest) - 1];
                 pm[t] = acc;
                 touched |= 1u << (t >> 5);
             }
@@ -1527,8 +1538,9 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
             nr_s[r] = nr;
             const float l1 = info.w ? (float)info.x / nr : 0.f;
             l_s[r] = make_float2(l1, bound * l1);
-            if (info.w) s_nz |= 1u << r;
+            if (info.w) atomicOr(&s_nz, 1u << r);
         }
+        if (nrep_now == 0) return;                                   // (several founders at once: the caller refreshes the summary)
         __syncwarp();
         const bool on = lane < nrep_now && ((s_nz >> lane) & 1u);
         float lo = on ? l_s[lane].y : INFINITY, hi = on ? l_s[lane].x : 0.f;
@@ -1675,7 +1687,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                     const uint32_t fn = info.z - info.y;
                     const uint2* sruns = fn <= 64 ? s_runs64 + k * 64 : nullptr;
                     uint32_t M = nrep ? size_mask(info, nrep) : 0u;
-                    if (M && info.w) M = warp_shared_mask(info, M, sruns);
+                    if (M && info.w && fn <= 64) M = warp_shared_mask(info, M, sruns);     // (longer rows: the CTA-wide scratch does it, once)
                     uint32_t code = kReject;
                     if (M) {
                         if (fn > 64) {
@@ -1705,6 +1717,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                     }
                     if (lane == 0) s_out[par_c][k] = code;
                 }
+                if (tid < 32) s_pair[tid] = 0;
                 __syncthreads();                                   // R1: every row of the round decided
                 if (tid == 0 && produced != published) st_release_u64(out_ctrl, make_ctrl(s + 1, produced, 0));
                 published = produced;
@@ -1712,19 +1725,128 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                 par_c ^= 1;
                 const uint32_t my_type = my_code & 0xFFu;
                 const bool founding = nrep < kStageReps;
-                const uint32_t evm = __ballot_sync(0xffffffffu, lane < nrows && (my_type == kAccept || my_type == kSolo || (my_type == kReject && founding)));
-                const uint32_t e = evm ? __ffs(evm) - 1 : nrows;    // the first row that changes the stage (relative to fk)
+                const uint32_t my_n = lane < nrows ? s_finfo[fk + lane].z - s_finfo[fk + lane].y : 0u;
+                const uint32_t stopm = __ballot_sync(0xffffffffu, lane < nrows && (my_type == kAccept || my_type == kSolo));
+                const uint32_t e_stop = stopm ? __ffs(stopm) - 1 : nrows;
+                const uint32_t rejm_all = __ballot_sync(0xffffffffu, lane < e_stop && my_type == kReject);
+                uint32_t founders = 0, e = e_stop;
+                if (founding && rejm_all) {
+                    // ---- founders, several per round ----
+                    // Every row that joins nothing founds a representative -- but the second must also be tested against the first.
+                    // Thread (i, j) of the CTA tests row j of the batch against a cluster made of row i alone with the sparse
+                    // similarity (fast_decide's formula over two block lists in shared memory); rows that pass nothing, in order,
+                    // are founded together, a warp each.  A row that might join an earlier founder of the round ends it and is
+                    // decided in the next round.
+                    {
+                        const uint32_t i = wid, j = lane;            // thread (i, j), i < j
+                        bool maybe = false;
+                        if (i < j && j < e_stop && ((rejm_all >> i) & 1u) && ((rejm_all >> j) & 1u)) {
+                            const uint4 ii = s_finfo[fk + i], ij = s_finfo[fk + j];
+                            const uint32_t ni = ii.z - ii.y, nj = ij.z - ij.y;
+                            if (ni > 64 || nj > 64 || ii.w == 0 || ij.w == 0) {
+                                maybe = true;
+                            } else {
+                                const uint2* ri = s_runs64 + (fk + i) * 64;
+                                const uint2* rj = s_runs64 + (fk + j) * 64;
+                                const float nci = sqrtf((float)ii.w), ncj = sqrtf((float)ij.w);
+                                float msum = 0.f;
+                                uint32_t a = 0, b = 0;
+                                while (a < ni && b < nj) {
+                                    const uint2 pa = ri[a], pb = rj[b];
+                                    if (pa.x == pb.x) {
+                                        if (pa.y >> 31) msum += fminf((float)(pa.y & 0x7FFFFFFFu) / nci, (float)(pb.y & 0x7FFFFFFFu) / ncj);
+                                        ++a;
+                                        ++b;
+                                    } else if (pa.x < pb.x) {
+                                        ++a;
+                                    } else {
+                                        ++b;
+                                    }
+                                }
+                                const float sim = msum / ((float)ii.x / nci + (float)ij.x / ncj - msum);
+                                maybe = !(sim < bound);
+                            }
+                        }
+                        const uint32_t mm = __ballot_sync(0xffffffffu, maybe);     // lanes = j, this warp = i
+                        for (uint32_t rest = mm; rest; rest &= rest - 1)
+                            if (lane == (uint32_t)(__ffs(rest) - 1)) atomicOr(&s_pair[lane], 1u << i);
+                    }
+                    __syncthreads();
+                    uint32_t count = 0;
+                    e = e_stop;
+                    for (uint32_t j = 0; j < e_stop; ++j) {          // (every thread runs the same scan)
+                        if (!((rejm_all >> j) & 1u)) continue;       // a certain join: stays valid, its representative comes first
+                        const uint32_t nj = __shfl_sync(0xffffffffu, my_n, j);
+                        if ((s_pair[j] & founders) || nrep + count == kStageReps || (nj > 64 && founders)) { e = j; break; }
+                        founders |= 1u << j;
+                        ++count;
+                        if (nj > 64) { e = j + 1; break; }           // (founded through the dense refresh below, alone)
+                    }
+                }
                 // settle the rows before it
                 const uint32_t cjm = __ballot_sync(0xffffffffu, lane < e && my_type == kCertain);
-                const uint32_t rjm = __ballot_sync(0xffffffffu, lane < e && my_type == kReject);     // (only with 32 representatives)
+                const uint32_t rjm = __ballot_sync(0xffffffffu, lane < e && my_type == kReject && !founding);     // (only with 32 representatives)
                 if (wid == 0 && lane < e) {
                     const uint32_t ps = s_fpos[fk + lane];
                     if (my_type == kCertain) {
                         const uint32_t r = my_code >> 8;
                         atomicAdd(&s_add[r], s_runs64[(fk + lane) * 64].y & 0x7FFFFFFFu);
                         p.cluster_ids[ps] = base + r;
-                    } else {
+                    } else if (!founding) {
                         out[produced + __popc(rjm & ((1u << lane) - 1u))] = ps;
+                    }
+                }
+                if (founders) {
+                    // ---- found them: warp w takes the w-th, representative nrep + w ----
+                    const uint32_t count = __popc(founders);
+                    bool big_last = false;
+                    if (wid < count) {
+                        const uint32_t j = __fns(founders, 0, (int)wid + 1);
+                        const uint32_t r = nrep + wid;
+                        const uint4 info = s_finfo[fk + j];
+                        const uint32_t fn = info.z - info.y;
+                        if (lane == 0) p.cluster_ids[s_fpos[fk + j]] = base + r;
+                        if (fn <= 64) {
+                            const uint2* sruns = s_runs64 + (fk + j) * 64;
+                            for (uint32_t x = lane; x < fn; x += 32) {     // the representative was all zero: plain stores
+                                const uint2 pr = sruns[x];
+                                repd[(size_t)r * p.nb + pr.x] = pr.y & 0x7FFFFFFFu;
+                                atomicOr(&slots[pr.x], 1u << r);
+                            }
+                            found_sparse(info, r, 0u, sruns);
+                            if (lane == 0 && fn == 1 && (sruns[0].y >> 31)) {   // a single kept block: certain joins possible
+                                single_s[r] = sruns[0].x;
+                                sc_s[r] = sruns[0].y & 0x7FFFFFFFu;
+                            }
+                        }
+                    }
+                    {   // (a founder of more than 64 runs is the last of its round)
+                        const uint32_t jl = 31 - __clz(founders);
+                        big_last = __shfl_sync(0xffffffffu, my_n, jl) > 64;
+                        if (big_last) {
+                            const uint32_t r = nrep + count - 1;
+                            absorb(s_finfo[fk + jl], r);
+                            refresh(r, nrep + count);
+                        }
+                    }
+                    nrep += count;
+                    tr_found += count;
+                    __syncthreads();
+                    if (wid == 0) {                                // the size-bound summary over all representatives
+                        const bool on = lane < nrep && ((s_nz >> lane) & 1u);
+                        float lo = on ? l_s[lane].y : INFINITY, hi = on ? l_s[lane].x : 0.f;
+#pragma unroll
+                        for (int x = 1; x < 32; x <<= 1) {
+                            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, x));
+                            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, x));
+                        }
+                        if (lane == 0) { s_blr_min = lo; s_lr_max = hi; }
+                    }
+                    __syncthreads();
+                    if (nrep == kStageReps) {
+                        fresh_steps = 0;
+                        careful = false;
+                        if (tid == 0 && p.trace_ts && s <= p.M) p.trace_ts[3 * s + 1] = now_ns();
                     }
                 }
                 produced += __popc(rjm);
@@ -1752,6 +1874,12 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                     cursor = fb_base + fb_n;
                     if (!founding && calm_rows >= 64) careful = false;
                     tr_found_cyc += clock64() - tf0;
+                    continue;
+                }
+                if (founders || (founding && e < e_stop)) {        // founders were made (or the stage is full): the row at e is decided next round
+                    cursor = fb_base + fk + e;
+                    tr_found_cyc += clock64() - tf0;
+                    dbg_cyc_careful += clock64() - tf0;
                     continue;
                 }
                 // ---- the event row ----
@@ -1829,7 +1957,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                 continue;
             }
             // ---- streaming step: up to 1024 rows, one per thread, against all 32 representatives ----
-            constexpr uint32_t kCpwB = 2;                       // event rows a warp evaluates per step
+            constexpr uint32_t kCpwB = 4;                       // event rows a warp evaluates per step (measured: 11 % of the rows of a step are events)
             // the first steps after the founding are short and publish at once: the next stage is waiting for its first rows
             const bool fresh = fresh_steps < 3;
             ++fresh_steps;
@@ -1944,10 +2072,14 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                     const uint32_t k = nth_ev(rk);
                     const uint4 kinfo = __ldg(p.pos_info + __ldcg(in + cursor + k));
                     uint32_t mk = s_mask[k];
-                    if ((longs[k >> 5] >> (k & 31)) & 1u) mk = warp_shared_mask(kinfo, mk, nullptr);
                     const uint32_t kn = kinfo.z - kinfo.y;
+                    // (a warp walks 32 runs per round trip: beyond a few hundred runs the CTA-wide scratch is faster, bound included)
+                    // (measured: sending every row of > 256 runs to the CTA-wide scratch instead costs 2x -- 88 M scratch passes on the
+                    //  2^20-row graph where the warps reject all but 3 M -- so the warps keep the bound; kept as a switch)
+                    const bool unmasked = false;
+                    if (!unmasked && ((longs[k >> 5] >> (k & 31)) & 1u)) mk = warp_shared_mask(kinfo, mk, nullptr);
                     if (kn > 64) {                             // left for the scratch pass below
-                        if (lane == 0) s_qmask[rk] = mk;
+                        if (lane == 0) { s_qmask[rk] = mk; s_qun[rk] = unmasked; }
                         continue;
                     }
                     if (lane == 0) s_qmask[rk] = 0;
@@ -1984,7 +2116,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                 const uint4 kinfo = __ldg(p.pos_info + __ldcg(in + cursor + k));
                 expand_row(kinfo);
                 __syncthreads();
-                scratch_pass(kinfo, mk, k << 5, &s_first[par_b]);
+                const uint32_t mk2 = s_qun[rk] ? shared_mask_scratch(kinfo, mk) : mk;      // (uniform)
+                if (mk2) scratch_pass(kinfo, mk2, k << 5, &s_first[par_b]);
                 clear_row(kinfo);
                 __syncthreads();
                 ++tr_long;
