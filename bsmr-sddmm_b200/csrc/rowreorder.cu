@@ -1196,6 +1196,47 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
         acc = __ballot_sync(0xffffffffu, yes);
         amb = __ballot_sync(0xffffffffu, zero_case || (mine && !yes && !no));
     };
+    // The same decision for a row of more than 64 runs, read from global memory: lanes = runs (128 in flight), one candidate
+    // representative after the other in ascending order, stopping at the first certain acceptance.  cand = the candidates that
+    // are not certainly rejected, up to and including that acceptance; exact = false when one of them needs the exact evaluation.
+    auto fast_decide_long = [&](const uint4 info, const uint32_t M, uint32_t& cand, bool& exact_needed) {
+        const float nc = sqrtf((float)info.w);
+        const float lc = (float)info.x / nc;
+        cand = 0;
+        exact_needed = false;
+        for (uint32_t rest = M; rest; rest &= rest - 1) {
+            const uint32_t r = __ffs(rest) - 1;
+            if (sq_s[r] == 0 || info.w == 0) {                        // a zero norm: the exact path knows the reference's rule
+                cand |= 1u << r;
+                exact_needed = true;
+                continue;
+            }
+            const uint32_t* rd = repd + (size_t)r * p.nb;
+            const float nr = nr_s[r];
+            float msum = 0.f;
+            for (uint32_t j0 = info.y; j0 < info.z; j0 += 128) {
+                uint2 pr4[4];
+                uint32_t v4[4];
+#pragma unroll
+                for (uint32_t u = 0; u < 4; ++u) {
+                    const uint32_t j = j0 + 32 * u + lane;
+                    pr4[u] = j < info.z ? __ldg(p.enc_pair + j) : make_uint2(0u, 0u);
+                }
+#pragma unroll
+                for (uint32_t u = 0; u < 4; ++u) v4[u] = (pr4[u].y >> 31) ? __ldcg(rd + pr4[u].x) : 0u;
+#pragma unroll
+                for (uint32_t u = 0; u < 4; ++u)
+                    if (v4[u]) msum += fminf((float)v4[u] / nr, (float)(pr4[u].y & 0x7FFFFFFFu) / nc);
+            }
+#pragma unroll
+            for (int x = 1; x < 32; x <<= 1) msum += __shfl_xor_sync(0xffffffffu, msum, x);
+            const float sim = msum / (l_s[r].x + lc - msum);
+            if (sim < bound) continue;                                // certainly not
+            cand |= 1u << r;
+            if (sim > p.alpha + 1e-3f) break;                         // certainly: the row goes no further
+            exact_needed = true;
+        }
+    };
     // Rows of 33..64 runs, one warp, runs staged in shared memory (`wr`, ascending blocks).  Same arithmetic as evaluate_pair;
     // a lane holds two runs (lane, lane + 32).  The run that comes first among those of a reference thread t leads it (found
     // with a match inside each half and a per-warp bitmap of the threads across the halves) and sums the thread's terms in
@@ -2078,8 +2119,19 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                     //  2^20-row graph where the warps reject all but 3 M -- so the warps keep the bound; kept as a switch)
                     const bool unmasked = false;
                     if (!unmasked && ((longs[k >> 5] >> (k & 31)) & 1u)) mk = warp_shared_mask(kinfo, mk, nullptr);
-                    if (kn > 64) {                             // left for the scratch pass below
-                        if (lane == 0) { s_qmask[rk] = mk; s_qun[rk] = unmasked; }
+                    if (kn > 64) {
+                        // the sparse similarity settles most long rows here, a warp each; the CTA-wide scratch pass below is for
+                        // the pairs inside alpha +- 1e-3
+                        // (one pass over the row per candidate: with many candidates on a very long row -- the hub rows against
+                        //  each other at the end of the order, 2 ms per row -- the scratch pass, all candidates at once, is the cheaper one)
+                        uint32_t cand = mk;
+                        bool exact_needed = unmasked || __popc(mk) * ((kn + 127u) >> 7) > 24u;
+                        if (mk && !exact_needed) fast_decide_long(kinfo, mk, cand, exact_needed);
+                        if (cand && !exact_needed) {           // its highest bit is a certain acceptance, everything below a rejection
+                            if (lane == 0) atomicMin(&s_first[par_b], (k << 5) | (31u - __clz(cand)));
+                            cand = 0;
+                        }
+                        if (lane == 0) { s_qmask[rk] = cand; s_qun[rk] = unmasked; }
                         continue;
                     }
                     if (lane == 0) s_qmask[rk] = 0;

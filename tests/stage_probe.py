@@ -3,7 +3,8 @@ against the reference's GPU permutation on nips, and against the cluster-per-CTA
 
     python tests/stage_probe.py small            every small case x alpha x block size x reduction mode against the oracle
     python tests/stage_probe.py nips             nips against the golden, mask98 against the cluster-per-CTA kernel
-    python tests/stage_probe.py graph <scale> [both]   R-MAT 2^scale rows: stage kernel (and, with `both`, the other kernel + comparison)
+    python tests/stage_probe.py graph <scale> [both|one] [alpha] [edges] [out.npy]   R-MAT 2^scale rows: stage kernel (and, with `both`, the
+                                                 cluster-per-CTA kernel + comparison); optionally saves the permutation
 
 One JSON line per measurement.  Run under `timeout`.
 """
@@ -78,13 +79,16 @@ def main():
         scale = int(sys.argv[2])
         both = len(sys.argv) > 3 and sys.argv[3] == "both"
         alpha = float(sys.argv[4]) if len(sys.argv) > 4 else 0.3
-        edges = int(30.0e6 / (1 << 20) * (1 << scale))
+        edges = int(sys.argv[5]) if len(sys.argv) > 5 else int(30.0e6 / (1 << 20) * (1 << scale))
         n, ro, ci, rows = rmat_device(torch, scale, edges, seed=scale)
         del rows
         plan = pkg.Plan(ctx, n, n, ro, ci, on_device=True)
         b = timed_reorder(pkg, plan, alpha, 0, pkg.ROW_STAGE_ON)
         pb = plan.vector("reordered_rows")
-        out = {"scale": scale, "alpha": alpha, "nnz": edges, "nonempty_rows": int(len(pb)), "stage": b}
+        out = {"scale": scale, "alpha": alpha, "nnz": edges, "nonempty_rows": int(len(pb)), "stage": b,
+               "perm_is_permutation_of_nonempty_rows": bool(len(np.unique(pb)) == len(pb))}
+        if len(sys.argv) > 6:                       # keep the order for later runs (bench.py loads it through bsmr_plan_set_row_order)
+            np.save(sys.argv[6], pb)
         if both:
             a = timed_reorder(pkg, plan, alpha, 0, pkg.ROW_STAGE_OFF)
             pa = plan.vector("reordered_rows")
