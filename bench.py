@@ -559,6 +559,10 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--k", type=int, default=K_DEFAULT)
     ap.add_argument("--quick", action="store_true", help="headline line only: skip the other configs, the batch and the comparators")
+    ap.add_argument("--cluster-8m", action="store_true",
+                    help="configs[4] with the real BSMR row order instead of the identity: the clustering of 4.6e6 non-empty rows takes "
+                         "minutes, so it is not part of the default run (profiles/ holds the run)")
+    ap.add_argument("--only-8m", action="store_true", help="with --cluster-8m: skip every other configuration")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -746,11 +750,11 @@ def main():
     if not args.quick:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from graph8m_probe import rmat_device
-        for k in (32, 256):
+        for k in (() if args.only_8m else (32, 256)):
             configs.append(measure_config(torch, pkg, ctx, stream, flush, "nips K=%d (configs[%d])" % (k, 0 if k == 32 else 1), M, N, ro, ci, k,
                                           pkg.ROW_REFERENCE_COMPAT, False, peak))
             log(configs[-1]["name"])
-        for s in (70, 90, 98):
+        for s in (() if args.only_8m else (70, 90, 98)):
             Mm, Nm, rom, cim = pkg.synth.dlmc_mask(s / 100.0)
             configs.append(measure_config(torch, pkg, ctx, stream, flush, "mask %d %% K=64 (configs[2])" % s, Mm, Nm, rom, cim, 64,
                                           pkg.ROW_REFERENCE_COMPAT, False, peak))
@@ -761,28 +765,33 @@ def main():
         # not a BASELINE.json configuration: the structure BSMR is built for (rows that share column supports in groups of
         # ~80: dense 16 x 16 blocks after clustering, but no 256-row group dense enough for the wide kernel) -- the one
         # workload here whose tensor-core work goes through the dense-block kernel
-        Mb, Nb, rob, cib = pkg.synth.block_structured(16000, 16000, seed=5, groups=200, cols_per_group=96, noise=0.001)
-        configs.append(measure_config(torch, pkg, ctx, stream, flush, "block-structured 16000^2, 200 column supports of 96, K=128 (extra: the dense-block kernel's case)",
-                                      Mb, Nb, rob, cib, 128, pkg.ROW_REFERENCE_COMPAT, False, peak))
-        log(configs[-1]["name"])
-        n, rog, cig, rws = rmat_device(torch, GRAPH1M["scale"], GRAPH1M["edges"], seed=GRAPH1M["scale"])
-        del rws
-        configs.append(measure_config(torch, pkg, ctx, stream, flush, "graph 2^20 rows, 3e7 nnz, K=128 (configs[3]), BSMR row order", n, n, rog, cig,
-                                      GRAPH1M["K"], pkg.ROW_REFERENCE_COMPAT, True, peak, steps=6, fp16=True))
-        log(configs[-1]["name"])
-        del rog, cig
-        torch.cuda.empty_cache()
+        if not args.only_8m:
+            Mb, Nb, rob, cib = pkg.synth.block_structured(16000, 16000, seed=5, groups=200, cols_per_group=96, noise=0.001)
+            configs.append(measure_config(torch, pkg, ctx, stream, flush, "block-structured 16000^2, 200 column supports of 96, K=128 (extra: the dense-block kernel's case)",
+                                          Mb, Nb, rob, cib, 128, pkg.ROW_REFERENCE_COMPAT, False, peak))
+            log(configs[-1]["name"])
+            n, rog, cig, rws = rmat_device(torch, GRAPH1M["scale"], GRAPH1M["edges"], seed=GRAPH1M["scale"])
+            del rws
+            configs.append(measure_config(torch, pkg, ctx, stream, flush, "graph 2^20 rows, 3e7 nnz, K=128 (configs[3]), BSMR row order", n, n, rog, cig,
+                                          GRAPH1M["K"], pkg.ROW_REFERENCE_COMPAT, True, peak, steps=6, fp16=True))
+            log(configs[-1]["name"])
+            del rog, cig
+            torch.cuda.empty_cache()
         n, rog, cig, rws = rmat_device(torch, GRAPH8M["scale"], GRAPH8M["edges"], seed=GRAPH8M["scale"])
         del rws
         configs.append(measure_config(torch, pkg, ctx, stream, flush, "graph 2^23 rows, 2.5e8 nnz, K=256 (configs[4]) on 1 GPU, identity row order", n, n,
                                       rog, cig, GRAPH8M["K"], pkg.ROW_IDENTITY, True, peak, steps=4, fp16=True, e2e_host=2))
+        if args.cluster_8m:
+            log(configs[-1]["name"])
+            configs.append(measure_config(torch, pkg, ctx, stream, flush, "graph 2^23 rows, 2.5e8 nnz, K=256 (configs[4]) on 1 GPU, BSMR row order", n, n,
+                                          rog, cig, GRAPH8M["K"], pkg.ROW_REFERENCE_COMPAT, True, peak, steps=4, fp16=True))
         log(configs[-1]["name"])
         del rog, cig
         torch.cuda.empty_cache()
         pts = [("nips", 32, "cusparse"), ("nips", 32, "bsmr_ref"), ("nips", 128, "cusparse"), ("nips", 128, "bsmr_ref"),
                ("nips", 256, "cusparse"), ("mask70", 64, "cusparse"), ("mask90", 64, "cusparse"), ("mask90", 64, "bsmr_ref"),
                ("mask98", 64, "cusparse")]
-        comparators = run_comparators(pts)
+        comparators = None if args.only_8m else run_comparators(pts)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
