@@ -2105,6 +2105,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
             const uint32_t evaluated = min(total_ev, kWarps * kCpwB);
             const uint32_t take_eff = total_ev > evaluated ? nth_ev(evaluated) : take;
             tr_events += evaluated;
+            // (measured dead end: fetching position -> pos_info of a warp's four event rows together and the next row's runs while the
+            //  current one is decided -- 16 dependent round trips down to 7 -- was 5 % SLOWER: the extra live state spills at 64 registers)
             const long long te0 = clock64();
 #pragma unroll 1
             for (uint32_t q = 0; q < kCpwB; ++q) {
@@ -2403,11 +2405,12 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
         BSMR_TRY(cluster_ids.alloc(M ? M : 1));
         BSMR_TRY(status.alloc(4));
         uint32_t clusters_true = 0;
-        // Which kernel: graph-shaped inputs (many short rows, no per-warp scratch) run the stage kernel -- 32 consecutive
+        // Which kernel: graph-shaped inputs (>= 2^15 non-empty rows of at most 128 nnz on average) run the stage kernel -- 32 consecutive
         // clusters per CTA -- everything else the cluster-per-CTA kernel.  BSMR_ROW_STAGE_ON / _OFF force either (same permutation).
         const size_t stage_smem = (static_cast<size_t>((nb + 3u) & ~3u) + kStageReps * 1024 + kStageReps * 32 + 1024) * 4 + static_cast<size_t>((nb + 3u) & ~3u) * 2;
         const bool stage_fits = stage_smem <= 220 * 1024 && alpha >= 0.0f && block_size <= 65535u && nb <= kStageTerms * bd;
-        const bool graph_sized = !use_scratch && (M - zero_rows) >= (1u << 15);
+        // (not "the per-warp scratch does not fit": at 2^23 rows the block size is 3314 and it does -- the choice is about the rows)
+        const bool graph_sized = (M - zero_rows) >= (1u << 15) && static_cast<uint64_t>(nnz) <= 128ull * (M - zero_rows);
         const bool use_stage = stage_fits && ((flags & BSMR_ROW_STAGE_ON) ? true : (flags & BSMR_ROW_STAGE_OFF) ? false
                                               : (graph_sized && !(flags & (BSMR_ROW_THREAD_PRUNE_ON | BSMR_ROW_THREAD_PRUNE_OFF))));
         void* const kernel_fn = use_stage ? reinterpret_cast<void*>(bsa_stage_kernel) : reinterpret_cast<void*>(bsa_cluster_kernel);

@@ -97,7 +97,7 @@ int bsmr_plan_destroy(bsmr_plan* plan);
 #define BSMR_ROW_THREAD_PRUNE_OFF 8u
 /* or-ed in: the stage kernel (one CTA per run of 32 consecutive clusters: a row is tested against 32 representatives at
  * once and forwarded once) or the cluster-per-CTA kernel.  Default: the stage kernel on graph-shaped inputs (>= 2^15
- * non-empty rows, no per-warp scratch).  Same permutation either way.                                              */
+ * non-empty rows of at most 128 nnz on average).  Same permutation either way.                                    */
 #define BSMR_ROW_STAGE_ON         16u
 #define BSMR_ROW_STAGE_OFF        32u
 
