@@ -1677,6 +1677,11 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
         for (;;) {
             if (cursor >= avail) {
                 if (in_done) break;
+                if (produced != published) {                 // nothing to do until more rows arrive: do not sit on the ones already decided
+                    __syncthreads();                           // (at the end of the order the rows trickle through 148 stages one at a time)
+                    if (tid == 0) st_release_u64(out_ctrl, make_ctrl(s + 1, produced, 0));
+                    published = produced;
+                }
                 ++tr_polls;
                 {
                     const long long t0 = clock64();
