@@ -900,7 +900,10 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
     const uint32_t nw = p.bd >> 5;
     const float bound = p.alpha - 1e-3f;
     constexpr uint32_t kWarps = kClusterThreads / 32;
-    constexpr uint32_t kWalkMax = 64;
+#ifndef BSMR_STAGE_WALK_MAX
+#define BSMR_STAGE_WALK_MAX 64
+#endif
+    constexpr uint32_t kWalkMax = BSMR_STAGE_WALK_MAX;      // runs a thread walks itself (measured: 128 -> 3.5 s instead of 3.0 s at 2^20 rows, 25.4 instead of 23.8 s at 2^22)
     constexpr uint32_t kNone = 0xFFFFFFFFu;
     const bool cj_on = p.alpha < 1.0f;         // similarity 1 must be an acceptance
     uint32_t* const repd = p.repd + (size_t)blockIdx.x * kStageReps * p.nb;     // dense representatives of this CTA
