@@ -25,6 +25,10 @@
 // include/cudaUtil.cuh:27-45).  Every float operation below is performed in that same order on
 // the same operands, so the decisions -- and therefore the permutation -- are identical.
 // BSMR_ROW_EXACT_REDUCE switches the lossy tree for a complete one.
+//
+// Two clustering kernels produce that permutation: bsa_cluster_kernel (one CTA per live cluster; inputs with long rows, where a
+// per-warp dense scratch pays) and bsa_stage_kernel (one CTA per run of 32 consecutive clusters; graph-shaped inputs: 13x at
+// 2^20 rows, and the only one that finishes 2^23 rows in minutes).  row_reorder() picks by the shape of the input.
 #include <cooperative_groups.h>
 #include <cub/cub.cuh>
 #include <thrust/iterator/transform_iterator.h>
@@ -648,9 +652,6 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_cluster_kernel(Cluster
                 // at the pace of that bookkeeping.  Here a THREAD applies the bounds to its candidate (the size bound in O(1),
                 // the shared-nnz bound by walking the row's <= 64 runs); warps evaluate only the survivors, in order, up to the
                 // first that joins.  The rejections are the same integers and comparisons, so the permutation is unchanged.
-                // (variants measured on the 2^20-row graph, profiles/r02m_*, r02n_*: 8 survivors per warp with a warp-wide prune for the
-                // long rows 67.9 s, walks of up to 256 runs 45.9 s, this one 38.8 s: a warp's survivors are serial round trips, a
-                // long walk idles 31 lanes, and either way a longer step starves the children)
                 // (variants measured on the 2^20-row graph, profiles/r02m_*, r02n_*: 8 survivors per warp with a warp-wide prune for
                 // the long rows 67.9 s, walks of up to 256 runs 45.9 s, this one 38.8 s: a warp's survivors are serial round trips, a
                 // long walk idles 31 lanes, and either way a longer step starves the children)

@@ -377,7 +377,7 @@ def test_dlmc_masks_full_size(pkg, ctx, oracle, sparsity):
         assert oracle.check_data(cpu, dP.cpu().numpy()) == 0, (sparsity, flags)
 
 
-@pytest.mark.parametrize("alpha", [0.1, 0.3, 0.5, 0.7, 0.9])
+@pytest.mark.parametrize("alpha", [0.0, 0.1, 0.3, 0.5, 0.7, 0.9, 1.0])
 def test_row_reorder_both_clustering_steps_vs_oracle(pkg, ctx, oracle, alpha):
     """Three forms of the clustering: the cluster-per-CTA kernel with a warp per candidate (per-warp scratch; the default where
     rows are long), the same kernel with a thread per candidate for the cheap rejections, and the stage kernel (32 consecutive
