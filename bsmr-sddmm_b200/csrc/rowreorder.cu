@@ -890,8 +890,11 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
     __shared__ float s_fv[32 * 32];            // found_sparse: per warp, the normalised counts of a chunk of runs
     __shared__ uint32_t s_pair[32];            // batch founding: bit i of word j = row j of the batch might join a cluster founded by row i
     __shared__ uint32_t s_anyq;                // a long row of the step is queued for the scratch pass
-    __shared__ uint8_t s_qun[128];             // ... and whether the shared-nnz bound is still to be applied (very long rows)
-    __shared__ uint32_t s_qmask[128];           // per event row of the step: representatives left for the scratch pass (rows of > 32 runs)
+#ifndef BSMR_STAGE_CPW
+#define BSMR_STAGE_CPW 4
+#endif
+    __shared__ uint8_t s_qun[32 * BSMR_STAGE_CPW];             // ... and whether the shared-nnz bound is still to be applied (very long rows)
+    __shared__ uint32_t s_qmask[32 * BSMR_STAGE_CPW];           // per event row of the step: representatives left for the scratch pass (rows of > 32 runs)
     __shared__ uint32_t s_touched;             // reference warps that own a block of the row in the scratch
     __shared__ float2 s_res[kStageReps * 32];  // scratch pass: per (representative, reference warp) the {min, max} sums
     __shared__ unsigned long long s_ctrl;
@@ -2008,7 +2011,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) bsa_stage_kernel(ClusterPa
                 continue;
             }
             // ---- streaming step: up to 1024 rows, one per thread, against all 32 representatives ----
-            constexpr uint32_t kCpwB = 4;                       // event rows a warp evaluates per step (measured: 11 % of the rows of a step are events)
+            // (measured: 8 per warp -> 3.4 s instead of 3.0 s at 2^20 rows, 23.6 against 23.8 s at 2^22)
+            constexpr uint32_t kCpwB = BSMR_STAGE_CPW;                       // event rows a warp evaluates per step (measured: 11 % of the rows of a step are events)
             // the first steps after the founding are short and publish at once: the next stage is waiting for its first rows
             const bool fresh = fresh_steps < 3;
             ++fresh_steps;
