@@ -2467,7 +2467,13 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
         // Which kernel: graph-shaped inputs (>= 2^15 non-empty rows of at most 128 nnz on average) run the stage kernel -- 32 consecutive
         // clusters per CTA -- everything else the cluster-per-CTA kernel.  BSMR_ROW_STAGE_ON / _OFF force either (same permutation).
         const size_t stage_smem = (static_cast<size_t>((nb + 3u) & ~3u) + kStageReps * 1024 + kStageReps * 32 + 1024) * 4 + static_cast<size_t>((nb + 3u) & ~3u) * 2;
-        const bool stage_fits = stage_smem <= 220 * 1024 && alpha >= 0.0f && block_size <= 65535u && nb <= kStageTerms * bd;
+        // (dynamic + the kernel's static shared memory against the opt-in limit: a kernel that does not fit must fall back, not fail)
+        cudaFuncAttributes stage_attr{};
+        BSMR_CUDA_OK(cudaFuncGetAttributes(&stage_attr, bsa_stage_kernel));
+        int smem_optin = 0;
+        BSMR_CUDA_OK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+        const bool stage_fits = stage_smem + stage_attr.sharedSizeBytes <= static_cast<size_t>(smem_optin) && alpha >= 0.0f && block_size <= 65535u &&
+                                nb <= kStageTerms * bd;
         // (not "the per-warp scratch does not fit": at 2^23 rows the block size is 3314 and it does -- the choice is about the rows)
         const bool graph_sized = (M - zero_rows) >= (1u << 15) && static_cast<uint64_t>(nnz) <= 128ull * (M - zero_rows);
         const bool use_stage = stage_fits && ((flags & BSMR_ROW_STAGE_ON) ? true : (flags & BSMR_ROW_STAGE_OFF) ? false
