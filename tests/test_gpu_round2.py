@@ -444,6 +444,22 @@ def test_stage_kernel_equals_cluster_per_cta_kernel_on_graphs(pkg, ctx, scale, a
     assert np.array_equal(out[0][0], out[1][0])
 
 
+def test_stage_kernel_request_falls_back_when_it_does_not_fit(pkg, ctx):
+    """18 750 column blocks do not fit the stage kernel's shared memory: BSMR_ROW_STAGE_ON must fall back to the cluster-per-CTA
+    kernel (same permutation as BSMR_ROW_STAGE_OFF), not fail."""
+    rng = np.random.default_rng(9)
+    M, N = 1500, 300000
+    keys = np.unique(rng.integers(0, M, 30000).astype(np.int64) * N + rng.integers(0, N, 30000))
+    M, N, ro, ci = pkg.synth.csr_from_rows_cols(M, N, keys // N, keys % N)
+    out = []
+    for step in (pkg.ROW_STAGE_ON, pkg.ROW_STAGE_OFF):
+        plan = pkg.Plan(ctx, M, N, ro, ci)
+        plan.row_reorder(0.3, block_size=16, flags=step)
+        out.append((plan.vector("reordered_rows"), plan.info()["num_clusters_true"]))
+        plan.close()
+    assert out[0][1] == out[1][1] and np.array_equal(out[0][0], out[1][0])
+
+
 def sampled_check(torch, dA, dB, dP, ro_dev, ci_dev, nnz, n=1 << 17, seed=3):
     """size-independent parity: n sampled entries against fp64 dot products of the same rows"""
     g = torch.Generator(device="cuda")
