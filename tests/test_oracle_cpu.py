@@ -186,3 +186,70 @@ def test_nips_permutation_golden(pkg, oracle, golden_dir):
     assert int(g["input_checksum"]) == int(ci.astype(np.uint64).sum()) * 1000003 + int(ro.astype(np.uint64).sum())
     perm, compat, _ = oracle.row_reordering_indexed(M, N, ro, ci, float(g["alpha"]), int(g["block_size"]))
     assert np.array_equal(perm, g["perm_ref_gpu"]) and compat == int(g["num_clusters"])
+
+
+def _kept_warps(blockdim, exact):
+    """Which reference warps survive the shared-memory tree (include/cudaUtil.cuh:27-45): lossy for odd warp counts."""
+    nw = blockdim // 32
+    first = nw // 2
+    if exact:
+        p2 = 1
+        while p2 < nw:
+            p2 <<= 1
+        first = p2 // 2
+    contrib = [{w} if w < nw else set() for w in range(64)]
+    s = first
+    while s >= 1:
+        for w in range(s):
+            contrib[w] |= contrib[w + s]
+        s >>= 1
+    return contrib[0]
+
+
+def _sparse_similarity(rep, cmp_, blockdim, exact):
+    """The identity the stage clustering kernel decides with: max(a, c) = a + c - min(a, c) per block, so
+    sim = min-sum / (L1(rep) + L1(row) - min-sum) over the blocks the reference's reduction keeps; min-sum only has terms where
+    both are non-zero."""
+    nb = len(rep)
+    kept = np.isin((np.arange(nb) % blockdim) // 32, sorted(_kept_warps(blockdim, exact)))
+    r = np.where(kept, rep, 0).astype(np.float64)
+    c = np.where(kept, cmp_, 0).astype(np.float64)
+    if not r.any() or not c.any():
+        return None
+    a, b = r / np.sqrt((r * r).sum()), c / np.sqrt((c * c).sum())
+    m = np.minimum(a, b).sum()
+    return m / (a.sum() + b.sum() - m)
+
+
+@pytest.mark.parametrize("exact", [False, True])
+def test_sparse_similarity_identity_against_the_oracle(oracle, exact):
+    """The stage kernel takes a (row, representative) pair as decided when the sparse similarity is outside alpha +- 1e-3 and
+    evaluates in the reference's operation order only inside: the two must agree far better than that.  Random sparse encodings,
+    power-of-two and odd (lossy: 7, 21 warps) reference CTA sizes."""
+    rng = np.random.default_rng(11)
+    worst = 0.0
+    for nb in (40, 777, 2048, 2532, 6132):
+        bd = oracle.clustering_blockdim(nb)
+        for _ in range(60):
+            n_r, n_c = int(rng.integers(1, 200)), int(rng.integers(1, 200))
+            rep = np.zeros(nb, dtype=np.uint32)
+            cmp_ = np.zeros(nb, dtype=np.uint32)
+            hubs = rng.integers(0, max(1, nb // 16), 8)                         # shared hub blocks, like an R-MAT graph
+            for enc, n in ((rep, n_r), (cmp_, n_c)):
+                idx = np.concatenate([rng.integers(0, nb, n), hubs[: rng.integers(0, 9)]])
+                np.add.at(enc, idx, rng.integers(1, 40, len(idx)).astype(np.uint32))
+            want = _sparse_similarity(rep, cmp_, bd, exact)
+            if want is None:
+                continue
+            got = oracle.similarity(rep, cmp_, bd, exact=exact)
+            worst = max(worst, abs(got - want))
+    assert worst < 2e-5, worst
+
+
+def test_single_block_clusters_normalise_to_exactly_one():
+    """Certain joins of the stage kernel: a representative that is one column block with count c normalises to c / sqrt(c*c) in
+    fp32, which is exactly 1 for every count below 2^16 (above, the reference's uint32 c*c wraps) -- so a single-run row joining
+    it changes nothing that any later decision reads."""
+    c = np.arange(1, 65536, dtype=np.uint64)
+    nr = np.sqrt((c * c).astype(np.float32))
+    assert np.all(c.astype(np.float32) / nr == np.float32(1.0))
