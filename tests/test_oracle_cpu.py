@@ -243,7 +243,7 @@ def test_sparse_similarity_identity_against_the_oracle(oracle, exact):
                 continue
             got = oracle.similarity(rep, cmp_, bd, exact=exact)
             worst = max(worst, abs(got - want))
-    assert worst < 2e-5, worst
+    assert worst < 1e-6, worst            # measured: 7.6e-8
 
 
 def test_single_block_clusters_normalise_to_exactly_one():
