@@ -444,6 +444,26 @@ def test_stage_kernel_equals_cluster_per_cta_kernel_on_graphs(pkg, ctx, scale, a
     assert np.array_equal(out[0][0], out[1][0])
 
 
+@pytest.mark.parametrize("scale", [15, 16])
+def test_graph_clustering_vs_cpu_oracle_golden(pkg, ctx, golden_dir, scale):
+    """R-MAT graphs of 2^15 / 2^16 rows (15 799 / ~31 000 clusters) against permutations the CPU oracle computed once
+    (`tests/golden/make_graph_golden.py`: minutes to half an hour on one core, hence a committed fixture): both clustering
+    kernels, permutation and both cluster counts."""
+    path = os.path.join(golden_dir, "graph%d_perm_oracle.npz" % scale)
+    if not os.path.exists(path):
+        pytest.skip("no golden for graph%d" % scale)
+    g = np.load(path)
+    _, M, N, ro, ci = named_case(pkg, "graph%d" % scale)
+    assert (M, N, len(ci)) == (int(g["M"]), int(g["N"]), int(g["nnz"]))
+    for step in (pkg.ROW_STAGE_ON, pkg.ROW_STAGE_OFF):
+        plan = pkg.Plan(ctx, M, N, ro, ci)
+        plan.row_reorder(float(g["alpha"]), block_size=int(g["block_size"]), flags=step)
+        info = plan.info()
+        assert np.array_equal(plan.vector("reordered_rows"), g["perm"]), step
+        assert info["num_clusters"] == int(g["num_clusters"]) and info["num_clusters_true"] == int(g["num_clusters_true"]), step
+        plan.close()
+
+
 def test_stage_kernel_request_falls_back_when_it_does_not_fit(pkg, ctx):
     """18 750 column blocks do not fit the stage kernel's shared memory: BSMR_ROW_STAGE_ON must fall back to the cluster-per-CTA
     kernel (same permutation as BSMR_ROW_STAGE_OFF), not fail."""
