@@ -2567,8 +2567,12 @@ int row_reorder(bsmr_plan* plan, float alpha, uint32_t block_size, uint32_t flag
                             fprintf(stderr, "[bsmr stage] %6u: %llu %llu %llu %llu %llu %llu %.1f %.1f\n", c, sd[8 * c], sd[8 * c + 1], sd[8 * c + 2], sd[8 * c + 3],
                                     sd[8 * c + 4], sd[8 * c + 5], sd[8 * c + 6] / 1e6, sd[8 * c + 7] / 1e6);
                     }
+#ifdef BSMR_DEBUG
                     const char* tv = std::getenv("BSMR_TRACE");
                     const bool all = tv && tv[0] == 'a';
+#else
+                    const bool all = false;                    // (the release library reads no environment variable)
+#endif
                     for (uint32_t c = 1; c <= nc; c = (all || c < 8) ? c + 1 : c + (nc / 12 ? nc / 12 : 1))
                         fprintf(stderr, "[bsmr trace]   %6u: %10.1f %10.1f %10.1f\n", c, us(ts[3 * c]), us(ts[3 * c + 1]), us(ts[3 * c + 2]));
                     fprintf(stderr, "[bsmr trace]   %6u: %10.1f %10.1f %10.1f\n", nc, us(ts[3 * nc]), us(ts[3 * nc + 1]), us(ts[3 * nc + 2]));
