@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from cases import small_cases
+from cases import named_case, small_cases
 
 COL_VECS = ["dense_cols", "dense_col_offsets", "sparse_cols", "sparse_col_offsets", "sparse_value_offsets"]
 
@@ -86,7 +86,7 @@ def test_mtx_loader_rejections(oracle, ref, tmp_path):
 
 def test_golden_fixtures(pkg, oracle, golden_dir):
     """Fixtures produced by the reference library (tests/golden/make_golden.py); they travel to the GPU box."""
-    files = sorted(f for f in os.listdir(golden_dir) if f.endswith(".npz") and f != "nips_perm_ref_gpu.npz")
+    files = sorted(f for f in os.listdir(golden_dir) if f.endswith(".npz") and not f.endswith(("_perm_ref_gpu.npz", "_perm_oracle.npz")))
     assert files, "no golden fixtures committed"
     for f in files:
         g = np.load(os.path.join(golden_dir, f))
@@ -253,3 +253,18 @@ def test_single_block_clusters_normalise_to_exactly_one():
     c = np.arange(1, 65536, dtype=np.uint64)
     nr = np.sqrt((c * c).astype(np.float32))
     assert np.all(c.astype(np.float32) / nr == np.float32(1.0))
+
+
+def test_graph_goldens_are_permutations_with_consistent_counts(pkg, golden_dir):
+    """The oracle-made graph fixtures (tests/golden/make_graph_golden.py): each holds a permutation of the graph's non-empty rows
+    and cluster counts that fit it; the GPU tests compare the clustering kernels with them."""
+    files = sorted(f for f in os.listdir(golden_dir) if f.endswith("_perm_oracle.npz"))
+    assert files
+    for f in files:
+        g = np.load(os.path.join(golden_dir, f))
+        scale = int(f[len("graph"):f.index("_")])
+        _, M, N, ro, ci = named_case(pkg, "graph%d" % scale)
+        assert (M, N, len(ci)) == (int(g["M"]), int(g["N"]), int(g["nnz"])), f
+        nonempty = np.nonzero(np.diff(ro.astype(np.int64)))[0]
+        assert np.array_equal(np.sort(g["perm"]), nonempty.astype(np.uint32)), f
+        assert 1 < int(g["num_clusters_true"]) <= len(nonempty), f
