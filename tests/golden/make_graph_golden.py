@@ -1,5 +1,5 @@
 """Golden permutations of R-MAT graphs from the CPU oracle (sparse restatement, `oracle_row_reordering_indexed`), for sizes the
-oracle needs minutes for (2^15 rows: ~7 min, 2^16 rows: ~30 min on one core) -- too slow for the test suite, so computed once here
+oracle needs minutes to hours for (2^15 rows: 8 min, 2^16 rows: 34 min, 2^17 rows: 125 min on one core) -- too slow for the test suite, so computed once here
 and committed; the GPU tests compare both clustering kernels with them.
 
     python tests/golden/make_graph_golden.py 15        ->  tests/golden/graph15_perm_oracle.npz
